@@ -1,0 +1,112 @@
+"""ctypes binding of the C-ABI library ``libtactilesr_b200.so`` (declared in include/tactilesr_b200.h).
+
+There is no CPU fallback and no torch/cuDNN fallback: if the library is missing or a call fails the
+error is raised.  Pointers are passed as integers (``tensor.data_ptr()``), streams as the raw
+``cudaStream_t`` of ``torch.cuda.current_stream()``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtactilesr_b200.so")
+
+_P, _I, _L, _F, _Z = c_void_p, c_int, c_longlong, c_float, c_size_t
+
+# name -> (restype, argtypes).  Every entry here must be declared in include/tactilesr_b200.h
+# (tests/test_abi.py checks both directions).
+SIGNATURES = {
+    "tsr_last_error": (c_char_p, []),
+    "tsr_version": (_I, []),
+    "tsr_check_device": (_I, []),
+    "tsr_launch_count": (_L, []),
+    "tsr_launch_count_reset": (None, []),
+    # fp32 convolutions
+    "tsr_pack_conv_weight_f32": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "tsr_conv2d_f32": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "tsr_conv2d_wgrad_f32_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),
+    "tsr_conv2d_wgrad_f32": (_I, [_P, _I, _P, _I, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "tsr_colsum_workspace": (_Z, [_L, _I]),
+    "tsr_colsum_f32": (_I, [_P, _I, _L, _I, _P, _P, _Z, _I, _P]),
+    "tsr_head_fwd": (_I, [_P, _L, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "tsr_head_wgrad_workspace": (_Z, [_I]),
+    "tsr_head_wgrad": (_I, [_P, _L, _P, _I, _I, _P, _P, _Z, _I, _I, _I, _P]),
+    "tsr_tail_fwd": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "tsr_tail_dgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "tsr_tail_wgrad_workspace": (_Z, [_I, _I, _I, _I]),
+    "tsr_tail_wgrad": (_I, [_P, _I, _I, _P, _P, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _P]),
+    # elementwise / reductions
+    "tsr_bn_workspace": (_Z, [_L, _I]),
+    "tsr_bn_train_stats": (_I, [_P, _I, _I, _L, _I, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _Z, _P]),
+    "tsr_bn_eval_coeffs": (_I, [_I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P]),
+    "tsr_bn_apply": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _L, _I, _I, _P]),
+    "tsr_bn_backward_workspace": (_Z, [_L, _I]),
+    "tsr_bn_backward": (_I, [_P, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _P, _Z, _P]),
+    "tsr_relu_backward": (_I, [_P, _I, _P, _I, _P, _I, _I, _L, _I, _P]),
+    "tsr_copy_channels": (_I, [_P, _I, _I, _P, _I, _I, _L, _I, _P]),
+    "tsr_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "tsr_nhwc_to_nchw": (_I, [_P, _I, _I, _P, _I, _I, _I, _P]),
+    "tsr_mse_hr_workspace": (_Z, []),
+    "tsr_mse_hr_loss": (_I, [_P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _F, _P, _Z, _P]),
+    "tsr_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _L, _F, _P]),
+    # tPSFNet
+    "tsr_sgemm_strided": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _I, _I, _I, _P, _I, _I, _P]),
+    "tsr_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "tsr_linear_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "tsr_psf_forward": (_I, [_P, _P, _P, _P, _P, _I, _P]),
+    "tsr_psf_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    # tensor-core (tcgen05) convolutions
+    "tsr_pack_conv_weight_bf16": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "tsr_conv2d_tc": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
+    "tsr_conv2d_tc_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),
+    "tsr_conv2d_wgrad_tc": (_I, [_P, _I, _P, _I, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "tsr_conv2d_wgrad_tc_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),
+    "tsr_tc_selftest": (_I, [_I, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class TsrError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load the library (once).  Raises if it has not been built -- there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TsrError(
+                f"{LIB_PATH} not found: build it with `python -m tactilesr_b200.csrc.build` "
+                "(or __graft_entry__.build()); tactilesr_b200 has no CPU / PyTorch fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)   # AttributeError if the symbol is missing: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().tsr_last_error().decode("utf-8", "replace")
+        raise TsrError(f"{what or 'tactilesr_b200'} failed (code {rc}): {msg}")
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point and raise on a non-zero code."""
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        check(rc, name)
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().tsr_launch_count())

@@ -1,0 +1,735 @@
+// fp32-accurate convolution kernels (NHWC activations, implicit GEMM on the FFMA pipe).
+//
+// This is the "fp32 mode" of the hot path (north_star tolerance <= 1e-5 relative): every
+// product and sum is fp32, the reduction order is fixed (deterministic), weight gradients
+// use a two-level split-K reduction.  The tensor-core (tcgen05) path lives in conv_tc.cu.
+//
+// Replaces the ATen/cuDNN calls behind nn.Conv2d at reference
+// model/tactileSR_model.py:37,41,47,53,55,61,168,174,180,186,191,219,220 and their autograd
+// backward (cpu/trainer.py:353).
+#include "common.cuh"
+
+namespace {
+
+constexpr int FLAG_RELU = 1;
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: OIHW fp32 -> [tap][ci][co] (forward) and [tap'][co][ci] with flipped taps (dgrad)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_weight_f32_kernel(const float* __restrict__ w, float* __restrict__ wf,
+                                       float* __restrict__ wd, int Cout, int Cin, int KS) {
+  int taps = KS * KS;
+  long long n = (long long)Cout * Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int t = (int)(i % taps);
+    long long r = i / taps;
+    int ci = (int)(r % Cin);
+    int co = (int)(r / Cin);
+    float v = w[i];
+    if (wf) wf[((long long)t * Cin + ci) * Cout + co] = v;
+    if (wd) wd[((long long)(taps - 1 - t) * Cout + co) * Cin + ci] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward / data-gradient: out[p][co] = sum_{tap,ci} in[p+shift(tap)][ci] * wp[tap][ci][co]
+// tile 128 pixels x 64 couts x 16 channels, 256 threads, 8x4 outputs per thread
+// ---------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 64, BK = 16, APAD = 4;
+
+__global__ void __launch_bounds__(256)
+conv2d_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restrict__ wp,
+                  const float* __restrict__ bias, const float* residual, int res_ld,
+                  float* out, int out_ld, int Mtotal, int H, int W, int Cin, int Cout, int KS,
+                  int flags) {
+  __shared__ __align__(16) float As[2][BK][BM + APAD];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+
+  const int tid = threadIdx.x;
+  const int tn = tid & 15, tm = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int pad = KS >> 1;
+  const int HW = H * W;
+
+  // the two A-load slots of this thread: pixel (tid>>2) and 64 + (tid>>2), channel quad tid&3
+  int ay[2], ax[2];
+  long long abase[2];
+  bool avalid[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    int m = (tid >> 2) + s * 64;
+    int p = m0 + m;
+    avalid[s] = p < Mtotal;
+    int pp = avalid[s] ? p : 0;
+    int b = pp / HW, rem = pp - b * HW;
+    ay[s] = rem / W;
+    ax[s] = rem - ay[s] * W;
+    abase[s] = (long long)b * HW;
+  }
+  const int ac4 = (tid & 3) * 4;
+  const int bk = tid >> 4, bn4 = (tid & 15) * 4;
+  const int cchunks = Cin / BK;
+  const int nk = KS * KS * cchunks;
+
+  float4 ra[2], rb;
+  auto load_global = [&](int kc) {
+    int tap = kc / cchunks;
+    int c0 = (kc - tap * cchunks) * BK;
+    int dy = tap / KS - pad, dx = tap % KS - pad;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      int yy = ay[s] + dy, xx = ax[s] + dx;
+      bool ok = avalid[s] && yy >= 0 && yy < H && xx >= 0 && xx < W;
+      ra[s] = ok ? *reinterpret_cast<const float4*>(in + (abase[s] + (long long)yy * W + xx) * in_ld + c0 + ac4)
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    rb = *reinterpret_cast<const float4*>(wp + ((long long)tap * Cin + c0 + bk) * Cout + n0 + bn4);
+  };
+  auto store_smem = [&](int buf) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      int m = (tid >> 2) + s * 64;
+      As[buf][ac4 + 0][m] = ra[s].x;
+      As[buf][ac4 + 1][m] = ra[s].y;
+      As[buf][ac4 + 2][m] = ra[s].z;
+      As[buf][ac4 + 3][m] = ra[s].w;
+    }
+    *reinterpret_cast<float4*>(&Bs[buf][bk][bn4]) = rb;
+  };
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  load_global(0);
+  store_smem(0);
+  __syncthreads();
+  for (int kc = 0; kc < nk; ++kc) {
+    int buf = kc & 1;
+    if (kc + 1 < nk) load_global(kc + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8 + 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tn * 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    if (kc + 1 < nk) store_smem(buf ^ 1);
+    __syncthreads();
+  }
+
+  const int n = n0 + tn * 4;
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) bv = *reinterpret_cast<const float4*>(bias + n);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int p = m0 + tm * 8 + i;
+    if (p >= Mtotal) continue;
+    float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
+    if (residual) {
+      float4 r = *reinterpret_cast<const float4*>(residual + (long long)p * res_ld + n);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (flags & FLAG_RELU) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    *reinterpret_cast<float4*>(out + (long long)p * out_ld + n) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient, level 1: partial[s][tap][ci][co] = sum_{p in split s} in[p+shift][ci]*dout[p][co]
+// tile 64 ci x 64 co, 16 pixels per K step, 256 threads, 4x4 outputs per thread
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv2d_wgrad_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restrict__ dout,
+                        int dout_ld, float* __restrict__ partial, int Mtotal, int H, int W, int Cin,
+                        int Cout, int KS, int pix_per_split) {
+  __shared__ __align__(16) float As[2][16][64];
+  __shared__ __align__(16) float Bs[2][16][64];
+  const int tid = threadIdx.x;
+  const int ctiles = Cin / 64, otiles = Cout / 64;
+  int t = blockIdx.x;
+  const int ot = t % otiles; t /= otiles;
+  const int ct = t % ctiles; t /= ctiles;
+  const int tap = t;
+  const int pad = KS >> 1;
+  const int dy = tap / KS - pad, dx = tap % KS - pad;
+  const int HW = H * W;
+  const int ci0 = ct * 64, co0 = ot * 64;
+  const int pbeg = blockIdx.y * pix_per_split;
+  const int pend = min(pbeg + pix_per_split, Mtotal);
+  const int lk = tid >> 4, l4 = (tid & 15) * 4;
+  const int ti = tid >> 4, tj = tid & 15;   // ci = ti*4.., co = tj*4..
+
+  float4 ra, rb;
+  auto load_global = [&](int p0) {
+    int p = p0 + lk;
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = ra;
+    if (p < pend) {
+      int b = p / HW, rem = p - b * HW;
+      int y = rem / W, x = rem - y * W;
+      int yy = y + dy, xx = x + dx;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        ra = *reinterpret_cast<const float4*>(in + ((long long)b * HW + (long long)yy * W + xx) * in_ld + ci0 + l4);
+      rb = *reinterpret_cast<const float4*>(dout + (long long)p * dout_ld + co0 + l4);
+    }
+  };
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  int nsteps = (pend - pbeg + 15) / 16;
+  if (nsteps > 0) {
+    load_global(pbeg);
+    *reinterpret_cast<float4*>(&As[0][lk][l4]) = ra;
+    *reinterpret_cast<float4*>(&Bs[0][lk][l4]) = rb;
+  }
+  __syncthreads();
+  for (int s = 0; s < nsteps; ++s) {
+    int buf = s & 1;
+    if (s + 1 < nsteps) load_global(pbeg + (s + 1) * 16);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ti * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tj * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (s + 1 < nsteps) {
+      *reinterpret_cast<float4*>(&As[buf ^ 1][lk][l4]) = ra;
+      *reinterpret_cast<float4*>(&Bs[buf ^ 1][lk][l4]) = rb;
+    }
+    __syncthreads();
+  }
+  float* dst = partial + ((long long)blockIdx.y * KS * KS + tap) * Cin * Cout;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(dst + (long long)(ci0 + ti * 4 + i) * Cout + co0 + tj * 4) =
+        make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+}
+
+// level 2: dw_oihw[co][ci][tap] (+)= sum_s partial[s][tap][ci][co]   (fixed order => deterministic)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int S,
+                                    int taps, int Cin, int Cout, int accumulate) {
+  long long n = (long long)taps * Cin * Cout;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int co = (int)(i % Cout);
+  long long r = i / Cout;
+  int ci = (int)(r % Cin);
+  int tap = (int)(r / Cin);
+  float s = 0.f;
+  for (int k = 0; k < S; ++k) s += partial[(long long)k * n + i];
+  long long o = ((long long)co * Cin + ci) * taps + tap;
+  dw[o] = accumulate ? dw[o] + s : s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-channel column sums (bias gradients): two-level, deterministic
+// ---------------------------------------------------------------------------------------------
+__global__ void colsum_partial_kernel(const float* __restrict__ x, int ld, int npix, int C,
+                                      float* __restrict__ partial, int rows_per_block) {
+  // blockDim = (C/4 threads in x... ) generic: thread handles channel quad q = tid % (C/4), row lane = tid / (C/4)
+  int q4 = C / 4;
+  int lanes = blockDim.x / q4;
+  int q = threadIdx.x % q4, lane = threadIdx.x / q4;
+  int r0 = blockIdx.x * rows_per_block;
+  int r1 = min(r0 + rows_per_block, npix);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane < lanes)
+    for (int r = r0 + lane; r < r1; r += lanes) {
+      float4 v = *reinterpret_cast<const float4*>(x + (long long)r * ld + q * 4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  extern __shared__ float4 sm[];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  if (lane == 0) {
+    for (int l = 1; l < lanes; ++l) {
+      float4 v = sm[l * q4 + q];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(partial + (long long)blockIdx.x * C + q * 4) = s;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int nblocks, int C,
+                                    float* __restrict__ out, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += (double)partial[(long long)b * C + c];
+  out[c] = accumulate ? out[c] + (float)s : (float)s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// head: bilinear x sf upsample of a (3,4,4) taxel frame fused with the 3x3 conv 3->64 (no bias)
+// reference: nn.Upsample + nn.Conv2d at tactileSR_model.py:35-37, 60-61 (+ReLU :62), :107,122
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void build_upsampled(const float* __restrict__ xs /*3x16*/, float* up, int sf) {
+  // up: (H+2) x (W+2) x 3 with a zero ring; H = W = 4*sf.  ATen: src = (d+0.5)/sf - 0.5 clamped at 0.
+  const int H = 4 * sf, P = H + 2;
+  const float scale = 1.0f / (float)sf;
+  for (int i = threadIdx.x; i < P * P; i += blockDim.x) {
+    int yy = i / P - 1, xx = i % P - 1;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < H) {
+      float sy = fmaxf(scale * (yy + 0.5f) - 0.5f, 0.f), sx = fmaxf(scale * (xx + 0.5f) - 0.5f, 0.f);
+      int y0 = (int)sy, x0 = (int)sx;
+      int y1 = min(y0 + 1, 3), x1 = min(x0 + 1, 3);
+      float ly = sy - y0, lx = sx - x0;
+      float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+#define TSR_UP(c) (w00 * xs[c * 16 + y0 * 4 + x0] + w01 * xs[c * 16 + y0 * 4 + x1] + \
+                   w10 * xs[c * 16 + y1 * 4 + x0] + w11 * xs[c * 16 + y1 * 4 + x1])
+      v0 = TSR_UP(0); v1 = TSR_UP(1); v2 = TSR_UP(2);
+#undef TSR_UP
+    }
+    up[i * 3 + 0] = v0; up[i * 3 + 1] = v1; up[i * 3 + 2] = v2;
+  }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const float* __restrict__ x, long long x_bstride, const float* __restrict__ w /*64,3,3,3*/,
+                OutT* __restrict__ out, int out_ld, int B, int sf, int relu) {
+  extern __shared__ float smem[];
+  float* ws = smem;              // [27][64]  (q = tap*3 + c)
+  float* xs = ws + 27 * 64;      // 48
+  float* up = xs + 48;           // (H+2)^2*3
+  const int H = 4 * sf, P = H + 2;
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
+    int co = i & 63, q = i >> 6;
+    int tap = q / 3, c = q % 3;
+    ws[i] = w[(co * 3 + c) * 9 + tap];
+  }
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x < 48) xs[threadIdx.x] = x[(long long)b * x_bstride + threadIdx.x];
+    __syncthreads();
+    build_upsampled(xs, up, sf);
+    __syncthreads();
+    for (int it = threadIdx.x; it < H * H * 16; it += blockDim.x) {
+      int g = it & 15, p = it >> 4;
+      int y = p / H, xx = p - y * H;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const float* u = up + ((y + tap / 3) * P + xx + tap % 3) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float a = u[c];
+          float4 wv = *reinterpret_cast<const float4*>(ws + (tap * 3 + c) * 64 + g * 4);
+          acc.x = fmaf(a, wv.x, acc.x); acc.y = fmaf(a, wv.y, acc.y);
+          acc.z = fmaf(a, wv.z, acc.z); acc.w = fmaf(a, wv.w, acc.w);
+        }
+      }
+      if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+      st4(out + ((long long)b * H * H + p) * out_ld + g * 4, acc);
+    }
+  }
+}
+
+// head weight gradient, level 1: one partial [27][64] per CTA, CTAs stride over samples
+template <typename GT>
+__global__ void __launch_bounds__(256)
+head_wgrad_kernel(const float* __restrict__ x, long long x_bstride, const GT* __restrict__ dout, int dout_ld,
+                  float* __restrict__ partial, int B, int sf) {
+  extern __shared__ float smem[];
+  float* xs = smem;
+  float* up = xs + 48;
+  const int H = 4 * sf, P = H + 2;
+  const int co = threadIdx.x & 63, qb = threadIdx.x >> 6;   // q = qb + 4j, j < 7 (27 taps*chan)
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x < 48) xs[threadIdx.x] = x[(long long)b * x_bstride + threadIdx.x];
+    __syncthreads();
+    build_upsampled(xs, up, sf);
+    __syncthreads();
+    const GT* d = dout + (long long)b * H * H * dout_ld + co;
+    for (int p = 0; p < H * H; ++p) {
+      float g = ldf(d + (long long)p * dout_ld);
+      int y = p / H, xx = p - y * H;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        int q = qb + 4 * j;
+        if (q < 27) {
+          int tap = q / 3, c = q - tap * 3;
+          acc[j] = fmaf(up[((y + tap / 3) * P + xx + tap % 3) * 3 + c], g, acc[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    int q = qb + 4 * j;
+    if (q < 27) partial[((long long)blockIdx.x * 27 + q) * 64 + co] = acc[j];
+  }
+}
+__global__ void head_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ dw,
+                                         int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;   // i = q*64 + co
+  if (i >= 27 * 64) return;
+  int co = i & 63, q = i >> 6;
+  int tap = q / 3, c = q % 3;
+  float s = 0.f;
+  for (int k = 0; k < nparts; ++k) s += partial[(long long)k * 27 * 64 + i];
+  int o = (co * 3 + c) * 9 + tap;
+  dw[o] = accumulate ? dw[o] + s : s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tail: 3x3 conv Cin -> 1 (no bias) + ReLU.   reference tactileSR_model.py:55-56, :125-126
+// ---------------------------------------------------------------------------------------------
+template <typename InT>
+__global__ void __launch_bounds__(256)
+tail_fwd_kernel(const InT* __restrict__ in, int in_ld, const float* __restrict__ w /*1,Cin,3,3*/,
+                float* __restrict__ out, int Mtotal, int H, int W, int Cin, int relu) {
+  extern __shared__ float ws[];   // [9][Cin]
+  for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) {
+    int ci = i % Cin, tap = i / Cin;
+    ws[i] = w[ci * 9 + tap];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int HW = H * W;
+  for (int p = blockIdx.x * nw + warp; p < Mtotal; p += gridDim.x * nw) {
+    int b = p / HW, rem = p - b * HW;
+    int y = rem / W, x = rem - y * W;
+    float s = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const InT* src = in + ((long long)b * HW + (long long)yy * W + xx) * in_ld;
+      for (int c = lane * 4; c < Cin; c += 128) {
+        float4 v = ld4(src + c);
+        float4 wv = *reinterpret_cast<const float4*>(ws + tap * Cin + c);
+        s += v.x * wv.x + v.y * wv.y + v.z * wv.z + v.w * wv.w;
+      }
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[p] = relu ? fmaxf(s, 0.f) : s;
+  }
+}
+
+// tail data gradient: din[p][ci] = sum_tap dz[p - shift(tap)] * w[tap][ci],  dz = dout * (out > 0)
+template <typename GT>
+__global__ void __launch_bounds__(256)
+tail_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out_act,
+                  const float* __restrict__ w, GT* __restrict__ din, int din_ld, int Mtotal, int H, int W,
+                  int Cin, int relu) {
+  extern __shared__ float ws[];   // [9][Cin]
+  for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) {
+    int ci = i % Cin, tap = i / Cin;
+    ws[i] = w[ci * 9 + tap];
+  }
+  __syncthreads();
+  const int q4 = Cin / 4, HW = H * W;
+  long long total = (long long)Mtotal * q4;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total;
+       it += (long long)gridDim.x * blockDim.x) {
+    int q = (int)(it % q4);
+    int p = (int)(it / q4);
+    int b = p / HW, rem = p - b * HW;
+    int y = rem / W, x = rem - y * W;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      // output pixel o = p - shift(tap) used input p with weight tap
+      int yy = y - (tap / 3 - 1), xx = x - (tap % 3 - 1);
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      int o = b * HW + yy * W + xx;
+      float g = dout[o];
+      if (relu && !(out_act[o] > 0.f)) g = 0.f;
+      float4 wv = *reinterpret_cast<const float4*>(ws + tap * Cin + q * 4);
+      acc.x = fmaf(g, wv.x, acc.x); acc.y = fmaf(g, wv.y, acc.y);
+      acc.z = fmaf(g, wv.z, acc.z); acc.w = fmaf(g, wv.w, acc.w);
+    }
+    st4(din + (long long)p * din_ld + q * 4, acc);
+  }
+}
+
+// tail weight gradient, level 1: partial[blk][9][Cin]; thread = (channel quad, pixel lane)
+template <typename InT>
+__global__ void __launch_bounds__(256)
+tail_wgrad_kernel(const InT* __restrict__ in, int in_ld, const float* __restrict__ dout,
+                  const float* __restrict__ out_act, float* __restrict__ partial, int Mtotal, int H, int W,
+                  int Cin, int relu, int pix_per_block) {
+  extern __shared__ float4 red[];   // [lanes][q4] reused per tap
+  const int q4 = Cin / 4, lanes = blockDim.x / q4;
+  const int q = threadIdx.x % q4, lane = threadIdx.x / q4;
+  const int HW = H * W;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, Mtotal);
+  float4 acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = p0 + lane; p < p1; p += lanes) {
+    float g = dout[p];
+    if (relu && !(out_act[p] > 0.f)) g = 0.f;
+    if (g == 0.f) continue;
+    int b = p / HW, rem = p - b * HW;
+    int y = rem / W, x = rem - y * W;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      float4 v = ld4(in + ((long long)b * HW + (long long)yy * W + xx) * in_ld + q * 4);
+      acc[tap].x = fmaf(g, v.x, acc[tap].x); acc[tap].y = fmaf(g, v.y, acc[tap].y);
+      acc[tap].z = fmaf(g, v.z, acc[tap].z); acc[tap].w = fmaf(g, v.w, acc[tap].w);
+    }
+  }
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    __syncthreads();
+    red[lane * q4 + q] = acc[tap];
+    __syncthreads();
+    if (lane == 0) {
+      float4 s = acc[tap];
+      for (int l = 1; l < lanes; ++l) {
+        float4 v = red[l * q4 + q];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      *reinterpret_cast<float4*>(partial + ((long long)blockIdx.x * 9 + tap) * Cin + q * 4) = s;
+    }
+  }
+}
+__global__ void tail_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int Cin,
+                                         float* __restrict__ dw, int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;   // i = tap*Cin + ci
+  if (i >= 9 * Cin) return;
+  int ci = i % Cin, tap = i / Cin;
+  double s = 0.0;
+  for (int k = 0; k < nparts; ++k) s += (double)partial[(long long)k * 9 * Cin + i];
+  int o = ci * 9 + tap;
+  dw[o] = accumulate ? dw[o] + (float)s : (float)s;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int tsr_pack_conv_weight_f32(const float* w_oihw, float* w_fwd, float* w_dgrad, int Cout, int Cin, int KS,
+                             cudaStream_t stream) {
+  TSR_REQUIRE(w_oihw && (w_fwd || w_dgrad), "pack_conv_weight_f32: null pointer");
+  long long n = (long long)Cout * Cin * KS * KS;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 2048) blocks = 2048;
+  pack_weight_f32_kernel<<<blocks, 256, 0, stream>>>(w_oihw, w_fwd, w_dgrad, Cout, Cin, KS);
+  TSR_CHECK_LAUNCH("pack_conv_weight_f32");
+  return TSR_OK;
+}
+
+int tsr_conv2d_f32(const float* in, int in_ld, const float* w_packed, const float* bias,
+                   const float* residual, int res_ld, float* out, int out_ld, int B, int H, int W, int Cin,
+                   int Cout, int KS, int flags, cudaStream_t stream) {
+  TSR_REQUIRE(in && w_packed && out, "conv2d_f32: null pointer");
+  TSR_REQUIRE(Cin % 16 == 0 && Cout % 64 == 0, "conv2d_f32: need Cin %% 16 == 0 and Cout %% 64 == 0 (got %d, %d)", Cin, Cout);
+  TSR_REQUIRE(KS == 1 || KS == 3 || KS == 5, "conv2d_f32: kernel size %d unsupported", KS);
+  TSR_REQUIRE(in_ld % 4 == 0 && out_ld % 4 == 0 && (!residual || res_ld % 4 == 0), "conv2d_f32: row strides must be multiples of 4");
+  long long M = (long long)B * H * W;
+  TSR_REQUIRE(M > 0 && M < (1ll << 31), "conv2d_f32: bad pixel count");
+  dim3 grid(tsr_cdiv(M, BM), Cout / BN);
+  conv2d_f32_kernel<<<grid, 256, 0, stream>>>(in, in_ld, w_packed, bias, residual, res_ld, out, out_ld, (int)M,
+                                              H, W, Cin, Cout, KS, flags);
+  TSR_CHECK_LAUNCH("conv2d_f32");
+  return TSR_OK;
+}
+
+static int wgrad_splits(long long M, int tiles) {
+  int s = (4 * 148 + tiles - 1) / tiles;
+  int maxs = (int)((M + 255) / 256);
+  if (s > maxs) s = maxs;
+  if (s < 1) s = 1;
+  if (s > 256) s = 256;
+  return s;
+}
+
+size_t tsr_conv2d_wgrad_f32_workspace(int B, int H, int W, int Cin, int Cout, int KS) {
+  long long M = (long long)B * H * W;
+  int tiles = KS * KS * (Cin / 64) * (Cout / 64);
+  if (tiles <= 0) return 0;
+  return (size_t)wgrad_splits(M, tiles) * KS * KS * Cin * Cout * sizeof(float);
+}
+
+int tsr_conv2d_wgrad_f32(const float* in, int in_ld, const float* dout, int dout_ld, float* dw_oihw,
+                         void* workspace, size_t ws_bytes, int B, int H, int W, int Cin, int Cout, int KS,
+                         int accumulate, cudaStream_t stream) {
+  TSR_REQUIRE(in && dout && dw_oihw && workspace, "conv2d_wgrad_f32: null pointer");
+  TSR_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv2d_wgrad_f32: need Cin, Cout %% 64 == 0 (got %d, %d)", Cin, Cout);
+  TSR_REQUIRE(in_ld % 4 == 0 && dout_ld % 4 == 0, "conv2d_wgrad_f32: row strides must be multiples of 4");
+  long long M = (long long)B * H * W;
+  int taps = KS * KS;
+  int tiles = taps * (Cin / 64) * (Cout / 64);
+  int S = wgrad_splits(M, tiles);
+  size_t need = (size_t)S * taps * Cin * Cout * sizeof(float);
+  if (ws_bytes < need) {
+    tsr_set_error("conv2d_wgrad_f32: workspace too small (%zu < %zu)", ws_bytes, need);
+    return TSR_ERR_WORKSPACE;
+  }
+  int pps = (int)(((M + S - 1) / S + 15) / 16 * 16);
+  conv2d_wgrad_f32_kernel<<<dim3(tiles, S), 256, 0, stream>>>(in, in_ld, dout, dout_ld, (float*)workspace,
+                                                              (int)M, H, W, Cin, Cout, KS, pps);
+  TSR_CHECK_LAUNCH("conv2d_wgrad_f32");
+  long long n = (long long)taps * Cin * Cout;
+  wgrad_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>((const float*)workspace, dw_oihw, S, taps, Cin,
+                                                                  Cout, accumulate);
+  TSR_CHECK_LAUNCH("wgrad_reduce");
+  return TSR_OK;
+}
+
+size_t tsr_colsum_workspace(long long npix, int C) {
+  int nb = tsr_cdiv(npix, 1024);
+  if (nb > 1024) nb = 1024;
+  return (size_t)nb * C * sizeof(float);
+}
+
+int tsr_colsum_f32(const float* x, int ld, long long npix, int C, float* out, void* workspace, size_t ws_bytes,
+                   int accumulate, cudaStream_t stream) {
+  TSR_REQUIRE(x && out && workspace, "colsum_f32: null pointer");
+  TSR_REQUIRE(C % 4 == 0 && C <= 1024 && ld % 4 == 0, "colsum_f32: C must be a multiple of 4 and <= 1024");
+  int nb = tsr_cdiv(npix, 1024);
+  if (nb > 1024) nb = 1024;
+  int rpb = tsr_cdiv(npix, nb);
+  nb = tsr_cdiv(npix, rpb);
+  TSR_REQUIRE(ws_bytes >= (size_t)nb * C * sizeof(float), "colsum_f32: workspace too small");
+  int q4 = C / 4;
+  int threads = (256 / q4) * q4;
+  if (threads < q4) threads = q4;
+  colsum_partial_kernel<<<nb, threads, threads * sizeof(float4), stream>>>(x, ld, (int)npix, C, (float*)workspace, rpb);
+  TSR_CHECK_LAUNCH("colsum_partial");
+  colsum_final_kernel<<<tsr_cdiv(C, 128), 128, 0, stream>>>((const float*)workspace, nb, C, out, accumulate);
+  TSR_CHECK_LAUNCH("colsum_final");
+  return TSR_OK;
+}
+
+static size_t head_smem(int sf) { return (size_t)(27 * 64 + 48 + (4 * sf + 2) * (4 * sf + 2) * 3) * sizeof(float); }
+
+int tsr_head_fwd(const float* x, long long x_bstride, const float* w_oihw, void* out, int out_ld, int out_bf16,
+                 int B, int sf, int relu, cudaStream_t stream) {
+  TSR_REQUIRE(x && w_oihw && out, "head_fwd: null pointer");
+  TSR_REQUIRE(sf >= 1 && sf <= 24, "head_fwd: scale_factor %d unsupported (1..24)", sf);
+  TSR_REQUIRE(out_ld % 4 == 0, "head_fwd: out_ld must be a multiple of 4");
+  size_t smem = head_smem(sf);
+  int grid = B < 148 * 4 ? B : 148 * 4;
+  if (out_bf16) {
+    TSR_CUDA(cudaFuncSetAttribute(head_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(x, x_bstride, w_oihw, (__nv_bfloat16*)out, out_ld, B, sf, relu);
+  } else {
+    TSR_CUDA(cudaFuncSetAttribute(head_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_fwd_kernel<float><<<grid, 256, smem, stream>>>(x, x_bstride, w_oihw, (float*)out, out_ld, B, sf, relu);
+  }
+  TSR_CHECK_LAUNCH("head_fwd");
+  return TSR_OK;
+}
+
+size_t tsr_head_wgrad_workspace(int B) {
+  int grid = B < 296 ? B : 296;
+  return (size_t)grid * 27 * 64 * sizeof(float);
+}
+
+int tsr_head_wgrad(const float* x, long long x_bstride, const void* dout, int dout_ld, int dout_bf16,
+                   float* dw_oihw, void* workspace, size_t ws_bytes, int B, int sf, int accumulate,
+                   cudaStream_t stream) {
+  TSR_REQUIRE(x && dout && dw_oihw && workspace, "head_wgrad: null pointer");
+  TSR_REQUIRE(sf >= 1 && sf <= 24, "head_wgrad: scale_factor %d unsupported", sf);
+  int grid = B < 296 ? B : 296;
+  TSR_REQUIRE(ws_bytes >= (size_t)grid * 27 * 64 * sizeof(float), "head_wgrad: workspace too small");
+  size_t smem = (size_t)(48 + (4 * sf + 2) * (4 * sf + 2) * 3) * sizeof(float);
+  if (dout_bf16) {
+    TSR_CUDA(cudaFuncSetAttribute(head_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_wgrad_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(x, x_bstride, (const __nv_bfloat16*)dout, dout_ld, (float*)workspace, B, sf);
+  } else {
+    TSR_CUDA(cudaFuncSetAttribute(head_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_wgrad_kernel<float><<<grid, 256, smem, stream>>>(x, x_bstride, (const float*)dout, dout_ld, (float*)workspace, B, sf);
+  }
+  TSR_CHECK_LAUNCH("head_wgrad");
+  head_wgrad_reduce_kernel<<<tsr_cdiv(27 * 64, 256), 256, 0, stream>>>((const float*)workspace, grid, dw_oihw, accumulate);
+  TSR_CHECK_LAUNCH("head_wgrad_reduce");
+  return TSR_OK;
+}
+
+int tsr_tail_fwd(const void* in, int in_ld, int in_bf16, const float* w_oihw, float* out, int B, int H, int W,
+                 int Cin, int relu, cudaStream_t stream) {
+  TSR_REQUIRE(in && w_oihw && out, "tail_fwd: null pointer");
+  TSR_REQUIRE(Cin % 4 == 0 && Cin <= 1024 && in_ld % 4 == 0, "tail_fwd: Cin must be a multiple of 4");
+  long long M = (long long)B * H * W;
+  int grid = tsr_cdiv(M, 8);
+  if (grid > 148 * 16) grid = 148 * 16;
+  size_t smem = (size_t)9 * Cin * sizeof(float);
+  if (in_bf16)
+    tail_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)in, in_ld, w_oihw, out, (int)M, H, W, Cin, relu);
+  else
+    tail_fwd_kernel<float><<<grid, 256, smem, stream>>>((const float*)in, in_ld, w_oihw, out, (int)M, H, W, Cin, relu);
+  TSR_CHECK_LAUNCH("tail_fwd");
+  return TSR_OK;
+}
+
+int tsr_tail_dgrad(const float* dout, const float* out_act, const float* w_oihw, void* din, int din_ld,
+                   int din_bf16, int B, int H, int W, int Cin, int relu, cudaStream_t stream) {
+  TSR_REQUIRE(dout && w_oihw && din && (!relu || out_act), "tail_dgrad: null pointer");
+  TSR_REQUIRE(Cin % 4 == 0 && din_ld % 4 == 0, "tail_dgrad: Cin must be a multiple of 4");
+  long long M = (long long)B * H * W;
+  long long total = M * (Cin / 4);
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 32) grid = 148 * 32;
+  size_t smem = (size_t)9 * Cin * sizeof(float);
+  if (din_bf16)
+    tail_dgrad_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(dout, out_act, w_oihw, (__nv_bfloat16*)din, din_ld, (int)M, H, W, Cin, relu);
+  else
+    tail_dgrad_kernel<float><<<grid, 256, smem, stream>>>(dout, out_act, w_oihw, (float*)din, din_ld, (int)M, H, W, Cin, relu);
+  TSR_CHECK_LAUNCH("tail_dgrad");
+  return TSR_OK;
+}
+
+static int tail_wgrad_blocks(long long M) {
+  int nb = tsr_cdiv(M, 512);
+  if (nb > 592) nb = 592;
+  return nb;
+}
+size_t tsr_tail_wgrad_workspace(int B, int H, int W, int Cin) {
+  return (size_t)tail_wgrad_blocks((long long)B * H * W) * 9 * Cin * sizeof(float);
+}
+
+int tsr_tail_wgrad(const void* in, int in_ld, int in_bf16, const float* dout, const float* out_act,
+                   float* dw_oihw, void* workspace, size_t ws_bytes, int B, int H, int W, int Cin, int relu,
+                   int accumulate, cudaStream_t stream) {
+  TSR_REQUIRE(in && dout && dw_oihw && workspace && (!relu || out_act), "tail_wgrad: null pointer");
+  TSR_REQUIRE(Cin % 4 == 0 && Cin <= 1024 && in_ld % 4 == 0, "tail_wgrad: Cin must be a multiple of 4");
+  long long M = (long long)B * H * W;
+  int nb = tail_wgrad_blocks(M);
+  int ppb = tsr_cdiv(M, nb);
+  nb = tsr_cdiv(M, ppb);
+  TSR_REQUIRE(ws_bytes >= (size_t)nb * 9 * Cin * sizeof(float), "tail_wgrad: workspace too small");
+  int q4 = Cin / 4;
+  int threads = (256 / q4) * q4;
+  if (threads < q4) threads = q4;
+  size_t smem = (size_t)threads * sizeof(float4);
+  if (in_bf16)
+    tail_wgrad_kernel<__nv_bfloat16><<<nb, threads, smem, stream>>>((const __nv_bfloat16*)in, in_ld, dout, out_act, (float*)workspace, (int)M, H, W, Cin, relu, ppb);
+  else
+    tail_wgrad_kernel<float><<<nb, threads, smem, stream>>>((const float*)in, in_ld, dout, out_act, (float*)workspace, (int)M, H, W, Cin, relu, ppb);
+  TSR_CHECK_LAUNCH("tail_wgrad");
+  tail_wgrad_reduce_kernel<<<tsr_cdiv(9 * Cin, 256), 256, 0, stream>>>((const float*)workspace, nb, Cin, dw_oihw, accumulate);
+  TSR_CHECK_LAUNCH("tail_wgrad_reduce");
+  return TSR_OK;
+}
+
+}  // extern "C"

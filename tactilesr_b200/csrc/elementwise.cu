@@ -1,0 +1,561 @@
+// HBM-bound kernels of the SR path: BatchNorm (train/eval, forward/backward), ReLU backward,
+// fused MSE loss + HR-label preparation, fused Adam, layout conversion.
+// All take NHWC activations [pixel][ld] with C channels starting at the given pointer; storage is
+// fp32 (fp32 mode) or bf16 (tensor-core mode).  Loads/stores are 4 channels wide, reductions are
+// two-level (per-block partials in a fixed order, then one finalising block) => deterministic.
+//
+// Replaces nn.BatchNorm2d / nn.ReLU / nn.MSELoss / F.interpolate / optim.Adam at reference
+// model/tactileSR_model.py:38-39,42-43,48-49,169-170,..., train/tactileSR_train.py:39,44-45,49,212.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm statistics: partial[blk][0][C] = sum x, partial[blk][1][C] = sum x^2
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void bn_stats_partial_kernel(const T* __restrict__ x, int ld, int npix, int C,
+                                        float* __restrict__ partial, int rows_per_block) {
+  extern __shared__ float4 sm[];
+  const int q4 = C / 4, lanes = blockDim.x / q4;
+  const int q = threadIdx.x % q4, lane = threadIdx.x / q4;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, npix);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
+  for (int r = r0 + lane; r < r1; r += lanes) {
+    float4 v = ld4(x + (long long)r * ld + q * 4);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    ss.x = fmaf(v.x, v.x, ss.x); ss.y = fmaf(v.y, v.y, ss.y); ss.z = fmaf(v.z, v.z, ss.z); ss.w = fmaf(v.w, v.w, ss.w);
+  }
+  sm[threadIdx.x] = s;
+  sm[blockDim.x + threadIdx.x] = ss;
+  __syncthreads();
+  if (lane == 0) {
+    for (int l = 1; l < lanes; ++l) {
+      float4 a = sm[l * q4 + q], b = sm[blockDim.x + l * q4 + q];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      ss.x += b.x; ss.y += b.y; ss.z += b.z; ss.w += b.w;
+    }
+    *reinterpret_cast<float4*>(partial + ((long long)blockIdx.x * 2 + 0) * C + q * 4) = s;
+    *reinterpret_cast<float4*>(partial + ((long long)blockIdx.x * 2 + 1) * C + q * 4) = ss;
+  }
+}
+
+// finalise: batch mean / biased var -> scale, shift, saved mean / invstd; running-stat update with
+// momentum and the unbiased variance (nn.BatchNorm2d semantics), num_batches_tracked += 1.
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double n,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ nbt, float momentum, float eps,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    s += (double)partial[((long long)b * 2 + 0) * C + c];
+    ss += (double)partial[((long long)b * 2 + 1) * C + c];
+  }
+  double mean = s / n;
+  double var = ss / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  double invstd = 1.0 / sqrt(var + (double)eps);
+  float sc = (float)((double)gamma[c] * invstd);
+  scale[c] = sc;
+  shift[c] = (float)((double)beta[c] - mean * (double)gamma[c] * invstd);
+  save_mean[c] = (float)mean;
+  save_invstd[c] = (float)invstd;
+  if (running_mean) {
+    double unbiased = n > 1.0 ? var * (n / (n - 1.0)) : var;
+    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
+    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+  }
+}
+
+// eval mode: scale/shift from the running statistics
+__global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      float eps, float* __restrict__ scale, float* __restrict__ shift,
+                                      float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float invstd = 1.0f / sqrtf(running_var[c] + eps);
+  float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - running_mean[c] * sc;
+  save_mean[c] = running_mean[c];
+  save_invstd[c] = invstd;
+}
+
+template <typename Tin, typename Tout>
+__global__ void bn_apply_kernel(const Tin* __restrict__ x, int x_ld, const float* __restrict__ scale,
+                                const float* __restrict__ shift, Tout* __restrict__ out, int out_ld,
+                                long long npix, int C, int relu) {
+  const int q4 = C / 4;
+  long long total = npix * q4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int q = (int)(i % q4);
+    long long p = i / q4;
+    float4 v = ld4(x + p * x_ld + q * 4);
+    float4 sc = *reinterpret_cast<const float4*>(scale + q * 4);
+    float4 sh = *reinterpret_cast<const float4*>(shift + q * 4);
+    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    st4(out + p * out_ld + q * 4, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm backward.  z = y*scale + shift, a = relu(z).  Given da:
+//   dz = da * [z > 0],  xhat = (y - mean) * invstd
+//   level 1: partial sums of dz and dz*xhat;  finalise: dgamma, dbeta, c1 = sum dz / n, c2 = sum dz*xhat / n
+//   apply:   dy = gamma*invstd * (dz - c1 - xhat*c2)           (train)   |   dy = dz * scale  (eval)
+// ------------------------------------------------------------------------------------------
+template <typename Tg, typename Ty>
+__global__ void bn_bwd_partial_kernel(const Tg* __restrict__ da, int da_ld, const Ty* __restrict__ y, int y_ld,
+                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                      int npix, int C, int relu, float* __restrict__ partial, int rows_per_block) {
+  extern __shared__ float4 sm[];
+  const int q4 = C / 4, lanes = blockDim.x / q4;
+  const int q = threadIdx.x % q4, lane = threadIdx.x / q4;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, npix);
+  const float4 sc = *reinterpret_cast<const float4*>(scale + q * 4);
+  const float4 sh = *reinterpret_cast<const float4*>(shift + q * 4);
+  const float4 mu = *reinterpret_cast<const float4*>(mean + q * 4);
+  const float4 is = *reinterpret_cast<const float4*>(invstd + q * 4);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), sx = s;
+  for (int r = r0 + lane; r < r1; r += lanes) {
+    float4 g = ld4(da + (long long)r * da_ld + q * 4);
+    float4 v = ld4(y + (long long)r * y_ld + q * 4);
+    if (relu) {
+      if (!(fmaf(v.x, sc.x, sh.x) > 0.f)) g.x = 0.f;
+      if (!(fmaf(v.y, sc.y, sh.y) > 0.f)) g.y = 0.f;
+      if (!(fmaf(v.z, sc.z, sh.z) > 0.f)) g.z = 0.f;
+      if (!(fmaf(v.w, sc.w, sh.w) > 0.f)) g.w = 0.f;
+    }
+    s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+    sx.x = fmaf(g.x, (v.x - mu.x) * is.x, sx.x); sx.y = fmaf(g.y, (v.y - mu.y) * is.y, sx.y);
+    sx.z = fmaf(g.z, (v.z - mu.z) * is.z, sx.z); sx.w = fmaf(g.w, (v.w - mu.w) * is.w, sx.w);
+  }
+  sm[threadIdx.x] = s;
+  sm[blockDim.x + threadIdx.x] = sx;
+  __syncthreads();
+  if (lane == 0) {
+    for (int l = 1; l < lanes; ++l) {
+      float4 a = sm[l * q4 + q], b = sm[blockDim.x + l * q4 + q];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      sx.x += b.x; sx.y += b.y; sx.z += b.z; sx.w += b.w;
+    }
+    *reinterpret_cast<float4*>(partial + ((long long)blockIdx.x * 2 + 0) * C + q * 4) = s;
+    *reinterpret_cast<float4*>(partial + ((long long)blockIdx.x * 2 + 1) * C + q * 4) = sx;
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double n,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
+                                       float* __restrict__ c1, float* __restrict__ c2, int training) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, sx = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    s += (double)partial[((long long)b * 2 + 0) * C + c];
+    sx += (double)partial[((long long)b * 2 + 1) * C + c];
+  }
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)sx : (float)sx;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
+  c1[c] = training ? (float)(s / n) : 0.f;
+  c2[c] = training ? (float)(sx / n) : 0.f;
+}
+
+template <typename Tg, typename Ty, typename To>
+__global__ void bn_bwd_apply_kernel(const Tg* __restrict__ da, int da_ld, const Ty* __restrict__ y, int y_ld,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ c1, const float* __restrict__ c2,
+                                    To* __restrict__ dy, int dy_ld, long long npix, int C, int relu) {
+  const int q4 = C / 4;
+  long long total = npix * q4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int q = (int)(i % q4);
+    long long p = i / q4;
+    float4 g = ld4(da + p * da_ld + q * 4);
+    float4 v = ld4(y + p * y_ld + q * 4);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + q * 4);
+    const float4 sh = *reinterpret_cast<const float4*>(shift + q * 4);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + q * 4);
+    const float4 is = *reinterpret_cast<const float4*>(invstd + q * 4);
+    const float4 k1 = *reinterpret_cast<const float4*>(c1 + q * 4);
+    const float4 k2 = *reinterpret_cast<const float4*>(c2 + q * 4);
+    if (relu) {
+      if (!(fmaf(v.x, sc.x, sh.x) > 0.f)) g.x = 0.f;
+      if (!(fmaf(v.y, sc.y, sh.y) > 0.f)) g.y = 0.f;
+      if (!(fmaf(v.z, sc.z, sh.z) > 0.f)) g.z = 0.f;
+      if (!(fmaf(v.w, sc.w, sh.w) > 0.f)) g.w = 0.f;
+    }
+    float4 o;
+    o.x = sc.x * (g.x - k1.x - (v.x - mu.x) * is.x * k2.x);
+    o.y = sc.y * (g.y - k1.y - (v.y - mu.y) * is.y * k2.y);
+    o.z = sc.z * (g.z - k1.z - (v.z - mu.z) * is.z * k2.z);
+    o.w = sc.w * (g.w - k1.w - (v.w - mu.w) * is.w * k2.w);
+    st4(dy + p * dy_ld + q * 4, o);
+  }
+}
+
+// dz = da * [a > 0]   (ReLU fused into a conv epilogue: a is the stored activation)
+template <typename Tg, typename Ta, typename To>
+__global__ void relu_bwd_kernel(const Tg* __restrict__ da, int da_ld, const Ta* __restrict__ a, int a_ld,
+                                To* __restrict__ dz, int dz_ld, long long npix, int C) {
+  const int q4 = C / 4;
+  long long total = npix * q4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int q = (int)(i % q4);
+    long long p = i / q4;
+    float4 g = ld4(da + p * da_ld + q * 4);
+    float4 v = ld4(a + p * a_ld + q * 4);
+    if (!(v.x > 0.f)) g.x = 0.f;
+    if (!(v.y > 0.f)) g.y = 0.f;
+    if (!(v.z > 0.f)) g.z = 0.f;
+    if (!(v.w > 0.f)) g.w = 0.f;
+    st4(dz + p * dz_ld + q * 4, g);
+  }
+}
+
+// strided copy / dtype conversion of channel slices (NHWC), also used for fp32 <-> bf16
+template <typename Ti, typename To>
+__global__ void copy_kernel(const Ti* __restrict__ x, int x_ld, To* __restrict__ out, int out_ld, long long npix, int C) {
+  const int q4 = C / 4;
+  long long total = npix * q4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int q = (int)(i % q4);
+    long long p = i / q4;
+    st4(out + p * out_ld + q * 4, ld4(x + p * x_ld + q * 4));
+  }
+}
+
+// NCHW fp32 <-> NHWC (fp32 / bf16); small generic kernels for the module boundary
+template <typename To>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, To* __restrict__ out, int out_ld, int B, int C, int HW) {
+  long long total = (long long)B * C * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long r = i / C;
+    int p = (int)(r % HW);
+    int b = (int)(r / HW);
+    stf(out + ((long long)b * HW + p) * out_ld + c, x[((long long)b * C + c) * HW + p]);
+  }
+}
+template <typename Ti>
+__global__ void nhwc_to_nchw_kernel(const Ti* __restrict__ x, int x_ld, float* __restrict__ out, int B, int C, int HW) {
+  long long total = (long long)B * C * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int p = (int)(i % HW);
+    long long r = i / HW;
+    int c = (int)(r % C);
+    int b = (int)(r / C);
+    out[i] = ldf(x + ((long long)b * HW + p) * x_ld + c);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused MSE loss + HR label preparation (train/tactileSR_train.py:44-45,49):
+//   HR = bilinear_resize(HR_raw / scale_num, (H, W));  loss = mean((out - HR)^2);  dout = 2 (out - HR) / N
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bilinear_src(int d, float scale, int n_in, int& i0, int& i1, float& l1) {
+  float s = fmaxf(scale * (d + 0.5f) - 0.5f, 0.f);
+  i0 = min((int)s, n_in - 1);
+  i1 = min(i0 + 1, n_in - 1);
+  l1 = s - i0;
+}
+
+__global__ void mse_hr_kernel(const float* __restrict__ out, const float* __restrict__ hr_raw, float inv_scale_num,
+                              int B, int H, int W, int Hin, int Win, float* __restrict__ dout, float grad_scale,
+                              float* __restrict__ partial) {
+  const long long total = (long long)B * H * W;
+  const float sy = (float)Hin / (float)H, sx = (float)Win / (float)W;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % W);
+    long long r = i / W;
+    int y = (int)(r % H);
+    int b = (int)(r / H);
+    float hr;
+    if (Hin == H && Win == W) {
+      hr = hr_raw[i] * inv_scale_num;
+    } else {
+      int y0, y1, x0, x1;
+      float ly, lx;
+      bilinear_src(y, sy, Hin, y0, y1, ly);
+      bilinear_src(x, sx, Win, x0, x1, lx);
+      const float* src = hr_raw + (long long)b * Hin * Win;
+      float v00 = src[y0 * Win + x0] * inv_scale_num, v01 = src[y0 * Win + x1] * inv_scale_num;
+      float v10 = src[y1 * Win + x0] * inv_scale_num, v11 = src[y1 * Win + x1] * inv_scale_num;
+      hr = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+    }
+    float d = out[i] - hr;
+    acc = fmaf(d, d, acc);
+    if (dout) dout[i] = d * grad_scale;
+  }
+  __shared__ float red[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+  }
+}
+__global__ void sum_final_kernel(const float* __restrict__ partial, int n, double mul, float* __restrict__ out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += (double)partial[i];
+    *out = (float)(s * mul);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused Adam (torch.optim.Adam, coupled L2 weight decay, no amsgrad) over a flat fp32 buffer
+// ------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+                            float inv_bc1, float inv_sqrt_bc2, float grad_scale) {
+  long long i4 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
+  for (; i4 < n; i4 += (long long)gridDim.x * blockDim.x * 4) {
+    if (i4 + 4 <= n) {
+      float4 pp = *reinterpret_cast<float4*>(p + i4), gg = *reinterpret_cast<const float4*>(g + i4);
+      float4 mm = *reinterpret_cast<float4*>(m + i4), vv = *reinterpret_cast<float4*>(v + i4);
+      float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float gr = fmaf(wd, pa[k], ga[k] * grad_scale);
+        ma[k] = b1 * ma[k] + (1.f - b1) * gr;
+        va[k] = b2 * va[k] + (1.f - b2) * gr * gr;
+        float denom = sqrtf(va[k]) * inv_sqrt_bc2 + eps;
+        pa[k] -= (lr * inv_bc1) * (ma[k] / denom);
+      }
+      *reinterpret_cast<float4*>(p + i4) = pp;
+      *reinterpret_cast<float4*>(m + i4) = mm;
+      *reinterpret_cast<float4*>(v + i4) = vv;
+    } else {
+      for (long long i = i4; i < n; ++i) {
+        float gr = fmaf(wd, p[i], g[i] * grad_scale);
+        m[i] = b1 * m[i] + (1.f - b1) * gr;
+        v[i] = b2 * v[i] + (1.f - b2) * gr * gr;
+        float denom = sqrtf(v[i]) * inv_sqrt_bc2 + eps;
+        p[i] -= (lr * inv_bc1) * (m[i] / denom);
+      }
+    }
+  }
+}
+
+inline int ew_grid(long long total) {
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+inline int red_blocks(long long npix, int& rows_per_block) {
+  int nb = tsr_cdiv(npix, 512);
+  if (nb > 592) nb = 592;
+  if (nb < 1) nb = 1;
+  rows_per_block = tsr_cdiv(npix, nb);
+  return tsr_cdiv(npix, rows_per_block);
+}
+inline int red_threads(int C) {
+  int q4 = C / 4;
+  int t = (256 / q4) * q4;
+  return t < q4 ? q4 : t;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t tsr_bn_workspace(long long npix, int C) {
+  int rpb;
+  return (size_t)red_blocks(npix, rpb) * 2 * C * sizeof(float);
+}
+
+// training-mode statistics of y -> scale/shift (+ saved mean/invstd), running stats updated in place.
+int tsr_bn_train_stats(const void* y, int y_ld, int y_bf16, long long npix, int C, const float* gamma,
+                       const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
+                       float momentum, float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
+                       void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  TSR_REQUIRE(y && gamma && beta && scale && shift && save_mean && save_invstd && workspace, "bn_train_stats: null pointer");
+  TSR_REQUIRE(C % 4 == 0 && C <= 1024 && y_ld % 4 == 0, "bn_train_stats: C must be a multiple of 4 and <= 1024");
+  TSR_REQUIRE(npix > 0 && npix < (1ll << 31), "bn_train_stats: bad pixel count");
+  int rpb, nb = red_blocks(npix, rpb), th = red_threads(C);
+  TSR_REQUIRE(ws_bytes >= (size_t)nb * 2 * C * sizeof(float), "bn_train_stats: workspace too small");
+  size_t smem = (size_t)2 * th * sizeof(float4);
+  if (y_bf16)
+    bn_stats_partial_kernel<__nv_bfloat16><<<nb, th, smem, stream>>>((const __nv_bfloat16*)y, y_ld, (int)npix, C, (float*)workspace, rpb);
+  else
+    bn_stats_partial_kernel<float><<<nb, th, smem, stream>>>((const float*)y, y_ld, (int)npix, C, (float*)workspace, rpb);
+  TSR_CHECK_LAUNCH("bn_stats_partial");
+  bn_finalize_kernel<<<tsr_cdiv(C, 128), 128, 0, stream>>>((const float*)workspace, nb, C, (double)npix, gamma, beta,
+                                                           running_mean, running_var, num_batches_tracked, momentum,
+                                                           eps, scale, shift, save_mean, save_invstd);
+  TSR_CHECK_LAUNCH("bn_finalize");
+  return TSR_OK;
+}
+
+int tsr_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, float* scale, float* shift, float* save_mean,
+                       float* save_invstd, cudaStream_t stream) {
+  TSR_REQUIRE(gamma && beta && running_mean && running_var && scale && shift && save_mean && save_invstd, "bn_eval_coeffs: null pointer");
+  bn_eval_coeffs_kernel<<<tsr_cdiv(C, 128), 128, 0, stream>>>(C, gamma, beta, running_mean, running_var, eps, scale, shift, save_mean, save_invstd);
+  TSR_CHECK_LAUNCH("bn_eval_coeffs");
+  return TSR_OK;
+}
+
+#define TSR_DISPATCH2(A_BF16, B_BF16, KERNEL, GRID, BLOCK, SMEM, ...)                                   \
+  do {                                                                                                  \
+    if (A_BF16) {                                                                                       \
+      if (B_BF16) KERNEL<__nv_bfloat16, __nv_bfloat16><<<GRID, BLOCK, SMEM, stream>>>(__VA_ARGS__);     \
+      else KERNEL<__nv_bfloat16, float><<<GRID, BLOCK, SMEM, stream>>>(__VA_ARGS__);                    \
+    } else {                                                                                            \
+      if (B_BF16) KERNEL<float, __nv_bfloat16><<<GRID, BLOCK, SMEM, stream>>>(__VA_ARGS__);             \
+      else KERNEL<float, float><<<GRID, BLOCK, SMEM, stream>>>(__VA_ARGS__);                            \
+    }                                                                                                   \
+  } while (0)
+
+int tsr_bn_apply(const void* y, int y_ld, int y_bf16, const float* scale, const float* shift, void* out, int out_ld,
+                 int out_bf16, long long npix, int C, int relu, cudaStream_t stream) {
+  TSR_REQUIRE(y && scale && shift && out, "bn_apply: null pointer");
+  TSR_REQUIRE(C % 4 == 0 && y_ld % 4 == 0 && out_ld % 4 == 0, "bn_apply: C and strides must be multiples of 4");
+  int grid = ew_grid(npix * (C / 4));
+#define ARGS(Ti, To) (const Ti*)y, y_ld, scale, shift, (To*)out, out_ld, npix, C, relu
+  if (y_bf16) {
+    if (out_bf16) bn_apply_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>(ARGS(__nv_bfloat16, __nv_bfloat16));
+    else bn_apply_kernel<__nv_bfloat16, float><<<grid, 256, 0, stream>>>(ARGS(__nv_bfloat16, float));
+  } else {
+    if (out_bf16) bn_apply_kernel<float, __nv_bfloat16><<<grid, 256, 0, stream>>>(ARGS(float, __nv_bfloat16));
+    else bn_apply_kernel<float, float><<<grid, 256, 0, stream>>>(ARGS(float, float));
+  }
+#undef ARGS
+  TSR_CHECK_LAUNCH("bn_apply");
+  return TSR_OK;
+}
+
+// BatchNorm(+ReLU) backward: da -> dy, dgamma, dbeta.  act_bf16 applies to da, y and dy alike.
+int tsr_bn_backward(const void* da, int da_ld, const void* y, int y_ld, void* dy, int dy_ld, int act_bf16,
+                    const float* scale, const float* shift, const float* save_mean, const float* save_invstd,
+                    float* dgamma, float* dbeta, int accumulate, long long npix, int C, int relu, int training,
+                    void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  TSR_REQUIRE(da && y && dy && scale && shift && save_mean && save_invstd && workspace, "bn_backward: null pointer");
+  TSR_REQUIRE(C % 4 == 0 && C <= 1024 && da_ld % 4 == 0 && y_ld % 4 == 0 && dy_ld % 4 == 0, "bn_backward: C and strides must be multiples of 4");
+  int rpb, nb = red_blocks(npix, rpb), th = red_threads(C);
+  size_t need = (size_t)nb * 2 * C * sizeof(float) + 2 * (size_t)C * sizeof(float);
+  TSR_REQUIRE(ws_bytes >= need, "bn_backward: workspace too small");
+  float* partial = (float*)workspace;
+  float* c1 = partial + (size_t)nb * 2 * C;
+  float* c2 = c1 + C;
+  size_t smem = (size_t)2 * th * sizeof(float4);
+  if (act_bf16)
+    bn_bwd_partial_kernel<__nv_bfloat16, __nv_bfloat16><<<nb, th, smem, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
+  else
+    bn_bwd_partial_kernel<float, float><<<nb, th, smem, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
+  TSR_CHECK_LAUNCH("bn_bwd_partial");
+  bn_bwd_finalize_kernel<<<tsr_cdiv(C, 128), 128, 0, stream>>>(partial, nb, C, (double)npix, dgamma, dbeta, accumulate, c1, c2, training);
+  TSR_CHECK_LAUNCH("bn_bwd_finalize");
+  int grid = ew_grid(npix * (C / 4));
+  if (act_bf16)
+    bn_bwd_apply_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (__nv_bfloat16*)dy, dy_ld, npix, C, relu);
+  else
+    bn_bwd_apply_kernel<float, float, float><<<grid, 256, 0, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (float*)dy, dy_ld, npix, C, relu);
+  TSR_CHECK_LAUNCH("bn_bwd_apply");
+  return TSR_OK;
+}
+
+size_t tsr_bn_backward_workspace(long long npix, int C) {
+  int rpb;
+  return (size_t)red_blocks(npix, rpb) * 2 * C * sizeof(float) + 2 * (size_t)C * sizeof(float);
+}
+
+int tsr_relu_backward(const void* da, int da_ld, const void* a, int a_ld, void* dz, int dz_ld, int act_bf16,
+                      long long npix, int C, cudaStream_t stream) {
+  TSR_REQUIRE(da && a && dz, "relu_backward: null pointer");
+  TSR_REQUIRE(C % 4 == 0 && da_ld % 4 == 0 && a_ld % 4 == 0 && dz_ld % 4 == 0, "relu_backward: C and strides must be multiples of 4");
+  int grid = ew_grid(npix * (C / 4));
+  if (act_bf16)
+    relu_bwd_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)a, a_ld, (__nv_bfloat16*)dz, dz_ld, npix, C);
+  else
+    relu_bwd_kernel<float, float, float><<<grid, 256, 0, stream>>>((const float*)da, da_ld, (const float*)a, a_ld, (float*)dz, dz_ld, npix, C);
+  TSR_CHECK_LAUNCH("relu_backward");
+  return TSR_OK;
+}
+
+int tsr_copy_channels(const void* x, int x_ld, int x_bf16, void* out, int out_ld, int out_bf16, long long npix, int C,
+                      cudaStream_t stream) {
+  TSR_REQUIRE(x && out, "copy_channels: null pointer");
+  TSR_REQUIRE(C % 4 == 0 && x_ld % 4 == 0 && out_ld % 4 == 0, "copy_channels: C and strides must be multiples of 4");
+  int grid = ew_grid(npix * (C / 4));
+  if (x_bf16) {
+    if (out_bf16) copy_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)out, out_ld, npix, C);
+    else copy_kernel<__nv_bfloat16, float><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, x_ld, (float*)out, out_ld, npix, C);
+  } else {
+    if (out_bf16) copy_kernel<float, __nv_bfloat16><<<grid, 256, 0, stream>>>((const float*)x, x_ld, (__nv_bfloat16*)out, out_ld, npix, C);
+    else copy_kernel<float, float><<<grid, 256, 0, stream>>>((const float*)x, x_ld, (float*)out, out_ld, npix, C);
+  }
+  TSR_CHECK_LAUNCH("copy_channels");
+  return TSR_OK;
+}
+
+int tsr_nchw_to_nhwc(const float* x, void* out, int out_ld, int out_bf16, int B, int C, int HW, cudaStream_t stream) {
+  TSR_REQUIRE(x && out, "nchw_to_nhwc: null pointer");
+  int grid = ew_grid((long long)B * C * HW);
+  if (out_bf16) nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, (__nv_bfloat16*)out, out_ld, B, C, HW);
+  else nchw_to_nhwc_kernel<float><<<grid, 256, 0, stream>>>(x, (float*)out, out_ld, B, C, HW);
+  TSR_CHECK_LAUNCH("nchw_to_nhwc");
+  return TSR_OK;
+}
+
+int tsr_nhwc_to_nchw(const void* x, int x_ld, int x_bf16, float* out, int B, int C, int HW, cudaStream_t stream) {
+  TSR_REQUIRE(x && out, "nhwc_to_nchw: null pointer");
+  int grid = ew_grid((long long)B * C * HW);
+  if (x_bf16) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, x_ld, out, B, C, HW);
+  else nhwc_to_nchw_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, x_ld, out, B, C, HW);
+  TSR_CHECK_LAUNCH("nhwc_to_nchw");
+  return TSR_OK;
+}
+
+size_t tsr_mse_hr_workspace(void) { return 1024 * sizeof(float); }
+
+// loss = mean((out - resize(hr_raw / scale_num))^2) -> *loss (device scalar); dout = 2 (out - HR) / N * grad_mul
+int tsr_mse_hr_loss(const float* out, const float* hr_raw, float scale_num, int B, int H, int W, int Hin, int Win,
+                    float* loss, float* dout, float grad_mul, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  TSR_REQUIRE(out && hr_raw && loss && workspace, "mse_hr_loss: null pointer");
+  TSR_REQUIRE(ws_bytes >= 1024 * sizeof(float), "mse_hr_loss: workspace too small");
+  long long N = (long long)B * H * W;
+  int grid = (int)((N + 255) / 256);
+  if (grid > 1024) grid = 1024;
+  mse_hr_kernel<<<grid, 256, 0, stream>>>(out, hr_raw, 1.0f / scale_num, B, H, W, Hin, Win, dout,
+                                          (float)(2.0 / (double)N) * grad_mul, (float*)workspace);
+  TSR_CHECK_LAUNCH("mse_hr");
+  sum_final_kernel<<<1, 32, 0, stream>>>((const float*)workspace, grid, 1.0 / (double)N, loss);
+  TSR_CHECK_LAUNCH("sum_final");
+  return TSR_OK;
+}
+
+int tsr_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, long long step, float grad_scale, cudaStream_t stream) {
+  TSR_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "adam_step: bad argument");
+  if (n == 0) return TSR_OK;
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  int grid = ew_grid((n + 3) / 4);
+  adam_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)(1.0 / bc1),
+                                        (float)(1.0 / sqrt(bc2)), grad_scale);
+  TSR_CHECK_LAUNCH("adam_step");
+  return TSR_OK;
+}
+
+}  // extern "C"

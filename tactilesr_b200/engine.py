@@ -1,0 +1,566 @@
+"""Layer-program executor for the SR conv stacks.
+
+A module's forward is lowered to a short list of ops over NHWC activation buffers; each op's
+``fwd`` / ``bwd`` launches the hand-written CUDA kernels through the C ABI (``_lib``).  The whole
+program is one ``torch.autograd.Function`` node (``_ProgramFn``), so the reference's
+``loss.backward()`` / ``optimizer.step()`` protocol (cpu/trainer.py:346-362) keeps working while
+the forward+backward of reference model/tactileSR_model.py runs entirely in our kernels.
+
+Two numeric modes (``tactilesr_b200.set_precision``):
+  * "fp32": activations fp32, FFMA implicit-GEMM kernels (conv_f32.cu) -- <= 1e-5 parity mode.
+  * "bf16": activations bf16, tcgen05 implicit-GEMM kernels (conv_tc.cu), fp32 accumulate/statistics.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+_PRECISION = "fp32"
+_WEIGHT_EPOCH = 0          # bumped by FusedAdam.step (in-place kernel updates do not bump ._version)
+
+
+def set_precision(mode: str) -> None:
+    global _PRECISION
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def bump_weight_epoch() -> None:
+    global _WEIGHT_EPOCH
+    _WEIGHT_EPOCH += 1
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------
+# symbolic buffers / views
+# ---------------------------------------------------------------------------------------------
+@dataclass(eq=False)
+class Buf:
+    name: str
+    C: int
+    kind: str = "act"       # "act": NHWC activation in the mode dtype; "plane": (B,H,W) fp32 single channel
+
+
+@dataclass(eq=False)
+class View:
+    buf: Buf
+    c0: int
+    C: int
+
+    @staticmethod
+    def of(buf: Buf) -> "View":
+        return View(buf, 0, buf.C)
+
+
+class RunCtx:
+    """Per-call state: concrete tensors of the symbolic buffers, saved statistics, gradients."""
+
+    def __init__(self, mode: str, B: int, H: int, W: int, device, training: bool, need_grad: bool):
+        self.mode, self.B, self.H, self.W = mode, B, H, W
+        self.device, self.training, self.need_grad = device, training, need_grad
+        self.bf16 = 1 if mode == "bf16" else 0
+        self.act_dtype = torch.bfloat16 if self.bf16 else torch.float32
+        self.esize = 2 if self.bf16 else 4
+        self.npix = B * H * W
+        self.bufs: Dict[Buf, torch.Tensor] = {}
+        self.grads: Dict[Buf, torch.Tensor] = {}
+        self.grad_written: Dict[Buf, bool] = {}
+        self.saved: Dict[object, tuple] = {}
+        self.x: Optional[torch.Tensor] = None
+        self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        self._ws: Optional[torch.Tensor] = None
+
+    # -- buffers ------------------------------------------------------------------------------
+    def alloc(self, buf: Buf) -> torch.Tensor:
+        t = self.bufs.get(buf)
+        if t is None:
+            if buf.kind == "plane":
+                t = torch.empty((self.npix,), dtype=torch.float32, device=self.device)
+            else:
+                t = torch.empty((self.npix, buf.C), dtype=self.act_dtype, device=self.device)
+            self.bufs[buf] = t
+        return t
+
+    def vptr(self, v: View, grad: bool = False) -> Tuple[int, int]:
+        t = self.galloc(v.buf) if grad else self.alloc(v.buf)
+        es = 4 if v.buf.kind == "plane" else self.esize
+        return t.data_ptr() + v.c0 * es, v.buf.C
+
+    def galloc(self, buf: Buf) -> torch.Tensor:
+        t = self.grads.get(buf)
+        if t is None:
+            if buf.kind == "plane":
+                t = torch.empty((self.npix,), dtype=torch.float32, device=self.device)
+            else:
+                t = torch.empty((self.npix, buf.C), dtype=self.act_dtype, device=self.device)
+            self.grads[buf] = t
+            self.grad_written[buf] = False
+        return t
+
+    def workspace(self, nbytes: int) -> Tuple[int, int]:
+        nbytes = max(int(nbytes), 256)
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        return self._ws.data_ptr(), self._ws.numel()
+
+    def pgrad(self, p: torch.nn.Parameter) -> Tuple[torch.Tensor, int]:
+        """(gradient tensor for p, accumulate flag).  A parameter used by several ops accumulates."""
+        g = self.param_grads.get(p)
+        if g is None:
+            # FusedAdam exposes a view of its flat gradient buffer; write there directly when autograd will
+            # adopt the tensor as p.grad (p.grad is None), otherwise hand autograd a fresh tensor to accumulate.
+            g = getattr(p, "_tsr_flat_grad", None) if p.grad is None else None
+            if g is None or g.device != p.device:
+                g = torch.empty_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+            self.param_grads[p] = g
+            return g, 0
+        return g, 1
+
+
+# ---------------------------------------------------------------------------------------------
+# packed-weight cache
+# ---------------------------------------------------------------------------------------------
+class _PackCache:
+    def __init__(self):
+        self.store: Dict[Tuple, Tuple[Tuple, torch.Tensor, torch.Tensor]] = {}
+
+    def get(self, w: torch.Tensor, mode: str, need_dgrad: bool):
+        key = (id(w), mode)
+        tag = (w.data_ptr(), w._version, _WEIGHT_EPOCH, tuple(w.shape))
+        hit = self.store.get(key)
+        if hit is not None and hit[0] == tag and (hit[2] is not None or not need_dgrad):
+            return hit[1], hit[2]
+        Cout, Cin, K, _ = w.shape
+        dt = torch.bfloat16 if mode == "bf16" else torch.float32
+        wf = torch.empty((K * K * Cin * Cout,), dtype=dt, device=w.device)
+        wd = torch.empty_like(wf) if need_dgrad else None
+        fn = "tsr_pack_conv_weight_bf16" if mode == "bf16" else "tsr_pack_conv_weight_f32"
+        wc = w.detach().contiguous()
+        _lib.call(fn, wc.data_ptr(), wf.data_ptr(), _ptr(wd), Cout, Cin, K, _lib.stream_ptr())
+        self.store[key] = (tag, wf, wd)
+        return wf, wd
+
+
+_PACK = _PackCache()
+
+
+# ---------------------------------------------------------------------------------------------
+# ops
+# ---------------------------------------------------------------------------------------------
+class Op:
+    def fwd(self, c: RunCtx) -> None:
+        raise NotImplementedError
+
+    def bwd(self, c: RunCtx) -> None:
+        raise NotImplementedError
+
+    def params(self) -> Sequence[torch.nn.Parameter]:
+        return ()
+
+    def reads(self) -> Sequence[Buf]:
+        return ()
+
+    def writes(self) -> Sequence[Buf]:
+        return ()
+
+
+def _first_write(c: RunCtx, buf: Buf) -> bool:
+    """True if this is the first gradient contribution to ``buf`` in the current backward."""
+    c.galloc(buf)
+    first = not c.grad_written[buf]
+    c.grad_written[buf] = True
+    return first
+
+
+class HeadOp(Op):
+    """Upsample(x sf, bilinear) + Conv2d(3 -> 64, 3x3, no bias) [+ ReLU]
+    (reference tactileSR_model.py:35-37, 60-62, 107 + 122)."""
+
+    def __init__(self, ch0: int, weight, out: View, relu: bool, sf: int):
+        self.ch0, self.weight, self.out, self.relu, self.sf = ch0, weight, out, relu, sf
+
+    def params(self):
+        return (self.weight,)
+
+    def writes(self):
+        return (self.out.buf,)
+
+    def _x(self, c: RunCtx):
+        x = c.x
+        return x.data_ptr() + self.ch0 * 16 * 4, x.shape[1] * 16
+
+    def fwd(self, c):
+        xp, xbs = self._x(c)
+        op, old = c.vptr(self.out)
+        _lib.call("tsr_head_fwd", xp, xbs, self.weight.data_ptr(), op, old, c.bf16, c.B, self.sf,
+                  1 if self.relu else 0, _lib.stream_ptr())
+
+    def bwd(self, c):
+        st = _lib.stream_ptr()
+        gp, gld = c.vptr(self.out, grad=True)
+        if self.relu:
+            ap, ald = c.vptr(self.out)
+            _lib.call("tsr_relu_backward", gp, gld, ap, ald, gp, gld, c.bf16, c.npix, self.out.C, st)
+        xp, xbs = self._x(c)
+        g, acc = c.pgrad(self.weight)
+        ws, wsb = c.workspace(_lib.lib().tsr_head_wgrad_workspace(c.B))
+        _lib.call("tsr_head_wgrad", xp, xbs, gp, gld, c.bf16, g.data_ptr(), ws, wsb, c.B, self.sf, acc, st)
+
+
+class ConvOp(Op):
+    """Conv2d(Cin -> Cout, k in {1,3,5}, same padding) with a fused epilogue: + bias, + residual, ReLU
+    (reference tactileSR_model.py:41,47,53,168,174,180,186,191+205-206,219-225)."""
+
+    def __init__(self, src: View, conv: torch.nn.Conv2d, out: View, relu: bool = False,
+                 residual: Optional[View] = None, src_needs_grad: bool = True):
+        self.src, self.conv, self.out, self.relu, self.residual = src, conv, out, relu, residual
+        self.src_needs_grad = src_needs_grad
+        self.K = conv.kernel_size[0]
+        self.Cin, self.Cout = conv.in_channels, conv.out_channels
+        assert src.C == self.Cin and out.C == self.Cout
+        assert conv.stride == (1, 1) and conv.padding == (self.K // 2, self.K // 2) and conv.groups == 1
+
+    def params(self):
+        return (self.conv.weight,) if self.conv.bias is None else (self.conv.weight, self.conv.bias)
+
+    def reads(self):
+        return (self.src.buf,) if self.residual is None else (self.src.buf, self.residual.buf)
+
+    def writes(self):
+        return (self.out.buf,)
+
+    def _conv(self, c: RunCtx, inp, inld, wpk, bias, res, resld, outp, outld, Cin, Cout, flags):
+        st = _lib.stream_ptr()
+        if c.bf16:
+            need = _lib.lib().tsr_conv2d_tc_workspace(c.B, c.H, c.W, Cin, Cout, self.K)
+            ws, wsb = c.workspace(need)
+            _lib.call("tsr_conv2d_tc", inp, inld, wpk, bias, res, resld, outp, outld, c.B, c.H, c.W, Cin, Cout,
+                      self.K, flags, ws, wsb, st)
+        else:
+            _lib.call("tsr_conv2d_f32", inp, inld, wpk, bias, res, resld, outp, outld, c.B, c.H, c.W, Cin, Cout,
+                      self.K, flags, st)
+
+    def fwd(self, c):
+        wf, _ = _PACK.get(self.conv.weight, c.mode, False)
+        ip, ild = c.vptr(self.src)
+        op, old = c.vptr(self.out)
+        rp, rld = c.vptr(self.residual) if self.residual is not None else (0, 0)
+        self._conv(c, ip, ild, wf.data_ptr(), _ptr(self.conv.bias), rp, rld, op, old, self.Cin, self.Cout,
+                   1 if self.relu else 0)
+
+    def bwd(self, c):
+        st = _lib.stream_ptr()
+        gp, gld = c.vptr(self.out, grad=True)
+        if self.relu:
+            ap, ald = c.vptr(self.out)
+            _lib.call("tsr_relu_backward", gp, gld, ap, ald, gp, gld, c.bf16, c.npix, self.Cout, st)
+        # residual branch: d(residual) += dz
+        if self.residual is not None:
+            first = _first_write(c, self.residual.buf)
+            rp, rld = c.vptr(self.residual, grad=True)
+            if first:
+                _lib.call("tsr_copy_channels", gp, gld, c.bf16, rp, rld, c.bf16, c.npix, self.Cout, st)
+            else:
+                raise NotImplementedError("residual gradient accumulation after another writer")
+        # weight / bias gradients
+        ip, ild = c.vptr(self.src)
+        g, acc = c.pgrad(self.conv.weight)
+        if c.bf16:
+            need = _lib.lib().tsr_conv2d_wgrad_tc_workspace(c.B, c.H, c.W, self.Cin, self.Cout, self.K)
+            ws, wsb = c.workspace(need)
+            _lib.call("tsr_conv2d_wgrad_tc", ip, ild, gp, gld, g.data_ptr(), ws, wsb, c.B, c.H, c.W, self.Cin,
+                      self.Cout, self.K, acc, st)
+        else:
+            need = _lib.lib().tsr_conv2d_wgrad_f32_workspace(c.B, c.H, c.W, self.Cin, self.Cout, self.K)
+            ws, wsb = c.workspace(need)
+            _lib.call("tsr_conv2d_wgrad_f32", ip, ild, gp, gld, g.data_ptr(), ws, wsb, c.B, c.H, c.W, self.Cin,
+                      self.Cout, self.K, acc, st)
+        if self.conv.bias is not None:
+            gb, accb = c.pgrad(self.conv.bias)
+            if c.bf16:
+                # bias gradient of a bf16 activation gradient: reduce through the BN-statistics kernel path
+                tmp = c.grads[self.out.buf][:, self.out.c0:self.out.c0 + self.Cout].float().sum(0)
+                gb.copy_(gb + tmp if accb else tmp)
+            else:
+                ws, wsb = c.workspace(_lib.lib().tsr_colsum_workspace(c.npix, self.Cout))
+                _lib.call("tsr_colsum_f32", gp, gld, c.npix, self.Cout, gb.data_ptr(), ws, wsb, accb, st)
+        # data gradient
+        if self.src_needs_grad:
+            _, wd = _PACK.get(self.conv.weight, c.mode, True)
+            first = _first_write(c, self.src.buf)
+            dp, dld = c.vptr(self.src, grad=True)
+            self._conv(c, gp, gld, wd.data_ptr(), 0, 0 if first else dp, 0 if first else dld, dp, dld, self.Cout,
+                       self.Cin, 0)
+
+
+class BNReLUOp(Op):
+    """BatchNorm2d (train: batch statistics + running-stat update; eval: running stats) [+ ReLU]
+    (reference tactileSR_model.py:38-39, 42-43, 48-49, 169-170, 175-176, 181-182, 187-188)."""
+
+    def __init__(self, src: View, bn: torch.nn.BatchNorm2d, out: View, relu: bool = True):
+        self.src, self.bn, self.out, self.relu = src, bn, out, relu
+        assert src.C == bn.num_features == out.C
+
+    def params(self):
+        return (self.bn.weight, self.bn.bias)
+
+    def reads(self):
+        return (self.src.buf,)
+
+    def writes(self):
+        return (self.out.buf,)
+
+    def fwd(self, c):
+        st = _lib.stream_ptr()
+        bn, C = self.bn, self.src.C
+        coef = torch.empty((4, C), dtype=torch.float32, device=c.device)
+        sc, sh, mu, iv = (coef[i].data_ptr() for i in range(4))
+        yp, yld = c.vptr(self.src)
+        use_batch = c.training or bn.running_mean is None
+        if use_batch:
+            ws, wsb = c.workspace(_lib.lib().tsr_bn_workspace(c.npix, C))
+            track = c.training and bn.track_running_stats and bn.running_mean is not None
+            mom = 0.1 if bn.momentum is None else bn.momentum
+            _lib.call("tsr_bn_train_stats", yp, yld, c.bf16, c.npix, C, bn.weight.data_ptr(), bn.bias.data_ptr(),
+                      _ptr(bn.running_mean) if track else 0, _ptr(bn.running_var) if track else 0,
+                      _ptr(bn.num_batches_tracked) if track else 0, mom, bn.eps, sc, sh, mu, iv, ws, wsb, st)
+        else:
+            _lib.call("tsr_bn_eval_coeffs", C, bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                      bn.running_var.data_ptr(), bn.eps, sc, sh, mu, iv, st)
+        op, old = c.vptr(self.out)
+        _lib.call("tsr_bn_apply", yp, yld, c.bf16, sc, sh, op, old, c.bf16, c.npix, C, 1 if self.relu else 0, st)
+        c.saved[self] = (coef, use_batch)
+
+    def bwd(self, c):
+        st = _lib.stream_ptr()
+        C = self.src.C
+        coef, use_batch = c.saved[self]
+        sc, sh, mu, iv = (coef[i].data_ptr() for i in range(4))
+        gp, gld = c.vptr(self.out, grad=True)
+        yp, yld = c.vptr(self.src)
+        first = _first_write(c, self.src.buf)
+        assert first, "BN input has a single consumer"
+        dp, dld = c.vptr(self.src, grad=True)
+        gw, accw = c.pgrad(self.bn.weight)
+        gb, accb = c.pgrad(self.bn.bias)
+        assert accw == accb
+        ws, wsb = c.workspace(_lib.lib().tsr_bn_backward_workspace(c.npix, C))
+        _lib.call("tsr_bn_backward", gp, gld, yp, yld, dp, dld, c.bf16, sc, sh, mu, iv, gw.data_ptr(), gb.data_ptr(),
+                  accw, c.npix, C, 1 if self.relu else 0, 1 if use_batch else 0, ws, wsb, st)
+
+
+class TailOp(Op):
+    """Conv2d(Cin -> 1, 3x3, no bias) + ReLU writing the (B,1,H,W) fp32 result
+    (reference tactileSR_model.py:55-56, 125-126)."""
+
+    def __init__(self, src: View, conv: torch.nn.Conv2d, out: Buf, relu: bool = True):
+        self.src, self.conv, self.out, self.relu = src, conv, out, relu
+        assert conv.out_channels == 1 and conv.kernel_size == (3, 3) and conv.bias is None
+
+    def params(self):
+        return (self.conv.weight,)
+
+    def reads(self):
+        return (self.src.buf,)
+
+    def writes(self):
+        return (self.out,)
+
+    def fwd(self, c):
+        ip, ild = c.vptr(self.src)
+        _lib.call("tsr_tail_fwd", ip, ild, c.bf16, self.conv.weight.data_ptr(), c.alloc(self.out).data_ptr(), c.B, c.H,
+                  c.W, self.src.C, 1 if self.relu else 0, _lib.stream_ptr())
+
+    def bwd(self, c):
+        st = _lib.stream_ptr()
+        dout = c.grads[self.out]
+        out = c.bufs[self.out]
+        ip, ild = c.vptr(self.src)
+        g, acc = c.pgrad(self.conv.weight)
+        ws, wsb = c.workspace(_lib.lib().tsr_tail_wgrad_workspace(c.B, c.H, c.W, self.src.C))
+        _lib.call("tsr_tail_wgrad", ip, ild, c.bf16, dout.data_ptr(), out.data_ptr(), g.data_ptr(), ws, wsb, c.B, c.H,
+                  c.W, self.src.C, 1 if self.relu else 0, acc, st)
+        first = _first_write(c, self.src.buf)
+        assert first
+        dp, dld = c.vptr(self.src, grad=True)
+        _lib.call("tsr_tail_dgrad", dout.data_ptr(), out.data_ptr(), self.conv.weight.data_ptr(), dp, dld, c.bf16, c.B,
+                  c.H, c.W, self.src.C, 1 if self.relu else 0, st)
+
+
+class InputOp(Op):
+    """NCHW fp32 module input -> NHWC activation buffer (standalone MSRB / ResBlock use)."""
+
+    def __init__(self, out: Buf):
+        self.out = out
+
+    def writes(self):
+        return (self.out,)
+
+    def fwd(self, c):
+        x = c.x
+        t = c.alloc(self.out)
+        _lib.call("tsr_nchw_to_nhwc", x.data_ptr(), t.data_ptr(), self.out.C, c.bf16, c.B, self.out.C, c.H * c.W,
+                  _lib.stream_ptr())
+
+    def bwd(self, c):
+        pass
+
+
+# ---------------------------------------------------------------------------------------------
+# program
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class Program:
+    ops: List[Op] = field(default_factory=list)
+    out: Optional[Buf] = None          # result buffer: "plane" (B,1,H,W) or "act" (returned as NCHW fp32)
+    sf: int = 10                       # spatial size = 4*sf for head programs; None => taken from the input
+    input_is_taxel: bool = True
+    wants_input_grad: bool = False
+    in_buf: Optional[Buf] = None
+    taps: Dict[str, View] = field(default_factory=dict)
+
+    def add(self, op: Op) -> Op:
+        self.ops.append(op)
+        return op
+
+    def parameters(self) -> List[torch.nn.Parameter]:
+        seen, out = set(), []
+        for op in self.ops:
+            for p in op.params():
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    out.append(p)
+        return out
+
+
+def _check_device(x: torch.Tensor) -> None:
+    if not x.is_cuda:
+        raise _lib.TsrError("tactilesr_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+
+
+def run_forward(prog: Program, x: torch.Tensor, training: bool, need_grad: bool, mode: Optional[str] = None,
+                keep_taps: bool = False):
+    _check_device(x)
+    mode = mode or _PRECISION
+    x = x.detach().contiguous().float()
+    B = x.shape[0]
+    if prog.input_is_taxel:
+        H = W = x.shape[-1] * prog.sf
+    else:
+        H, W = x.shape[-2], x.shape[-1]
+    c = RunCtx(mode, B, H, W, x.device, training, need_grad)
+    c.x = x
+    keep = need_grad or keep_taps
+    last_use: Dict[Buf, int] = {}
+    if not keep:
+        for i, op in enumerate(prog.ops):
+            for b in op.reads():
+                last_use[b] = i
+    for i, op in enumerate(prog.ops):
+        op.fwd(c)
+        if not keep:
+            for b in op.reads():
+                if last_use.get(b) == i and b is not prog.out:
+                    c.bufs.pop(b, None)
+    if prog.out.kind == "plane":
+        out = c.bufs[prog.out].view(B, 1, H, W)
+    else:
+        out = torch.empty((B, prog.out.C, H, W), dtype=torch.float32, device=x.device)
+        t = c.bufs[prog.out]
+        _lib.call("tsr_nhwc_to_nchw", t.data_ptr(), prog.out.C, c.bf16, out.data_ptr(), B, prog.out.C, H * W,
+                  _lib.stream_ptr())
+    return out, c
+
+
+def run_backward(prog: Program, c: RunCtx, dout: torch.Tensor, hooks=None) -> Dict[torch.nn.Parameter, torch.Tensor]:
+    dout = dout.detach().contiguous().float()
+    if prog.out.kind == "plane":
+        c.grads[prog.out] = dout.view(-1)
+        c.grad_written[prog.out] = True
+    else:
+        g = c.galloc(prog.out)
+        c.grad_written[prog.out] = True
+        _lib.call("tsr_nchw_to_nhwc", dout.data_ptr(), g.data_ptr(), prog.out.C, c.bf16, c.B, prog.out.C, c.H * c.W,
+                  _lib.stream_ptr())
+    # reverse sweep; gradient buffers are dropped as soon as their producer has consumed them
+    for i in range(len(prog.ops) - 1, -1, -1):
+        op = prog.ops[i]
+        needed = [b for b in op.writes()]
+        if any(b not in c.grads for b in needed):
+            continue   # dead branch (no gradient reaches this op)
+        op.bwd(c)
+        if hooks is not None:
+            hooks(i, op, c)
+        for b in needed:
+            if not (prog.wants_input_grad and b is prog.in_buf) and not _written_earlier(prog, i, b):
+                c.grads.pop(b, None)
+    return c.param_grads
+
+
+def _written_earlier(prog: Program, i: int, b: Buf) -> bool:
+    """True if an op before index i also writes (a slice of) buffer b, i.e. its gradient is still needed."""
+    for j in range(i):
+        if b in prog.ops[j].writes():
+            return True
+    return False
+
+
+class _ProgramFn(torch.autograd.Function):
+    """One autograd node for a whole layer program: forward + hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, holder, x, *params):
+        prog: Program = holder["prog"]
+        need_grad = holder["need_grad"]
+        out, c = run_forward(prog, x, holder["training"], need_grad, holder.get("mode"))
+        if need_grad:
+            ctx.prog, ctx.c, ctx.params, ctx.holder = prog, c, params, holder
+        holder["ctx"] = c
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        prog, c = ctx.prog, ctx.c
+        if c is None:
+            raise RuntimeError("tactilesr_b200: backward through the same forward twice is not supported")
+        hooks = ctx.holder.get("grad_hook")
+        pg = run_backward(prog, c, dout, hooks)
+        grads = []
+        for p in ctx.params:
+            g = pg.get(p)
+            grads.append(g if (g is not None and p.requires_grad) else None)
+        gx = None
+        if prog.wants_input_grad and ctx.needs_input_grad[1]:
+            gb = c.grads.get(prog.in_buf)
+            if gb is not None:
+                gx = torch.empty((c.B, prog.in_buf.C, c.H, c.W), dtype=torch.float32, device=c.device)
+                _lib.call("tsr_nhwc_to_nchw", gb.data_ptr(), prog.in_buf.C, c.bf16, gx.data_ptr(), c.B, prog.in_buf.C,
+                          c.H * c.W, _lib.stream_ptr())
+        fin = ctx.holder.get("grad_done")
+        if fin is not None:
+            fin(pg)
+        ctx.c = None   # release activations
+        return (None, gx, *grads)
+
+
+def apply_program(prog: Program, x: torch.Tensor, training: bool, mode: Optional[str] = None,
+                  extra: Optional[dict] = None) -> torch.Tensor:
+    params = prog.parameters()
+    need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or
+                                             (prog.wants_input_grad and x.requires_grad))
+    holder = {"prog": prog, "training": training, "need_grad": need_grad, "mode": mode}
+    if extra:
+        holder.update(extra)
+    return _ProgramFn.apply(holder, x, *params)

@@ -1,0 +1,119 @@
+"""Drop-in tPSFNet: same class, constructor, attributes and ``state_dict`` (``MLP_layer.{1,3,5,7}``) as
+reference ``model/tPSFNet.py:13-141``; ``forward`` runs the MLP and the fused per-sample PSF kernels
+(csrc/mlp.cu, csrc/psf.cu) instead of the python ``for i in range(B)`` loop (:118-125).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+_ACT = {"none": 0, "relu": 1, "softplus": 2}
+
+
+def _distance_table(h: int, w: int, cy: float, cx: float) -> torch.Tensor:
+    # reference `_sdf` (:67-76): Euclidean distance of (row, col) to the centre, evaluated in double
+    r = torch.arange(h, dtype=torch.float64)[:, None] - cy
+    c = torch.arange(w, dtype=torch.float64)[None, :] - cx
+    return torch.sqrt(r * r + c * c).to(torch.float32)
+
+
+class _PSFFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, depth, w1, b1, w2, b2, w3, b3, w4, b4):
+        if not x.is_cuda:
+            raise _lib.TsrError("tactilesr_b200.tPSFNet runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+        st = _lib.stream_ptr()
+        B = x.shape[0]
+        x2 = x.detach().reshape(B, -1).contiguous().float()
+        d = depth.detach().reshape(B, 100, 100).contiguous().float()
+        dev = x.device
+        ws = [w.detach().contiguous() for w in (w1, w2, w3, w4)]
+        bs = [b.detach().contiguous() for b in (b1, b2, b3, b4)]
+        acts = [x2]
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            y = torch.empty((B, w.shape[0]), dtype=torch.float32, device=dev)
+            _lib.call("tsr_linear_fwd", acts[-1].data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), B, w.shape[0],
+                      w.shape[1], _ACT["softplus"] if i == 3 else _ACT["relu"], st)
+            acts.append(y)
+        ab = acts[-1]
+        HR = torch.empty((B, 1, 100, 100), dtype=torch.float32, device=dev)
+        LRd = torch.empty((B, 1, 4, 4), dtype=torch.float32, device=dev)
+        psf = torch.empty((B, 1, 99, 99), dtype=torch.float32, device=dev)
+        _lib.call("tsr_psf_forward", ab.data_ptr(), d.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), B, st)
+        ctx.save_for_backward(d, HR, *acts, *ws)
+        return HR, LRd, psf, ab.view(B, 1, 3).clone()
+
+    @staticmethod
+    def backward(ctx, dHR, dLRd, dpsf, dab_direct):
+        st = _lib.stream_ptr()
+        saved = ctx.saved_tensors
+        d, HR = saved[0], saved[1]
+        acts, ws = list(saved[2:7]), list(saved[7:11])
+        B = d.shape[0]
+        dev = d.device
+        ab = acts[-1]
+
+        def prep(g):
+            return None if g is None else g.detach().contiguous().float()
+        dHR, dLRd, dpsf, dab_direct = prep(dHR), prep(dLRd), prep(dpsf), prep(dab_direct)
+        dab = torch.empty((B, 3), dtype=torch.float32, device=dev)
+        _lib.call("tsr_psf_backward", ab.data_ptr(), d.data_ptr(), HR.data_ptr(),
+                  0 if dLRd is None else dLRd.data_ptr(), 0 if dHR is None else dHR.data_ptr(),
+                  0 if dpsf is None else dpsf.data_ptr(), dab.data_ptr(), B, st)
+        if dab_direct is not None:
+            dab = dab + dab_direct.view(B, 3)
+        grads = []
+        dy = dab
+        for i in (3, 2, 1, 0):
+            w = ws[i]
+            N, K = w.shape
+            dpre = torch.empty((B, N), dtype=torch.float32, device=dev)
+            dw = torch.empty_like(w)
+            db = torch.empty((N,), dtype=torch.float32, device=dev)
+            dx = torch.empty((B, K), dtype=torch.float32, device=dev) if i > 0 else None
+            _lib.call("tsr_linear_bwd", dy.data_ptr(), acts[i + 1].data_ptr(), acts[i].data_ptr(), w.data_ptr(),
+                      dpre.data_ptr(), dw.data_ptr(), db.data_ptr(), 0 if dx is None else dx.data_ptr(), B, N, K,
+                      _ACT["softplus"] if i == 3 else _ACT["relu"], 0, st)
+            grads = [dw, db] + grads
+            dy = dx
+        return (None, None, *grads)
+
+
+class tPSFNet(nn.Module):
+    def __init__(self, gama, perception_scale, size=(100, 100), device=None):
+        super().__init__()
+        self.gama = gama
+        self.perception_scale = perception_scale
+        # reference :21-23 stores the argument as given (None stays None)
+        self.device = device
+
+        self.MLP_layer = nn.Sequential(
+            nn.Flatten(),
+            nn.Linear(16 * 3, 256), nn.ReLU(),
+            nn.Linear(256, 1024), nn.ReLU(),
+            nn.Linear(1024, 256), nn.ReLU(),
+            nn.Linear(256, 3), nn.Softplus())
+        self._init_weights(self.MLP_layer)
+        self.zeroPad_func = nn.ZeroPad2d(padding=(48, 48, 48, 48))
+
+        # constant distance fields (reference :41-55): plain attributes, not buffers, not in state_dict.
+        sdf = _distance_table(99, 99, 49, 49)
+        sdf = 10 * (sdf - sdf.min()) / (sdf.max() - sdf.min())
+        self.PSF_sdf = sdf[None, None].to(device) if device is not None else sdf[None, None]
+        m = torch.stack([torch.stack([_distance_table(100, 100, 12 + 25 * i, 12 + 25 * j) for j in range(4)])
+                         for i in range(4)])
+        m = 10 * (m - m.min()) / (m.max() - m.min())
+        self.LR_masking_sdf = m.to(device) if device is not None else m
+
+    def _init_weights(self, modules):
+        for m in modules:
+            if isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, mean=0, std=0.03)
+
+    def forward(self, x, depth):
+        assert x.shape[0] == depth.shape[0], "Batch size of LR tactile and depth should be the same!"
+        L = self.MLP_layer
+        return _PSFFn.apply(x, depth, L[1].weight, L[1].bias, L[3].weight, L[3].bias, L[5].weight, L[5].bias,
+                            L[7].weight, L[7].bias)

@@ -1,0 +1,247 @@
+"""Drop-in SR networks: same classes, constructor arguments, attribute names, parameter registration
+order and ``state_dict`` layout as reference ``model/tactileSR_model.py`` (TactileSR :18-98,
+TactileSRCNN :101-153, MSRB :157-214, ResBlock :216-225, Leaky_Res_Block :227-241) -- the stock
+``nn.Conv2d`` / ``nn.BatchNorm2d`` objects are kept purely as parameter holders (so RNG order at
+construction and checkpoint keys are identical by construction), while ``forward`` lowers the module to a
+layer program executed by hand-written sm_100a kernels (``tactilesr_b200.engine``).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import engine as E
+
+
+def _kaiming_and_bn_init(root: nn.Module) -> None:
+    # reference `_init_network` (tactileSR_model.py:92-98, 130-136, 208-214)
+    for m in root.modules():
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        elif isinstance(m, nn.BatchNorm2d):
+            nn.init.constant_(m.weight, 0.1)
+            nn.init.constant_(m.bias, 0.1)
+
+
+def _conv_bn_relu(cin: int, cout: int, k: int) -> nn.Sequential:
+    return nn.Sequential(nn.Conv2d(cin, cout, k, padding=k // 2), nn.BatchNorm2d(cout), nn.ReLU(True))
+
+
+def _stack(block, count: int) -> nn.Sequential:
+    return nn.Sequential(*[block() for _ in range(count)])
+
+
+class _ProgramModule(nn.Module):
+    """Mixin: run a layer program on CUDA inputs."""
+
+    precision = None   # None -> global tactilesr_b200.get_precision()
+
+    def _run(self, prog: E.Program, x: torch.Tensor) -> torch.Tensor:
+        return E.apply_program(prog, x, self.training, self.precision, getattr(self, "_engine_extra", None))
+
+
+class MSRB(_ProgramModule):
+    """Multi-scale residual block (reference :157-214)."""
+
+    def __init__(self, n_feats=64):
+        super().__init__()
+        self.conv_3_1 = _conv_bn_relu(n_feats, n_feats, 3)
+        self.conv_5_1 = _conv_bn_relu(n_feats, n_feats, 5)
+        self.conv_3_2 = _conv_bn_relu(n_feats * 2, n_feats * 2, 3)
+        self.conv_5_2 = _conv_bn_relu(n_feats * 2, n_feats * 2, 5)
+        self.confusion = nn.Conv2d(n_feats * 4, n_feats, 1, padding=0, stride=1)
+        self.relu = nn.ReLU(inplace=True)
+        _kaiming_and_bn_init(self)
+
+    def _emit(self, prog: E.Program, x: E.View, out: E.View, tag: str) -> None:
+        n = self.confusion.out_channels
+        i2 = E.Buf(tag + ".i2", 2 * n)
+        i3 = E.Buf(tag + ".i3", 4 * n)
+        for seq, src, dst in ((self.conv_3_1, x, E.View(i2, 0, n)), (self.conv_5_1, x, E.View(i2, n, n)),
+                              (self.conv_3_2, E.View.of(i2), E.View(i3, 0, 2 * n)),
+                              (self.conv_5_2, E.View.of(i2), E.View(i3, 2 * n, 2 * n))):
+            y = E.Buf(f"{tag}.y{dst.c0}_{dst.C}_{seq[0].kernel_size[0]}", dst.C)
+            prog.add(E.ConvOp(src, seq[0], E.View.of(y)))
+            prog.add(E.BNReLUOp(E.View.of(y), seq[1], dst, relu=True))
+        prog.add(E.ConvOp(E.View.of(i3), self.confusion, out, relu=True, residual=x))
+
+    def forward(self, x):
+        n = self.confusion.out_channels
+        prog = E.Program(input_is_taxel=False, wants_input_grad=True)
+        xin, out = E.Buf("x", n), E.Buf("out", n)
+        prog.in_buf, prog.out = xin, out
+        prog.add(E.InputOp(xin))
+        self._emit(prog, E.View.of(xin), E.View.of(out), "msrb")
+        return self._run(prog, x)
+
+
+class ResBlock(_ProgramModule):
+    """relu(x + conv2(relu(conv1(x)))) (reference :216-225)."""
+
+    def __init__(self, n_feats=64):
+        super().__init__()
+        self.conv1 = nn.Conv2d(n_feats, n_feats, kernel_size=3, padding=1)
+        self.conv2 = nn.Conv2d(n_feats, n_feats, kernel_size=3, padding=1)
+
+    def _emit(self, prog: E.Program, x: E.View, out: E.View, tag: str) -> None:
+        y = E.Buf(tag + ".y", self.conv1.out_channels)
+        prog.add(E.ConvOp(x, self.conv1, E.View.of(y), relu=True))
+        prog.add(E.ConvOp(E.View.of(y), self.conv2, out, relu=True, residual=x))
+
+    def forward(self, x):
+        n = self.conv1.in_channels
+        prog = E.Program(input_is_taxel=False, wants_input_grad=True)
+        xin, out = E.Buf("x", n), E.Buf("out", n)
+        prog.in_buf, prog.out = xin, out
+        prog.add(E.InputOp(xin))
+        self._emit(prog, E.View.of(xin), E.View.of(out), "res")
+        return self._run(prog, x)
+
+
+class Leaky_Res_Block(nn.Module):
+    """Unused by every entry point of the reference (:227-241); kept as a stock-PyTorch class so that
+    imports keep working.  Not part of the accelerated hot path."""
+
+    def __init__(self, in_channel=64, out_channel=64, strides=1):
+        super().__init__()
+        self.block = nn.Sequential(
+            nn.Conv2d(in_channel, out_channel, kernel_size=3, stride=strides, padding=1, bias=False),
+            nn.BatchNorm2d(out_channel),
+            nn.LeakyReLU(1, inplace=True),
+            nn.Conv2d(out_channel, out_channel, kernel_size=3, padding=1, bias=False),
+            nn.BatchNorm2d(out_channel),
+        )
+        self.relu = nn.LeakyReLU(0.2, inplace=True)
+
+    def forward(self, x):
+        return self.relu(self.block(x) + x)
+
+
+def _emit_stack(prog: E.Program, stack: nn.Sequential, x: E.View, out: E.View, tag: str) -> None:
+    """A Sequential of MSRB / ResBlock modules (``patternFeatureExtra_layer`` / ``forceFeatureExtra_layer``;
+    re-read on every forward because tactileSRSeqs_train.py:56-57 re-assigns them)."""
+    blocks = list(stack)
+    if not blocks:
+        raise ValueError("empty feature-extraction stack")
+    cur = x
+    for i, blk in enumerate(blocks):
+        if not hasattr(blk, "_emit"):
+            raise TypeError(f"{type(blk).__name__} is not a tactilesr_b200 block")
+        dst = out if i == len(blocks) - 1 else E.View.of(E.Buf(f"{tag}.{i}", x.C))
+        blk._emit(prog, cur, dst, f"{tag}.{i}")
+        prog.taps[f"{tag}{i}"] = dst
+        cur = dst
+
+
+class TactileSR(_ProgramModule):
+    """STSR / MTSR (ToH 2024) network, reference :18-98."""
+
+    def __init__(self, scale_factor=10, seqsCnt=1, axisCnt=3, patternFeatureExtraLayerCnt=6, forceFeatureExtraLayerCnt=1):
+        super().__init__()
+        self.taxel_cnt = 4
+        self.scale_factor = scale_factor
+        self.seqsCnt = seqsCnt
+        self.axisCnt = axisCnt
+
+        self.patternFeatureExtra_layer = self.make_layer(MSRB, patternFeatureExtraLayerCnt)
+        self.forceFeatureExtra_layer = self.make_layer(ResBlock, forceFeatureExtraLayerCnt)
+        self.inputLayer_pattern_list = nn.ModuleList()
+        for _ in range(seqsCnt):
+            self.inputLayer_pattern_list.append(nn.Sequential(
+                nn.Upsample(scale_factor=scale_factor, mode="bilinear", align_corners=False),
+                nn.Conv2d(axisCnt, 64, kernel_size=3, stride=1, padding=1, bias=False), nn.BatchNorm2d(64), nn.ReLU(True),
+                nn.Conv2d(64, 64, kernel_size=3, stride=1, padding=1, bias=False), nn.BatchNorm2d(64), nn.ReLU(True)))
+        self.inputContact_layer = nn.Sequential(
+            nn.Conv2d(seqsCnt * 64, 64, kernel_size=3, stride=1, padding=1, bias=False), nn.BatchNorm2d(64), nn.ReLU(True))
+        self.output_layer = nn.Sequential(
+            nn.Conv2d(128, 128, kernel_size=3, stride=1, padding=1, bias=False), nn.ReLU(True),
+            nn.Conv2d(128, 1, kernel_size=3, stride=1, padding=1, bias=False), nn.ReLU(True))
+        self.input_layer_force = nn.Sequential(
+            nn.Upsample(scale_factor=scale_factor, mode="bilinear", align_corners=False),
+            nn.Conv2d(axisCnt, 64, kernel_size=3, stride=1, padding=1, bias=False), nn.ReLU(True))
+        self._init_network()
+
+    def make_layer(self, block, num_of_layer):
+        return _stack(block, num_of_layer)
+
+    def _init_network(self):
+        _kaiming_and_bn_init(self)
+
+    def _program(self) -> E.Program:
+        if self.axisCnt != 3:
+            raise NotImplementedError("tactilesr_b200 head kernel is specialised for axisCnt == 3")
+        sf = int(self.scale_factor)
+        S = self.seqsCnt
+        prog = E.Program(sf=sf, input_is_taxel=True)
+        frames = E.Buf("frames", 64 * S)
+        for s in range(S):
+            seq = self.inputLayer_pattern_list[s]
+            y1, a1, y2 = E.Buf(f"head{s}.y1", 64), E.Buf(f"head{s}.a1", 64), E.Buf(f"head{s}.y2", 64)
+            prog.add(E.HeadOp(3 * s, seq[1].weight, E.View.of(y1), relu=False, sf=sf))
+            prog.add(E.BNReLUOp(E.View.of(y1), seq[2], E.View.of(a1)))
+            prog.add(E.ConvOp(E.View.of(a1), seq[4], E.View.of(y2)))
+            prog.add(E.BNReLUOp(E.View.of(y2), seq[5], E.View(frames, 64 * s, 64)))
+        yc, contact = E.Buf("contact.y", 64), E.Buf("contact", 64)
+        prog.add(E.ConvOp(E.View.of(frames), self.inputContact_layer[0], E.View.of(yc)))
+        prog.add(E.BNReLUOp(E.View.of(yc), self.inputContact_layer[1], E.View.of(contact)))
+        prog.taps["inputContact"] = E.View.of(contact)
+        fused = E.Buf("fused", 128)                        # cat(force, pattern) (reference :81)
+        _emit_stack(prog, self.patternFeatureExtra_layer, E.View.of(contact), E.View(fused, 64, 64), "msrb")
+        f0 = E.Buf("force.in", 64)
+        prog.add(E.HeadOp(0, self.input_layer_force[1].weight, E.View.of(f0), relu=True, sf=sf))
+        _emit_stack(prog, self.forceFeatureExtra_layer, E.View.of(f0), E.View(fused, 0, 64), "res")
+        prog.taps["force"] = E.View(fused, 0, 64)
+        o0, out = E.Buf("out0", 128), E.Buf("sr", 1, kind="plane")
+        prog.add(E.ConvOp(E.View.of(fused), self.output_layer[0], E.View.of(o0), relu=True))
+        prog.taps["output0"] = E.View.of(o0)
+        prog.add(E.TailOp(E.View.of(o0), self.output_layer[2], out, relu=True))
+        prog.out = out
+        return prog
+
+    def forward(self, x):
+        assert x.shape[1] == self.seqsCnt * self.axisCnt, "input channel should be same with seqsCnt x axisCnt!"
+        # the reference's trailing F.interpolate(size=(4*sf, 4*sf)) (:83) maps 4*sf -> 4*sf: identity, elided.
+        return self._run(self._program(), x)
+
+
+class TactileSRCNN(_ProgramModule):
+    """TactileSRCNN / TactileSRGAN generator (IROS 2022), reference :101-153."""
+
+    def __init__(self):
+        super().__init__()
+        self.msrb_layer = self._make_layer(MSRB, 6)
+        self.input_zyx = nn.Sequential(
+            nn.Conv2d(3, 64, kernel_size=3, stride=1, padding=1, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+            nn.Conv2d(64, 64, kernel_size=3, stride=1, padding=1, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+            nn.Conv2d(64, 64, kernel_size=3, stride=1, padding=1, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True))
+        self.upSample = nn.Upsample(scale_factor=10, mode="bilinear", align_corners=False)
+        self.output = nn.Sequential(nn.Conv2d(64, 1, kernel_size=3, stride=1, padding=1, bias=False), nn.ReLU(inplace=True))
+        self._init_network()
+
+    def _init_network(self):
+        _kaiming_and_bn_init(self)
+
+    def _make_layer(self, block, num_of_layer):
+        return _stack(block, num_of_layer)
+
+    def _program(self) -> E.Program:
+        prog = E.Program(sf=10, input_is_taxel=True)
+        z = self.input_zyx
+        y = E.Buf("in.y0", 64)
+        prog.add(E.HeadOp(0, z[0].weight, E.View.of(y), relu=False, sf=10))
+        a = E.Buf("in.a0", 64)
+        prog.add(E.BNReLUOp(E.View.of(y), z[1], E.View.of(a)))
+        for j in (3, 6):
+            y, a2 = E.Buf(f"in.y{j}", 64), E.Buf(f"in.a{j}", 64)
+            prog.add(E.ConvOp(E.View.of(a), z[j], E.View.of(y)))
+            prog.add(E.BNReLUOp(E.View.of(y), z[j + 1], E.View.of(a2)))
+            a = a2
+        feat = E.Buf("feat", 64)
+        _emit_stack(prog, self.msrb_layer, E.View.of(a), E.View.of(feat), "msrb")
+        out = E.Buf("sr", 1, kind="plane")
+        prog.add(E.TailOp(E.View.of(feat), self.output[0], out, relu=True))
+        prog.out = out
+        return prog
+
+    def forward(self, x):
+        return self._run(self._program(), x)

@@ -1,0 +1,209 @@
+"""GPU parity of the SR path (fp32 mode) against the golden vectors minted from the unmodified reference
+and against the CPU oracle.  Tolerances (rel-L2 unless noted):
+  outputs / taps / BN stats : 2e-5 vs the fp64 reference (the reference's own fp32 noise is 1-3e-6; north_star 1e-5
+                              is checked on the final output against the fp32 reference)
+  parameter gradients       : 2e-3 on the summary vs fp64 (reference fp32-vs-fp64 itself: up to 4e-4, ReLU flips)
+  zero-gradient conv biases : absolute 1e-6
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import load_golden, rel_l2, summarize, summary_close, sr_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(S, seed_w, cls=None):
+    from oracle import tactilesr_oracle as so
+    from tactilesr_b200.model import TactileSR
+    m = TactileSR(seqsCnt=S)
+    m.load_state_dict(so.make_state(so.tactilesr_layout(S), seed_w), strict=True)
+    return m.cuda()
+
+
+def _tap(c, view):
+    t = c.bufs[view.buf][:, view.c0:view.c0 + view.C].float()
+    return t.view(c.B, c.H, c.W, view.C).permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("S", [1, 7])
+def test_sr_train_forward_backward_matches_reference(S):
+    import tactilesr_b200 as tb
+    from tactilesr_b200 import engine as E
+    tb.set_precision("fp32")
+    g = load_golden(f"tactilesr_fwdbwd_s{S}.npz")
+    m = _model(S, int(g["seed_w"])).train()
+    LR, HR_raw = sr_inputs(int(g["B"]), S, int(g["seed_x"]))
+    LR, HR_raw = LR.cuda(), HR_raw.cuda()
+    # taps through the engine (no autograd), on a copy so BN running stats are not advanced twice
+    import copy
+    m2 = copy.deepcopy(m)
+    prog = m2._program()
+    out_t, c = E.run_forward(prog, LR, True, False, "fp32", keep_taps=True)
+    names = {"inputContact": "inputContact", "force": "force", "output0": "output0"}
+    names.update({f"msrb{i}": f"msrb{i}" for i in range(6)})
+    for k, gk in names.items():
+        ok, err = summary_close(summarize(_tap(c, prog.taps[k])), g[f"f64/tap/{gk}"], 2e-5)
+        assert ok, (k, err)
+    # public API: forward + fused loss + backward
+    from tactilesr_b200.functional import mse_hr_loss
+    out = m(LR)
+    assert out.shape == (int(g["B"]), 1, 40, 40)
+    assert rel_l2(out, g["f64/out"]) < 2e-5
+    assert rel_l2(out, g["f32/out"]) < 1e-5
+    loss = mse_hr_loss(out, HR_raw, 10.0)
+    assert abs(loss.item() - float(g["f64/loss"])) / float(g["f64/loss"]) < 1e-5
+    loss.backward()
+    worst = 0.0
+    assert [n for n, _ in m.named_parameters()] == [str(x) for x in g["param_names"]]
+    for (n, p), want in zip(m.named_parameters(), g["f64/grad_summary"]):
+        got = summarize(p.grad)
+        if ".0.bias" in n and ("conv_3_" in n or "conv_5_" in n):
+            assert got[0] < 1e-6, (n, got[0])      # true gradient is exactly 0 (bias before train-mode BN)
+            continue
+        ok, err = summary_close(got, want, 2e-3)
+        assert ok, (n, err)
+        worst = max(worst, max(err))
+    print("worst grad summary error", worst)
+    sd = m.state_dict()
+    for n, want in zip([str(x) for x in g["bn_names"]], g["f64/bn_summary"]):
+        ok, err = summary_close(summarize(sd[n]), want, 2e-5)
+        assert ok, (n, err)
+    for k, v in sd.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == 1, k
+
+
+@pytest.mark.parametrize("S", [1, 7])
+def test_sr_eval_forward_matches_reference(S):
+    import tactilesr_b200 as tb
+    tb.set_precision("fp32")
+    g = load_golden(f"tactilesr_fwdbwd_s{S}.npz")
+    m = _model(S, int(g["seed_w"])).eval()
+    LR, _ = sr_inputs(int(g["B"]), S, int(g["seed_x"]))
+    with torch.no_grad():
+        out = m(LR.cuda())
+    assert rel_l2(out, g["f64/out_eval"]) < 2e-5
+    assert rel_l2(out, g["f32/out_eval"]) < 1e-5
+    assert (out > 0).float().mean() > 0.2
+
+
+def test_sr_matches_cpu_oracle_on_fresh_inputs():
+    """Same seeded weights / inputs through the CUDA path and the CPU oracle (fp64), ragged batch of 3."""
+    import tactilesr_b200 as tb
+    from oracle import tactilesr_oracle as so
+    from tactilesr_b200.functional import mse_hr_loss
+    tb.set_precision("fp32")
+    S, B = 1, 3
+    sd = so.make_state(so.tactilesr_layout(S), 77)
+    LR, HR_raw = sr_inputs(B, S, 78)
+    loss_o, out_o, grads_o, stats_o = so.loss_and_grads({k: v.double() if v.is_floating_point() else v for k, v in sd.items()},
+                                                        LR.double(), HR_raw.double(), True)
+    m = _model(S, 77).train()
+    out = m(LR.cuda())
+    loss = mse_hr_loss(out, HR_raw.cuda(), 10.0)
+    loss.backward()
+    assert rel_l2(out, out_o) < 2e-5
+    assert abs(loss.item() - float(loss_o)) / float(loss_o) < 1e-5
+    for n, p in m.named_parameters():
+        go = grads_o[n]
+        if go.norm() < 1e-9:
+            assert p.grad.norm().item() < 1e-6
+        else:
+            assert rel_l2(p.grad, go) < 2e-3, n
+
+
+def test_adam_three_steps_match_stock_adam():
+    import tactilesr_b200 as tb
+    from tactilesr_b200.functional import mse_hr_loss
+    from tactilesr_b200.optim import FusedAdam
+    tb.set_precision("fp32")
+    g = load_golden("tactilesr_adam_s1.npz")
+    m = _model(1, int(g["seed_w"])).train()
+    opt = FusedAdam(m.parameters(), lr=1e-3, weight_decay=1e-2)
+    losses = []
+    for t in range(int(g["steps"])):
+        LR, HR_raw = sr_inputs(int(g["B"]), 1, int(g["seed_x0"]) + t)
+        loss = mse_hr_loss(m(LR.cuda()), HR_raw.cuda(), 10.0)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    np.testing.assert_allclose(losses, g["f64/losses"], rtol=2e-4)
+    sd = m.state_dict()
+    for n, want in zip([str(x) for x in g["state_names"]], g["f64/state_summary"]):
+        got = summarize(sd[n])
+        k = min(len(got), len(want))
+        if n.endswith("num_batches_tracked"):
+            assert got[1] == want[1]
+            continue
+        # Adam's first steps move every weight by ~lr regardless of gradient scale: compare absolutely to lr
+        assert np.abs(got[3:k] - want[3:k]).max() < 2e-4, (n, np.abs(got[3:k] - want[3:k]).max())
+        assert abs(got[0] - want[0]) / max(want[0], 1e-12) < 1e-3, n
+    osd = opt.state_dict()
+    assert set(osd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    assert float(osd["state"][0]["step"]) == 3.0
+    ref_keys = set(torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))]).state_dict()["param_groups"][0].keys())
+    assert set(osd["param_groups"][0].keys()) == ref_keys
+
+
+def test_srcnn_forward_matches_reference():
+    import tactilesr_b200 as tb
+    from oracle import tactilesr_oracle as so
+    from tactilesr_b200.model import TactileSRCNN
+    tb.set_precision("fp32")
+    g = load_golden("tactilesrcnn_fwd.npz")
+    m = TactileSRCNN()
+    sd0 = so.make_state(so.tactilesrcnn_layout(), int(g["seed_w"]))
+    m.load_state_dict(sd0, strict=True)
+    m = m.cuda()
+    LR, _ = sr_inputs(int(g["B"]), 1, int(g["seed_x"]))
+    m.eval()
+    with torch.no_grad():
+        assert rel_l2(m(LR.cuda()), g["f64/out_eval"]) < 2e-5
+    m.train()
+    with torch.no_grad():
+        assert rel_l2(m(LR.cuda()), g["f64/out_train"]) < 2e-5
+
+
+def test_standalone_blocks_match_torch_reference():
+    """MSRB / ResBlock used on their own (NCHW in/out, gradient to the input) against the same stock layers
+    evaluated by PyTorch on the CPU in fp64."""
+    import copy
+    import tactilesr_b200 as tb
+    from tactilesr_b200.model import MSRB, ResBlock
+    tb.set_precision("fp32")
+    torch.manual_seed(5)
+    for blk in (MSRB(), ResBlock()):
+        for mod in blk.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                torch.nn.init.uniform_(mod.weight, 0.5, 1.5)
+        x = torch.randn(2, 64, 40, 40)
+        ref = copy.deepcopy(blk).double()
+        xr = x.double().requires_grad_(True)
+        if isinstance(blk, MSRB):
+            i2 = torch.cat([ref.conv_3_1(xr), ref.conv_5_1(xr)], 1)
+            i3 = torch.cat([ref.conv_3_2(i2), ref.conv_5_2(i2)], 1)
+            yr = torch.relu(ref.confusion(i3) + xr)
+        else:
+            yr = torch.relu(xr + ref.conv2(torch.relu(ref.conv1(xr))))
+        w = torch.randn_like(yr)
+        (yr * w).sum().backward()
+        blk = blk.cuda()
+        xg = x.cuda().requires_grad_(True)
+        y = blk(xg)
+        (y * w.float().cuda()).sum().backward()
+        assert rel_l2(y, yr) < 2e-5
+        assert rel_l2(xg.grad, xr.grad) < 1e-4
+        for (n, p), (_, pr) in zip(blk.named_parameters(), ref.named_parameters()):
+            if pr.grad.norm() < 1e-9:
+                continue
+            assert rel_l2(p.grad, pr.grad) < 1e-3, n
+
+
+def test_cpu_input_is_rejected():
+    from tactilesr_b200.model import TactileSR
+    from tactilesr_b200 import TsrError
+    with pytest.raises(TsrError):
+        TactileSR()(torch.zeros(1, 3, 4, 4))

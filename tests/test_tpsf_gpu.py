@@ -1,0 +1,96 @@
+"""GPU parity of the tPSFNet path against the golden vectors from the unmodified reference and the CPU oracle.
+Tolerances: outputs 2e-5 rel-L2 vs fp64 (reference fp32 noise 4e-7); gradients 1e-3 on the l2 norm and rel-L2."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import load_golden, rel_l2, summarize
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(g):
+    from oracle import tpsf_oracle as po
+    from tactilesr_b200.model import tPSFNet
+    m = tPSFNet(gama=1.4, perception_scale=None, device="cuda")
+    m.load_state_dict(po.make_state(int(g["seed_w"])), strict=True)
+    m = m.cuda()
+    LR_raw = torch.from_numpy(g["LR_raw"])
+    depth = po.synthetic_depth(int(g["B"]), int(g["seed_x"]) + 1)
+    return m, LR_raw, depth
+
+
+def test_tpsf_forward_backward_matches_reference():
+    g = load_golden("tpsf_fwdbwd.npz")
+    m, LR_raw, depth = _setup(g)
+    LR = LR_raw.cuda() / 100
+    HR, LRd, psf, ab = m(LR, depth.cuda().unsqueeze(1))
+    assert HR.shape == (4, 1, 100, 100) and LRd.shape == (4, 1, 4, 4) and psf.shape == (4, 1, 99, 99) and ab.shape == (4, 1, 3)
+    assert rel_l2(ab, g["f64/alphaBeta"]) < 2e-6
+    assert rel_l2(HR, g["f64/HR"]) < 2e-5
+    assert rel_l2(LRd, g["f64/LRd"]) < 2e-5
+    assert rel_l2(psf[:, 0, 49], g["f64/psf_center_row"]) < 2e-5
+    for b in range(4):
+        got = summarize(psf[b])
+        assert abs(got[0] - g["f64/psf_summary"][b][0]) / g["f64/psf_summary"][b][0] < 2e-5
+    loss = torch.nn.functional.mse_loss(LR[:, 2:3], LRd)
+    assert abs(loss.item() - float(g["f64/loss"])) / float(g["f64/loss"]) < 2e-5
+    loss.backward()
+    for (n, p), want in zip(m.named_parameters(), g["f64/grad_summary"]):
+        got = summarize(p.grad)
+        assert abs(got[0] - want[0]) / want[0] < 1e-3, (n, got[0], want[0])
+        k = min(len(got), len(want))
+        scale = max(np.abs(want[3:k]).max(), 1e-30)
+        assert np.abs(got[3:k] - want[3:k]).max() / scale < 1e-3, n
+
+
+def test_tpsf_all_output_gradients_match_cpu_oracle():
+    """Gradients through every output (HR, LR_degrade, psf, alphaBeta), with gamma large enough that the
+    mask minimum m = exp(-100/gamma) does not underflow."""
+    from oracle import tpsf_oracle as po
+    from tactilesr_b200.model import tPSFNet
+    B = 3
+    sd = po.make_state(9)
+    sd["MLP_layer.7.bias"] = sd["MLP_layer.7.bias"] + torch.tensor([0.5, 1.0, 30.0])   # alpha, beta, gamma up
+    gen = torch.Generator().manual_seed(10)
+    LR = torch.rand(B, 3, 4, 4, generator=gen) * 13
+    depth = po.synthetic_depth(B, 11)
+    wHR = torch.rand(B, 1, 100, 100, generator=gen)
+    wL = torch.rand(B, 1, 4, 4, generator=gen) * 100
+    wP = torch.rand(B, 1, 99, 99, generator=gen)
+    wA = torch.rand(B, 1, 3, generator=gen)
+    leaf = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    HRo, LRdo, psfo, abo = po.tpsf_forward(leaf, LR.double(), depth.double().unsqueeze(1))
+    tot = (HRo * wHR).sum() + (LRdo * wL).sum() + (psfo * wP).sum() + (abo * wA).sum()
+    go = torch.autograd.grad(tot, list(leaf.values()))
+    m = tPSFNet(1.4, None, device="cuda")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    HR, LRd, psf, ab = m(LR.cuda(), depth.cuda().unsqueeze(1))
+    assert rel_l2(HR, HRo) < 2e-5 and rel_l2(LRd, LRdo) < 2e-5 and rel_l2(psf, psfo) < 2e-5 and rel_l2(ab, abo) < 2e-6
+    ((HR * wHR.cuda()).sum() + (LRd * wL.cuda()).sum() + (psf * wP.cuda()).sum() + (ab * wA.cuda()).sum()).backward()
+    for (n, p), gref in zip(m.named_parameters(), go):
+        assert rel_l2(p.grad, gref) < 1e-3, (n, rel_l2(p.grad, gref))
+
+
+def test_tpsf_edge_cases():
+    """single-sample batch; all-contact and single-pixel-contact depth maps (mask edge cases)."""
+    from oracle import tpsf_oracle as po
+    from tactilesr_b200.model import tPSFNet
+    sd = po.make_state(3)
+    m = tPSFNet(1.4, None, device="cuda")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    depth = torch.zeros(3, 1, 100, 100)
+    depth[0] = 1.0                       # every pixel is contact: HR is the constant second max (= 0)
+    depth[1, 0, 50, 50] = 1.0            # one contact pixel
+    depth[2, 0, :, :50] = 0.5            # no pixel reaches 1: contact = the 0.5 plateau
+    LR = torch.rand(3, 3, 4, 4, generator=torch.Generator().manual_seed(4)) * 13
+    HRo, LRdo, psfo, abo = po.tpsf_forward({k: v.double() for k, v in sd.items()}, LR.double(), depth.double())
+    for sl in (slice(0, 3), slice(1, 2)):
+        HR, LRd, psf, ab = m(LR[sl].cuda(), depth[sl].cuda())
+        assert torch.isfinite(HR).all() and torch.isfinite(LRd).all()
+        assert (HR - HRo[sl].float().cuda()).abs().max() <= 2e-5 * max(HRo[sl].abs().max().item(), 1e-6) + 1e-7
+        assert rel_l2(LRd, LRdo[sl]) < 5e-5 or LRdo[sl].abs().max() < 1e-12
+    with pytest.raises(AssertionError):
+        m(LR.cuda(), depth[:2].cuda())
