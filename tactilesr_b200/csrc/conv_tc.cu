@@ -1,10 +1,428 @@
-// placeholder until the tcgen05 kernels land (next commit)
+// Tensor-core convolution for sm_100a: implicit GEMM on tcgen05.mma with TMEM accumulators, activation
+// halo tiles staged once per CTA by TMA (zero-filled padding), weights streamed through an mbarrier ring
+// by bulk copies.  bf16 operands, fp32 accumulation.
+//
+//   out[p][co] = epilogue( sum_{tap, ci} in[p + shift(tap)][ci] * w[tap][ci][co] )
+//
+// Work decomposition ("tall plane"): the B samples are stacked vertically with `pad` virtual zero rows
+// after each sample (pitch Hp = H + pad), so a CTA block is simply TM/8 consecutive virtual rows x 8
+// columns = T M-tiles of 128 pixels, and every tap is a pure (row, column) shift inside one shared-memory
+// halo tile.  The A operand of each MMA is a *window* of that halo tile: the UMMA shared-memory descriptor
+// starts at row (ky*P + kx) of the tile, 8-row core groups are P*128 B apart (P = 16-pixel pitch), so no
+// im2col copy is ever materialised and each activation byte is read from L2 once per CTA instead of once
+// per tap.  The B operand (weights, pre-swizzled on the host side into the SWIZZLE_128B image) is streamed
+// per (channel chunk, tap) with cp.async.bulk.
+//
+// Warp roles (7 warps): 0 = A/TMA producer, 1 = MMA issuer + TMEM owner, 2 = B producer, 3..6 = epilogue
+// (TMEM -> registers -> bias / residual / ReLU -> bf16 global stores).
+//
+// Replaces the cuDNN dispatch behind nn.Conv2d for the channel-heavy convs of reference
+// model/tactileSR_model.py:41,47,53,168,174,180,186,191,219,220 (forward) and their data gradients.
 #include "common.cuh"
-extern "C" {
-int tsr_pack_conv_weight_bf16(const float*, void*, void*, int, int, int, cudaStream_t) { tsr_set_error("tc path not built"); return TSR_ERR_UNSUPPORTED; }
-int tsr_conv2d_tc(const void*, int, const void*, const float*, const void*, int, void*, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t) { tsr_set_error("tc path not built"); return TSR_ERR_UNSUPPORTED; }
-size_t tsr_conv2d_tc_workspace(int, int, int, int, int, int) { return 0; }
-int tsr_conv2d_wgrad_tc(const void*, int, const void*, int, float*, void*, size_t, int, int, int, int, int, int, int, cudaStream_t) { tsr_set_error("tc path not built"); return TSR_ERR_UNSUPPORTED; }
-size_t tsr_conv2d_wgrad_tc_workspace(int, int, int, int, int, int) { return 0; }
-int tsr_tc_selftest(int, void*, void*, cudaStream_t) { tsr_set_error("tc path not built"); return TSR_ERR_UNSUPPORTED; }
+#include <cuda.h>
+
+namespace {
+
+constexpr int FLAG_RELU = 1;
+constexpr int T_TILES = 2;          // M-tiles (128 pixels each) per CTA
+constexpr int NB_STAGES = 3;        // weight ring depth
+constexpr int NA_SLOTS = 2;         // activation chunk slots
+constexpr int NUM_THREADS = 224;
+
+int g_desc_mode = 0;                // 0: base_offset = 0, 1: base_offset = (addr >> 7) & 7
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a lost arrival must never hang the GPU box -- trap instead (surfaces as a CUDA error)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("tactilesr_b200 conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major / MN-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [49,52) base offset, [61,64) layout=2
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t lbo_bytes, int mode) {
+  uint64_t d = (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  if (mode == 1) d |= (uint64_t)((addr >> 7) & 7) << 49;
+  d |= 2ull << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=f32 (bit4), A=bf16 (bit7), B=bf16 (bit10), majors bit15/16,
+// N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct ConvParams {
+  const __nv_bfloat16* w;        // pre-swizzled [chunk][tap][N][64]
+  const float* bias;             // [N] or null
+  const __nv_bfloat16* residual; // [pix][res_ld] or null
+  __nv_bfloat16* out;            // [pix][out_ld]
+  int res_ld, out_ld;
+  int B, H, W, Hp, Vtotal;       // Hp = H + pad, Vtotal = B * Hp
+  int KS, pad, P, rows;          // P = smem pixel pitch of a halo row, rows = 16*T + 2*pad
+  int nchunks, nxg, flags, desc_mode;
+};
+
+template <int N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve (1024-aligned): A slots | B stages | barriers | tmem ptr
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_slot_bytes = (uint32_t)p.rows * p.P * 128u;
+  const uint32_t a_base = base;
+  const uint32_t b_base = a_base + NA_SLOTS * a_slot_bytes;
+  constexpr uint32_t B_STAGE = N * 128u;
+  const uint32_t bar_base = b_base + NB_STAGES * B_STAGE;
+  auto a_full = [&](int i) { return bar_base + 8u * i; };
+  auto a_empty = [&](int i) { return bar_base + 8u * (NA_SLOTS + i); };
+  auto b_full = [&](int i) { return bar_base + 8u * (2 * NA_SLOTS + i); };
+  auto b_empty = [&](int i) { return bar_base + 8u * (2 * NA_SLOTS + NB_STAGES + i); };
+  const uint32_t tmem_full = bar_base + 8u * (2 * NA_SLOTS + 2 * NB_STAGES);
+  const uint32_t tmem_slot = tmem_full + 8u;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int xg = blockIdx.x % p.nxg, vb = blockIdx.x / p.nxg;
+  const int x0 = xg * 8, v0 = vb * (16 * T_TILES);
+  const int taps = p.KS * p.KS;
+  constexpr uint32_t TMEM_COLS = T_TILES * N;   // 128 or 256: power of two >= 32
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NA_SLOTS; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < NB_STAGES; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== A producer: one TMA box (64 ch x (8+2pad) px x 1 row) per virtual halo row =====
+    if (lane == 0) {
+      const uint32_t row_bytes = (uint32_t)(8 + 2 * p.pad) * 128u;
+      for (int c = 0; c < p.nchunks; ++c) {
+        const int slot = c % NA_SLOTS;
+        mbar_wait(a_empty(slot), ((c / NA_SLOTS) & 1) ^ 1);
+        mbar_expect_tx(a_full(slot), row_bytes * p.rows);
+        const uint32_t dst0 = a_base + slot * a_slot_bytes;
+        for (int r = 0; r < p.rows; ++r) {
+          const int vr = v0 - p.pad + r;
+          int n = 0, y = p.H;   // out-of-bounds row => TMA zero fill
+          if (vr >= 0 && vr < p.Vtotal) { n = vr / p.Hp; y = vr - n * p.Hp; }
+          tma_load_4d(dst0 + (uint32_t)r * p.P * 128u, &tmap, c * 64, x0 - p.pad, y, n, a_full(slot));
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== B producer: one pre-swizzled [N][64] weight tile per (chunk, tap) =====
+    if (lane == 0) {
+      const int total = p.nchunks * taps;
+      for (int it = 0; it < total; ++it) {
+        const int st = it % NB_STAGES;
+        mbar_wait(b_empty(st), ((it / NB_STAGES) & 1) ^ 1);
+        mbar_expect_tx(b_full(st), B_STAGE);
+        bulk_load(b_base + st * B_STAGE, p.w + (size_t)it * N * 64, B_STAGE, b_full(st));
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, N, 0, 0);
+      const uint32_t sbo_a = (uint32_t)p.P * 128u;
+      int it = 0;
+      for (int c = 0; c < p.nchunks; ++c) {
+        const int slot = c % NA_SLOTS;
+        mbar_wait(a_full(slot), (c / NA_SLOTS) & 1);
+        tc_fence_after();
+        const uint32_t a0 = a_base + slot * a_slot_bytes;
+        for (int t = 0; t < taps; ++t, ++it) {
+          const int st = it % NB_STAGES;
+          mbar_wait(b_full(st), (it / NB_STAGES) & 1);
+          tc_fence_after();
+          const int ky = t / p.KS, kx = t - ky * p.KS;
+          const uint32_t b0 = b_base + st * B_STAGE;
+#pragma unroll
+          for (int mt = 0; mt < T_TILES; ++mt) {
+            const uint32_t arow = a0 + (uint32_t)((mt * 16 + ky) * p.P + kx) * 128u;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = make_desc(arow + kk * 32u, sbo_a, 16u, p.desc_mode);
+              const uint64_t bd = make_desc(b0 + kk * 32u, 1024u, 16u, 0);
+              umma_bf16(tmem_base + mt * N, ad, bd, idesc, (it | kk) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(b_empty(st));
+        }
+        umma_commit(a_empty(slot));
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ===== epilogue: warps 3..6 own TMEM lanes 32*(warp%4).. =====
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int r = q * 32 + lane;          // accumulator row = pixel within the M-tile
+    const int wx = r & 7, vrow = r >> 3;
+#pragma unroll 1
+    for (int mt = 0; mt < T_TILES; ++mt) {
+      const int vr = v0 + mt * 16 + vrow;
+      const int n = vr / p.Hp, y = vr - n * p.Hp;
+      const bool valid = vr < p.Vtotal && y < p.H;
+      const long long pix = ((long long)n * p.H + y) * p.W + x0 + wx;
+#pragma unroll 1
+      for (int j = 0; j < N / 16; ++j) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + mt * N + j * 16, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
+          if (p.bias) {
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) {
+              float4 bv = *reinterpret_cast<const float4*>(p.bias + j * 16 + k);
+              f[k] += bv.x; f[k + 1] += bv.y; f[k + 2] += bv.z; f[k + 3] += bv.w;
+            }
+          }
+          if (p.residual) {
+            const __nv_bfloat16* rp = p.residual + pix * p.res_ld + j * 16;
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) {
+              float4 rv = ld4(rp + k);
+              f[k] += rv.x; f[k + 1] += rv.y; f[k + 2] += rv.z; f[k + 3] += rv.w;
+            }
+          }
+          if (p.flags & FLAG_RELU) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
+          }
+          uint32_t o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+            o[k] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_ld + j * 16);
+          op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: OIHW fp32 -> bf16 [chunk][tap][N rows][64] in the SWIZZLE_128B shared-memory image
+//   forward: rows = co, K = ci;   dgrad: rows = ci, K = co, taps flipped
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                        __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int KS) {
+  const int taps = KS * KS;
+  const long long n = (long long)Cout * Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const long long r = i / taps;
+    const int ci = (int)(r % Cin);
+    const int co = (int)(r / Cin);
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+    if (wf) {   // tile (chunk = ci/64, tap t): row co, k = ci%64
+      const int c = ci >> 6, k = ci & 63;
+      const long long tile = ((long long)c * taps + t) * Cout * 64;
+      wf[tile + (long long)co * 64 + (((k >> 3) ^ (co & 7)) << 3) + (k & 7)] = v;
+    }
+    if (wd) {   // tile (chunk = co/64, tap taps-1-t): row ci, k = co%64
+      const int c = co >> 6, k = co & 63;
+      const long long tile = ((long long)c * taps + (taps - 1 - t)) * Cin * 64;
+      wd[tile + (long long)ci * 64 + (((k >> 3) ^ (ci & 7)) << 3) + (k & 7)] = v;
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+size_t conv_smem_bytes(int N, int KS) {
+  int pad = KS / 2;
+  int P = pad ? 16 : 8;
+  int rows = 16 * T_TILES + 2 * pad;
+  return 1024 + (size_t)NA_SLOTS * rows * P * 128 + (size_t)NB_STAGES * N * 128 + 256;
+}
+
+template <int N>
+int launch_conv(const CUtensorMap& tmap, const ConvParams& p, int grid, cudaStream_t stream) {
+  size_t smem = conv_smem_bytes(N, p.KS);
+  TSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv_tc_kernel<N><<<grid, NUM_THREADS, smem, stream>>>(tmap, p);
+  TSR_CHECK_LAUNCH("conv2d_tc");
+  return TSR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void tsr_set_tc_desc_mode(int mode) { g_desc_mode = mode; }
+int tsr_get_tc_desc_mode(void) { return g_desc_mode; }
+
+int tsr_pack_conv_weight_bf16(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int KS,
+                              cudaStream_t stream) {
+  TSR_REQUIRE(w_oihw && (w_fwd || w_dgrad), "pack_conv_weight_bf16: null pointer");
+  TSR_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "pack_conv_weight_bf16: Cin, Cout must be multiples of 64");
+  long long n = (long long)Cout * Cin * KS * KS;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 2048) blocks = 2048;
+  pack_weight_bf16_kernel<<<blocks, 256, 0, stream>>>(w_oihw, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad, Cout, Cin, KS);
+  TSR_CHECK_LAUNCH("pack_conv_weight_bf16");
+  return TSR_OK;
+}
+
+size_t tsr_conv2d_tc_workspace(int, int, int, int, int, int) { return 0; }
+
+// bf16 NHWC convolution on the tensor cores.  in: [B*H*W][in_ld] (Cin channels from `in`), w_packed from
+// tsr_pack_conv_weight_bf16, bias fp32 [Cout] or NULL, residual bf16 [pix][res_ld] or NULL, out bf16.
+int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* bias, const void* residual,
+                  int res_ld, void* out, int out_ld, int B, int H, int W, int Cin, int Cout, int KS, int flags,
+                  void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  (void)workspace; (void)ws_bytes;
+  TSR_REQUIRE(in && w_packed && out, "conv2d_tc: null pointer");
+  TSR_REQUIRE(Cout == 64 || Cout == 128, "conv2d_tc: Cout must be 64 or 128 (got %d)", Cout);
+  TSR_REQUIRE(Cin % 64 == 0 && Cin > 0, "conv2d_tc: Cin must be a multiple of 64 (got %d)", Cin);
+  TSR_REQUIRE(KS == 1 || KS == 3 || KS == 5, "conv2d_tc: kernel size %d unsupported", KS);
+  TSR_REQUIRE(W % 8 == 0, "conv2d_tc: W must be a multiple of 8 (got %d)", W);
+  TSR_REQUIRE(in_ld % 8 == 0 && out_ld % 8 == 0 && (!residual || res_ld % 8 == 0), "conv2d_tc: row strides must be multiples of 8");
+  TSR_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)w_packed & 15) == 0, "conv2d_tc: pointers must be 16-byte aligned");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { tsr_set_error("conv2d_tc: cuTensorMapEncodeTiled unavailable"); return TSR_ERR_CUDA; }
+  const int pad = KS / 2;
+  CUtensorMap tmap;
+  cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)in_ld * 2, (cuuint64_t)W * in_ld * 2, (cuuint64_t)H * W * in_ld * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(8 + 2 * pad), 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { tsr_set_error("conv2d_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return TSR_ERR_CUDA; }
+  ConvParams p;
+  p.w = (const __nv_bfloat16*)w_packed;
+  p.bias = bias;
+  p.residual = (const __nv_bfloat16*)residual;
+  p.out = (__nv_bfloat16*)out;
+  p.res_ld = res_ld; p.out_ld = out_ld;
+  p.B = B; p.H = H; p.W = W; p.Hp = H + pad; p.Vtotal = B * (H + pad);
+  p.KS = KS; p.pad = pad; p.P = pad ? 16 : 8; p.rows = 16 * T_TILES + 2 * pad;
+  p.nchunks = Cin / 64; p.nxg = W / 8; p.flags = flags; p.desc_mode = g_desc_mode;
+  const int nvb = tsr_cdiv(p.Vtotal, 16 * T_TILES);
+  const int grid = nvb * p.nxg;
+  return Cout == 128 ? launch_conv<128>(tmap, p, grid, stream) : launch_conv<64>(tmap, p, grid, stream);
+}
+
+int tsr_conv2d_wgrad_tc(const void*, int, const void*, int, float*, void*, size_t, int, int, int, int, int, int, int,
+                        cudaStream_t) {
+  tsr_set_error("conv2d_wgrad_tc: not built yet");
+  return TSR_ERR_UNSUPPORTED;
+}
+size_t tsr_conv2d_wgrad_tc_workspace(int, int, int, int, int, int) { return 0; }
+int tsr_tc_selftest(int, void*, void*, cudaStream_t) { return TSR_OK; }
+
+}  // extern "C"
