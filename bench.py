@@ -1,0 +1,302 @@
+#!/usr/bin/env python3
+"""Headline benchmark of the tactileSR hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32] [--batch B]
+
+A "step" is one training iteration of TactileSR(seqsCnt=1) -- forward + fused HR-prep/MSE loss + backward + fused Adam
+(+ the bucketed NCCL gradient all-reduce when N > 1) -- on one synthetic batch of B samples per GPU (weak scaling).
+``value`` times K steps with the batches already resident in HBM; ``e2e`` times the same steps through the public
+trainer API (``Trainer_tactileSR.train_one_iter``) with pinned HOST batches, so the H2D copies of LR / HR and the D2H
+read of the loss are inside the timed region.  ``--impl reference`` times the CPU oracle port of the reference
+(PyTorch-CPU, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_SAMPLE_TRAIN = 43.916e9     # SURVEY.md section 8d, TactileSR S=1 forward+backward (2*MAC of the convs)
+FLOP_PER_SAMPLE_FWD = 14.642e9
+SR_CONFIG = dict(seqsCnt=1, axisCnt=3, HR_scale_num=10, scale_factor=10, patternFeatureExtraLayerCnt=6,
+                 forceFeatureExtraLayerCnt=1, lr=1e-3, weight_decay=1e-2)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_batches(n, B, seed, pin):
+    """LR (B,3,4,4) in taxel units 0..8 and HR_raw (B,1,100,100) in 0..250."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        LR = torch.rand(B, 3, 4, 4, generator=g) * 8
+        HR = torch.rand(B, 1, 100, 100, generator=g) * 250
+        if pin:
+            LR, HR = LR.pin_memory(), HR.pin_memory()
+        out.append((LR, HR))
+    return out
+
+
+def cpu_reference_steps(B, steps, warmup, seed=42):
+    """The reference's CPU path (oracle port: PyTorch-CPU arithmetic, stock autograd, Adam) on `steps` batches of B."""
+    import torch
+    from oracle import tactilesr_oracle as so
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = so.make_state(so.tactilesr_layout(1), seed, nondegenerate=False)
+    batches = synthetic_batches(steps + warmup, B, seed + 1, False)
+    keys = so.param_keys(sd)
+    m = {k: torch.zeros_like(sd[k]) for k in keys}
+    v = {k: torch.zeros_like(sd[k]) for k in keys}
+    times = []
+    for t, (LR, HR) in enumerate(batches, start=1):
+        t0 = time.perf_counter()
+        loss, _, g, new_stats = so.loss_and_grads(sd, LR, HR, True)
+        for k in keys:
+            sd[k], m[k], v[k] = so.adam_step(sd[k], g[k], m[k], v[k], t, 1e-3, 1e-2)
+        sd.update(new_stats)
+        times.append(time.perf_counter() - t0)
+    times = times[warmup:]
+    return B * len(times) / sum(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = 32
+    steps, warmup = max(1, min(args.steps, 4)), max(1, min(args.warmup, 1))
+    val, cores = cpu_reference_steps(B, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "SR train samples/sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 * B / val, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "TactileSR(seqsCnt=1) train step: fwd + HR-prep/MSE + bwd + Adam(lr 1e-3, wd 1e-2), fp32, CPU",
+                   "batch_per_step": B, "bounded_sample": f"{steps} steps of the reference's own batch size 32"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} train steps of B=32 (reference config/default.py:46) after {warmup} warm-up"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def time_dominant_kernel(B, reps=10):
+    """conv_tc_kernel<128> on the MSRB conv_5_2 shape (128->128, 5x5, 53.7 % of the forward FLOPs): algorithmic FLOPs per
+    launch / CUDA-event time on the launching stream."""
+    import torch
+    from tactilesr_b200 import _lib
+    dev = "cuda"
+    x = torch.randn(B * 1600, 128, device=dev).to(torch.bfloat16)
+    w = torch.randn(128, 128, 5, 5, device=dev) * 0.02
+    wf = torch.empty(25 * 128 * 128, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(B * 1600, 128, dtype=torch.bfloat16, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call("tsr_pack_conv_weight_bf16", w.data_ptr(), wf.data_ptr(), 0, 128, 128, 5, st)
+
+    def launch():
+        _lib.call("tsr_conv2d_tc", x.data_ptr(), 128, wf.data_ptr(), 0, 0, 0, out.data_ptr(), 128, B, 40, 40, 128, 128, 5, 0, 0, 0, st)
+    for _ in range(3):
+        launch()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * B * 1600 * 128 * 128 * 25
+    return flops / (ms * 1e-3) / 1e12, ms, flops
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import tactilesr_b200 as tb
+    from tactilesr_b200 import _lib
+    from tactilesr_b200.cpu import distributed as D
+    from tactilesr_b200.train.tactileSR_train import Trainer_tactileSR, build_model_and_optimizer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; tactilesr_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    rank, local_rank, world = D.init_distributed()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    _lib.check(_lib.lib().tsr_check_device(), "device check")
+    tb.set_precision(args.precision)
+    B = args.batch
+    torch.manual_seed(42)                                   # identical weights on every rank
+    model, opt = build_model_and_optimizer(SR_CONFIG, dev)
+    nb = 4                                                  # rotating distinct batches
+    host = synthetic_batches(nb, B, 1000 + rank, pin=True)
+    devb = [(a.to(dev), b.to(dev)) for a, b in host]
+
+    class Loader:
+        def __init__(self, items): self.items = items
+        def __len__(self): return len(self.items)
+        def __iter__(self):
+            while True:
+                for it in self.items:
+                    yield it
+
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.8)
+    tr = Trainer_tactileSR(SR_CONFIG, model=model, optimizer=opt, lr_scheduler=sched, data_loader=Loader(devb),
+                           max_iters=10 ** 9, log_period=10 ** 9, device=dev)
+    tr._setup_dp()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(tr, steps, sync_loss):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            tr.train_one_iter()
+            if sync_loss:
+                # end-to-end: the user reads the loss of every step back to the host (reference cpu/trainer.py:259)
+                _ = float(tr._loss_acc.item())
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), _lib.launch_count() - l0
+
+    for _ in range(max(args.warmup, 3)):
+        tr.train_one_iter()
+    with ClockSampler(local_rank) as cs:
+        ms_dev, launches = timed(tr, args.steps, False)
+    clocks = cs.summary()
+    tr._data_iter = iter(Loader(host))                      # same trainer, batches now start in pinned host memory
+    for _ in range(2):
+        tr.train_one_iter()
+    ms_e2e, _ = timed(tr, args.steps, True)
+
+    total = B * world * args.steps
+    value = total / (ms_dev * 1e-3)
+    e2e = total / (ms_e2e * 1e-3)
+    if rank != 0:
+        return
+    pk = peaks()
+    roof = None
+    if args.precision == "bf16":
+        tf, kms, kflops = time_dominant_kernel(B)
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel<128> 5x5 128->128 (MSRB conv_5_2 forward shape)", "achieved": tf,
+                "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": tf / pk["tf_burst"], "peak_source": pk["src"] + " bf16 burst",
+                "ms_per_launch": kms, "flops_per_launch": kflops, "traffic": None}
+    else:
+        roof = {"bound": "tensor", "kernel": "whole fp32 step (FFMA implicit GEMM; fp32-accurate parity mode)",
+                "achieved": value / world * FLOP_PER_SAMPLE_TRAIN / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                "frac": value / world * FLOP_PER_SAMPLE_TRAIN / 1e12 / pk["tf_sust"], "peak_source": pk["src"] + " bf16 sustained", "traffic": None}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores = cpu_reference_steps(32, 3, 1)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": "3 train steps of B=32 (reference batch size, config/default.py:46) after 1 warm-up; oracle port of the reference CPU path"}
+    line = {
+        "metric": "SR train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": "TactileSR(seqsCnt=1) train step: fwd + fused HR-prep/MSE + bwd + fused Adam(lr 1e-3, wd 1e-2)"
+                               + (" + bucketed NCCL grad all-reduce" if world > 1 else ""),
+                   "per_gpu_batch": B, "global_batch": B * world, "input": "LR (B,3,4,4), HR (B,1,100,100)",
+                   "precision_mode": args.precision, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (saved activations, B x ~26-52 MB) >> 126 MB L2; 4 rotating input batches"},
+        "tensor_roofline_frac_step": value / world * FLOP_PER_SAMPLE_TRAIN / 1e12 / pk["tf_sust"],
+        "roofline": roof, "cpu_baseline": cpu,
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": B * (3 * 16 + 100 * 100) * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("TSR_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("TSR_BENCH_BATCH", "256")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
