@@ -325,6 +325,178 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient on the tensor cores:
+//   dW[tap][ci][co] = sum_pix x[pix + shift(tap)][ci] * dy[pix][co]
+// as D[M = co][N = 64 ci] += A[M][K = pixels] * B[N][K]^T with BOTH operands MN-major: a shared-memory row is one
+// pixel's 64 channels (128 B, SWIZZLE_128B) -- exactly the image the forward kernel's TMA boxes produce -- so the same
+// halo tile serves every tap through a shifted descriptor start address, and K = 16 pixels per MMA are two 8-pixel
+// core groups one virtual row apart.  A CTA owns (tap group of <= 8 taps) x (one 64-channel ci chunk) x (a contiguous
+// range of pixel blocks); its <= 8 x 64 fp32 accumulator columns stay in TMEM across the whole pixel range and are
+// written once, as a partial [split][tap][ci][co], which wgrad_reduce sums in a fixed order (deterministic two-level
+// reduction, same second level as the fp32 path).
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_STAGES = 3;
+constexpr int WG_MAX_TAPS = 8;
+
+struct WgradParams {
+  float* partial;               // [nsplit][taps][Cin][Cout]
+  int B, H, W, Hp, Vtotal;
+  int KS, pad, P, rows;         // rows = 16 + 2*pad halo rows per block
+  int Cin, Cout, cochunks;      // cochunks = Cout / 64
+  int ngroups, nchunks, nxg;
+  int nblocks, blocks_per_split;
+  int dy_stage_bytes, stage_bytes;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + WG_STAGES * (uint32_t)p.stage_bytes;
+  auto full = [&](int i) { return bar_base + 8u * i; };
+  auto empty = [&](int i) { return bar_base + 8u * (WG_STAGES + i); };
+  const uint32_t tmem_full = bar_base + 8u * (2 * WG_STAGES);
+  const uint32_t tmem_slot = tmem_full + 8u;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // blockIdx.x -> (tap group, ci chunk); blockIdx.y -> pixel split
+  const int grp = blockIdx.x % p.ngroups, chunk = blockIdx.x / p.ngroups;
+  const int taps = p.KS * p.KS;
+  const int tpg = (taps + p.ngroups - 1) / p.ngroups;          // taps per group (<= 8)
+  const int tap0 = grp * tpg;
+  const int ntap = min(tpg, taps - tap0);
+  const int blk0 = blockIdx.y * p.blocks_per_split;
+  const int blk1 = min(blk0 + p.blocks_per_split, p.nblocks);
+  const int nblk = max(blk1 - blk0, 0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t x_row_bytes = (uint32_t)(8 + 2 * p.pad) * 128u;
+      const uint32_t tx = x_row_bytes * p.rows + 16u * 1024u * p.cochunks;
+      for (int i = 0; i < nblk; ++i) {
+        const int st = i % WG_STAGES;
+        mbar_wait(empty(st), ((i / WG_STAGES) & 1) ^ 1);
+        mbar_expect_tx(full(st), tx);
+        const int b = blk0 + i;
+        const int xg = b % p.nxg, vb = b / p.nxg;
+        const int x0 = xg * 8, v0 = vb * 16;
+        const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
+        const uint32_t xs0 = dy0 + (uint32_t)p.dy_stage_bytes;
+        for (int r = 0; r < 16; ++r) {
+          const int vr = v0 + r;
+          int n = 0, y = p.H;
+          if (vr < p.Vtotal) { n = vr / p.Hp; y = vr - n * p.Hp; }
+          for (int cc = 0; cc < p.cochunks; ++cc)
+            tma_load_4d(dy0 + (uint32_t)cc * 16384u + (uint32_t)r * 1024u, &tmap_dy, cc * 64, x0, y, n, full(st));
+        }
+        for (int r = 0; r < p.rows; ++r) {
+          const int vr = v0 - p.pad + r;
+          int n = 0, y = p.H;
+          if (vr >= 0 && vr < p.Vtotal) { n = vr / p.Hp; y = vr - n * p.Hp; }
+          tma_load_4d(xs0 + (uint32_t)r * p.P * 128u, &tmap_x, chunk * 64, x0 - p.pad, y, n, full(st));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // A = dy (M = co, MN-major; two 64-channel atoms LBO = 16 KB apart when Cout = 128; for Cout = 64 the second
+      // atom aliases the first (LBO = 0): accumulator rows 64..127 are duplicates and are never read back).
+      const uint32_t idesc = make_idesc(128, 64, 1, 1);
+      const uint32_t lbo_a = p.cochunks == 2 ? 16384u : 0u;
+      const uint32_t sbo_x = (uint32_t)p.P * 128u;
+      for (int i = 0; i < nblk; ++i) {
+        const int st = i % WG_STAGES;
+        mbar_wait(full(st), (i / WG_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
+        const uint32_t xs0 = dy0 + (uint32_t)p.dy_stage_bytes;
+        for (int g = 0; g < ntap; ++g) {
+          const int t = tap0 + g;
+          const int ky = t / p.KS, kx = t - ky * p.KS;
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            const uint64_t ad = make_desc(dy0 + (uint32_t)s * 2048u, 1024u, lbo_a, 0);
+            const uint64_t bd = make_desc(xs0 + (uint32_t)((2 * s + ky) * p.P + kx) * 128u, sbo_x, 0u, 0);
+            umma_bf16(tmem_base + g * 64, ad, bd, idesc, (i | s) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(empty(st));
+      }
+      umma_commit(tmem_full);
+    }
+  } else if (warp >= 3) {
+    if (nblk > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      const int q = warp & 3;
+      const int co = q * 32 + lane;
+      if (co < p.Cout) {
+        for (int g = 0; g < ntap; ++g) {
+          float* dst = p.partial + (((size_t)blockIdx.y * taps + tap0 + g) * p.Cin + (size_t)chunk * 64) * p.Cout + co;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + g * 64 + j * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) dst[(size_t)(j * 16 + k) * p.Cout] = __uint_as_float(v[k]);
+          }
+        }
+      }
+      tc_fence_before();
+    } else {
+      // empty split: its partial slice must still be defined for the fixed-order reduction
+      const int q = warp & 3;
+      const int co = q * 32 + lane;
+      if (co < p.Cout)
+        for (int g = 0; g < ntap; ++g) {
+          float* dst = p.partial + (((size_t)blockIdx.y * taps + tap0 + g) * p.Cin + (size_t)chunk * 64) * p.Cout + co;
+          for (int k = 0; k < 64; ++k) dst[(size_t)k * p.Cout] = 0.f;
+        }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// level 2 (shared with the fp32 path's layout): dw_oihw[co][ci][tap] (+)= sum_s partial[s][tap][ci][co]
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int S, int taps,
+                                       int Cin, int Cout, int accumulate) {
+  long long n = (long long)taps * Cin * Cout;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int co = (int)(i % Cout);
+  long long r = i / Cout;
+  int ci = (int)(r % Cin);
+  int tap = (int)(r / Cin);
+  float s = 0.f;
+  for (int k = 0; k < S; ++k) s += partial[(long long)k * n + i];
+  long long o = ((long long)co * Cin + ci) * taps + tap;
+  dw[o] = accumulate ? dw[o] + s : s;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -417,12 +589,83 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
   return Cout == 128 ? launch_conv<128>(tmap, p, grid, stream) : launch_conv<64>(tmap, p, grid, stream);
 }
 
-int tsr_conv2d_wgrad_tc(const void*, int, const void*, int, float*, void*, size_t, int, int, int, int, int, int, int,
-                        cudaStream_t) {
-  tsr_set_error("conv2d_wgrad_tc: not built yet");
-  return TSR_ERR_UNSUPPORTED;
+static void wgrad_plan(int B, int H, int W, int Cin, int Cout, int KS, int* ngroups, int* nsplit, int* nblocks,
+                       int* bps) {
+  const int pad = KS / 2, taps = KS * KS;
+  *ngroups = (taps + WG_MAX_TAPS - 1) / WG_MAX_TAPS;
+  const int Vtotal = B * (H + pad);
+  *nblocks = tsr_cdiv(Vtotal, 16) * (W / 8);
+  const int ctas = *ngroups * (Cin / 64);
+  int s = (148 + ctas - 1) / ctas;
+  if (s > *nblocks) s = *nblocks;
+  if (s < 1) s = 1;
+  *bps = tsr_cdiv(*nblocks, s);
+  *nsplit = tsr_cdiv(*nblocks, *bps);
 }
-size_t tsr_conv2d_wgrad_tc_workspace(int, int, int, int, int, int) { return 0; }
+
+size_t tsr_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS) {
+  int ng, ns, nb, bps;
+  wgrad_plan(B, H, W, Cin, Cout, KS, &ng, &ns, &nb, &bps);
+  return (size_t)ns * KS * KS * Cin * Cout * sizeof(float);
+}
+
+// dw_oihw (fp32, [Cout][Cin][KS][KS]) (+)= wgrad of the conv;  in / dout are bf16 NHWC views.
+int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
+                        size_t ws_bytes, int B, int H, int W, int Cin, int Cout, int KS, int accumulate,
+                        cudaStream_t stream) {
+  TSR_REQUIRE(in && dout && dw_oihw && workspace, "conv2d_wgrad_tc: null pointer");
+  TSR_REQUIRE(Cout == 64 || Cout == 128, "conv2d_wgrad_tc: Cout must be 64 or 128 (got %d)", Cout);
+  TSR_REQUIRE(Cin % 64 == 0 && Cin > 0, "conv2d_wgrad_tc: Cin must be a multiple of 64 (got %d)", Cin);
+  TSR_REQUIRE(KS == 1 || KS == 3 || KS == 5, "conv2d_wgrad_tc: kernel size %d unsupported", KS);
+  TSR_REQUIRE(W % 8 == 0, "conv2d_wgrad_tc: W must be a multiple of 8");
+  TSR_REQUIRE(in_ld % 8 == 0 && dout_ld % 8 == 0, "conv2d_wgrad_tc: row strides must be multiples of 8");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { tsr_set_error("conv2d_wgrad_tc: cuTensorMapEncodeTiled unavailable"); return TSR_ERR_CUDA; }
+  const int pad = KS / 2, taps = KS * KS;
+  WgradParams p;
+  int nsplit = 1;
+  wgrad_plan(B, H, W, Cin, Cout, KS, &p.ngroups, &nsplit, &p.nblocks, &p.blocks_per_split);
+  size_t need = (size_t)nsplit * taps * Cin * Cout * sizeof(float);
+  if (ws_bytes < need) { tsr_set_error("conv2d_wgrad_tc: workspace too small (%zu < %zu)", ws_bytes, need); return TSR_ERR_WORKSPACE; }
+  CUtensorMap tmx, tmdy;
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)in_ld * 2, (cuuint64_t)W * in_ld * 2, (cuuint64_t)H * W * in_ld * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(8 + 2 * pad), 1, 1};
+    CUresult r = enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { tsr_set_error("conv2d_wgrad_tc: tensor map (x) failed (%d)", (int)r); return TSR_ERR_CUDA; }
+  }
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)dout_ld * 2, (cuuint64_t)W * dout_ld * 2, (cuuint64_t)H * W * dout_ld * 2};
+    cuuint32_t box[4] = {64, 8, 1, 1};
+    CUresult r = enc(&tmdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dout), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { tsr_set_error("conv2d_wgrad_tc: tensor map (dy) failed (%d)", (int)r); return TSR_ERR_CUDA; }
+  }
+  p.partial = (float*)workspace;
+  p.B = B; p.H = H; p.W = W; p.Hp = H + pad; p.Vtotal = B * (H + pad);
+  p.KS = KS; p.pad = pad; p.P = pad ? 16 : 8; p.rows = 16 + 2 * pad;
+  p.Cin = Cin; p.Cout = Cout; p.cochunks = Cout / 64;
+  p.nchunks = Cin / 64; p.nxg = W / 8;
+  p.dy_stage_bytes = 16 * 1024 * p.cochunks;
+  p.stage_bytes = p.dy_stage_bytes + p.rows * p.P * 128;
+  size_t smem = 1024 + (size_t)WG_STAGES * p.stage_bytes + 256;
+  TSR_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(p.ngroups * p.nchunks, nsplit);
+  wgrad_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmx, tmdy, p);
+  TSR_CHECK_LAUNCH("conv2d_wgrad_tc");
+  long long n = (long long)taps * Cin * Cout;
+  wgrad_tc_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>((const float*)workspace, dw_oihw, nsplit, taps, Cin,
+                                                                    Cout, accumulate);
+  TSR_CHECK_LAUNCH("wgrad_tc_reduce");
+  return TSR_OK;
+}
+
 int tsr_tc_selftest(int, void*, void*, cudaStream_t) { return TSR_OK; }
 
 }  // extern "C"

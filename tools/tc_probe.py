@@ -43,15 +43,26 @@ def case(KS, Cin, Cout, B, mode, H=40, W=40, flags=0):
         torch.cuda.synchronize()
         refd = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wb, padding=KS // 2).permute(0, 2, 3, 1)
         err2 = ((dx.float() - refd).norm() / refd.norm()).item()
-    print(f"RESULT KS={KS} Cin={Cin} Cout={Cout} B={B} mode={mode} fwd_rel_err={err.item():.3e} dgrad_rel_err={err2:.3e}", flush=True)
+    # wgrad: dW = sum_pix x (x) dy
+    err3 = -1.0
+    if Cout in (64, 128):
+        L.tsr_conv2d_wgrad_tc_workspace.restype = __import__("ctypes").c_size_t
+        need = L.tsr_conv2d_wgrad_tc_workspace(B, H, W, Cin, Cout, KS)
+        ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+        dw = torch.zeros(Cout, Cin, KS, KS, device=dev)
+        _lib.call("tsr_conv2d_wgrad_tc", x.data_ptr(), Cin, dy.data_ptr(), Cout, dw.data_ptr(), ws.data_ptr(), ws.numel(), B, H, W, Cin, Cout, KS, 0, st)
+        torch.cuda.synchronize()
+        refw = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Cout, Cin, KS, KS), dy.float().permute(0, 3, 1, 2), padding=KS // 2)
+        err3 = ((dw - refw).norm() / refw.norm()).item()
+    print(f"RESULT KS={KS} Cin={Cin} Cout={Cout} B={B} mode={mode} fwd_rel_err={err.item():.3e} dgrad_rel_err={err2:.3e} wgrad_rel_err={err3:.3e}", flush=True)
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "case":
         case(*[int(a) for a in sys.argv[2:7]])
         sys.exit(0)
-    cases = [(1, 64, 64, 2, 0), (1, 256, 64, 2, 0), (3, 64, 64, 2, 0), (3, 64, 64, 2, 1), (5, 128, 128, 3, 0), (5, 128, 128, 3, 1),
-             (3, 448, 64, 2, 0), (3, 128, 128, 5, 0), (5, 64, 64, 1, 0)]
+    cases = [(1, 64, 64, 2, 0), (1, 256, 64, 2, 0), (3, 64, 64, 2, 0), (5, 128, 128, 3, 0),
+             (3, 448, 64, 2, 0), (3, 128, 128, 5, 0), (5, 64, 64, 1, 0), (3, 64, 128, 7, 0)]
     for c in cases:
         try:
             r = subprocess.run([sys.executable, __file__, "case", *map(str, c)], capture_output=True, text=True, timeout=120)
