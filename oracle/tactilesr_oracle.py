@@ -142,8 +142,8 @@ def bilinear_matrix(n_in: int, n_out: int, dtype=torch.float64) -> Tensor:
 def upsample_bilinear(x: Tensor, n_out: int) -> Tensor:
     """nn.Upsample(scale_factor, 'bilinear', align_corners=False) (tactileSR_model.py:35,60):
     separable, rows then columns."""
-    mh = bilinear_matrix(x.shape[-2], n_out, x.dtype)
-    mw = bilinear_matrix(x.shape[-1], n_out, x.dtype)
+    mh = bilinear_matrix(x.shape[-2], n_out, x.dtype).to(x.device)
+    mw = bilinear_matrix(x.shape[-1], n_out, x.dtype).to(x.device)
     return torch.einsum("yh,bchw,xw->bcyx", mh, x, mw)
 
 
@@ -260,8 +260,8 @@ def tactilesrcnn_forward(sd, x, training: bool, new_stats=None) -> Tensor:
 def prep_hr(HR_raw: Tensor, HR_scale_num: float = 10.0, hw: int = 40) -> Tensor:
     """HR / HR_scale_num then bilinear resize to (hw, hw) (train/tactileSR_train.py:44-45)."""
     HR = HR_raw / HR_scale_num
-    mh = bilinear_matrix(HR.shape[-2], hw, HR.dtype)
-    mw = bilinear_matrix(HR.shape[-1], hw, HR.dtype)
+    mh = bilinear_matrix(HR.shape[-2], hw, HR.dtype).to(HR.device)
+    mw = bilinear_matrix(HR.shape[-1], hw, HR.dtype).to(HR.device)
     return torch.einsum("yh,bchw,xw->bcyx", mh, HR, mw)
 
 

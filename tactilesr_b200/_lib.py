@@ -29,7 +29,7 @@ SIGNATURES = {
     "tsr_conv2d_wgrad_f32_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),
     "tsr_conv2d_wgrad_f32": (_I, [_P, _I, _P, _I, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tsr_colsum_workspace": (_Z, [_L, _I]),
-    "tsr_colsum_f32": (_I, [_P, _I, _L, _I, _P, _P, _Z, _I, _P]),
+    "tsr_colsum": (_I, [_P, _I, _I, _L, _I, _P, _P, _Z, _I, _P]),
     "tsr_head_fwd": (_I, [_P, _L, _P, _P, _I, _I, _I, _I, _I, _P]),
     "tsr_head_wgrad_workspace": (_Z, [_I]),
     "tsr_head_wgrad": (_I, [_P, _L, _P, _I, _I, _P, _P, _Z, _I, _I, _I, _P]),

@@ -242,7 +242,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 // ---------------------------------------------------------------------------------------------
 // per-channel column sums (bias gradients): two-level, deterministic
 // ---------------------------------------------------------------------------------------------
-__global__ void colsum_partial_kernel(const float* __restrict__ x, int ld, int npix, int C,
+template <typename T>
+__global__ void colsum_partial_kernel(const T* __restrict__ x, int ld, int npix, int C,
                                       float* __restrict__ partial, int rows_per_block) {
   // blockDim = (C/4 threads in x... ) generic: thread handles channel quad q = tid % (C/4), row lane = tid / (C/4)
   int q4 = C / 4;
@@ -253,7 +254,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ x, int ld, int n
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (lane < lanes)
     for (int r = r0 + lane; r < r1; r += lanes) {
-      float4 v = *reinterpret_cast<const float4*>(x + (long long)r * ld + q * 4);
+      float4 v = ld4(x + (long long)r * ld + q * 4);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
   extern __shared__ float4 sm[];
@@ -601,19 +602,22 @@ size_t tsr_colsum_workspace(long long npix, int C) {
   return (size_t)nb * C * sizeof(float);
 }
 
-int tsr_colsum_f32(const float* x, int ld, long long npix, int C, float* out, void* workspace, size_t ws_bytes,
-                   int accumulate, cudaStream_t stream) {
-  TSR_REQUIRE(x && out && workspace, "colsum_f32: null pointer");
-  TSR_REQUIRE(C % 4 == 0 && C <= 1024 && ld % 4 == 0, "colsum_f32: C must be a multiple of 4 and <= 1024");
+int tsr_colsum(const void* x, int ld, int x_bf16, long long npix, int C, float* out, void* workspace, size_t ws_bytes,
+               int accumulate, cudaStream_t stream) {
+  TSR_REQUIRE(x && out && workspace, "colsum: null pointer");
+  TSR_REQUIRE(C % 4 == 0 && C <= 1024 && ld % 4 == 0, "colsum: C must be a multiple of 4 and <= 1024");
   int nb = tsr_cdiv(npix, 1024);
   if (nb > 1024) nb = 1024;
   int rpb = tsr_cdiv(npix, nb);
   nb = tsr_cdiv(npix, rpb);
-  TSR_REQUIRE(ws_bytes >= (size_t)nb * C * sizeof(float), "colsum_f32: workspace too small");
+  TSR_REQUIRE(ws_bytes >= (size_t)nb * C * sizeof(float), "colsum: workspace too small");
   int q4 = C / 4;
   int threads = (256 / q4) * q4;
   if (threads < q4) threads = q4;
-  colsum_partial_kernel<<<nb, threads, threads * sizeof(float4), stream>>>(x, ld, (int)npix, C, (float*)workspace, rpb);
+  if (x_bf16)
+    colsum_partial_kernel<__nv_bfloat16><<<nb, threads, threads * sizeof(float4), stream>>>((const __nv_bfloat16*)x, ld, (int)npix, C, (float*)workspace, rpb);
+  else
+    colsum_partial_kernel<float><<<nb, threads, threads * sizeof(float4), stream>>>((const float*)x, ld, (int)npix, C, (float*)workspace, rpb);
   TSR_CHECK_LAUNCH("colsum_partial");
   colsum_final_kernel<<<tsr_cdiv(C, 128), 128, 0, stream>>>((const float*)workspace, nb, C, out, accumulate);
   TSR_CHECK_LAUNCH("colsum_final");

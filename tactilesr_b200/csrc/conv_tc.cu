@@ -131,6 +131,7 @@ struct ConvParams {
   int B, H, W, Hp, Vtotal;       // Hp = H + pad, Vtotal = B * Hp
   int KS, pad, P, rows;          // P = smem pixel pitch of a halo row, rows = 16*T + 2*pad
   int nchunks, nxg, flags, desc_mode;
+  int w_tile_elems;              // elements between consecutive (chunk, tap) weight tiles = Cout_total * 64
 };
 
 template <int N>
@@ -199,7 +200,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
         const int st = it % NB_STAGES;
         mbar_wait(b_empty(st), ((it / NB_STAGES) & 1) ^ 1);
         mbar_expect_tx(b_full(st), B_STAGE);
-        bulk_load(b_base + st * B_STAGE, p.w + (size_t)it * N * 64, B_STAGE, b_full(st));
+        bulk_load(b_base + st * B_STAGE, p.w + (size_t)it * p.w_tile_elems, B_STAGE, b_full(st));
       }
     }
   } else if (warp == 1) {
@@ -557,7 +558,7 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
                   void* workspace, size_t ws_bytes, cudaStream_t stream) {
   (void)workspace; (void)ws_bytes;
   TSR_REQUIRE(in && w_packed && out, "conv2d_tc: null pointer");
-  TSR_REQUIRE(Cout == 64 || Cout == 128, "conv2d_tc: Cout must be 64 or 128 (got %d)", Cout);
+  TSR_REQUIRE(Cout % 64 == 0 && Cout > 0, "conv2d_tc: Cout must be a multiple of 64 (got %d)", Cout);
   TSR_REQUIRE(Cin % 64 == 0 && Cin > 0, "conv2d_tc: Cin must be a multiple of 64 (got %d)", Cin);
   TSR_REQUIRE(KS == 1 || KS == 3 || KS == 5, "conv2d_tc: kernel size %d unsupported", KS);
   TSR_REQUIRE(W % 8 == 0, "conv2d_tc: W must be a multiple of 8 (got %d)", W);
@@ -576,17 +577,25 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { tsr_set_error("conv2d_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return TSR_ERR_CUDA; }
   ConvParams p;
-  p.w = (const __nv_bfloat16*)w_packed;
-  p.bias = bias;
-  p.residual = (const __nv_bfloat16*)residual;
-  p.out = (__nv_bfloat16*)out;
   p.res_ld = res_ld; p.out_ld = out_ld;
   p.B = B; p.H = H; p.W = W; p.Hp = H + pad; p.Vtotal = B * (H + pad);
   p.KS = KS; p.pad = pad; p.P = pad ? 16 : 8; p.rows = 16 * T_TILES + 2 * pad;
   p.nchunks = Cin / 64; p.nxg = W / 8; p.flags = flags; p.desc_mode = g_desc_mode;
+  p.w_tile_elems = Cout * 64;
   const int nvb = tsr_cdiv(p.Vtotal, 16 * T_TILES);
   const int grid = nvb * p.nxg;
-  return Cout == 128 ? launch_conv<128>(tmap, p, grid, stream) : launch_conv<64>(tmap, p, grid, stream);
+  // output channels are produced in groups of 128 (or a trailing 64): rows n0.. of every pre-swizzled weight tile
+  for (int n0 = 0; n0 < Cout;) {
+    const int nt = (Cout - n0) >= 128 ? 128 : 64;
+    p.w = (const __nv_bfloat16*)w_packed + (size_t)n0 * 64;
+    p.bias = bias ? bias + n0 : nullptr;
+    p.residual = residual ? (const __nv_bfloat16*)residual + n0 : nullptr;
+    p.out = (__nv_bfloat16*)out + n0;
+    int rc = nt == 128 ? launch_conv<128>(tmap, p, grid, stream) : launch_conv<64>(tmap, p, grid, stream);
+    if (rc) return rc;
+    n0 += nt;
+  }
+  return TSR_OK;
 }
 
 static void wgrad_plan(int B, int H, int W, int Cin, int Cout, int KS, int* ngroups, int* nsplit, int* nblocks,

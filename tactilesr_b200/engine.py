@@ -133,13 +133,13 @@ class RunCtx:
 # packed-weight cache
 # ---------------------------------------------------------------------------------------------
 class _PackCache:
-    def __init__(self):
-        self.store: Dict[Tuple, Tuple[Tuple, torch.Tensor, torch.Tensor]] = {}
+    """Packed weights live on the Parameter object itself (``_tsr_pack``), so they die with it -- a process-wide dict
+    keyed by id()/data_ptr would alias a freed parameter with a new one that reuses both."""
 
     def get(self, w: torch.Tensor, mode: str, need_dgrad: bool):
-        key = (id(w), mode)
-        tag = (w.data_ptr(), w._version, _WEIGHT_EPOCH, tuple(w.shape))
-        hit = self.store.get(key)
+        tag = (w.data_ptr(), w._version, _WEIGHT_EPOCH, tuple(w.shape), w.device)
+        store = w.__dict__.setdefault("_tsr_pack", {})
+        hit = store.get(mode)
         if hit is not None and hit[0] == tag and (hit[2] is not None or not need_dgrad):
             return hit[1], hit[2]
         Cout, Cin, K, _ = w.shape
@@ -149,7 +149,7 @@ class _PackCache:
         fn = "tsr_pack_conv_weight_bf16" if mode == "bf16" else "tsr_pack_conv_weight_f32"
         wc = w.detach().contiguous()
         _lib.call(fn, wc.data_ptr(), wf.data_ptr(), _ptr(wd), Cout, Cin, K, _lib.stream_ptr())
-        self.store[key] = (tag, wf, wd)
+        store[mode] = (tag, wf, wd)
         return wf, wd
 
 
@@ -289,13 +289,8 @@ class ConvOp(Op):
                       self.Cout, self.K, acc, st)
         if self.conv.bias is not None:
             gb, accb = c.pgrad(self.conv.bias)
-            if c.bf16:
-                # bias gradient of a bf16 activation gradient: reduce through the BN-statistics kernel path
-                tmp = c.grads[self.out.buf][:, self.out.c0:self.out.c0 + self.Cout].float().sum(0)
-                gb.copy_(gb + tmp if accb else tmp)
-            else:
-                ws, wsb = c.workspace(_lib.lib().tsr_colsum_workspace(c.npix, self.Cout))
-                _lib.call("tsr_colsum_f32", gp, gld, c.npix, self.Cout, gb.data_ptr(), ws, wsb, accb, st)
+            ws, wsb = c.workspace(_lib.lib().tsr_colsum_workspace(c.npix, self.Cout))
+            _lib.call("tsr_colsum", gp, gld, c.bf16, c.npix, self.Cout, gb.data_ptr(), ws, wsb, accb, st)
         # data gradient
         if self.src_needs_grad:
             _, wd = _PACK.get(self.conv.weight, c.mode, True)
