@@ -270,11 +270,19 @@ __global__ void colsum_partial_kernel(const T* __restrict__ x, int ld, int npix,
 }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int nblocks, int C,
                                     float* __restrict__ out, int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += (double)partial[(long long)b * C + c];
-  out[c] = accumulate ? out[c] + (float)s : (float)s;
+  // block = (32 channels, 32 partial-row lanes); fixed-order double accumulation
+  __shared__ double sh[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double a = 0.0;
+  if (c < C)
+    for (int r = threadIdx.y; r < nblocks; r += 32) a += (double)partial[(long long)r * C + c];
+  sh[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double s = 0.0;
+    for (int r = 0; r < 32; ++r) s += sh[r][threadIdx.x];
+    out[c] = accumulate ? out[c] + (float)s : (float)s;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -619,7 +627,7 @@ int tsr_colsum(const void* x, int ld, int x_bf16, long long npix, int C, float* 
   else
     colsum_partial_kernel<float><<<nb, threads, threads * sizeof(float4), stream>>>((const float*)x, ld, (int)npix, C, (float*)workspace, rpb);
   TSR_CHECK_LAUNCH("colsum_partial");
-  colsum_final_kernel<<<tsr_cdiv(C, 128), 128, 0, stream>>>((const float*)workspace, nb, C, out, accumulate);
+  colsum_final_kernel<<<tsr_cdiv(C, 32), dim3(32, 32), 0, stream>>>((const float*)workspace, nb, C, out, accumulate);
   TSR_CHECK_LAUNCH("colsum_final");
   return TSR_OK;
 }

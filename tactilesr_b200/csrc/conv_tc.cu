@@ -20,6 +20,7 @@
 // model/tactileSR_model.py:41,47,53,168,174,180,186,191,219,220 (forward) and their data gradients.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -29,7 +30,11 @@ constexpr int NB_STAGES = 3;        // weight ring depth
 constexpr int NA_SLOTS = 2;         // activation chunk slots
 constexpr int NUM_THREADS = 224;
 
-int g_desc_mode = 0;                // 0: base_offset = 0, 1: base_offset = (addr >> 7) & 7
+// experiment switches (env TSR_TC_MODE or tsr_set_tc_desc_mode): bit0 = descriptor base_offset from the address
+// (wrong on B200: the swizzle phase is taken from the absolute smem address), bit1 = 16-pixel halo pitch in the forward
+// kernel instead of the dense TMA-box pitch, bit2 = v1 weight-gradient kernel (tall-plane blocks, per-row TMA).
+static int env_mode() { const char* e = getenv("TSR_TC_MODE"); return e ? atoi(e) : 0; }
+int g_desc_mode = env_mode();
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -123,7 +128,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 }
 
 struct ConvParams {
-  const __nv_bfloat16* w;        // pre-swizzled [chunk][tap][N][64]
+  const __nv_bfloat16* w;        // pre-swizzled [chunk][tap][Cout_total][64]
   const float* bias;             // [N] or null
   const __nv_bfloat16* residual; // [pix][res_ld] or null
   __nv_bfloat16* out;            // [pix][out_ld]
@@ -132,38 +137,48 @@ struct ConvParams {
   int KS, pad, P, rows;          // P = smem pixel pitch of a halo row, rows = 16*T + 2*pad
   int nchunks, nxg, flags, desc_mode;
   int w_tile_elems;              // elements between consecutive (chunk, tap) weight tiles = Cout_total * 64
+  int nblocks, nb_stages;        // CTA blocks (persistent loop), depth of the weight ring (<= MAX_NB)
 };
 
+constexpr int MAX_NB = 8;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent: gridDim.x CTAs (one per SM) stride over the blocks.  The activation-chunk ring, the weight ring and the
+// two TMEM accumulator buffers all run on global counters, so the TMA producers prefetch the next block's halo while
+// the current block is still in its main loop and the epilogue of block i overlaps the MMAs of block i+1.
 template <int N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve (1024-aligned): A slots | B stages | barriers | tmem ptr
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_slot_bytes = (uint32_t)p.rows * p.P * 128u;
+  const uint32_t a_slot_bytes = ((uint32_t)p.rows * p.P * 128u + 1023u) & ~1023u;
   const uint32_t a_base = base;
   const uint32_t b_base = a_base + NA_SLOTS * a_slot_bytes;
   constexpr uint32_t B_STAGE = N * 128u;
-  const uint32_t bar_base = b_base + NB_STAGES * B_STAGE;
+  const int NB = p.nb_stages;
+  const uint32_t bar_base = b_base + NB * B_STAGE;
   auto a_full = [&](int i) { return bar_base + 8u * i; };
   auto a_empty = [&](int i) { return bar_base + 8u * (NA_SLOTS + i); };
   auto b_full = [&](int i) { return bar_base + 8u * (2 * NA_SLOTS + i); };
-  auto b_empty = [&](int i) { return bar_base + 8u * (2 * NA_SLOTS + NB_STAGES + i); };
-  const uint32_t tmem_full = bar_base + 8u * (2 * NA_SLOTS + 2 * NB_STAGES);
-  const uint32_t tmem_slot = tmem_full + 8u;
+  auto b_empty = [&](int i) { return bar_base + 8u * (2 * NA_SLOTS + MAX_NB + i); };
+  auto t_full = [&](int i) { return bar_base + 8u * (2 * NA_SLOTS + 2 * MAX_NB + i); };
+  auto t_empty = [&](int i) { return bar_base + 8u * (2 * NA_SLOTS + 2 * MAX_NB + 2 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NA_SLOTS + 2 * MAX_NB + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int xg = blockIdx.x % p.nxg, vb = blockIdx.x / p.nxg;
-  const int x0 = xg * 8, v0 = vb * (16 * T_TILES);
   const int taps = p.KS * p.KS;
-  constexpr uint32_t TMEM_COLS = T_TILES * N;   // 128 or 256: power of two >= 32
+  constexpr uint32_t ACC_COLS = T_TILES * N;      // one accumulator buffer
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;    // 256 or 512
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA_SLOTS; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < NB_STAGES; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < NB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -179,28 +194,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
     // ===== A producer: one TMA box (64 ch x (8+2pad) px x 1 row) per virtual halo row =====
     if (lane == 0) {
       const uint32_t row_bytes = (uint32_t)(8 + 2 * p.pad) * 128u;
-      for (int c = 0; c < p.nchunks; ++c) {
-        const int slot = c % NA_SLOTS;
-        mbar_wait(a_empty(slot), ((c / NA_SLOTS) & 1) ^ 1);
-        mbar_expect_tx(a_full(slot), row_bytes * p.rows);
-        const uint32_t dst0 = a_base + slot * a_slot_bytes;
-        for (int r = 0; r < p.rows; ++r) {
-          const int vr = v0 - p.pad + r;
-          int n = 0, y = p.H;   // out-of-bounds row => TMA zero fill
-          if (vr >= 0 && vr < p.Vtotal) { n = vr / p.Hp; y = vr - n * p.Hp; }
-          tma_load_4d(dst0 + (uint32_t)r * p.P * 128u, &tmap, c * 64, x0 - p.pad, y, n, a_full(slot));
+      int ac = 0;
+      for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x) {
+        const int xg = blk % p.nxg, vb = blk / p.nxg;
+        const int x0 = xg * 8, v0 = vb * (16 * T_TILES);
+        for (int c = 0; c < p.nchunks; ++c, ++ac) {
+          const int slot = ac % NA_SLOTS;
+          mbar_wait(a_empty(slot), ((ac / NA_SLOTS) & 1) ^ 1);
+          mbar_expect_tx(a_full(slot), row_bytes * p.rows);
+          const uint32_t dst0 = a_base + slot * a_slot_bytes;
+          for (int r = 0; r < p.rows; ++r) {
+            const int vr = v0 - p.pad + r;
+            int n = 0, y = p.H;   // out-of-bounds row => TMA zero fill
+            if (vr >= 0 && vr < p.Vtotal) { n = vr / p.Hp; y = vr - n * p.Hp; }
+            tma_load_4d(dst0 + (uint32_t)r * p.P * 128u, &tmap, c * 64, x0 - p.pad, y, n, a_full(slot));
+          }
         }
       }
     }
   } else if (warp == 2) {
-    // ===== B producer: one pre-swizzled [N][64] weight tile per (chunk, tap) =====
+    // ===== B producer: one pre-swizzled [N][64] weight tile per (chunk, tap), same sequence for every block =====
     if (lane == 0) {
-      const int total = p.nchunks * taps;
-      for (int it = 0; it < total; ++it) {
-        const int st = it % NB_STAGES;
-        mbar_wait(b_empty(st), ((it / NB_STAGES) & 1) ^ 1);
-        mbar_expect_tx(b_full(st), B_STAGE);
-        bulk_load(b_base + st * B_STAGE, p.w + (size_t)it * p.w_tile_elems, B_STAGE, b_full(st));
+      const int per_block = p.nchunks * taps;
+      int it = 0;
+      for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x) {
+        for (int k = 0; k < per_block; ++k, ++it) {
+          const int st = it % NB;
+          mbar_wait(b_empty(st), ((it / NB) & 1) ^ 1);
+          mbar_expect_tx(b_full(st), B_STAGE);
+          bulk_load(b_base + st * B_STAGE, p.w + (size_t)k * p.w_tile_elems, B_STAGE, b_full(st));
+        }
       }
     }
   } else if (warp == 1) {
@@ -208,89 +231,106 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(128, N, 0, 0);
       const uint32_t sbo_a = (uint32_t)p.P * 128u;
-      int it = 0;
-      for (int c = 0; c < p.nchunks; ++c) {
-        const int slot = c % NA_SLOTS;
-        mbar_wait(a_full(slot), (c / NA_SLOTS) & 1);
+      int it = 0, ac = 0, lb = 0;
+      for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x, ++lb) {
+        const int buf = lb & 1;
+        mbar_wait(t_empty(buf), ((lb >> 1) & 1) ^ 1);     // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t a0 = a_base + slot * a_slot_bytes;
-        for (int t = 0; t < taps; ++t, ++it) {
-          const int st = it % NB_STAGES;
-          mbar_wait(b_full(st), (it / NB_STAGES) & 1);
+        const uint32_t acc0 = tmem_base + buf * ACC_COLS;
+        for (int c = 0; c < p.nchunks; ++c, ++ac) {
+          const int slot = ac % NA_SLOTS;
+          mbar_wait(a_full(slot), (ac / NA_SLOTS) & 1);
           tc_fence_after();
-          const int ky = t / p.KS, kx = t - ky * p.KS;
-          const uint32_t b0 = b_base + st * B_STAGE;
+          const uint32_t a0 = a_base + slot * a_slot_bytes;
+          for (int t = 0; t < taps; ++t, ++it) {
+            const int st = it % NB;
+            mbar_wait(b_full(st), (it / NB) & 1);
+            tc_fence_after();
+            const int ky = t / p.KS, kx = t - ky * p.KS;
+            const uint32_t b0 = b_base + st * B_STAGE;
 #pragma unroll
-          for (int mt = 0; mt < T_TILES; ++mt) {
-            const uint32_t arow = a0 + (uint32_t)((mt * 16 + ky) * p.P + kx) * 128u;
+            for (int mt = 0; mt < T_TILES; ++mt) {
+              const uint32_t arow = a0 + (uint32_t)((mt * 16 + ky) * p.P + kx) * 128u;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ad = make_desc(arow + kk * 32u, sbo_a, 16u, p.desc_mode);
-              const uint64_t bd = make_desc(b0 + kk * 32u, 1024u, 16u, 0);
-              umma_bf16(tmem_base + mt * N, ad, bd, idesc, (it | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t ad = make_desc(arow + kk * 32u, sbo_a, 16u, p.desc_mode & 1);
+                const uint64_t bd = make_desc(b0 + kk * 32u, 1024u, 16u, 0);
+                umma_bf16(acc0 + mt * N, ad, bd, idesc, (c | t | kk) != 0 ? 1u : 0u);
+              }
             }
+            umma_commit(b_empty(st));
           }
-          umma_commit(b_empty(st));
+          umma_commit(a_empty(slot));
         }
-        umma_commit(a_empty(slot));
+        umma_commit(t_full(buf));
       }
-      umma_commit(tmem_full);
     }
   } else {
     // ===== epilogue: warps 3..6 own TMEM lanes 32*(warp%4).. =====
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
     const int q = warp & 3;
     const int r = q * 32 + lane;          // accumulator row = pixel within the M-tile
     const int wx = r & 7, vrow = r >> 3;
+    int lb = 0;
+    for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x, ++lb) {
+      const int buf = lb & 1;
+      const int xg = blk % p.nxg, vb = blk / p.nxg;
+      const int x0 = xg * 8, v0 = vb * (16 * T_TILES);
+      mbar_wait(t_full(buf), (lb >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int mt = 0; mt < T_TILES; ++mt) {
-      const int vr = v0 + mt * 16 + vrow;
-      const int n = vr / p.Hp, y = vr - n * p.Hp;
-      const bool valid = vr < p.Vtotal && y < p.H;
-      const long long pix = ((long long)n * p.H + y) * p.W + x0 + wx;
+      for (int mt = 0; mt < T_TILES; ++mt) {
+        const int vr = v0 + mt * 16 + vrow;
+        const int n = vr / p.Hp, y = vr - n * p.Hp;
+        const bool valid = vr < p.Vtotal && y < p.H;
+        const long long pix = ((long long)n * p.H + y) * p.W + x0 + wx;
 #pragma unroll 1
-      for (int j = 0; j < N / 16; ++j) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + mt * N + j * 16, v);
-        tmem_ld_wait();
-        if (valid) {
-          float f[16];
+        for (int j = 0; j < N / 16; ++j) {
+          uint32_t v[16];
+          tmem_ld16(acc0 + mt * N + j * 16, v);
+          tmem_ld_wait();
+          if (valid) {
+            float f[16];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
-          if (p.bias) {
+            for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
+            if (p.bias) {
 #pragma unroll
-            for (int k = 0; k < 16; k += 4) {
-              float4 bv = *reinterpret_cast<const float4*>(p.bias + j * 16 + k);
-              f[k] += bv.x; f[k + 1] += bv.y; f[k + 2] += bv.z; f[k + 3] += bv.w;
+              for (int k = 0; k < 16; k += 4) {
+                float4 bv = *reinterpret_cast<const float4*>(p.bias + j * 16 + k);
+                f[k] += bv.x; f[k + 1] += bv.y; f[k + 2] += bv.z; f[k + 3] += bv.w;
+              }
             }
-          }
-          if (p.residual) {
-            const __nv_bfloat16* rp = p.residual + pix * p.res_ld + j * 16;
+            if (p.residual) {
+              const __nv_bfloat16* rp = p.residual + pix * p.res_ld + j * 16;
 #pragma unroll
-            for (int k = 0; k < 16; k += 4) {
-              float4 rv = ld4(rp + k);
-              f[k] += rv.x; f[k + 1] += rv.y; f[k + 2] += rv.z; f[k + 3] += rv.w;
+              for (int k = 0; k < 16; k += 4) {
+                float4 rv = ld4(rp + k);
+                f[k] += rv.x; f[k + 1] += rv.y; f[k + 2] += rv.z; f[k + 3] += rv.w;
+              }
             }
-          }
-          if (p.flags & FLAG_RELU) {
+            if (p.flags & FLAG_RELU) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
-          }
-          uint32_t o[8];
+              for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
+            }
+            uint32_t o[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-            o[k] = *reinterpret_cast<uint32_t*>(&h);
+            for (int k = 0; k < 8; ++k) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+              o[k] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_ld + j * 16);
+            op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            op[1] = make_uint4(o[4], o[5], o[6], o[7]);
           }
-          uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_ld + j * 16);
-          op[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          op[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
       }
+      // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty(buf));
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -368,9 +408,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   // blockIdx.x -> (tap group, ci chunk); blockIdx.y -> pixel split
   const int grp = blockIdx.x % p.ngroups, chunk = blockIdx.x / p.ngroups;
   const int taps = p.KS * p.KS;
-  const int tpg = (taps + p.ngroups - 1) / p.ngroups;          // taps per group (<= 8)
-  const int tap0 = grp * tpg;
-  const int ntap = min(tpg, taps - tap0);
+  const int tbase = taps / p.ngroups, trem = taps % p.ngroups;    // balanced tap groups (<= 8 taps each)
+  const int tap0 = grp * tbase + min(grp, trem);
+  const int ntap = tbase + (grp < trem ? 1 : 0);
   const int blk0 = blockIdx.y * p.blocks_per_split;
   const int blk1 = min(blk0 + p.blocks_per_split, p.nblocks);
   const int nblk = max(blk1 - blk0, 0);
@@ -482,6 +522,135 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   }
 }
 
+// ---- v2: per-sample 8x8 pixel tiles, ONE dense TMA box per operand tile, deeper ring -------------------------
+// A stage is one 8x8 tile of one sample: dy box {64 co, 8, 8, 1} per co chunk (8 KB each) and the x halo box
+// {64 ci, 8+2pad, 8+2pad, 1} (dense pitch P = 8+2pad pixels; out-of-image pixels are TMA zero fill).  K = 64 pixels
+// = 4 MMA K-steps of two 8-pixel groups one row apart.
+constexpr int WG2_MAX_STAGES = 8;
+
+struct Wgrad2Params {
+  float* partial;               // [nsplit][taps][Cin][Cout]
+  int B, H, W, KS, pad, P;
+  int Cin, Cout, cochunks;
+  int ngroups, nchunks;
+  int tiles_x, tiles_per_sample, nblocks, blocks_per_split;
+  int dy_stage_bytes, stage_bytes, nstages;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                 const Wgrad2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int NS = p.nstages;
+  const uint32_t bar_base = base + NS * (uint32_t)p.stage_bytes;
+  auto full = [&](int i) { return bar_base + 8u * i; };
+  auto empty = [&](int i) { return bar_base + 8u * (WG2_MAX_STAGES + i); };
+  const uint32_t tmem_full = bar_base + 8u * (2 * WG2_MAX_STAGES);
+  const uint32_t tmem_slot = tmem_full + 8u;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = blockIdx.x % p.ngroups, chunk = blockIdx.x / p.ngroups;
+  const int taps = p.KS * p.KS;
+  const int tbase = taps / p.ngroups, trem = taps % p.ngroups;      // balanced tap groups
+  const int tap0 = grp * tbase + min(grp, trem);
+  const int ntap = tbase + (grp < trem ? 1 : 0);
+  const int blk0 = blockIdx.y * p.blocks_per_split;
+  const int blk1 = min(blk0 + p.blocks_per_split, p.nblocks);
+  const int nblk = max(blk1 - blk0, 0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)p.P * p.P * 128u + 8192u * p.cochunks;
+      for (int i = 0; i < nblk; ++i) {
+        const int st = i % NS;
+        mbar_wait(empty(st), ((i / NS) & 1) ^ 1);
+        mbar_expect_tx(full(st), tx);
+        const int b = blk0 + i;
+        const int n = b / p.tiles_per_sample, t = b - n * p.tiles_per_sample;
+        const int y0 = (t / p.tiles_x) * 8, x0 = (t % p.tiles_x) * 8;
+        const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
+        for (int cc = 0; cc < p.cochunks; ++cc)
+          tma_load_4d(dy0 + (uint32_t)cc * 8192u, &tmap_dy, cc * 64, x0, y0, n, full(st));
+        tma_load_4d(dy0 + (uint32_t)p.dy_stage_bytes, &tmap_x, chunk * 64, x0 - p.pad, y0 - p.pad, n, full(st));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, 64, 1, 1);
+      const uint32_t lbo_a = p.cochunks == 2 ? 8192u : 0u;     // Cout = 64: second MN atom aliases the first
+      const uint32_t sbo_x = (uint32_t)p.P * 128u;
+      for (int i = 0; i < nblk; ++i) {
+        const int st = i % NS;
+        mbar_wait(full(st), (i / NS) & 1);
+        tc_fence_after();
+        const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
+        const uint32_t xs0 = dy0 + (uint32_t)p.dy_stage_bytes;
+        for (int g = 0; g < ntap; ++g) {
+          const int t = tap0 + g;
+          const int ky = t / p.KS, kx = t - ky * p.KS;
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const uint64_t ad = make_desc(dy0 + (uint32_t)s * 2048u, 1024u, lbo_a, 0);
+            const uint64_t bd = make_desc(xs0 + (uint32_t)((2 * s + ky) * p.P + kx) * 128u, sbo_x, 0u, 0);
+            umma_bf16(tmem_base + g * 64, ad, bd, idesc, (i | s) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(empty(st));
+      }
+      umma_commit(tmem_full);
+    }
+  } else if (warp >= 3) {
+    const int q = warp & 3;
+    const int co = q * 32 + lane;
+    if (nblk > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      if (q * 32 < p.Cout) {
+        for (int g = 0; g < ntap; ++g) {
+          float* dst = p.partial + (((size_t)blockIdx.y * taps + tap0 + g) * p.Cin + (size_t)chunk * 64) * p.Cout + co;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + g * 64 + j * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) dst[(size_t)(j * 16 + k) * p.Cout] = __uint_as_float(v[k]);
+          }
+        }
+      }
+      tc_fence_before();
+    } else if (co < p.Cout) {
+      for (int g = 0; g < ntap; ++g) {
+        float* dst = p.partial + (((size_t)blockIdx.y * taps + tap0 + g) * p.Cin + (size_t)chunk * 64) * p.Cout + co;
+        for (int k = 0; k < 64; ++k) dst[(size_t)k * p.Cout] = 0.f;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
 // level 2 (shared with the fp32 path's layout): dw_oihw[co][ci][tap] (+)= sum_s partial[s][tap][ci][co]
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int S, int taps,
                                        int Cin, int Cout, int accumulate) {
@@ -514,17 +683,35 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-size_t conv_smem_bytes(int N, int KS) {
-  int pad = KS / 2;
-  int P = pad ? 16 : 8;
-  int rows = 16 * T_TILES + 2 * pad;
-  return 1024 + (size_t)NA_SLOTS * rows * P * 128 + (size_t)NB_STAGES * N * 128 + 256;
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+// shared-memory plan of the forward kernel: A slots fixed by the geometry, the weight ring takes what is left
+void conv_smem_plan(int N, int rows, int P, size_t* smem, int* nb) {
+  size_t a = ((size_t)rows * P * 128 + 1023) & ~(size_t)1023;
+  size_t fixed = 1024 + NA_SLOTS * a + 512;
+  int stages = (int)((SMEM_LIMIT - fixed) / ((size_t)N * 128));
+  if (stages > MAX_NB) stages = MAX_NB;
+  *nb = stages;
+  *smem = fixed + (size_t)stages * N * 128;
 }
 
 template <int N>
-int launch_conv(const CUtensorMap& tmap, const ConvParams& p, int grid, cudaStream_t stream) {
-  size_t smem = conv_smem_bytes(N, p.KS);
+int launch_conv(const CUtensorMap& tmap, ConvParams p, cudaStream_t stream) {
+  size_t smem;
+  conv_smem_plan(N, p.rows, p.P, &smem, &p.nb_stages);
+  if (p.nb_stages < 2) { tsr_set_error("conv2d_tc: shared memory plan infeasible"); return TSR_ERR_UNSUPPORTED; }
   TSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = p.nblocks < num_sms() ? p.nblocks : num_sms();
   conv_tc_kernel<N><<<grid, NUM_THREADS, smem, stream>>>(tmap, p);
   TSR_CHECK_LAUNCH("conv2d_tc");
   return TSR_OK;
@@ -579,11 +766,12 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
   ConvParams p;
   p.res_ld = res_ld; p.out_ld = out_ld;
   p.B = B; p.H = H; p.W = W; p.Hp = H + pad; p.Vtotal = B * (H + pad);
-  p.KS = KS; p.pad = pad; p.P = pad ? 16 : 8; p.rows = 16 * T_TILES + 2 * pad;
+  // halo pitch: dense (8 + 2*pad pixels, the TMA box width) unless desc-mode bit 1 asks for the 16-pixel pitch
+  p.KS = KS; p.pad = pad; p.P = (g_desc_mode & 2) ? (pad ? 16 : 8) : 8 + 2 * pad; p.rows = 16 * T_TILES + 2 * pad;
   p.nchunks = Cin / 64; p.nxg = W / 8; p.flags = flags; p.desc_mode = g_desc_mode;
   p.w_tile_elems = Cout * 64;
   const int nvb = tsr_cdiv(p.Vtotal, 16 * T_TILES);
-  const int grid = nvb * p.nxg;
+  p.nblocks = nvb * p.nxg;
   // output channels are produced in groups of 128 (or a trailing 64): rows n0.. of every pre-swizzled weight tile
   for (int n0 = 0; n0 < Cout;) {
     const int nt = (Cout - n0) >= 128 ? 128 : 64;
@@ -591,7 +779,7 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
     p.bias = bias ? bias + n0 : nullptr;
     p.residual = residual ? (const __nv_bfloat16*)residual + n0 : nullptr;
     p.out = (__nv_bfloat16*)out + n0;
-    int rc = nt == 128 ? launch_conv<128>(tmap, p, grid, stream) : launch_conv<64>(tmap, p, grid, stream);
+    int rc = nt == 128 ? launch_conv<128>(tmap, p, stream) : launch_conv<64>(tmap, p, stream);
     if (rc) return rc;
     n0 += nt;
   }
@@ -600,12 +788,16 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
 
 static void wgrad_plan(int B, int H, int W, int Cin, int Cout, int KS, int* ngroups, int* nsplit, int* nblocks,
                        int* bps) {
-  const int pad = KS / 2, taps = KS * KS;
+  const int taps = KS * KS;
   *ngroups = (taps + WG_MAX_TAPS - 1) / WG_MAX_TAPS;
-  const int Vtotal = B * (H + pad);
-  *nblocks = tsr_cdiv(Vtotal, 16) * (W / 8);
+  if (g_desc_mode & 4) {        // v1 kernel: tall-plane 8x16 blocks
+    const int pad = KS / 2;
+    *nblocks = tsr_cdiv(B * (H + pad), 16) * (W / 8);
+  } else {                      // v2 kernel: per-sample 8x8 tiles
+    *nblocks = B * (H / 8) * (W / 8);
+  }
   const int ctas = *ngroups * (Cin / 64);
-  int s = (148 + ctas - 1) / ctas;
+  int s = num_sms() / ctas;     // a single wave: never more CTAs than SMs
   if (s > *nblocks) s = *nblocks;
   if (s < 1) s = 1;
   *bps = tsr_cdiv(*nblocks, s);
@@ -641,7 +833,7 @@ int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld
   {
     cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)in_ld * 2, (cuuint64_t)W * in_ld * 2, (cuuint64_t)H * W * in_ld * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)(8 + 2 * pad), 1, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)(8 + 2 * pad), (g_desc_mode & 4) ? 1u : (cuuint32_t)(8 + 2 * pad), 1};
     CUresult r = enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -650,24 +842,45 @@ int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld
   {
     cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)dout_ld * 2, (cuuint64_t)W * dout_ld * 2, (cuuint64_t)H * W * dout_ld * 2};
-    cuuint32_t box[4] = {64, 8, 1, 1};
+    cuuint32_t box[4] = {64, 8, (g_desc_mode & 4) ? 1u : 8u, 1};
     CUresult r = enc(&tmdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dout), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { tsr_set_error("conv2d_wgrad_tc: tensor map (dy) failed (%d)", (int)r); return TSR_ERR_CUDA; }
   }
-  p.partial = (float*)workspace;
-  p.B = B; p.H = H; p.W = W; p.Hp = H + pad; p.Vtotal = B * (H + pad);
-  p.KS = KS; p.pad = pad; p.P = pad ? 16 : 8; p.rows = 16 + 2 * pad;
-  p.Cin = Cin; p.Cout = Cout; p.cochunks = Cout / 64;
-  p.nchunks = Cin / 64; p.nxg = W / 8;
-  p.dy_stage_bytes = 16 * 1024 * p.cochunks;
-  p.stage_bytes = p.dy_stage_bytes + p.rows * p.P * 128;
-  size_t smem = 1024 + (size_t)WG_STAGES * p.stage_bytes + 256;
-  TSR_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(p.ngroups * p.nchunks, nsplit);
-  wgrad_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmx, tmdy, p);
-  TSR_CHECK_LAUNCH("conv2d_wgrad_tc");
+  if (g_desc_mode & 4) {
+    p.partial = (float*)workspace;
+    p.B = B; p.H = H; p.W = W; p.Hp = H + pad; p.Vtotal = B * (H + pad);
+    p.KS = KS; p.pad = pad; p.P = pad ? 16 : 8; p.rows = 16 + 2 * pad;
+    p.Cin = Cin; p.Cout = Cout; p.cochunks = Cout / 64;
+    p.nchunks = Cin / 64; p.nxg = W / 8;
+    p.dy_stage_bytes = 16 * 1024 * p.cochunks;
+    p.stage_bytes = p.dy_stage_bytes + p.rows * p.P * 128;
+    size_t smem = 1024 + (size_t)WG_STAGES * p.stage_bytes + 256;
+    TSR_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(p.ngroups * p.nchunks, nsplit);
+    wgrad_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmx, tmdy, p);
+    TSR_CHECK_LAUNCH("conv2d_wgrad_tc");
+  } else {
+    TSR_REQUIRE(H % 8 == 0, "conv2d_wgrad_tc: H must be a multiple of 8");
+    Wgrad2Params q;
+    q.partial = (float*)workspace;
+    q.B = B; q.H = H; q.W = W; q.KS = KS; q.pad = pad; q.P = 8 + 2 * pad;
+    q.Cin = Cin; q.Cout = Cout; q.cochunks = Cout / 64;
+    q.ngroups = p.ngroups; q.nchunks = Cin / 64;
+    q.tiles_x = W / 8; q.tiles_per_sample = (H / 8) * (W / 8);
+    q.nblocks = p.nblocks; q.blocks_per_split = p.blocks_per_split;
+    q.dy_stage_bytes = 8192 * q.cochunks;
+    q.stage_bytes = (q.dy_stage_bytes + q.P * q.P * 128 + 1023) & ~1023;
+    int ns = (int)((SMEM_LIMIT - 1024 - 512) / (size_t)q.stage_bytes);
+    if (ns > WG2_MAX_STAGES) ns = WG2_MAX_STAGES;
+    q.nstages = ns;
+    size_t smem = 1024 + (size_t)ns * q.stage_bytes + 512;
+    TSR_CUDA(cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(q.ngroups * q.nchunks, nsplit);
+    wgrad_tc2_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmx, tmdy, q);
+    TSR_CHECK_LAUNCH("conv2d_wgrad_tc2");
+  }
   long long n = (long long)taps * Cin * Cout;
   wgrad_tc_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>((const float*)workspace, dw_oihw, nsplit, taps, Cin,
                                                                     Cout, accumulate);

@@ -10,6 +10,25 @@
 
 namespace {
 
+// Second-level reduction shared by the finalising kernels: block = (32 channels, 32 partial-row lanes); returns, for
+// threadIdx.y == 0, the fixed-order double sums over all level-1 partial rows of quantities 0 and 1 of channel c.
+__device__ __forceinline__ void reduce_partials2(const float* __restrict__ partial, int nblocks, int C, int c,
+                                                 double& s0, double& s1) {
+  __shared__ double sh[2][32][33];
+  double a = 0.0, b = 0.0;
+  if (c < C)
+    for (int r = threadIdx.y; r < nblocks; r += 32) {
+      a += (double)partial[((long long)r * 2 + 0) * C + c];
+      b += (double)partial[((long long)r * 2 + 1) * C + c];
+    }
+  sh[0][threadIdx.y][threadIdx.x] = a;
+  sh[1][threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  s0 = 0.0; s1 = 0.0;
+  if (threadIdx.y == 0)
+    for (int r = 0; r < 32; ++r) { s0 += sh[0][r][threadIdx.x]; s1 += sh[1][r][threadIdx.x]; }
+}
+
 // ------------------------------------------------------------------------------------------
 // BatchNorm statistics: partial[blk][0][C] = sum x, partial[blk][1][C] = sum x^2
 // ------------------------------------------------------------------------------------------
@@ -48,14 +67,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblock
                                    long long* __restrict__ nbt, float momentum, float eps,
                                    float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && nbt) *nbt += 1;
-  if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += (double)partial[((long long)b * 2 + 0) * C + c];
-    ss += (double)partial[((long long)b * 2 + 1) * C + c];
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (c == 0 && threadIdx.y == 0 && nbt) *nbt += 1;
+  double s, ss;
+  reduce_partials2(partial, nblocks, C, c, s, ss);
+  if (c >= C || threadIdx.y != 0) return;
   double mean = s / n;
   double var = ss / n - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -156,13 +172,10 @@ __global__ void bn_bwd_partial_kernel(const Tg* __restrict__ da, int da_ld, cons
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double n,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
                                        float* __restrict__ c1, float* __restrict__ c2, int training) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, sx = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += (double)partial[((long long)b * 2 + 0) * C + c];
-    sx += (double)partial[((long long)b * 2 + 1) * C + c];
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, sx;
+  reduce_partials2(partial, nblocks, C, c, s, sx);
+  if (c >= C || threadIdx.y != 0) return;
   if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)sx : (float)sx;
   if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
   c1[c] = training ? (float)(s / n) : 0.f;
@@ -400,7 +413,7 @@ int tsr_bn_train_stats(const void* y, int y_ld, int y_bf16, long long npix, int 
   else
     bn_stats_partial_kernel<float><<<nb, th, smem, stream>>>((const float*)y, y_ld, (int)npix, C, (float*)workspace, rpb);
   TSR_CHECK_LAUNCH("bn_stats_partial");
-  bn_finalize_kernel<<<tsr_cdiv(C, 128), 128, 0, stream>>>((const float*)workspace, nb, C, (double)npix, gamma, beta,
+  bn_finalize_kernel<<<tsr_cdiv(C, 32), dim3(32, 32), 0, stream>>>((const float*)workspace, nb, C, (double)npix, gamma, beta,
                                                            running_mean, running_var, num_batches_tracked, momentum,
                                                            eps, scale, shift, save_mean, save_invstd);
   TSR_CHECK_LAUNCH("bn_finalize");
@@ -464,7 +477,7 @@ int tsr_bn_backward(const void* da, int da_ld, const void* y, int y_ld, void* dy
   else
     bn_bwd_partial_kernel<float, float><<<nb, th, smem, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
   TSR_CHECK_LAUNCH("bn_bwd_partial");
-  bn_bwd_finalize_kernel<<<tsr_cdiv(C, 128), 128, 0, stream>>>(partial, nb, C, (double)npix, dgamma, dbeta, accumulate, c1, c2, training);
+  bn_bwd_finalize_kernel<<<tsr_cdiv(C, 32), dim3(32, 32), 0, stream>>>(partial, nb, C, (double)npix, dgamma, dbeta, accumulate, c1, c2, training);
   TSR_CHECK_LAUNCH("bn_bwd_finalize");
   int grid = ew_grid(npix * (C / 4));
   if (act_bf16)
