@@ -106,6 +106,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+// one leader lane of a fully converged warp (the same lane every time for a full mask)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major / MN-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -117,6 +123,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes,
   d |= 1ull << 46;
   if (mode == 1) d |= (uint64_t)((addr >> 7) & 7) << 49;
   d |= 2ull << 61;
+  return d;
+}
+
+// The issuing thread is a single lane: every ALU instruction in its loop costs ~4 cycles of dependent issue, so the
+// descriptors are split into a constant high word and a low word that only ever needs an integer add.
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo_bytes) {
+  return ((addr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
 
@@ -227,42 +247,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop converged (keeps the address math in uniform registers);
+    // one elected lane issues the tcgen05 instructions =====
+    {
       constexpr uint32_t idesc = make_idesc(128, N, 0, 0);
-      const uint32_t sbo_a = (uint32_t)p.P * 128u;
+      const uint32_t a_hi = desc_hi((uint32_t)p.P * 128u), b_hi = desc_hi(1024u);
+      const uint32_t row_units = (uint32_t)p.P * 8u;            // one halo row, in 16-byte descriptor units
+      const uint32_t mt_units = 16u * row_units;                 // next M-tile = 16 halo rows further
+      const uint32_t wrap_units = row_units - (uint32_t)p.KS * 8u;
       int it = 0, ac = 0, lb = 0;
       for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x, ++lb) {
         const int buf = lb & 1;
         mbar_wait(t_empty(buf), ((lb >> 1) & 1) ^ 1);     // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t acc0 = tmem_base + buf * ACC_COLS;
+        uint32_t first = 0u;                              // 0 only for the very first MMA of the block
         for (int c = 0; c < p.nchunks; ++c, ++ac) {
           const int slot = ac % NA_SLOTS;
           mbar_wait(a_full(slot), (ac / NA_SLOTS) & 1);
           tc_fence_after();
-          const uint32_t a0 = a_base + slot * a_slot_bytes;
+          uint32_t a_lo = desc_lo(a_base + slot * a_slot_bytes, 16u);   // window start of tap (0,0), M-tile 0
+          int kx = 0;
           for (int t = 0; t < taps; ++t, ++it) {
             const int st = it % NB;
             mbar_wait(b_full(st), (it / NB) & 1);
             tc_fence_after();
-            const int ky = t / p.KS, kx = t - ky * p.KS;
-            const uint32_t b0 = b_base + st * B_STAGE;
+            const uint32_t b_lo = desc_lo(b_base + st * B_STAGE, 16u);
+            if (elect_one()) {
 #pragma unroll
-            for (int mt = 0; mt < T_TILES; ++mt) {
-              const uint32_t arow = a0 + (uint32_t)((mt * 16 + ky) * p.P + kx) * 128u;
+              for (int mt = 0; mt < T_TILES; ++mt) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t ad = make_desc(arow + kk * 32u, sbo_a, 16u, p.desc_mode & 1);
-                const uint64_t bd = make_desc(b0 + kk * 32u, 1024u, 16u, 0);
-                umma_bf16(acc0 + mt * N, ad, bd, idesc, (c | t | kk) != 0 ? 1u : 0u);
+                for (int kk = 0; kk < 4; ++kk) {
+                  umma_bf16(acc0 + mt * N, desc_join(a_lo + mt * mt_units + kk * 2u, a_hi), desc_join(b_lo + kk * 2u, b_hi),
+                            idesc, (first | (uint32_t)kk) ? 1u : 0u);
+                }
               }
+              umma_commit(b_empty(st));
             }
-            umma_commit(b_empty(st));
+            __syncwarp();
+            first = 1u;
+            // next tap: one pixel to the right, or wrap to the start of the next halo row
+            a_lo += 8u;
+            if (++kx == p.KS) { kx = 0; a_lo += wrap_units; }
           }
-          umma_commit(a_empty(slot));
+          if (elect_one()) umma_commit(a_empty(slot));
+          __syncwarp();
         }
-        umma_commit(t_full(buf));
+        if (elect_one()) umma_commit(t_full(buf));
+        __syncwarp();
       }
     }
   } else {
@@ -592,29 +624,42 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc(128, 64, 1, 1);
       const uint32_t lbo_a = p.cochunks == 2 ? 8192u : 0u;     // Cout = 64: second MN atom aliases the first
-      const uint32_t sbo_x = (uint32_t)p.P * 128u;
+      const uint32_t a_hi = desc_hi(1024u), b_hi = desc_hi((uint32_t)p.P * 128u);
+      const uint32_t row_units = (uint32_t)p.P * 8u;
+      const uint32_t wrap_units = row_units - (uint32_t)p.KS * 8u;
+      const uint32_t tap_start = (uint32_t)((tap0 / p.KS) * p.P + tap0 % p.KS) * 8u;
+      const int kx_start = tap0 % p.KS;
+      uint32_t first = 0u;
       for (int i = 0; i < nblk; ++i) {
         const int st = i % NS;
         mbar_wait(full(st), (i / NS) & 1);
         tc_fence_after();
         const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
-        const uint32_t xs0 = dy0 + (uint32_t)p.dy_stage_bytes;
+        const uint32_t a_lo = desc_lo(dy0, lbo_a);
+        uint32_t b_lo = desc_lo(dy0 + (uint32_t)p.dy_stage_bytes, 0u) + tap_start;
+        int kx = kx_start;
+        const bool leader = elect_one();
         for (int g = 0; g < ntap; ++g) {
-          const int t = tap0 + g;
-          const int ky = t / p.KS, kx = t - ky * p.KS;
+          if (leader) {
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            const uint64_t ad = make_desc(dy0 + (uint32_t)s * 2048u, 1024u, lbo_a, 0);
-            const uint64_t bd = make_desc(xs0 + (uint32_t)((2 * s + ky) * p.P + kx) * 128u, sbo_x, 0u, 0);
-            umma_bf16(tmem_base + g * 64, ad, bd, idesc, (i | s) != 0 ? 1u : 0u);
+            for (int s = 0; s < 4; ++s) {
+              // K-step s: dy rows 2s, 2s+1 (2 KB apart per step); x window rows 2s+ky, 2s+1+ky
+              umma_bf16(tmem_base + g * 64, desc_join(a_lo + s * 128u, a_hi), desc_join(b_lo + s * 2u * row_units, b_hi), idesc,
+                        (first | (uint32_t)s) ? 1u : 0u);
+            }
           }
+          b_lo += 8u;
+          if (++kx == p.KS) { kx = 0; b_lo += wrap_units; }
         }
-        umma_commit(empty(st));
+        first = 1u;
+        if (leader) umma_commit(empty(st));
+        __syncwarp();
       }
-      umma_commit(tmem_full);
+      if (elect_one()) umma_commit(tmem_full);
+      __syncwarp();
     }
   } else if (warp >= 3) {
     const int q = warp & 3;
