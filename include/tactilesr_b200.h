@@ -1,0 +1,163 @@
+/*
+ * tactilesr_b200 -- C ABI of libtactilesr_b200.so (sm_100a only).
+ *
+ * The reference (wmtlab/tactileSR) has no FFI: its hot path is `nn.Module.forward` + autograd calling ATen / cuDNN /
+ * cuBLAS.  The drop-in boundary is therefore the Python module protocol (the modules under tactilesr_b200/model/ keep the reference's
+ * classes, constructor arguments and state_dict layout); *underneath* it every operation of the path is one of the
+ * entry points below.  Each declaration cites the reference call it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; the library never allocates or frees, never synchronises, and
+ *     launches on the given `stream` only;
+ *   - activations are NHWC: `x` points at the first of `C` consecutive channels of pixel 0 and `ld` is the channel
+ *     count of the underlying buffer (so channel slices of a concat buffer are addressed without a copy);
+ *   - `*_bf16` flags select the storage type of an activation operand: 0 = float, 1 = __nv_bfloat16;
+ *   - weights and their gradients keep PyTorch's OIHW fp32 layout (`state_dict()` compatible); packed copies are made by
+ *     tsr_pack_conv_weight_*;
+ *   - return value 0 = success; otherwise an error code (1 bad argument, 2 CUDA error, 3 unsupported, 4 workspace too
+ *     small) with a message in tsr_last_error().  There is no CPU fallback and no library (cuDNN/cuBLAS) fallback.
+ *   - `*_workspace` functions return the scratch bytes the matching call needs.
+ */
+#ifndef TACTILESR_B200_H
+#define TACTILESR_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* tsr_stream_t; /* == cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------------------------- */
+const char* tsr_last_error(void);
+int tsr_version(void);
+int tsr_check_device(void);               /* 0 iff the current device is compute capability 10.x */
+long long tsr_launch_count(void);         /* kernels launched by this library since the last reset */
+void tsr_launch_count_reset(void);
+
+/* ---- fp32-accurate convolutions (FFMA implicit GEMM) -------------------------------------------------------- */
+/* nn.Conv2d weights (model/tactileSR_model.py:41,47,53,168,174,180,186,191,219,220) -> [tap][ci][co] (forward) and
+ * [flipped tap][co][ci] (data gradient); either output may be NULL. */
+int tsr_pack_conv_weight_f32(const float* w_oihw, float* w_fwd, float* w_dgrad, int Cout, int Cin, int KS,
+                             tsr_stream_t stream);
+/* out = [relu]( conv_KSxKS(in, w_packed) [+ bias] [+ residual] ), same padding.  Forward of nn.Conv2d (+ the fused
+ * `output += x; relu` of MSRB.forward :204-206 and ResBlock.forward :222-225); with w_dgrad it is the data gradient.
+ * flags bit0 = ReLU.  Cin % 16 == 0, Cout % 64 == 0, KS in {1,3,5}. */
+int tsr_conv2d_f32(const float* in, int in_ld, const float* w_packed, const float* bias, const float* residual,
+                   int res_ld, float* out, int out_ld, int B, int H, int W, int Cin, int Cout, int KS, int flags,
+                   tsr_stream_t stream);
+size_t tsr_conv2d_wgrad_f32_workspace(int B, int H, int W, int Cin, int Cout, int KS);
+/* dw_oihw (+)= sum_pix in[pix+shift] (x) dout[pix]: autograd weight gradient of nn.Conv2d (cpu/trainer.py:353);
+ * deterministic two-level (split-K, then fixed-order) reduction. */
+int tsr_conv2d_wgrad_f32(const float* in, int in_ld, const float* dout, int dout_ld, float* dw_oihw, void* workspace,
+                         size_t ws_bytes, int B, int H, int W, int Cin, int Cout, int KS, int accumulate,
+                         tsr_stream_t stream);
+size_t tsr_colsum_workspace(long long npix, int C);
+/* out[c] (+)= sum_pix x[pix][c]: bias gradient of nn.Conv2d. */
+int tsr_colsum(const void* x, int ld, int x_bf16, long long npix, int C, float* out, void* workspace, size_t ws_bytes,
+               int accumulate, tsr_stream_t stream);
+
+/* ---- head / tail convolutions (memory bound) ------------------------------------------------------------------ */
+/* nn.Upsample(scale_factor=sf, bilinear, align_corners=False) + nn.Conv2d(3 -> 64, 3x3, no bias) [+ ReLU]
+ * (model/tactileSR_model.py:35-37, 60-62; TactileSRCNN :107 + :122).  x: NCHW fp32 (B, *, 4, 4), 3 channels starting
+ * at `x`, sample stride x_bstride floats. */
+int tsr_head_fwd(const float* x, long long x_bstride, const float* w_oihw, void* out, int out_ld, int out_bf16, int B,
+                 int sf, int relu, tsr_stream_t stream);
+size_t tsr_head_wgrad_workspace(int B);
+int tsr_head_wgrad(const float* x, long long x_bstride, const void* dout, int dout_ld, int dout_bf16, float* dw_oihw,
+                   void* workspace, size_t ws_bytes, int B, int sf, int accumulate, tsr_stream_t stream);
+/* nn.Conv2d(Cin -> 1, 3x3, no bias) + ReLU (model/tactileSR_model.py:55-56, :125-126); out is (B,1,H,W) fp32. */
+int tsr_tail_fwd(const void* in, int in_ld, int in_bf16, const float* w_oihw, float* out, int B, int H, int W, int Cin,
+                 int relu, tsr_stream_t stream);
+int tsr_tail_dgrad(const float* dout, const float* out_act, const float* w_oihw, void* din, int din_ld, int din_bf16,
+                   int B, int H, int W, int Cin, int relu, tsr_stream_t stream);
+size_t tsr_tail_wgrad_workspace(int B, int H, int W, int Cin);
+int tsr_tail_wgrad(const void* in, int in_ld, int in_bf16, const float* dout, const float* out_act, float* dw_oihw,
+                   void* workspace, size_t ws_bytes, int B, int H, int W, int Cin, int relu, int accumulate,
+                   tsr_stream_t stream);
+
+/* ---- BatchNorm / ReLU / layout --------------------------------------------------------------------------------- */
+size_t tsr_bn_workspace(long long npix, int C);
+/* nn.BatchNorm2d in training mode (model/tactileSR_model.py:38,42,48,169,175,181,187): batch mean / biased variance of
+ * y -> scale, shift, saved mean / invstd; running_mean / running_var (momentum, unbiased variance) and
+ * num_batches_tracked are updated in place when non-NULL. */
+int tsr_bn_train_stats(const void* y, int y_ld, int y_bf16, long long npix, int C, const float* gamma,
+                       const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
+                       float momentum, float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
+                       void* workspace, size_t ws_bytes, tsr_stream_t stream);
+/* eval mode: scale / shift from the running statistics. */
+int tsr_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, float* scale, float* shift, float* save_mean,
+                       float* save_invstd, tsr_stream_t stream);
+/* out = [relu](y * scale + shift): BatchNorm2d + nn.ReLU(True), written into a channel slice (replaces torch.cat
+ * :74, :81, :200, :203). */
+int tsr_bn_apply(const void* y, int y_ld, int y_bf16, const float* scale, const float* shift, void* out, int out_ld,
+                 int out_bf16, long long npix, int C, int relu, tsr_stream_t stream);
+size_t tsr_bn_backward_workspace(long long npix, int C);
+/* autograd backward of BatchNorm2d(+ReLU): da -> dy, dgamma, dbeta (deterministic two-level reductions). */
+int tsr_bn_backward(const void* da, int da_ld, const void* y, int y_ld, void* dy, int dy_ld, int act_bf16,
+                    const float* scale, const float* shift, const float* save_mean, const float* save_invstd,
+                    float* dgamma, float* dbeta, int accumulate, long long npix, int C, int relu, int training,
+                    void* workspace, size_t ws_bytes, tsr_stream_t stream);
+/* dz = da * [a > 0] for a ReLU fused into a conv epilogue. */
+int tsr_relu_backward(const void* da, int da_ld, const void* a, int a_ld, void* dz, int dz_ld, int act_bf16,
+                      long long npix, int C, tsr_stream_t stream);
+int tsr_copy_channels(const void* x, int x_ld, int x_bf16, void* out, int out_ld, int out_bf16, long long npix, int C,
+                      tsr_stream_t stream);
+int tsr_nchw_to_nhwc(const float* x, void* out, int out_ld, int out_bf16, int B, int C, int HW, tsr_stream_t stream);
+int tsr_nhwc_to_nchw(const void* x, int x_ld, int x_bf16, float* out, int B, int C, int HW, tsr_stream_t stream);
+
+/* ---- loss / optimizer ------------------------------------------------------------------------------------------- */
+size_t tsr_mse_hr_workspace(void);
+/* train/tactileSR_train.py:44-45,49 fused: HR = bilinear_resize(hr_raw / scale_num, (H,W)); *loss = mean((out-HR)^2);
+ * dout = 2 (out - HR) / N * grad_mul (dout may be NULL). */
+int tsr_mse_hr_loss(const float* out, const float* hr_raw, float scale_num, int B, int H, int W, int Hin, int Win,
+                    float* loss, float* dout, float grad_mul, void* workspace, size_t ws_bytes, tsr_stream_t stream);
+/* torch.optim.Adam step (coupled L2 weight decay, no amsgrad; train/tactileSR_train.py:212, tPSFNet_train.py:201)
+ * over a flat fp32 buffer of n elements; `step` is the 1-based step count, lr a host scalar read every call. */
+int tsr_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, long long step, float grad_scale, tsr_stream_t stream);
+
+/* ---- tPSFNet ----------------------------------------------------------------------------------------------------- */
+/* C[m][n] = act(sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] + bias[n]); act 0 none, 1 relu, 2 softplus. */
+int tsr_sgemm_strided(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn,
+                      float* C, long long ldc, int M, int N, int K, const float* bias, int act, int accumulate,
+                      tsr_stream_t stream);
+/* nn.Linear (+ReLU / Softplus) of MLP_layer (model/tPSFNet.py:26-36) and its backward. */
+int tsr_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int N, int K, int act,
+                   tsr_stream_t stream);
+int tsr_linear_bwd(const float* dy, const float* out, const float* x, const float* w, float* dpre, float* dw, float* db,
+                   float* dx, int M, int N, int K, int act, int accumulate, tsr_stream_t stream);
+/* The per-sample loop of tPSFNet.forward (model/tPSFNet.py:118-125): tactilePSF :78-83, depth2tactile :85-100 (dense
+ * 99x99 correlation + second-max fill) and degradation_process :129-141, fused, one CTA per sample.
+ * alphaBeta (B,3), depth (B,100,100) -> HR (B,100,100), LRd (B,16), psf (B,99,99; may be NULL). */
+int tsr_psf_forward(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, int B,
+                    tsr_stream_t stream);
+/* its backward: d alphaBeta (B,3) from dLRd (B,16), dHR (B,100,100), dpsf (B,99,99) -- each may be NULL (= 0). */
+int tsr_psf_backward(const float* alphaBeta, const float* depth, const float* HR, const float* dLRd, const float* dHR,
+                     const float* dpsf, float* dalphaBeta, int B, tsr_stream_t stream);
+
+/* ---- tensor-core convolutions (tcgen05 / TMEM / TMA, bf16 operands, fp32 accumulate) ------------------------------ */
+/* OIHW fp32 -> bf16 [ci chunk][tap][Cout][64] tiles in the SWIZZLE_128B shared-memory image (forward) and the flipped /
+ * transposed set for the data gradient.  Cin, Cout % 64 == 0. */
+int tsr_pack_conv_weight_bf16(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int KS,
+                              tsr_stream_t stream);
+size_t tsr_conv2d_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS);
+/* bf16 NHWC convolution, same semantics as tsr_conv2d_f32 (bias fp32, residual / out bf16).  W % 8 == 0. */
+int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* bias, const void* residual, int res_ld,
+                  void* out, int out_ld, int B, int H, int W, int Cin, int Cout, int KS, int flags, void* workspace,
+                  size_t ws_bytes, tsr_stream_t stream);
+size_t tsr_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS);
+/* weight gradient (fp32 OIHW) of bf16 activations / gradients; bit-deterministic.  H, W % 8 == 0, Cout in {64,128}. */
+int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
+                        size_t ws_bytes, int B, int H, int W, int Cin, int Cout, int KS, int accumulate,
+                        tsr_stream_t stream);
+/* experiment switches of the tensor-core kernels (see csrc/conv_tc.cu); 0 = production configuration. */
+void tsr_set_tc_desc_mode(int mode);
+int tsr_get_tc_desc_mode(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TACTILESR_B200_H */

@@ -63,7 +63,6 @@ SIGNATURES = {
     "tsr_conv2d_tc_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),
     "tsr_conv2d_wgrad_tc": (_I, [_P, _I, _P, _I, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tsr_conv2d_wgrad_tc_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),
-    "tsr_tc_selftest": (_I, [_I, _P, _P, _P]),
     "tsr_set_tc_desc_mode": (None, [_I]),
     "tsr_get_tc_desc_mode": (_I, []),
 }

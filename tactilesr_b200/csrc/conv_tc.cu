@@ -933,6 +933,5 @@ int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld
   return TSR_OK;
 }
 
-int tsr_tc_selftest(int, void*, void*, cudaStream_t) { return TSR_OK; }
 
 }  // extern "C"
