@@ -352,17 +352,21 @@ head_fwd_kernel(const float* __restrict__ x, long long x_bstride, const float* _
   }
 }
 
-// head weight gradient, level 1: one partial [27][64] per CTA, CTAs stride over samples
+// head weight gradient, level 1: one partial [27][64] per CTA, CTAs stride over samples.
+// 1024 threads = 64 output channels x 16 pixel lanes; a warp shares its pixel (the upsampled value is a shared-memory
+// broadcast) and reads 32 consecutive channels of dout (coalesced); each thread keeps all 27 (tap, axis) sums.
 template <typename GT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 head_wgrad_kernel(const float* __restrict__ x, long long x_bstride, const GT* __restrict__ dout, int dout_ld,
                   float* __restrict__ partial, int B, int sf) {
   extern __shared__ float smem[];
-  float* xs = smem;
-  float* up = xs + 48;
+  float* xs = smem;                       // 48
+  float* up = xs + 48;                    // (H+2)^2 * 3, later reused for the lane reduction
   const int H = 4 * sf, P = H + 2;
-  const int co = threadIdx.x & 63, qb = threadIdx.x >> 6;   // q = qb + 4j, j < 7 (27 taps*chan)
-  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int co = threadIdx.x & 63, pl = threadIdx.x >> 6;   // pixel lane 0..15
+  float acc[27];
+#pragma unroll
+  for (int q = 0; q < 27; ++q) acc[q] = 0.f;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
     if (threadIdx.x < 48) xs[threadIdx.x] = x[(long long)b * x_bstride + threadIdx.x];
@@ -370,23 +374,33 @@ head_wgrad_kernel(const float* __restrict__ x, long long x_bstride, const GT* __
     build_upsampled(xs, up, sf);
     __syncthreads();
     const GT* d = dout + (long long)b * H * H * dout_ld + co;
-    for (int p = 0; p < H * H; ++p) {
-      float g = ldf(d + (long long)p * dout_ld);
-      int y = p / H, xx = p - y * H;
+    for (int p = pl; p < H * H; p += 16) {
+      const float g = ldf(d + (long long)p * dout_ld);
+      const int y = p / H, xx = p - y * H;
+      const float* u = up + (y * P + xx) * 3;
 #pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        int q = qb + 4 * j;
-        if (q < 27) {
-          int tap = q / 3, c = q - tap * 3;
-          acc[j] = fmaf(up[((y + tap / 3) * P + xx + tap % 3) * 3 + c], g, acc[j]);
-        }
+      for (int tap = 0; tap < 9; ++tap) {
+        const float* ut = u + ((tap / 3) * P + tap % 3) * 3;
+        acc[tap * 3 + 0] = fmaf(ut[0], g, acc[tap * 3 + 0]);
+        acc[tap * 3 + 1] = fmaf(ut[1], g, acc[tap * 3 + 1]);
+        acc[tap * 3 + 2] = fmaf(ut[2], g, acc[tap * 3 + 2]);
       }
     }
   }
+  // fixed-order reduction over the 16 pixel lanes, 27 values at a time through shared memory
+  __syncthreads();
+  float* red = up;                        // needs 16*64*27 floats = 110 KB?  no: reduce one q at a time (1024 floats)
 #pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    int q = qb + 4 * j;
-    if (q < 27) partial[((long long)blockIdx.x * 27 + q) * 64 + co] = acc[j];
+  for (int q = 0; q < 27; ++q) {
+    red[pl * 64 + co] = acc[q];
+    __syncthreads();
+    if (pl == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int l = 0; l < 16; ++l) s += red[l * 64 + co];
+      partial[((long long)blockIdx.x * 27 + q) * 64 + co] = s;
+    }
+    __syncthreads();
   }
 }
 __global__ void head_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ dw,
@@ -664,13 +678,15 @@ int tsr_head_wgrad(const float* x, long long x_bstride, const void* dout, int do
   TSR_REQUIRE(sf >= 1 && sf <= 24, "head_wgrad: scale_factor %d unsupported", sf);
   int grid = B < 296 ? B : 296;
   TSR_REQUIRE(ws_bytes >= (size_t)grid * 27 * 64 * sizeof(float), "head_wgrad: workspace too small");
-  size_t smem = (size_t)(48 + (4 * sf + 2) * (4 * sf + 2) * 3) * sizeof(float);
+  size_t up_floats = (size_t)(4 * sf + 2) * (4 * sf + 2) * 3;
+  if (up_floats < 1024) up_floats = 1024;
+  size_t smem = (48 + up_floats) * sizeof(float);
   if (dout_bf16) {
     TSR_CUDA(cudaFuncSetAttribute(head_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_wgrad_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(x, x_bstride, (const __nv_bfloat16*)dout, dout_ld, (float*)workspace, B, sf);
+    head_wgrad_kernel<__nv_bfloat16><<<grid, 1024, smem, stream>>>(x, x_bstride, (const __nv_bfloat16*)dout, dout_ld, (float*)workspace, B, sf);
   } else {
     TSR_CUDA(cudaFuncSetAttribute(head_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_wgrad_kernel<float><<<grid, 256, smem, stream>>>(x, x_bstride, (const float*)dout, dout_ld, (float*)workspace, B, sf);
+    head_wgrad_kernel<float><<<grid, 1024, smem, stream>>>(x, x_bstride, (const float*)dout, dout_ld, (float*)workspace, B, sf);
   }
   TSR_CHECK_LAUNCH("head_wgrad");
   head_wgrad_reduce_kernel<<<tsr_cdiv(27 * 64, 256), 256, 0, stream>>>((const float*)workspace, grid, dw_oihw, accumulate);

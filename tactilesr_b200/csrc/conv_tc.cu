@@ -27,7 +27,7 @@ namespace {
 constexpr int FLAG_RELU = 1;
 constexpr int T_TILES = 2;          // M-tiles (128 pixels each) per CTA
 constexpr int NB_STAGES = 3;        // weight ring depth
-constexpr int NA_SLOTS = 2;         // activation chunk slots
+constexpr int MAX_NA = 8;           // activation chunk slots (2 for 3x3 / 5x5, more for the bandwidth-bound 1x1)
 constexpr int NUM_THREADS = 224;
 
 // experiment switches (env TSR_TC_MODE or tsr_set_tc_desc_mode): bit0 = descriptor base_offset from the address
@@ -158,6 +158,7 @@ struct ConvParams {
   int nchunks, nxg, flags, desc_mode;
   int w_tile_elems;              // elements between consecutive (chunk, tap) weight tiles = Cout_total * 64
   int nblocks, nb_stages;        // CTA blocks (persistent loop), depth of the weight ring (<= MAX_NB)
+  int na_slots;                  // activation chunk slots (<= MAX_NA)
 };
 
 constexpr int MAX_NB = 8;
@@ -176,17 +177,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_slot_bytes = ((uint32_t)p.rows * p.P * 128u + 1023u) & ~1023u;
   const uint32_t a_base = base;
+  const int NA_SLOTS = p.na_slots;
   const uint32_t b_base = a_base + NA_SLOTS * a_slot_bytes;
   constexpr uint32_t B_STAGE = N * 128u;
   const int NB = p.nb_stages;
   const uint32_t bar_base = b_base + NB * B_STAGE;
   auto a_full = [&](int i) { return bar_base + 8u * i; };
-  auto a_empty = [&](int i) { return bar_base + 8u * (NA_SLOTS + i); };
-  auto b_full = [&](int i) { return bar_base + 8u * (2 * NA_SLOTS + i); };
-  auto b_empty = [&](int i) { return bar_base + 8u * (2 * NA_SLOTS + MAX_NB + i); };
-  auto t_full = [&](int i) { return bar_base + 8u * (2 * NA_SLOTS + 2 * MAX_NB + i); };
-  auto t_empty = [&](int i) { return bar_base + 8u * (2 * NA_SLOTS + 2 * MAX_NB + 2 + i); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * NA_SLOTS + 2 * MAX_NB + 4);
+  auto a_empty = [&](int i) { return bar_base + 8u * (MAX_NA + i); };
+  auto b_full = [&](int i) { return bar_base + 8u * (2 * MAX_NA + i); };
+  auto b_empty = [&](int i) { return bar_base + 8u * (2 * MAX_NA + MAX_NB + i); };
+  auto t_full = [&](int i) { return bar_base + 8u * (2 * MAX_NA + 2 * MAX_NB + i); };
+  auto t_empty = [&](int i) { return bar_base + 8u * (2 * MAX_NA + 2 * MAX_NB + 2 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_NA + 2 * MAX_NB + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -211,8 +213,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ===== A producer: one TMA box (64 ch x (8+2pad) px x 1 row) per virtual halo row =====
-    if (lane == 0) {
+    // ===== A producer: one TMA box (64 ch x (8+2pad) px x 1 row) per virtual halo row, issued by all 32 lanes in
+    // parallel (a single lane issuing 36 boxes per chunk was the bottleneck of the short 64-channel main loops);
+    // the 1x1 conv has no halo and its rows are contiguous across samples, so one 32-row box per chunk suffices =====
+    {
       const uint32_t row_bytes = (uint32_t)(8 + 2 * p.pad) * 128u;
       int ac = 0;
       for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x) {
@@ -220,15 +224,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
         const int x0 = xg * 8, v0 = vb * (16 * T_TILES);
         for (int c = 0; c < p.nchunks; ++c, ++ac) {
           const int slot = ac % NA_SLOTS;
-          mbar_wait(a_empty(slot), ((ac / NA_SLOTS) & 1) ^ 1);
-          mbar_expect_tx(a_full(slot), row_bytes * p.rows);
           const uint32_t dst0 = a_base + slot * a_slot_bytes;
-          for (int r = 0; r < p.rows; ++r) {
-            const int vr = v0 - p.pad + r;
-            int n = 0, y = p.H;   // out-of-bounds row => TMA zero fill
-            if (vr >= 0 && vr < p.Vtotal) { n = vr / p.Hp; y = vr - n * p.Hp; }
-            tma_load_4d(dst0 + (uint32_t)r * p.P * 128u, &tmap, c * 64, x0 - p.pad, y, n, a_full(slot));
+          if (lane == 0) {
+            mbar_wait(a_empty(slot), ((ac / NA_SLOTS) & 1) ^ 1);
+            mbar_expect_tx(a_full(slot), row_bytes * p.rows);
           }
+          __syncwarp();
+          if (p.pad == 0) {
+            if (lane == 0) tma_load_4d(dst0, &tmap, c * 64, x0, v0, 0, a_full(slot));
+          } else {
+            for (int r = lane; r < p.rows; r += 32) {
+              const int vr = v0 - p.pad + r;
+              int n = 0, y = p.H;   // out-of-bounds row => TMA zero fill
+              if (vr >= 0 && vr < p.Vtotal) { n = vr / p.Hp; y = vr - n * p.Hp; }
+              tma_load_4d(dst0 + (uint32_t)r * p.P * 128u, &tmap, c * 64, x0 - p.pad, y, n, a_full(slot));
+            }
+          }
+          __syncwarp();
         }
       }
     }
@@ -741,9 +753,9 @@ int num_sms() {
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 // shared-memory plan of the forward kernel: A slots fixed by the geometry, the weight ring takes what is left
-void conv_smem_plan(int N, int rows, int P, size_t* smem, int* nb) {
+void conv_smem_plan(int N, int rows, int P, int na, size_t* smem, int* nb) {
   size_t a = ((size_t)rows * P * 128 + 1023) & ~(size_t)1023;
-  size_t fixed = 1024 + NA_SLOTS * a + 512;
+  size_t fixed = 1024 + na * a + 512;
   int stages = (int)((SMEM_LIMIT - fixed) / ((size_t)N * 128));
   if (stages > MAX_NB) stages = MAX_NB;
   *nb = stages;
@@ -753,7 +765,8 @@ void conv_smem_plan(int N, int rows, int P, size_t* smem, int* nb) {
 template <int N>
 int launch_conv(const CUtensorMap& tmap, ConvParams p, cudaStream_t stream) {
   size_t smem;
-  conv_smem_plan(N, p.rows, p.P, &smem, &p.nb_stages);
+  p.na_slots = p.KS == 1 ? 5 : 2;
+  conv_smem_plan(N, p.rows, p.P, p.na_slots, &smem, &p.nb_stages);
   if (p.nb_stages < 2) { tsr_set_error("conv2d_tc: shared memory plan infeasible"); return TSR_ERR_UNSUPPORTED; }
   TSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = p.nblocks < num_sms() ? p.nblocks : num_sms();
@@ -804,6 +817,10 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
   cuuint64_t gstr[3] = {(cuuint64_t)in_ld * 2, (cuuint64_t)W * in_ld * 2, (cuuint64_t)H * W * in_ld * 2};
   cuuint32_t box[4] = {64, (cuuint32_t)(8 + 2 * pad), 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (pad == 0) {   // no halo: rows of consecutive samples are contiguous => one (B*H)-row dimension, 32-row boxes
+    gdim[2] = (cuuint64_t)H * B; gdim[3] = 1;
+    box[2] = 16 * T_TILES;
+  }
   CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -369,9 +369,169 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// 16-byte-per-thread variants used when every activation operand has the same storage type
+// (the engine's case): 8 bf16 / 4 fp32 channels per access.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_stats_partial_v_kernel(const T* __restrict__ x, int ld, int npix, int C, float* __restrict__ partial,
+                          int rows_per_block) {
+  constexpr int N = V16<T>::N;
+  extern __shared__ float smf[];
+  const int qn = C / N, lanes = blockDim.x / qn;
+  const int q = threadIdx.x % qn, lane = threadIdx.x / qn;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, npix);
+  float s[N], ss[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+  if (lane < lanes)
+    for (int r = r0 + lane; r < r1; r += lanes) {
+      float v[N];
+      V16<T>::load(x + (long long)r * ld + q * N, v);
+#pragma unroll
+      for (int i = 0; i < N; ++i) { s[i] += v[i]; ss[i] = fmaf(v[i], v[i], ss[i]); }
+    }
+  // smem layout: [lane][2][C]
+  if (lane < lanes) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      smf[(lane * 2 + 0) * C + q * N + i] = s[i];
+      smf[(lane * 2 + 1) * C + q * N + i] = ss[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l) a += smf[l * 2 * C + c];
+    partial[(long long)blockIdx.x * 2 * C + c] = a;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_apply_v_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ scale, const float* __restrict__ shift,
+                  T* __restrict__ out, int out_ld, long long npix, int C, int relu) {
+  constexpr int N = V16<T>::N;
+  const int qn = C / N;
+  const long long total = npix * qn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % qn);
+    const long long p = i / qn;
+    float v[N];
+    V16<T>::load(x + p * x_ld + q * N, v);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      v[k] = fmaf(v[k], __ldg(scale + q * N + k), __ldg(shift + q * N + k));
+      if (relu) v[k] = fmaxf(v[k], 0.f);
+    }
+    V16<T>::store(out + p * out_ld + q * N, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_partial_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict__ y, int y_ld,
+                        const float* __restrict__ scale, const float* __restrict__ shift,
+                        const float* __restrict__ mean, const float* __restrict__ invstd, int npix, int C, int relu,
+                        float* __restrict__ partial, int rows_per_block) {
+  constexpr int N = V16<T>::N;
+  extern __shared__ float smf[];
+  const int qn = C / N, lanes = blockDim.x / qn;
+  const int q = threadIdx.x % qn, lane = threadIdx.x / qn;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, npix);
+  float sc[N], sh[N], mu[N], is[N], s[N], sx[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    sc[i] = scale[q * N + i]; sh[i] = shift[q * N + i]; mu[i] = mean[q * N + i]; is[i] = invstd[q * N + i];
+    s[i] = 0.f; sx[i] = 0.f;
+  }
+  if (lane < lanes)
+    for (int r = r0 + lane; r < r1; r += lanes) {
+      float g[N], v[N];
+      V16<T>::load(da + (long long)r * da_ld + q * N, g);
+      V16<T>::load(y + (long long)r * y_ld + q * N, v);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        if (relu && !(fmaf(v[i], sc[i], sh[i]) > 0.f)) g[i] = 0.f;
+        s[i] += g[i];
+        sx[i] = fmaf(g[i], (v[i] - mu[i]) * is[i], sx[i]);
+      }
+    }
+  if (lane < lanes) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      smf[(lane * 2 + 0) * C + q * N + i] = s[i];
+      smf[(lane * 2 + 1) * C + q * N + i] = sx[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l) a += smf[l * 2 * C + c];
+    partial[(long long)blockIdx.x * 2 * C + c] = a;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict__ y, int y_ld,
+                      const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                      const float* __restrict__ invstd, const float* __restrict__ c1, const float* __restrict__ c2,
+                      T* __restrict__ dy, int dy_ld, long long npix, int C, int relu) {
+  constexpr int N = V16<T>::N;
+  const int qn = C / N;
+  const long long total = npix * qn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % qn);
+    const long long p = i / qn;
+    float g[N], v[N], o[N];
+    V16<T>::load(da + p * da_ld + q * N, g);
+    V16<T>::load(y + p * y_ld + q * N, v);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const int c = q * N + k;
+      const float sc = __ldg(scale + c);
+      if (relu && !(fmaf(v[k], sc, __ldg(shift + c)) > 0.f)) g[k] = 0.f;
+      o[k] = sc * (g[k] - __ldg(c1 + c) - (v[k] - __ldg(mean + c)) * __ldg(invstd + c) * __ldg(c2 + c));
+    }
+    V16<T>::store(dy + p * dy_ld + q * N, o);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+relu_bwd_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict__ a, int a_ld, T* __restrict__ dz, int dz_ld,
+                  long long npix, int C) {
+  constexpr int N = V16<T>::N;
+  const int qn = C / N;
+  const long long total = npix * qn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % qn);
+    const long long p = i / qn;
+    float g[N], v[N];
+    V16<T>::load(da + p * da_ld + q * N, g);
+    V16<T>::load(a + p * a_ld + q * N, v);
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if (!(v[k] > 0.f)) g[k] = 0.f;
+    V16<T>::store(dz + p * dz_ld + q * N, g);
+  }
+}
+
+inline int redv_threads(int C, int N) {
+  int qn = C / N;
+  int t = (256 / qn) * qn;
+  return t < qn ? qn : t;
+}
+
 inline int ew_grid(long long total) {
   long long g = (total + 255) / 256;
-  if (g > 148 * 16) g = 148 * 16;
+  if (g > 148 * 32) g = 148 * 32;
   if (g < 1) g = 1;
   return (int)g;
 }
@@ -407,11 +567,18 @@ int tsr_bn_train_stats(const void* y, int y_ld, int y_bf16, long long npix, int 
   TSR_REQUIRE(npix > 0 && npix < (1ll << 31), "bn_train_stats: bad pixel count");
   int rpb, nb = red_blocks(npix, rpb), th = red_threads(C);
   TSR_REQUIRE(ws_bytes >= (size_t)nb * 2 * C * sizeof(float), "bn_train_stats: workspace too small");
-  size_t smem = (size_t)2 * th * sizeof(float4);
-  if (y_bf16)
+  if (y_bf16 && C % 8 == 0 && y_ld % 8 == 0) {
+    int tv = redv_threads(C, 8);
+    size_t smv = (size_t)(tv / (C / 8)) * 2 * C * sizeof(float);
+    bn_stats_partial_v_kernel<__nv_bfloat16><<<nb, tv, smv, stream>>>((const __nv_bfloat16*)y, y_ld, (int)npix, C, (float*)workspace, rpb);
+  } else if (!y_bf16) {
+    int tv = redv_threads(C, 4);
+    size_t smv = (size_t)(tv / (C / 4)) * 2 * C * sizeof(float);
+    bn_stats_partial_v_kernel<float><<<nb, tv, smv, stream>>>((const float*)y, y_ld, (int)npix, C, (float*)workspace, rpb);
+  } else {
+    size_t smem = (size_t)2 * th * sizeof(float4);
     bn_stats_partial_kernel<__nv_bfloat16><<<nb, th, smem, stream>>>((const __nv_bfloat16*)y, y_ld, (int)npix, C, (float*)workspace, rpb);
-  else
-    bn_stats_partial_kernel<float><<<nb, th, smem, stream>>>((const float*)y, y_ld, (int)npix, C, (float*)workspace, rpb);
+  }
   TSR_CHECK_LAUNCH("bn_stats_partial");
   bn_finalize_kernel<<<tsr_cdiv(C, 32), dim3(32, 32), 0, stream>>>((const float*)workspace, nb, C, (double)npix, gamma, beta,
                                                            running_mean, running_var, num_batches_tracked, momentum,
@@ -446,7 +613,11 @@ int tsr_bn_apply(const void* y, int y_ld, int y_bf16, const float* scale, const 
   TSR_REQUIRE(C % 4 == 0 && y_ld % 4 == 0 && out_ld % 4 == 0, "bn_apply: C and strides must be multiples of 4");
   int grid = ew_grid(npix * (C / 4));
 #define ARGS(Ti, To) (const Ti*)y, y_ld, scale, shift, (To*)out, out_ld, npix, C, relu
-  if (y_bf16) {
+  if (y_bf16 && out_bf16 && C % 8 == 0 && y_ld % 8 == 0 && out_ld % 8 == 0) {
+    bn_apply_v_kernel<__nv_bfloat16><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>(ARGS(__nv_bfloat16, __nv_bfloat16));
+  } else if (!y_bf16 && !out_bf16) {
+    bn_apply_v_kernel<float><<<grid, 256, 0, stream>>>(ARGS(float, float));
+  } else if (y_bf16) {
     if (out_bf16) bn_apply_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>(ARGS(__nv_bfloat16, __nv_bfloat16));
     else bn_apply_kernel<__nv_bfloat16, float><<<grid, 256, 0, stream>>>(ARGS(__nv_bfloat16, float));
   } else {
@@ -471,19 +642,29 @@ int tsr_bn_backward(const void* da, int da_ld, const void* y, int y_ld, void* dy
   float* partial = (float*)workspace;
   float* c1 = partial + (size_t)nb * 2 * C;
   float* c2 = c1 + C;
-  size_t smem = (size_t)2 * th * sizeof(float4);
-  if (act_bf16)
+  const bool v8 = act_bf16 && C % 8 == 0 && da_ld % 8 == 0 && y_ld % 8 == 0 && dy_ld % 8 == 0;
+  if (v8) {
+    int tv = redv_threads(C, 8);
+    size_t smv = (size_t)(tv / (C / 8)) * 2 * C * sizeof(float);
+    bn_bwd_partial_v_kernel<__nv_bfloat16><<<nb, tv, smv, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
+  } else if (!act_bf16) {
+    int tv = redv_threads(C, 4);
+    size_t smv = (size_t)(tv / (C / 4)) * 2 * C * sizeof(float);
+    bn_bwd_partial_v_kernel<float><<<nb, tv, smv, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
+  } else {
+    size_t smem = (size_t)2 * th * sizeof(float4);
     bn_bwd_partial_kernel<__nv_bfloat16, __nv_bfloat16><<<nb, th, smem, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
-  else
-    bn_bwd_partial_kernel<float, float><<<nb, th, smem, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
+  }
   TSR_CHECK_LAUNCH("bn_bwd_partial");
   bn_bwd_finalize_kernel<<<tsr_cdiv(C, 32), dim3(32, 32), 0, stream>>>(partial, nb, C, (double)npix, dgamma, dbeta, accumulate, c1, c2, training);
   TSR_CHECK_LAUNCH("bn_bwd_finalize");
   int grid = ew_grid(npix * (C / 4));
-  if (act_bf16)
-    bn_bwd_apply_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (__nv_bfloat16*)dy, dy_ld, npix, C, relu);
+  if (v8)
+    bn_bwd_apply_v_kernel<__nv_bfloat16><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (__nv_bfloat16*)dy, dy_ld, npix, C, relu);
+  else if (!act_bf16)
+    bn_bwd_apply_v_kernel<float><<<grid, 256, 0, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (float*)dy, dy_ld, npix, C, relu);
   else
-    bn_bwd_apply_kernel<float, float, float><<<grid, 256, 0, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (float*)dy, dy_ld, npix, C, relu);
+    bn_bwd_apply_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (__nv_bfloat16*)dy, dy_ld, npix, C, relu);
   TSR_CHECK_LAUNCH("bn_bwd_apply");
   return TSR_OK;
 }
@@ -498,10 +679,12 @@ int tsr_relu_backward(const void* da, int da_ld, const void* a, int a_ld, void* 
   TSR_REQUIRE(da && a && dz, "relu_backward: null pointer");
   TSR_REQUIRE(C % 4 == 0 && da_ld % 4 == 0 && a_ld % 4 == 0 && dz_ld % 4 == 0, "relu_backward: C and strides must be multiples of 4");
   int grid = ew_grid(npix * (C / 4));
-  if (act_bf16)
+  if (act_bf16 && C % 8 == 0 && da_ld % 8 == 0 && a_ld % 8 == 0 && dz_ld % 8 == 0)
+    relu_bwd_v_kernel<__nv_bfloat16><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)a, a_ld, (__nv_bfloat16*)dz, dz_ld, npix, C);
+  else if (act_bf16)
     relu_bwd_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)a, a_ld, (__nv_bfloat16*)dz, dz_ld, npix, C);
   else
-    relu_bwd_kernel<float, float, float><<<grid, 256, 0, stream>>>((const float*)da, da_ld, (const float*)a, a_ld, (float*)dz, dz_ld, npix, C);
+    relu_bwd_v_kernel<float><<<grid, 256, 0, stream>>>((const float*)da, da_ld, (const float*)a, a_ld, (float*)dz, dz_ld, npix, C);
   TSR_CHECK_LAUNCH("relu_backward");
   return TSR_OK;
 }
