@@ -532,10 +532,19 @@ class _ProgramFn(torch.autograd.Function):
             raise RuntimeError("tactilesr_b200: backward through the same forward twice is not supported")
         hooks = ctx.holder.get("grad_hook")
         pg = run_backward(prog, c, dout, hooks)
-        grads = []
+        # Parameter gradients are delivered straight into ``.grad`` (first contribution: the tensor the kernels wrote --
+        # for FusedAdam parameters a view of its flat gradient buffer, so no copy and the data-parallel all-reduce works
+        # in place; later contributions: accumulated).  Returning them through autograd instead would make
+        # AccumulateGrad clone every tensor we still hold a reference to.
+        grads = [None] * len(ctx.params)
         for p in ctx.params:
             g = pg.get(p)
-            grads.append(g if (g is not None and p.requires_grad) else None)
+            if g is None or not p.requires_grad:
+                continue
+            if p.grad is None:
+                p.grad = g
+            else:
+                p.grad.add_(g)
         gx = None
         if prog.wants_input_grad and ctx.needs_input_grad[1]:
             gb = c.grads.get(prog.in_buf)
