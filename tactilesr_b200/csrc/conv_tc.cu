@@ -579,6 +579,7 @@ struct Wgrad2Params {
   int ngroups, nchunks;
   int tiles_x, tiles_per_sample, nblocks, blocks_per_split;
   int dy_stage_bytes, stage_bytes, nstages;
+  int nch, xtile_bytes;         // 64-channel ci chunks per CTA (1 or 2 => MMA N = 64 or 128), bytes of one x halo tile
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -621,7 +622,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)p.P * p.P * 128u + 8192u * p.cochunks;
+      const uint32_t tx = (uint32_t)p.P * p.P * 128u * p.nch + 8192u * p.cochunks;
       for (int i = 0; i < nblk; ++i) {
         const int st = i % NS;
         mbar_wait(empty(st), ((i / NS) & 1) ^ 1);
@@ -632,12 +633,15 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
         for (int cc = 0; cc < p.cochunks; ++cc)
           tma_load_4d(dy0 + (uint32_t)cc * 8192u, &tmap_dy, cc * 64, x0, y0, n, full(st));
-        tma_load_4d(dy0 + (uint32_t)p.dy_stage_bytes, &tmap_x, chunk * 64, x0 - p.pad, y0 - p.pad, n, full(st));
+        for (int h = 0; h < p.nch; ++h)
+          tma_load_4d(dy0 + (uint32_t)p.dy_stage_bytes + (uint32_t)h * p.xtile_bytes, &tmap_x, (chunk * p.nch + h) * 64,
+                      x0 - p.pad, y0 - p.pad, n, full(st));
       }
     }
   } else if (warp == 1) {
     {
-      const uint32_t idesc = make_idesc(128, 64, 1, 1);
+      const int NN = 64 * p.nch;
+      const uint32_t idesc = make_idesc(128, NN, 1, 1);
       const uint32_t lbo_a = p.cochunks == 2 ? 8192u : 0u;     // Cout = 64: second MN atom aliases the first
       const uint32_t a_hi = desc_hi(1024u), b_hi = desc_hi((uint32_t)p.P * 128u);
       const uint32_t row_units = (uint32_t)p.P * 8u;
@@ -651,7 +655,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         tc_fence_after();
         const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
         const uint32_t a_lo = desc_lo(dy0, lbo_a);
-        uint32_t b_lo = desc_lo(dy0 + (uint32_t)p.dy_stage_bytes, 0u) + tap_start;
+        uint32_t b_lo = desc_lo(dy0 + (uint32_t)p.dy_stage_bytes, (uint32_t)p.xtile_bytes) + tap_start;
         int kx = kx_start;
         const bool leader = elect_one();
         for (int g = 0; g < ntap; ++g) {
@@ -659,7 +663,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
               // K-step s: dy rows 2s, 2s+1 (2 KB apart per step); x window rows 2s+ky, 2s+1+ky
-              umma_bf16(tmem_base + g * 64, desc_join(a_lo + s * 128u, a_hi), desc_join(b_lo + s * 2u * row_units, b_hi), idesc,
+              umma_bf16(tmem_base + g * NN, desc_join(a_lo + s * 128u, a_hi), desc_join(b_lo + s * 2u * row_units, b_hi), idesc,
                         (first | (uint32_t)s) ? 1u : 0u);
             }
           }
@@ -680,12 +684,13 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       mbar_wait(tmem_full, 0);
       tc_fence_after();
       if (q * 32 < p.Cout) {
+        const int NN = 64 * p.nch;
         for (int g = 0; g < ntap; ++g) {
-          float* dst = p.partial + (((size_t)blockIdx.y * taps + tap0 + g) * p.Cin + (size_t)chunk * 64) * p.Cout + co;
+          float* dst = p.partial + (((size_t)blockIdx.y * taps + tap0 + g) * p.Cin + (size_t)chunk * NN) * p.Cout + co;
 #pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < NN / 16; ++j) {
             uint32_t v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + g * 64 + j * 16, v);
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + g * NN + j * 16, v);
             tmem_ld_wait();
 #pragma unroll
             for (int k = 0; k < 16; ++k) dst[(size_t)(j * 16 + k) * p.Cout] = __uint_as_float(v[k]);
@@ -695,8 +700,8 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       tc_fence_before();
     } else if (co < p.Cout) {
       for (int g = 0; g < ntap; ++g) {
-        float* dst = p.partial + (((size_t)blockIdx.y * taps + tap0 + g) * p.Cin + (size_t)chunk * 64) * p.Cout + co;
-        for (int k = 0; k < 64; ++k) dst[(size_t)k * p.Cout] = 0.f;
+        float* dst = p.partial + (((size_t)blockIdx.y * taps + tap0 + g) * p.Cin + (size_t)chunk * 64 * p.nch) * p.Cout + co;
+        for (int k = 0; k < 64 * p.nch; ++k) dst[(size_t)k * p.Cout] = 0.f;
       }
     }
   }
@@ -848,17 +853,21 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
   return TSR_OK;
 }
 
+static int wgrad_nch(int Cin) { return (!(g_desc_mode & 4) && !(g_desc_mode & 8) && Cin % 128 == 0) ? 2 : 1; }
+
 static void wgrad_plan(int B, int H, int W, int Cin, int Cout, int KS, int* ngroups, int* nsplit, int* nblocks,
                        int* bps) {
   const int taps = KS * KS;
-  *ngroups = (taps + WG_MAX_TAPS - 1) / WG_MAX_TAPS;
+  const int nch = wgrad_nch(Cin);
+  const int max_taps = WG_MAX_TAPS / nch;          // TMEM: taps * 64 * nch <= 512 columns
+  *ngroups = (taps + max_taps - 1) / max_taps;
   if (g_desc_mode & 4) {        // v1 kernel: tall-plane 8x16 blocks
     const int pad = KS / 2;
     *nblocks = tsr_cdiv(B * (H + pad), 16) * (W / 8);
   } else {                      // v2 kernel: per-sample 8x8 tiles
     *nblocks = B * (H / 8) * (W / 8);
   }
-  const int ctas = *ngroups * (Cin / 64);
+  const int ctas = *ngroups * (Cin / (64 * nch));
   int s = num_sms() / ctas;     // a single wave: never more CTAs than SMs
   if (s > *nblocks) s = *nblocks;
   if (s < 1) s = 1;
@@ -929,11 +938,13 @@ int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld
     q.partial = (float*)workspace;
     q.B = B; q.H = H; q.W = W; q.KS = KS; q.pad = pad; q.P = 8 + 2 * pad;
     q.Cin = Cin; q.Cout = Cout; q.cochunks = Cout / 64;
-    q.ngroups = p.ngroups; q.nchunks = Cin / 64;
+    q.nch = wgrad_nch(Cin);
+    q.ngroups = p.ngroups; q.nchunks = Cin / (64 * q.nch);
     q.tiles_x = W / 8; q.tiles_per_sample = (H / 8) * (W / 8);
     q.nblocks = p.nblocks; q.blocks_per_split = p.blocks_per_split;
     q.dy_stage_bytes = 8192 * q.cochunks;
-    q.stage_bytes = (q.dy_stage_bytes + q.P * q.P * 128 + 1023) & ~1023;
+    q.xtile_bytes = (q.P * q.P * 128 + 1023) & ~1023;
+    q.stage_bytes = q.dy_stage_bytes + q.nch * q.xtile_bytes;
     int ns = (int)((SMEM_LIMIT - 1024 - 512) / (size_t)q.stage_bytes);
     if (ns > WG2_MAX_STAGES) ns = WG2_MAX_STAGES;
     q.nstages = ns;
