@@ -413,18 +413,20 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_apply_v_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ scale, const float* __restrict__ shift,
                   T* __restrict__ out, int out_ld, long long npix, int C, int relu) {
+  // each thread owns one 16-byte channel vector (fixed q) and strides over pixels: coefficients live in registers
   constexpr int N = V16<T>::N;
-  const int qn = C / N;
-  const long long total = npix * qn;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i % qn);
-    const long long p = i / qn;
+  const int qn = C / N;                       // divides 256
+  const int q = threadIdx.x % qn;
+  float sc[N], sh[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) { sc[k] = scale[q * N + k]; sh[k] = shift[q * N + k]; }
+  const long long pstride = (long long)gridDim.x * (256 / qn);
+  for (long long p = (long long)blockIdx.x * (256 / qn) + threadIdx.x / qn; p < npix; p += pstride) {
     float v[N];
     V16<T>::load(x + p * x_ld + q * N, v);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      v[k] = fmaf(v[k], __ldg(scale + q * N + k), __ldg(shift + q * N + k));
+      v[k] = fmaf(v[k], sc[k], sh[k]);
       if (relu) v[k] = fmaxf(v[k], 0.f);
     }
     V16<T>::store(out + p * out_ld + q * N, v);
@@ -481,22 +483,28 @@ bn_bwd_apply_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict__
                       const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                       const float* __restrict__ invstd, const float* __restrict__ c1, const float* __restrict__ c2,
                       T* __restrict__ dy, int dy_ld, long long npix, int C, int relu) {
+  // dy = sc*(g - c1 - (v - mu)*is*c2) = sc*g + kb*v + kc with per-channel constants held in registers
   constexpr int N = V16<T>::N;
   const int qn = C / N;
-  const long long total = npix * qn;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i % qn);
-    const long long p = i / qn;
+  const int q = threadIdx.x % qn;
+  float sc[N], sh[N], kb[N], kc[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int c = q * N + k;
+    sc[k] = scale[c]; sh[k] = shift[c];
+    const float t = sc[k] * invstd[c] * c2[c];
+    kb[k] = -t;
+    kc[k] = fmaf(t, mean[c], -sc[k] * c1[c]);
+  }
+  const long long pstride = (long long)gridDim.x * (256 / qn);
+  for (long long p = (long long)blockIdx.x * (256 / qn) + threadIdx.x / qn; p < npix; p += pstride) {
     float g[N], v[N], o[N];
     V16<T>::load(da + p * da_ld + q * N, g);
     V16<T>::load(y + p * y_ld + q * N, v);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      const int c = q * N + k;
-      const float sc = __ldg(scale + c);
-      if (relu && !(fmaf(v[k], sc, __ldg(shift + c)) > 0.f)) g[k] = 0.f;
-      o[k] = sc * (g[k] - __ldg(c1 + c) - (v[k] - __ldg(mean + c)) * __ldg(invstd + c) * __ldg(c2 + c));
+      if (relu && !(fmaf(v[k], sc[k], sh[k]) > 0.f)) g[k] = 0.f;
+      o[k] = fmaf(sc[k], g[k], fmaf(kb[k], v[k], kc[k]));
     }
     V16<T>::store(dy + p * dy_ld + q * N, o);
   }
@@ -537,7 +545,7 @@ inline int ew_grid(long long total) {
 }
 inline int red_blocks(long long npix, int& rows_per_block) {
   int nb = tsr_cdiv(npix, 512);
-  if (nb > 592) nb = 592;
+  if (nb > 296) nb = 296;
   if (nb < 1) nb = 1;
   rows_per_block = tsr_cdiv(npix, nb);
   return tsr_cdiv(npix, rows_per_block);
@@ -613,9 +621,9 @@ int tsr_bn_apply(const void* y, int y_ld, int y_bf16, const float* scale, const 
   TSR_REQUIRE(C % 4 == 0 && y_ld % 4 == 0 && out_ld % 4 == 0, "bn_apply: C and strides must be multiples of 4");
   int grid = ew_grid(npix * (C / 4));
 #define ARGS(Ti, To) (const Ti*)y, y_ld, scale, shift, (To*)out, out_ld, npix, C, relu
-  if (y_bf16 && out_bf16 && C % 8 == 0 && y_ld % 8 == 0 && out_ld % 8 == 0) {
+  if (y_bf16 && out_bf16 && C % 8 == 0 && 256 % (C / 8) == 0 && y_ld % 8 == 0 && out_ld % 8 == 0) {
     bn_apply_v_kernel<__nv_bfloat16><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>(ARGS(__nv_bfloat16, __nv_bfloat16));
-  } else if (!y_bf16 && !out_bf16) {
+  } else if (!y_bf16 && !out_bf16 && 256 % (C / 4) == 0) {
     bn_apply_v_kernel<float><<<grid, 256, 0, stream>>>(ARGS(float, float));
   } else if (y_bf16) {
     if (out_bf16) bn_apply_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>(ARGS(__nv_bfloat16, __nv_bfloat16));
@@ -642,18 +650,22 @@ int tsr_bn_backward(const void* da, int da_ld, const void* y, int y_ld, void* dy
   float* partial = (float*)workspace;
   float* c1 = partial + (size_t)nb * 2 * C;
   float* c2 = c1 + C;
-  const bool v8 = act_bf16 && C % 8 == 0 && da_ld % 8 == 0 && y_ld % 8 == 0 && dy_ld % 8 == 0;
+  const bool v8 = act_bf16 && C % 8 == 0 && 256 % (C / 8) == 0 && da_ld % 8 == 0 && y_ld % 8 == 0 && dy_ld % 8 == 0;
+  const bool v4 = !act_bf16 && 256 % (C / 4) == 0;
   if (v8) {
     int tv = redv_threads(C, 8);
     size_t smv = (size_t)(tv / (C / 8)) * 2 * C * sizeof(float);
     bn_bwd_partial_v_kernel<__nv_bfloat16><<<nb, tv, smv, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
-  } else if (!act_bf16) {
+  } else if (v4) {
     int tv = redv_threads(C, 4);
     size_t smv = (size_t)(tv / (C / 4)) * 2 * C * sizeof(float);
     bn_bwd_partial_v_kernel<float><<<nb, tv, smv, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
   } else {
     size_t smem = (size_t)2 * th * sizeof(float4);
-    bn_bwd_partial_kernel<__nv_bfloat16, __nv_bfloat16><<<nb, th, smem, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
+    if (act_bf16)
+      bn_bwd_partial_kernel<__nv_bfloat16, __nv_bfloat16><<<nb, th, smem, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
+    else
+      bn_bwd_partial_kernel<float, float><<<nb, th, smem, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
   }
   TSR_CHECK_LAUNCH("bn_bwd_partial");
   bn_bwd_finalize_kernel<<<tsr_cdiv(C, 32), dim3(32, 32), 0, stream>>>(partial, nb, C, (double)npix, dgamma, dbeta, accumulate, c1, c2, training);
@@ -661,10 +673,12 @@ int tsr_bn_backward(const void* da, int da_ld, const void* y, int y_ld, void* dy
   int grid = ew_grid(npix * (C / 4));
   if (v8)
     bn_bwd_apply_v_kernel<__nv_bfloat16><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (__nv_bfloat16*)dy, dy_ld, npix, C, relu);
-  else if (!act_bf16)
+  else if (v4)
     bn_bwd_apply_v_kernel<float><<<grid, 256, 0, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (float*)dy, dy_ld, npix, C, relu);
-  else
+  else if (act_bf16)
     bn_bwd_apply_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (__nv_bfloat16*)dy, dy_ld, npix, C, relu);
+  else
+    bn_bwd_apply_kernel<float, float, float><<<grid, 256, 0, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (float*)dy, dy_ld, npix, C, relu);
   TSR_CHECK_LAUNCH("bn_bwd_apply");
   return TSR_OK;
 }

@@ -227,6 +227,7 @@ class ConvOp(Op):
                  residual: Optional[View] = None, src_needs_grad: bool = True):
         self.src, self.conv, self.out, self.relu, self.residual = src, conv, out, relu, residual
         self.src_needs_grad = src_needs_grad
+        self.bn_consumer = None      # set by the program builder when the output feeds a BNReLUOp directly
         self.K = conv.kernel_size[0]
         self.Cin, self.Cout = conv.in_channels, conv.out_channels
         assert src.C == self.Cin and out.C == self.Cout
@@ -289,8 +290,16 @@ class ConvOp(Op):
                       self.Cout, self.K, acc, st)
         if self.conv.bias is not None:
             gb, accb = c.pgrad(self.conv.bias)
-            ws, wsb = c.workspace(_lib.lib().tsr_colsum_workspace(c.npix, self.Cout))
-            _lib.call("tsr_colsum", gp, gld, c.bf16, c.npix, self.Cout, gb.data_ptr(), ws, wsb, accb, st)
+            bn = self.bn_consumer
+            if bn is not None and c.saved[bn][1]:
+                # The gradient reaching a bias that feeds a batch-statistics BatchNorm is sum_pix dy with dy the BN
+                # backward output, which is identically 0 (the reference computes fp32 rounding noise ~1e-8 of the layer's
+                # gradient scale here, SURVEY section 0 pitfall 2): write the exact value instead of reducing 2 GB of zeros.
+                if not accb:
+                    gb.zero_()
+            else:
+                ws, wsb = c.workspace(_lib.lib().tsr_colsum_workspace(c.npix, self.Cout))
+                _lib.call("tsr_colsum", gp, gld, c.bf16, c.npix, self.Cout, gb.data_ptr(), ws, wsb, accb, st)
         # data gradient
         if self.src_needs_grad:
             _, wd = _PACK.get(self.conv.weight, c.mode, True)

@@ -61,8 +61,8 @@ class MSRB(_ProgramModule):
                               (self.conv_3_2, E.View.of(i2), E.View(i3, 0, 2 * n)),
                               (self.conv_5_2, E.View.of(i2), E.View(i3, 2 * n, 2 * n))):
             y = E.Buf(f"{tag}.y{dst.c0}_{dst.C}_{seq[0].kernel_size[0]}", dst.C)
-            prog.add(E.ConvOp(src, seq[0], E.View.of(y)))
-            prog.add(E.BNReLUOp(E.View.of(y), seq[1], dst, relu=True))
+            cv = prog.add(E.ConvOp(src, seq[0], E.View.of(y)))
+            cv.bn_consumer = prog.add(E.BNReLUOp(E.View.of(y), seq[1], dst, relu=True))
         prog.add(E.ConvOp(E.View.of(i3), self.confusion, out, relu=True, residual=x))
 
     def forward(self, x):
