@@ -173,6 +173,62 @@ def time_dominant_kernel(B, reps=10):
     return flops / (ms * 1e-3) / 1e12, ms, flops
 
 
+
+def measure_extras(dev, model, B):
+    """Other configurations of BASELINE.json (reported, not the headline): SR inference (C3) and tPSFNet train (C2)."""
+    import torch
+    from tactilesr_b200.model import tPSFNet
+    from tactilesr_b200.optim import FusedAdam
+    out = {}
+
+    def timeit(fn, reps):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    # C3: eval-mode forward, no_grad
+    model.eval()
+    Bi = max(B, 1024)
+    LR = torch.rand(Bi, 3, 4, 4, device=dev) * 8
+    with torch.no_grad():
+        ms = timeit(lambda: model(LR), 5)
+    model.train()
+    out["sr_infer_samples_per_s"] = Bi / (ms * 1e-3)
+    out["sr_infer_batch"] = Bi
+    out["sr_infer_tensor_frac_of_sustained_peak"] = Bi / (ms * 1e-3) * FLOP_PER_SAMPLE_FWD / 1e12 / peaks()["tf_sust"]
+    # C2: tPSFNet train step (fp32 kernels): fwd + MSE(LR[:,2:3], LR_degrade) + bwd + Adam(1e-4, wd 1e-5), B=256
+    Bp = 256
+    pm = tPSFNet(gama=1.4, perception_scale=None, device=dev).to(dev)
+    popt = FusedAdam(pm.parameters(), lr=1e-4, weight_decay=1e-5)
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(Bp, 3, 4, 4, generator=g) * 13).to(dev)
+    yy, xx = torch.meshgrid(torch.arange(100.0), torch.arange(100.0), indexing="ij")
+    cx = torch.rand(Bp, generator=g) * 50 + 25
+    cy = torch.rand(Bp, generator=g) * 50 + 25
+    r = torch.rand(Bp, generator=g) * 20 + 10
+    depth = torch.clamp((r[:, None, None] - ((yy - cy[:, None, None]) ** 2 + (xx - cx[:, None, None]) ** 2).sqrt()) / 2 + 0.5, 0, 1)
+    depth = depth.unsqueeze(1).to(dev)
+
+    def pstep():
+        HR, LRd, _, _ = pm(x, depth)
+        loss = torch.nn.functional.mse_loss(x[:, 2:3], LRd)
+        popt.zero_grad()
+        loss.backward()
+        popt.step()
+    ms = timeit(pstep, 5)
+    out["tpsf_train_samples_per_s"] = Bp / (ms * 1e-3)
+    out["tpsf_train_batch"] = Bp
+    with torch.no_grad():
+        ms = timeit(lambda: pm(x, depth), 5)
+    out["tpsf_fwd_samples_per_s"] = Bp / (ms * 1e-3)
+    out["tpsf_fwd_hbm_frac"] = Bp / (ms * 1e-3) * 119472 / 1e9 / peaks()["hbm"]
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -241,6 +297,10 @@ def run_ours(args):
         tr.train_one_iter()
     ms_e2e, _ = timed(tr, args.steps, True)
 
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras = measure_extras(dev, model, B)
+
     total = B * world * args.steps
     value = total / (ms_dev * 1e-3)
     e2e = total / (ms_e2e * 1e-3)
@@ -275,7 +335,7 @@ def run_ours(args):
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": B * (3 * 16 + 100 * 100) * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "clocks": clocks,
+        "gpu_launches": launches, "clocks": clocks, "extra": extras,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -288,9 +348,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("TSR_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("TSR_BENCH_BATCH", "256")))
+    ap.add_argument("--precision", default=os.environ.get("TSR_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("TSR_BENCH_BATCH", "512")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -36,8 +36,17 @@ class _ProgramModule(nn.Module):
 
     precision = None   # None -> global tactilesr_b200.get_precision()
 
+    # inference micro-batch: eval-mode BatchNorm uses running statistics, so samples are independent and a huge batch
+    # (config C3 sweeps to 256k samples = 53 GB per 64-channel tensor) is processed in chunks with identical results.
+    eval_chunk = 4096
+
     def _run(self, prog: E.Program, x: torch.Tensor) -> torch.Tensor:
-        return E.apply_program(prog, x, self.training, self.precision, getattr(self, "_engine_extra", None))
+        extra = getattr(self, "_engine_extra", None)
+        if not self.training and not torch.is_grad_enabled() and x.shape[0] > self.eval_chunk:
+            outs = [E.apply_program(prog, x[i:i + self.eval_chunk], False, self.precision, extra)
+                    for i in range(0, x.shape[0], self.eval_chunk)]
+            return torch.cat(outs, 0)
+        return E.apply_program(prog, x, self.training, self.precision, extra)
 
 
 class MSRB(_ProgramModule):
