@@ -32,7 +32,8 @@ constexpr int NUM_THREADS = 224;
 
 // experiment switches (env TSR_TC_MODE or tsr_set_tc_desc_mode): bit0 = descriptor base_offset from the address
 // (wrong on B200: the swizzle phase is taken from the absolute smem address), bit1 = 16-pixel halo pitch in the forward
-// kernel instead of the dense TMA-box pitch, bit2 = v1 weight-gradient kernel (tall-plane blocks, per-row TMA).
+// kernel instead of the dense TMA-box pitch, bit2 = v1 weight-gradient kernel (tall-plane blocks, per-row TMA),
+// bit3 = N=64 weight-gradient tiles only, bit4 = single-CTA (cta_group::1) forward kernel also for N = 128.
 static int env_mode() { const char* e = getenv("TSR_TC_MODE"); return e ? atoi(e) : 0; }
 int g_desc_mode = env_mode();
 
@@ -379,6 +380,275 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) of the forward kernel for N = 128: two CTAs of one cluster (adjacent SMs of a TPC)
+// each own one block (their own halo tile and their own 128 TMEM lanes per M-tile); the 128x64 weight tile is split
+// between them (64 rows each, same shared-memory offset) and ONE tcgen05.mma.cta_group::2 of the leader CTA (M = 256)
+// drives both tensor cores.  Per SM and MMA this reads 4 KB of A + 2 KB of B from shared memory (96 B/clk instead of
+// the 128 B/clk that saturate the shared-memory port with cta_group::1) and halves the weight traffic from L2.
+// Protocol (as in the canonical 2-SM GEMM): both CTAs' TMA loads complete on the LEADER's "full" barriers
+// (.cta_group::2, peer bit of the barrier address cleared; leader arrives with expect_tx of both halves, the peer
+// arrives remotely without tx); tcgen05.commit multicasts "empty"/"accumulator ready" to both CTAs; both epilogues
+// arrive (remotely for the peer) on the leader's "accumulator drained" barrier.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                                uint32_t bar_leader) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_leader) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap wmap,
+                    const ConvParams p) {
+  constexpr int N = 128;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_slot_bytes = ((uint32_t)p.rows * p.P * 128u + 1023u) & ~1023u;
+  const int NA_SLOTS = p.na_slots;
+  const uint32_t a_base = base;
+  const uint32_t b_base = a_base + NA_SLOTS * a_slot_bytes;
+  constexpr uint32_t B_HALF = 64u * 128u;         // this CTA's 64 rows of the 128 x 64 weight tile
+  const int NB = p.nb_stages;
+  const uint32_t bar_base = b_base + NB * B_HALF;
+  auto a_full = [&](int i) { return bar_base + 8u * i; };
+  auto a_empty = [&](int i) { return bar_base + 8u * (MAX_NA + i); };
+  auto b_full = [&](int i) { return bar_base + 8u * (2 * MAX_NA + i); };
+  auto b_empty = [&](int i) { return bar_base + 8u * (2 * MAX_NA + MAX_NB + i); };
+  auto t_full = [&](int i) { return bar_base + 8u * (2 * MAX_NA + 2 * MAX_NB + i); };
+  auto t_empty = [&](int i) { return bar_base + 8u * (2 * MAX_NA + 2 * MAX_NB + 2 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_NA + 2 * MAX_NB + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int taps = p.KS * p.KS;
+  constexpr uint32_t ACC_COLS = T_TILES * N;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;    // 512
+  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const int npb = (p.nblocks + 1) >> 1;           // pair-blocks
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NA_SLOTS; ++i) { mbar_init(a_full(i), 2); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(b_full(i), 2); mbar_init(b_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== A producer (both CTAs): own block's halo rows, completing on the leader's a_full =====
+    const uint32_t row_bytes = (uint32_t)(8 + 2 * p.pad) * 128u;
+    int ac = 0;
+    for (int pb = pair; pb < npb; pb += npairs) {
+      const int blk = 2 * pb + (int)rank;          // may be == nblocks for the last odd block: all rows out of range
+      const int xg = blk % p.nxg, vb = blk / p.nxg;
+      const int x0 = xg * 8, v0 = vb * (16 * T_TILES);
+      for (int c = 0; c < p.nchunks; ++c, ++ac) {
+        const int slot = ac % NA_SLOTS;
+        const uint32_t dst0 = a_base + slot * a_slot_bytes;
+        const uint32_t full_leader = a_full(slot) & PEER_MASK;
+        if (lane == 0) mbar_wait(a_empty(slot), ((ac / NA_SLOTS) & 1) ^ 1);
+        __syncwarp();
+        if (p.pad == 0) {
+          if (lane == 0) tma_load_4d_2sm(dst0, &tmap, c * 64, x0, v0, 0, full_leader);
+        } else {
+          for (int r = lane; r < p.rows; r += 32) {
+            const int vr = v0 - p.pad + r;
+            int n = 0, y = p.H;
+            if (vr >= 0 && vr < p.Vtotal) { n = vr / p.Hp; y = vr - n * p.Hp; }
+            tma_load_4d_2sm(dst0 + (uint32_t)r * p.P * 128u, &tmap, c * 64, x0 - p.pad, y, n, full_leader);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_expect_tx(a_full(slot), 2u * row_bytes * p.rows);
+          else mbar_arrive_cluster(full_leader);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== B producer (both CTAs): rows rank*64.. of each [128][64] weight tile =====
+    if (lane == 0) {
+      const int per_block = p.nchunks * taps;
+      const int rows_per_tile = p.w_tile_elems / 64;     // Cout_total
+      int it = 0;
+      for (int pb = pair; pb < npb; pb += npairs) {
+        for (int k = 0; k < per_block; ++k, ++it) {
+          const int st = it % NB;
+          const uint32_t full_leader = b_full(st) & PEER_MASK;
+          mbar_wait(b_empty(st), ((it / NB) & 1) ^ 1);
+          tma_load_2d_2sm(b_base + st * B_HALF, &wmap, 0, k * rows_per_tile + (int)rank * 64, full_leader);
+          if (leader) mbar_expect_tx(b_full(st), 2u * B_HALF);
+          else mbar_arrive_cluster(full_leader);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: leader CTA only =====
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc(256, N, 0, 0);
+      const uint32_t a_hi = desc_hi((uint32_t)p.P * 128u), b_hi = desc_hi(1024u);
+      const uint32_t row_units = (uint32_t)p.P * 8u;
+      const uint32_t mt_units = 16u * row_units;
+      const uint32_t wrap_units = row_units - (uint32_t)p.KS * 8u;
+      int it = 0, ac = 0, lb = 0;
+      for (int pb = pair; pb < npb; pb += npairs, ++lb) {
+        const int buf = lb & 1;
+        mbar_wait(t_empty(buf), ((lb >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + buf * ACC_COLS;
+        uint32_t first = 0u;
+        for (int c = 0; c < p.nchunks; ++c, ++ac) {
+          const int slot = ac % NA_SLOTS;
+          mbar_wait(a_full(slot), (ac / NA_SLOTS) & 1);
+          tc_fence_after();
+          uint32_t a_lo = desc_lo(a_base + slot * a_slot_bytes, 16u);
+          int kx = 0;
+          for (int t = 0; t < taps; ++t, ++it) {
+            const int st = it % NB;
+            mbar_wait(b_full(st), (it / NB) & 1);
+            tc_fence_after();
+            const uint32_t b_lo = desc_lo(b_base + st * B_HALF, 16u);
+            if (elect_one()) {
+#pragma unroll
+              for (int mt = 0; mt < T_TILES; ++mt) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  umma_bf16_2sm(acc0 + mt * N, desc_join(a_lo + mt * mt_units + kk * 2u, a_hi),
+                                desc_join(b_lo + kk * 2u, b_hi), idesc, (first | (uint32_t)kk) ? 1u : 0u);
+                }
+              }
+              umma_commit_2sm(b_empty(st));
+            }
+            __syncwarp();
+            first = 1u;
+            a_lo += 8u;
+            if (++kx == p.KS) { kx = 0; a_lo += wrap_units; }
+          }
+          if (elect_one()) umma_commit_2sm(a_empty(slot));
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit_2sm(t_full(buf));
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): own 128 TMEM lanes =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int wx = r & 7, vrow = r >> 3;
+    int lb = 0;
+    for (int pb = pair; pb < npb; pb += npairs, ++lb) {
+      const int buf = lb & 1;
+      const int blk = 2 * pb + (int)rank;
+      const int xg = blk % p.nxg, vb = blk / p.nxg;
+      const int x0 = xg * 8, v0 = vb * (16 * T_TILES);
+      mbar_wait(t_full(buf), (lb >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int mt = 0; mt < T_TILES; ++mt) {
+        const int vr = v0 + mt * 16 + vrow;
+        const int n = vr / p.Hp, y = vr - n * p.Hp;
+        const bool valid = blk < p.nblocks && vr < p.Vtotal && y < p.H;
+        const long long pix = ((long long)n * p.H + y) * p.W + x0 + wx;
+#pragma unroll 1
+        for (int j = 0; j < N / 16; ++j) {
+          uint32_t v[16];
+          tmem_ld16(acc0 + mt * N + j * 16, v);
+          tmem_ld_wait();
+          if (valid) {
+            float f[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
+            if (p.bias) {
+#pragma unroll
+              for (int k = 0; k < 16; k += 4) {
+                float4 bv = *reinterpret_cast<const float4*>(p.bias + j * 16 + k);
+                f[k] += bv.x; f[k + 1] += bv.y; f[k + 2] += bv.z; f[k + 3] += bv.w;
+              }
+            }
+            if (p.residual) {
+              const __nv_bfloat16* rp = p.residual + pix * p.res_ld + j * 16;
+#pragma unroll
+              for (int k = 0; k < 16; k += 4) {
+                float4 rv = ld4(rp + k);
+                f[k] += rv.x; f[k + 1] += rv.y; f[k + 2] += rv.z; f[k + 3] += rv.w;
+              }
+            }
+            if (p.flags & FLAG_RELU) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
+            }
+            uint32_t o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+              o[k] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_ld + j * 16);
+            op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(t_empty(buf) & PEER_MASK);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
@@ -767,6 +1037,36 @@ void conv_smem_plan(int N, int rows, int P, int na, size_t* smem, int* nb) {
   *smem = fixed + (size_t)stages * N * 128;
 }
 
+int launch_conv_pair(const CUtensorMap& tmap, ConvParams p, int cout_total, int n0, const void* w_packed,
+                     cudaStream_t stream) {
+  EncodeTiledFn enc = get_encode();
+  // weights as a plain 2D byte image [nchunks*taps*Cout_total rows][128 B]; already in the swizzled layout
+  CUtensorMap wmap;
+  const int taps = p.KS * p.KS;
+  cuuint64_t gdim[2] = {64, (cuuint64_t)p.nchunks * taps * cout_total};
+  cuuint64_t gstr[1] = {128};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { tsr_set_error("conv2d_tc: weight tensor map failed (%d)", (int)r); return TSR_ERR_CUDA; }
+  (void)n0;
+  p.na_slots = p.KS == 1 ? 5 : 2;
+  size_t a = ((size_t)p.rows * p.P * 128 + 1023) & ~(size_t)1023;
+  size_t fixed = 1024 + p.na_slots * a + 512;
+  int stages = (int)((SMEM_LIMIT - fixed) / 8192);
+  if (stages > MAX_NB) stages = MAX_NB;
+  p.nb_stages = stages;
+  size_t smem = fixed + (size_t)stages * 8192;
+  TSR_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int npb = (p.nblocks + 1) / 2;
+  int pairs = npb < num_sms() / 2 ? npb : num_sms() / 2;
+  conv_tc_pair_kernel<<<2 * pairs, NUM_THREADS, smem, stream>>>(tmap, wmap, p);
+  TSR_CHECK_LAUNCH("conv2d_tc_pair");
+  return TSR_OK;
+}
+
 template <int N>
 int launch_conv(const CUtensorMap& tmap, ConvParams p, cudaStream_t stream) {
   size_t smem;
@@ -846,7 +1146,11 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
     p.bias = bias ? bias + n0 : nullptr;
     p.residual = residual ? (const __nv_bfloat16*)residual + n0 : nullptr;
     p.out = (__nv_bfloat16*)out + n0;
-    int rc = nt == 128 ? launch_conv<128>(tmap, p, stream) : launch_conv<64>(tmap, p, stream);
+    int rc;
+    if (nt == 128 && !(g_desc_mode & 16))   // bit 4 set = force the single-CTA kernel
+      rc = launch_conv_pair(tmap, p, Cout, n0, (const __nv_bfloat16*)w_packed + (size_t)n0 * 64, stream);
+    else
+      rc = nt == 128 ? launch_conv<128>(tmap, p, stream) : launch_conv<64>(tmap, p, stream);
     if (rc) return rc;
     n0 += nt;
   }
