@@ -435,17 +435,17 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
                : "memory");
 }
 
+template <int N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap wmap,
                     const ConvParams p) {
-  constexpr int N = 128;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_slot_bytes = ((uint32_t)p.rows * p.P * 128u + 1023u) & ~1023u;
   const int NA_SLOTS = p.na_slots;
   const uint32_t a_base = base;
   const uint32_t b_base = a_base + NA_SLOTS * a_slot_bytes;
-  constexpr uint32_t B_HALF = 64u * 128u;         // this CTA's 64 rows of the 128 x 64 weight tile
+  constexpr uint32_t B_HALF = (N / 2) * 128u;     // this CTA's N/2 rows of the N x 64 weight tile
   const int NB = p.nb_stages;
   const uint32_t bar_base = b_base + NB * B_HALF;
   auto a_full = [&](int i) { return bar_base + 8u * i; };
@@ -463,7 +463,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
   const bool leader = rank == 0;
   const int taps = p.KS * p.KS;
   constexpr uint32_t ACC_COLS = T_TILES * N;
-  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;    // 512
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;    // 512 or 256
   const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
   const int npb = (p.nblocks + 1) >> 1;           // pair-blocks
 
@@ -524,7 +524,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
           const int st = it % NB;
           const uint32_t full_leader = b_full(st) & PEER_MASK;
           mbar_wait(b_empty(st), ((it / NB) & 1) ^ 1);
-          tma_load_2d_2sm(b_base + st * B_HALF, &wmap, 0, k * rows_per_tile + (int)rank * 64, full_leader);
+          tma_load_2d_2sm(b_base + st * B_HALF, &wmap, 0, k * rows_per_tile + (int)rank * (N / 2), full_leader);
           if (leader) mbar_expect_tx(b_full(st), 2u * B_HALF);
           else mbar_arrive_cluster(full_leader);
         }
@@ -1037,6 +1037,7 @@ void conv_smem_plan(int N, int rows, int P, int na, size_t* smem, int* nb) {
   *smem = fixed + (size_t)stages * N * 128;
 }
 
+template <int N>
 int launch_conv_pair(const CUtensorMap& tmap, ConvParams p, int cout_total, int n0, const void* w_packed,
                      cudaStream_t stream) {
   EncodeTiledFn enc = get_encode();
@@ -1045,7 +1046,7 @@ int launch_conv_pair(const CUtensorMap& tmap, ConvParams p, int cout_total, int 
   const int taps = p.KS * p.KS;
   cuuint64_t gdim[2] = {64, (cuuint64_t)p.nchunks * taps * cout_total};
   cuuint64_t gstr[1] = {128};
-  cuuint32_t box[2] = {64, 64};
+  cuuint32_t box[2] = {64, N / 2};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(&wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1055,14 +1056,15 @@ int launch_conv_pair(const CUtensorMap& tmap, ConvParams p, int cout_total, int 
   p.na_slots = p.KS == 1 ? 5 : 2;
   size_t a = ((size_t)p.rows * p.P * 128 + 1023) & ~(size_t)1023;
   size_t fixed = 1024 + p.na_slots * a + 512;
-  int stages = (int)((SMEM_LIMIT - fixed) / 8192);
+  constexpr size_t half = (size_t)(N / 2) * 128;
+  int stages = (int)((SMEM_LIMIT - fixed) / half);
   if (stages > MAX_NB) stages = MAX_NB;
   p.nb_stages = stages;
-  size_t smem = fixed + (size_t)stages * 8192;
-  TSR_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  size_t smem = fixed + (size_t)stages * half;
+  TSR_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int npb = (p.nblocks + 1) / 2;
   int pairs = npb < num_sms() / 2 ? npb : num_sms() / 2;
-  conv_tc_pair_kernel<<<2 * pairs, NUM_THREADS, smem, stream>>>(tmap, wmap, p);
+  conv_tc_pair_kernel<N><<<2 * pairs, NUM_THREADS, smem, stream>>>(tmap, wmap, p);
   TSR_CHECK_LAUNCH("conv2d_tc_pair");
   return TSR_OK;
 }
@@ -1148,7 +1150,9 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
     p.out = (__nv_bfloat16*)out + n0;
     int rc;
     if (nt == 128 && !(g_desc_mode & 16))   // bit 4 set = force the single-CTA kernel
-      rc = launch_conv_pair(tmap, p, Cout, n0, (const __nv_bfloat16*)w_packed + (size_t)n0 * 64, stream);
+      rc = launch_conv_pair<128>(tmap, p, Cout, n0, (const __nv_bfloat16*)w_packed + (size_t)n0 * 64, stream);
+    else if (nt == 64 && !(g_desc_mode & 16) && !(g_desc_mode & 32))
+      rc = launch_conv_pair<64>(tmap, p, Cout, n0, (const __nv_bfloat16*)w_packed + (size_t)n0 * 64, stream);
     else
       rc = nt == 128 ? launch_conv<128>(tmap, p, stream) : launch_conv<64>(tmap, p, stream);
     if (rc) return rc;
