@@ -983,6 +983,181 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   }
 }
 
+// ---- v3: operand roles swapped so that no accumulator row is wasted --------------------------------------------
+// D[M = 128 rows of ci][N = Cout] += A(x window, MN-major) * B(dy, MN-major)^T.  The two 64-row atoms of the A operand
+// are LBO bytes apart, and LBO is free: for Cin % 128 == 0 they are the two channel chunks of one tap (LBO = halo tile
+// size); otherwise they are TWO DIFFERENT TAPS of the same chunk (LBO = byte distance of the two windows inside the one
+// halo tile), so a 64-channel layer fills all 128 rows with useful work (v2 duplicated 64 rows: half the MMAs wasted).
+// One accumulator of Cout columns per M-group; a CTA owns up to 512/Cout M-groups over its whole pixel range.
+struct Wgrad3Params {
+  float* partial;               // [nsplit][taps][Cin][Cout]
+  int B, H, W, KS, pad, P;
+  int Cin, Cout, cochunks;
+  int tap_mode;                 // 0: atoms = 2 chunks of one tap, 1: atoms = 2 taps of one chunk
+  int ngroups_total;            // M-groups per chunk unit: taps (mode 0) or ceil(taps/2) (mode 1)
+  int gpc;                      // M-groups per CTA (<= 512 / Cout)
+  int ncta_groups, nunits;      // CTA grid.x = ncta_groups * nunits (unit = chunk pair / chunk)
+  int tiles_x, tiles_per_sample, nblocks, blocks_per_split;
+  int dy_stage_bytes, xtile_bytes, stage_bytes, nstages;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                 const Wgrad3Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int NS = p.nstages;
+  const uint32_t bar_base = base + NS * (uint32_t)p.stage_bytes;
+  auto full = [&](int i) { return bar_base + 8u * i; };
+  auto empty = [&](int i) { return bar_base + 8u * (WG2_MAX_STAGES + i); };
+  const uint32_t tmem_full = bar_base + 8u * (2 * WG2_MAX_STAGES);
+  const uint32_t tmem_slot = tmem_full + 8u;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = blockIdx.x % p.ncta_groups, unit = blockIdx.x / p.ncta_groups;
+  const int taps = p.KS * p.KS;
+  const int gbase = p.ngroups_total / p.ncta_groups, grem = p.ngroups_total % p.ncta_groups;   // balanced
+  const int g0 = cg * gbase + min(cg, grem);
+  const int ng = gbase + (cg < grem ? 1 : 0);
+  const int nxt = p.tap_mode ? 1 : 2;              // x halo tiles (chunks) per stage
+  const int blk0 = blockIdx.y * p.blocks_per_split;
+  const int blk1 = min(blk0 + p.blocks_per_split, p.nblocks);
+  const int nblk = max(blk1 - blk0, 0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)p.P * p.P * 128u * nxt + 8192u * p.cochunks;
+      for (int i = 0; i < nblk; ++i) {
+        const int st = i % NS;
+        mbar_wait(empty(st), ((i / NS) & 1) ^ 1);
+        mbar_expect_tx(full(st), tx);
+        const int b = blk0 + i;
+        const int n = b / p.tiles_per_sample, t = b - n * p.tiles_per_sample;
+        const int y0 = (t / p.tiles_x) * 8, x0 = (t % p.tiles_x) * 8;
+        const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
+        for (int cc = 0; cc < p.cochunks; ++cc)
+          tma_load_4d(dy0 + (uint32_t)cc * 8192u, &tmap_dy, cc * 64, x0, y0, n, full(st));
+        for (int h = 0; h < nxt; ++h)
+          tma_load_4d(dy0 + (uint32_t)p.dy_stage_bytes + (uint32_t)h * p.xtile_bytes, &tmap_x, (unit * nxt + h) * 64,
+                      x0 - p.pad, y0 - p.pad, n, full(st));
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(128, p.Cout, 1, 1);
+    const uint32_t a_hi = desc_hi((uint32_t)p.P * 128u), b_hi = desc_hi(1024u);
+    const uint32_t row_units = (uint32_t)p.P * 8u;
+    const uint32_t lbo_b = p.cochunks == 2 ? 8192u : 0u;
+    // per-M-group descriptor low-word increments (window offset | LBO << 16), computed once: the per-stage loop of
+    // the single issuing lane must stay free of integer divisions
+    uint32_t gword[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      uint32_t w = 0u;
+      if (g < ng) {
+        if (p.tap_mode) {
+          const int t1 = 2 * (g0 + g), t2 = min(t1 + 1, taps - 1);
+          const uint32_t o1 = (uint32_t)((t1 / p.KS) * p.P + t1 % p.KS) * 8u;
+          const uint32_t o2 = (uint32_t)((t2 / p.KS) * p.P + t2 % p.KS) * 8u;
+          w = o1 | ((o2 - o1) << 16);
+        } else {
+          const int t1 = g0 + g;
+          w = ((uint32_t)((t1 / p.KS) * p.P + t1 % p.KS) * 8u) | (((uint32_t)p.xtile_bytes >> 4) << 16);
+        }
+      }
+      gword[g] = w;
+    }
+    uint32_t first = 0u;
+    for (int i = 0; i < nblk; ++i) {
+      const int st = i % NS;
+      mbar_wait(full(st), (i / NS) & 1);
+      tc_fence_after();
+      const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
+      const uint32_t xs_lo = desc_lo(dy0 + (uint32_t)p.dy_stage_bytes, 0u);
+      const uint32_t b_lo = desc_lo(dy0, lbo_b);
+      if (elect_one()) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (g < ng) {
+            const uint32_t a_lo = xs_lo + gword[g];
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+              umma_bf16(tmem_base + g * p.Cout, desc_join(a_lo + s * 2u * row_units, a_hi),
+                        desc_join(b_lo + s * 128u, b_hi), idesc, (first | (uint32_t)s) ? 1u : 0u);
+          }
+        }
+        umma_commit(empty(st));
+      }
+      __syncwarp();
+      first = 1u;
+    }
+    if (elect_one()) umma_commit(tmem_full);
+    __syncwarp();
+  } else if (warp >= 3) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // accumulator row: atom = r / 64, ci_local = r % 64
+    const int atom = r >> 6, cil = r & 63;
+    if (nblk > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+    for (int g = 0; g < ng; ++g) {
+      int tap, ci;
+      bool valid = true;
+      if (p.tap_mode) {
+        const int t1 = 2 * (g0 + g);
+        tap = t1 + atom;
+        valid = tap < taps;                      // odd tap count: the last group's second atom is a duplicate
+        ci = unit * 64 + cil;
+      } else {
+        tap = g0 + g;
+        ci = (unit * 2 + atom) * 64 + cil;
+      }
+      float* dst = p.partial + (((size_t)blockIdx.y * taps + (valid ? tap : 0)) * p.Cin + ci) * p.Cout;
+#pragma unroll 1
+      for (int j = 0; j < p.Cout / 16; ++j) {
+        uint32_t v[16];
+        if (nblk > 0) {
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + g * p.Cout + j * 16, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = 0u;
+        }
+        if (valid) {
+          float4* d4 = reinterpret_cast<float4*>(dst + j * 16);
+          d4[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+          d4[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+          d4[2] = make_float4(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+          d4[3] = make_float4(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]), __uint_as_float(v[15]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
 // level 2 (shared with the fp32 path's layout): dw_oihw[co][ci][tap] (+)= sum_s partial[s][tap][ci][co]
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int S, int taps,
                                        int Cin, int Cout, int accumulate) {
@@ -1162,20 +1337,42 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
 }
 
 static int wgrad_nch(int Cin) { return (!(g_desc_mode & 4) && !(g_desc_mode & 8) && Cin % 128 == 0) ? 2 : 1; }
+static bool wgrad_v3() { return !(g_desc_mode & 4) && !(g_desc_mode & 64); }
+
+struct Wgrad3Plan { int tap_mode, ngroups_total, gpc, ncta_groups, nunits; };
+static Wgrad3Plan wgrad3_plan(int Cin, int Cout, int KS) {
+  Wgrad3Plan q;
+  const int taps = KS * KS;
+  q.tap_mode = (Cin % 128 == 0) ? 0 : 1;
+  q.ngroups_total = q.tap_mode ? (taps + 1) / 2 : taps;
+  const int max_g = 512 / Cout;
+  q.ncta_groups = (q.ngroups_total + max_g - 1) / max_g;
+  q.gpc = (q.ngroups_total + q.ncta_groups - 1) / q.ncta_groups;
+  q.nunits = q.tap_mode ? Cin / 64 : Cin / 128;
+  return q;
+}
 
 static void wgrad_plan(int B, int H, int W, int Cin, int Cout, int KS, int* ngroups, int* nsplit, int* nblocks,
                        int* bps) {
   const int taps = KS * KS;
-  const int nch = wgrad_nch(Cin);
-  const int max_taps = WG_MAX_TAPS / nch;          // TMEM: taps * 64 * nch <= 512 columns
-  *ngroups = (taps + max_taps - 1) / max_taps;
-  if (g_desc_mode & 4) {        // v1 kernel: tall-plane 8x16 blocks
-    const int pad = KS / 2;
-    *nblocks = tsr_cdiv(B * (H + pad), 16) * (W / 8);
-  } else {                      // v2 kernel: per-sample 8x8 tiles
+  int ctas;
+  if (wgrad_v3()) {
+    Wgrad3Plan q = wgrad3_plan(Cin, Cout, KS);
+    *ngroups = q.ncta_groups;
     *nblocks = B * (H / 8) * (W / 8);
+    ctas = q.ncta_groups * q.nunits;
+  } else {
+    const int nch = wgrad_nch(Cin);
+    const int max_taps = WG_MAX_TAPS / nch;          // TMEM: taps * 64 * nch <= 512 columns
+    *ngroups = (taps + max_taps - 1) / max_taps;
+    if (g_desc_mode & 4) {        // v1 kernel: tall-plane 8x16 blocks
+      const int pad = KS / 2;
+      *nblocks = tsr_cdiv(B * (H + pad), 16) * (W / 8);
+    } else {                      // v2 kernel: per-sample 8x8 tiles
+      *nblocks = B * (H / 8) * (W / 8);
+    }
+    ctas = *ngroups * (Cin / (64 * nch));
   }
-  const int ctas = *ngroups * (Cin / (64 * nch));
   int s = num_sms() / ctas;     // a single wave: never more CTAs than SMs
   if (s > *nblocks) s = *nblocks;
   if (s < 1) s = 1;
@@ -1240,6 +1437,28 @@ int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld
     dim3 grid(p.ngroups * p.nchunks, nsplit);
     wgrad_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmx, tmdy, p);
     TSR_CHECK_LAUNCH("conv2d_wgrad_tc");
+  } else if (wgrad_v3()) {
+    TSR_REQUIRE(H % 8 == 0, "conv2d_wgrad_tc: H must be a multiple of 8");
+    Wgrad3Plan pl = wgrad3_plan(Cin, Cout, KS);
+    Wgrad3Params q;
+    q.partial = (float*)workspace;
+    q.B = B; q.H = H; q.W = W; q.KS = KS; q.pad = pad; q.P = 8 + 2 * pad;
+    q.Cin = Cin; q.Cout = Cout; q.cochunks = Cout / 64;
+    q.tap_mode = pl.tap_mode; q.ngroups_total = pl.ngroups_total; q.gpc = pl.gpc;
+    q.ncta_groups = pl.ncta_groups; q.nunits = pl.nunits;
+    q.tiles_x = W / 8; q.tiles_per_sample = (H / 8) * (W / 8);
+    q.nblocks = p.nblocks; q.blocks_per_split = p.blocks_per_split;
+    q.dy_stage_bytes = 8192 * q.cochunks;
+    q.xtile_bytes = (q.P * q.P * 128 + 1023) & ~1023;
+    q.stage_bytes = q.dy_stage_bytes + (pl.tap_mode ? 1 : 2) * q.xtile_bytes;
+    int ns = (int)((SMEM_LIMIT - 1024 - 512) / (size_t)q.stage_bytes);
+    if (ns > WG2_MAX_STAGES) ns = WG2_MAX_STAGES;
+    q.nstages = ns;
+    size_t smem = 1024 + (size_t)ns * q.stage_bytes + 512;
+    TSR_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(q.ncta_groups * q.nunits, nsplit);
+    wgrad_tc3_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmx, tmdy, q);
+    TSR_CHECK_LAUNCH("conv2d_wgrad_tc3");
   } else {
     TSR_REQUIRE(H % 8 == 0, "conv2d_wgrad_tc: H must be a multiple of 8");
     Wgrad2Params q;
