@@ -418,35 +418,60 @@ __global__ void head_wgrad_reduce_kernel(const float* __restrict__ partial, int 
 // ---------------------------------------------------------------------------------------------
 // tail: 3x3 conv Cin -> 1 (no bias) + ReLU.   reference tactileSR_model.py:55-56, :125-126
 // ---------------------------------------------------------------------------------------------
+// A CTA owns TR = 4 rows x W columns of one sample: the (TR+2) x (W+2) x Cin halo tile is staged once in shared memory
+// (coalesced 16-byte loads, zero fill = padding), so every input element is read from HBM/L2 once instead of 9 times;
+// then one warp per output pixel: lane = 4 channels, the 9x4 weights of the lane stay in registers, warp-shuffle sum.
+constexpr int TAIL_TR = 4;
 template <typename InT>
 __global__ void __launch_bounds__(256)
 tail_fwd_kernel(const InT* __restrict__ in, int in_ld, const float* __restrict__ w /*1,Cin,3,3*/,
-                float* __restrict__ out, int Mtotal, int H, int W, int Cin, int relu) {
-  extern __shared__ float ws[];   // [9][Cin]
-  for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) {
-    int ci = i % Cin, tap = i / Cin;
-    ws[i] = w[ci * 9 + tap];
+                float* __restrict__ out, int B, int H, int W, int Cin, int relu) {
+  extern __shared__ __align__(16) uint8_t tail_smem[];
+  constexpr int VEC = 16 / sizeof(InT);                 // elements per 16-byte access
+  const int pitch = Cin + VEC;                          // padded pixel pitch (elements): conflict-free lane access
+  InT* tile = reinterpret_cast<InT*>(tail_smem);
+  const int strips = (H + TAIL_TR - 1) / TAIL_TR;
+  const int b = blockIdx.x / strips, y0 = (blockIdx.x % strips) * TAIL_TR;
+  const int PW = W + 2, PH = TAIL_TR + 2;
+  const int vpp = Cin / VEC;                            // vectors per pixel
+  for (int i = threadIdx.x; i < PH * PW * vpp; i += blockDim.x) {
+    const int v = i % vpp, pix = i / vpp;
+    const int px = pix % PW - 1, py = y0 + pix / PW - 1;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (px >= 0 && px < W && py >= 0 && py < H)
+      val = *reinterpret_cast<const uint4*>(in + ((long long)(b * H + py) * W + px) * in_ld + v * VEC);
+    *reinterpret_cast<uint4*>(tile + (long long)pix * pitch + v * VEC) = val;
   }
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int HW = H * W;
-  for (int p = blockIdx.x * nw + warp; p < Mtotal; p += gridDim.x * nw) {
-    int b = p / HW, rem = p - b * HW;
-    int y = rem / W, x = rem - y * W;
-    float s = 0.f;
+  // this lane's weights: channels c = lane*4 + 128*k (k = 0 for Cin <= 128)
+  float wr[9][4];
+  const int c0 = lane * 4;
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      const InT* src = in + ((long long)b * HW + (long long)yy * W + xx) * in_ld;
-      for (int c = lane * 4; c < Cin; c += 128) {
-        float4 v = ld4(src + c);
-        float4 wv = *reinterpret_cast<const float4*>(ws + tap * Cin + c);
-        s += v.x * wv.x + v.y * wv.y + v.z * wv.z + v.w * wv.w;
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wr[t][j] = (c0 + j < Cin) ? w[(c0 + j) * 9 + t] : 0.f;
+  __syncthreads();
+  for (int p = warp; p < TAIL_TR * W; p += nw) {
+    const int ty = p / W, x = p - ty * W;
+    if (y0 + ty >= H) break;
+    float s = 0.f;
+    if (c0 < Cin) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const InT* src = tile + (long long)((ty + t / 3) * PW + x + t % 3) * pitch + c0;
+        const float4 v = ld4(src);
+        s = fmaf(v.x, wr[t][0], fmaf(v.y, wr[t][1], fmaf(v.z, wr[t][2], fmaf(v.w, wr[t][3], s))));
       }
     }
+    if (Cin > 128) {   // generic tail for wider inputs (not used by the reference networks)
+      for (int c = c0 + 128; c < Cin; c += 128)
+        for (int t = 0; t < 9; ++t) {
+          const float4 v = ld4(tile + (long long)((ty + t / 3) * PW + x + t % 3) * pitch + c);
+          s += v.x * w[c * 9 + t] + v.y * w[(c + 1) * 9 + t] + v.z * w[(c + 2) * 9 + t] + v.w * w[(c + 3) * 9 + t];
+        }
+    }
     s = warp_sum(s);
-    if (lane == 0) out[p] = relu ? fmaxf(s, 0.f) : s;
+    if (lane == 0) out[((long long)b * H + y0 + ty) * W + x] = relu ? fmaxf(s, 0.f) : s;
   }
 }
 
@@ -456,34 +481,38 @@ __global__ void __launch_bounds__(256)
 tail_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out_act,
                   const float* __restrict__ w, GT* __restrict__ din, int din_ld, int Mtotal, int H, int W,
                   int Cin, int relu) {
-  extern __shared__ float ws[];   // [9][Cin]
-  for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) {
-    int ci = i % Cin, tap = i / Cin;
-    ws[i] = w[ci * 9 + tap];
-  }
-  __syncthreads();
-  const int q4 = Cin / 4, HW = H * W;
-  long long total = (long long)Mtotal * q4;
-  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total;
-       it += (long long)gridDim.x * blockDim.x) {
-    int q = (int)(it % q4);
-    int p = (int)(it / q4);
-    int b = p / HW, rem = p - b * HW;
-    int y = rem / W, x = rem - y * W;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // one warp per pixel, lane = 4 channels (weights in registers); the 9 neighbouring output gradients are loaded
+  // first (independent, warp-uniform addresses), then 36 FMAs and one coalesced store of the pixel's channel row
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int HW = H * W;
+  for (int c0 = lane * 4; c0 < Cin; c0 += 128) {
+    float wr[9][4];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      // output pixel o = p - shift(tap) used input p with weight tap
-      int yy = y - (tap / 3 - 1), xx = x - (tap % 3 - 1);
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      int o = b * HW + yy * W + xx;
-      float g = dout[o];
-      if (relu && !(out_act[o] > 0.f)) g = 0.f;
-      float4 wv = *reinterpret_cast<const float4*>(ws + tap * Cin + q * 4);
-      acc.x = fmaf(g, wv.x, acc.x); acc.y = fmaf(g, wv.y, acc.y);
-      acc.z = fmaf(g, wv.z, acc.z); acc.w = fmaf(g, wv.w, acc.w);
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wr[t][j] = w[(c0 + j) * 9 + t];
+    for (int p = blockIdx.x * nw + warp; p < Mtotal; p += gridDim.x * nw) {
+      const int b = p / HW, rem = p - b * HW;
+      const int y = rem / W, x = rem - y * W;
+      float g[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        // output pixel o = p - shift(tap) used input p with weight tap
+        const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
+        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        const int o = ok ? b * HW + yy * W + xx : p;
+        float gv = ok ? dout[o] : 0.f;
+        if (relu && ok && !(out_act[o] > 0.f)) gv = 0.f;
+        g[t] = gv;
+      }
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        acc.x = fmaf(g[t], wr[t][0], acc.x); acc.y = fmaf(g[t], wr[t][1], acc.y);
+        acc.z = fmaf(g[t], wr[t][2], acc.z); acc.w = fmaf(g[t], wr[t][3], acc.w);
+      }
+      st4(din + (long long)p * din_ld + c0, acc);
     }
-    st4(din + (long long)p * din_ld + q * 4, acc);
   }
 }
 
@@ -698,14 +727,20 @@ int tsr_tail_fwd(const void* in, int in_ld, int in_bf16, const float* w_oihw, fl
                  int Cin, int relu, cudaStream_t stream) {
   TSR_REQUIRE(in && w_oihw && out, "tail_fwd: null pointer");
   TSR_REQUIRE(Cin % 4 == 0 && Cin <= 1024 && in_ld % 4 == 0, "tail_fwd: Cin must be a multiple of 4");
-  long long M = (long long)B * H * W;
-  int grid = tsr_cdiv(M, 8);
-  if (grid > 148 * 16) grid = 148 * 16;
-  size_t smem = (size_t)9 * Cin * sizeof(float);
-  if (in_bf16)
-    tail_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)in, in_ld, w_oihw, out, (int)M, H, W, Cin, relu);
-  else
-    tail_fwd_kernel<float><<<grid, 256, smem, stream>>>((const float*)in, in_ld, w_oihw, out, (int)M, H, W, Cin, relu);
+  TSR_REQUIRE(Cin % 8 == 0, "tail_fwd: Cin must be a multiple of 8");
+  const int strips = (H + TAIL_TR - 1) / TAIL_TR;
+  const int grid = B * strips;
+  if (in_bf16) {
+    size_t smem = (size_t)(TAIL_TR + 2) * (W + 2) * (Cin + 8) * 2;
+    TSR_REQUIRE(smem <= 227 * 1024, "tail_fwd: tile does not fit in shared memory");
+    TSR_CUDA(cudaFuncSetAttribute(tail_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tail_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)in, in_ld, w_oihw, out, B, H, W, Cin, relu);
+  } else {
+    size_t smem = (size_t)(TAIL_TR + 2) * (W + 2) * (Cin + 4) * 4;
+    TSR_REQUIRE(smem <= 227 * 1024, "tail_fwd: tile does not fit in shared memory");
+    TSR_CUDA(cudaFuncSetAttribute(tail_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tail_fwd_kernel<float><<<grid, 256, smem, stream>>>((const float*)in, in_ld, w_oihw, out, B, H, W, Cin, relu);
+  }
   TSR_CHECK_LAUNCH("tail_fwd");
   return TSR_OK;
 }
@@ -715,14 +750,12 @@ int tsr_tail_dgrad(const float* dout, const float* out_act, const float* w_oihw,
   TSR_REQUIRE(dout && w_oihw && din && (!relu || out_act), "tail_dgrad: null pointer");
   TSR_REQUIRE(Cin % 4 == 0 && din_ld % 4 == 0, "tail_dgrad: Cin must be a multiple of 4");
   long long M = (long long)B * H * W;
-  long long total = M * (Cin / 4);
-  int grid = (int)((total + 255) / 256);
+  int grid = (int)((M + 7) / 8);
   if (grid > 148 * 32) grid = 148 * 32;
-  size_t smem = (size_t)9 * Cin * sizeof(float);
   if (din_bf16)
-    tail_dgrad_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(dout, out_act, w_oihw, (__nv_bfloat16*)din, din_ld, (int)M, H, W, Cin, relu);
+    tail_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(dout, out_act, w_oihw, (__nv_bfloat16*)din, din_ld, (int)M, H, W, Cin, relu);
   else
-    tail_dgrad_kernel<float><<<grid, 256, smem, stream>>>(dout, out_act, w_oihw, (float*)din, din_ld, (int)M, H, W, Cin, relu);
+    tail_dgrad_kernel<float><<<grid, 256, 0, stream>>>(dout, out_act, w_oihw, (float*)din, din_ld, (int)M, H, W, Cin, relu);
   TSR_CHECK_LAUNCH("tail_dgrad");
   return TSR_OK;
 }

@@ -386,13 +386,27 @@ bn_stats_partial_v_kernel(const T* __restrict__ x, int ld, int npix, int C, floa
   float s[N], ss[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) { s[i] = 0.f; ss[i] = 0.f; }
-  if (lane < lanes)
-    for (int r = r0 + lane; r < r1; r += lanes) {
+  if (lane < lanes) {
+    int r = r0 + lane;
+    for (; r + 3 * lanes < r1; r += 4 * lanes) {       // 4 independent 16-byte loads in flight per thread
+      float v0[N], v1[N], v2[N], v3[N];
+      V16<T>::load(x + (long long)r * ld + q * N, v0);
+      V16<T>::load(x + (long long)(r + lanes) * ld + q * N, v1);
+      V16<T>::load(x + (long long)(r + 2 * lanes) * ld + q * N, v2);
+      V16<T>::load(x + (long long)(r + 3 * lanes) * ld + q * N, v3);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        s[i] += (v0[i] + v1[i]) + (v2[i] + v3[i]);
+        ss[i] = fmaf(v0[i], v0[i], fmaf(v1[i], v1[i], fmaf(v2[i], v2[i], fmaf(v3[i], v3[i], ss[i]))));
+      }
+    }
+    for (; r < r1; r += lanes) {
       float v[N];
       V16<T>::load(x + (long long)r * ld + q * N, v);
 #pragma unroll
       for (int i = 0; i < N; ++i) { s[i] += v[i]; ss[i] = fmaf(v[i], v[i], ss[i]); }
     }
+  }
   // smem layout: [lane][2][C]
   if (lane < lanes) {
 #pragma unroll
@@ -450,8 +464,23 @@ bn_bwd_partial_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict
     sc[i] = scale[q * N + i]; sh[i] = shift[q * N + i]; mu[i] = mean[q * N + i]; is[i] = invstd[q * N + i];
     s[i] = 0.f; sx[i] = 0.f;
   }
-  if (lane < lanes)
-    for (int r = r0 + lane; r < r1; r += lanes) {
+  if (lane < lanes) {
+    int r = r0 + lane;
+    for (; r + lanes < r1; r += 2 * lanes) {            // 4 independent 16-byte loads in flight per thread
+      float g0[N], v0[N], g1[N], v1[N];
+      V16<T>::load(da + (long long)r * da_ld + q * N, g0);
+      V16<T>::load(y + (long long)r * y_ld + q * N, v0);
+      V16<T>::load(da + (long long)(r + lanes) * da_ld + q * N, g1);
+      V16<T>::load(y + (long long)(r + lanes) * y_ld + q * N, v1);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        if (relu && !(fmaf(v0[i], sc[i], sh[i]) > 0.f)) g0[i] = 0.f;
+        if (relu && !(fmaf(v1[i], sc[i], sh[i]) > 0.f)) g1[i] = 0.f;
+        s[i] += g0[i] + g1[i];
+        sx[i] = fmaf(g0[i], (v0[i] - mu[i]) * is[i], fmaf(g1[i], (v1[i] - mu[i]) * is[i], sx[i]));
+      }
+    }
+    for (; r < r1; r += lanes) {
       float g[N], v[N];
       V16<T>::load(da + (long long)r * da_ld + q * N, g);
       V16<T>::load(y + (long long)r * y_ld + q * N, v);
@@ -462,6 +491,7 @@ bn_bwd_partial_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict
         sx[i] = fmaf(g[i], (v[i] - mu[i]) * is[i], sx[i]);
       }
     }
+  }
   if (lane < lanes) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
