@@ -310,9 +310,14 @@ def run_ours(args):
     roof = None
     if args.precision == "bf16":
         tf, kms, kflops = time_dominant_kernel(B)
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel<128> 5x5 128->128 (MSRB conv_5_2 forward shape)", "achieved": tf,
-                "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": tf / pk["tf_burst"], "peak_source": pk["src"] + " bf16 burst",
-                "ms_per_launch": kms, "flops_per_launch": kflops, "traffic": None}
+        # DRAM traffic per launch from the committed ncu --set full capture of this kernel at B = 512
+        # (profiles/r01_conv_tc_pair_5x5_128_b512.txt: dram read 210.6 MB + write 160.8 MB; algorithmic in+out 419 MB)
+        traffic = 371.39e6 if B == 512 else None
+        roof = {"bound": "tensor", "kernel": "conv_tc_pair_kernel<128> (cta_group::2) 5x5 128->128, MSRB conv_5_2 forward shape",
+                "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": tf / pk["tf_burst"],
+                "peak_source": pk["src"] + " bf16 burst (kernel timed alone)", "ms_per_launch": kms, "flops_per_launch": kflops,
+                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                "algorithmic_bytes_per_launch": B * 1600 * (128 + 128) * 2 + 25 * 128 * 128 * 2}
     else:
         roof = {"bound": "tensor", "kernel": "whole fp32 step (FFMA implicit GEMM; fp32-accurate parity mode)",
                 "achieved": value / world * FLOP_PER_SAMPLE_TRAIN / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s",
