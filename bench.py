@@ -308,7 +308,7 @@ def run_ours(args):
         return
     pk = peaks()
     roof = None
-    if args.precision == "bf16":
+    if args.precision in ("bf16", "fp16"):
         tf, kms, kflops = time_dominant_kernel(B)
         # DRAM traffic per launch from the committed ncu --set full capture of this kernel at B = 512
         # (profiles/r01_conv_tc_pair_5x5_128_b512.txt: dram read 210.6 MB + write 160.8 MB; algorithmic in+out 419 MB)
@@ -330,7 +330,7 @@ def run_ours(args):
     line = {
         "metric": "SR train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "fp16 activations / bf16 gradients", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": {"workload": "TactileSR(seqsCnt=1) train step: fwd + fused HR-prep/MSE + bwd + fused Adam(lr 1e-3, wd 1e-2)"
                                + (" + bucketed NCCL grad all-reduce" if world > 1 else ""),
                    "per_gpu_batch": B, "global_batch": B * world, "input": "LR (B,3,4,4), HR (B,1,100,100)",
@@ -353,7 +353,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("TSR_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("TSR_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16", "fp16"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("TSR_BENCH_BATCH", "512")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")

@@ -11,7 +11,9 @@
  *     launches on the given `stream` only;
  *   - activations are NHWC: `x` points at the first of `C` consecutive channels of pixel 0 and `ld` is the channel
  *     count of the underlying buffer (so channel slices of a concat buffer are addressed without a copy);
- *   - `*_bf16` flags select the storage type of an activation operand: 0 = float, 1 = __nv_bfloat16;
+ *   - `*_bf16` arguments are storage-type codes of an activation operand: 0 = float, 1 = __nv_bfloat16, 2 = __half
+ *     (for tsr_bn_backward / tsr_relu_backward, whose operands mix gradients and saved activations: 0 = all float,
+ *     1 = all bf16, 2 = gradients bf16 + saved activation fp16 -- the "fp16" precision mode);
  *   - weights and their gradients keep PyTorch's OIHW fp32 layout (`state_dict()` compatible); packed copies are made by
  *     tsr_pack_conv_weight_*;
  *   - return value 0 = success; otherwise an error code (1 bad argument, 2 CUDA error, 3 unsupported, 4 workspace too
@@ -143,13 +145,18 @@ int tsr_psf_backward(const float* alphaBeta, const float* depth, const float* HR
  * transposed set for the data gradient.  Cin, Cout % 64 == 0. */
 int tsr_pack_conv_weight_bf16(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int KS,
                               tsr_stream_t stream);
+/* same packing with fp16 elements: forward weights of the "fp16" precision mode (fp16 activations, bf16 gradients) */
+int tsr_pack_conv_weight_f16(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int KS,
+                             tsr_stream_t stream);
 size_t tsr_conv2d_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS);
-/* bf16 NHWC convolution, same semantics as tsr_conv2d_f32 (bias fp32, residual / out bf16).  W % 8 == 0. */
+/* bf16 NHWC convolution, same semantics as tsr_conv2d_f32 (bias fp32, residual / out bf16).  W % 8 == 0.
+   flags bit 1 (value 2): in / weights / residual / out are fp16 instead of bf16 (same kernels, kind::f16 format field). */
 int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* bias, const void* residual, int res_ld,
                   void* out, int out_ld, int B, int H, int W, int Cin, int Cout, int KS, int flags, void* workspace,
                   size_t ws_bytes, tsr_stream_t stream);
 size_t tsr_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS);
-/* weight gradient (fp32 OIHW) of bf16 activations / gradients; bit-deterministic.  H, W % 8 == 0, Cout in {64,128}. */
+/* weight gradient (fp32 OIHW) of bf16 activations / gradients; bit-deterministic.  H, W % 8 == 0, Cout in {64,128}.
+   (The "fp16" precision mode hands this a bf16 copy of the conv input: tcgen05 kind::f16 rejects fp16 x bf16.) */
 int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
                         size_t ws_bytes, int B, int H, int W, int Cin, int Cout, int KS, int accumulate,
                         tsr_stream_t stream);

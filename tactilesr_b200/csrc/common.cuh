@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -61,7 +62,23 @@ __device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat16
 __device__ __forceinline__ void stf(float* p, float v) { *p = v; }
 __device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-// 4-wide vector access (16 B for fp32, 8 B for bf16)
+__device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void stf(__half* p, float v) { *p = __float2half_rn(v); }
+
+// storage-type codes of the `*_bf16` / dtype arguments of the C ABI
+#define TSR_DT_F32 0
+#define TSR_DT_BF16 1
+#define TSR_DT_F16 2
+
+// run BODY with T bound to the storage type selected by CODE
+#define TSR_DISPATCH_T(CODE, T, ...)                              \
+  do {                                                            \
+    if ((CODE) == TSR_DT_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else if ((CODE) == TSR_DT_F16) { using T = __half; __VA_ARGS__; }    \
+    else { using T = float; __VA_ARGS__; }                        \
+  } while (0)
+
+// 4-wide vector access (16 B for fp32, 8 B for bf16 / fp16)
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
@@ -72,6 +89,20 @@ __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
 }
 __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+__device__ __forceinline__ float4 ld4(const __half* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __half2 a = *reinterpret_cast<__half2*>(&u.x), b = *reinterpret_cast<__half2*>(&u.y);
+  float2 fa = __half22float2(a), fb = __half22float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(__half* p, float4 v) {
+  __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
   uint2 u;
   u.x = *reinterpret_cast<uint32_t*>(&a);
   u.y = *reinterpret_cast<uint32_t*>(&b);
@@ -107,6 +138,28 @@ template <> struct V16<__nv_bfloat16> {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <> struct V16<__half> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const __half* p, float (&f)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      float2 t = __half22float2(h);
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ static __forceinline__ void store(__half* p, const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
       w[i] = *reinterpret_cast<uint32_t*>(&h);
     }
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);

@@ -665,10 +665,7 @@ int tsr_colsum(const void* x, int ld, int x_bf16, long long npix, int C, float* 
   int q4 = C / 4;
   int threads = (256 / q4) * q4;
   if (threads < q4) threads = q4;
-  if (x_bf16)
-    colsum_partial_kernel<__nv_bfloat16><<<nb, threads, threads * sizeof(float4), stream>>>((const __nv_bfloat16*)x, ld, (int)npix, C, (float*)workspace, rpb);
-  else
-    colsum_partial_kernel<float><<<nb, threads, threads * sizeof(float4), stream>>>((const float*)x, ld, (int)npix, C, (float*)workspace, rpb);
+  TSR_DISPATCH_T(x_bf16, T, colsum_partial_kernel<T><<<nb, threads, threads * sizeof(float4), stream>>>((const T*)x, ld, (int)npix, C, (float*)workspace, rpb));
   TSR_CHECK_LAUNCH("colsum_partial");
   colsum_final_kernel<<<tsr_cdiv(C, 32), dim3(32, 32), 0, stream>>>((const float*)workspace, nb, C, out, accumulate);
   TSR_CHECK_LAUNCH("colsum_final");
@@ -684,13 +681,9 @@ int tsr_head_fwd(const float* x, long long x_bstride, const float* w_oihw, void*
   TSR_REQUIRE(out_ld % 4 == 0, "head_fwd: out_ld must be a multiple of 4");
   size_t smem = head_smem(sf);
   int grid = B < 148 * 4 ? B : 148 * 4;
-  if (out_bf16) {
-    TSR_CUDA(cudaFuncSetAttribute(head_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(x, x_bstride, w_oihw, (__nv_bfloat16*)out, out_ld, B, sf, relu);
-  } else {
-    TSR_CUDA(cudaFuncSetAttribute(head_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_fwd_kernel<float><<<grid, 256, smem, stream>>>(x, x_bstride, w_oihw, (float*)out, out_ld, B, sf, relu);
-  }
+  TSR_DISPATCH_T(out_bf16, T,
+                 TSR_CUDA(cudaFuncSetAttribute(head_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                 head_fwd_kernel<T><<<grid, 256, smem, stream>>>(x, x_bstride, w_oihw, (T*)out, out_ld, B, sf, relu));
   TSR_CHECK_LAUNCH("head_fwd");
   return TSR_OK;
 }
@@ -710,13 +703,9 @@ int tsr_head_wgrad(const float* x, long long x_bstride, const void* dout, int do
   size_t up_floats = (size_t)(4 * sf + 2) * (4 * sf + 2) * 3;
   if (up_floats < 1024) up_floats = 1024;
   size_t smem = (48 + up_floats) * sizeof(float);
-  if (dout_bf16) {
-    TSR_CUDA(cudaFuncSetAttribute(head_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_wgrad_kernel<__nv_bfloat16><<<grid, 1024, smem, stream>>>(x, x_bstride, (const __nv_bfloat16*)dout, dout_ld, (float*)workspace, B, sf);
-  } else {
-    TSR_CUDA(cudaFuncSetAttribute(head_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_wgrad_kernel<float><<<grid, 1024, smem, stream>>>(x, x_bstride, (const float*)dout, dout_ld, (float*)workspace, B, sf);
-  }
+  TSR_DISPATCH_T(dout_bf16, T,
+                 TSR_CUDA(cudaFuncSetAttribute(head_wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                 head_wgrad_kernel<T><<<grid, 1024, smem, stream>>>(x, x_bstride, (const T*)dout, dout_ld, (float*)workspace, B, sf));
   TSR_CHECK_LAUNCH("head_wgrad");
   head_wgrad_reduce_kernel<<<tsr_cdiv(27 * 64, 256), 256, 0, stream>>>((const float*)workspace, grid, dw_oihw, accumulate);
   TSR_CHECK_LAUNCH("head_wgrad_reduce");
@@ -730,17 +719,11 @@ int tsr_tail_fwd(const void* in, int in_ld, int in_bf16, const float* w_oihw, fl
   TSR_REQUIRE(Cin % 8 == 0, "tail_fwd: Cin must be a multiple of 8");
   const int strips = (H + TAIL_TR - 1) / TAIL_TR;
   const int grid = B * strips;
-  if (in_bf16) {
-    size_t smem = (size_t)(TAIL_TR + 2) * (W + 2) * (Cin + 8) * 2;
-    TSR_REQUIRE(smem <= 227 * 1024, "tail_fwd: tile does not fit in shared memory");
-    TSR_CUDA(cudaFuncSetAttribute(tail_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tail_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)in, in_ld, w_oihw, out, B, H, W, Cin, relu);
-  } else {
-    size_t smem = (size_t)(TAIL_TR + 2) * (W + 2) * (Cin + 4) * 4;
-    TSR_REQUIRE(smem <= 227 * 1024, "tail_fwd: tile does not fit in shared memory");
-    TSR_CUDA(cudaFuncSetAttribute(tail_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tail_fwd_kernel<float><<<grid, 256, smem, stream>>>((const float*)in, in_ld, w_oihw, out, B, H, W, Cin, relu);
-  }
+  TSR_DISPATCH_T(in_bf16, T,
+                 size_t smem = (size_t)(TAIL_TR + 2) * (W + 2) * (Cin + 16 / sizeof(T)) * sizeof(T);
+                 TSR_REQUIRE(smem <= 227 * 1024, "tail_fwd: tile does not fit in shared memory");
+                 TSR_CUDA(cudaFuncSetAttribute(tail_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                 tail_fwd_kernel<T><<<grid, 256, smem, stream>>>((const T*)in, in_ld, w_oihw, out, B, H, W, Cin, relu));
   TSR_CHECK_LAUNCH("tail_fwd");
   return TSR_OK;
 }
@@ -752,10 +735,7 @@ int tsr_tail_dgrad(const float* dout, const float* out_act, const float* w_oihw,
   long long M = (long long)B * H * W;
   int grid = (int)((M + 7) / 8);
   if (grid > 148 * 32) grid = 148 * 32;
-  if (din_bf16)
-    tail_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(dout, out_act, w_oihw, (__nv_bfloat16*)din, din_ld, (int)M, H, W, Cin, relu);
-  else
-    tail_dgrad_kernel<float><<<grid, 256, 0, stream>>>(dout, out_act, w_oihw, (float*)din, din_ld, (int)M, H, W, Cin, relu);
+  TSR_DISPATCH_T(din_bf16, T, tail_dgrad_kernel<T><<<grid, 256, 0, stream>>>(dout, out_act, w_oihw, (T*)din, din_ld, (int)M, H, W, Cin, relu));
   TSR_CHECK_LAUNCH("tail_dgrad");
   return TSR_OK;
 }
@@ -783,10 +763,7 @@ int tsr_tail_wgrad(const void* in, int in_ld, int in_bf16, const float* dout, co
   int threads = (256 / q4) * q4;
   if (threads < q4) threads = q4;
   size_t smem = (size_t)threads * sizeof(float4);
-  if (in_bf16)
-    tail_wgrad_kernel<__nv_bfloat16><<<nb, threads, smem, stream>>>((const __nv_bfloat16*)in, in_ld, dout, out_act, (float*)workspace, (int)M, H, W, Cin, relu, ppb);
-  else
-    tail_wgrad_kernel<float><<<nb, threads, smem, stream>>>((const float*)in, in_ld, dout, out_act, (float*)workspace, (int)M, H, W, Cin, relu, ppb);
+  TSR_DISPATCH_T(in_bf16, T, tail_wgrad_kernel<T><<<nb, threads, smem, stream>>>((const T*)in, in_ld, dout, out_act, (float*)workspace, (int)M, H, W, Cin, relu, ppb));
   TSR_CHECK_LAUNCH("tail_wgrad");
   tail_wgrad_reduce_kernel<<<tsr_cdiv(9 * Cin, 256), 256, 0, stream>>>((const float*)workspace, nb, Cin, dw_oihw, accumulate);
   TSR_CHECK_LAUNCH("tail_wgrad_reduce");

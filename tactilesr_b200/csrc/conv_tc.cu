@@ -25,6 +25,7 @@
 namespace {
 
 constexpr int FLAG_RELU = 1;
+constexpr int FLAG_F16 = 2;          // activations / weights / residual / output are fp16 instead of bf16
 constexpr int T_TILES = 2;          // M-tiles (128 pixels each) per CTA
 constexpr int NB_STAGES = 3;        // weight ring depth
 constexpr int MAX_NA = 8;           // activation chunk slots (2 for 3x3 / 5x5, more for the bandwidth-bound 1x1)
@@ -143,8 +144,11 @@ __device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) {
 
 // kind::f16 instruction descriptor: D=f32 (bit4), A=bf16 (bit7), B=bf16 (bit10), majors bit15/16,
 // N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// (format code of kind::f16 operands: 0 = fp16, 1 = bf16.  A and B are separate fields, but B200 raises an illegal
+// instruction for a_format != b_format -- measured -- so both operands always share one format)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, int a_bf16 = 1,
+                                                  int b_bf16 = 1) {
+  return (1u << 4) | ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -263,7 +267,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
     // ===== MMA issuer: the whole warp runs the loop converged (keeps the address math in uniform registers);
     // one elected lane issues the tcgen05 instructions =====
     {
-      constexpr uint32_t idesc = make_idesc(128, N, 0, 0);
+      const int bf = (p.flags & FLAG_F16) ? 0 : 1;
+      const uint32_t idesc = make_idesc(128, N, 0, 0, bf, bf);
       const uint32_t a_hi = desc_hi((uint32_t)p.P * 128u), b_hi = desc_hi(1024u);
       const uint32_t row_units = (uint32_t)p.P * 8u;            // one halo row, in 16-byte descriptor units
       const uint32_t mt_units = 16u * row_units;                 // next M-tile = 16 halo rows further
@@ -349,7 +354,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
               const __nv_bfloat16* rp = p.residual + pix * p.res_ld + j * 16;
 #pragma unroll
               for (int k = 0; k < 16; k += 4) {
-                float4 rv = ld4(rp + k);
+                float4 rv = (p.flags & FLAG_F16) ? ld4(reinterpret_cast<const __half*>(rp) + k) : ld4(rp + k);
                 f[k] += rv.x; f[k + 1] += rv.y; f[k + 2] += rv.z; f[k + 3] += rv.w;
               }
             }
@@ -358,10 +363,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
               for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
             }
             uint32_t o[8];
+            if (p.flags & FLAG_F16) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-              o[k] = *reinterpret_cast<uint32_t*>(&h);
+              for (int k = 0; k < 8; ++k) {
+                __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+                o[k] = *reinterpret_cast<uint32_t*>(&h);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                o[k] = *reinterpret_cast<uint32_t*>(&h);
+              }
             }
             uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_ld + j * 16);
             op[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -533,7 +546,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
   } else if (warp == 1) {
     // ===== MMA issuer: leader CTA only =====
     if (leader) {
-      constexpr uint32_t idesc = make_idesc(256, N, 0, 0);
+      const int bf = (p.flags & FLAG_F16) ? 0 : 1;
+      const uint32_t idesc = make_idesc(256, N, 0, 0, bf, bf);
       const uint32_t a_hi = desc_hi((uint32_t)p.P * 128u), b_hi = desc_hi(1024u);
       const uint32_t row_units = (uint32_t)p.P * 8u;
       const uint32_t mt_units = 16u * row_units;
@@ -619,7 +633,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
               const __nv_bfloat16* rp = p.residual + pix * p.res_ld + j * 16;
 #pragma unroll
               for (int k = 0; k < 16; k += 4) {
-                float4 rv = ld4(rp + k);
+                float4 rv = (p.flags & FLAG_F16) ? ld4(reinterpret_cast<const __half*>(rp) + k) : ld4(rp + k);
                 f[k] += rv.x; f[k + 1] += rv.y; f[k + 2] += rv.z; f[k + 3] += rv.w;
               }
             }
@@ -628,10 +642,18 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
               for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
             }
             uint32_t o[8];
+            if (p.flags & FLAG_F16) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-              o[k] = *reinterpret_cast<uint32_t*>(&h);
+              for (int k = 0; k < 8; ++k) {
+                __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+                o[k] = *reinterpret_cast<uint32_t*>(&h);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                o[k] = *reinterpret_cast<uint32_t*>(&h);
+              }
             }
             uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_ld + j * 16);
             op[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -656,8 +678,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
 // weight packing: OIHW fp32 -> bf16 [chunk][tap][N rows][64] in the SWIZZLE_128B shared-memory image
 //   forward: rows = co, K = ci;   dgrad: rows = ci, K = co, taps flipped
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
-                                        __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int KS) {
+template <typename T>
+__global__ void pack_weight_bf16_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int Cout,
+                                        int Cin, int KS) {
   const int taps = KS * KS;
   const long long n = (long long)Cout * Cin * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -666,7 +689,8 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat
     const long long r = i / taps;
     const int ci = (int)(r % Cin);
     const int co = (int)(r / Cin);
-    const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+    T v;
+    stf(&v, w[i]);
     if (wf) {   // tile (chunk = ci/64, tap t): row co, k = ci%64
       const int c = ci >> 6, k = ci & 63;
       const long long tile = ((long long)c * taps + t) * Cout * 64;
@@ -1271,8 +1295,21 @@ int tsr_pack_conv_weight_bf16(const float* w_oihw, void* w_fwd, void* w_dgrad, i
   long long n = (long long)Cout * Cin * KS * KS;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 2048) blocks = 2048;
-  pack_weight_bf16_kernel<<<blocks, 256, 0, stream>>>(w_oihw, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad, Cout, Cin, KS);
+  pack_weight_bf16_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(w_oihw, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad, Cout, Cin, KS);
   TSR_CHECK_LAUNCH("pack_conv_weight_bf16");
+  return TSR_OK;
+}
+
+// same tile image with fp16 elements (forward weights of the "fp16" precision mode)
+int tsr_pack_conv_weight_f16(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int KS,
+                             cudaStream_t stream) {
+  TSR_REQUIRE(w_oihw && (w_fwd || w_dgrad), "pack_conv_weight_f16: null pointer");
+  TSR_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "pack_conv_weight_f16: Cin, Cout must be multiples of 64");
+  long long n = (long long)Cout * Cin * KS * KS;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 2048) blocks = 2048;
+  pack_weight_bf16_kernel<__half><<<blocks, 256, 0, stream>>>(w_oihw, (__half*)w_fwd, (__half*)w_dgrad, Cout, Cin, KS);
+  TSR_CHECK_LAUNCH("pack_conv_weight_f16");
   return TSR_OK;
 }
 

@@ -447,9 +447,9 @@ bn_apply_v_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ s
   }
 }
 
-template <typename T>
+template <typename T, typename Ty = T>
 __global__ void __launch_bounds__(256)
-bn_bwd_partial_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict__ y, int y_ld,
+bn_bwd_partial_v_kernel(const T* __restrict__ da, int da_ld, const Ty* __restrict__ y, int y_ld,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ mean, const float* __restrict__ invstd, int npix, int C, int relu,
                         float* __restrict__ partial, int rows_per_block) {
@@ -469,9 +469,9 @@ bn_bwd_partial_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict
     for (; r + lanes < r1; r += 2 * lanes) {            // 4 independent 16-byte loads in flight per thread
       float g0[N], v0[N], g1[N], v1[N];
       V16<T>::load(da + (long long)r * da_ld + q * N, g0);
-      V16<T>::load(y + (long long)r * y_ld + q * N, v0);
+      V16<Ty>::load(y + (long long)r * y_ld + q * N, v0);
       V16<T>::load(da + (long long)(r + lanes) * da_ld + q * N, g1);
-      V16<T>::load(y + (long long)(r + lanes) * y_ld + q * N, v1);
+      V16<Ty>::load(y + (long long)(r + lanes) * y_ld + q * N, v1);
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         if (relu && !(fmaf(v0[i], sc[i], sh[i]) > 0.f)) g0[i] = 0.f;
@@ -483,7 +483,7 @@ bn_bwd_partial_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict
     for (; r < r1; r += lanes) {
       float g[N], v[N];
       V16<T>::load(da + (long long)r * da_ld + q * N, g);
-      V16<T>::load(y + (long long)r * y_ld + q * N, v);
+      V16<Ty>::load(y + (long long)r * y_ld + q * N, v);
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         if (relu && !(fmaf(v[i], sc[i], sh[i]) > 0.f)) g[i] = 0.f;
@@ -507,9 +507,9 @@ bn_bwd_partial_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict
   }
 }
 
-template <typename T>
+template <typename T, typename Ty = T>
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict__ y, int y_ld,
+bn_bwd_apply_v_kernel(const T* __restrict__ da, int da_ld, const Ty* __restrict__ y, int y_ld,
                       const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                       const float* __restrict__ invstd, const float* __restrict__ c1, const float* __restrict__ c2,
                       T* __restrict__ dy, int dy_ld, long long npix, int C, int relu) {
@@ -530,7 +530,7 @@ bn_bwd_apply_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict__
   for (long long p = (long long)blockIdx.x * (256 / qn) + threadIdx.x / qn; p < npix; p += pstride) {
     float g[N], v[N], o[N];
     V16<T>::load(da + p * da_ld + q * N, g);
-    V16<T>::load(y + p * y_ld + q * N, v);
+    V16<Ty>::load(y + p * y_ld + q * N, v);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       if (relu && !(fmaf(v[k], sc[k], sh[k]) > 0.f)) g[k] = 0.f;
@@ -540,9 +540,9 @@ bn_bwd_apply_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict__
   }
 }
 
-template <typename T>
+template <typename T, typename Ta = T>
 __global__ void __launch_bounds__(256)
-relu_bwd_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict__ a, int a_ld, T* __restrict__ dz, int dz_ld,
+relu_bwd_v_kernel(const T* __restrict__ da, int da_ld, const Ta* __restrict__ a, int a_ld, T* __restrict__ dz, int dz_ld,
                   long long npix, int C) {
   constexpr int N = V16<T>::N;
   const int qn = C / N;
@@ -553,7 +553,7 @@ relu_bwd_v_kernel(const T* __restrict__ da, int da_ld, const T* __restrict__ a, 
     const long long p = i / qn;
     float g[N], v[N];
     V16<T>::load(da + p * da_ld + q * N, g);
-    V16<T>::load(a + p * a_ld + q * N, v);
+    V16<Ta>::load(a + p * a_ld + q * N, v);
 #pragma unroll
     for (int k = 0; k < N; ++k)
       if (!(v[k] > 0.f)) g[k] = 0.f;
@@ -608,14 +608,17 @@ int tsr_bn_train_stats(const void* y, int y_ld, int y_bf16, long long npix, int 
   if (y_bf16 && C % 8 == 0 && y_ld % 8 == 0) {
     int tv = redv_threads(C, 8);
     size_t smv = (size_t)(tv / (C / 8)) * 2 * C * sizeof(float);
-    bn_stats_partial_v_kernel<__nv_bfloat16><<<nb, tv, smv, stream>>>((const __nv_bfloat16*)y, y_ld, (int)npix, C, (float*)workspace, rpb);
+    if (y_bf16 == TSR_DT_F16)
+      bn_stats_partial_v_kernel<__half><<<nb, tv, smv, stream>>>((const __half*)y, y_ld, (int)npix, C, (float*)workspace, rpb);
+    else
+      bn_stats_partial_v_kernel<__nv_bfloat16><<<nb, tv, smv, stream>>>((const __nv_bfloat16*)y, y_ld, (int)npix, C, (float*)workspace, rpb);
   } else if (!y_bf16) {
     int tv = redv_threads(C, 4);
     size_t smv = (size_t)(tv / (C / 4)) * 2 * C * sizeof(float);
     bn_stats_partial_v_kernel<float><<<nb, tv, smv, stream>>>((const float*)y, y_ld, (int)npix, C, (float*)workspace, rpb);
   } else {
     size_t smem = (size_t)2 * th * sizeof(float4);
-    bn_stats_partial_kernel<__nv_bfloat16><<<nb, th, smem, stream>>>((const __nv_bfloat16*)y, y_ld, (int)npix, C, (float*)workspace, rpb);
+    TSR_DISPATCH_T(y_bf16, T, bn_stats_partial_kernel<T><<<nb, th, smem, stream>>>((const T*)y, y_ld, (int)npix, C, (float*)workspace, rpb));
   }
   TSR_CHECK_LAUNCH("bn_stats_partial");
   bn_finalize_kernel<<<tsr_cdiv(C, 32), dim3(32, 32), 0, stream>>>((const float*)workspace, nb, C, (double)npix, gamma, beta,
@@ -651,16 +654,13 @@ int tsr_bn_apply(const void* y, int y_ld, int y_bf16, const float* scale, const 
   TSR_REQUIRE(C % 4 == 0 && y_ld % 4 == 0 && out_ld % 4 == 0, "bn_apply: C and strides must be multiples of 4");
   int grid = ew_grid(npix * (C / 4));
 #define ARGS(Ti, To) (const Ti*)y, y_ld, scale, shift, (To*)out, out_ld, npix, C, relu
-  if (y_bf16 && out_bf16 && C % 8 == 0 && 256 % (C / 8) == 0 && y_ld % 8 == 0 && out_ld % 8 == 0) {
-    bn_apply_v_kernel<__nv_bfloat16><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>(ARGS(__nv_bfloat16, __nv_bfloat16));
+  if (y_bf16 && y_bf16 == out_bf16 && C % 8 == 0 && 256 % (C / 8) == 0 && y_ld % 8 == 0 && out_ld % 8 == 0) {
+    if (y_bf16 == TSR_DT_F16) bn_apply_v_kernel<__half><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>(ARGS(__half, __half));
+    else bn_apply_v_kernel<__nv_bfloat16><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>(ARGS(__nv_bfloat16, __nv_bfloat16));
   } else if (!y_bf16 && !out_bf16 && 256 % (C / 4) == 0) {
     bn_apply_v_kernel<float><<<grid, 256, 0, stream>>>(ARGS(float, float));
-  } else if (y_bf16) {
-    if (out_bf16) bn_apply_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>(ARGS(__nv_bfloat16, __nv_bfloat16));
-    else bn_apply_kernel<__nv_bfloat16, float><<<grid, 256, 0, stream>>>(ARGS(__nv_bfloat16, float));
   } else {
-    if (out_bf16) bn_apply_kernel<float, __nv_bfloat16><<<grid, 256, 0, stream>>>(ARGS(float, __nv_bfloat16));
-    else bn_apply_kernel<float, float><<<grid, 256, 0, stream>>>(ARGS(float, float));
+    TSR_DISPATCH_T(y_bf16, Ti, TSR_DISPATCH_T(out_bf16, To, bn_apply_kernel<Ti, To><<<grid, 256, 0, stream>>>(ARGS(Ti, To))));
   }
 #undef ARGS
   TSR_CHECK_LAUNCH("bn_apply");
@@ -680,20 +680,27 @@ int tsr_bn_backward(const void* da, int da_ld, const void* y, int y_ld, void* dy
   float* partial = (float*)workspace;
   float* c1 = partial + (size_t)nb * 2 * C;
   float* c2 = c1 + C;
+  // act_bf16: 0 = everything fp32, 1 = everything bf16, 2 = gradients (da, dy) bf16 + saved activation y fp16
   const bool v8 = act_bf16 && C % 8 == 0 && 256 % (C / 8) == 0 && da_ld % 8 == 0 && y_ld % 8 == 0 && dy_ld % 8 == 0;
   const bool v4 = !act_bf16 && 256 % (C / 4) == 0;
+  typedef __nv_bfloat16 bf;
   if (v8) {
     int tv = redv_threads(C, 8);
     size_t smv = (size_t)(tv / (C / 8)) * 2 * C * sizeof(float);
-    bn_bwd_partial_v_kernel<__nv_bfloat16><<<nb, tv, smv, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
+    if (act_bf16 == TSR_DT_F16)
+      bn_bwd_partial_v_kernel<bf, __half><<<nb, tv, smv, stream>>>((const bf*)da, da_ld, (const __half*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
+    else
+      bn_bwd_partial_v_kernel<bf, bf><<<nb, tv, smv, stream>>>((const bf*)da, da_ld, (const bf*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
   } else if (v4) {
     int tv = redv_threads(C, 4);
     size_t smv = (size_t)(tv / (C / 4)) * 2 * C * sizeof(float);
     bn_bwd_partial_v_kernel<float><<<nb, tv, smv, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
   } else {
     size_t smem = (size_t)2 * th * sizeof(float4);
-    if (act_bf16)
-      bn_bwd_partial_kernel<__nv_bfloat16, __nv_bfloat16><<<nb, th, smem, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
+    if (act_bf16 == TSR_DT_F16)
+      bn_bwd_partial_kernel<bf, __half><<<nb, th, smem, stream>>>((const bf*)da, da_ld, (const __half*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
+    else if (act_bf16)
+      bn_bwd_partial_kernel<bf, bf><<<nb, th, smem, stream>>>((const bf*)da, da_ld, (const bf*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
     else
       bn_bwd_partial_kernel<float, float><<<nb, th, smem, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
   }
@@ -701,12 +708,16 @@ int tsr_bn_backward(const void* da, int da_ld, const void* y, int y_ld, void* dy
   bn_bwd_finalize_kernel<<<tsr_cdiv(C, 32), dim3(32, 32), 0, stream>>>(partial, nb, C, (double)npix, dgamma, dbeta, accumulate, c1, c2, training);
   TSR_CHECK_LAUNCH("bn_bwd_finalize");
   int grid = ew_grid(npix * (C / 4));
-  if (v8)
-    bn_bwd_apply_v_kernel<__nv_bfloat16><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (__nv_bfloat16*)dy, dy_ld, npix, C, relu);
+  if (v8 && act_bf16 == TSR_DT_F16)
+    bn_bwd_apply_v_kernel<bf, __half><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>((const bf*)da, da_ld, (const __half*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (bf*)dy, dy_ld, npix, C, relu);
+  else if (v8)
+    bn_bwd_apply_v_kernel<bf, bf><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>((const bf*)da, da_ld, (const bf*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (bf*)dy, dy_ld, npix, C, relu);
   else if (v4)
     bn_bwd_apply_v_kernel<float><<<grid, 256, 0, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (float*)dy, dy_ld, npix, C, relu);
+  else if (act_bf16 == TSR_DT_F16)
+    bn_bwd_apply_kernel<bf, __half, bf><<<grid, 256, 0, stream>>>((const bf*)da, da_ld, (const __half*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (bf*)dy, dy_ld, npix, C, relu);
   else if (act_bf16)
-    bn_bwd_apply_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (__nv_bfloat16*)dy, dy_ld, npix, C, relu);
+    bn_bwd_apply_kernel<bf, bf, bf><<<grid, 256, 0, stream>>>((const bf*)da, da_ld, (const bf*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (bf*)dy, dy_ld, npix, C, relu);
   else
     bn_bwd_apply_kernel<float, float, float><<<grid, 256, 0, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (float*)dy, dy_ld, npix, C, relu);
   TSR_CHECK_LAUNCH("bn_bwd_apply");
@@ -723,10 +734,17 @@ int tsr_relu_backward(const void* da, int da_ld, const void* a, int a_ld, void* 
   TSR_REQUIRE(da && a && dz, "relu_backward: null pointer");
   TSR_REQUIRE(C % 4 == 0 && da_ld % 4 == 0 && a_ld % 4 == 0 && dz_ld % 4 == 0, "relu_backward: C and strides must be multiples of 4");
   int grid = ew_grid(npix * (C / 4));
-  if (act_bf16 && C % 8 == 0 && da_ld % 8 == 0 && a_ld % 8 == 0 && dz_ld % 8 == 0)
-    relu_bwd_v_kernel<__nv_bfloat16><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)a, a_ld, (__nv_bfloat16*)dz, dz_ld, npix, C);
+  // act_bf16: 0 = fp32, 1 = bf16, 2 = gradients (da, dz) bf16 + stored activation a fp16
+  typedef __nv_bfloat16 bf;
+  const bool v8 = act_bf16 && C % 8 == 0 && da_ld % 8 == 0 && a_ld % 8 == 0 && dz_ld % 8 == 0;
+  if (v8 && act_bf16 == TSR_DT_F16)
+    relu_bwd_v_kernel<bf, __half><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>((const bf*)da, da_ld, (const __half*)a, a_ld, (bf*)dz, dz_ld, npix, C);
+  else if (v8)
+    relu_bwd_v_kernel<bf, bf><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>((const bf*)da, da_ld, (const bf*)a, a_ld, (bf*)dz, dz_ld, npix, C);
+  else if (act_bf16 == TSR_DT_F16)
+    relu_bwd_kernel<bf, __half, bf><<<grid, 256, 0, stream>>>((const bf*)da, da_ld, (const __half*)a, a_ld, (bf*)dz, dz_ld, npix, C);
   else if (act_bf16)
-    relu_bwd_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)da, da_ld, (const __nv_bfloat16*)a, a_ld, (__nv_bfloat16*)dz, dz_ld, npix, C);
+    relu_bwd_kernel<bf, bf, bf><<<grid, 256, 0, stream>>>((const bf*)da, da_ld, (const bf*)a, a_ld, (bf*)dz, dz_ld, npix, C);
   else
     relu_bwd_v_kernel<float><<<grid, 256, 0, stream>>>((const float*)da, da_ld, (const float*)a, a_ld, (float*)dz, dz_ld, npix, C);
   TSR_CHECK_LAUNCH("relu_backward");
@@ -738,13 +756,7 @@ int tsr_copy_channels(const void* x, int x_ld, int x_bf16, void* out, int out_ld
   TSR_REQUIRE(x && out, "copy_channels: null pointer");
   TSR_REQUIRE(C % 4 == 0 && x_ld % 4 == 0 && out_ld % 4 == 0, "copy_channels: C and strides must be multiples of 4");
   int grid = ew_grid(npix * (C / 4));
-  if (x_bf16) {
-    if (out_bf16) copy_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)out, out_ld, npix, C);
-    else copy_kernel<__nv_bfloat16, float><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, x_ld, (float*)out, out_ld, npix, C);
-  } else {
-    if (out_bf16) copy_kernel<float, __nv_bfloat16><<<grid, 256, 0, stream>>>((const float*)x, x_ld, (__nv_bfloat16*)out, out_ld, npix, C);
-    else copy_kernel<float, float><<<grid, 256, 0, stream>>>((const float*)x, x_ld, (float*)out, out_ld, npix, C);
-  }
+  TSR_DISPATCH_T(x_bf16, Ti, TSR_DISPATCH_T(out_bf16, To, copy_kernel<Ti, To><<<grid, 256, 0, stream>>>((const Ti*)x, x_ld, (To*)out, out_ld, npix, C)));
   TSR_CHECK_LAUNCH("copy_channels");
   return TSR_OK;
 }
@@ -752,8 +764,7 @@ int tsr_copy_channels(const void* x, int x_ld, int x_bf16, void* out, int out_ld
 int tsr_nchw_to_nhwc(const float* x, void* out, int out_ld, int out_bf16, int B, int C, int HW, cudaStream_t stream) {
   TSR_REQUIRE(x && out, "nchw_to_nhwc: null pointer");
   int grid = ew_grid((long long)B * C * HW);
-  if (out_bf16) nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(x, (__nv_bfloat16*)out, out_ld, B, C, HW);
-  else nchw_to_nhwc_kernel<float><<<grid, 256, 0, stream>>>(x, (float*)out, out_ld, B, C, HW);
+  TSR_DISPATCH_T(out_bf16, T, nchw_to_nhwc_kernel<T><<<grid, 256, 0, stream>>>(x, (T*)out, out_ld, B, C, HW));
   TSR_CHECK_LAUNCH("nchw_to_nhwc");
   return TSR_OK;
 }
@@ -761,8 +772,7 @@ int tsr_nchw_to_nhwc(const float* x, void* out, int out_ld, int out_bf16, int B,
 int tsr_nhwc_to_nchw(const void* x, int x_ld, int x_bf16, float* out, int B, int C, int HW, cudaStream_t stream) {
   TSR_REQUIRE(x && out, "nhwc_to_nchw: null pointer");
   int grid = ew_grid((long long)B * C * HW);
-  if (x_bf16) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, x_ld, out, B, C, HW);
-  else nhwc_to_nchw_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, x_ld, out, B, C, HW);
+  TSR_DISPATCH_T(x_bf16, T, nhwc_to_nchw_kernel<T><<<grid, 256, 0, stream>>>((const T*)x, x_ld, out, B, C, HW));
   TSR_CHECK_LAUNCH("nhwc_to_nchw");
   return TSR_OK;
 }

@@ -6,9 +6,13 @@ program is one ``torch.autograd.Function`` node (``_ProgramFn``), so the referen
 ``loss.backward()`` / ``optimizer.step()`` protocol (cpu/trainer.py:346-362) keeps working while
 the forward+backward of reference model/tactileSR_model.py runs entirely in our kernels.
 
-Two numeric modes (``tactilesr_b200.set_precision``):
+Three numeric modes (``tactilesr_b200.set_precision``):
   * "fp32": activations fp32, FFMA implicit-GEMM kernels (conv_f32.cu) -- <= 1e-5 parity mode.
-  * "bf16": activations bf16, tcgen05 implicit-GEMM kernels (conv_tc.cu), fp32 accumulate/statistics.
+  * "bf16": activations and gradients bf16, tcgen05 implicit-GEMM kernels (conv_tc.cu), fp32 accumulate/statistics.
+  * "fp16": same tcgen05 kernels at the same speed, but activations and forward weights are stored as fp16
+    (10 mantissa bits, the TF32 mantissa: ~8x less rounding error than bf16 -- the <= 1e-2 tensor-core mode);
+    gradients stay bf16 (range matters there); tcgen05 kind::f16 rejects fp16 x bf16 operands, so when gradients
+    are needed every conv keeps a bf16 copy of its input for the weight-gradient kernel.
 """
 from __future__ import annotations
 
@@ -25,8 +29,8 @@ _WEIGHT_EPOCH = 0          # bumped by FusedAdam.step (in-place kernel updates d
 
 def set_precision(mode: str) -> None:
     global _PRECISION
-    if mode not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
+    if mode not in ("fp32", "bf16", "fp16"):
+        raise ValueError("precision must be 'fp32', 'bf16' or 'fp16'")
     _PRECISION = mode
 
 
@@ -70,9 +74,15 @@ class RunCtx:
     def __init__(self, mode: str, B: int, H: int, W: int, device, training: bool, need_grad: bool):
         self.mode, self.B, self.H, self.W = mode, B, H, W
         self.device, self.training, self.need_grad = device, training, need_grad
-        self.bf16 = 1 if mode == "bf16" else 0
-        self.act_dtype = torch.bfloat16 if self.bf16 else torch.float32
-        self.esize = 2 if self.bf16 else 4
+        # storage-type codes of the C ABI (0 float, 1 bf16, 2 fp16): activations, gradients, and the combined code of
+        # the kernels that read both (tsr_bn_backward / tsr_relu_backward)
+        self.act = {"fp32": 0, "bf16": 1, "fp16": 2}[mode]
+        self.grd = 0 if mode == "fp32" else 1
+        self.mix = self.act
+        self.tc = mode != "fp32"
+        self.act_dtype = (torch.float32, torch.bfloat16, torch.float16)[self.act]
+        self.grad_dtype = (torch.float32, torch.bfloat16)[self.grd]
+        self.esize = 2 if self.tc else 4
         self.npix = B * H * W
         self.bufs: Dict[Buf, torch.Tensor] = {}
         self.grads: Dict[Buf, torch.Tensor] = {}
@@ -80,6 +90,7 @@ class RunCtx:
         self.saved: Dict[object, tuple] = {}
         self.x: Optional[torch.Tensor] = None
         self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        self.xsave: Dict[tuple, torch.Tensor] = {}      # "fp16" mode: bf16 copies of conv inputs (wgrad operands)
         self._ws: Optional[torch.Tensor] = None
 
     # -- buffers ------------------------------------------------------------------------------
@@ -104,7 +115,7 @@ class RunCtx:
             if buf.kind == "plane":
                 t = torch.empty((self.npix,), dtype=torch.float32, device=self.device)
             else:
-                t = torch.empty((self.npix, buf.C), dtype=self.act_dtype, device=self.device)
+                t = torch.empty((self.npix, buf.C), dtype=self.grad_dtype, device=self.device)
             self.grads[buf] = t
             self.grad_written[buf] = False
         return t
@@ -143,12 +154,19 @@ class _PackCache:
         if hit is not None and hit[0] == tag and (hit[2] is not None or not need_dgrad):
             return hit[1], hit[2]
         Cout, Cin, K, _ = w.shape
-        dt = torch.bfloat16 if mode == "bf16" else torch.float32
+        dt = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[mode]
         wf = torch.empty((K * K * Cin * Cout,), dtype=dt, device=w.device)
-        wd = torch.empty_like(wf) if need_dgrad else None
-        fn = "tsr_pack_conv_weight_bf16" if mode == "bf16" else "tsr_pack_conv_weight_f32"
         wc = w.detach().contiguous()
-        _lib.call(fn, wc.data_ptr(), wf.data_ptr(), _ptr(wd), Cout, Cin, K, _lib.stream_ptr())
+        st = _lib.stream_ptr()
+        if mode == "fp16":       # forward weights fp16, data-gradient weights bf16 (gradients are bf16 tensors)
+            wd = torch.empty_like(wf, dtype=torch.bfloat16) if need_dgrad else None
+            _lib.call("tsr_pack_conv_weight_f16", wc.data_ptr(), wf.data_ptr(), 0, Cout, Cin, K, st)
+            if need_dgrad:
+                _lib.call("tsr_pack_conv_weight_bf16", wc.data_ptr(), 0, wd.data_ptr(), Cout, Cin, K, st)
+        else:
+            wd = torch.empty_like(wf) if need_dgrad else None
+            fn = "tsr_pack_conv_weight_bf16" if mode == "bf16" else "tsr_pack_conv_weight_f32"
+            _lib.call(fn, wc.data_ptr(), wf.data_ptr(), _ptr(wd), Cout, Cin, K, st)
         store[mode] = (tag, wf, wd)
         return wf, wd
 
@@ -204,7 +222,7 @@ class HeadOp(Op):
     def fwd(self, c):
         xp, xbs = self._x(c)
         op, old = c.vptr(self.out)
-        _lib.call("tsr_head_fwd", xp, xbs, self.weight.data_ptr(), op, old, c.bf16, c.B, self.sf,
+        _lib.call("tsr_head_fwd", xp, xbs, self.weight.data_ptr(), op, old, c.act, c.B, self.sf,
                   1 if self.relu else 0, _lib.stream_ptr())
 
     def bwd(self, c):
@@ -212,11 +230,11 @@ class HeadOp(Op):
         gp, gld = c.vptr(self.out, grad=True)
         if self.relu:
             ap, ald = c.vptr(self.out)
-            _lib.call("tsr_relu_backward", gp, gld, ap, ald, gp, gld, c.bf16, c.npix, self.out.C, st)
+            _lib.call("tsr_relu_backward", gp, gld, ap, ald, gp, gld, c.mix, c.npix, self.out.C, st)
         xp, xbs = self._x(c)
         g, acc = c.pgrad(self.weight)
         ws, wsb = c.workspace(_lib.lib().tsr_head_wgrad_workspace(c.B))
-        _lib.call("tsr_head_wgrad", xp, xbs, gp, gld, c.bf16, g.data_ptr(), ws, wsb, c.B, self.sf, acc, st)
+        _lib.call("tsr_head_wgrad", xp, xbs, gp, gld, c.grd, g.data_ptr(), ws, wsb, c.B, self.sf, acc, st)
 
 
 class ConvOp(Op):
@@ -242,19 +260,36 @@ class ConvOp(Op):
     def writes(self):
         return (self.out.buf,)
 
-    def _conv(self, c: RunCtx, inp, inld, wpk, bias, res, resld, outp, outld, Cin, Cout, flags):
+    def _conv(self, c: RunCtx, inp, inld, wpk, bias, res, resld, outp, outld, Cin, Cout, flags, on_grads=False):
         st = _lib.stream_ptr()
-        if c.bf16:
+        if c.tc:
             need = _lib.lib().tsr_conv2d_tc_workspace(c.B, c.H, c.W, Cin, Cout, self.K)
             ws, wsb = c.workspace(need)
+            if c.act == 2 and not on_grads:
+                flags |= 2      # fp16 activations / weights (forward); data gradients run on bf16 tensors
             _lib.call("tsr_conv2d_tc", inp, inld, wpk, bias, res, resld, outp, outld, c.B, c.H, c.W, Cin, Cout,
                       self.K, flags, ws, wsb, st)
         else:
             _lib.call("tsr_conv2d_f32", inp, inld, wpk, bias, res, resld, outp, outld, c.B, c.H, c.W, Cin, Cout,
                       self.K, flags, st)
 
+    def _wgrad_input(self, c: RunCtx):
+        """(pointer, ld) of the conv input as the weight-gradient kernel wants it (bf16 in both tensor-core modes)."""
+        if c.act != 2:
+            return c.vptr(self.src)
+        key = (self.src.buf, self.src.c0, self.src.C)
+        t = c.xsave.get(key)
+        if t is None:
+            t = torch.empty((c.npix, self.src.C), dtype=torch.bfloat16, device=c.device)
+            ip, ild = c.vptr(self.src)
+            _lib.call("tsr_copy_channels", ip, ild, 2, t.data_ptr(), self.src.C, 1, c.npix, self.src.C, _lib.stream_ptr())
+            c.xsave[key] = t
+        return t.data_ptr(), self.src.C
+
     def fwd(self, c):
         wf, _ = _PACK.get(self.conv.weight, c.mode, False)
+        if c.need_grad:
+            self._wgrad_input(c)
         ip, ild = c.vptr(self.src)
         op, old = c.vptr(self.out)
         rp, rld = c.vptr(self.residual) if self.residual is not None else (0, 0)
@@ -266,22 +301,23 @@ class ConvOp(Op):
         gp, gld = c.vptr(self.out, grad=True)
         if self.relu:
             ap, ald = c.vptr(self.out)
-            _lib.call("tsr_relu_backward", gp, gld, ap, ald, gp, gld, c.bf16, c.npix, self.Cout, st)
+            _lib.call("tsr_relu_backward", gp, gld, ap, ald, gp, gld, c.mix, c.npix, self.Cout, st)
         # residual branch: d(residual) += dz
         if self.residual is not None:
             first = _first_write(c, self.residual.buf)
             rp, rld = c.vptr(self.residual, grad=True)
             if first:
-                _lib.call("tsr_copy_channels", gp, gld, c.bf16, rp, rld, c.bf16, c.npix, self.Cout, st)
+                _lib.call("tsr_copy_channels", gp, gld, c.grd, rp, rld, c.grd, c.npix, self.Cout, st)
             else:
                 raise NotImplementedError("residual gradient accumulation after another writer")
         # weight / bias gradients
         ip, ild = c.vptr(self.src)
         g, acc = c.pgrad(self.conv.weight)
-        if c.bf16:
+        if c.tc:
             need = _lib.lib().tsr_conv2d_wgrad_tc_workspace(c.B, c.H, c.W, self.Cin, self.Cout, self.K)
             ws, wsb = c.workspace(need)
-            _lib.call("tsr_conv2d_wgrad_tc", ip, ild, gp, gld, g.data_ptr(), ws, wsb, c.B, c.H, c.W, self.Cin,
+            xp, xld = self._wgrad_input(c)
+            _lib.call("tsr_conv2d_wgrad_tc", xp, xld, gp, gld, g.data_ptr(), ws, wsb, c.B, c.H, c.W, self.Cin,
                       self.Cout, self.K, acc, st)
         else:
             need = _lib.lib().tsr_conv2d_wgrad_f32_workspace(c.B, c.H, c.W, self.Cin, self.Cout, self.K)
@@ -299,14 +335,14 @@ class ConvOp(Op):
                     gb.zero_()
             else:
                 ws, wsb = c.workspace(_lib.lib().tsr_colsum_workspace(c.npix, self.Cout))
-                _lib.call("tsr_colsum", gp, gld, c.bf16, c.npix, self.Cout, gb.data_ptr(), ws, wsb, accb, st)
+                _lib.call("tsr_colsum", gp, gld, c.grd, c.npix, self.Cout, gb.data_ptr(), ws, wsb, accb, st)
         # data gradient
         if self.src_needs_grad:
             _, wd = _PACK.get(self.conv.weight, c.mode, True)
             first = _first_write(c, self.src.buf)
             dp, dld = c.vptr(self.src, grad=True)
             self._conv(c, gp, gld, wd.data_ptr(), 0, 0 if first else dp, 0 if first else dld, dp, dld, self.Cout,
-                       self.Cin, 0)
+                       self.Cin, 0, on_grads=True)
 
 
 class BNReLUOp(Op):
@@ -337,14 +373,14 @@ class BNReLUOp(Op):
             ws, wsb = c.workspace(_lib.lib().tsr_bn_workspace(c.npix, C))
             track = c.training and bn.track_running_stats and bn.running_mean is not None
             mom = 0.1 if bn.momentum is None else bn.momentum
-            _lib.call("tsr_bn_train_stats", yp, yld, c.bf16, c.npix, C, bn.weight.data_ptr(), bn.bias.data_ptr(),
+            _lib.call("tsr_bn_train_stats", yp, yld, c.act, c.npix, C, bn.weight.data_ptr(), bn.bias.data_ptr(),
                       _ptr(bn.running_mean) if track else 0, _ptr(bn.running_var) if track else 0,
                       _ptr(bn.num_batches_tracked) if track else 0, mom, bn.eps, sc, sh, mu, iv, ws, wsb, st)
         else:
             _lib.call("tsr_bn_eval_coeffs", C, bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
                       bn.running_var.data_ptr(), bn.eps, sc, sh, mu, iv, st)
         op, old = c.vptr(self.out)
-        _lib.call("tsr_bn_apply", yp, yld, c.bf16, sc, sh, op, old, c.bf16, c.npix, C, 1 if self.relu else 0, st)
+        _lib.call("tsr_bn_apply", yp, yld, c.act, sc, sh, op, old, c.act, c.npix, C, 1 if self.relu else 0, st)
         c.saved[self] = (coef, use_batch)
 
     def bwd(self, c):
@@ -361,7 +397,7 @@ class BNReLUOp(Op):
         gb, accb = c.pgrad(self.bn.bias)
         assert accw == accb
         ws, wsb = c.workspace(_lib.lib().tsr_bn_backward_workspace(c.npix, C))
-        _lib.call("tsr_bn_backward", gp, gld, yp, yld, dp, dld, c.bf16, sc, sh, mu, iv, gw.data_ptr(), gb.data_ptr(),
+        _lib.call("tsr_bn_backward", gp, gld, yp, yld, dp, dld, c.mix, sc, sh, mu, iv, gw.data_ptr(), gb.data_ptr(),
                   accw, c.npix, C, 1 if self.relu else 0, 1 if use_batch else 0, ws, wsb, st)
 
 
@@ -384,7 +420,7 @@ class TailOp(Op):
 
     def fwd(self, c):
         ip, ild = c.vptr(self.src)
-        _lib.call("tsr_tail_fwd", ip, ild, c.bf16, self.conv.weight.data_ptr(), c.alloc(self.out).data_ptr(), c.B, c.H,
+        _lib.call("tsr_tail_fwd", ip, ild, c.act, self.conv.weight.data_ptr(), c.alloc(self.out).data_ptr(), c.B, c.H,
                   c.W, self.src.C, 1 if self.relu else 0, _lib.stream_ptr())
 
     def bwd(self, c):
@@ -394,12 +430,12 @@ class TailOp(Op):
         ip, ild = c.vptr(self.src)
         g, acc = c.pgrad(self.conv.weight)
         ws, wsb = c.workspace(_lib.lib().tsr_tail_wgrad_workspace(c.B, c.H, c.W, self.src.C))
-        _lib.call("tsr_tail_wgrad", ip, ild, c.bf16, dout.data_ptr(), out.data_ptr(), g.data_ptr(), ws, wsb, c.B, c.H,
+        _lib.call("tsr_tail_wgrad", ip, ild, c.act, dout.data_ptr(), out.data_ptr(), g.data_ptr(), ws, wsb, c.B, c.H,
                   c.W, self.src.C, 1 if self.relu else 0, acc, st)
         first = _first_write(c, self.src.buf)
         assert first
         dp, dld = c.vptr(self.src, grad=True)
-        _lib.call("tsr_tail_dgrad", dout.data_ptr(), out.data_ptr(), self.conv.weight.data_ptr(), dp, dld, c.bf16, c.B,
+        _lib.call("tsr_tail_dgrad", dout.data_ptr(), out.data_ptr(), self.conv.weight.data_ptr(), dp, dld, c.grd, c.B,
                   c.H, c.W, self.src.C, 1 if self.relu else 0, st)
 
 
@@ -415,7 +451,7 @@ class InputOp(Op):
     def fwd(self, c):
         x = c.x
         t = c.alloc(self.out)
-        _lib.call("tsr_nchw_to_nhwc", x.data_ptr(), t.data_ptr(), self.out.C, c.bf16, c.B, self.out.C, c.H * c.W,
+        _lib.call("tsr_nchw_to_nhwc", x.data_ptr(), t.data_ptr(), self.out.C, c.act, c.B, self.out.C, c.H * c.W,
                   _lib.stream_ptr())
 
     def bwd(self, c):
@@ -483,7 +519,7 @@ def run_forward(prog: Program, x: torch.Tensor, training: bool, need_grad: bool,
     else:
         out = torch.empty((B, prog.out.C, H, W), dtype=torch.float32, device=x.device)
         t = c.bufs[prog.out]
-        _lib.call("tsr_nhwc_to_nchw", t.data_ptr(), prog.out.C, c.bf16, out.data_ptr(), B, prog.out.C, H * W,
+        _lib.call("tsr_nhwc_to_nchw", t.data_ptr(), prog.out.C, c.act, out.data_ptr(), B, prog.out.C, H * W,
                   _lib.stream_ptr())
     return out, c
 
@@ -496,7 +532,7 @@ def run_backward(prog: Program, c: RunCtx, dout: torch.Tensor, hooks=None) -> Di
     else:
         g = c.galloc(prog.out)
         c.grad_written[prog.out] = True
-        _lib.call("tsr_nchw_to_nhwc", dout.data_ptr(), g.data_ptr(), prog.out.C, c.bf16, c.B, prog.out.C, c.H * c.W,
+        _lib.call("tsr_nchw_to_nhwc", dout.data_ptr(), g.data_ptr(), prog.out.C, c.grd, c.B, prog.out.C, c.H * c.W,
                   _lib.stream_ptr())
     # reverse sweep; gradient buffers are dropped as soon as their producer has consumed them
     for i in range(len(prog.ops) - 1, -1, -1):
@@ -559,7 +595,7 @@ class _ProgramFn(torch.autograd.Function):
             gb = c.grads.get(prog.in_buf)
             if gb is not None:
                 gx = torch.empty((c.B, prog.in_buf.C, c.H, c.W), dtype=torch.float32, device=c.device)
-                _lib.call("tsr_nhwc_to_nchw", gb.data_ptr(), prog.in_buf.C, c.bf16, gx.data_ptr(), c.B, prog.in_buf.C,
+                _lib.call("tsr_nhwc_to_nchw", gb.data_ptr(), prog.in_buf.C, c.grd, gx.data_ptr(), c.B, prog.in_buf.C,
                           c.H * c.W, _lib.stream_ptr())
         fin = ctx.holder.get("grad_done")
         if fin is not None:

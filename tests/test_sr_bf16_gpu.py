@@ -123,7 +123,7 @@ def test_bf16_loss_curve_tracks_fp32_mode():
     from tactilesr_b200.optim import FusedAdam
     curves = {}
     try:
-        for mode in ("fp32", "bf16"):
+        for mode in ("fp32", "bf16", "fp16"):
             tb.set_precision(mode)
             torch.manual_seed(42)
             m = TactileSR().cuda().train()
@@ -143,3 +143,71 @@ def test_bf16_loss_curve_tracks_fp32_mode():
     print("loss curve max rel diff", rel.max(), curves["fp32"][[0, 10, 39]], curves["bf16"][[0, 10, 39]])
     assert rel.mean() < 5e-2 and rel.max() < 0.15, (rel.mean(), rel.max())
     assert curves["bf16"][-1] < curves["bf16"][0]
+    rel16 = np.abs(curves["fp16"] - curves["fp32"]) / curves["fp32"]
+    print("fp16 loss curve mean / max rel diff", rel16.mean(), rel16.max())
+    assert rel16.mean() < 5e-2 and rel16.max() < 0.15, (rel16.mean(), rel16.max())
+
+
+@pytest.mark.parametrize("Cin,Cout,KS,B", [(64, 64, 3, 2), (128, 128, 5, 3), (256, 64, 1, 2), (64, 128, 3, 1)])
+def test_tc_conv_fp16_forward(Cin, Cout, KS, B):
+    """"fp16" precision mode at kernel level: forward conv on fp16 operands (flags bit 1) against fp32 math on the same
+    rounded operands, and the fp16 -> bf16 copy that feeds the (all-bf16) weight-gradient kernel."""
+    import torch.nn.functional as F
+    from tactilesr_b200 import _lib
+    torch.manual_seed(7 * Cin + Cout + KS)
+    H = W = 40
+    dev = "cuda"
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(B, H, W, Cin, device=dev).to(torch.float16)
+    w = torch.randn(Cout, Cin, KS, KS, device=dev) / (Cin * KS * KS) ** 0.5
+    wh = w.to(torch.float16).float()
+    bias = torch.randn(Cout, device=dev)
+    res = torch.randn(B, H, W, Cout, device=dev).to(torch.float16)
+    wf = torch.empty(KS * KS * Cin * Cout, dtype=torch.float16, device=dev)
+    _lib.call("tsr_pack_conv_weight_f16", w.data_ptr(), wf.data_ptr(), 0, Cout, Cin, KS, st)
+    out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=dev)
+    _lib.call("tsr_conv2d_tc", x.data_ptr(), Cin, wf.data_ptr(), bias.data_ptr(), res.data_ptr(), Cout, out.data_ptr(), Cout,
+              B, H, W, Cin, Cout, KS, 1 | 2, 0, 0, st)
+    ref = torch.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wh, bias, padding=KS // 2).permute(0, 2, 3, 1) + res.float())
+    e = rel_l2(out.float(), ref)
+    assert e < 5e-4, e                              # fp16 rounding of the stored output (2^-12 per element)
+    xb = torch.empty(B, H, W, Cin, dtype=torch.bfloat16, device=dev)
+    _lib.call("tsr_copy_channels", x.data_ptr(), Cin, 2, xb.data_ptr(), Cin, 1, B * H * W, Cin, st)
+    assert torch.equal(xb, x.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("S", [1, 7])
+def test_sr_fp16_train_step_within_1e_2(S):
+    """"fp16" tensor-core mode (fp16 activations / forward weights = the TF32 mantissa, bf16 gradients, fp32
+    accumulation): north_star's <= 1e-2 relative bound on the SR output, train and eval, against the fp64 reference run;
+    parameter gradients at 5e-2 rel-L2 (bf16 gradient tensors) or the autocast yardstick, whichever is larger."""
+    import tactilesr_b200 as tb
+    from tactilesr_b200.functional import mse_hr_loss
+    g = load_golden(f"tactilesr_fwdbwd_s{S}.npz")
+    y_out, y_g, g64, y_eval = _autocast_yardstick(S, g)
+    tb.set_precision("fp16")
+    try:
+        m = _model(S, int(g["seed_w"])).train()
+        LR, HR_raw = sr_inputs(int(g["B"]), S, int(g["seed_x"]))
+        out = m(LR.cuda())
+        e_out = rel_l2(out, g["f64/out"])
+        print(f"fp16 S={S}: out rel-L2 ours {e_out:.3e}  (autocast-bf16 yardstick {y_out:.3e})")
+        assert e_out < 1e-2, e_out
+        loss = mse_hr_loss(out, HR_raw.cuda(), 10.0)
+        assert abs(loss.item() - float(g["f64/loss"])) / float(g["f64/loss"]) < 1e-2
+        loss.backward()
+        errs = []
+        for n, p in m.named_parameters():
+            if n not in y_g:
+                continue
+            e = rel_l2(p.grad, g64[n])
+            errs.append(e)
+            assert e < max(5e-2, 1.5 * y_g[n]), (n, e, y_g[n])
+        print(f"fp16 S={S}: grad rel-L2 median {np.median(errs):.2e} max {np.max(errs):.2e}")
+        m = _model(S, int(g["seed_w"])).eval()
+        with torch.no_grad():
+            e_eval = rel_l2(m(LR.cuda()), g["f64/out_eval"])
+        print(f"fp16 S={S}: eval out rel-L2 ours {e_eval:.3e}")
+        assert e_eval < 1e-2, e_eval
+    finally:
+        tb.set_precision("fp32")
