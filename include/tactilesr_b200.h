@@ -136,6 +136,14 @@ int tsr_linear_bwd(const float* dy, const float* out, const float* x, const floa
  * alphaBeta (B,3), depth (B,100,100) -> HR (B,100,100), LRd (B,16), psf (B,99,99; may be NULL). */
 int tsr_psf_forward(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, int B,
                     tsr_stream_t stream);
+/* the two implementations behind tsr_psf_forward: tcgen05 (fp16 hi/lo split operands, fp32-accurate; default) and FFMA;
+ * tsr_set_psf_mode(0 | 1) selects which one tsr_psf_forward runs. */
+int tsr_psf_forward_tc(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, int B,
+                       tsr_stream_t stream);
+int tsr_psf_forward_ffma(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, int B,
+                         tsr_stream_t stream);
+void tsr_set_psf_mode(int mode);
+int tsr_get_psf_mode(void);
 /* its backward: d alphaBeta (B,3) from dLRd (B,16), dHR (B,100,100), dpsf (B,99,99) -- each may be NULL (= 0). */
 int tsr_psf_backward(const float* alphaBeta, const float* depth, const float* HR, const float* dLRd, const float* dHR,
                      const float* dpsf, float* dalphaBeta, int B, tsr_stream_t stream);

@@ -56,6 +56,10 @@ SIGNATURES = {
     "tsr_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "tsr_linear_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "tsr_psf_forward": (_I, [_P, _P, _P, _P, _P, _I, _P]),
+    "tsr_psf_forward_tc": (_I, [_P, _P, _P, _P, _P, _I, _P]),
+    "tsr_psf_forward_ffma": (_I, [_P, _P, _P, _P, _P, _I, _P]),
+    "tsr_set_psf_mode": (None, [_I]),
+    "tsr_get_psf_mode": (_I, []),
     "tsr_psf_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P]),
     # tensor-core (tcgen05) convolutions
     "tsr_pack_conv_weight_bf16": (_I, [_P, _P, _P, _I, _I, _I, _P]),

@@ -389,8 +389,9 @@ constexpr size_t BWD_SMEM = (size_t)(4 * PLANE + 2 * TABN + 5 * 4 * N + N + 32 +
 
 extern "C" {
 
-// (HR, LRd, psf) = PSF forward model of `depth` (B,100,100) under alphaBeta (B,3).  psf may be NULL.
-int tsr_psf_forward(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, int B,
+// FFMA version of tsr_psf_forward (the default is the tensor-core kernel of psf_tc.cu; tsr_set_psf_mode(1) selects
+// this one): one CTA per sample, register-window separable passes.
+int tsr_psf_forward_ffma(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, int B,
                     cudaStream_t stream) {
   TSR_REQUIRE(alphaBeta && depth && HR && LRd && B > 0, "psf_forward: bad argument");
   TSR_CUDA(cudaFuncSetAttribute(psf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));

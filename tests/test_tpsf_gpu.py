@@ -94,3 +94,34 @@ def test_tpsf_edge_cases():
         assert rel_l2(LRd, LRdo[sl]) < 5e-5 or LRdo[sl].abs().max() < 1e-12
     with pytest.raises(AssertionError):
         m(LR.cuda(), depth[:2].cuda())
+
+
+@pytest.mark.parametrize("B", [1, 5, 700])
+def test_psf_tensor_core_forward_matches_ffma_forward(B):
+    """The tcgen05 forward (fp16 hi/lo split operands, fp32 TMEM accumulation) against the FFMA forward on the same
+    inputs, through the C ABI: wide beta / gamma ranges, ragged batch (700 > 2 CTAs x 148 SMs => persistent loop),
+    a depth map scaled by 3 (power-of-two pre-scaling path) and an all-zero one."""
+    from oracle import tpsf_oracle as po
+    from tactilesr_b200 import _lib
+    g = torch.Generator().manual_seed(B)
+    ab = torch.stack([torch.rand(B, generator=g) * 2 + 0.2, torch.rand(B, generator=g) * 3 + 0.25,
+                      torch.rand(B, generator=g) * 40 + 0.4], 1).cuda().contiguous()
+    depth = po.synthetic_depth(min(B, 16), 5).repeat((B + 15) // 16, 1, 1)[:B].clone()
+    if B > 2:
+        depth[1] *= 3.0
+        depth[2] = 0.0
+    depth = depth.cuda().contiguous()
+    st = torch.cuda.current_stream().cuda_stream
+    outs = {}
+    for name in ("tsr_psf_forward_ffma", "tsr_psf_forward_tc"):
+        HR = torch.empty(B, 100, 100, device="cuda"); LRd = torch.empty(B, 16, device="cuda"); psf = torch.empty(B, 99, 99, device="cuda")
+        _lib.call(name, ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), B, st)
+        outs[name] = (HR, LRd, psf)
+    (h0, l0, p0), (h1, l1, p1) = outs["tsr_psf_forward_ffma"], outs["tsr_psf_forward_tc"]
+    assert torch.isfinite(h1).all() and torch.isfinite(l1).all()
+    assert torch.equal(p0, p1)
+    scale = h0.flatten(1).abs().amax(1).clamp_min(1e-20)[:, None, None]
+    err = ((h1 - h0).abs() / scale).max().item()
+    print(f"psf tc vs ffma B={B}: HR max err / sample max {err:.2e}, rel-L2 {rel_l2(h1, h0):.2e}, LRd rel-L2 {rel_l2(l1, l0):.2e}")
+    assert err < 1e-5, err
+    assert rel_l2(h1, h0) < 3e-6 and rel_l2(l1, l0) < 1e-5
