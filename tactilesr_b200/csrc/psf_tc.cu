@@ -11,12 +11,13 @@
 // in TMEM (the dropped lo*lo term is 2^-22 relative).  Measured against the fp64 reference run: ~1e-6 rel-L2.
 //
 // Per sample (one CTA, 256 threads; two CTAs per SM overlap each other's phases):
-//   A  tables e(t), Ex_i(t);  depth max (contact threshold);  E -> smem (K-major SWIZZLE_128B, hi and lo tiles);
-//      depth^T -> smem (same layout; 4-byte transposing loads, 16-byte swizzled stores) + contact-mask bytes
+//   A  depth plane -> registers (its only global read: 32 contiguous bytes per thread and item); tables e(t), Ex_i(t);
+//      depth max (contact threshold);  E -> smem (K-major SWIZZLE_128B, hi and lo tiles);  depth -> smem as it lies in
+//      HBM (row = k: the MN-major B operand, hi and lo tiles) + contact-mask bytes
 //   B  GEMM1  T = E * D      (M=128, N=112, K=7x16; 21 MMAs)      -> TMEM columns [0,112)
+//      (the psf output, a pure function of alpha / beta, is written to HBM while GEMM1 runs)
 //   X  T: TMEM -> registers -> hi/lo fp16 -> smem, over the dead depth tiles (all 8 warps: 4 lane quarters x 2 halves)
 //   C  GEMM2  HR = T * E     (E symmetric: the same E tiles are the B operand)   -> TMEM columns [128,240)
-//      (the psf output, a pure function of alpha / beta, is written to HBM while GEMM2 runs)
 //   E  epilogue: second-max fill (tPSFNet.py:95-97), HR store, LRd = 1e-4 (Ex HR Ex^T - m sum HR) / (1 - m)
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -29,19 +30,22 @@ constexpr float CP2 = 100.0f / 4802.0f;
 constexpr float CM2 = 100.0f / 15138.0f;
 
 constexpr uint32_t ROWS = 104;                 // allocated rows of a tile (13 groups of 8); MMAs over-read up to row 127
-constexpr uint32_t ATOM = ROWS * 128u;         // one 64-wide K atom: rows x 128 B, SWIZZLE_128B
-constexpr uint32_t TILE = 2u * ATOM;           // K = 112 = 64 + 48
-constexpr uint32_t OFF_E_HI = 0, OFF_E_LO = TILE, OFF_X_HI = 2 * TILE, OFF_X_LO = 3 * TILE;
-constexpr uint32_t OFF_TAB = 4 * TILE;                       // float e(t), t = 0..99  (+ pad)
-constexpr uint32_t OFF_TAB2 = OFF_TAB + 128 * 4;             // uint32 (hi | lo << 16) of 2^14 e(|j - 99|), j = 0..198 (+ pad)
-constexpr uint32_t OFF_EX = OFF_TAB2 + 208 * 4;              // float Ex_i(t), 4 x 100
-constexpr uint32_t OFF_MASK = OFF_EX + 400 * 4;              // contact bytes [13][112]: bit j of [cg][n] <-> depth[8 cg + j][n]
-constexpr uint32_t OFF_RED = OFF_MASK + 13 * 112;            // float scratch [8][20]
+constexpr uint32_t ATOM = ROWS * 128u;         // one 64-wide atom: rows x 128 B, SWIZZLE_128B
+constexpr uint32_t TILE = 2u * ATOM;           // 112 = 64 + 48 elements along the atom direction
+// X tiles first: GEMM1 reads K rows 96..111 of the (MN-major) depth tiles, i.e. 1 KB past a tile's 104 rows -- for X_lo
+// that lands in E_hi (always finite; it meets the zero K-padding of E).  Over-reads of M / N rows >= 104 only produce
+// accumulator rows / columns that are never used.
+constexpr uint32_t OFF_X_HI = 0, OFF_X_LO = TILE, OFF_E_HI = 2 * TILE, OFF_E_LO = 3 * TILE;
+constexpr uint32_t OFF_TAB = 4 * TILE;                       // float e(t), t = 0..99 (+ pad)
+constexpr uint32_t TAB2_LEN = 208;                           // per shifted copy
+constexpr uint32_t OFF_TAB2 = OFF_TAB + 128 * 4;             // 4 shifted copies of uint32 (hi | lo << 16) of 16 e(|j - 99|) [banded]
+constexpr uint32_t OFF_EX = OFF_TAB2 + 4 * TAB2_LEN * 4;     // float4 (Ex_0..Ex_3)(t), t = 0..99
+constexpr uint32_t OFF_MASK = OFF_EX + 100 * 16;             // contact bytes [104][16]: bit j of [k][cg] <-> depth[k][8 cg + j]
+constexpr uint32_t OFF_RED = OFF_MASK + 104 * 16;            // float scratch [8][20]
 constexpr uint32_t OFF_BAR = (OFF_RED + 8 * 20 * 4 + 15u) & ~15u;   // 2 mbarriers + tmem slot
 constexpr uint32_t SMEM_USED = OFF_BAR + 32;
-// the last A tile (X_lo) is over-read by (128 - 104) rows = 3 KB: the tables behind it cover that
 static_assert(SMEM_USED - 4 * TILE >= 3072, "the tables must cover the over-read of the last tile");
-constexpr size_t SMEM_BYTES = 1024 + ((SMEM_USED + 15) & ~15u);
+constexpr size_t SMEM_BYTES = (SMEM_USED + 15) & ~15u;
 static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -53,19 +57,19 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       : "memory");
 }
 
-// byte offset of the 16-byte chunk holding k = 8 cg .. 8 cg + 7 of row r in a K-major SWIZZLE_128B tile
+// byte offset of the 16-byte chunk cg (elements 8 cg .. 8 cg + 7 along the contiguous direction) of row r of a tile
 __device__ __forceinline__ uint32_t chunk_off(int r, int cg) {
   return (uint32_t)(cg >> 3) * ATOM + (uint32_t)r * 128u + (uint32_t)(((cg & 7) ^ (r & 7)) << 4);
 }
 
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-}
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
-// x (already scaled) -> fp16 hi, fp16 lo with hi + lo = x to ~22 bits
-__device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
-  hi = __float2half_rn(x);
-  lo = __float2half_rn(x - __half2float(hi));
+// (x0, x1) -> packed fp16 hi pair and lo pair with hi + lo = x to ~22 bits
+__device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 f = __half22float2(h);
+  hi = h2_bits(h);
+  lo = h2_bits(__floats2half2_rn(x0 - f.x, x1 - f.y));
 }
 
 __device__ __forceinline__ float block_max256(float v, float* red) {
@@ -79,7 +83,9 @@ __device__ __forceinline__ float block_max256(float v, float* red) {
   return t;
 }
 
-// one GEMM: D[128 x 112] (TMEM) = sum of three hi/lo products of K-major tiles A (rows = M) and B (rows = N)
+// D[128 x 112] (TMEM) = A_hi B_hi + A_lo B_hi + A_hi B_lo.  A: K-major tile.  B: K-major tile (b_mn = 0) or MN-major
+// tile (b_mn = 1: rows = K, the two 64-wide N atoms are ATOM bytes apart).
+template <int B_MN>
 __device__ __forceinline__ void issue_gemm3(uint32_t tmem_d, uint32_t a_hi_addr, uint32_t a_lo_addr, uint32_t b_hi_addr,
                                             uint32_t b_lo_addr, uint32_t idesc) {
   const uint32_t hi_word = desc_hi(1024u);
@@ -90,31 +96,41 @@ __device__ __forceinline__ void issue_gemm3(uint32_t tmem_d, uint32_t a_hi_addr,
     const uint32_t b0 = pass == 2 ? b_lo_addr : b_hi_addr;
 #pragma unroll
     for (int ks = 0; ks < 7; ++ks) {
-      const uint32_t off = (uint32_t)(ks >> 2) * ATOM + (uint32_t)(ks & 3) * 32u;
-      umma_f16(tmem_d, desc_join(desc_lo(a0 + off, 16u), hi_word), desc_join(desc_lo(b0 + off, 16u), hi_word), idesc, acc);
+      const uint32_t koff = (uint32_t)(ks >> 2) * ATOM + (uint32_t)(ks & 3) * 32u;     // 16 elements along K, K-major
+      const uint64_t ad = desc_join(desc_lo(a0 + koff, 16u), hi_word);
+      const uint64_t bd = B_MN ? desc_join(desc_lo(b0 + (uint32_t)ks * 2048u, ATOM), hi_word)   // 16 K rows further
+                               : desc_join(desc_lo(b0 + koff, 16u), hi_word);
+      umma_f16(tmem_d, ad, bd, idesc, acc);
       acc = 1u;
     }
   }
 }
 
+constexpr int ITEMS = 13 * N;                  // (row, 8-element chunk) work items of a 100 x 100 plane
+constexpr int IPT = (ITEMS + NT - 1) / NT;     // 6 (the last round only for 20 threads)
+
 __global__ void __launch_bounds__(NT, 2)
 psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth, float* __restrict__ HR,
                   float* __restrict__ LRd, float* __restrict__ psf, int B) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const uint32_t base = smem_u32(sm);
   float* tab = reinterpret_cast<float*>(sm + OFF_TAB);
   uint32_t* tab2 = reinterpret_cast<uint32_t*>(sm + OFF_TAB2);
-  float* ex = reinterpret_cast<float*>(sm + OFF_EX);
+  float4* ex4 = reinterpret_cast<float4*>(sm + OFF_EX);
   uint8_t* maskb = sm + OFF_MASK;
   float* red = reinterpret_cast<float*>(sm + OFF_RED);
   const uint32_t bar1 = base + OFF_BAR, bar2 = bar1 + 8u, tmem_slot = bar1 + 16u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + 16);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((base & 1023u) != 0u) {                  // SWIZZLE_128B atoms are addressed by absolute shared-memory address bits
+    if (tid == 0) printf("tactilesr_b200 psf_tc: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
 
-  // one-time: zero all four tiles (K padding columns, rows 100..103), barriers, TMEM
+  // one-time: zero all four tiles (padding chunks, rows 100..103) and the mask table, barriers, TMEM
   for (uint32_t i = tid; i < 4 * TILE / 16; i += NT) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (uint32_t i = tid; i < 104 * 16 / 4; i += NT) reinterpret_cast<uint32_t*>(maskb)[i] = 0u;
   if (tid == 0) {
     mbar_init(bar1, 1);
     mbar_init(bar2, 1);
@@ -128,9 +144,10 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t idesc = make_idesc(128, 112, 0, 0, 0, 0);    // fp16 x fp16 -> fp32, both K-major
+  const uint32_t idesc1 = make_idesc(128, 112, 0, 1, 0, 0);   // fp16 x fp16 -> fp32; A K-major, B MN-major
+  const uint32_t idesc2 = make_idesc(128, 112, 0, 0, 0, 0);   // both K-major
 
-  // epilogue geometry: TMEM lane quarter q = warp % 4, row m = 32 q + lane; column half h = warp / 4 (56 columns each)
+  // epilogue geometry: TMEM lane quarter q = warp % 4, row m = 32 q + lane; column half = warp / 4 (56 columns each)
   const int q = warp & 3, half = warp >> 2;
   const int m = q * 32 + lane;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -141,7 +158,28 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     const float alpha = ab[b * 3 + 0], beta = ab[b * 3 + 1], gamma = ab[b * 3 + 2];
     const float* dsrc = depth + (size_t)b * N * N;
 
-    // ---- phase A1: tables, depth max / abs-max ----
+    // ---- phase A1: this thread's depth chunks -> registers (the only global read of the plane); tables; depth max ----
+    float dreg[IPT][8];
+    float lmax = -INFINITY, lamax = 0.f;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const int item = tid + i * NT;
+      const int k = item / 13, cg = item - k * 13;      // row k, columns 8 cg .. 8 cg + 7: consecutive lanes are contiguous
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+      if (item < ITEMS) {
+        const float4* src = reinterpret_cast<const float4*>(dsrc + k * N + cg * 8);
+        a = src[0];
+        lmax = fmaxf(fmaxf(lmax, fmaxf(a.x, a.y)), fmaxf(a.z, a.w));
+        if (cg < 12) {                                   // chunk 12 holds columns 96..99 only
+          c = src[1];
+          lmax = fmaxf(fmaxf(lmax, fmaxf(c.x, c.y)), fmaxf(c.z, c.w));
+        }
+      }
+      dreg[i][0] = a.x; dreg[i][1] = a.y; dreg[i][2] = a.z; dreg[i][3] = a.w;
+      dreg[i][4] = c.x; dreg[i][5] = c.y; dreg[i][6] = c.z; dreg[i][7] = c.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) lamax = fmaxf(lamax, fabsf(dreg[i][j]));
+    }
     {
       const float inv_b2 = 1.0f / (beta * beta);
       if (tid < N) tab[tid] = expf(-(CP2 * (float)(tid * tid)) * inv_b2);
@@ -149,66 +187,58 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       for (int i = tid; i < 4 * N; i += NT) {
         const int k = i / N, t = i - k * N;
         const float d = (float)(t - 12 - 25 * k);
-        ex[i] = expf(-(CM2 * d * d) * inv_g);
+        reinterpret_cast<float*>(ex4)[t * 4 + k] = expf(-(CM2 * d * d) * inv_g);
       }
     }
-    float lmax = -INFINITY, lamax = 0.f;
-    for (int i = tid; i < N * N / 4; i += NT) {
-      const float4 v = reinterpret_cast<const float4*>(dsrc)[i];
-      lmax = fmaxf(fmaxf(lmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-      lamax = fmaxf(fmaxf(lamax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
-    }
-    const float dmax = block_max256(lmax, red);        // (syncs: tables visible)
+    const float dmax = block_max256(lmax, red);        // (syncs: tab visible)
     const float amax = block_max256(lamax, red);
     const float thr = dmax - 1e-3f;
     int dexp = 0;
     if (amax > 0.f) (void)frexpf(amax, &dexp);         // amax = f * 2^dexp, f in [0.5, 1)
-    const float sD = ldexpf(1.0f, 14 - dexp);          // |depth| * sD < 2^14
-    // packed (hi, lo) of 2^14 e(|j - 99|)
-    if (tid < 199) {
-      const int t = tid < 99 ? 99 - tid : tid - 99;
-      __half h, l;
-      split_h(t <= 49 ? tab[t] * 16384.0f : 0.f, h, l);      // the PSF has 99 taps: E is banded, |k - m| <= 49
-      tab2[tid] = pack_h2(h, l);
+    const float sD = ldexpf(1.0f, 4 - dexp);           // |depth| sD < 16
+    // 4 shifted copies of the packed (hi, lo) table of 16 e(|j - 99|), so that any 8 consecutive entries are two
+    // aligned 16-byte loads.  The PSF has 99 taps: E is banded, entries with |k - m| > 49 are 0.
+    for (int i = tid; i < 4 * (int)TAB2_LEN; i += NT) {
+      const int s = i / (int)TAB2_LEN, qn = i - s * (int)TAB2_LEN;
+      const int j = qn + s;
+      const int t = j < 99 ? 99 - j : j - 99;
+      uint32_t hi, lo;
+      split_h2(t <= 49 ? tab[t] * 16.0f : 0.f, 0.f, hi, lo);
+      tab2[i] = (hi & 0xFFFFu) | (lo << 16);
     }
     __syncthreads();
 
-    // ---- phase A2: E tiles, transposed depth tiles + contact bytes ----
-    for (int item = tid; item < 13 * N; item += NT) {
-      const int cg = item / N, r = item - cg * N;      // row r (= m of E, = n of depth^T), k = 8 cg .. 8 cg + 7
-      const int k0 = cg * 8;
-      const int kv = cg == 12 ? 4 : 8;                 // valid k (k < 100)
-      // E[r][k] = e(|k - r|)
-      uint32_t eh[4], el[4];
+    // ---- phase A2: E tiles (K-major), depth tiles (MN-major: row = k, as in HBM) + contact bytes ----
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t p0 = (2 * j < kv) ? tab2[k0 + 2 * j - r + 99] : 0u;
-        const uint32_t p1 = (2 * j + 1 < kv) ? tab2[k0 + 2 * j + 1 - r + 99] : 0u;
-        eh[j] = (p0 & 0xFFFFu) | (p1 << 16);
-        el[j] = (p0 >> 16) | (p1 & 0xFFFF0000u);
+    for (int i = 0; i < IPT; ++i) {
+      const int item = tid + i * NT;
+      if (item < ITEMS) {
+        const int r = item / 13, cg = item - r * 13;
+        const uint32_t off = chunk_off(r, cg);
+        {   // E[r][8 cg + j] = e(|8 cg + j - r|): entries start .. start + 7 of the table
+          const int start = 8 * cg - r + 99;
+          const int s = start & 3;
+          const uint4* tp = reinterpret_cast<const uint4*>(tab2 + s * (int)TAB2_LEN + (start - s));
+          const uint4 p0 = tp[0];
+          uint4 p1 = tp[1];
+          if (cg == 12) p1 = make_uint4(0u, 0u, 0u, 0u);       // k = 100..103: K padding
+          const uint4 eh = make_uint4(__byte_perm(p0.x, p0.y, 0x5410), __byte_perm(p0.z, p0.w, 0x5410),
+                                      __byte_perm(p1.x, p1.y, 0x5410), __byte_perm(p1.z, p1.w, 0x5410));
+          const uint4 el = make_uint4(__byte_perm(p0.x, p0.y, 0x7632), __byte_perm(p0.z, p0.w, 0x7632),
+                                      __byte_perm(p1.x, p1.y, 0x7632), __byte_perm(p1.z, p1.w, 0x7632));
+          *reinterpret_cast<uint4*>(sm + OFF_E_HI + off) = eh;
+          *reinterpret_cast<uint4*>(sm + OFF_E_LO + off) = el;
+        }
+        uint32_t dh[4], dl[4], bits = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_h2(dreg[i][2 * j] * sD, dreg[i][2 * j + 1] * sD, dh[j], dl[j]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (dreg[i][j] > thr && (cg < 12 || j < 4)) bits |= 1u << j;
+        *reinterpret_cast<uint4*>(sm + OFF_X_HI + off) = make_uint4(dh[0], dh[1], dh[2], dh[3]);
+        *reinterpret_cast<uint4*>(sm + OFF_X_LO + off) = make_uint4(dl[0], dl[1], dl[2], dl[3]);
+        maskb[r * 16 + cg] = (uint8_t)bits;
       }
-      const uint32_t off = chunk_off(r, cg);
-      *reinterpret_cast<uint4*>(sm + OFF_E_HI + off) = make_uint4(eh[0], eh[1], eh[2], eh[3]);
-      *reinterpret_cast<uint4*>(sm + OFF_E_LO + off) = make_uint4(el[0], el[1], el[2], el[3]);
-      // depth^T[n = r][k]: lanes are consecutive n => every k is one coalesced 4-byte load per warp
-      float dv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dv[j] = j < kv ? dsrc[(k0 + j) * N + r] : 0.f;
-      uint32_t dh[4], dl[4], bits = 0u;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __half h0, l0, h1, l1;
-        split_h(dv[2 * j] * sD, h0, l0);
-        split_h(dv[2 * j + 1] * sD, h1, l1);
-        dh[j] = pack_h2(h0, h1);
-        dl[j] = pack_h2(l0, l1);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < kv && dv[j] > thr) bits |= 1u << j;
-      *reinterpret_cast<uint4*>(sm + OFF_X_HI + off) = make_uint4(dh[0], dh[1], dh[2], dh[3]);
-      *reinterpret_cast<uint4*>(sm + OFF_X_LO + off) = make_uint4(dl[0], dl[1], dl[2], dl[3]);
-      maskb[cg * 112 + r] = (uint8_t)bits;
     }
     fence_proxy_async();
     tc_fence_before();
@@ -218,39 +248,51 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_gemm3(tmem_base, base + OFF_E_HI, base + OFF_E_LO, base + OFF_X_HI, base + OFF_X_LO, idesc);
+        issue_gemm3<1>(tmem_base, base + OFF_E_HI, base + OFF_E_LO, base + OFF_X_HI, base + OFF_X_LO, idesc1);
         umma_commit(bar1);
       }
       __syncwarp();
     }
+    // psf = alpha e(u) e(v)  (tPSFNet.py:83), written while GEMM1 runs: warp w owns rows u = w, w + 8, ...
+    if (psf) {
+      float* pdst = psf + (size_t)b * 99 * 99;
+      float ev[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int v = lane + 32 * c;
+        ev[c] = v < 99 ? tab[v < 49 ? 49 - v : v - 49] : 0.f;
+      }
+      for (int u = warp; u < 99; u += NT / 32) {
+        const float eu = tab[u < 49 ? 49 - u : u - 49];
+        float* row = pdst + u * 99;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (lane + 32 * c < 99) row[lane + 32 * c] = alpha * (eu * ev[c]);
+      }
+    }
     mbar_wait(bar1, ph);
     tc_fence_after();
 
-    // ---- phase X: T -> hi/lo fp16 -> smem (over the depth tiles, which GEMM1 has finished reading) ----
-    // accumulator = 2^14 sD T;  written as 2^(8 - dexp) T  (|T| <= 100 |depth|max  =>  < 2^15)
-    {
-      const float sx = 1.0f / 1048576.0f;              // 2^-20 = 2^(8 - dexp) / (2^14 sD)
+    // ---- phase X: T -> hi/lo fp16 -> smem (K-major, over the depth tiles, which GEMM1 has finished reading) ----
+    // accumulator = 16 sD T = 2^(8 - dexp) T,  |T| <= 99 |depth|max  =>  < 2^15: no rescaling needed
 #pragma unroll 1
-      for (int g = 0; g < 7; ++g) {
-        const int cg = half * 7 + g;
-        uint32_t v[8];
-        tmem_ld8(tmem_base + lane_addr + (uint32_t)(cg * 8), v);
-        tmem_ld_wait();
-        if (m < (int)ROWS) {
-          uint32_t th[4], tl[4];
+    for (int g = 0; g < 7; ++g) {
+      const int cg = half * 7 + g;
+      uint32_t v[8];
+      tmem_ld8(tmem_base + lane_addr + (uint32_t)(cg * 8), v);
+      tmem_ld_wait();
+      if (m < (int)ROWS) {
+        uint32_t th[4], tl[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const bool ok0 = cg * 8 + 2 * j < N, ok1 = cg * 8 + 2 * j + 1 < N;     // columns >= 100 are padding: force 0
-            __half h0, l0, h1, l1;
-            split_h(ok0 ? __uint_as_float(v[2 * j]) * sx : 0.f, h0, l0);
-            split_h(ok1 ? __uint_as_float(v[2 * j + 1]) * sx : 0.f, h1, l1);
-            th[j] = pack_h2(h0, h1);
-            tl[j] = pack_h2(l0, l1);
-          }
-          const uint32_t off = chunk_off(m, cg);
-          *reinterpret_cast<uint4*>(sm + OFF_X_HI + off) = make_uint4(th[0], th[1], th[2], th[3]);
-          *reinterpret_cast<uint4*>(sm + OFF_X_LO + off) = make_uint4(tl[0], tl[1], tl[2], tl[3]);
+        for (int j = 0; j < 4; ++j) {
+          // columns >= 100 are padding (depth-tile garbage): force 0
+          const float x0 = cg * 8 + 2 * j < N ? __uint_as_float(v[2 * j]) : 0.f;
+          const float x1 = cg * 8 + 2 * j + 1 < N ? __uint_as_float(v[2 * j + 1]) : 0.f;
+          split_h2(x0, x1, th[j], tl[j]);
         }
+        const uint32_t off = chunk_off(m, cg);
+        *reinterpret_cast<uint4*>(sm + OFF_X_HI + off) = make_uint4(th[0], th[1], th[2], th[3]);
+        *reinterpret_cast<uint4*>(sm + OFF_X_LO + off) = make_uint4(tl[0], tl[1], tl[2], tl[3]);
       }
     }
     fence_proxy_async();
@@ -261,25 +303,18 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_gemm3(tmem_base + 128u, base + OFF_X_HI, base + OFF_X_LO, base + OFF_E_HI, base + OFF_E_LO, idesc);
+        issue_gemm3<0>(tmem_base + 128u, base + OFF_X_HI, base + OFF_X_LO, base + OFF_E_HI, base + OFF_E_LO, idesc2);
         umma_commit(bar2);
       }
       __syncwarp();
     }
-    // psf = alpha e(u) e(v)  (tPSFNet.py:83), written while GEMM2 runs
-    if (psf) {
-      float* pdst = psf + (size_t)b * 99 * 99;
-      for (int i = tid; i < 99 * 99; i += NT) {
-        const int u = i / 99, v = i - u * 99;
-        pdst[i] = alpha * (tab[u < 49 ? 49 - u : u - 49] * tab[v < 49 ? 49 - v : v - 49]);
-      }
-    }
     mbar_wait(bar2, ph);
     tc_fence_after();
 
-    // ---- phase E: epilogue.  accumulator = 2^(8 - dexp) 2^14 (E D E) ----
-    const float cs = alpha * ldexpf(1.0f, dexp - 22);
+    // ---- phase E: epilogue.  accumulator = 2^(8 - dexp) 16 (E D E) ----
+    const float cs = alpha * ldexpf(1.0f, dexp - 12);
     const uint32_t acc2 = tmem_base + 128u + lane_addr;
+    const uint8_t* mrow = maskb + (m < (int)ROWS ? m : 0) * 16;
     // pass 1: second max = max over the conv result with the contact pixels zeroed (tPSFNet.py:95-97)
     float m2 = 0.f;
 #pragma unroll 1
@@ -288,12 +323,11 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       uint32_t v[8];
       tmem_ld8(acc2 + (uint32_t)(cg * 8), v);
       tmem_ld_wait();
-      if (m < N) {
+      if (m < N && cg < 13) {
+        const uint32_t bits = mrow[cg] | (cg == 12 ? 0xF0u : 0u);       // columns >= 100: treated like contact (skipped)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int n = cg * 8 + j;
-          if (n < N && !((maskb[(m >> 3) * 112 + n] >> (m & 7)) & 1)) m2 = fmaxf(m2, __uint_as_float(v[j]) * cs);
-        }
+        for (int j = 0; j < 8; ++j)
+          if (!((bits >> j) & 1u)) m2 = fmaxf(m2, __uint_as_float(v[j]) * cs);
       }
     }
     m2 = block_max256(m2, red);
@@ -306,35 +340,33 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       uint32_t v[8];
       tmem_ld8(acc2 + (uint32_t)(cg * 8), v);
       tmem_ld_wait();
-      if (m < N && cg * 8 < N) {
+      if (m < N && cg < 13) {
+        const uint32_t bits = mrow[cg];
+        const int nv = cg == 12 ? 4 : 8;
         float h[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int n = cg * 8 + j;
-          const bool contact = n < N && ((maskb[(m >> 3) * 112 + n] >> (m & 7)) & 1);
-          h[j] = n < N ? (contact ? m2 : __uint_as_float(v[j]) * cs) : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int n = cg * 8 + j;
-          if (n < N) {
+          h[j] = ((bits >> j) & 1u) ? m2 : __uint_as_float(v[j]) * cs;
+          if (j < nv) {
+            const float4 e4 = ex4[cg * 8 + j];
             rs += h[j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rj[i] = fmaf(h[j], ex[i * N + n], rj[i]);
+            rj[0] = fmaf(h[j], e4.x, rj[0]); rj[1] = fmaf(h[j], e4.y, rj[1]);
+            rj[2] = fmaf(h[j], e4.z, rj[2]); rj[3] = fmaf(h[j], e4.w, rj[3]);
           }
         }
         *reinterpret_cast<float4*>(hdst + cg * 8) = make_float4(h[0], h[1], h[2], h[3]);
-        if (cg * 8 + 4 < N) *reinterpret_cast<float4*>(hdst + cg * 8 + 4) = make_float4(h[4], h[5], h[6], h[7]);
+        if (cg < 12) *reinterpret_cast<float4*>(hdst + cg * 8 + 4) = make_float4(h[4], h[5], h[6], h[7]);
       }
     }
     // LRd[i][j] = 1e-4 (sum_m Ex_i(m) R_j(m) - mm sum HR) / (1 - mm),  R_j(m) = sum_n HR[m][n] Ex_j(n)
     {
       float p[17];
+      const float4 em = m < N ? ex4[m] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float ei[4] = {em.x, em.y, em.z, em.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float e = m < N ? ex[i * N + m] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) p[i * 4 + j] = e * rj[j];
+        for (int j = 0; j < 4; ++j) p[i * 4 + j] = ei[i] * rj[j];
       }
       p[16] = m < N ? rs : 0.f;
 #pragma unroll
