@@ -109,6 +109,24 @@ __device__ __forceinline__ void issue_gemm3(uint32_t tmem_d, uint32_t a_hi_addr,
 constexpr int ITEMS = 13 * N;                  // (row, 8-element chunk) work items of a 100 x 100 plane
 constexpr int IPT = (ITEMS + NT - 1) / NT;     // 6 (the last round only for 20 threads)
 
+// this thread's chunks of one depth plane -> registers: item = (row k, columns 8 cg .. 8 cg + 7), consecutive lanes read
+// consecutive 32-byte pieces; chunk 12 of a row holds columns 96..99 only (the rest reads as 0)
+__device__ __forceinline__ void load_plane(const float* __restrict__ dsrc, int tid, float (&dreg)[IPT][8]) {
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const int item = tid + i * NT;
+    const int k = item / 13, cg = item - k * 13;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+    if (item < ITEMS) {
+      const float4* src = reinterpret_cast<const float4*>(dsrc + k * N + cg * 8);
+      a = __ldg(src);
+      if (cg < 12) c = __ldg(src + 1);
+    }
+    dreg[i][0] = a.x; dreg[i][1] = a.y; dreg[i][2] = a.z; dreg[i][3] = a.w;
+    dreg[i][4] = c.x; dreg[i][5] = c.y; dreg[i][6] = c.z; dreg[i][7] = c.w;
+  }
+}
+
 __global__ void __launch_bounds__(NT, 2)
 psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth, float* __restrict__ HR,
                   float* __restrict__ LRd, float* __restrict__ psf, int B) {
@@ -152,31 +170,24 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
   const int m = q * 32 + lane;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
 
+  float dreg[IPT][8];
+  if ((int)blockIdx.x < B) load_plane(depth + (size_t)blockIdx.x * N * N, tid, dreg);
   int it = 0;
   for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
     const uint32_t ph = (uint32_t)(it & 1);
     const float alpha = ab[b * 3 + 0], beta = ab[b * 3 + 1], gamma = ab[b * 3 + 2];
-    const float* dsrc = depth + (size_t)b * N * N;
 
-    // ---- phase A1: this thread's depth chunks -> registers (the only global read of the plane); tables; depth max ----
-    float dreg[IPT][8];
+    // ---- phase A1: depth max over this thread's chunks (loaded into registers one sample ahead); tables ----
     float lmax = -INFINITY, lamax = 0.f;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
       const int item = tid + i * NT;
-      const int k = item / 13, cg = item - k * 13;      // row k, columns 8 cg .. 8 cg + 7: consecutive lanes are contiguous
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+      const int cg = item % 13;
       if (item < ITEMS) {
-        const float4* src = reinterpret_cast<const float4*>(dsrc + k * N + cg * 8);
-        a = src[0];
-        lmax = fmaxf(fmaxf(lmax, fmaxf(a.x, a.y)), fmaxf(a.z, a.w));
-        if (cg < 12) {                                   // chunk 12 holds columns 96..99 only
-          c = src[1];
-          lmax = fmaxf(fmaxf(lmax, fmaxf(c.x, c.y)), fmaxf(c.z, c.w));
-        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < 4 || cg < 12) lmax = fmaxf(lmax, dreg[i][j]);      // chunk 12 holds columns 96..99 only
       }
-      dreg[i][0] = a.x; dreg[i][1] = a.y; dreg[i][2] = a.z; dreg[i][3] = a.w;
-      dreg[i][4] = c.x; dreg[i][5] = c.y; dreg[i][6] = c.z; dreg[i][7] = c.w;
 #pragma unroll
       for (int j = 0; j < 8; ++j) lamax = fmaxf(lamax, fabsf(dreg[i][j]));
     }
@@ -253,6 +264,8 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       }
       __syncwarp();
     }
+    // the next sample's plane: its loads stay in flight until the top of the next iteration
+    if (b + (int)gridDim.x < B) load_plane(depth + (size_t)(b + gridDim.x) * N * N, tid, dreg);
     // psf = alpha e(u) e(v)  (tPSFNet.py:83), written while GEMM1 runs: warp w owns rows u = w, w + 8, ...
     if (psf) {
       float* pdst = psf + (size_t)b * 99 * 99;
@@ -360,7 +373,7 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     }
     // LRd[i][j] = 1e-4 (sum_m Ex_i(m) R_j(m) - mm sum HR) / (1 - mm),  R_j(m) = sum_n HR[m][n] Ex_j(n)
     {
-      float p[17];
+      float p[16];
       const float4 em = m < N ? ex4[m] : make_float4(0.f, 0.f, 0.f, 0.f);
       const float ei[4] = {em.x, em.y, em.z, em.w};
 #pragma unroll
@@ -368,14 +381,22 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
 #pragma unroll
         for (int j = 0; j < 4; ++j) p[i * 4 + j] = ei[i] * rj[j];
       }
-      p[16] = m < N ? rs : 0.f;
+      // transposing warp reduction: every exchange halves the values a lane carries (16 shuffles instead of 80);
+      // lane l ends with the warp sum of value (l >> 1)
 #pragma unroll
-      for (int k = 0; k < 17; ++k) p[k] = warp_sum(p[k]);
-      __syncthreads();                                  // (red was last read by block_max256)
-      if (lane == 0) {
+      for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
 #pragma unroll
-        for (int k = 0; k < 17; ++k) red[warp * 20 + k] = p[k];
+        for (int k = 0; k < w; ++k) {
+          const float keep = up ? p[k + w] : p[k], send = up ? p[k] : p[k + w];
+          p[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
       }
+      p[0] += __shfl_xor_sync(0xffffffffu, p[0], 1);
+      const float tot_w = warp_sum(m < N ? rs : 0.f);
+      __syncthreads();                                  // (red was last read by block_max256)
+      if ((lane & 1) == 0) red[warp * 20 + (lane >> 1)] = p[0];
+      if (lane == 0) red[warp * 20 + 16] = tot_w;
       __syncthreads();
       if (tid < 16) {
         float s = 0.f, tot = 0.f;
