@@ -56,7 +56,9 @@ SIGNATURES = {
     "tsr_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "tsr_linear_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "tsr_psf_forward": (_I, [_P, _P, _P, _P, _P, _I, _P]),
-    "tsr_psf_forward_tc": (_I, [_P, _P, _P, _P, _P, _I, _P]),
+    "tsr_psf_forward_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
+    "tsr_psf_backward_tc": (_I, [_P, _P, _P, _P, _P, _I, _P]),
+    "tsr_psf_aux_floats": (_Z, []),
     "tsr_psf_forward_ffma": (_I, [_P, _P, _P, _P, _P, _I, _P]),
     "tsr_set_psf_mode": (None, [_I]),
     "tsr_get_psf_mode": (_I, []),

@@ -85,11 +85,11 @@ __device__ __forceinline__ float block_max256(float v, float* red) {
 
 // D[128 x 112] (TMEM) = A_hi B_hi + A_lo B_hi + A_hi B_lo.  A: K-major tile.  B: K-major tile (b_mn = 0) or MN-major
 // tile (b_mn = 1: rows = K, the two 64-wide N atoms are ATOM bytes apart).
-template <int B_MN>
+template <int B_MN, int ACCUMULATE = 0>
 __device__ __forceinline__ void issue_gemm3(uint32_t tmem_d, uint32_t a_hi_addr, uint32_t a_lo_addr, uint32_t b_hi_addr,
                                             uint32_t b_lo_addr, uint32_t idesc) {
   const uint32_t hi_word = desc_hi(1024u);
-  uint32_t acc = 0u;
+  uint32_t acc = ACCUMULATE;
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
     const uint32_t a0 = pass == 1 ? a_lo_addr : a_hi_addr;
@@ -127,9 +127,129 @@ __device__ __forceinline__ void load_plane(const float* __restrict__ dsrc, int t
   }
 }
 
+
+// 4 shifted copies of the packed (hi | lo << 16) fp16 table of the banded Toeplitz generator, so that any 8 consecutive
+// entries are two aligned 16-byte loads.  kind 0: 16 e(t);  1: 16 e(t) t^2;  2: 32768 e(t)   (t = |j - 99| <= 49, else 0:
+// the PSF has 99 taps)
+template <int KIND>
+__device__ __forceinline__ void build_tab2(const float* tab, uint32_t* tab2, int tid) {
+  for (int i = tid; i < 4 * (int)TAB2_LEN; i += NT) {
+    const int s = i / (int)TAB2_LEN, qn = i - s * (int)TAB2_LEN;
+    const int j = qn + s;
+    const int t = j < 99 ? 99 - j : j - 99;
+    float x = 0.f;
+    if (t <= 49) x = KIND == 0 ? tab[t] * 16.0f : (KIND == 1 ? tab[t] * (float)(16 * t * t) : tab[t] * 32768.0f);
+    uint32_t hi, lo;
+    split_h2(x, 0.f, hi, lo);
+    tab2[i] = (hi & 0xFFFFu) | (lo << 16);
+  }
+}
+
+// K-major hi / lo tiles of the Toeplitz matrix from the table: M[r][8 cg + j] = gen(|8 cg + j - r|)
+__device__ __forceinline__ void build_toeplitz_tiles(const uint32_t* tab2, uint8_t* t_hi, uint8_t* t_lo, int tid) {
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const int item = tid + i * NT;
+    if (item < ITEMS) {
+      const int r = item / 13, cg = item - r * 13;
+      const int start = 8 * cg - r + 99;
+      const int s = start & 3;
+      const uint4* tp = reinterpret_cast<const uint4*>(tab2 + s * (int)TAB2_LEN + (start - s));
+      const uint4 p0 = tp[0];
+      uint4 p1 = tp[1];
+      if (cg == 12) p1 = make_uint4(0u, 0u, 0u, 0u);       // k = 100..103: K padding
+      const uint32_t off = chunk_off(r, cg);
+      *reinterpret_cast<uint4*>(t_hi + off) = make_uint4(__byte_perm(p0.x, p0.y, 0x5410), __byte_perm(p0.z, p0.w, 0x5410),
+                                                         __byte_perm(p1.x, p1.y, 0x5410), __byte_perm(p1.z, p1.w, 0x5410));
+      *reinterpret_cast<uint4*>(t_lo + off) = make_uint4(__byte_perm(p0.x, p0.y, 0x7632), __byte_perm(p0.z, p0.w, 0x7632),
+                                                         __byte_perm(p1.x, p1.y, 0x7632), __byte_perm(p1.z, p1.w, 0x7632));
+    }
+  }
+}
+
+// the register-held depth plane -> hi / lo tiles as it lies in HBM (row = k: the MN-major B operand) + contact bytes
+__device__ __forceinline__ void store_plane_tiles(const float (&dreg)[IPT][8], float sD, float thr, uint8_t* x_hi,
+                                                  uint8_t* x_lo, uint8_t* maskb, int tid) {
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const int item = tid + i * NT;
+    if (item < ITEMS) {
+      const int r = item / 13, cg = item - r * 13;
+      const uint32_t off = chunk_off(r, cg);
+      uint32_t dh[4], dl[4], bits = 0u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_h2(dreg[i][2 * j] * sD, dreg[i][2 * j + 1] * sD, dh[j], dl[j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (dreg[i][j] > thr && (cg < 12 || j < 4)) bits |= 1u << j;
+      *reinterpret_cast<uint4*>(x_hi + off) = make_uint4(dh[0], dh[1], dh[2], dh[3]);
+      *reinterpret_cast<uint4*>(x_lo + off) = make_uint4(dl[0], dl[1], dl[2], dl[3]);
+      maskb[r * 16 + cg] = (uint8_t)bits;
+    }
+  }
+}
+
+// accumulator (TMEM, 112 columns at acc) * scale -> K-major hi / lo tiles; thread = (row m, column half)
+__device__ __forceinline__ void acc_to_tiles(uint32_t acc, float scale, uint8_t* x_hi, uint8_t* x_lo, int m, int half) {
+#pragma unroll 1
+  for (int g = 0; g < 7; ++g) {
+    const int cg = half * 7 + g;
+    uint32_t v[8];
+    tmem_ld8(acc + (uint32_t)(cg * 8), v);
+    tmem_ld_wait();
+    if (m < (int)ROWS) {
+      uint32_t th[4], tl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // columns >= 100 are padding (depth-tile garbage): force 0
+        const float x0 = cg * 8 + 2 * j < N ? __uint_as_float(v[2 * j]) * scale : 0.f;
+        const float x1 = cg * 8 + 2 * j + 1 < N ? __uint_as_float(v[2 * j + 1]) * scale : 0.f;
+        split_h2(x0, x1, th[j], tl[j]);
+      }
+      const uint32_t off = chunk_off(m, cg);
+      *reinterpret_cast<uint4*>(x_hi + off) = make_uint4(th[0], th[1], th[2], th[3]);
+      *reinterpret_cast<uint4*>(x_lo + off) = make_uint4(tl[0], tl[1], tl[2], tl[3]);
+    }
+  }
+}
+
+// depth max / abs-max over this thread's register-held chunks
+__device__ __forceinline__ void plane_max(const float (&dreg)[IPT][8], int tid, float& lmax, float& lamax) {
+  lmax = -INFINITY; lamax = 0.f;
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const int item = tid + i * NT;
+    const int cg = item % 13;
+    if (item < ITEMS) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < 4 || cg < 12) lmax = fmaxf(lmax, dreg[i][j]);      // chunk 12 holds columns 96..99 only
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lamax = fmaxf(lamax, fabsf(dreg[i][j]));
+  }
+}
+
+// e(t) and the (Ex_0..Ex_3)(t) table of one sample
+__device__ __forceinline__ void build_tables(float beta, float gamma, float* tab, float4* ex4, int tid) {
+  const float inv_b2 = 1.0f / (beta * beta);
+  if (tid < N) tab[tid] = expf(-(CP2 * (float)(tid * tid)) * inv_b2);
+  const float inv_g = 1.0f / gamma;
+  for (int i = tid; i < 4 * N; i += NT) {
+    const int k = i / N, t = i - k * N;
+    const float d = (float)(t - 12 - 25 * k);
+    reinterpret_cast<float*>(ex4)[t * 4 + k] = expf(-(CM2 * d * d) * inv_g);
+  }
+}
+
+// forward -> backward hand-over, AUX_STRIDE floats per sample: rows m = 0..99 hold U_j(m) = sum_n HR[m][n] Ex_j(n),
+// U2_j(m) = sum_n HR[m][n] Ex_j(n) (n - 12 - 25 j)^2 (j = 0..3), the row sum and 3 pad floats; row 100 = {second max}
+constexpr int AUX_ROW = 12;
+constexpr int AUX_STRIDE = 101 * AUX_ROW;
+
 __global__ void __launch_bounds__(NT, 2)
 psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth, float* __restrict__ HR,
-                  float* __restrict__ LRd, float* __restrict__ psf, int B) {
+                  float* __restrict__ LRd, float* __restrict__ psf, float* __restrict__ aux, int B) {
   extern __shared__ __align__(1024) uint8_t sm[];
   const uint32_t base = smem_u32(sm);
   float* tab = reinterpret_cast<float*>(sm + OFF_TAB);
@@ -178,79 +298,21 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     const float alpha = ab[b * 3 + 0], beta = ab[b * 3 + 1], gamma = ab[b * 3 + 2];
 
     // ---- phase A1: depth max over this thread's chunks (loaded into registers one sample ahead); tables ----
-    float lmax = -INFINITY, lamax = 0.f;
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const int item = tid + i * NT;
-      const int cg = item % 13;
-      if (item < ITEMS) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < 4 || cg < 12) lmax = fmaxf(lmax, dreg[i][j]);      // chunk 12 holds columns 96..99 only
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) lamax = fmaxf(lamax, fabsf(dreg[i][j]));
-    }
-    {
-      const float inv_b2 = 1.0f / (beta * beta);
-      if (tid < N) tab[tid] = expf(-(CP2 * (float)(tid * tid)) * inv_b2);
-      const float inv_g = 1.0f / gamma;
-      for (int i = tid; i < 4 * N; i += NT) {
-        const int k = i / N, t = i - k * N;
-        const float d = (float)(t - 12 - 25 * k);
-        reinterpret_cast<float*>(ex4)[t * 4 + k] = expf(-(CM2 * d * d) * inv_g);
-      }
-    }
+    float lmax, lamax;
+    plane_max(dreg, tid, lmax, lamax);
+    build_tables(beta, gamma, tab, ex4, tid);
     const float dmax = block_max256(lmax, red);        // (syncs: tab visible)
     const float amax = block_max256(lamax, red);
     const float thr = dmax - 1e-3f;
     int dexp = 0;
     if (amax > 0.f) (void)frexpf(amax, &dexp);         // amax = f * 2^dexp, f in [0.5, 1)
     const float sD = ldexpf(1.0f, 4 - dexp);           // |depth| sD < 16
-    // 4 shifted copies of the packed (hi, lo) table of 16 e(|j - 99|), so that any 8 consecutive entries are two
-    // aligned 16-byte loads.  The PSF has 99 taps: E is banded, entries with |k - m| > 49 are 0.
-    for (int i = tid; i < 4 * (int)TAB2_LEN; i += NT) {
-      const int s = i / (int)TAB2_LEN, qn = i - s * (int)TAB2_LEN;
-      const int j = qn + s;
-      const int t = j < 99 ? 99 - j : j - 99;
-      uint32_t hi, lo;
-      split_h2(t <= 49 ? tab[t] * 16.0f : 0.f, 0.f, hi, lo);
-      tab2[i] = (hi & 0xFFFFu) | (lo << 16);
-    }
+    build_tab2<0>(tab, tab2, tid);
     __syncthreads();
 
     // ---- phase A2: E tiles (K-major), depth tiles (MN-major: row = k, as in HBM) + contact bytes ----
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const int item = tid + i * NT;
-      if (item < ITEMS) {
-        const int r = item / 13, cg = item - r * 13;
-        const uint32_t off = chunk_off(r, cg);
-        {   // E[r][8 cg + j] = e(|8 cg + j - r|): entries start .. start + 7 of the table
-          const int start = 8 * cg - r + 99;
-          const int s = start & 3;
-          const uint4* tp = reinterpret_cast<const uint4*>(tab2 + s * (int)TAB2_LEN + (start - s));
-          const uint4 p0 = tp[0];
-          uint4 p1 = tp[1];
-          if (cg == 12) p1 = make_uint4(0u, 0u, 0u, 0u);       // k = 100..103: K padding
-          const uint4 eh = make_uint4(__byte_perm(p0.x, p0.y, 0x5410), __byte_perm(p0.z, p0.w, 0x5410),
-                                      __byte_perm(p1.x, p1.y, 0x5410), __byte_perm(p1.z, p1.w, 0x5410));
-          const uint4 el = make_uint4(__byte_perm(p0.x, p0.y, 0x7632), __byte_perm(p0.z, p0.w, 0x7632),
-                                      __byte_perm(p1.x, p1.y, 0x7632), __byte_perm(p1.z, p1.w, 0x7632));
-          *reinterpret_cast<uint4*>(sm + OFF_E_HI + off) = eh;
-          *reinterpret_cast<uint4*>(sm + OFF_E_LO + off) = el;
-        }
-        uint32_t dh[4], dl[4], bits = 0u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) split_h2(dreg[i][2 * j] * sD, dreg[i][2 * j + 1] * sD, dh[j], dl[j]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (dreg[i][j] > thr && (cg < 12 || j < 4)) bits |= 1u << j;
-        *reinterpret_cast<uint4*>(sm + OFF_X_HI + off) = make_uint4(dh[0], dh[1], dh[2], dh[3]);
-        *reinterpret_cast<uint4*>(sm + OFF_X_LO + off) = make_uint4(dl[0], dl[1], dl[2], dl[3]);
-        maskb[r * 16 + cg] = (uint8_t)bits;
-      }
-    }
+    build_toeplitz_tiles(tab2, sm + OFF_E_HI, sm + OFF_E_LO, tid);
+    store_plane_tiles(dreg, sD, thr, sm + OFF_X_HI, sm + OFF_X_LO, maskb, tid);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -288,26 +350,7 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
 
     // ---- phase X: T -> hi/lo fp16 -> smem (K-major, over the depth tiles, which GEMM1 has finished reading) ----
     // accumulator = 16 sD T = 2^(8 - dexp) T,  |T| <= 99 |depth|max  =>  < 2^15: no rescaling needed
-#pragma unroll 1
-    for (int g = 0; g < 7; ++g) {
-      const int cg = half * 7 + g;
-      uint32_t v[8];
-      tmem_ld8(tmem_base + lane_addr + (uint32_t)(cg * 8), v);
-      tmem_ld_wait();
-      if (m < (int)ROWS) {
-        uint32_t th[4], tl[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          // columns >= 100 are padding (depth-tile garbage): force 0
-          const float x0 = cg * 8 + 2 * j < N ? __uint_as_float(v[2 * j]) : 0.f;
-          const float x1 = cg * 8 + 2 * j + 1 < N ? __uint_as_float(v[2 * j + 1]) : 0.f;
-          split_h2(x0, x1, th[j], tl[j]);
-        }
-        const uint32_t off = chunk_off(m, cg);
-        *reinterpret_cast<uint4*>(sm + OFF_X_HI + off) = make_uint4(th[0], th[1], th[2], th[3]);
-        *reinterpret_cast<uint4*>(sm + OFF_X_LO + off) = make_uint4(tl[0], tl[1], tl[2], tl[3]);
-      }
-    }
+    acc_to_tiles(tmem_base + lane_addr, 1.0f, sm + OFF_X_HI, sm + OFF_X_LO, m, half);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -323,6 +366,17 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     }
     mbar_wait(bar2, ph);
     tc_fence_after();
+    // the T tiles are dead now: their memory holds (Ex_j(t) (t - 12 - 25 j)^2) and the half-row hand-over of the
+    // backward statistics (both only needed when the backward hand-over `aux` is requested)
+    float4* ex24 = reinterpret_cast<float4*>(sm + OFF_X_HI);
+    float* xch = reinterpret_cast<float*>(sm + OFF_X_HI + 2048);
+    if (aux) {
+      for (int i = tid; i < 4 * N; i += NT) {
+        const int t = i >> 2, k = i & 3;
+        const float d = (float)(t - 12 - 25 * k);
+        reinterpret_cast<float*>(ex24)[i] = reinterpret_cast<const float*>(ex4)[i] * (d * d);
+      }
+    }
 
     // ---- phase E: epilogue.  accumulator = 2^(8 - dexp) 16 (E D E) ----
     const float cs = alpha * ldexpf(1.0f, dexp - 12);
@@ -345,7 +399,7 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     }
     m2 = block_max256(m2, red);
     // pass 2: fill, store HR, accumulate the degradation sums of this thread's row segment
-    float rj[4] = {0.f, 0.f, 0.f, 0.f}, rs = 0.f;
+    float rj[4] = {0.f, 0.f, 0.f, 0.f}, r2[4] = {0.f, 0.f, 0.f, 0.f}, rs = 0.f;
     float* hdst = HR + (size_t)b * N * N + (size_t)m * N;
 #pragma unroll 1
     for (int g = 0; g < 7; ++g) {
@@ -365,6 +419,11 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
             rs += h[j];
             rj[0] = fmaf(h[j], e4.x, rj[0]); rj[1] = fmaf(h[j], e4.y, rj[1]);
             rj[2] = fmaf(h[j], e4.z, rj[2]); rj[3] = fmaf(h[j], e4.w, rj[3]);
+            if (aux) {
+              const float4 f4 = ex24[cg * 8 + j];
+              r2[0] = fmaf(h[j], f4.x, r2[0]); r2[1] = fmaf(h[j], f4.y, r2[1]);
+              r2[2] = fmaf(h[j], f4.z, r2[2]); r2[3] = fmaf(h[j], f4.w, r2[3]);
+            }
           }
         }
         *reinterpret_cast<float4*>(hdst + cg * 8) = make_float4(h[0], h[1], h[2], h[3]);
@@ -394,6 +453,12 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       }
       p[0] += __shfl_xor_sync(0xffffffffu, p[0], 1);
       const float tot_w = warp_sum(m < N ? rs : 0.f);
+      if (aux && half == 1 && m < N) {                  // upper column half -> lower-half thread of the same row
+        float4* x4 = reinterpret_cast<float4*>(xch + m * AUX_ROW);
+        x4[0] = make_float4(rj[0], rj[1], rj[2], rj[3]);
+        x4[1] = make_float4(r2[0], r2[1], r2[2], r2[3]);
+        x4[2] = make_float4(rs, 0.f, 0.f, 0.f);
+      }
       __syncthreads();                                  // (red was last read by block_max256)
       if ((lane & 1) == 0) red[warp * 20 + (lane >> 1)] = p[0];
       if (lane == 0) red[warp * 20 + 16] = tot_w;
@@ -405,8 +470,251 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
         const float mm = expf(-100.0f / gamma);
         LRd[b * 16 + tid] = 1e-4f * (s - mm * tot) / (1.0f - mm);
       }
+      if (aux && half == 0 && m < N) {
+        const float4* x4 = reinterpret_cast<const float4*>(xch + m * AUX_ROW);
+        const float4 a0 = x4[0], a1 = x4[1], a2 = x4[2];
+        float4* dst = reinterpret_cast<float4*>(aux + (size_t)b * AUX_STRIDE + m * AUX_ROW);
+        dst[0] = make_float4(rj[0] + a0.x, rj[1] + a0.y, rj[2] + a0.z, rj[3] + a0.w);
+        dst[1] = make_float4(r2[0] + a1.x, r2[1] + a1.y, r2[2] + a1.z, r2[3] + a1.w);
+        dst[2] = make_float4(rs + a2.x, 0.f, 0.f, 0.f);
+      }
+      if (aux && tid == 0) aux[(size_t)b * AUX_STRIDE + 100 * AUX_ROW] = m2;
     }
     // all TMEM reads and shared-memory reads of this sample are complete before the next sample overwrites them
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward of the PSF model for the training case (gradient arrives through LR_degrade only, train/tPSFNet_train.py:
+// 186-189): d(alpha, beta, gamma) from dLRd, the depth plane and the forward's hand-over `aux`.
+//   w(m,n)  = kk (sum_j Ex_j(n) Qt_j(m) - mm gsum),  Qt_j(m) = sum_i g_ij Ex_i(m),  kk = 1e-4 / (1 - mm), mm = exp(-100/gamma)
+//   d alpha = sum_{non-contact} w HR / alpha = [sum_all w HR - m2 sum_contact w] / alpha   (HR = m2 on the contact set)
+//   d beta  = alpha 2 cp2 / beta^3 * sum_{non-contact} w P3,   P3 = E2 D E + E D E2,  E2[m][k] = e(|k-m|) (k-m)^2
+//   d gamma = closed form in G0 = sum g_ij S_ij, G1 = sum g_ij S1_ij, sum HR (psf.cu psf_bwd_kernel), all three linear in
+//             the per-row statistics U, U2, row sum that the forward left in `aux`
+// P3 takes four 100^3 contractions; they run as tcgen05.mma on fp16 hi/lo split operands exactly like the forward:
+//   T = E D -> acc0;  T2 = E2 D -> acc1;  acc0' = T E2  (+)=  T2 E      (the two products share one accumulator: the
+//   operand scales are chosen so that both carry 2^(12 - dexp))
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 2)
+psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth, const float* __restrict__ aux,
+                  const float* __restrict__ dLRd, float* __restrict__ dab, int B) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const uint32_t base = smem_u32(sm);
+  float* tab = reinterpret_cast<float*>(sm + OFF_TAB);
+  uint32_t* tab2 = reinterpret_cast<uint32_t*>(sm + OFF_TAB2);
+  float4* ex4 = reinterpret_cast<float4*>(sm + OFF_EX);
+  uint8_t* maskb = sm + OFF_MASK;
+  float* red = reinterpret_cast<float*>(sm + OFF_RED);
+  const uint32_t bar1 = base + OFF_BAR, tmem_slot = bar1 + 16u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((base & 1023u) != 0u) {
+    if (tid == 0) printf("tactilesr_b200 psf_tc: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  for (uint32_t i = tid; i < 4 * TILE / 16; i += NT) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (uint32_t i = tid; i < 104 * 16 / 4; i += NT) reinterpret_cast<uint32_t*>(maskb)[i] = 0u;
+  if (tid == 0) {
+    mbar_init(bar1, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t idesc1 = make_idesc(128, 112, 0, 1, 0, 0);   // A K-major, B MN-major (depth as it lies in HBM)
+  const uint32_t idesc2 = make_idesc(128, 112, 0, 0, 0, 0);   // both K-major
+
+  const int q = warp & 3, half = warp >> 2;
+  const int m = q * 32 + lane;
+  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+  const uint32_t acc0 = tmem_base + lane_addr, acc1 = tmem_base + 128u + lane_addr;
+  uint8_t* const e_hi = sm + OFF_E_HI; uint8_t* const e_lo = sm + OFF_E_LO;
+  uint8_t* const x_hi = sm + OFF_X_HI; uint8_t* const x_lo = sm + OFF_X_LO;
+
+  float dreg[IPT][8];
+  if ((int)blockIdx.x < B) load_plane(depth + (size_t)blockIdx.x * N * N, tid, dreg);
+  uint32_t nph = 0;                       // completed phases of bar1 (4 per sample)
+  auto wait_mma = [&]() {
+    mbar_wait(bar1, nph & 1u);
+    ++nph;
+    tc_fence_after();
+  };
+  auto publish = [&]() {                  // generic-proxy smem writes -> visible to the MMA; all TMEM reads retired
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+  };
+
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const float alpha = ab[b * 3 + 0], beta = ab[b * 3 + 1], gamma = ab[b * 3 + 2];
+    float g[16], gsum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) { g[t] = dLRd[b * 16 + t]; gsum += g[t]; }
+
+    // ---- tables, depth max, E and depth tiles ----
+    float lmax, lamax;
+    plane_max(dreg, tid, lmax, lamax);
+    build_tables(beta, gamma, tab, ex4, tid);
+    const float dmax = block_max256(lmax, red);
+    const float amax = block_max256(lamax, red);
+    const float thr = dmax - 1e-3f;
+    int dexp = 0;
+    if (amax > 0.f) (void)frexpf(amax, &dexp);
+    const float sD = ldexpf(1.0f, 4 - dexp);
+    build_tab2<0>(tab, tab2, tid);
+    __syncthreads();
+    build_toeplitz_tiles(tab2, e_hi, e_lo, tid);
+    store_plane_tiles(dreg, sD, thr, x_hi, x_lo, maskb, tid);
+    publish();
+
+    // ---- GEMM 1: T = E D -> acc0  (2^(8 - dexp) T) ----
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        issue_gemm3<1>(tmem_base, base + OFF_E_HI, base + OFF_E_LO, base + OFF_X_HI, base + OFF_X_LO, idesc1);
+        umma_commit(bar1);
+      }
+      __syncwarp();
+    }
+    if (b + (int)gridDim.x < B) load_plane(depth + (size_t)(b + gridDim.x) * N * N, tid, dreg);
+    build_tab2<1>(tab, tab2, tid);        // (all reads of the E table finished before publish())
+    __syncthreads();
+    wait_mma();
+    build_toeplitz_tiles(tab2, e_hi, e_lo, tid);      // E2 over E
+    publish();
+
+    // ---- GEMM 2: T2 = E2 D -> acc1  (2^(8 - dexp) T2) ----
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        issue_gemm3<1>(tmem_base + 128u, base + OFF_E_HI, base + OFF_E_LO, base + OFF_X_HI, base + OFF_X_LO, idesc1);
+        umma_commit(bar1);
+      }
+      __syncwarp();
+    }
+    build_tab2<2>(tab, tab2, tid);        // 2^15 e(t) for the last product
+    wait_mma();
+    acc_to_tiles(acc0, 1.0f, x_hi, x_lo, m, half);    // T over the depth tiles
+    publish();
+
+    // ---- GEMM 3: acc0 = T E2  (2^(12 - dexp)) ----
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        issue_gemm3<0>(tmem_base, base + OFF_X_HI, base + OFF_X_LO, base + OFF_E_HI, base + OFF_E_LO, idesc2);
+        umma_commit(bar1);
+      }
+      __syncwarp();
+    }
+    wait_mma();
+    acc_to_tiles(acc1, 1.0f / 2048.0f, x_hi, x_lo, m, half);    // 2^(-3 - dexp) T2 over T;  |T2| < 2^(18 + dexp)
+    build_toeplitz_tiles(tab2, e_hi, e_lo, tid);                // 2^15 E over E2
+    publish();
+
+    // ---- GEMM 4: acc0 += T2 E ----
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        issue_gemm3<0, 1>(tmem_base, base + OFF_X_HI, base + OFF_X_LO, base + OFF_E_HI, base + OFF_E_LO, idesc2);
+        umma_commit(bar1);
+      }
+      __syncwarp();
+    }
+    // per-row factors while the MMAs run
+    const float mm = expf(-100.0f / gamma);
+    const float mg = mm * gsum;
+    const float4 em = m < N ? ex4[m] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float ei[4] = {em.x, em.y, em.z, em.w};
+    float qt[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) qt[j] = ei[0] * g[j] + ei[1] * g[4 + j] + ei[2] * g[8 + j] + ei[3] * g[12 + j];
+    float G0 = 0.f, G1 = 0.f, tot = 0.f;
+    if (half == 0 && m < N) {             // d gamma / d alpha statistics from the forward's per-row sums
+      const float4* a4 = reinterpret_cast<const float4*>(aux + (size_t)b * AUX_STRIDE + m * AUX_ROW);
+      const float4 u = a4[0], u2 = a4[1];
+      tot = a4[2].x;
+      const float uu[4] = {u.x, u.y, u.z, u.w}, vv[4] = {u2.x, u2.y, u2.z, u2.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float ai = 0.f, bi = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { ai = fmaf(g[i * 4 + j], uu[j], ai); bi = fmaf(g[i * 4 + j], vv[j], bi); }
+        const float d = (float)(m - 12 - 25 * i);
+        G0 = fmaf(ei[i], ai, G0);
+        G1 = fmaf(ei[i] * (d * d), ai, fmaf(ei[i], bi, G1));
+      }
+    }
+    wait_mma();
+
+    // ---- epilogue over acc0 = 2^(12 - dexp) P3 ----
+    float dbs = 0.f, cw = 0.f, cnt = 0.f;
+    const uint8_t* mrow = maskb + (m < (int)ROWS ? m : 0) * 16;
+#pragma unroll 1
+    for (int gI = 0; gI < 7; ++gI) {
+      const int cg = half * 7 + gI;
+      uint32_t v[8];
+      tmem_ld8(acc0 + (uint32_t)(cg * 8), v);
+      tmem_ld_wait();
+      if (m < N && cg < 13) {
+        const uint32_t bits = mrow[cg];
+        const int nv = cg == 12 ? 4 : 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < nv) {
+            const float4 e4 = ex4[cg * 8 + j];
+            const float wc = fmaf(e4.x, qt[0], fmaf(e4.y, qt[1], fmaf(e4.z, qt[2], e4.w * qt[3])));
+            const bool contact = (bits >> j) & 1u;
+            dbs = fmaf(contact ? 0.f : wc - mg, __uint_as_float(v[j]), dbs);
+            cw += contact ? wc : 0.f;
+          }
+        }
+        cnt += (float)__popc(bits & (cg == 12 ? 0x0Fu : 0xFFu));
+      }
+    }
+    {
+      float p[6] = {dbs, cw, cnt, G0, G1, tot};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) p[k] = warp_sum(p[k]);
+      __syncthreads();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) red[warp * 20 + k] = p[k];
+      }
+      __syncthreads();
+      if (tid == 0) {
+        float r[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int w = 0; w < NT / 32; ++w)
+#pragma unroll
+          for (int k = 0; k < 6; ++k) r[k] += red[w * 20 + k];
+        const float om = 1.0f - mm, kk = 1e-4f / om;
+        const float m2 = aux[(size_t)b * AUX_STRIDE + 100 * AUX_ROW];
+        const float s_all = kk * (r[3] - mg * r[5]);                 // sum over all pixels of w HR
+        const float s_c = m2 * kk * (r[1] - mg * r[2]);              // its contact part (HR = m2 there)
+        const float inv_g2 = 1.0f / (gamma * gamma);
+        const float mp = mm * 100.0f * inv_g2;
+        dab[b * 3 + 0] = (s_all - s_c) / alpha;
+        dab[b * 3 + 1] = alpha * 2.0f * CP2 / (beta * beta * beta) * kk * ldexpf(1.0f, dexp - 12) * r[0];
+        dab[b * 3 + 2] = 1e-4f * ((CM2 * inv_g2 * r[4] - mp * r[5] * gsum) / om + (r[3] - mm * r[5] * gsum) * mp / (om * om));
+      }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -432,17 +740,35 @@ int tsr_get_psf_mode(void) { return g_psf_mode; }
 int tsr_psf_forward_ffma(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, int B,
                          cudaStream_t stream);
 
-int tsr_psf_forward_tc(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, int B,
-                       cudaStream_t stream) {
-  TSR_REQUIRE(alphaBeta && depth && HR && LRd && B > 0, "psf_forward_tc: bad argument");
-  TSR_REQUIRE(((uintptr_t)depth & 15) == 0 && ((uintptr_t)HR & 15) == 0, "psf_forward_tc: depth / HR must be 16-byte aligned");
-  TSR_CUDA(cudaFuncSetAttribute(psf_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+size_t tsr_psf_aux_floats(void) { return (size_t)AUX_STRIDE; }
+
+static int psf_tc_grid(int B) {
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  int grid = B < 2 * sms ? B : 2 * sms;
-  psf_fwd_tc_kernel<<<grid, NT, SMEM_BYTES, stream>>>(alphaBeta, depth, HR, LRd, psf, B);
+  return B < 2 * sms ? B : 2 * sms;
+}
+
+// aux (B x tsr_psf_aux_floats() floats, or NULL): per-row statistics of HR for tsr_psf_backward_tc
+int tsr_psf_forward_tc(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, float* aux, int B,
+                       cudaStream_t stream) {
+  TSR_REQUIRE(alphaBeta && depth && HR && LRd && B > 0, "psf_forward_tc: bad argument");
+  TSR_REQUIRE(((uintptr_t)depth & 15) == 0 && ((uintptr_t)HR & 15) == 0 && ((uintptr_t)aux & 15) == 0,
+              "psf_forward_tc: depth / HR / aux must be 16-byte aligned");
+  TSR_CUDA(cudaFuncSetAttribute(psf_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  psf_fwd_tc_kernel<<<psf_tc_grid(B), NT, SMEM_BYTES, stream>>>(alphaBeta, depth, HR, LRd, psf, aux, B);
   TSR_CHECK_LAUNCH("psf_forward_tc");
+  return TSR_OK;
+}
+
+// d alphaBeta (B,3) from dLRd (B,16) alone (the training case), from the depth planes and the forward's aux
+int tsr_psf_backward_tc(const float* alphaBeta, const float* depth, const float* aux, const float* dLRd,
+                        float* dalphaBeta, int B, cudaStream_t stream) {
+  TSR_REQUIRE(alphaBeta && depth && aux && dLRd && dalphaBeta && B > 0, "psf_backward_tc: bad argument");
+  TSR_REQUIRE(((uintptr_t)depth & 15) == 0 && ((uintptr_t)aux & 15) == 0, "psf_backward_tc: depth / aux must be 16-byte aligned");
+  TSR_CUDA(cudaFuncSetAttribute(psf_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  psf_bwd_tc_kernel<<<psf_tc_grid(B), NT, SMEM_BYTES, stream>>>(alphaBeta, depth, aux, dLRd, dalphaBeta, B);
+  TSR_CHECK_LAUNCH("psf_backward_tc");
   return TSR_OK;
 }
 
@@ -450,7 +776,7 @@ int tsr_psf_forward_tc(const float* alphaBeta, const float* depth, float* HR, fl
 int tsr_psf_forward(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, int B,
                     cudaStream_t stream) {
   if (g_psf_mode == 1) return tsr_psf_forward_ffma(alphaBeta, depth, HR, LRd, psf, B, stream);
-  return tsr_psf_forward_tc(alphaBeta, depth, HR, LRd, psf, B, stream);
+  return tsr_psf_forward_tc(alphaBeta, depth, HR, LRd, psf, nullptr, B, stream);
 }
 
 }  // extern "C"

@@ -41,8 +41,19 @@ class _PSFFn(torch.autograd.Function):
         HR = torch.empty((B, 1, 100, 100), dtype=torch.float32, device=dev)
         LRd = torch.empty((B, 1, 4, 4), dtype=torch.float32, device=dev)
         psf = torch.empty((B, 1, 99, 99), dtype=torch.float32, device=dev)
-        _lib.call("tsr_psf_forward", ab.data_ptr(), d.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), B, st)
-        ctx.save_for_backward(d, HR, *acts, *ws)
+        L = _lib.lib()
+        aux = None
+        if L.tsr_get_psf_mode() == 0:
+            # tcgen05 forward; when a backward may follow it also leaves the per-row statistics of HR the tcgen05
+            # backward needs (4.8 KB per sample) so that the backward never re-reads HR
+            if any(ctx.needs_input_grad):
+                aux = torch.empty((B, int(L.tsr_psf_aux_floats())), dtype=torch.float32, device=dev)
+            _lib.call("tsr_psf_forward_tc", ab.data_ptr(), d.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(),
+                      0 if aux is None else aux.data_ptr(), B, st)
+        else:
+            _lib.call("tsr_psf_forward_ffma", ab.data_ptr(), d.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), B, st)
+        ctx.has_aux = aux is not None
+        ctx.save_for_backward(d, HR, *acts, *ws, *([aux] if aux is not None else []))
         return HR, LRd, psf, ab.view(B, 1, 3).clone()
 
     @staticmethod
@@ -59,9 +70,14 @@ class _PSFFn(torch.autograd.Function):
             return None if g is None else g.detach().contiguous().float()
         dHR, dLRd, dpsf, dab_direct = prep(dHR), prep(dLRd), prep(dpsf), prep(dab_direct)
         dab = torch.empty((B, 3), dtype=torch.float32, device=dev)
-        _lib.call("tsr_psf_backward", ab.data_ptr(), d.data_ptr(), HR.data_ptr(),
-                  0 if dLRd is None else dLRd.data_ptr(), 0 if dHR is None else dHR.data_ptr(),
-                  0 if dpsf is None else dpsf.data_ptr(), dab.data_ptr(), B, st)
+        if ctx.has_aux and dHR is None and dpsf is None and dLRd is not None:
+            # the training case (train/tPSFNet_train.py:186-189: only LR_degrade is supervised): tcgen05 backward
+            _lib.call("tsr_psf_backward_tc", ab.data_ptr(), d.data_ptr(), saved[11].data_ptr(), dLRd.data_ptr(),
+                      dab.data_ptr(), B, st)
+        else:
+            _lib.call("tsr_psf_backward", ab.data_ptr(), d.data_ptr(), HR.data_ptr(),
+                      0 if dLRd is None else dLRd.data_ptr(), 0 if dHR is None else dHR.data_ptr(),
+                      0 if dpsf is None else dpsf.data_ptr(), dab.data_ptr(), B, st)
         if dab_direct is not None:
             dab = dab + dab_direct.view(B, 3)
         grads = []

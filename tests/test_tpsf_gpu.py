@@ -115,7 +115,10 @@ def test_psf_tensor_core_forward_matches_ffma_forward(B):
     outs = {}
     for name in ("tsr_psf_forward_ffma", "tsr_psf_forward_tc"):
         HR = torch.empty(B, 100, 100, device="cuda"); LRd = torch.empty(B, 16, device="cuda"); psf = torch.empty(B, 99, 99, device="cuda")
-        _lib.call(name, ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), B, st)
+        if name.endswith("_tc"):
+            _lib.call(name, ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), 0, B, st)
+        else:
+            _lib.call(name, ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), B, st)
         outs[name] = (HR, LRd, psf)
     (h0, l0, p0), (h1, l1, p1) = outs["tsr_psf_forward_ffma"], outs["tsr_psf_forward_tc"]
     assert torch.isfinite(h1).all() and torch.isfinite(l1).all()
@@ -125,3 +128,32 @@ def test_psf_tensor_core_forward_matches_ffma_forward(B):
     print(f"psf tc vs ffma B={B}: HR max err / sample max {err:.2e}, rel-L2 {rel_l2(h1, h0):.2e}, LRd rel-L2 {rel_l2(l1, l0):.2e}")
     assert err < 1e-5, err
     assert rel_l2(h1, h0) < 3e-6 and rel_l2(l1, l0) < 1e-5
+
+
+@pytest.mark.parametrize("B", [3, 700])
+def test_psf_tensor_core_backward_matches_ffma_backward(B):
+    """tcgen05 backward (training case: gradient through LR_degrade only; P3 = E2 D E + E D E2 as four split-operand
+    contractions, d gamma / d alpha from the forward's per-row statistics) against the FFMA backward, through the C ABI."""
+    from oracle import tpsf_oracle as po
+    from tactilesr_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(100 + B)
+    ab = torch.stack([torch.rand(B, generator=g) * 2 + 0.2, torch.rand(B, generator=g) * 3 + 0.25,
+                      torch.rand(B, generator=g) * 40 + 0.4], 1).cuda().contiguous()
+    depth = po.synthetic_depth(min(B, 16), 6).repeat((B + 15) // 16, 1, 1)[:B].clone()
+    depth[1] *= 3.0
+    depth = depth.cuda().contiguous()
+    dL = (torch.randn(B, 16, generator=g) * 0.3).cuda().contiguous()
+    st = torch.cuda.current_stream().cuda_stream
+    HR = torch.empty(B, 100, 100, device="cuda"); LRd = torch.empty(B, 16, device="cuda")
+    aux = torch.empty(B, int(L.tsr_psf_aux_floats()), device="cuda")
+    _lib.call("tsr_psf_forward_tc", ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), LRd.data_ptr(), 0, aux.data_ptr(), B, st)
+    d0 = torch.empty(B, 3, device="cuda"); d1 = torch.empty(B, 3, device="cuda")
+    _lib.call("tsr_psf_backward", ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), dL.data_ptr(), 0, 0, d0.data_ptr(), B, st)
+    _lib.call("tsr_psf_backward_tc", ab.data_ptr(), depth.data_ptr(), aux.data_ptr(), dL.data_ptr(), d1.data_ptr(), B, st)
+    assert torch.isfinite(d1).all()
+    for c, name in enumerate(("alpha", "beta", "gamma")):
+        e = rel_l2(d1[:, c], d0[:, c])
+        worst = ((d1[:, c] - d0[:, c]).abs() / d0[:, c].abs().clamp_min(1e-3 * d0[:, c].abs().max())).max().item()
+        print(f"psf bwd tc vs ffma B={B} d{name}: rel-L2 {e:.2e}, worst per-sample {worst:.2e}")
+        assert e < 2e-4 and worst < 2e-3, (name, e, worst)

@@ -10,10 +10,13 @@ yy, xx = torch.meshgrid(torch.arange(100.0, device="cuda"), torch.arange(100.0, 
 depth = torch.clamp((20 - ((yy - 50) ** 2 + (xx - 45) ** 2).sqrt()) / 2 + 0.5, 0, 1).expand(B, 100, 100).contiguous()
 HR = torch.empty(B, 100, 100, device="cuda"); LRd = torch.empty(B, 16, device="cuda"); psf = torch.empty(B, 99, 99, device="cuda")
 dL = torch.rand(B, 16, device="cuda"); dab = torch.empty(B, 3, device="cuda")
-f_tc = lambda: _lib.call("tsr_psf_forward_tc", ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), B, st)
+aux = torch.empty(B, int(_lib.lib().tsr_psf_aux_floats()), device="cuda")
+f_tc = lambda: _lib.call("tsr_psf_forward_tc", ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), 0, B, st)
+f_tca = lambda: _lib.call("tsr_psf_forward_tc", ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), aux.data_ptr(), B, st)
+b_tc = lambda: _lib.call("tsr_psf_backward_tc", ab.data_ptr(), depth.data_ptr(), aux.data_ptr(), dL.data_ptr(), dab.data_ptr(), B, st)
 f_ff = lambda: _lib.call("tsr_psf_forward_ffma", ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), B, st)
 b = lambda: _lib.call("tsr_psf_backward", ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), dL.data_ptr(), 0, 0, dab.data_ptr(), B, st)
-for name, fn in (("fwd tcgen05", f_tc), ("fwd ffma", f_ff), ("bwd", b)):
+for name, fn in (("fwd tcgen05", f_tc), ("fwd tcgen05 + aux", f_tca), ("fwd ffma", f_ff), ("bwd tcgen05", b_tc), ("bwd ffma", b)):
     for _ in range(2): fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
