@@ -93,9 +93,10 @@ int tsr_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float
                        const float* running_var, float eps, float* scale, float* shift, float* save_mean,
                        float* save_invstd, tsr_stream_t stream);
 /* out = [relu](y * scale + shift): BatchNorm2d + nn.ReLU(True), written into a channel slice (replaces torch.cat
- * :74, :81, :200, :203). */
+ * :74, :81, :200, :203).  out2_bf16 (may be NULL; 16-bit y / out only): a second copy of the result as bf16 with row
+ * stride out2_ld -- the weight-gradient operand kept by the "fp16" precision mode. */
 int tsr_bn_apply(const void* y, int y_ld, int y_bf16, const float* scale, const float* shift, void* out, int out_ld,
-                 int out_bf16, long long npix, int C, int relu, tsr_stream_t stream);
+                 int out_bf16, long long npix, int C, int relu, void* out2_bf16, int out2_ld, tsr_stream_t stream);
 size_t tsr_bn_backward_workspace(long long npix, int C);
 /* autograd backward of BatchNorm2d(+ReLU): da -> dy, dgamma, dbeta (deterministic two-level reductions). */
 int tsr_bn_backward(const void* da, int da_ld, const void* y, int y_ld, void* dy, int dy_ld, int act_bf16,

@@ -41,7 +41,7 @@ SIGNATURES = {
     "tsr_bn_workspace": (_Z, [_L, _I]),
     "tsr_bn_train_stats": (_I, [_P, _I, _I, _L, _I, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _Z, _P]),
     "tsr_bn_eval_coeffs": (_I, [_I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P]),
-    "tsr_bn_apply": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _L, _I, _I, _P]),
+    "tsr_bn_apply": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _L, _I, _I, _P, _I, _P]),
     "tsr_bn_backward_workspace": (_Z, [_L, _I]),
     "tsr_bn_backward": (_I, [_P, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _P, _Z, _P]),
     "tsr_relu_backward": (_I, [_P, _I, _P, _I, _P, _I, _I, _L, _I, _P]),

@@ -426,8 +426,10 @@ bn_stats_partial_v_kernel(const T* __restrict__ x, int ld, int npix, int C, floa
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_apply_v_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ scale, const float* __restrict__ shift,
-                  T* __restrict__ out, int out_ld, long long npix, int C, int relu) {
-  // each thread owns one 16-byte channel vector (fixed q) and strides over pixels: coefficients live in registers
+                  T* __restrict__ out, int out_ld, long long npix, int C, int relu, __nv_bfloat16* __restrict__ out2,
+                  int out2_ld) {
+  // each thread owns one 16-byte channel vector (fixed q) and strides over pixels: coefficients live in registers.
+  // out2 (optional, 16-bit T only): a second, bf16 copy of the result -- the weight-gradient operand of the "fp16" mode
   constexpr int N = V16<T>::N;
   const int qn = C / N;                       // divides 256
   const int q = threadIdx.x % qn;
@@ -444,6 +446,9 @@ bn_apply_v_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ s
       if (relu) v[k] = fmaxf(v[k], 0.f);
     }
     V16<T>::store(out + p * out_ld + q * N, v);
+    if constexpr (N == 8) {
+      if (out2) V16<__nv_bfloat16>::store(out2 + p * out2_ld + q * N, v);
+    }
   }
 }
 
@@ -649,18 +654,23 @@ int tsr_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float
   } while (0)
 
 int tsr_bn_apply(const void* y, int y_ld, int y_bf16, const float* scale, const float* shift, void* out, int out_ld,
-                 int out_bf16, long long npix, int C, int relu, cudaStream_t stream) {
+                 int out_bf16, long long npix, int C, int relu, void* out2_bf16, int out2_ld, cudaStream_t stream) {
   TSR_REQUIRE(y && scale && shift && out, "bn_apply: null pointer");
   TSR_REQUIRE(C % 4 == 0 && y_ld % 4 == 0 && out_ld % 4 == 0, "bn_apply: C and strides must be multiples of 4");
   int grid = ew_grid(npix * (C / 4));
+  __nv_bfloat16* o2 = (__nv_bfloat16*)out2_bf16;
 #define ARGS(Ti, To) (const Ti*)y, y_ld, scale, shift, (To*)out, out_ld, npix, C, relu
-  if (y_bf16 && y_bf16 == out_bf16 && C % 8 == 0 && 256 % (C / 8) == 0 && y_ld % 8 == 0 && out_ld % 8 == 0) {
-    if (y_bf16 == TSR_DT_F16) bn_apply_v_kernel<__half><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>(ARGS(__half, __half));
-    else bn_apply_v_kernel<__nv_bfloat16><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>(ARGS(__nv_bfloat16, __nv_bfloat16));
-  } else if (!y_bf16 && !out_bf16 && 256 % (C / 4) == 0) {
-    bn_apply_v_kernel<float><<<grid, 256, 0, stream>>>(ARGS(float, float));
+  if (y_bf16 && y_bf16 == out_bf16 && C % 8 == 0 && 256 % (C / 8) == 0 && y_ld % 8 == 0 && out_ld % 8 == 0 &&
+      (!o2 || out2_ld % 8 == 0)) {
+    if (y_bf16 == TSR_DT_F16) bn_apply_v_kernel<__half><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>(ARGS(__half, __half), o2, out2_ld);
+    else bn_apply_v_kernel<__nv_bfloat16><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>(ARGS(__nv_bfloat16, __nv_bfloat16), o2, out2_ld);
   } else {
-    TSR_DISPATCH_T(y_bf16, Ti, TSR_DISPATCH_T(out_bf16, To, bn_apply_kernel<Ti, To><<<grid, 256, 0, stream>>>(ARGS(Ti, To))));
+    TSR_REQUIRE(!o2, "bn_apply: the second (bf16) output needs 16-bit operands with C %% 8 == 0");
+    if (!y_bf16 && !out_bf16 && 256 % (C / 4) == 0) {
+      bn_apply_v_kernel<float><<<grid, 256, 0, stream>>>(ARGS(float, float), nullptr, 0);
+    } else {
+      TSR_DISPATCH_T(y_bf16, Ti, TSR_DISPATCH_T(out_bf16, To, bn_apply_kernel<Ti, To><<<grid, 256, 0, stream>>>(ARGS(Ti, To))));
+    }
   }
 #undef ARGS
   TSR_CHECK_LAUNCH("bn_apply");

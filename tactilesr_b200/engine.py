@@ -90,7 +90,10 @@ class RunCtx:
         self.saved: Dict[object, tuple] = {}
         self.x: Optional[torch.Tensor] = None
         self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
-        self.xsave: Dict[tuple, torch.Tensor] = {}      # "fp16" mode: bf16 copies of conv inputs (wgrad operands)
+        # "fp16" mode with gradients: bf16 shadow of every buffer some conv reads (the weight-gradient operand; tcgen05
+        # kind::f16 cannot mix an fp16 x with a bf16 dy).  Producers write their channel slice of the shadow.
+        self.shadow: Dict[Buf, torch.Tensor] = {}
+        self.conv_inputs: set = set()
         self._ws: Optional[torch.Tensor] = None
 
     # -- buffers ------------------------------------------------------------------------------
@@ -119,6 +122,24 @@ class RunCtx:
             self.grads[buf] = t
             self.grad_written[buf] = False
         return t
+
+    def wants_shadow(self, buf: Buf) -> bool:
+        return self.act == 2 and self.need_grad and buf in self.conv_inputs
+
+    def sptr(self, v: View) -> Tuple[int, int]:
+        """(pointer, ld) of view v inside the bf16 shadow of its buffer."""
+        t = self.shadow.get(v.buf)
+        if t is None:
+            t = torch.empty((self.npix, v.buf.C), dtype=torch.bfloat16, device=self.device)
+            self.shadow[v.buf] = t
+        return t.data_ptr() + v.c0 * 2, v.buf.C
+
+    def shadow_fill(self, v: View) -> None:
+        """Copy the freshly written fp16 view into the shadow (producers without a fused second output)."""
+        if self.wants_shadow(v.buf):
+            ip, ild = self.vptr(v)
+            sp, sld = self.sptr(v)
+            _lib.call("tsr_copy_channels", ip, ild, 2, sp, sld, 1, self.npix, v.C, _lib.stream_ptr())
 
     def workspace(self, nbytes: int) -> Tuple[int, int]:
         nbytes = max(int(nbytes), 256)
@@ -224,6 +245,7 @@ class HeadOp(Op):
         op, old = c.vptr(self.out)
         _lib.call("tsr_head_fwd", xp, xbs, self.weight.data_ptr(), op, old, c.act, c.B, self.sf,
                   1 if self.relu else 0, _lib.stream_ptr())
+        c.shadow_fill(self.out)
 
     def bwd(self, c):
         st = _lib.stream_ptr()
@@ -275,26 +297,16 @@ class ConvOp(Op):
 
     def _wgrad_input(self, c: RunCtx):
         """(pointer, ld) of the conv input as the weight-gradient kernel wants it (bf16 in both tensor-core modes)."""
-        if c.act != 2:
-            return c.vptr(self.src)
-        key = (self.src.buf, self.src.c0, self.src.C)
-        t = c.xsave.get(key)
-        if t is None:
-            t = torch.empty((c.npix, self.src.C), dtype=torch.bfloat16, device=c.device)
-            ip, ild = c.vptr(self.src)
-            _lib.call("tsr_copy_channels", ip, ild, 2, t.data_ptr(), self.src.C, 1, c.npix, self.src.C, _lib.stream_ptr())
-            c.xsave[key] = t
-        return t.data_ptr(), self.src.C
+        return c.sptr(self.src) if c.act == 2 else c.vptr(self.src)
 
     def fwd(self, c):
         wf, _ = _PACK.get(self.conv.weight, c.mode, False)
-        if c.need_grad:
-            self._wgrad_input(c)
         ip, ild = c.vptr(self.src)
         op, old = c.vptr(self.out)
         rp, rld = c.vptr(self.residual) if self.residual is not None else (0, 0)
         self._conv(c, ip, ild, wf.data_ptr(), _ptr(self.conv.bias), rp, rld, op, old, self.Cin, self.Cout,
                    1 if self.relu else 0)
+        c.shadow_fill(self.out)
 
     def bwd(self, c):
         st = _lib.stream_ptr()
@@ -380,7 +392,8 @@ class BNReLUOp(Op):
             _lib.call("tsr_bn_eval_coeffs", C, bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
                       bn.running_var.data_ptr(), bn.eps, sc, sh, mu, iv, st)
         op, old = c.vptr(self.out)
-        _lib.call("tsr_bn_apply", yp, yld, c.act, sc, sh, op, old, c.act, c.npix, C, 1 if self.relu else 0, st)
+        o2, o2ld = c.sptr(self.out) if c.wants_shadow(self.out.buf) else (0, 0)
+        _lib.call("tsr_bn_apply", yp, yld, c.act, sc, sh, op, old, c.act, c.npix, C, 1 if self.relu else 0, o2, o2ld, st)
         c.saved[self] = (coef, use_batch)
 
     def bwd(self, c):
@@ -453,6 +466,7 @@ class InputOp(Op):
         t = c.alloc(self.out)
         _lib.call("tsr_nchw_to_nhwc", x.data_ptr(), t.data_ptr(), self.out.C, c.act, c.B, self.out.C, c.H * c.W,
                   _lib.stream_ptr())
+        c.shadow_fill(View.of(self.out))
 
     def bwd(self, c):
         pass
@@ -502,6 +516,7 @@ def run_forward(prog: Program, x: torch.Tensor, training: bool, need_grad: bool,
         H, W = x.shape[-2], x.shape[-1]
     c = RunCtx(mode, B, H, W, x.device, training, need_grad)
     c.x = x
+    c.conv_inputs = {op.src.buf for op in prog.ops if isinstance(op, ConvOp)}
     keep = need_grad or keep_taps
     last_use: Dict[Buf, int] = {}
     if not keep:
