@@ -130,8 +130,10 @@ int tsr_sgemm_strided(const float* A, long long sam, long long sak, const float*
 /* nn.Linear (+ReLU / Softplus) of MLP_layer (model/tPSFNet.py:26-36) and its backward. */
 int tsr_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int N, int K, int act,
                    tsr_stream_t stream);
+size_t tsr_linear_bwd_workspace(int M, int N, int K);
 int tsr_linear_bwd(const float* dy, const float* out, const float* x, const float* w, float* dpre, float* dw, float* db,
-                   float* dx, int M, int N, int K, int act, int accumulate, tsr_stream_t stream);
+                   float* dx, int M, int N, int K, int act, int accumulate, void* workspace, size_t ws_bytes,
+                   tsr_stream_t stream);
 /* The per-sample loop of tPSFNet.forward (model/tPSFNet.py:118-125): tactilePSF :78-83, depth2tactile :85-100 (dense
  * 99x99 correlation + second-max fill) and degradation_process :129-141, fused, one CTA per sample.
  * alphaBeta (B,3), depth (B,100,100) -> HR (B,100,100), LRd (B,16), psf (B,99,99; may be NULL). */

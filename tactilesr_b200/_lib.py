@@ -54,7 +54,8 @@ SIGNATURES = {
     # tPSFNet
     "tsr_sgemm_strided": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _I, _I, _I, _P, _I, _I, _P]),
     "tsr_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "tsr_linear_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "tsr_linear_bwd_workspace": (_Z, [_I, _I, _I]),
+    "tsr_linear_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "tsr_psf_forward": (_I, [_P, _P, _P, _P, _P, _I, _P]),
     "tsr_psf_forward_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
     "tsr_psf_backward_tc": (_I, [_P, _P, _P, _P, _P, _I, _P]),

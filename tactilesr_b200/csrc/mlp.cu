@@ -8,66 +8,104 @@ namespace {
 
 // C[m][n] = epilogue( sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] )
 // epilogue: + bias[n]; act 0 none / 1 relu / 2 softplus(beta=1, threshold=20); accumulate adds to C.
+// 128 x 64 x 16 tiles, 256 threads, 8 x 4 outputs per thread; operands are staged k-major in shared memory so that the
+// inner loop is three 16-byte shared loads per 32 FMAs.  gridDim.z > 1 splits K into contiguous ranges whose partial
+// products go to C + z * split_stride (no epilogue); sgemm_split_reduce_kernel sums them in a fixed order.
+constexpr int TM = 128, TN = 64, TK = 16;
+
 __global__ void __launch_bounds__(256)
 sgemm_strided_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ Bm,
                      long long sbk, long long sbn, float* __restrict__ C, long long ldc, int M, int N, int K,
-                     const float* __restrict__ bias, int act, int accumulate) {
-  __shared__ float As[16][64 + 1];
-  __shared__ float Bs[16][64 + 1];
+                     const float* __restrict__ bias, int act, int accumulate, int k_per_split, long long split_stride) {
+  __shared__ __align__(16) float As[TK][TM + 4];
+  __shared__ __align__(16) float Bs[TK][TN + 4];
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  float acc[4][4];
+  const int tx = tid & 15, ty = tid >> 4;          // thread tile: rows ty*8.., columns tx*4..
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
+  float acc[8][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  for (int k0 = kbeg; k0 < kend; k0 += TK) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int idx = tid + r * 256;          // 1024 elements per operand tile
-      // choose the fastest-varying tile index to follow the operand's unit stride
+    for (int r = 0; r < TM * TK / 256; ++r) {
+      const int idx = tid + r * 256;
+      // the fastest-varying tile index follows the operand's unit stride
       int ka, ma;
-      if (sak == 1) { ka = idx & 15; ma = idx >> 4; } else { ma = idx & 63; ka = idx >> 6; }
-      int gm = m0 + ma, gk = k0 + ka;
-      As[ka][ma] = (gm < M && gk < K) ? A[gm * sam + gk * sak] : 0.f;
+      if (sak == 1) { ka = idx & (TK - 1); ma = idx / TK; } else { ma = idx & (TM - 1); ka = idx / TM; }
+      const int gm = m0 + ma, gk = k0 + ka;
+      As[ka][ma] = (gm < M && gk < kend) ? A[gm * sam + gk * sak] : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < TN * TK / 256; ++r) {
+      const int idx = tid + r * 256;
       int kb, nb;
-      if (sbk == 1) { kb = idx & 15; nb = idx >> 4; } else { nb = idx & 63; kb = idx >> 6; }
-      int gn = n0 + nb;
-      gk = k0 + kb;
-      Bs[kb][nb] = (gn < N && gk < K) ? Bm[gk * sbk + gn * sbn] : 0.f;
+      if (sbk == 1) { kb = idx & (TK - 1); nb = idx / TK; } else { nb = idx & (TN - 1); kb = idx / TN; }
+      const int gn = n0 + nb, gk = k0 + kb;
+      Bs[kb][nb] = (gn < N && gk < kend) ? Bm[gk * sbk + gn * sbn] : 0.f;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      float a[4], b[4];
+    for (int k = 0; k < TK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
     __syncthreads();
   }
+  float* Cz = C + (long long)blockIdx.z * split_stride;
+  const bool partial = gridDim.z > 1;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int m = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
     if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int n = n0 + tx * 4 + j;
+      const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       float v = acc[i][j];
+      float* c = Cz + m * ldc + n;
+      if (partial) { *c = v; continue; }
       if (bias) v += bias[n];
       if (act == 1) v = fmaxf(v, 0.f);
       else if (act == 2) v = v > 20.f ? v : log1pf(expf(v));
-      float* c = C + m * ldc + n;
       *c = accumulate ? *c + v : v;
     }
   }
+}
+
+// C[i] (+)= sum_z partial[z][i], fixed order
+__global__ void sgemm_split_reduce_kernel(const float* __restrict__ partial, int S, long long n, float* __restrict__ C,
+                                          int accumulate) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < S; ++z) s += partial[(long long)z * n + i];
+    C[i] = accumulate ? C[i] + s : s;
+  }
+}
+
+// deterministic column sums of an [M][N] matrix: one block per column, fixed-order tree
+__global__ void __launch_bounds__(256)
+colsum_block_kernel(const float* __restrict__ x, int M, int N, float* __restrict__ out, int accumulate) {
+  __shared__ float sh[256];
+  const int n = blockIdx.x;
+  float s = 0.f;
+  for (int m = threadIdx.x; m < M; m += 256) s += x[(long long)m * N + n];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = accumulate ? out[n] + sh[0] : sh[0];
 }
 
 // dpre = dY * act'(pre), expressed through the stored output: relu: [out > 0]; softplus: 1 - exp(-out)
@@ -81,15 +119,6 @@ __global__ void act_backward_kernel(const float* __restrict__ dy, const float* _
   }
 }
 
-// deterministic column sum of a small [M][N] matrix: one thread per column
-__global__ void colsum_small_kernel(const float* __restrict__ x, int M, int N, float* __restrict__ out, int accumulate) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float s = 0.f;
-  for (int m = 0; m < M; ++m) s += x[(long long)m * N + n];
-  out[n] = accumulate ? out[n] + s : s;
-}
-
 }  // namespace
 
 extern "C" {
@@ -98,8 +127,8 @@ int tsr_sgemm_strided(const float* A, long long sam, long long sak, const float*
                       float* C, long long ldc, int M, int N, int K, const float* bias, int act, int accumulate,
                       cudaStream_t stream) {
   TSR_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "sgemm_strided: bad argument");
-  dim3 grid(tsr_cdiv(N, 64), tsr_cdiv(M, 64));
-  sgemm_strided_kernel<<<grid, 256, 0, stream>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act, accumulate);
+  dim3 grid(tsr_cdiv(N, TN), tsr_cdiv(M, TM));
+  sgemm_strided_kernel<<<grid, 256, 0, stream>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, act, accumulate, K, 0);
   TSR_CHECK_LAUNCH("sgemm_strided");
   return TSR_OK;
 }
@@ -110,9 +139,26 @@ int tsr_linear_fwd(const float* x, const float* w, const float* b, float* y, int
   return tsr_sgemm_strided(x, K, 1, w, 1, K, y, N, M, N, K, b, act, 0, stream);
 }
 
-// given dy and the stored output `out` of the layer: dpre (scratch [M][N]), dW[N][K] (+)=, db[N] (+)=, dx[M][K] (optional)
+// splits of the batch dimension for the weight gradient: enough CTAs to fill the GPU, at least 256 rows each
+static int linear_wgrad_splits(int M, int N, int K) {
+  int tiles = tsr_cdiv(K, TN) * tsr_cdiv(N, TM);
+  int s = (2 * 148 + tiles - 1) / tiles;
+  int maxs = M / 256;
+  if (s > maxs) s = maxs;
+  if (s > 64) s = 64;
+  return s < 1 ? 1 : s;
+}
+
+size_t tsr_linear_bwd_workspace(int M, int N, int K) {
+  int s = linear_wgrad_splits(M, N, K);
+  return s > 1 ? (size_t)s * N * K * sizeof(float) : 0;
+}
+
+// given dy and the stored output `out` of the layer: dpre (scratch [M][N]), dW[N][K] (+)=, db[N] (+)=, dx[M][K] (optional).
+// workspace: tsr_linear_bwd_workspace(M, N, K) bytes (split-batch partial weight gradients, summed in a fixed order).
 int tsr_linear_bwd(const float* dy, const float* out, const float* x, const float* w, float* dpre, float* dw,
-                   float* db, float* dx, int M, int N, int K, int act, int accumulate, cudaStream_t stream) {
+                   float* db, float* dx, int M, int N, int K, int act, int accumulate, void* workspace, size_t ws_bytes,
+                   cudaStream_t stream) {
   TSR_REQUIRE(dy && out && x && w && dpre && dw && db, "linear_bwd: null pointer");
   long long n = (long long)M * N;
   int grid = (int)((n + 255) / 256);
@@ -120,13 +166,26 @@ int tsr_linear_bwd(const float* dy, const float* out, const float* x, const floa
   act_backward_kernel<<<grid, 256, 0, stream>>>(dy, out, dpre, n, act);
   TSR_CHECK_LAUNCH("act_backward");
   // dW[n][k] = sum_m dpre[m][n] x[m][k]:  A(n, m) = dpre[m*N + n], B(m, k) = x[m*K + k]
-  int rc = tsr_sgemm_strided(dpre, 1, N, x, K, 1, dw, K, N, K, M, nullptr, 0, accumulate, stream);
-  if (rc) return rc;
-  colsum_small_kernel<<<tsr_cdiv(N, 128), 128, 0, stream>>>(dpre, M, N, db, accumulate);
-  TSR_CHECK_LAUNCH("colsum_small");
+  const int S = linear_wgrad_splits(M, N, K);
+  if (S > 1) {
+    TSR_REQUIRE(workspace && ws_bytes >= (size_t)S * N * K * sizeof(float), "linear_bwd: workspace too small");
+    const int kps = tsr_cdiv(tsr_cdiv(M, S), TK) * TK;
+    dim3 g3(tsr_cdiv(K, TN), tsr_cdiv(N, TM), tsr_cdiv(M, kps));
+    sgemm_strided_kernel<<<g3, 256, 0, stream>>>(dpre, 1, N, x, K, 1, (float*)workspace, K, N, K, M, nullptr, 0, 0, kps,
+                                                 (long long)N * K);
+    TSR_CHECK_LAUNCH("linear_wgrad_split");
+    long long nk = (long long)N * K;
+    sgemm_split_reduce_kernel<<<(int)((nk + 255) / 256), 256, 0, stream>>>((const float*)workspace, (int)g3.z, nk, dw, accumulate);
+    TSR_CHECK_LAUNCH("linear_wgrad_reduce");
+  } else {
+    int rc = tsr_sgemm_strided(dpre, 1, N, x, K, 1, dw, K, N, K, M, nullptr, 0, accumulate, stream);
+    if (rc) return rc;
+  }
+  colsum_block_kernel<<<N, 256, 0, stream>>>(dpre, M, N, db, accumulate);
+  TSR_CHECK_LAUNCH("colsum_block");
   if (dx) {
     // dx[m][k] = sum_n dpre[m][n] w[n][k]
-    rc = tsr_sgemm_strided(dpre, N, 1, w, K, 1, dx, K, M, K, N, nullptr, 0, 0, stream);
+    int rc = tsr_sgemm_strided(dpre, N, 1, w, K, 1, dx, K, M, K, N, nullptr, 0, 0, stream);
     if (rc) return rc;
   }
   return TSR_OK;

@@ -89,9 +89,11 @@ class _PSFFn(torch.autograd.Function):
             dw = torch.empty_like(w)
             db = torch.empty((N,), dtype=torch.float32, device=dev)
             dx = torch.empty((B, K), dtype=torch.float32, device=dev) if i > 0 else None
+            nws = int(_lib.lib().tsr_linear_bwd_workspace(B, N, K))
+            wsp = torch.empty((max(nws, 16),), dtype=torch.uint8, device=dev)
             _lib.call("tsr_linear_bwd", dy.data_ptr(), acts[i + 1].data_ptr(), acts[i].data_ptr(), w.data_ptr(),
                       dpre.data_ptr(), dw.data_ptr(), db.data_ptr(), 0 if dx is None else dx.data_ptr(), B, N, K,
-                      _ACT["softplus"] if i == 3 else _ACT["relu"], 0, st)
+                      _ACT["softplus"] if i == 3 else _ACT["relu"], 0, wsp.data_ptr(), wsp.numel(), st)
             grads = [dw, db] + grads
             dy = dx
         return (None, None, *grads)
