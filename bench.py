@@ -202,6 +202,22 @@ def measure_extras(dev, model, B):
     out["sr_infer_samples_per_s"] = Bi / (ms * 1e-3)
     out["sr_infer_batch"] = Bi
     out["sr_infer_tensor_frac_of_sustained_peak"] = Bi / (ms * 1e-3) * FLOP_PER_SAMPLE_FWD / 1e12 / peaks()["tf_sust"]
+    # TactileSRCNN (reference model/tactileSR_model.py:101-153; same kernels, different wiring): train step at the same batch
+    from tactilesr_b200.functional import mse_hr_loss
+    from tactilesr_b200.model import TactileSRCNN
+    cnn = TactileSRCNN().to(dev).train()
+    copt = FusedAdam(cnn.parameters(), lr=1e-3, weight_decay=1e-2)
+    LRc = torch.rand(B, 3, 4, 4, device=dev) * 8
+    HRc = torch.rand(B, 1, 100, 100, device=dev) * 250
+
+    def cstep():
+        loss = mse_hr_loss(cnn(LRc), HRc, 10.0)
+        copt.zero_grad()
+        loss.backward()
+        copt.step()
+    ms = timeit(cstep, 5)
+    out["tactilesrcnn_train_samples_per_s"] = B / (ms * 1e-3)
+    del cnn, copt
     # C2: tPSFNet train step: fwd + MSE(LR[:,2:3], LR_degrade) + bwd + Adam(1e-4, wd 1e-5); B = 256 is the reference
     # batch (config/default.py:18) -- 30 MB of traffic, launch-latency bound -- and B = 8192 shows the kernels
     g = torch.Generator().manual_seed(3)

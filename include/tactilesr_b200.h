@@ -117,6 +117,12 @@ size_t tsr_mse_hr_workspace(void);
  * dout = 2 (out - HR) / N * grad_mul (dout may be NULL). */
 int tsr_mse_hr_loss(const float* out, const float* hr_raw, float scale_num, int B, int H, int W, int Hin, int Win,
                     float* loss, float* dout, float grad_mul, void* workspace, size_t ws_bytes, tsr_stream_t stream);
+/* eval_func (train/tactileSR_train.py:76-94) per-sample metrics with the label preparation fused: sum of squared errors,
+ * calculationPSNR and calculationSSIM (utility/tools.py:49-81; psnr_div = the reference's shape[0] * shape[1] of the
+ * (1,H,W) slice = H).  out (B,1,H,W), hr_raw (B,1,Hin,Win) -> sqerr / psnr / ssim (B each). */
+int tsr_eval_metrics(const float* out, const float* hr_raw, float scale_num, int B, int H, int W, int Hin, int Win,
+                     float max_value, float psnr_div, float c1, float c2, float* sqerr, float* psnr, float* ssim,
+                     tsr_stream_t stream);
 /* torch.optim.Adam step (coupled L2 weight decay, no amsgrad; train/tactileSR_train.py:212, tPSFNet_train.py:201)
  * over a flat fp32 buffer of n elements; `step` is the 1-based step count, lr a host scalar read every call. */
 int tsr_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

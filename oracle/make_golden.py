@@ -208,9 +208,29 @@ def golden_tpsf():
     np.savez_compressed(os.path.join(OUT, "tpsf_fwdbwd.npz"), **rec)
 
 
+def golden_eval():
+    """eval_func's loop body (train/tactileSR_train.py:76-94) with the reference's own calculationPSNR / calculationSSIM."""
+    from utility.tools import calculationPSNR, calculationSSIM
+    B = 5
+    rec = {"B": B, "seed_x": 601}
+    g = torch.Generator().manual_seed(rec["seed_x"])
+    out = torch.relu(torch.randn(B, 1, 40, 40, generator=g) * 5 + 6)
+    HR_raw = torch.rand(B, 1, 100, 100, generator=g) * 250
+    for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        o, HR = out.to(dtype), HR_raw.to(dtype) / 10
+        HR = F.interpolate(HR, size=(40, 40), mode="bilinear", align_corners=False)
+        rec[f"{tag}/mse"] = nn.MSELoss()(o, HR).double().numpy()
+        rec[f"{tag}/psnr"] = np.array([float(calculationPSNR(o[i], HR[i], maxValue=250)) for i in range(B)])
+        rec[f"{tag}/ssim"] = np.array([float(calculationSSIM(o[i], HR[i])) for i in range(B)])
+    np.savez_compressed(os.path.join(OUT, "eval_metrics.npz"), **rec)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--eval-only" in sys.argv:
+        golden_eval()
+        sys.exit(0)
     golden_sr_init()
     print("init done")
     golden_tpsf()
@@ -221,5 +241,6 @@ if __name__ == "__main__":
     print("fwdbwd done")
     golden_sr_adam()
     print("adam done")
+    golden_eval()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

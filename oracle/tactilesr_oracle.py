@@ -313,3 +313,29 @@ def train_steps(sd, batches, lr: float = 1e-3, wd: float = 1e-2, HR_scale_num: f
             sd[k], m[k], v[k] = adam_step(sd[k], g[k], m[k], v[k], t, lr, wd)
         sd.update(new_stats)
     return losses, sd
+
+
+# --------------------------------------------------------------------------------------
+# evaluation metrics (reference utility/tools.py:49-81, train/tactileSR_train.py:76-94)
+# --------------------------------------------------------------------------------------
+def psnr(p1: Tensor, p2: Tensor, max_value: float) -> Tensor:
+    """calculationPSNR (utility/tools.py:49-62): note the divisor is shape[0] * shape[1] of whatever is passed in --
+    eval_func passes (1, H, W) slices, so it is H."""
+    mse = ((p1 - p2) ** 2).sum() / (p1.shape[0] * p1.shape[1])
+    return 10 * torch.log10(max_value ** 2 / mse)
+
+
+def ssim(p1: Tensor, p2: Tensor, C1: float = 0.01 ** 2, C2: float = 0.03 ** 2) -> Tensor:
+    """calculationSSIM (utility/tools.py:65-81): whole-image means / variances, no window."""
+    mu1, mu2 = p1.mean(), p2.mean()
+    s1, s2, s12 = (p1 * p1).mean() - mu1 * mu1, (p2 * p2).mean() - mu2 * mu2, (p1 * p2).mean() - mu1 * mu2
+    return ((2 * mu1 * mu2 + C1) * (2 * s12 + C2)) / ((mu1 * mu1 + mu2 * mu2 + C1) * (s1 + s2 + C2))
+
+
+def eval_batch(out: Tensor, HR_raw: Tensor, HR_scale_num: float = 10.0, max_value: float = 250.0):
+    """One iteration of eval_func's loop body (train/tactileSR_train.py:76-94): (mse, per-sample psnr, per-sample ssim)."""
+    HR = prep_hr(HR_raw, HR_scale_num, out.shape[-1])
+    mse = ((out - HR) ** 2).mean()
+    ps = torch.stack([psnr(out[i], HR[i], max_value) for i in range(out.shape[0])])
+    ss = torch.stack([ssim(out[i], HR[i]) for i in range(out.shape[0])])
+    return mse, ps, ss

@@ -326,6 +326,64 @@ __global__ void mse_hr_kernel(const float* __restrict__ out, const float* __rest
     if (threadIdx.x == 0) partial[blockIdx.x] = v;
   }
 }
+// ------------------------------------------------------------------------------------------
+// evaluation metrics of eval_func (reference train/tactileSR_train.py:76-94, utility/tools.py:49-81), one block per
+// sample, HR label preparation (HR / scale_num, bilinear resize) fused as in mse_hr_kernel:
+//   sqerr = sum (out - HR)^2;   PSNR = 10 log10(max^2 / (sqerr / psnr_div));
+//   SSIM  = ((2 mu1 mu2 + C1)(2 s12 + C2)) / ((mu1^2 + mu2^2 + C1)(s1 + s2 + C2))  with whole-image statistics
+// (psnr_div is the reference's `pattern.shape[0] * pattern.shape[1]` of the (1, H, W) slice it passes, i.e. H, not H*W)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+eval_metrics_kernel(const float* __restrict__ out, const float* __restrict__ hr_raw, float inv_scale_num, int H, int W,
+                    int Hin, int Win, float max_value, float psnr_div, float c1, float c2, float* __restrict__ sqerr,
+                    float* __restrict__ psnr, float* __restrict__ ssim) {
+  const int b = blockIdx.x;
+  const int npx = H * W;
+  const float sy = (float)Hin / (float)H, sx = (float)Win / (float)W;
+  const float* o = out + (long long)b * npx;
+  const float* src = hr_raw + (long long)b * Hin * Win;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // d^2, o, h, o^2, h^2, o h
+  for (int i = threadIdx.x; i < npx; i += blockDim.x) {
+    const int x = i % W, y = i / W;
+    float hr;
+    if (Hin == H && Win == W) {
+      hr = src[i] * inv_scale_num;
+    } else {
+      int y0, y1, x0, x1;
+      float ly, lx;
+      bilinear_src(y, sy, Hin, y0, y1, ly);
+      bilinear_src(x, sx, Win, x0, x1, lx);
+      const float v00 = src[y0 * Win + x0] * inv_scale_num, v01 = src[y0 * Win + x1] * inv_scale_num;
+      const float v10 = src[y1 * Win + x0] * inv_scale_num, v11 = src[y1 * Win + x1] * inv_scale_num;
+      hr = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+    }
+    const float ov = o[i], d = ov - hr;
+    acc[0] = fmaf(d, d, acc[0]); acc[1] += ov; acc[2] += hr;
+    acc[3] = fmaf(ov, ov, acc[3]); acc[4] = fmaf(hr, hr, acc[4]); acc[5] = fmaf(ov, hr, acc[5]);
+  }
+  __shared__ float red[6][8];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float v = warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[6];
+    for (int k = 0; k < 6; ++k) {
+      double a = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += (double)red[k][w];
+      t[k] = a;
+    }
+    const double n = (double)npx;
+    sqerr[b] = (float)t[0];
+    psnr[b] = (float)(10.0 * log10((double)max_value * (double)max_value / (t[0] / (double)psnr_div)));
+    const double mu1 = t[1] / n, mu2 = t[2] / n;
+    const double s1 = t[3] / n - mu1 * mu1, s2 = t[4] / n - mu2 * mu2, s12 = t[5] / n - mu1 * mu2;
+    ssim[b] = (float)(((2.0 * mu1 * mu2 + c1) * (2.0 * s12 + c2)) / ((mu1 * mu1 + mu2 * mu2 + c1) * (s1 + s2 + c2)));
+  }
+}
+
 __global__ void sum_final_kernel(const float* __restrict__ partial, int n, double mul, float* __restrict__ out) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     double s = 0.0;
@@ -802,6 +860,17 @@ int tsr_mse_hr_loss(const float* out, const float* hr_raw, float scale_num, int 
   TSR_CHECK_LAUNCH("mse_hr");
   sum_final_kernel<<<1, 32, 0, stream>>>((const float*)workspace, grid, 1.0 / (double)N, loss);
   TSR_CHECK_LAUNCH("sum_final");
+  return TSR_OK;
+}
+
+// per-sample evaluation metrics (eval_func): out (B,1,H,W) fp32, hr_raw (B,1,Hin,Win) fp32 -> sqerr[B], psnr[B], ssim[B]
+int tsr_eval_metrics(const float* out, const float* hr_raw, float scale_num, int B, int H, int W, int Hin, int Win,
+                     float max_value, float psnr_div, float c1, float c2, float* sqerr, float* psnr, float* ssim,
+                     cudaStream_t stream) {
+  TSR_REQUIRE(out && hr_raw && sqerr && psnr && ssim && B > 0, "eval_metrics: bad argument");
+  eval_metrics_kernel<<<B, 256, 0, stream>>>(out, hr_raw, 1.0f / scale_num, H, W, Hin, Win, max_value, psnr_div, c1, c2,
+                                             sqerr, psnr, ssim);
+  TSR_CHECK_LAUNCH("eval_metrics");
   return TSR_OK;
 }
 

@@ -6,7 +6,7 @@ from __future__ import annotations
 import torch
 
 from ..cpu.trainer import Trainer
-from ..functional import mse_hr_loss
+from ..functional import eval_metrics, mse_hr_loss
 from ..model.tactileSR_model import TactileSR
 from ..optim import FusedAdam
 
@@ -40,3 +40,25 @@ def build_model_and_optimizer(config, device):
                       forceFeatureExtraLayerCnt=config["forceFeatureExtraLayerCnt"]).to(device)
     optimizer = FusedAdam(model.parameters(), lr=config["lr"], weight_decay=config["weight_decay"])
     return model, optimizer
+
+
+def eval_func(model, test_loader, config, device=None):
+    """reference eval_func (train/tactileSR_train.py:64-101) without its per-sample python loop and per-batch host
+    syncs: label preparation, MSE, PSNR and SSIM of a batch are one kernel; the three running sums stay on the device
+    and are read back once.  Returns (loss, ssim, psnr) averaged over the batches exactly as the reference logs them.
+    Like the reference it runs the model in eval mode (and, unlike it, under ``torch.no_grad()``)."""
+    device = device if device is not None else next(model.parameters()).device
+    seqsCnt, axisCnt = config["seqsCnt"], config["axisCnt"]
+    acc = torch.zeros(3, dtype=torch.float64, device=device)
+    n = 0
+    model.eval()
+    with torch.no_grad():
+        for LR, HR in test_loader:
+            LR = LR.to(device, non_blocking=True).float()[:, :seqsCnt * axisCnt]
+            HR = HR.to(device, non_blocking=True).float()
+            out = model(LR)
+            mse, psnr, ssim = eval_metrics(out, HR, config["HR_scale_num"], config["sensorMaxVaule_factor"])
+            acc += torch.stack([mse.double(), ssim.double().mean(), psnr.double().mean()])
+            n += 1
+    loss, ssim, psnr = (acc / max(n, 1)).tolist()
+    return loss, ssim, psnr

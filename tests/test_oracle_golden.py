@@ -104,3 +104,18 @@ def test_tpsf_tables_match_reference():
     g = load_golden("tpsf_fwdbwd.npz")
     np.testing.assert_allclose(summarize(po.psf_sdf()), g["PSF_sdf_summary"], rtol=1e-6)
     np.testing.assert_allclose(summarize(po.masking_sdf()), g["LR_masking_sdf_summary"], rtol=1e-6)
+
+
+def test_eval_metrics_oracle_matches_reference():
+    """oracle.psnr / ssim / eval_batch vs the reference's calculationPSNR / calculationSSIM run on eval_func's slices."""
+    import torch
+    from oracle import tactilesr_oracle as so
+    g = load_golden("eval_metrics.npz")
+    gen = torch.Generator().manual_seed(int(g["seed_x"]))
+    B = int(g["B"])
+    out = torch.relu(torch.randn(B, 1, 40, 40, generator=gen) * 5 + 6)
+    HR_raw = torch.rand(B, 1, 100, 100, generator=gen) * 250
+    mse, ps, ss = so.eval_batch(out.double(), HR_raw.double(), 10.0, 250.0)
+    assert abs(mse.item() - float(g["f64/mse"])) / float(g["f64/mse"]) < 1e-12
+    assert np.abs(ps.numpy() - g["f64/psnr"]).max() < 1e-10
+    assert np.abs(ss.numpy() - g["f64/ssim"]).max() < 1e-12
