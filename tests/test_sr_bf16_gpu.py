@@ -211,3 +211,42 @@ def test_sr_fp16_train_step_within_1e_2(S):
         assert e_eval < 1e-2, e_eval
     finally:
         tb.set_precision("fp32")
+
+
+@pytest.mark.parametrize("mode", ["fp16", "bf16"])
+def test_large_batch_properties(mode):
+    """Size-independent properties at a BASELINE-sized inference batch (C3, B = 4096): eval-mode outputs do not depend
+    on how the batch is split (samples are independent once BN uses running statistics), repeated calls are
+    bit-identical, outputs are finite and non-negative (final ReLU); and a training step is bit-deterministic."""
+    import tactilesr_b200 as tb
+    from tactilesr_b200.functional import mse_hr_loss
+    from tactilesr_b200.model import TactileSR
+    tb.set_precision(mode)
+    try:
+        torch.manual_seed(0)
+        m = TactileSR().cuda().train()
+        LR, HR_raw = sr_inputs(64, 1, 77)
+        with torch.no_grad():
+            m(LR.cuda())                       # non-trivial running statistics
+        m.eval()
+        B = 4096
+        x = (torch.rand(B, 3, 4, 4, generator=torch.Generator().manual_seed(78)) * 8).cuda()
+        with torch.no_grad():
+            full = m(x)
+            again = m(x)
+            parts = torch.cat([m(x[:1000]), m(x[1000:1001]), m(x[1001:])])
+        assert full.shape == (B, 1, 40, 40) and torch.isfinite(full).all() and (full >= 0).all()
+        assert torch.equal(full, again)
+        assert torch.equal(full, parts)
+        # training-step determinism (two-level fixed-order reductions everywhere)
+        losses, grads = [], []
+        for _ in range(2):
+            torch.manual_seed(1)
+            mt = TactileSR().cuda().train()
+            loss = mse_hr_loss(mt(LR.cuda()), HR_raw.cuda(), 10.0)
+            loss.backward()
+            losses.append(loss.detach().clone())
+            grads.append(mt.patternFeatureExtra_layer[0].conv_5_2[0].weight.grad.clone())
+        assert torch.equal(losses[0], losses[1]) and torch.equal(grads[0], grads[1])
+    finally:
+        tb.set_precision("fp32")
