@@ -357,7 +357,7 @@ def run_ours(args):
         tf, kms, kflops = time_dominant_kernel(B, f16=args.precision == "fp16")
         # DRAM traffic per launch from the committed ncu --set full capture of this kernel at B = 512
         # (profiles/r01_conv_tc_pair_5x5_128_b512.txt: dram read 210.6 MB + write 160.8 MB; algorithmic in+out 419 MB)
-        traffic = 371.39e6 if B == 512 else None
+        traffic = {512: 371.39e6}.get(B)     # measured per batch size; None if this B was never captured
         roof = {"bound": "tensor", "kernel": "conv_tc_pair_kernel<128> (cta_group::2) 5x5 128->128, MSRB conv_5_2 forward shape",
                 "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": tf / pk["tf_burst"],
                 "peak_source": pk["src"] + " bf16 burst (kernel timed alone)", "ms_per_launch": kms, "flops_per_launch": kflops,
@@ -401,7 +401,7 @@ def main():
     # default = the tensor-core mode that meets north_star's <= 1e-2 bound on the SR output (fp16 activations, fp32
     # accumulation, bf16 gradients); "bf16" is ~5 % faster and 8x less accurate, "fp32" is the <= 1e-5 parity mode
     ap.add_argument("--precision", default=os.environ.get("TSR_BENCH_PRECISION", "fp16"), choices=["fp32", "bf16", "fp16"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("TSR_BENCH_BATCH", "512")))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("TSR_BENCH_BATCH", "1024")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
