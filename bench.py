@@ -355,9 +355,10 @@ def run_ours(args):
     roof = None
     if args.precision in ("bf16", "fp16"):
         tf, kms, kflops = time_dominant_kernel(B, f16=args.precision == "fp16")
-        # DRAM traffic per launch from the committed ncu --set full capture of this kernel at B = 512
-        # (profiles/r01_conv_tc_pair_5x5_128_b512.txt: dram read 210.6 MB + write 160.8 MB; algorithmic in+out 419 MB)
-        traffic = {512: 371.39e6}.get(B)     # measured per batch size; None if this B was never captured
+        # DRAM traffic per launch from the committed ncu --set full captures of this kernel
+        # (profiles/r01_conv_tc_pair_5x5_128_b512.txt: read 210.6 MB + write 160.8 MB, algorithmic in+out 419 MB;
+        #  profiles/r01_conv_tc_pair_5x5_128_b1024.txt: read 420.4 MB + write 370.0 MB, algorithmic 840 MB)
+        traffic = {512: 371.39e6, 1024: 790.39e6}.get(B)     # None if this batch size was never captured
         roof = {"bound": "tensor", "kernel": "conv_tc_pair_kernel<128> (cta_group::2) 5x5 128->128, MSRB conv_5_2 forward shape",
                 "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": tf / pk["tf_burst"],
                 "peak_source": pk["src"] + " bf16 burst (kernel timed alone)", "ms_per_launch": kms, "flops_per_launch": kflops,
