@@ -19,11 +19,60 @@ def _distance_table(h: int, w: int, cy: float, cx: float) -> torch.Tensor:
     return torch.sqrt(r * r + c * c).to(torch.float32)
 
 
+def _linear_fwd(x, w, b, act, st):
+    """y = act(x W^T + b).  Layers whose shape fits the fp32 implicit-GEMM convolution kernels (K % 16 == 0,
+    N % 64 == 0: 48->256, 256->1024, 1024->256) run as 1x1 convolutions over M = batch "pixels" (register-prefetching
+    128x64 FFMA tiles, csrc/conv_f32.cu); the 256->3 softplus head uses the small strided SGEMM (csrc/mlp.cu)."""
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    if act != "softplus" and K % 16 == 0 and N % 64 == 0:
+        wT = torch.empty((K * N,), dtype=torch.float32, device=x.device)        # [ci][co] = W^T
+        _lib.call("tsr_pack_conv_weight_f32", w.data_ptr(), wT.data_ptr(), 0, N, K, 1, st)
+        _lib.call("tsr_conv2d_f32", x.data_ptr(), K, wT.data_ptr(), b.data_ptr(), 0, 0, y.data_ptr(), N, M, 1, 1, K, N, 1,
+                  1 if act == "relu" else 0, st)
+    else:
+        _lib.call("tsr_linear_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), M, N, K, _ACT[act], st)
+    return y
+
+
+def _linear_bwd(dy, out, x, w, act, need_dx, st):
+    """(dW, db, dx) of y = act(x W^T + b) given dy and the stored output; same kernel choice as _linear_fwd."""
+    M, K = x.shape
+    N = w.shape[0]
+    dev = x.device
+    L = _lib.lib()
+    dw = torch.empty_like(w)
+    db = torch.empty((N,), dtype=torch.float32, device=dev)
+    dx = torch.empty((M, K), dtype=torch.float32, device=dev) if need_dx else None
+    if act == "relu" and K % 64 == 0 and N % 64 == 0:
+        dpre = torch.empty((M, N), dtype=torch.float32, device=dev)
+        _lib.call("tsr_relu_backward", dy.data_ptr(), N, out.data_ptr(), N, dpre.data_ptr(), N, 0, M, N, st)
+        nws = max(int(L.tsr_conv2d_wgrad_f32_workspace(M, 1, 1, K, N, 1)), int(L.tsr_colsum_workspace(M, N)), 256)
+        ws = torch.empty((nws,), dtype=torch.uint8, device=dev)
+        _lib.call("tsr_conv2d_wgrad_f32", x.data_ptr(), K, dpre.data_ptr(), N, dw.data_ptr(), ws.data_ptr(), nws, M, 1, 1, K, N,
+                  1, 0, st)
+        _lib.call("tsr_colsum", dpre.data_ptr(), N, 0, M, N, db.data_ptr(), ws.data_ptr(), nws, 0, st)
+        if need_dx:     # dx = dpre W: W [N][K] is already the [ci = N][co = K] image the kernel wants
+            _lib.call("tsr_conv2d_f32", dpre.data_ptr(), N, w.data_ptr(), 0, 0, 0, dx.data_ptr(), K, M, 1, 1, N, K, 1, 0, st)
+    else:
+        dpre = torch.empty((M, N), dtype=torch.float32, device=dev)
+        nws = int(L.tsr_linear_bwd_workspace(M, N, K))
+        wsp = torch.empty((max(nws, 16),), dtype=torch.uint8, device=dev)
+        _lib.call("tsr_linear_bwd", dy.data_ptr(), out.data_ptr(), x.data_ptr(), w.data_ptr(), dpre.data_ptr(),
+                  dw.data_ptr(), db.data_ptr(), 0 if dx is None else dx.data_ptr(), M, N, K, _ACT[act], 0,
+                  wsp.data_ptr(), wsp.numel(), st)
+    return dw, db, dx
+
+
 class _PSFFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, depth, w1, b1, w2, b2, w3, b3, w4, b4):
         if not x.is_cuda:
             raise _lib.TsrError("tactilesr_b200.tPSFNet runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+        # outputs that take no part in the loss must reach backward as None, not as materialised zero tensors: the
+        # training case (gradient through LR_degrade only) is what selects the tcgen05 backward
+        ctx.set_materialize_grads(False)
         st = _lib.stream_ptr()
         B = x.shape[0]
         x2 = x.detach().reshape(B, -1).contiguous().float()
@@ -33,10 +82,7 @@ class _PSFFn(torch.autograd.Function):
         bs = [b.detach().contiguous() for b in (b1, b2, b3, b4)]
         acts = [x2]
         for i, (w, b) in enumerate(zip(ws, bs)):
-            y = torch.empty((B, w.shape[0]), dtype=torch.float32, device=dev)
-            _lib.call("tsr_linear_fwd", acts[-1].data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), B, w.shape[0],
-                      w.shape[1], _ACT["softplus"] if i == 3 else _ACT["relu"], st)
-            acts.append(y)
+            acts.append(_linear_fwd(acts[-1], w, b, "softplus" if i == 3 else "relu", st))
         ab = acts[-1]
         HR = torch.empty((B, 1, 100, 100), dtype=torch.float32, device=dev)
         LRd = torch.empty((B, 1, 4, 4), dtype=torch.float32, device=dev)
@@ -69,6 +115,8 @@ class _PSFFn(torch.autograd.Function):
         def prep(g):
             return None if g is None else g.detach().contiguous().float()
         dHR, dLRd, dpsf, dab_direct = prep(dHR), prep(dLRd), prep(dpsf), prep(dab_direct)
+        if dHR is None and dLRd is None and dpsf is None and dab_direct is None:
+            return (None,) * 10
         dab = torch.empty((B, 3), dtype=torch.float32, device=dev)
         if ctx.has_aux and dHR is None and dpsf is None and dLRd is not None:
             # the training case (train/tPSFNet_train.py:186-189: only LR_degrade is supervised): tcgen05 backward
@@ -83,17 +131,7 @@ class _PSFFn(torch.autograd.Function):
         grads = []
         dy = dab
         for i in (3, 2, 1, 0):
-            w = ws[i]
-            N, K = w.shape
-            dpre = torch.empty((B, N), dtype=torch.float32, device=dev)
-            dw = torch.empty_like(w)
-            db = torch.empty((N,), dtype=torch.float32, device=dev)
-            dx = torch.empty((B, K), dtype=torch.float32, device=dev) if i > 0 else None
-            nws = int(_lib.lib().tsr_linear_bwd_workspace(B, N, K))
-            wsp = torch.empty((max(nws, 16),), dtype=torch.uint8, device=dev)
-            _lib.call("tsr_linear_bwd", dy.data_ptr(), acts[i + 1].data_ptr(), acts[i].data_ptr(), w.data_ptr(),
-                      dpre.data_ptr(), dw.data_ptr(), db.data_ptr(), 0 if dx is None else dx.data_ptr(), B, N, K,
-                      _ACT["softplus"] if i == 3 else _ACT["relu"], 0, wsp.data_ptr(), wsp.numel(), st)
+            dw, db, dx = _linear_bwd(dy, acts[i + 1], acts[i], ws[i], "softplus" if i == 3 else "relu", i > 0, st)
             grads = [dw, db] + grads
             dy = dx
         return (None, None, *grads)
