@@ -89,6 +89,10 @@ int tsr_bn_train_stats(const void* y, int y_ld, int y_bf16, long long npix, int 
                        float momentum, float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
                        void* workspace, size_t ws_bytes, tsr_stream_t stream);
 /* eval mode: scale / shift from the running statistics. */
+int tsr_bn_finalize_partials(const float* partial, int nrows, long long npix, int C, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                             float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
+                             tsr_stream_t stream);
 int tsr_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, float* scale, float* shift, float* save_mean,
                        float* save_invstd, tsr_stream_t stream);
@@ -175,7 +179,11 @@ size_t tsr_conv2d_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS);
    flags bit 1 (value 2): in / weights / residual / out are fp16 instead of bf16 (same kernels, kind::f16 format field). */
 int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* bias, const void* residual, int res_ld,
                   void* out, int out_ld, int B, int H, int W, int Cin, int Cout, int KS, int flags, void* workspace,
-                  size_t ws_bytes, tsr_stream_t stream);
+                  size_t ws_bytes, float* bn_partial, tsr_stream_t stream);
+/* bn_partial (may be NULL): [tsr_conv2d_tc_stat_rows()][2][Cout] floats receiving partial sums / sums of squares of the
+   stored output from the epilogue (batch statistics of the BatchNorm that follows, nn.BatchNorm2d at
+   tactileSR_model.py:42,48,169,...); finish them with tsr_bn_finalize_partials. */
+int tsr_conv2d_tc_stat_rows(void);
 size_t tsr_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS);
 /* weight gradient (fp32 OIHW) of bf16 activations / gradients; bit-deterministic.  H, W % 8 == 0, Cout in {64,128}.
    (The "fp16" precision mode hands this a bf16 copy of the conv input: tcgen05 kind::f16 rejects fp16 x bf16.) */

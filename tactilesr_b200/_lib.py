@@ -40,6 +40,7 @@ SIGNATURES = {
     # elementwise / reductions
     "tsr_bn_workspace": (_Z, [_L, _I]),
     "tsr_bn_train_stats": (_I, [_P, _I, _I, _L, _I, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _Z, _P]),
+    "tsr_bn_finalize_partials": (_I, [_P, _I, _L, _I, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
     "tsr_bn_eval_coeffs": (_I, [_I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P]),
     "tsr_bn_apply": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _L, _I, _I, _P, _I, _P]),
     "tsr_bn_backward_workspace": (_Z, [_L, _I]),
@@ -68,7 +69,8 @@ SIGNATURES = {
     # tensor-core (tcgen05) convolutions
     "tsr_pack_conv_weight_bf16": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "tsr_pack_conv_weight_f16": (_I, [_P, _P, _P, _I, _I, _I, _P]),
-    "tsr_conv2d_tc": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
+    "tsr_conv2d_tc": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P, _P]),
+    "tsr_conv2d_tc_stat_rows": (_I, []),
     "tsr_conv2d_tc_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),
     "tsr_conv2d_wgrad_tc": (_I, [_P, _I, _P, _I, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tsr_conv2d_wgrad_tc_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),

@@ -31,11 +31,13 @@ constexpr int T_TILES = 2;          // M-tiles (128 pixels each) per CTA
 constexpr int NB_STAGES = 3;        // weight ring depth
 constexpr int MAX_NA = 8;           // activation chunk slots (2 for 3x3 / 5x5, more for the bandwidth-bound 1x1)
 constexpr int NUM_THREADS = 224;
+constexpr int STAT_ROWS = 148 * 4;  // rows of the fused BatchNorm-statistics partials: (CTA, epilogue warp)
 
 // experiment switches (env TSR_TC_MODE or tsr_set_tc_desc_mode): bit0 = descriptor base_offset from the address
 // (wrong on B200: the swizzle phase is taken from the absolute smem address), bit1 = 16-pixel halo pitch in the forward
 // kernel instead of the dense TMA-box pitch, bit2 = v1 weight-gradient kernel (tall-plane blocks, per-row TMA),
-// bit3 = N=64 weight-gradient tiles only, bit4 = single-CTA (cta_group::1) forward kernel also for N = 128.
+// bit3 = N=64 weight-gradient tiles only, bit4 = single-CTA (cta_group::1) forward kernel also for N = 128,
+// bit7 = (engine) BatchNorm statistics in a separate pass instead of the conv epilogue.
 static int env_mode() { const char* e = getenv("TSR_TC_MODE"); return e ? atoi(e) : 0; }
 int g_desc_mode = env_mode();
 
@@ -51,10 +53,51 @@ struct ConvParams {
   int w_tile_elems;              // elements between consecutive (chunk, tap) weight tiles = Cout_total * 64
   int nblocks, nb_stages;        // CTA blocks (persistent loop), depth of the weight ring (<= MAX_NB)
   int na_slots;                  // activation chunk slots (<= MAX_NA)
+  float* bn_partial;             // optional [STAT_ROWS][2][bn_C] per-(CTA, epilogue warp) sums / sums of squares of the
+  int bn_C;                      // stored output (BatchNorm batch statistics fused into the epilogue), else null
 };
 
 constexpr int MAX_NB = 8;
 
+
+// Sum over the 32 lanes of a warp of 16 values per lane with 16 shuffles: every exchange halves the values a lane
+// carries; lane l ends with the warp sum of value (l >> 1).
+__device__ __forceinline__ float transpose_reduce16(float (&p)[16], int lane) {
+#pragma unroll
+  for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int k = 0; k < w; ++k) {
+      const float keep = up ? p[k + w] : p[k], send = up ? p[k] : p[k + w];
+      p[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  return p[0] + __shfl_xor_sync(0xffffffffu, p[0], 1);
+}
+
+// BatchNorm batch statistics of the 16 stored (rounded) output channels o[8] of this lane's pixel: per-channel sum and
+// sum of squares over the warp's 32 pixels, added to row `row` of the partial table.  Every (row, channel) address is
+// updated by exactly one lane of one warp, in program order => deterministic although it is a reduction instruction.
+__device__ __forceinline__ void bn_stats_accumulate(const uint32_t (&o)[8], bool valid, bool f16, float* __restrict__ part,
+                                                    int C, int row, int col0, int lane) {
+  float v[16], q[16];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float2 t;
+    if (f16) t = __half22float2(*reinterpret_cast<const __half2*>(&o[k]));
+    else t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o[k]));
+    v[2 * k] = valid ? t.x : 0.f;
+    v[2 * k + 1] = valid ? t.y : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) q[k] = v[k] * v[k];
+  const float s = transpose_reduce16(v, lane), ss = transpose_reduce16(q, lane);
+  if ((lane & 1) == 0) {
+    const int c = col0 + (lane >> 1);
+    atomicAdd(part + ((size_t)row * 2 + 0) * C + c, s);
+    atomicAdd(part + ((size_t)row * 2 + 1) * C + c, ss);
+  }
+}
 
 // Persistent: gridDim.x CTAs (one per SM) stride over the blocks.  The activation-chunk ring, the weight ring and the
 // two TMEM accumulator buffers all run on global counters, so the TMA producers prefetch the next block's halo while
@@ -223,6 +266,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
           uint32_t v[16];
           tmem_ld16(acc0 + mt * N + j * 16, v);
           tmem_ld_wait();
+          uint32_t o[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
           if (valid) {
             float f[16];
 #pragma unroll
@@ -246,7 +290,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
 #pragma unroll
               for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
             }
-            uint32_t o[8];
             if (p.flags & FLAG_F16) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
@@ -264,6 +307,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
             op[0] = make_uint4(o[0], o[1], o[2], o[3]);
             op[1] = make_uint4(o[4], o[5], o[6], o[7]);
           }
+          if (p.bn_partial)      // (warp-uniform: all 32 lanes take part in the shuffles)
+            bn_stats_accumulate(o, valid, (p.flags & FLAG_F16) != 0, p.bn_partial, p.bn_C, (int)blockIdx.x * 4 + q, j * 16, lane);
         }
       }
       // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back to the MMA warp
@@ -502,6 +547,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
           uint32_t v[16];
           tmem_ld16(acc0 + mt * N + j * 16, v);
           tmem_ld_wait();
+          uint32_t o[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
           if (valid) {
             float f[16];
 #pragma unroll
@@ -525,7 +571,6 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
 #pragma unroll
               for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
             }
-            uint32_t o[8];
             if (p.flags & FLAG_F16) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
@@ -543,6 +588,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             op[0] = make_uint4(o[0], o[1], o[2], o[3]);
             op[1] = make_uint4(o[4], o[5], o[6], o[7]);
           }
+          if (p.bn_partial)      // (warp-uniform: all 32 lanes take part in the shuffles)
+            bn_stats_accumulate(o, valid, (p.flags & FLAG_F16) != 0, p.bn_partial, p.bn_C, (int)blockIdx.x * 4 + q, j * 16, lane);
         }
       }
       tc_fence_before();
@@ -1201,10 +1248,16 @@ size_t tsr_conv2d_tc_workspace(int, int, int, int, int, int) { return 0; }
 
 // bf16 NHWC convolution on the tensor cores.  in: [B*H*W][in_ld] (Cin channels from `in`), w_packed from
 // tsr_pack_conv_weight_bf16, bias fp32 [Cout] or NULL, residual bf16 [pix][res_ld] or NULL, out bf16.
+// bn_partial (may be NULL): [tsr_conv2d_tc_stat_rows()][2][Cout] floats that receive per-(CTA, warp) partial sums and sums of
+// squares of the stored output -- the batch statistics of a BatchNorm that consumes this convolution, finished by
+// tsr_bn_finalize_partials without another pass over the tensor.
+int tsr_conv2d_tc_stat_rows(void) { return STAT_ROWS; }
+
 int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* bias, const void* residual,
                   int res_ld, void* out, int out_ld, int B, int H, int W, int Cin, int Cout, int KS, int flags,
-                  void* workspace, size_t ws_bytes, cudaStream_t stream) {
+                  void* workspace, size_t ws_bytes, float* bn_partial, cudaStream_t stream) {
   (void)workspace; (void)ws_bytes;
+  if (bn_partial) TSR_CUDA(cudaMemsetAsync(bn_partial, 0, (size_t)STAT_ROWS * 2 * Cout * sizeof(float), stream));
   TSR_REQUIRE(in && w_packed && out, "conv2d_tc: null pointer");
   TSR_REQUIRE(Cout % 64 == 0 && Cout > 0, "conv2d_tc: Cout must be a multiple of 64 (got %d)", Cout);
   TSR_REQUIRE(Cin % 64 == 0 && Cin > 0, "conv2d_tc: Cin must be a multiple of 64 (got %d)", Cin);
@@ -1244,6 +1297,8 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
     p.bias = bias ? bias + n0 : nullptr;
     p.residual = residual ? (const __nv_bfloat16*)residual + n0 : nullptr;
     p.out = (__nv_bfloat16*)out + n0;
+    p.bn_partial = bn_partial ? bn_partial + n0 : nullptr;
+    p.bn_C = Cout;
     int rc;
     if (nt == 128 && !(g_desc_mode & 16))   // bit 4 set = force the single-CTA kernel
       rc = launch_conv_pair<128>(tmap, p, Cout, n0, (const __nv_bfloat16*)w_packed + (size_t)n0 * 64, stream);

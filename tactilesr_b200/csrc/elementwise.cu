@@ -691,6 +691,21 @@ int tsr_bn_train_stats(const void* y, int y_ld, int y_bf16, long long npix, int 
   return TSR_OK;
 }
 
+// finalise batch statistics from partial sums some other kernel produced (the tensor-core conv epilogue):
+// partial[nrows][2][C] (sum, sum of squares) -> scale / shift / saved mean / invstd, running statistics updated.
+int tsr_bn_finalize_partials(const float* partial, int nrows, long long npix, int C, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                             float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
+                             cudaStream_t stream) {
+  TSR_REQUIRE(partial && gamma && beta && scale && shift && save_mean && save_invstd && nrows > 0 && npix > 0,
+              "bn_finalize_partials: bad argument");
+  bn_finalize_kernel<<<tsr_cdiv(C, 32), dim3(32, 32), 0, stream>>>(partial, nrows, C, (double)npix, gamma, beta, running_mean,
+                                                           running_var, num_batches_tracked, momentum, eps, scale, shift,
+                                                           save_mean, save_invstd);
+  TSR_CHECK_LAUNCH("bn_finalize");
+  return TSR_OK;
+}
+
 int tsr_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, float* scale, float* shift, float* save_mean,
                        float* save_invstd, cudaStream_t stream) {

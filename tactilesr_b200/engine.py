@@ -92,6 +92,7 @@ class RunCtx:
         self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         # "fp16" mode with gradients: bf16 shadow of every buffer some conv reads (the weight-gradient operand; tcgen05
         # kind::f16 cannot mix an fp16 x with a bf16 dy).  Producers write their channel slice of the shadow.
+        self.bn_partials: Dict[object, torch.Tensor] = {}      # BNReLUOp -> statistics partials from its conv's epilogue
         self.shadow: Dict[Buf, torch.Tensor] = {}
         self.conv_inputs: set = set()
         self._ws: Optional[torch.Tensor] = None
@@ -282,7 +283,8 @@ class ConvOp(Op):
     def writes(self):
         return (self.out.buf,)
 
-    def _conv(self, c: RunCtx, inp, inld, wpk, bias, res, resld, outp, outld, Cin, Cout, flags, on_grads=False):
+    def _conv(self, c: RunCtx, inp, inld, wpk, bias, res, resld, outp, outld, Cin, Cout, flags, on_grads=False,
+              bn_partial=0):
         st = _lib.stream_ptr()
         if c.tc:
             need = _lib.lib().tsr_conv2d_tc_workspace(c.B, c.H, c.W, Cin, Cout, self.K)
@@ -290,7 +292,7 @@ class ConvOp(Op):
             if c.act == 2 and not on_grads:
                 flags |= 2      # fp16 activations / weights (forward); data gradients run on bf16 tensors
             _lib.call("tsr_conv2d_tc", inp, inld, wpk, bias, res, resld, outp, outld, c.B, c.H, c.W, Cin, Cout,
-                      self.K, flags, ws, wsb, st)
+                      self.K, flags, ws, wsb, bn_partial, st)
         else:
             _lib.call("tsr_conv2d_f32", inp, inld, wpk, bias, res, resld, outp, outld, c.B, c.H, c.W, Cin, Cout,
                       self.K, flags, st)
@@ -304,8 +306,17 @@ class ConvOp(Op):
         ip, ild = c.vptr(self.src)
         op, old = c.vptr(self.out)
         rp, rld = c.vptr(self.residual) if self.residual is not None else (0, 0)
+        # batch statistics of the BatchNorm that consumes this output come out of the conv epilogue (tensor-core modes)
+        part = 0
+        bn = self.bn_consumer
+        if (c.tc and bn is not None and not (_lib.lib().tsr_get_tc_desc_mode() & 128)      # bit 7: separate statistics pass
+                and not self.relu and self.residual is None and bn.src.buf is self.out.buf
+                and bn.src.c0 == self.out.c0 and (c.training or bn.bn.running_mean is None)):
+            t = torch.empty((_lib.lib().tsr_conv2d_tc_stat_rows(), 2, self.Cout), dtype=torch.float32, device=c.device)
+            c.bn_partials[bn] = t
+            part = t.data_ptr()
         self._conv(c, ip, ild, wf.data_ptr(), _ptr(self.conv.bias), rp, rld, op, old, self.Cin, self.Cout,
-                   1 if self.relu else 0)
+                   1 if self.relu else 0, bn_partial=part)
         c.shadow_fill(self.out)
 
     def bwd(self, c):
@@ -381,7 +392,14 @@ class BNReLUOp(Op):
         sc, sh, mu, iv = (coef[i].data_ptr() for i in range(4))
         yp, yld = c.vptr(self.src)
         use_batch = c.training or bn.running_mean is None
-        if use_batch:
+        part = c.bn_partials.pop(self, None)
+        if use_batch and part is not None:
+            track = c.training and bn.track_running_stats and bn.running_mean is not None
+            mom = 0.1 if bn.momentum is None else bn.momentum
+            _lib.call("tsr_bn_finalize_partials", part.data_ptr(), part.shape[0], c.npix, C, bn.weight.data_ptr(),
+                      bn.bias.data_ptr(), _ptr(bn.running_mean) if track else 0, _ptr(bn.running_var) if track else 0,
+                      _ptr(bn.num_batches_tracked) if track else 0, mom, bn.eps, sc, sh, mu, iv, st)
+        elif use_batch:
             ws, wsb = c.workspace(_lib.lib().tsr_bn_workspace(c.npix, C))
             track = c.training and bn.track_running_stats and bn.running_mean is not None
             mom = 0.1 if bn.momentum is None else bn.momentum

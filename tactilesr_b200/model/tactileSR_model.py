@@ -188,11 +188,11 @@ class TactileSR(_ProgramModule):
             y1, a1, y2 = E.Buf(f"head{s}.y1", 64), E.Buf(f"head{s}.a1", 64), E.Buf(f"head{s}.y2", 64)
             prog.add(E.HeadOp(3 * s, seq[1].weight, E.View.of(y1), relu=False, sf=sf))
             prog.add(E.BNReLUOp(E.View.of(y1), seq[2], E.View.of(a1)))
-            prog.add(E.ConvOp(E.View.of(a1), seq[4], E.View.of(y2)))
-            prog.add(E.BNReLUOp(E.View.of(y2), seq[5], E.View(frames, 64 * s, 64)))
+            cv = prog.add(E.ConvOp(E.View.of(a1), seq[4], E.View.of(y2)))
+            cv.bn_consumer = prog.add(E.BNReLUOp(E.View.of(y2), seq[5], E.View(frames, 64 * s, 64)))
         yc, contact = E.Buf("contact.y", 64), E.Buf("contact", 64)
-        prog.add(E.ConvOp(E.View.of(frames), self.inputContact_layer[0], E.View.of(yc)))
-        prog.add(E.BNReLUOp(E.View.of(yc), self.inputContact_layer[1], E.View.of(contact)))
+        cv = prog.add(E.ConvOp(E.View.of(frames), self.inputContact_layer[0], E.View.of(yc)))
+        cv.bn_consumer = prog.add(E.BNReLUOp(E.View.of(yc), self.inputContact_layer[1], E.View.of(contact)))
         prog.taps["inputContact"] = E.View.of(contact)
         fused = E.Buf("fused", 128)                        # cat(force, pattern) (reference :81)
         _emit_stack(prog, self.patternFeatureExtra_layer, E.View.of(contact), E.View(fused, 64, 64), "msrb")
@@ -242,8 +242,8 @@ class TactileSRCNN(_ProgramModule):
         prog.add(E.BNReLUOp(E.View.of(y), z[1], E.View.of(a)))
         for j in (3, 6):
             y, a2 = E.Buf(f"in.y{j}", 64), E.Buf(f"in.a{j}", 64)
-            prog.add(E.ConvOp(E.View.of(a), z[j], E.View.of(y)))
-            prog.add(E.BNReLUOp(E.View.of(y), z[j + 1], E.View.of(a2)))
+            cv = prog.add(E.ConvOp(E.View.of(a), z[j], E.View.of(y)))
+            cv.bn_consumer = prog.add(E.BNReLUOp(E.View.of(y), z[j + 1], E.View.of(a2)))
             a = a2
         feat = E.Buf("feat", 64)
         _emit_stack(prog, self.msrb_layer, E.View.of(a), E.View.of(feat), "msrb")
