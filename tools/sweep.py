@@ -1,5 +1,5 @@
 """Configuration sweep of BASELINE.json (C2-C4 shapes) on one GPU; prints a markdown table (commit it under profiles/).
-  C3: TactileSR eval forward, batch 1k..256k, fp32 and bf16 modes
+  C3: TactileSR eval forward, batch 1k..256k, fp16 / bf16 / fp32 modes
   C4-shape: TactileSR(seqsCnt=7) train step (single GPU part)
   C2: tPSFNet train step, batch 256..8192
 """
@@ -37,7 +37,7 @@ with torch.no_grad():
     m(torch.rand(64, 3, 4, 4, device=dev) * 8)       # non-trivial running stats
 m.eval()
 quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
-for mode, batches in (("bf16", [1024, 4096, 16384, 65536, 262144]), ("fp32", [1024, 4096, 16384])):
+for mode, batches in (("fp16", [1024, 4096, 16384, 65536, 262144]), ("bf16", [1024, 16384, 262144]), ("fp32", [1024, 4096])):
     tb.set_precision(mode)
     for B in batches:
         if quick and B > 16384:
@@ -47,7 +47,7 @@ for mode, batches in (("bf16", [1024, 4096, 16384, 65536, 262144]), ("fp32", [10
             ms = timeit(lambda: m(LR), 1 if B >= 65536 else 3, warm=1)
         print(f"| C3 TactileSR S=1 eval forward | {mode} | {B} | {ms:.1f} | {B / ms * 1e3:.0f} | {B / ms * 1e3 * FWD[1] / 1e12:.0f} |", flush=True)
 for S in (1, 7):
-    for mode, B in (("bf16", 512), ("fp32", 64)):
+    for mode, B in (("fp16", 1024), ("bf16", 1024), ("fp32", 64)):
         tb.set_precision(mode)
         torch.manual_seed(1)
         ms_ = TactileSR(seqsCnt=S).to(dev).train()
@@ -62,7 +62,7 @@ for S in (1, 7):
         print(f"| C{'1' if S == 1 else '4'}-shape TactileSR S={S} train step | {mode} | {B} | {ms:.1f} | {B / ms * 1e3:.0f} | {B / ms * 1e3 * TRAIN[S] / 1e12:.0f} |", flush=True)
         del ms_, opt
 tb.set_precision("fp32")
-for B in (256, 2048, 8192):
+for B in (256, 2048, 8192, 32768):
     pm = tPSFNet(1.4, None, device=dev).to(dev)
     popt = FusedAdam(pm.parameters(), lr=1e-4, weight_decay=1e-5)
     x = torch.rand(B, 3, 4, 4, device=dev) * 13
