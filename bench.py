@@ -202,6 +202,25 @@ def measure_extras(dev, model, B):
     out["sr_infer_samples_per_s"] = Bi / (ms * 1e-3)
     out["sr_infer_batch"] = Bi
     out["sr_infer_tensor_frac_of_sustained_peak"] = Bi / (ms * 1e-3) * FLOP_PER_SAMPLE_FWD / 1e12 / peaks()["tf_sust"]
+    # C1's own batch size (config/default.py:46: 32): the iteration is launch-bound there; eager vs Trainer(cuda_graph=True)
+    from tactilesr_b200.train.tactileSR_train import Trainer_tactileSR, build_model_and_optimizer
+    for use_graph in (False, True):
+        torch.manual_seed(0)
+        m32, o32 = build_model_and_optimizer(SR_CONFIG, dev)
+        d32 = [(torch.rand(32, 3, 4, 4, device=dev) * 8, torch.rand(32, 1, 100, 100, device=dev) * 250) for _ in range(4)]
+
+        class L32:
+            def __len__(self): return 4
+            def __iter__(self):
+                while True:
+                    yield from d32
+        t32 = Trainer_tactileSR(SR_CONFIG, model=m32, optimizer=o32, lr_scheduler=torch.optim.lr_scheduler.StepLR(o32, 2, 0.8),
+                                data_loader=L32(), max_iters=10 ** 9, log_period=10 ** 9, device=dev, cuda_graph=use_graph)
+        for _ in range(4):
+            t32.train_one_iter()
+        ms = timeit(t32.train_one_iter, 20)
+        out["sr_train_b32_cuda_graph_samples_per_s" if use_graph else "sr_train_b32_eager_samples_per_s"] = 32 / (ms * 1e-3)
+        del t32, m32, o32
     # TactileSRCNN (reference model/tactileSR_model.py:101-153; same kernels, different wiring): train step at the same batch
     from tactilesr_b200.functional import mse_hr_loss
     from tactilesr_b200.model import TactileSRCNN

@@ -132,6 +132,11 @@ int tsr_eval_metrics(const float* out, const float* hr_raw, float scale_num, int
 int tsr_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, long long step, float grad_scale, tsr_stream_t stream);
 
+/* the same step with the step-dependent scalars in device memory, hyper = {lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)}: a
+ * captured CUDA graph can replay the launch while the host advances t and the learning-rate schedule. */
+int tsr_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* hyper, float beta1,
+                      float beta2, float eps, float weight_decay, float grad_scale, tsr_stream_t stream);
+
 /* ---- tPSFNet ----------------------------------------------------------------------------------------------------- */
 /* C[m][n] = act(sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] + bias[n]); act 0 none, 1 relu, 2 softplus. */
 int tsr_sgemm_strided(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn,

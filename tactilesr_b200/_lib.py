@@ -53,6 +53,7 @@ SIGNATURES = {
     "tsr_mse_hr_loss": (_I, [_P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _F, _P, _Z, _P]),
     "tsr_eval_metrics": (_I, [_P, _P, _F, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P]),
     "tsr_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _L, _F, _P]),
+    "tsr_adam_step_dev": (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P]),
     # tPSFNet
     "tsr_sgemm_strided": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _I, _I, _I, _P, _I, _I, _P]),
     "tsr_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),

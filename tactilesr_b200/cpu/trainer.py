@@ -203,7 +203,7 @@ class Trainer:
                  max_num_checkpoints: Optional[int] = None, checkpoint_period: int = 1, log_period: int = 50,
                  clip_grad_norm: float = 0.0, enable_amp: bool = False, by_epoch: bool = True, warmup_t: int = 0,
                  warmup_by_epoch: bool = False, warmup_mode: str = "fix", warmup_init_lr: float = 0.0,
-                 warmup_factor: float = 0.0, grad_bucket_bytes: int = 8 << 20):
+                 warmup_factor: float = 0.0, grad_bucket_bytes: int = 8 << 20, cuda_graph: bool = False):
         if enable_amp:
             raise NotImplementedError("enable_amp: use tactilesr_b200.set_precision('bf16') instead of autocast")
         model.train()
@@ -230,6 +230,12 @@ class Trainer:
         self._time_acc = {"data_time": 0.0, "iter_time": 0.0}
         self._dp: Optional[D.GradAllReduce] = None
         self._grad_bucket_bytes = grad_bucket_bytes
+        # cuda_graph (extension; the reference has no such switch): after two ordinary iterations the whole iteration
+        # (train_cal_loss + backward + optimizer step, ~450 kernel launches) is captured once per batch shape and
+        # replayed -- at the reference's batch size 32 the iteration is launch-bound, not GPU-bound.  Single GPU only.
+        self._use_graph = cuda_graph
+        self._graphs: Dict[tuple, tuple] = {}
+        self._eager_iters = 0
         self.register_hooks([_LRUpdateHook()])
 
     # -- bookkeeping identical in meaning to the reference ------------------------------------------
@@ -310,6 +316,11 @@ class Trainer:
             batch = next(self._data_iter)
         data_time = time.perf_counter() - t0
 
+        if self._graph_eligible(batch):
+            loss_dict = self._graphed_iter(batch)
+            self._log_iter_metrics(loss_dict, data_time, time.perf_counter() - t0)
+            return
+        self._eager_iters += 1
         losses, loss_dict = self.train_cal_loss(batch)
         self.optimizer.zero_grad()
         losses.backward()
@@ -323,6 +334,43 @@ class Trainer:
             clip_grad_norm_(self.model.parameters(), self._clip_grad_norm)
         self.optimizer.step()
         self._log_iter_metrics(loss_dict, data_time, time.perf_counter() - t0)
+
+    # -- CUDA-graph replay of the iteration ---------------------------------------------------------------
+    def _graph_eligible(self, batch) -> bool:
+        return (self._use_graph and self._eager_iters >= 2 and self._dp is None and D.get_world_size() == 1
+                and self._clip_grad_norm <= 0 and hasattr(self.optimizer, "enable_graph_mode")
+                and isinstance(batch, (tuple, list)) and all(torch.is_tensor(t) for t in batch))
+
+    def _graphed_iter(self, batch) -> Dict[str, torch.Tensor]:
+        dev = next(self.model_or_module.parameters()).device
+        key = tuple((tuple(t.shape), t.dtype) for t in batch)
+        opt = self.optimizer
+        entry = self._graphs.get(key)
+        if entry is None:
+            if opt._graph_hyper is None:
+                opt.enable_graph_mode()
+            static = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in batch]
+            for s_, t in zip(static, batch):
+                s_.copy_(t, non_blocking=True)
+            opt.update_graph_hyper()
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                losses, loss_dict = self.train_cal_loss(tuple(static))
+                opt.zero_grad()
+                losses.backward()
+                opt.step()                   # (host side of this call advanced the step counters once)
+            graph.replay()
+            entry = (graph, static, loss_dict)
+            self._graphs[key] = entry
+            return loss_dict
+        graph, static, loss_dict = entry
+        for s_, t in zip(static, batch):
+            s_.copy_(t, non_blocking=True)
+        opt.update_graph_hyper()
+        graph.replay()
+        opt.graph_advance()
+        return loss_dict
 
     def _log_iter_metrics(self, loss_dict: Dict[str, torch.Tensor], data_time: float, iter_time: float) -> None:
         total = sum(v.detach() for v in loss_dict.values())

@@ -397,7 +397,10 @@ __global__ void sum_final_kernel(const float* __restrict__ partial, int n, doubl
 // ------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
-                            float inv_bc1, float inv_sqrt_bc2, float grad_scale) {
+                            float inv_bc1, float inv_sqrt_bc2, float grad_scale, const float* __restrict__ hyper) {
+  // hyper (optional, device memory): {lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)} of this step -- lets a captured CUDA
+  // graph replay the launch while the host advances the step count and the learning-rate schedule
+  if (hyper) { lr = hyper[0]; inv_bc1 = 1.f; inv_sqrt_bc2 = hyper[1]; }
   long long i4 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
   for (; i4 < n; i4 += (long long)gridDim.x * blockDim.x * 4) {
     if (i4 + 4 <= n) {
@@ -897,8 +900,19 @@ int tsr_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
   double bc2 = 1.0 - pow((double)beta2, (double)step);
   int grid = ew_grid((n + 3) / 4);
   adam_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)(1.0 / bc1),
-                                        (float)(1.0 / sqrt(bc2)), grad_scale);
+                                        (float)(1.0 / sqrt(bc2)), grad_scale, nullptr);
   TSR_CHECK_LAUNCH("adam_step");
+  return TSR_OK;
+}
+
+// the same step with the step-dependent scalars read from device memory: hyper = {lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)}
+int tsr_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* hyper, float beta1,
+                      float beta2, float eps, float weight_decay, float grad_scale, cudaStream_t stream) {
+  TSR_REQUIRE(p && g && m && v && hyper && n >= 0, "adam_step_dev: bad argument");
+  if (n == 0) return TSR_OK;
+  int grid = ew_grid((n + 3) / 4);
+  adam_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, grad_scale, hyper);
+  TSR_CHECK_LAUNCH("adam_step_dev");
   return TSR_OK;
 }
 

@@ -8,8 +8,10 @@ the data-parallel all-reduce runs over the same flat gradient buffer.
 """
 from __future__ import annotations
 
+import math
 from typing import List
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -27,6 +29,7 @@ class FusedAdam(torch.optim.Optimizer):
                         decoupled_weight_decay=decoupled_weight_decay)
         super().__init__(params, defaults)
         self._flat = {}
+        self._graph_hyper = None       # CUDA-graph mode: per-group device {lr / bc1, 1 / sqrt(bc2)} (see enable_graph_mode)
 
     # -- flat storage -------------------------------------------------------------------------
     def _flatten_group(self, gi: int, group) -> dict:
@@ -67,6 +70,45 @@ class FusedAdam(torch.optim.Optimizer):
             self._flatten_group(gi, self.param_groups[gi])
         return self._flat[gi]["g"]
 
+    # -- CUDA-graph support -----------------------------------------------------------------------
+    def enable_graph_mode(self) -> None:
+        """From now on ``step`` reads the step-dependent scalars (bias corrections, learning rate) from device memory, so
+        the launch can be captured in a CUDA graph; the host refreshes them with ``update_graph_hyper`` before every
+        replay and advances its step counters with ``graph_advance`` afterwards.  Requires an ordinary step to have run
+        (flat buffers exist) and every parameter of a group to share one step count."""
+        self._graph_hyper = []
+        for gi, group in enumerate(self.param_groups):
+            if gi not in self._flat:
+                self._flatten_group(gi, group)
+            dev = self._flat[gi]["p"].device if self._flat.get(gi) else torch.device("cuda")
+            self._graph_hyper.append(torch.zeros(2, dtype=torch.float32, device=dev))
+
+    def disable_graph_mode(self) -> None:
+        self._graph_hyper = None
+
+    def update_graph_hyper(self) -> None:
+        """Scalars of the *next* step -> device (stream-ordered before the replay)."""
+        for gi, group in enumerate(self.param_groups):
+            f = self._flat.get(gi)
+            if not f:
+                continue
+            # bit-for-bit the scalars tsr_adam_step derives on the host: betas and lr as floats, bias corrections in
+            # double, their reciprocals rounded to float, the lr product in float
+            b1, b2 = (float(np.float32(b)) for b in group["betas"])
+            t = int(self.state[f["params"][0]]["step"]) + 1
+            inv_bc1 = np.float32(1.0 / (1.0 - math.pow(b1, float(t))))
+            vals = [float(np.float32(group["lr"]) * inv_bc1), float(np.float32(1.0 / math.sqrt(1.0 - math.pow(b2, float(t)))))]
+            # a fresh pageable source per call: the copy is staged before it returns, so the host (which runs many
+            # iterations ahead of the GPU) can never overwrite scalars an earlier replay has not consumed yet
+            self._graph_hyper[gi].copy_(torch.tensor(vals, dtype=torch.float32))
+
+    def graph_advance(self) -> None:
+        """Host bookkeeping of one replayed step: step counters and the packed-weight epoch."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                self.state[p]["step"] += 1
+        bump_weight_epoch()
+
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._flat = {}   # re-flatten around the loaded moments on the next step
@@ -100,10 +142,16 @@ class FusedAdam(torch.optim.Optimizer):
                     if p.grad.data_ptr() != f["g"].data_ptr() + o * 4:
                         f["g"][o:o + p.numel()].copy_(p.grad.reshape(-1))
                 step = steps.pop() + 1
-                _lib.call("tsr_adam_step", f["p"].data_ptr(), f["g"].data_ptr(), f["m"].data_ptr(), f["v"].data_ptr(),
-                          f["n"], lr, b1, b2, eps, wd, step, 1.0, st_ptr)
+                if self._graph_hyper is not None:
+                    _lib.call("tsr_adam_step_dev", f["p"].data_ptr(), f["g"].data_ptr(), f["m"].data_ptr(),
+                              f["v"].data_ptr(), f["n"], self._graph_hyper[gi].data_ptr(), b1, b2, eps, wd, 1.0, st_ptr)
+                else:
+                    _lib.call("tsr_adam_step", f["p"].data_ptr(), f["g"].data_ptr(), f["m"].data_ptr(), f["v"].data_ptr(),
+                              f["n"], lr, b1, b2, eps, wd, step, 1.0, st_ptr)
                 for p in params:
                     self.state[p]["step"] += 1
+            elif self._graph_hyper is not None:
+                raise _lib.TsrError("FusedAdam graph mode needs every parameter of a group to receive a gradient")
             else:
                 # stock Adam skips parameters without a gradient (e.g. the transplanted stacks of
                 # tactileSRSeqs_train.py:74-77 are not even in the optimizer): per-parameter launches.
