@@ -263,6 +263,24 @@ def measure_extras(dev, model, B):
         with torch.no_grad():
             ms = timeit(lambda: pm(x, depth), 5)
         out[f"tpsf_fwd_samples_per_s{tag}"] = Bp / (ms * 1e-3)
+        if Bp == 256:      # the same step through Trainer_tPSF with the iteration captured in a CUDA graph
+            from tactilesr_b200.train.tPSFNet_train import Trainer_tPSF
+            pdata = [(x * 100, depth[:, 0])] * 2
+
+            class LP:
+                def __len__(self): return 2
+                def __iter__(self):
+                    while True:
+                        yield from pdata
+            pm2 = tPSFNet(gama=1.4, perception_scale=None, device=dev).to(dev)
+            po2 = FusedAdam(pm2.parameters(), lr=1e-4, weight_decay=1e-5)
+            tp = Trainer_tPSF(100, model=pm2, optimizer=po2, lr_scheduler=torch.optim.lr_scheduler.StepLR(po2, 1, 0.9),
+                              data_loader=LP(), max_iters=10 ** 9, log_period=10 ** 9, device=dev, cuda_graph=True)
+            for _ in range(4):
+                tp.train_one_iter()
+            ms = timeit(tp.train_one_iter, 20)
+            out["tpsf_train_cuda_graph_samples_per_s"] = Bp / (ms * 1e-3)
+            del tp, pm2, po2
         if Bp != 256:
             # the two tcgen05 PSF kernels alone (HBM-bound: compulsory 119 472 B / sample forward,
             # 40 000 (depth) + 4 848 (row statistics) + 76 B backward), against the measured HBM copy peak

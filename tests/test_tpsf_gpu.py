@@ -157,3 +157,32 @@ def test_psf_tensor_core_backward_matches_ffma_backward(B):
         worst = ((d1[:, c] - d0[:, c]).abs() / d0[:, c].abs().clamp_min(1e-3 * d0[:, c].abs().max())).max().item()
         print(f"psf bwd tc vs ffma B={B} d{name}: rel-L2 {e:.2e}, worst per-sample {worst:.2e}")
         assert e < 2e-4 and worst < 2e-3, (name, e, worst)
+
+
+def test_trainer_tpsf_graph_and_eager_agree():
+    """Trainer_tPSF (train/tPSFNet_train.py:173-190 mirror): 6 iterations eager vs cuda_graph=True are bit-identical, and
+    the loss goes down; eval_func returns the reference's first-sample metrics."""
+    from tactilesr_b200.train.tPSFNet_train import Trainer_tPSF, build_model_and_optimizer, eval_func
+    from oracle import tpsf_oracle as po
+    cfg = dict(gama=1.4, perception_scale=None, lr=1e-3, weight_decay=1e-5, scale_num=100)
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(21)
+    data = [(torch.rand(8, 3, 4, 4, generator=g) * 1300, po.synthetic_depth(8, 30 + i)) for i in range(6)]
+    res = []
+    for use_graph in (False, True):
+        torch.manual_seed(3)
+        model, opt = build_model_and_optimizer(cfg, dev)
+        tr = Trainer_tPSF(100, model=model, optimizer=opt, lr_scheduler=torch.optim.lr_scheduler.StepLR(opt, 1, 0.9),
+                          data_loader=data, max_iters=100, log_period=10 ** 9, device=dev, cuda_graph=use_graph)
+        losses = []
+        for it in range(6):
+            tr.cur_iter = it
+            tr.train_one_iter()
+            losses.append(tr._loss_acc.clone()); tr._loss_acc, tr._loss_cnt = None, 0
+        res.append((torch.stack(losses).cpu(), [p.detach().clone() for p in model.parameters()]))
+        assert (len(tr._graphs) == 1) == use_graph
+    assert torch.equal(res[0][0], res[1][0]), (res[0][0], res[1][0])
+    for a, b in zip(res[0][1], res[1][1]):
+        assert torch.equal(a, b)
+    mse, ssim = eval_func(model, data[:2], cfg)
+    assert mse > 0 and -1.0 <= ssim <= 1.0
