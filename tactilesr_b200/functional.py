@@ -6,33 +6,14 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-
-
-class _MseHrFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, out, hr_raw, scale_num):
-        if not out.is_cuda:
-            raise _lib.TsrError("mse_hr_loss runs on CUDA tensors only (no CPU fallback)")
-        B, _, H, W = out.shape
-        o = out.detach().contiguous().float()
-        hr = hr_raw.detach().reshape(B, hr_raw.shape[-2], hr_raw.shape[-1]).contiguous().float()
-        loss = torch.empty((), dtype=torch.float32, device=out.device)
-        dout = torch.empty_like(o)
-        ws = torch.empty(int(_lib.lib().tsr_mse_hr_workspace()), dtype=torch.uint8, device=out.device)
-        _lib.call("tsr_mse_hr_loss", o.data_ptr(), hr.data_ptr(), float(scale_num), B, H, W, hr.shape[-2], hr.shape[-1],
-                  loss.data_ptr(), dout.data_ptr(), 1.0, ws.data_ptr(), ws.numel(), _lib.stream_ptr())
-        ctx.save_for_backward(dout)
-        return loss
-
-    @staticmethod
-    def backward(ctx, g):
-        (dout,) = ctx.saved_tensors
-        return dout * g, None, None
+from . import ops  # noqa: F401  (registers torch.ops.tactilesr.*)
 
 
 def mse_hr_loss(out: torch.Tensor, hr_raw: torch.Tensor, hr_scale_num: float = 10.0) -> torch.Tensor:
-    """mean((out - resize(hr_raw / hr_scale_num, out.shape[-2:]))**2)."""
-    return _MseHrFn.apply(out, hr_raw, hr_scale_num)
+    """mean((out - resize(hr_raw / hr_scale_num, out.shape[-2:]))**2)   (torch.ops.tactilesr.mse_hr_loss)."""
+    if not out.is_cuda:
+        raise _lib.TsrError("mse_hr_loss runs on CUDA tensors only (no CPU fallback)")
+    return torch.ops.tactilesr.mse_hr_loss(out, hr_raw, float(hr_scale_num))[0]
 
 
 def eval_metrics(out: torch.Tensor, hr_raw: torch.Tensor, hr_scale_num: float = 10.0, max_value: float = 250.0,
@@ -43,11 +24,6 @@ def eval_metrics(out: torch.Tensor, hr_raw: torch.Tensor, hr_scale_num: float = 
     / ``calculationSSIM(out[i], HR[i])`` on the reference's (1, H, W) slices (so the PSNR divisor is H, not H*W)."""
     if not out.is_cuda:
         raise _lib.TsrError("eval_metrics runs on CUDA tensors only (no CPU fallback)")
-    B, _, H, W = out.shape
-    o = out.detach().contiguous().float()
-    hr = hr_raw.detach().reshape(B, hr_raw.shape[-2], hr_raw.shape[-1]).contiguous().float()
-    res = torch.empty((3, B), dtype=torch.float32, device=out.device)
-    _lib.call("tsr_eval_metrics", o.data_ptr(), hr.data_ptr(), float(hr_scale_num), B, H, W, hr.shape[-2], hr.shape[-1],
-              float(max_value), float(out.shape[1] * H), float(C1), float(C2), res[0].data_ptr(), res[1].data_ptr(),
-              res[2].data_ptr(), _lib.stream_ptr())
-    return res[0].sum() / (B * out.shape[1] * H * W), res[1], res[2]
+    B, C, H, W = out.shape
+    res = torch.ops.tactilesr.eval_metrics(out, hr_raw, float(hr_scale_num), float(max_value), float(C1), float(C2))
+    return res[0].sum() / (B * C * H * W), res[1], res[2]

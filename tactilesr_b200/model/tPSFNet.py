@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
+from .. import ops  # noqa: F401  (registers torch.ops.tactilesr.*)
 
 _ACT = {"none": 0, "relu": 1, "softplus": 2}
 
@@ -65,76 +66,37 @@ def _linear_bwd(dy, out, x, w, act, need_dx, st):
     return dw, db, dx
 
 
-class _PSFFn(torch.autograd.Function):
+class _MLPFn(torch.autograd.Function):
+    """MLP_layer (reference model/tPSFNet.py:26-36): Flatten -> 48-256-1024-256-3 with ReLU / Softplus, forward and
+    hand-written backward on our GEMM kernels."""
+
     @staticmethod
-    def forward(ctx, x, depth, w1, b1, w2, b2, w3, b3, w4, b4):
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3, w4, b4):
         if not x.is_cuda:
             raise _lib.TsrError("tactilesr_b200.tPSFNet runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
-        # outputs that take no part in the loss must reach backward as None, not as materialised zero tensors: the
-        # training case (gradient through LR_degrade only) is what selects the tcgen05 backward
-        ctx.set_materialize_grads(False)
         st = _lib.stream_ptr()
         B = x.shape[0]
         x2 = x.detach().reshape(B, -1).contiguous().float()
-        d = depth.detach().reshape(B, 100, 100).contiguous().float()
-        dev = x.device
         ws = [w.detach().contiguous() for w in (w1, w2, w3, w4)]
         bs = [b.detach().contiguous() for b in (b1, b2, b3, b4)]
         acts = [x2]
         for i, (w, b) in enumerate(zip(ws, bs)):
             acts.append(_linear_fwd(acts[-1], w, b, "softplus" if i == 3 else "relu", st))
-        ab = acts[-1]
-        HR = torch.empty((B, 1, 100, 100), dtype=torch.float32, device=dev)
-        LRd = torch.empty((B, 1, 4, 4), dtype=torch.float32, device=dev)
-        psf = torch.empty((B, 1, 99, 99), dtype=torch.float32, device=dev)
-        L = _lib.lib()
-        aux = None
-        if L.tsr_get_psf_mode() == 0:
-            # tcgen05 forward; when a backward may follow it also leaves the per-row statistics of HR the tcgen05
-            # backward needs (4.8 KB per sample) so that the backward never re-reads HR
-            if any(ctx.needs_input_grad):
-                aux = torch.empty((B, int(L.tsr_psf_aux_floats())), dtype=torch.float32, device=dev)
-            _lib.call("tsr_psf_forward_tc", ab.data_ptr(), d.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(),
-                      0 if aux is None else aux.data_ptr(), B, st)
-        else:
-            _lib.call("tsr_psf_forward_ffma", ab.data_ptr(), d.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), B, st)
-        ctx.has_aux = aux is not None
-        ctx.save_for_backward(d, HR, *acts, *ws, *([aux] if aux is not None else []))
-        return HR, LRd, psf, ab.view(B, 1, 3).clone()
+        ctx.save_for_backward(*acts, *ws)
+        return acts[-1].clone()
 
     @staticmethod
-    def backward(ctx, dHR, dLRd, dpsf, dab_direct):
+    def backward(ctx, dab):
         st = _lib.stream_ptr()
         saved = ctx.saved_tensors
-        d, HR = saved[0], saved[1]
-        acts, ws = list(saved[2:7]), list(saved[7:11])
-        B = d.shape[0]
-        dev = d.device
-        ab = acts[-1]
-
-        def prep(g):
-            return None if g is None else g.detach().contiguous().float()
-        dHR, dLRd, dpsf, dab_direct = prep(dHR), prep(dLRd), prep(dpsf), prep(dab_direct)
-        if dHR is None and dLRd is None and dpsf is None and dab_direct is None:
-            return (None,) * 10
-        dab = torch.empty((B, 3), dtype=torch.float32, device=dev)
-        if ctx.has_aux and dHR is None and dpsf is None and dLRd is not None:
-            # the training case (train/tPSFNet_train.py:186-189: only LR_degrade is supervised): tcgen05 backward
-            _lib.call("tsr_psf_backward_tc", ab.data_ptr(), d.data_ptr(), saved[11].data_ptr(), dLRd.data_ptr(),
-                      dab.data_ptr(), B, st)
-        else:
-            _lib.call("tsr_psf_backward", ab.data_ptr(), d.data_ptr(), HR.data_ptr(),
-                      0 if dLRd is None else dLRd.data_ptr(), 0 if dHR is None else dHR.data_ptr(),
-                      0 if dpsf is None else dpsf.data_ptr(), dab.data_ptr(), B, st)
-        if dab_direct is not None:
-            dab = dab + dab_direct.view(B, 3)
+        acts, ws = list(saved[0:5]), list(saved[5:9])
         grads = []
-        dy = dab
+        dy = dab.detach().contiguous().float()
         for i in (3, 2, 1, 0):
             dw, db, dx = _linear_bwd(dy, acts[i + 1], acts[i], ws[i], "softplus" if i == 3 else "relu", i > 0, st)
             grads = [dw, db] + grads
             dy = dx
-        return (None, None, *grads)
+        return (None, *grads)
 
 
 class tPSFNet(nn.Module):
@@ -171,5 +133,10 @@ class tPSFNet(nn.Module):
     def forward(self, x, depth):
         assert x.shape[0] == depth.shape[0], "Batch size of LR tactile and depth should be the same!"
         L = self.MLP_layer
-        return _PSFFn.apply(x, depth, L[1].weight, L[1].bias, L[3].weight, L[3].bias, L[5].weight, L[5].bias,
-                            L[7].weight, L[7].bias)
+        B = x.shape[0]
+        ab = _MLPFn.apply(x, L[1].weight, L[1].bias, L[3].weight, L[3].bias, L[5].weight, L[5].bias, L[7].weight,
+                          L[7].bias)
+        # the python ``for i in range(B)`` loop of the reference (:118-125) is one custom op with autograd
+        # (torch.ops.tactilesr.psf_model); the forward -> backward hand-over is only produced when a backward can follow
+        HR, LRd, psf, _ = torch.ops.tactilesr.psf_model(ab, depth, torch.is_grad_enabled() and ab.requires_grad)
+        return HR, LRd, psf, ab.view(B, 1, 3)
