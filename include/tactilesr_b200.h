@@ -179,6 +179,10 @@ int tsr_pack_conv_weight_bf16(const float* w_oihw, void* w_fwd, void* w_dgrad, i
 /* same packing with fp16 elements: forward weights of the "fp16" precision mode (fp16 activations, bf16 gradients) */
 int tsr_pack_conv_weight_f16(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int KS,
                              tsr_stream_t stream);
+/* inference: fold an eval-mode BatchNorm (scale / shift of tsr_bn_eval_coeffs) that follows the convolution into the packed
+   forward weights (dtype 1 = bf16, 2 = fp16) and into bias_out[co] = scale[co] * bias[co] + shift[co] (bias may be NULL) */
+int tsr_pack_conv_weight_folded(const float* w_oihw, const float* bias, const float* scale, const float* shift, void* w_fwd,
+                                float* bias_out, int Cout, int Cin, int KS, int dtype, tsr_stream_t stream);
 size_t tsr_conv2d_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS);
 /* bf16 NHWC convolution, same semantics as tsr_conv2d_f32 (bias fp32, residual / out bf16).  W % 8 == 0.
    flags bit 1 (value 2): in / weights / residual / out are fp16 instead of bf16 (same kernels, kind::f16 format field). */

@@ -611,7 +611,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int Cout,
-                                        int Cin, int KS) {
+                                        int Cin, int KS, const float* __restrict__ co_scale = nullptr) {
   const int taps = KS * KS;
   const long long n = (long long)Cout * Cin * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -621,7 +621,7 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, T* __restri
     const int ci = (int)(r % Cin);
     const int co = (int)(r / Cin);
     T v;
-    stf(&v, w[i]);
+    stf(&v, co_scale ? w[i] * co_scale[co] : w[i]);      // (inference: an eval-mode BatchNorm folded into the weights)
     if (wf) {   // tile (chunk = ci/64, tap t): row co, k = ci%64
       const int c = ci >> 6, k = ci & 63;
       const long long tile = ((long long)c * taps + t) * Cout * 64;
@@ -1241,6 +1241,33 @@ int tsr_pack_conv_weight_f16(const float* w_oihw, void* w_fwd, void* w_dgrad, in
   if (blocks > 2048) blocks = 2048;
   pack_weight_bf16_kernel<__half><<<blocks, 256, 0, stream>>>(w_oihw, (__half*)w_fwd, (__half*)w_dgrad, Cout, Cin, KS);
   TSR_CHECK_LAUNCH("pack_conv_weight_f16");
+  return TSR_OK;
+}
+
+// Inference-time folding of an eval-mode BatchNorm that follows the convolution (y = scale * conv(x) + shift, scale / shift
+// from tsr_bn_eval_coeffs): forward weights scaled per output channel (dtype 1 = bf16, 2 = fp16) and the folded bias
+// bias_out[co] = scale[co] * bias[co] + shift[co]  (bias may be NULL).
+__global__ void fold_bias_kernel(const float* __restrict__ bias, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, float* __restrict__ out, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[c] = fmaf(scale[c], bias ? bias[c] : 0.f, shift[c]);
+}
+
+int tsr_pack_conv_weight_folded(const float* w_oihw, const float* bias, const float* scale, const float* shift, void* w_fwd,
+                                float* bias_out, int Cout, int Cin, int KS, int dtype, cudaStream_t stream) {
+  TSR_REQUIRE(w_oihw && scale && shift && w_fwd && bias_out, "pack_conv_weight_folded: null pointer");
+  TSR_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "pack_conv_weight_folded: Cin, Cout must be multiples of 64");
+  TSR_REQUIRE(dtype == TSR_DT_BF16 || dtype == TSR_DT_F16, "pack_conv_weight_folded: dtype must be 1 (bf16) or 2 (fp16)");
+  long long n = (long long)Cout * Cin * KS * KS;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 2048) blocks = 2048;
+  if (dtype == TSR_DT_F16)
+    pack_weight_bf16_kernel<__half><<<blocks, 256, 0, stream>>>(w_oihw, (__half*)w_fwd, (__half*)nullptr, Cout, Cin, KS, scale);
+  else
+    pack_weight_bf16_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(w_oihw, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)nullptr, Cout, Cin, KS, scale);
+  TSR_CHECK_LAUNCH("pack_conv_weight_folded");
+  fold_bias_kernel<<<tsr_cdiv(Cout, 128), 128, 0, stream>>>(bias, scale, shift, bias_out, Cout);
+  TSR_CHECK_LAUNCH("fold_bias");
   return TSR_OK;
 }
 

@@ -25,6 +25,7 @@ from . import _lib
 
 _PRECISION = "fp32"
 _WEIGHT_EPOCH = 0          # bumped by FusedAdam.step (in-place kernel updates do not bump ._version)
+_STATS_EPOCH = 0           # bumped whenever a training forward updates BatchNorm running statistics in place
 
 
 def set_precision(mode: str) -> None:
@@ -93,6 +94,8 @@ class RunCtx:
         # "fp16" mode with gradients: bf16 shadow of every buffer some conv reads (the weight-gradient operand; tcgen05
         # kind::f16 cannot mix an fp16 x with a bf16 dy).  Producers write their channel slice of the shadow.
         self.bn_partials: Dict[object, torch.Tensor] = {}      # BNReLUOp -> statistics partials from its conv's epilogue
+        self.folded: set = set()                               # BNReLUOps already applied by their (inference) conv
+        self.keep_taps = False
         self.shadow: Dict[Buf, torch.Tensor] = {}
         self.conv_inputs: set = set()
         self._ws: Optional[torch.Tensor] = None
@@ -191,6 +194,30 @@ class _PackCache:
             _lib.call(fn, wc.data_ptr(), wf.data_ptr(), _ptr(wd), Cout, Cin, K, st)
         store[mode] = (tag, wf, wd)
         return wf, wd
+
+
+    def get_folded(self, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, mode: str):
+        """Inference: forward pack of ``conv`` with the eval-mode BatchNorm ``bn`` folded in -> (packed weights, bias)."""
+        w = conv.weight
+        tag = (w.data_ptr(), w._version, _WEIGHT_EPOCH, _STATS_EPOCH, tuple(w.shape), w.device, bn.weight.data_ptr(),
+               bn.weight._version, bn.bias._version, bn.running_mean.data_ptr(), bn.running_mean._version,
+               bn.running_var._version, bn.eps, None if conv.bias is None else conv.bias._version)
+        store = w.__dict__.setdefault("_tsr_pack", {})
+        hit = store.get(mode + ":folded")
+        if hit is not None and hit[0] == tag:
+            return hit[1], hit[2]
+        Cout, Cin, K, _ = w.shape
+        st = _lib.stream_ptr()
+        coef = torch.empty((4, Cout), dtype=torch.float32, device=w.device)
+        _lib.call("tsr_bn_eval_coeffs", Cout, bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                  bn.running_var.data_ptr(), bn.eps, coef[0].data_ptr(), coef[1].data_ptr(), coef[2].data_ptr(),
+                  coef[3].data_ptr(), st)
+        wf = torch.empty((K * K * Cin * Cout,), dtype=torch.float16 if mode == "fp16" else torch.bfloat16, device=w.device)
+        bias = torch.empty((Cout,), dtype=torch.float32, device=w.device)
+        _lib.call("tsr_pack_conv_weight_folded", w.detach().contiguous().data_ptr(), _ptr(conv.bias), coef[0].data_ptr(),
+                  coef[1].data_ptr(), wf.data_ptr(), bias.data_ptr(), Cout, Cin, K, 2 if mode == "fp16" else 1, st)
+        store[mode + ":folded"] = (tag, wf, bias)
+        return wf, bias
 
 
 _PACK = _PackCache()
@@ -302,13 +329,25 @@ class ConvOp(Op):
         return c.sptr(self.src) if c.act == 2 else c.vptr(self.src)
 
     def fwd(self, c):
-        wf, _ = _PACK.get(self.conv.weight, c.mode, False)
         ip, ild = c.vptr(self.src)
+        bn = self.bn_consumer
+        if (c.tc and bn is not None and not c.training and not c.need_grad and not c.keep_taps and not self.relu
+                and self.residual is None and bn.bn.running_mean is not None and bn.bn.weight is not None
+                and bn.src.buf is self.out.buf
+                and bn.src.c0 == self.out.c0 and bn.src.C == self.Cout):
+            # inference: the eval-mode BatchNorm (+ReLU) that follows is folded into the weights / bias, and the result
+            # goes straight into the BatchNorm's output slice -- no BN kernels, no intermediate tensor
+            wf, bias = _PACK.get_folded(self.conv, bn.bn, c.mode)
+            op, old = c.vptr(bn.out)
+            self._conv(c, ip, ild, wf.data_ptr(), bias.data_ptr(), 0, 0, op, old, self.Cin, self.Cout,
+                       1 if bn.relu else 0)
+            c.folded.add(bn)
+            return
+        wf, _ = _PACK.get(self.conv.weight, c.mode, False)
         op, old = c.vptr(self.out)
         rp, rld = c.vptr(self.residual) if self.residual is not None else (0, 0)
         # batch statistics of the BatchNorm that consumes this output come out of the conv epilogue (tensor-core modes)
         part = 0
-        bn = self.bn_consumer
         if (c.tc and bn is not None and not (_lib.lib().tsr_get_tc_desc_mode() & 128)      # bit 7: separate statistics pass
                 and not self.relu and self.residual is None and bn.src.buf is self.out.buf
                 and bn.src.c0 == self.out.c0 and (c.training or bn.bn.running_mean is None)):
@@ -386,6 +425,8 @@ class BNReLUOp(Op):
         return (self.out.buf,)
 
     def fwd(self, c):
+        if self in c.folded:
+            return
         st = _lib.stream_ptr()
         bn, C = self.bn, self.src.C
         coef = torch.empty((4, C), dtype=torch.float32, device=c.device)
@@ -393,6 +434,9 @@ class BNReLUOp(Op):
         yp, yld = c.vptr(self.src)
         use_batch = c.training or bn.running_mean is None
         part = c.bn_partials.pop(self, None)
+        if use_batch and c.training and bn.track_running_stats and bn.running_mean is not None:
+            global _STATS_EPOCH
+            _STATS_EPOCH += 1
         if use_batch and part is not None:
             track = c.training and bn.track_running_stats and bn.running_mean is not None
             mom = 0.1 if bn.momentum is None else bn.momentum
@@ -535,6 +579,7 @@ def run_forward(prog: Program, x: torch.Tensor, training: bool, need_grad: bool,
     c = RunCtx(mode, B, H, W, x.device, training, need_grad)
     c.x = x
     c.conv_inputs = {op.src.buf for op in prog.ops if isinstance(op, ConvOp)}
+    c.keep_taps = keep_taps
     keep = need_grad or keep_taps
     last_use: Dict[Buf, int] = {}
     if not keep:
