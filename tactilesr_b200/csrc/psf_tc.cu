@@ -297,6 +297,9 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     const uint32_t ph = (uint32_t)(it & 1);
     const float alpha = ab[b * 3 + 0], beta = ab[b * 3 + 1], gamma = ab[b * 3 + 2];
 
+    // the previous sample's HR plane has left shared memory before store_plane_tiles overwrites it (the block_max
+    // barriers below order this wait against every other thread)
+    if (tid == 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     // ---- phase A1: depth max over this thread's chunks (loaded into registers one sample ahead); tables ----
     float lmax, lamax;
     plane_max(dreg, tid, lmax, lamax);
@@ -313,6 +316,17 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     // ---- phase A2: E tiles (K-major), depth tiles (MN-major: row = k, as in HBM) + contact bytes ----
     build_toeplitz_tiles(tab2, sm + OFF_E_HI, sm + OFF_E_LO, tid);
     store_plane_tiles(dreg, sD, thr, sm + OFF_X_HI, sm + OFF_X_LO, maskb, tid);
+    // Everything GEMM1 reads as K rows 100..111 meets the zero K-padding of E and must be finite, and the HR staging of
+    // the previous sample has been lying over the tiles: rows 100..103 of all four atoms, and -- rows 104..111 of an
+    // atom-0 are the first 8 rows of the following atom-1 -- the column chunks 5..7 of those rows, which no depth
+    // store covers (columns 104..127)
+    if (tid < 128) {
+      const int t4 = tid >> 5, r = 100 + ((tid >> 3) & 3), c = tid & 7;      // (tile half, atom) x row x 16-byte chunk
+      *reinterpret_cast<uint4*>(sm + (t4 >> 1) * TILE + (t4 & 1) * ATOM + r * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+    } else if (tid < 128 + 48) {
+      const int t = tid - 128, tile = t / 24, r = (t % 24) / 3, c = 5 + t % 3;
+      *reinterpret_cast<uint4*>(sm + tile * TILE + ATOM + r * 128 + ((c ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -328,8 +342,10 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     }
     // the next sample's plane: its loads stay in flight until the top of the next iteration
     if (b + (int)gridDim.x < B) load_plane(depth + (size_t)(b + gridDim.x) * N * N, tid, dreg);
-    // psf = alpha e(u) e(v)  (tPSFNet.py:83), written while GEMM1 runs: warp w owns rows u = w, w + 8, ...
-    if (psf) {
+    // psf = alpha e(u) e(v)  (tPSFNet.py:83): warp w owns rows u = u0 + w, u0 + w + 8, ...; rows 0..49 are written while
+    // GEMM1 runs, rows 50..98 while GEMM2 runs
+    auto write_psf = [&](int u0, int u1) {
+      if (!psf) return;
       float* pdst = psf + (size_t)b * 99 * 99;
       float ev[4];
 #pragma unroll
@@ -337,14 +353,15 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
         const int v = lane + 32 * c;
         ev[c] = v < 99 ? tab[v < 49 ? 49 - v : v - 49] : 0.f;
       }
-      for (int u = warp; u < 99; u += NT / 32) {
+      for (int u = u0 + warp; u < u1; u += NT / 32) {
         const float eu = tab[u < 49 ? 49 - u : u - 49];
         float* row = pdst + u * 99;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           if (lane + 32 * c < 99) row[lane + 32 * c] = alpha * (eu * ev[c]);
       }
-    }
+    };
+    write_psf(0, 50);
     mbar_wait(bar1, ph);
     tc_fence_after();
 
@@ -364,12 +381,16 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       }
       __syncwarp();
     }
+    write_psf(50, 99);
     mbar_wait(bar2, ph);
     tc_fence_after();
     // the T tiles are dead now: their memory holds (Ex_j(t) (t - 12 - 25 j)^2) and the half-row hand-over of the
     // backward statistics (both only needed when the backward hand-over `aux` is requested)
     float4* ex24 = reinterpret_cast<float4*>(sm + OFF_X_HI);
     float* xch = reinterpret_cast<float*>(sm + OFF_X_HI + 2048);
+    // ... and the finished HR plane (40 000 B, dense rows), which leaves for HBM as ONE bulk copy: a row per thread
+    // scattered straight to global memory costs 32 partial sectors per store instruction
+    float* hstage = reinterpret_cast<float*>(sm + OFF_X_HI + 8192);
     if (aux) {
       for (int i = tid; i < 4 * N; i += NT) {
         const int t = i >> 2, k = i & 3;
@@ -400,7 +421,7 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     m2 = block_max256(m2, red);
     // pass 2: fill, store HR, accumulate the degradation sums of this thread's row segment
     float rj[4] = {0.f, 0.f, 0.f, 0.f}, r2[4] = {0.f, 0.f, 0.f, 0.f}, rs = 0.f;
-    float* hdst = HR + (size_t)b * N * N + (size_t)m * N;
+    float* hdst = hstage + m * N;
 #pragma unroll 1
     for (int g = 0; g < 7; ++g) {
       const int cg = half * 7 + g;
@@ -453,6 +474,7 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       }
       p[0] += __shfl_xor_sync(0xffffffffu, p[0], 1);
       const float tot_w = warp_sum(m < N ? rs : 0.f);
+      fence_proxy_async();                              // the staged HR rows -> visible to the bulk-copy engine
       if (aux && half == 1 && m < N) {                  // upper column half -> lower-half thread of the same row
         float4* x4 = reinterpret_cast<float4*>(xch + m * AUX_ROW);
         x4[0] = make_float4(rj[0], rj[1], rj[2], rj[3]);
@@ -463,6 +485,12 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       if ((lane & 1) == 0) red[warp * 20 + (lane >> 1)] = p[0];
       if (lane == 0) red[warp * 20 + 16] = tot_w;
       __syncthreads();
+      if (tid == 32) {                                  // (all rows are staged: second __syncthreads above)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(HR + (size_t)b * N * N),
+                     "r"(base + OFF_X_HI + 8192u), "r"((uint32_t)(N * N * sizeof(float)))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
       if (tid < 16) {
         float s = 0.f, tot = 0.f;
 #pragma unroll
@@ -486,6 +514,7 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     tc_fence_after();
   }
 
+  if (tid == 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
