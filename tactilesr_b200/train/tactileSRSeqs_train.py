@@ -1,0 +1,42 @@
+"""Hot-path part of reference train/tactileSRSeqs_train.py: ``model_param_init`` (:43-59, the transplant of a trained
+single-frame model's two feature stacks into the 7-frame model) and the model / optimizer construction of ``main``
+(:62-77).  The trainer is the same ``Trainer_tactileSR`` (the reference imports it from train/tactileSR_train.py).
+
+Faithful to the reference's order of operations: the optimizer is built over the sequence model's *own* parameters
+BEFORE the transplant (:74 then :77), so the transplanted ``patternFeatureExtra_layer`` / ``forceFeatureExtra_layer``
+receive gradients but are never updated (frozen pre-trained feature extractors), while the per-frame heads,
+``inputContact_layer`` and ``output_layer`` train.  ``FusedAdam`` keeps that behaviour: parameters that never see a
+gradient are skipped exactly like ``torch.optim.Adam`` skips them.
+"""
+from __future__ import annotations
+
+import torch
+
+from ..model.tactileSR_model import TactileSR
+from ..optim import FusedAdam
+from .tactileSR_train import Trainer_tactileSR, eval_func  # noqa: F401  (same trainer / evaluation as the reference)
+
+
+def model_param_init(singleSR_config, seqsSR_config, seqsSR_model, device=None):
+    """reference :43-59.  ``seqsSR_config['load_checkpoint_dir']`` is a checkpoint written by the single-frame trainer
+    (ours or the reference's: same ``{'model': state_dict}`` layout)."""
+    device = device if device is not None else next(seqsSR_model.parameters()).device
+    checkpoint = torch.load(seqsSR_config["load_checkpoint_dir"], map_location=device, weights_only=False)
+    singleSR_model = TactileSR(scale_factor=singleSR_config["scale_factor"], seqsCnt=singleSR_config["seqsCnt"],
+                               axisCnt=singleSR_config["axisCnt"],
+                               patternFeatureExtraLayerCnt=singleSR_config["patternFeatureExtraLayerCnt"],
+                               forceFeatureExtraLayerCnt=singleSR_config["forceFeatureExtraLayerCnt"]).to(device)
+    singleSR_model.load_state_dict(checkpoint["model"], strict=False)
+    seqsSR_model.patternFeatureExtra_layer = singleSR_model.patternFeatureExtra_layer
+    seqsSR_model.forceFeatureExtra_layer = singleSR_model.forceFeatureExtra_layer
+    return seqsSR_model
+
+
+def build_model_and_optimizer(config, singleSR_config, device):
+    """reference main() :66-77: sequence model, Adam over ITS parameters, then the transplant."""
+    model = TactileSR(scale_factor=config["scale_factor"], seqsCnt=config["seqsCnt"], axisCnt=config["axisCnt"],
+                      patternFeatureExtraLayerCnt=config["patternFeatureExtraLayerCnt"],
+                      forceFeatureExtraLayerCnt=config["forceFeatureExtraLayerCnt"]).to(device)
+    optimizer = FusedAdam(model.parameters(), lr=config["lr"], weight_decay=config["weight_decay"])
+    model = model_param_init(singleSR_config, config, model, device)
+    return model, optimizer

@@ -136,3 +136,46 @@ def test_trainer_checkpoint_is_consumed_by_stock_adam(tmp_path):
     opt.step()
     worst = max(((p - q).abs().max() / q.abs().max().clamp_min(1e-12)).item() for p, q in zip(params, model.parameters()))
     assert worst < 5e-6, worst
+
+
+@pytest.mark.gpu
+def test_seqs_training_with_transplanted_stacks(tmp_path):
+    """train/tactileSRSeqs_train.py flow on the GPU: single-frame checkpoint -> 7-frame model with transplanted stacks ->
+    training steps.  As in the reference the optimizer was built before the transplant, so the transplanted stacks stay
+    bit-identical to the checkpoint while the heads / inputContact / output layers move, and the loss goes down."""
+    import tactilesr_b200 as tb
+    from tactilesr_b200.model import TactileSR
+    from tactilesr_b200.train.tactileSRSeqs_train import Trainer_tactileSR, build_model_and_optimizer
+    from tests.util import sr_inputs
+    tb.set_precision("fp16")
+    try:
+        dev = torch.device("cuda", 0)
+        single_cfg = dict(seqsCnt=1, axisCnt=3, HR_scale_num=10, scale_factor=10, patternFeatureExtraLayerCnt=6,
+                          forceFeatureExtraLayerCnt=1, lr=1e-3, weight_decay=1e-2)
+        torch.manual_seed(7)
+        single = TactileSR().to(dev)
+        ck = str(tmp_path / "epoch_50.pth")
+        torch.save({"model": single.state_dict()}, ck)
+        cfg = dict(single_cfg, seqsCnt=7, lr=1e-4, load_checkpoint_dir=ck)
+        torch.manual_seed(8)
+        model, opt = build_model_and_optimizer(cfg, single_cfg, dev)
+        ref_stack = {k: v.detach().clone() for k, v in model.patternFeatureExtra_layer.state_dict().items()}
+        head0 = model.inputContact_layer[0].weight.detach().clone()
+        g = torch.Generator().manual_seed(9)
+        loader = [(torch.rand(8, 21, 4, 4, generator=g) * 8, sr_inputs(8, 1, 50)[1]) for _ in range(2)] * 3
+        tr = Trainer_tactileSR(cfg, model=model, optimizer=opt, lr_scheduler=torch.optim.lr_scheduler.StepLR(opt, 2, 0.8),
+                               data_loader=loader, max_iters=100, log_period=10 ** 9, device=dev)
+        losses = []
+        for it in range(6):
+            tr.cur_iter = it
+            tr.train_one_iter()
+            losses.append(tr._loss_acc.item()); tr._loss_acc, tr._loss_cnt = None, 0
+        assert all(torch.isfinite(torch.tensor(losses)))
+        for k, v in model.patternFeatureExtra_layer.state_dict().items():
+            if "running" in k or "num_batches" in k:
+                continue            # BatchNorm statistics of the transplanted stacks do follow the new data
+            assert torch.equal(v, ref_stack[k]), k
+        assert not torch.equal(model.inputContact_layer[0].weight, head0)
+        assert model.patternFeatureExtra_layer[0].conv_3_1[0].weight.grad is not None
+    finally:
+        tb.set_precision("fp32")
