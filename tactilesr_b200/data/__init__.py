@@ -1,1 +1,2 @@
-from .srdataset import (TactileSRDataset, generate_seqs_sr_records, generate_sr_records, save_sr_dataset)  # noqa: F401
+from .srdataset import (DevicePrefetcher, TactileSRDataset, generate_seqs_sr_records, generate_sr_records,  # noqa: F401
+                        save_sr_dataset)

@@ -93,3 +93,36 @@ def test_batched_generation_equals_batch_one_loop(tmp_path):
     seqs = generate_seqs_sr_records(m, frames, depth, batch_size=5)
     assert seqs[0][0]["LR"].shape == (21, 4, 4) and list(seqs[0][0].keys()) == ["LR", "depth", "HR"]
     assert torch.equal(seqs[3][0]["LR"][:3], frames[3, 6] / 100) and torch.equal(seqs[3][0]["LR"][18:], frames[3, 0] / 100)
+
+
+@pytest.mark.gpu
+def test_device_prefetcher_yields_the_same_batches():
+    from tactilesr_b200.data import DevicePrefetcher
+    g = torch.Generator().manual_seed(1)
+    batches = [(torch.rand(4, 3, 4, 4, generator=g).pin_memory(), torch.rand(4, 1, 100, 100, generator=g).pin_memory())
+               for _ in range(5)]
+    got = list(DevicePrefetcher(batches, "cuda:0"))
+    assert len(got) == 5
+    for (a, b), (c, d) in zip(batches, got):
+        assert c.is_cuda and torch.equal(a, c.cpu()) and torch.equal(b, d.cpu())
+
+
+@pytest.mark.gpu
+def test_c_abi_error_paths():
+    """Bad arguments come back as error codes with a message (no crash, no silent fallback)."""
+    from tactilesr_b200 import TsrError, _lib
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.zeros(1, 40, 40, 64, dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros(9 * 64 * 64, dtype=torch.bfloat16, device="cuda")
+    o = torch.zeros(1, 40, 40, 64, dtype=torch.bfloat16, device="cuda")
+    rc = L.tsr_conv2d_tc(x.data_ptr(), 64, w.data_ptr(), 0, 0, 0, o.data_ptr(), 64, 1, 40, 40, 64, 32, 3, 0, 0, 0, 0, st)
+    assert rc == 1 and b"Cout" in L.tsr_last_error()
+    rc = L.tsr_conv2d_tc(x.data_ptr(), 64, w.data_ptr(), 0, 0, 0, o.data_ptr(), 64, 1, 40, 40, 64, 64, 7, 0, 0, 0, 0, st)
+    assert rc == 1 and b"kernel size" in L.tsr_last_error()
+    with pytest.raises(TsrError):
+        _lib.call("tsr_psf_forward", 0, 0, 0, 0, 0, 4, st)
+    dw = torch.zeros(64, 64, 3, 3, device="cuda")
+    rc = L.tsr_conv2d_wgrad_tc(x.data_ptr(), 64, o.data_ptr(), 64, dw.data_ptr(), w.data_ptr(), 16, 1, 40, 40, 64, 64, 3, 0, st)
+    assert rc == 4 and b"workspace" in L.tsr_last_error()
+    torch.cuda.synchronize()
