@@ -28,15 +28,13 @@ namespace {
 constexpr int FLAG_RELU = 1;
 constexpr int FLAG_F16 = 2;          // activations / weights / residual / output are fp16 instead of bf16
 constexpr int T_TILES = 2;          // M-tiles (128 pixels each) per CTA
-constexpr int NB_STAGES = 3;        // weight ring depth
 constexpr int MAX_NA = 8;           // activation chunk slots (2 for 3x3 / 5x5, more for the bandwidth-bound 1x1)
 constexpr int NUM_THREADS = 224;
 constexpr int STAT_ROWS = 148 * 4;  // rows of the fused BatchNorm-statistics partials: (CTA, epilogue warp)
 
-// experiment switches (env TSR_TC_MODE or tsr_set_tc_desc_mode): bit0 = descriptor base_offset from the address
-// (wrong on B200: the swizzle phase is taken from the absolute smem address), bit1 = 16-pixel halo pitch in the forward
-// kernel instead of the dense TMA-box pitch, bit2 = v1 weight-gradient kernel (tall-plane blocks, per-row TMA),
-// bit3 = N=64 weight-gradient tiles only, bit4 = single-CTA (cta_group::1) forward kernel also for N = 128,
+// experiment switches (env TSR_TC_MODE or tsr_set_tc_desc_mode): bit1 = 16-pixel halo pitch in the forward kernel
+// instead of the dense TMA-box pitch, bit4 = single-CTA (cta_group::1) forward kernel also for N = 128, bit5 = the same
+// for N = 64,
 // bit7 = (engine) BatchNorm statistics in a separate pass instead of the conv epilogue.
 static int env_mode() { const char* e = getenv("TSR_TC_MODE"); return e ? atoi(e) : 0; }
 int g_desc_mode = env_mode();
@@ -49,7 +47,7 @@ struct ConvParams {
   int res_ld, out_ld;
   int B, H, W, Hp, Vtotal;       // Hp = H + pad, Vtotal = B * Hp
   int KS, pad, P, rows;          // P = smem pixel pitch of a halo row, rows = 16*T + 2*pad
-  int nchunks, nxg, flags, desc_mode;
+  int nchunks, nxg, flags;
   int w_tile_elems;              // elements between consecutive (chunk, tap) weight tiles = Cout_total * 64
   int nblocks, nb_stages;        // CTA blocks (persistent loop), depth of the weight ring (<= MAX_NB)
   int na_slots;                  // activation chunk slots (<= MAX_NA)
@@ -639,306 +637,16 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, T* __restri
 // ------------------------------------------------------------------------------------------------
 // weight gradient on the tensor cores:
 //   dW[tap][ci][co] = sum_pix x[pix + shift(tap)][ci] * dy[pix][co]
-// as D[M = co][N = 64 ci] += A[M][K = pixels] * B[N][K]^T with BOTH operands MN-major: a shared-memory row is one
-// pixel's 64 channels (128 B, SWIZZLE_128B) -- exactly the image the forward kernel's TMA boxes produce -- so the same
-// halo tile serves every tap through a shifted descriptor start address, and K = 16 pixels per MMA are two 8-pixel
-// core groups one virtual row apart.  A CTA owns (tap group of <= 8 taps) x (one 64-channel ci chunk) x (a contiguous
-// range of pixel blocks); its <= 8 x 64 fp32 accumulator columns stay in TMEM across the whole pixel range and are
-// written once, as a partial [split][tap][ci][co], which wgrad_reduce sums in a fixed order (deterministic two-level
-// reduction, same second level as the fp32 path).
+// with BOTH operands MN-major: a shared-memory row is one pixel's 64 channels (128 B, SWIZZLE_128B) -- exactly the image
+// the forward kernel's TMA boxes produce -- so one x halo tile (8x8 pixels + halo of ONE sample, one dense TMA box)
+// serves every tap through a shifted descriptor start address, and K = 16 pixels per MMA are two 8-pixel core groups one
+// halo row apart.  A CTA owns a set of M-groups x (a contiguous range of pixel tiles); its accumulators stay in TMEM
+// across the whole range and are written once, as a partial [split][tap][ci][co], which wgrad_tc_reduce_kernel sums in a
+// fixed order (deterministic two-level reduction, same second level as the fp32 path).
 // ------------------------------------------------------------------------------------------------
-constexpr int WG_STAGES = 3;
-constexpr int WG_MAX_TAPS = 8;
-
-struct WgradParams {
-  float* partial;               // [nsplit][taps][Cin][Cout]
-  int B, H, W, Hp, Vtotal;
-  int KS, pad, P, rows;         // rows = 16 + 2*pad halo rows per block
-  int Cin, Cout, cochunks;      // cochunks = Cout / 64
-  int ngroups, nchunks, nxg;
-  int nblocks, blocks_per_split;
-  int dy_stage_bytes, stage_bytes;
-};
-
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
-                const WgradParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = base + WG_STAGES * (uint32_t)p.stage_bytes;
-  auto full = [&](int i) { return bar_base + 8u * i; };
-  auto empty = [&](int i) { return bar_base + 8u * (WG_STAGES + i); };
-  const uint32_t tmem_full = bar_base + 8u * (2 * WG_STAGES);
-  const uint32_t tmem_slot = tmem_full + 8u;
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // blockIdx.x -> (tap group, ci chunk); blockIdx.y -> pixel split
-  const int grp = blockIdx.x % p.ngroups, chunk = blockIdx.x / p.ngroups;
-  const int taps = p.KS * p.KS;
-  const int tbase = taps / p.ngroups, trem = taps % p.ngroups;    // balanced tap groups (<= 8 taps each)
-  const int tap0 = grp * tbase + min(grp, trem);
-  const int ntap = tbase + (grp < trem ? 1 : 0);
-  const int blk0 = blockIdx.y * p.blocks_per_split;
-  const int blk1 = min(blk0 + p.blocks_per_split, p.nblocks);
-  const int nblk = max(blk1 - blk0, 0);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
-    mbar_init(tmem_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t x_row_bytes = (uint32_t)(8 + 2 * p.pad) * 128u;
-      const uint32_t tx = x_row_bytes * p.rows + 16u * 1024u * p.cochunks;
-      for (int i = 0; i < nblk; ++i) {
-        const int st = i % WG_STAGES;
-        mbar_wait(empty(st), ((i / WG_STAGES) & 1) ^ 1);
-        mbar_expect_tx(full(st), tx);
-        const int b = blk0 + i;
-        const int xg = b % p.nxg, vb = b / p.nxg;
-        const int x0 = xg * 8, v0 = vb * 16;
-        const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
-        const uint32_t xs0 = dy0 + (uint32_t)p.dy_stage_bytes;
-        for (int r = 0; r < 16; ++r) {
-          const int vr = v0 + r;
-          int n = 0, y = p.H;
-          if (vr < p.Vtotal) { n = vr / p.Hp; y = vr - n * p.Hp; }
-          for (int cc = 0; cc < p.cochunks; ++cc)
-            tma_load_4d(dy0 + (uint32_t)cc * 16384u + (uint32_t)r * 1024u, &tmap_dy, cc * 64, x0, y, n, full(st));
-        }
-        for (int r = 0; r < p.rows; ++r) {
-          const int vr = v0 - p.pad + r;
-          int n = 0, y = p.H;
-          if (vr >= 0 && vr < p.Vtotal) { n = vr / p.Hp; y = vr - n * p.Hp; }
-          tma_load_4d(xs0 + (uint32_t)r * p.P * 128u, &tmap_x, chunk * 64, x0 - p.pad, y, n, full(st));
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // A = dy (M = co, MN-major; two 64-channel atoms LBO = 16 KB apart when Cout = 128; for Cout = 64 the second
-      // atom aliases the first (LBO = 0): accumulator rows 64..127 are duplicates and are never read back).
-      const uint32_t idesc = make_idesc(128, 64, 1, 1);
-      const uint32_t lbo_a = p.cochunks == 2 ? 16384u : 0u;
-      const uint32_t sbo_x = (uint32_t)p.P * 128u;
-      for (int i = 0; i < nblk; ++i) {
-        const int st = i % WG_STAGES;
-        mbar_wait(full(st), (i / WG_STAGES) & 1);
-        tc_fence_after();
-        const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
-        const uint32_t xs0 = dy0 + (uint32_t)p.dy_stage_bytes;
-        for (int g = 0; g < ntap; ++g) {
-          const int t = tap0 + g;
-          const int ky = t / p.KS, kx = t - ky * p.KS;
-#pragma unroll
-          for (int s = 0; s < 8; ++s) {
-            const uint64_t ad = make_desc(dy0 + (uint32_t)s * 2048u, 1024u, lbo_a, 0);
-            const uint64_t bd = make_desc(xs0 + (uint32_t)((2 * s + ky) * p.P + kx) * 128u, sbo_x, 0u, 0);
-            umma_bf16(tmem_base + g * 64, ad, bd, idesc, (i | s) != 0 ? 1u : 0u);
-          }
-        }
-        umma_commit(empty(st));
-      }
-      umma_commit(tmem_full);
-    }
-  } else if (warp >= 3) {
-    if (nblk > 0) {
-      mbar_wait(tmem_full, 0);
-      tc_fence_after();
-      const int q = warp & 3;
-      const int co = q * 32 + lane;
-      if (co < p.Cout) {
-        for (int g = 0; g < ntap; ++g) {
-          float* dst = p.partial + (((size_t)blockIdx.y * taps + tap0 + g) * p.Cin + (size_t)chunk * 64) * p.Cout + co;
-#pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            uint32_t v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + g * 64 + j * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 16; ++k) dst[(size_t)(j * 16 + k) * p.Cout] = __uint_as_float(v[k]);
-          }
-        }
-      }
-      tc_fence_before();
-    } else {
-      // empty split: its partial slice must still be defined for the fixed-order reduction
-      const int q = warp & 3;
-      const int co = q * 32 + lane;
-      if (co < p.Cout)
-        for (int g = 0; g < ntap; ++g) {
-          float* dst = p.partial + (((size_t)blockIdx.y * taps + tap0 + g) * p.Cin + (size_t)chunk * 64) * p.Cout + co;
-          for (int k = 0; k < 64; ++k) dst[(size_t)k * p.Cout] = 0.f;
-        }
-    }
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
-  }
-}
-
-// ---- v2: per-sample 8x8 pixel tiles, ONE dense TMA box per operand tile, deeper ring -------------------------
-// A stage is one 8x8 tile of one sample: dy box {64 co, 8, 8, 1} per co chunk (8 KB each) and the x halo box
-// {64 ci, 8+2pad, 8+2pad, 1} (dense pitch P = 8+2pad pixels; out-of-image pixels are TMA zero fill).  K = 64 pixels
-// = 4 MMA K-steps of two 8-pixel groups one row apart.
 constexpr int WG2_MAX_STAGES = 8;
 
-struct Wgrad2Params {
-  float* partial;               // [nsplit][taps][Cin][Cout]
-  int B, H, W, KS, pad, P;
-  int Cin, Cout, cochunks;
-  int ngroups, nchunks;
-  int tiles_x, tiles_per_sample, nblocks, blocks_per_split;
-  int dy_stage_bytes, stage_bytes, nstages;
-  int nch, xtile_bytes;         // 64-channel ci chunks per CTA (1 or 2 => MMA N = 64 or 128), bytes of one x halo tile
-};
-
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
-                 const Wgrad2Params p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int NS = p.nstages;
-  const uint32_t bar_base = base + NS * (uint32_t)p.stage_bytes;
-  auto full = [&](int i) { return bar_base + 8u * i; };
-  auto empty = [&](int i) { return bar_base + 8u * (WG2_MAX_STAGES + i); };
-  const uint32_t tmem_full = bar_base + 8u * (2 * WG2_MAX_STAGES);
-  const uint32_t tmem_slot = tmem_full + 8u;
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = blockIdx.x % p.ngroups, chunk = blockIdx.x / p.ngroups;
-  const int taps = p.KS * p.KS;
-  const int tbase = taps / p.ngroups, trem = taps % p.ngroups;      // balanced tap groups
-  const int tap0 = grp * tbase + min(grp, trem);
-  const int ntap = tbase + (grp < trem ? 1 : 0);
-  const int blk0 = blockIdx.y * p.blocks_per_split;
-  const int blk1 = min(blk0 + p.blocks_per_split, p.nblocks);
-  const int nblk = max(blk1 - blk0, 0);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
-    mbar_init(tmem_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t tx = (uint32_t)p.P * p.P * 128u * p.nch + 8192u * p.cochunks;
-      for (int i = 0; i < nblk; ++i) {
-        const int st = i % NS;
-        mbar_wait(empty(st), ((i / NS) & 1) ^ 1);
-        mbar_expect_tx(full(st), tx);
-        const int b = blk0 + i;
-        const int n = b / p.tiles_per_sample, t = b - n * p.tiles_per_sample;
-        const int y0 = (t / p.tiles_x) * 8, x0 = (t % p.tiles_x) * 8;
-        const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
-        for (int cc = 0; cc < p.cochunks; ++cc)
-          tma_load_4d(dy0 + (uint32_t)cc * 8192u, &tmap_dy, cc * 64, x0, y0, n, full(st));
-        for (int h = 0; h < p.nch; ++h)
-          tma_load_4d(dy0 + (uint32_t)p.dy_stage_bytes + (uint32_t)h * p.xtile_bytes, &tmap_x, (chunk * p.nch + h) * 64,
-                      x0 - p.pad, y0 - p.pad, n, full(st));
-      }
-    }
-  } else if (warp == 1) {
-    {
-      const int NN = 64 * p.nch;
-      const uint32_t idesc = make_idesc(128, NN, 1, 1);
-      const uint32_t lbo_a = p.cochunks == 2 ? 8192u : 0u;     // Cout = 64: second MN atom aliases the first
-      const uint32_t a_hi = desc_hi(1024u), b_hi = desc_hi((uint32_t)p.P * 128u);
-      const uint32_t row_units = (uint32_t)p.P * 8u;
-      const uint32_t wrap_units = row_units - (uint32_t)p.KS * 8u;
-      const uint32_t tap_start = (uint32_t)((tap0 / p.KS) * p.P + tap0 % p.KS) * 8u;
-      const int kx_start = tap0 % p.KS;
-      uint32_t first = 0u;
-      for (int i = 0; i < nblk; ++i) {
-        const int st = i % NS;
-        mbar_wait(full(st), (i / NS) & 1);
-        tc_fence_after();
-        const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
-        const uint32_t a_lo = desc_lo(dy0, lbo_a);
-        uint32_t b_lo = desc_lo(dy0 + (uint32_t)p.dy_stage_bytes, (uint32_t)p.xtile_bytes) + tap_start;
-        int kx = kx_start;
-        const bool leader = elect_one();
-        for (int g = 0; g < ntap; ++g) {
-          if (leader) {
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-              // K-step s: dy rows 2s, 2s+1 (2 KB apart per step); x window rows 2s+ky, 2s+1+ky
-              umma_bf16(tmem_base + g * NN, desc_join(a_lo + s * 128u, a_hi), desc_join(b_lo + s * 2u * row_units, b_hi), idesc,
-                        (first | (uint32_t)s) ? 1u : 0u);
-            }
-          }
-          b_lo += 8u;
-          if (++kx == p.KS) { kx = 0; b_lo += wrap_units; }
-        }
-        first = 1u;
-        if (leader) umma_commit(empty(st));
-        __syncwarp();
-      }
-      if (elect_one()) umma_commit(tmem_full);
-      __syncwarp();
-    }
-  } else if (warp >= 3) {
-    const int q = warp & 3;
-    const int co = q * 32 + lane;
-    if (nblk > 0) {
-      mbar_wait(tmem_full, 0);
-      tc_fence_after();
-      if (q * 32 < p.Cout) {
-        const int NN = 64 * p.nch;
-        for (int g = 0; g < ntap; ++g) {
-          float* dst = p.partial + (((size_t)blockIdx.y * taps + tap0 + g) * p.Cin + (size_t)chunk * NN) * p.Cout + co;
-#pragma unroll 1
-          for (int j = 0; j < NN / 16; ++j) {
-            uint32_t v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + g * NN + j * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 16; ++k) dst[(size_t)(j * 16 + k) * p.Cout] = __uint_as_float(v[k]);
-          }
-        }
-      }
-      tc_fence_before();
-    } else if (co < p.Cout) {
-      for (int g = 0; g < ntap; ++g) {
-        float* dst = p.partial + (((size_t)blockIdx.y * taps + tap0 + g) * p.Cin + (size_t)chunk * 64 * p.nch) * p.Cout + co;
-        for (int k = 0; k < 64 * p.nch; ++k) dst[(size_t)k * p.Cout] = 0.f;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
-  }
-}
-
-// ---- v3: operand roles swapped so that no accumulator row is wasted --------------------------------------------
+// Operand roles chosen so that no accumulator row is wasted:
 // D[M = 128 rows of ci][N = Cout] += A(x window, MN-major) * B(dy, MN-major)^T.  The two 64-row atoms of the A operand
 // are LBO bytes apart, and LBO is free: for Cin % 128 == 0 they are the two channel chunks of one tap (LBO = halo tile
 // size); otherwise they are TWO DIFFERENT TAPS of the same chunk (LBO = byte distance of the two windows inside the one
@@ -1313,7 +1021,7 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
   p.B = B; p.H = H; p.W = W; p.Hp = H + pad; p.Vtotal = B * (H + pad);
   // halo pitch: dense (8 + 2*pad pixels, the TMA box width) unless desc-mode bit 1 asks for the 16-pixel pitch
   p.KS = KS; p.pad = pad; p.P = (g_desc_mode & 2) ? (pad ? 16 : 8) : 8 + 2 * pad; p.rows = 16 * T_TILES + 2 * pad;
-  p.nchunks = Cin / 64; p.nxg = W / 8; p.flags = flags; p.desc_mode = g_desc_mode;
+  p.nchunks = Cin / 64; p.nxg = W / 8; p.flags = flags;
   p.w_tile_elems = Cout * 64;
   const int nvb = tsr_cdiv(p.Vtotal, 16 * T_TILES);
   p.nblocks = nvb * p.nxg;
@@ -1339,9 +1047,6 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
   return TSR_OK;
 }
 
-static int wgrad_nch(int Cin) { return (!(g_desc_mode & 4) && !(g_desc_mode & 8) && Cin % 128 == 0) ? 2 : 1; }
-static bool wgrad_v3() { return !(g_desc_mode & 4) && !(g_desc_mode & 64); }
-
 struct Wgrad3Plan { int tap_mode, ngroups_total, gpc, ncta_groups, nunits; };
 static Wgrad3Plan wgrad3_plan(int Cin, int Cout, int KS) {
   Wgrad3Plan q;
@@ -1355,28 +1060,12 @@ static Wgrad3Plan wgrad3_plan(int Cin, int Cout, int KS) {
   return q;
 }
 
-static void wgrad_plan(int B, int H, int W, int Cin, int Cout, int KS, int* ngroups, int* nsplit, int* nblocks,
-                       int* bps) {
-  const int taps = KS * KS;
-  int ctas;
-  if (wgrad_v3()) {
-    Wgrad3Plan q = wgrad3_plan(Cin, Cout, KS);
-    *ngroups = q.ncta_groups;
-    *nblocks = B * (H / 8) * (W / 8);
-    ctas = q.ncta_groups * q.nunits;
-  } else {
-    const int nch = wgrad_nch(Cin);
-    const int max_taps = WG_MAX_TAPS / nch;          // TMEM: taps * 64 * nch <= 512 columns
-    *ngroups = (taps + max_taps - 1) / max_taps;
-    if (g_desc_mode & 4) {        // v1 kernel: tall-plane 8x16 blocks
-      const int pad = KS / 2;
-      *nblocks = tsr_cdiv(B * (H + pad), 16) * (W / 8);
-    } else {                      // v2 kernel: per-sample 8x8 tiles
-      *nblocks = B * (H / 8) * (W / 8);
-    }
-    ctas = *ngroups * (Cin / (64 * nch));
-  }
-  int s = num_sms() / ctas;     // a single wave: never more CTAs than SMs
+// pixel-tile split: a single wave, never more CTAs than SMs
+static void wgrad_plan(int B, int H, int W, int Cin, int Cout, int KS, int* nsplit, int* nblocks, int* bps) {
+  Wgrad3Plan q = wgrad3_plan(Cin, Cout, KS);
+  *nblocks = B * (H / 8) * (W / 8);
+  const int ctas = q.ncta_groups * q.nunits;
+  int s = num_sms() / ctas;
   if (s > *nblocks) s = *nblocks;
   if (s < 1) s = 1;
   *bps = tsr_cdiv(*nblocks, s);
@@ -1384,8 +1073,8 @@ static void wgrad_plan(int B, int H, int W, int Cin, int Cout, int KS, int* ngro
 }
 
 size_t tsr_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS) {
-  int ng, ns, nb, bps;
-  wgrad_plan(B, H, W, Cin, Cout, KS, &ng, &ns, &nb, &bps);
+  int ns, nb, bps;
+  wgrad_plan(B, H, W, Cin, Cout, KS, &ns, &nb, &bps);
   return (size_t)ns * KS * KS * Cin * Cout * sizeof(float);
 }
 
@@ -1397,14 +1086,13 @@ int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld
   TSR_REQUIRE(Cout == 64 || Cout == 128, "conv2d_wgrad_tc: Cout must be 64 or 128 (got %d)", Cout);
   TSR_REQUIRE(Cin % 64 == 0 && Cin > 0, "conv2d_wgrad_tc: Cin must be a multiple of 64 (got %d)", Cin);
   TSR_REQUIRE(KS == 1 || KS == 3 || KS == 5, "conv2d_wgrad_tc: kernel size %d unsupported", KS);
-  TSR_REQUIRE(W % 8 == 0, "conv2d_wgrad_tc: W must be a multiple of 8");
+  TSR_REQUIRE(W % 8 == 0 && H % 8 == 0, "conv2d_wgrad_tc: H and W must be multiples of 8");
   TSR_REQUIRE(in_ld % 8 == 0 && dout_ld % 8 == 0, "conv2d_wgrad_tc: row strides must be multiples of 8");
   EncodeTiledFn enc = get_encode();
   if (!enc) { tsr_set_error("conv2d_wgrad_tc: cuTensorMapEncodeTiled unavailable"); return TSR_ERR_CUDA; }
   const int pad = KS / 2, taps = KS * KS;
-  WgradParams p;
-  int nsplit = 1;
-  wgrad_plan(B, H, W, Cin, Cout, KS, &p.ngroups, &nsplit, &p.nblocks, &p.blocks_per_split);
+  int nsplit = 1, nblocks = 0, bps = 0;
+  wgrad_plan(B, H, W, Cin, Cout, KS, &nsplit, &nblocks, &bps);
   size_t need = (size_t)nsplit * taps * Cin * Cout * sizeof(float);
   if (ws_bytes < need) { tsr_set_error("conv2d_wgrad_tc: workspace too small (%zu < %zu)", ws_bytes, need); return TSR_ERR_WORKSPACE; }
   CUtensorMap tmx, tmdy;
@@ -1412,7 +1100,7 @@ int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld
   {
     cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)in_ld * 2, (cuuint64_t)W * in_ld * 2, (cuuint64_t)H * W * in_ld * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)(8 + 2 * pad), (g_desc_mode & 4) ? 1u : (cuuint32_t)(8 + 2 * pad), 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)(8 + 2 * pad), (cuuint32_t)(8 + 2 * pad), 1};
     CUresult r = enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1421,69 +1109,32 @@ int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld
   {
     cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)dout_ld * 2, (cuuint64_t)W * dout_ld * 2, (cuuint64_t)H * W * dout_ld * 2};
-    cuuint32_t box[4] = {64, 8, (g_desc_mode & 4) ? 1u : 8u, 1};
+    cuuint32_t box[4] = {64, 8, 8, 1};
     CUresult r = enc(&tmdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dout), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { tsr_set_error("conv2d_wgrad_tc: tensor map (dy) failed (%d)", (int)r); return TSR_ERR_CUDA; }
   }
-  if (g_desc_mode & 4) {
-    p.partial = (float*)workspace;
-    p.B = B; p.H = H; p.W = W; p.Hp = H + pad; p.Vtotal = B * (H + pad);
-    p.KS = KS; p.pad = pad; p.P = pad ? 16 : 8; p.rows = 16 + 2 * pad;
-    p.Cin = Cin; p.Cout = Cout; p.cochunks = Cout / 64;
-    p.nchunks = Cin / 64; p.nxg = W / 8;
-    p.dy_stage_bytes = 16 * 1024 * p.cochunks;
-    p.stage_bytes = p.dy_stage_bytes + p.rows * p.P * 128;
-    size_t smem = 1024 + (size_t)WG_STAGES * p.stage_bytes + 256;
-    TSR_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(p.ngroups * p.nchunks, nsplit);
-    wgrad_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmx, tmdy, p);
-    TSR_CHECK_LAUNCH("conv2d_wgrad_tc");
-  } else if (wgrad_v3()) {
-    TSR_REQUIRE(H % 8 == 0, "conv2d_wgrad_tc: H must be a multiple of 8");
-    Wgrad3Plan pl = wgrad3_plan(Cin, Cout, KS);
-    Wgrad3Params q;
-    q.partial = (float*)workspace;
-    q.B = B; q.H = H; q.W = W; q.KS = KS; q.pad = pad; q.P = 8 + 2 * pad;
-    q.Cin = Cin; q.Cout = Cout; q.cochunks = Cout / 64;
-    q.tap_mode = pl.tap_mode; q.ngroups_total = pl.ngroups_total; q.gpc = pl.gpc;
-    q.ncta_groups = pl.ncta_groups; q.nunits = pl.nunits;
-    q.tiles_x = W / 8; q.tiles_per_sample = (H / 8) * (W / 8);
-    q.nblocks = p.nblocks; q.blocks_per_split = p.blocks_per_split;
-    q.dy_stage_bytes = 8192 * q.cochunks;
-    q.xtile_bytes = (q.P * q.P * 128 + 1023) & ~1023;
-    q.stage_bytes = q.dy_stage_bytes + (pl.tap_mode ? 1 : 2) * q.xtile_bytes;
-    int ns = (int)((SMEM_LIMIT - 1024 - 512) / (size_t)q.stage_bytes);
-    if (ns > WG2_MAX_STAGES) ns = WG2_MAX_STAGES;
-    q.nstages = ns;
-    size_t smem = 1024 + (size_t)ns * q.stage_bytes + 512;
-    TSR_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(q.ncta_groups * q.nunits, nsplit);
-    wgrad_tc3_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmx, tmdy, q);
-    TSR_CHECK_LAUNCH("conv2d_wgrad_tc3");
-  } else {
-    TSR_REQUIRE(H % 8 == 0, "conv2d_wgrad_tc: H must be a multiple of 8");
-    Wgrad2Params q;
-    q.partial = (float*)workspace;
-    q.B = B; q.H = H; q.W = W; q.KS = KS; q.pad = pad; q.P = 8 + 2 * pad;
-    q.Cin = Cin; q.Cout = Cout; q.cochunks = Cout / 64;
-    q.nch = wgrad_nch(Cin);
-    q.ngroups = p.ngroups; q.nchunks = Cin / (64 * q.nch);
-    q.tiles_x = W / 8; q.tiles_per_sample = (H / 8) * (W / 8);
-    q.nblocks = p.nblocks; q.blocks_per_split = p.blocks_per_split;
-    q.dy_stage_bytes = 8192 * q.cochunks;
-    q.xtile_bytes = (q.P * q.P * 128 + 1023) & ~1023;
-    q.stage_bytes = q.dy_stage_bytes + q.nch * q.xtile_bytes;
-    int ns = (int)((SMEM_LIMIT - 1024 - 512) / (size_t)q.stage_bytes);
-    if (ns > WG2_MAX_STAGES) ns = WG2_MAX_STAGES;
-    q.nstages = ns;
-    size_t smem = 1024 + (size_t)ns * q.stage_bytes + 512;
-    TSR_CUDA(cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(q.ngroups * q.nchunks, nsplit);
-    wgrad_tc2_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmx, tmdy, q);
-    TSR_CHECK_LAUNCH("conv2d_wgrad_tc2");
-  }
+  Wgrad3Plan pl = wgrad3_plan(Cin, Cout, KS);
+  Wgrad3Params q;
+  q.partial = (float*)workspace;
+  q.B = B; q.H = H; q.W = W; q.KS = KS; q.pad = pad; q.P = 8 + 2 * pad;
+  q.Cin = Cin; q.Cout = Cout; q.cochunks = Cout / 64;
+  q.tap_mode = pl.tap_mode; q.ngroups_total = pl.ngroups_total; q.gpc = pl.gpc;
+  q.ncta_groups = pl.ncta_groups; q.nunits = pl.nunits;
+  q.tiles_x = W / 8; q.tiles_per_sample = (H / 8) * (W / 8);
+  q.nblocks = nblocks; q.blocks_per_split = bps;
+  q.dy_stage_bytes = 8192 * q.cochunks;
+  q.xtile_bytes = (q.P * q.P * 128 + 1023) & ~1023;
+  q.stage_bytes = q.dy_stage_bytes + (pl.tap_mode ? 1 : 2) * q.xtile_bytes;
+  int ns = (int)((SMEM_LIMIT - 1024 - 512) / (size_t)q.stage_bytes);
+  if (ns > WG2_MAX_STAGES) ns = WG2_MAX_STAGES;
+  q.nstages = ns;
+  size_t smem = 1024 + (size_t)ns * q.stage_bytes + 512;
+  TSR_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(q.ncta_groups * q.nunits, nsplit);
+  wgrad_tc3_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmx, tmdy, q);
+  TSR_CHECK_LAUNCH("conv2d_wgrad_tc3");
   long long n = (long long)taps * Cin * Cout;
   wgrad_tc_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>((const float*)workspace, dw_oihw, nsplit, taps, Cin,
                                                                     Cout, accumulate);

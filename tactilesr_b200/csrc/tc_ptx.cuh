@@ -85,17 +85,8 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major / MN-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [49,52) base offset, [61,64) layout=2
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t lbo_bytes, int mode) {
-  uint64_t d = (uint64_t)((addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= 1ull << 46;
-  if (mode == 1) d |= (uint64_t)((addr >> 7) & 7) << 49;
-  d |= 2ull << 61;
-  return d;
-}
-
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [49,52) base offset (always 0 here: measured on B200,
+// the swizzle phase of TMA and UMMA follows the absolute shared-memory address), [61,64) layout=2 (SWIZZLE_128B).
 // The issuing thread is a single lane: every ALU instruction in its loop costs ~4 cycles of dependent issue, so the
 // descriptors are split into a constant high word and a low word that only ever needs an integer add.
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
