@@ -128,7 +128,8 @@ def run_reference(args):
     if rank != 0:
         return
     B = 32
-    steps, warmup = max(1, min(args.steps, 4)), max(1, min(args.warmup, 1))
+    # bounded sample: every step is one batch of the reference's own size (0.7 s on 16 cores), at most 20 steps
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
     val, cores = cpu_reference_steps(B, steps, warmup)
     line = {
         "impl": "reference", "metric": "SR train samples/sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
@@ -409,9 +410,9 @@ def run_ours(args):
                 "frac": value / world * FLOP_PER_SAMPLE_TRAIN / 1e12 / pk["tf_sust"], "peak_source": pk["src"] + " bf16 sustained", "traffic": None}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, cores = cpu_reference_steps(32, 3, 1)
+        v, cores = cpu_reference_steps(32, 12, 1)
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": "3 train steps of B=32 (reference batch size, config/default.py:46) after 1 warm-up; oracle port of the reference CPU path"}
+               "sample": "12 train steps of B=32 (reference batch size, config/default.py:46) after 1 warm-up; oracle port of the reference CPU path"}
     line = {
         "metric": "SR train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
