@@ -376,7 +376,11 @@ def run_ours(args):
 
     extras = {}
     if world == 1 and not args.no_extras:
-        extras = measure_extras(dev, model, B)
+        try:                                  # reported extras must never take the headline line down with them
+            extras = measure_extras(dev, model, B)
+        except Exception as e:                # noqa: BLE001
+            extras = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.synchronize()
         if args.precision != "bf16":          # the all-bf16 mode on the same trainer, for comparison
             tb.set_precision("bf16")
             tr._data_iter = iter(Loader(devb))
