@@ -161,7 +161,7 @@ def time_dominant_kernel(B, reps=10, f16=False):
     flags = 2 if f16 else 0
 
     def launch():
-        _lib.call("tsr_conv2d_tc", x.data_ptr(), 128, wf.data_ptr(), 0, 0, 0, out.data_ptr(), 128, B, 40, 40, 128, 128, 5, flags, 0, 0, 0, st)
+        _lib.call("tsr_conv2d_tc", x.data_ptr(), 128, wf.data_ptr(), 0, 0, 0, out.data_ptr(), 128, B, 40, 40, 128, 128, 5, flags, 0, 0, 0, 0, 0, st)
     for _ in range(3):
         launch()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

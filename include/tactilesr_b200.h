@@ -188,7 +188,9 @@ size_t tsr_conv2d_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS);
    flags bit 1 (value 2): in / weights / residual / out are fp16 instead of bf16 (same kernels, kind::f16 format field). */
 int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* bias, const void* residual, int res_ld,
                   void* out, int out_ld, int B, int H, int W, int Cin, int Cout, int KS, int flags, void* workspace,
-                  size_t ws_bytes, float* bn_partial, tsr_stream_t stream);
+                  size_t ws_bytes, float* bn_partial, void* out2_bf16, int out2_ld, tsr_stream_t stream);
+/* out2_bf16 (may be NULL): a second copy of the result as bf16 with row stride out2_ld (weight-gradient operand kept by the
+   "fp16" precision mode). */
 /* bn_partial (may be NULL): [tsr_conv2d_tc_stat_rows()][2][Cout] floats receiving partial sums / sums of squares of the
    stored output from the epilogue (batch statistics of the BatchNorm that follows, nn.BatchNorm2d at
    tactileSR_model.py:42,48,169,...); finish them with tsr_bn_finalize_partials. */

@@ -71,7 +71,7 @@ SIGNATURES = {
     "tsr_pack_conv_weight_bf16": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "tsr_pack_conv_weight_f16": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "tsr_pack_conv_weight_folded": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "tsr_conv2d_tc": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P, _P]),
+    "tsr_conv2d_tc": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P, _P, _I, _P]),
     "tsr_conv2d_tc_stat_rows": (_I, []),
     "tsr_conv2d_tc_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),
     "tsr_conv2d_wgrad_tc": (_I, [_P, _I, _P, _I, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -51,6 +51,8 @@ struct ConvParams {
   int w_tile_elems;              // elements between consecutive (chunk, tap) weight tiles = Cout_total * 64
   int nblocks, nb_stages;        // CTA blocks (persistent loop), depth of the weight ring (<= MAX_NB)
   int na_slots;                  // activation chunk slots (<= MAX_NA)
+  __nv_bfloat16* out2;           // optional second, bf16 copy of an fp16 output [pix][out2_ld] (weight-gradient operand of
+  int out2_ld;                   // the "fp16" precision mode), else null
   float* bn_partial;             // optional [STAT_ROWS][2][bn_C] per-(CTA, epilogue warp) sums / sums of squares of the
   int bn_C;                      // stored output (BatchNorm batch statistics fused into the epilogue), else null
 };
@@ -304,6 +306,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
             uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_ld + j * 16);
             op[0] = make_uint4(o[0], o[1], o[2], o[3]);
             op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            if (p.out2) {
+              uint32_t o2[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                o2[k] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              uint4* op2 = reinterpret_cast<uint4*>(p.out2 + pix * p.out2_ld + j * 16);
+              op2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+              op2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
+            }
           }
           if (p.bn_partial)      // (warp-uniform: all 32 lanes take part in the shuffles)
             bn_stats_accumulate(o, valid, (p.flags & FLAG_F16) != 0, p.bn_partial, p.bn_C, (int)blockIdx.x * 4 + q, j * 16, lane);
@@ -585,6 +598,17 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_ld + j * 16);
             op[0] = make_uint4(o[0], o[1], o[2], o[3]);
             op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            if (p.out2) {
+              uint32_t o2[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                o2[k] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              uint4* op2 = reinterpret_cast<uint4*>(p.out2 + pix * p.out2_ld + j * 16);
+              op2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+              op2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
+            }
           }
           if (p.bn_partial)      // (warp-uniform: all 32 lanes take part in the shuffles)
             bn_stats_accumulate(o, valid, (p.flags & FLAG_F16) != 0, p.bn_partial, p.bn_C, (int)blockIdx.x * 4 + q, j * 16, lane);
@@ -983,6 +1007,8 @@ size_t tsr_conv2d_tc_workspace(int, int, int, int, int, int) { return 0; }
 
 // bf16 NHWC convolution on the tensor cores.  in: [B*H*W][in_ld] (Cin channels from `in`), w_packed from
 // tsr_pack_conv_weight_bf16, bias fp32 [Cout] or NULL, residual bf16 [pix][res_ld] or NULL, out bf16.
+// out2_bf16 (may be NULL): a second copy of the result rounded to bf16, row stride out2_ld (the "fp16" precision mode keeps
+// it as the weight-gradient operand of the next convolution).
 // bn_partial (may be NULL): [tsr_conv2d_tc_stat_rows()][2][Cout] floats that receive per-(CTA, warp) partial sums and sums of
 // squares of the stored output -- the batch statistics of a BatchNorm that consumes this convolution, finished by
 // tsr_bn_finalize_partials without another pass over the tensor.
@@ -990,8 +1016,9 @@ int tsr_conv2d_tc_stat_rows(void) { return STAT_ROWS; }
 
 int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* bias, const void* residual,
                   int res_ld, void* out, int out_ld, int B, int H, int W, int Cin, int Cout, int KS, int flags,
-                  void* workspace, size_t ws_bytes, float* bn_partial, cudaStream_t stream) {
+                  void* workspace, size_t ws_bytes, float* bn_partial, void* out2_bf16, int out2_ld, cudaStream_t stream) {
   (void)workspace; (void)ws_bytes;
+  TSR_REQUIRE(!out2_bf16 || (out2_ld % 8 == 0 && ((uintptr_t)out2_bf16 & 15) == 0), "conv2d_tc: second output must be 16-byte aligned with a row stride that is a multiple of 8");
   if (bn_partial) TSR_CUDA(cudaMemsetAsync(bn_partial, 0, (size_t)STAT_ROWS * 2 * Cout * sizeof(float), stream));
   TSR_REQUIRE(in && w_packed && out, "conv2d_tc: null pointer");
   TSR_REQUIRE(Cout % 64 == 0 && Cout > 0, "conv2d_tc: Cout must be a multiple of 64 (got %d)", Cout);
@@ -1032,6 +1059,8 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
     p.bias = bias ? bias + n0 : nullptr;
     p.residual = residual ? (const __nv_bfloat16*)residual + n0 : nullptr;
     p.out = (__nv_bfloat16*)out + n0;
+    p.out2 = out2_bf16 ? (__nv_bfloat16*)out2_bf16 + n0 : nullptr;
+    p.out2_ld = out2_ld;
     p.bn_partial = bn_partial ? bn_partial + n0 : nullptr;
     p.bn_C = Cout;
     int rc;

@@ -10,23 +10,32 @@
 
 namespace {
 
-// Second-level reduction shared by the finalising kernels: block = (32 channels, 32 partial-row lanes); returns, for
-// threadIdx.y == 0, the fixed-order double sums over all level-1 partial rows of quantities 0 and 1 of channel c.
+// Second-level reduction shared by the finalising kernels: block = (FIN_CH channels, FIN_LANES partial-row lanes), i.e. few
+// channels and many row lanes per block, so that the <= 592 partial rows are two or three loads per thread and the kernel is
+// not one long dependent load chain; returns, for threadIdx.y == 0, the fixed-order double sums over all level-1
+// partial rows of quantities 0 and 1 of channel c (fixed-order tree => deterministic).
+constexpr int FIN_CH = 8, FIN_LANES = 128;
 __device__ __forceinline__ void reduce_partials2(const float* __restrict__ partial, int nblocks, int C, int c,
                                                  double& s0, double& s1) {
-  __shared__ double sh[2][32][33];
+  __shared__ double sh[2][FIN_LANES][FIN_CH + 1];
   double a = 0.0, b = 0.0;
   if (c < C)
-    for (int r = threadIdx.y; r < nblocks; r += 32) {
+    for (int r = threadIdx.y; r < nblocks; r += FIN_LANES) {
       a += (double)partial[((long long)r * 2 + 0) * C + c];
       b += (double)partial[((long long)r * 2 + 1) * C + c];
     }
   sh[0][threadIdx.y][threadIdx.x] = a;
   sh[1][threadIdx.y][threadIdx.x] = b;
   __syncthreads();
-  s0 = 0.0; s1 = 0.0;
-  if (threadIdx.y == 0)
-    for (int r = 0; r < 32; ++r) { s0 += sh[0][r][threadIdx.x]; s1 += sh[1][r][threadIdx.x]; }
+  for (int o = FIN_LANES / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.y < o) {
+      sh[0][threadIdx.y][threadIdx.x] += sh[0][threadIdx.y + o][threadIdx.x];
+      sh[1][threadIdx.y][threadIdx.x] += sh[1][threadIdx.y + o][threadIdx.x];
+    }
+    __syncthreads();
+  }
+  s0 = sh[0][0][threadIdx.x];
+  s1 = sh[1][0][threadIdx.x];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -67,7 +76,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblock
                                    long long* __restrict__ nbt, float momentum, float eps,
                                    float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int c = blockIdx.x * FIN_CH + threadIdx.x;
   if (c == 0 && threadIdx.y == 0 && nbt) *nbt += 1;
   double s, ss;
   reduce_partials2(partial, nblocks, C, c, s, ss);
@@ -172,7 +181,7 @@ __global__ void bn_bwd_partial_kernel(const Tg* __restrict__ da, int da_ld, cons
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double n,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
                                        float* __restrict__ c1, float* __restrict__ c2, int training) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int c = blockIdx.x * FIN_CH + threadIdx.x;
   double s, sx;
   reduce_partials2(partial, nblocks, C, c, s, sx);
   if (c >= C || threadIdx.y != 0) return;
@@ -687,7 +696,7 @@ int tsr_bn_train_stats(const void* y, int y_ld, int y_bf16, long long npix, int 
     TSR_DISPATCH_T(y_bf16, T, bn_stats_partial_kernel<T><<<nb, th, smem, stream>>>((const T*)y, y_ld, (int)npix, C, (float*)workspace, rpb));
   }
   TSR_CHECK_LAUNCH("bn_stats_partial");
-  bn_finalize_kernel<<<tsr_cdiv(C, 32), dim3(32, 32), 0, stream>>>((const float*)workspace, nb, C, (double)npix, gamma, beta,
+  bn_finalize_kernel<<<tsr_cdiv(C, FIN_CH), dim3(FIN_CH, FIN_LANES), 0, stream>>>((const float*)workspace, nb, C, (double)npix, gamma, beta,
                                                            running_mean, running_var, num_batches_tracked, momentum,
                                                            eps, scale, shift, save_mean, save_invstd);
   TSR_CHECK_LAUNCH("bn_finalize");
@@ -702,7 +711,7 @@ int tsr_bn_finalize_partials(const float* partial, int nrows, long long npix, in
                              cudaStream_t stream) {
   TSR_REQUIRE(partial && gamma && beta && scale && shift && save_mean && save_invstd && nrows > 0 && npix > 0,
               "bn_finalize_partials: bad argument");
-  bn_finalize_kernel<<<tsr_cdiv(C, 32), dim3(32, 32), 0, stream>>>(partial, nrows, C, (double)npix, gamma, beta, running_mean,
+  bn_finalize_kernel<<<tsr_cdiv(C, FIN_CH), dim3(FIN_CH, FIN_LANES), 0, stream>>>(partial, nrows, C, (double)npix, gamma, beta, running_mean,
                                                            running_var, num_batches_tracked, momentum, eps, scale, shift,
                                                            save_mean, save_invstd);
   TSR_CHECK_LAUNCH("bn_finalize");
@@ -791,7 +800,7 @@ int tsr_bn_backward(const void* da, int da_ld, const void* y, int y_ld, void* dy
       bn_bwd_partial_kernel<float, float><<<nb, th, smem, stream>>>((const float*)da, da_ld, (const float*)y, y_ld, scale, shift, save_mean, save_invstd, (int)npix, C, relu, partial, rpb);
   }
   TSR_CHECK_LAUNCH("bn_bwd_partial");
-  bn_bwd_finalize_kernel<<<tsr_cdiv(C, 32), dim3(32, 32), 0, stream>>>(partial, nb, C, (double)npix, dgamma, dbeta, accumulate, c1, c2, training);
+  bn_bwd_finalize_kernel<<<tsr_cdiv(C, FIN_CH), dim3(FIN_CH, FIN_LANES), 0, stream>>>(partial, nb, C, (double)npix, dgamma, dbeta, accumulate, c1, c2, training);
   TSR_CHECK_LAUNCH("bn_bwd_finalize");
   int grid = ew_grid(npix * (C / 4));
   if (v8 && act_bf16 == TSR_DT_F16)

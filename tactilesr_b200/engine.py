@@ -311,7 +311,7 @@ class ConvOp(Op):
         return (self.out.buf,)
 
     def _conv(self, c: RunCtx, inp, inld, wpk, bias, res, resld, outp, outld, Cin, Cout, flags, on_grads=False,
-              bn_partial=0):
+              bn_partial=0, out2=0, out2_ld=0):
         st = _lib.stream_ptr()
         if c.tc:
             need = _lib.lib().tsr_conv2d_tc_workspace(c.B, c.H, c.W, Cin, Cout, self.K)
@@ -319,7 +319,7 @@ class ConvOp(Op):
             if c.act == 2 and not on_grads:
                 flags |= 2      # fp16 activations / weights (forward); data gradients run on bf16 tensors
             _lib.call("tsr_conv2d_tc", inp, inld, wpk, bias, res, resld, outp, outld, c.B, c.H, c.W, Cin, Cout,
-                      self.K, flags, ws, wsb, bn_partial, st)
+                      self.K, flags, ws, wsb, bn_partial, out2, out2_ld, st)
         else:
             _lib.call("tsr_conv2d_f32", inp, inld, wpk, bias, res, resld, outp, outld, c.B, c.H, c.W, Cin, Cout,
                       self.K, flags, st)
@@ -354,9 +354,13 @@ class ConvOp(Op):
             t = torch.empty((_lib.lib().tsr_conv2d_tc_stat_rows(), 2, self.Cout), dtype=torch.float32, device=c.device)
             c.bn_partials[bn] = t
             part = t.data_ptr()
-        self._conv(c, ip, ild, wf.data_ptr(), _ptr(self.conv.bias), rp, rld, op, old, self.Cin, self.Cout,
-                   1 if self.relu else 0, bn_partial=part)
-        c.shadow_fill(self.out)
+        if c.tc and c.wants_shadow(self.out.buf):     # bf16 shadow of an fp16 output straight from the epilogue
+            o2, o2ld = c.sptr(self.out)
+            self._conv(c, ip, ild, wf.data_ptr(), _ptr(self.conv.bias), rp, rld, op, old, self.Cin, self.Cout,
+                       1 if self.relu else 0, bn_partial=part, out2=o2, out2_ld=o2ld)
+        else:
+            self._conv(c, ip, ild, wf.data_ptr(), _ptr(self.conv.bias), rp, rld, op, old, self.Cin, self.Cout,
+                       1 if self.relu else 0, bn_partial=part)
 
     def bwd(self, c):
         st = _lib.stream_ptr()

@@ -116,9 +116,9 @@ def test_c_abi_error_paths():
     x = torch.zeros(1, 40, 40, 64, dtype=torch.bfloat16, device="cuda")
     w = torch.zeros(9 * 64 * 64, dtype=torch.bfloat16, device="cuda")
     o = torch.zeros(1, 40, 40, 64, dtype=torch.bfloat16, device="cuda")
-    rc = L.tsr_conv2d_tc(x.data_ptr(), 64, w.data_ptr(), 0, 0, 0, o.data_ptr(), 64, 1, 40, 40, 64, 32, 3, 0, 0, 0, 0, st)
+    rc = L.tsr_conv2d_tc(x.data_ptr(), 64, w.data_ptr(), 0, 0, 0, o.data_ptr(), 64, 1, 40, 40, 64, 32, 3, 0, 0, 0, 0, 0, 0, st)
     assert rc == 1 and b"Cout" in L.tsr_last_error()
-    rc = L.tsr_conv2d_tc(x.data_ptr(), 64, w.data_ptr(), 0, 0, 0, o.data_ptr(), 64, 1, 40, 40, 64, 64, 7, 0, 0, 0, 0, st)
+    rc = L.tsr_conv2d_tc(x.data_ptr(), 64, w.data_ptr(), 0, 0, 0, o.data_ptr(), 64, 1, 40, 40, 64, 64, 7, 0, 0, 0, 0, 0, 0, st)
     assert rc == 1 and b"kernel size" in L.tsr_last_error()
     with pytest.raises(TsrError):
         _lib.call("tsr_psf_forward", 0, 0, 0, 0, 0, 4, st)

@@ -39,13 +39,13 @@ def test_tc_conv_fwd_dgrad_wgrad_against_fp32(Cin, Cout, KS, B):
     _lib.call("tsr_pack_conv_weight_bf16", w.data_ptr(), wf.data_ptr(), wd.data_ptr(), Cout, Cin, KS, st)
     out = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
     _lib.call("tsr_conv2d_tc", x.data_ptr(), Cin, wf.data_ptr(), bias.data_ptr(), res.data_ptr(), Cout, out.data_ptr(), Cout,
-              B, H, W, Cin, Cout, KS, 1, 0, 0, 0, st)
+              B, H, W, Cin, Cout, KS, 1, 0, 0, 0, 0, 0, st)
     ref = torch.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wb, bias, padding=KS // 2).permute(0, 2, 3, 1) + res.float())
     assert rel_l2(out.float(), ref) < 4e-3          # bf16 rounding of the stored output
     dy = torch.randn(B, H, W, Cout, device=dev).to(torch.bfloat16)
     if Cin in (64, 128):
         dx = torch.zeros(B, H, W, Cin, dtype=torch.bfloat16, device=dev)
-        _lib.call("tsr_conv2d_tc", dy.data_ptr(), Cout, wd.data_ptr(), 0, 0, 0, dx.data_ptr(), Cin, B, H, W, Cout, Cin, KS, 0, 0, 0, 0, st)
+        _lib.call("tsr_conv2d_tc", dy.data_ptr(), Cout, wd.data_ptr(), 0, 0, 0, dx.data_ptr(), Cin, B, H, W, Cout, Cin, KS, 0, 0, 0, 0, 0, 0, st)
         refd = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wb, padding=KS // 2).permute(0, 2, 3, 1)
         assert rel_l2(dx.float(), refd) < 4e-3
     need = L.tsr_conv2d_wgrad_tc_workspace(B, H, W, Cin, Cout, KS)
@@ -172,7 +172,7 @@ def test_tc_conv_fp16_forward(Cin, Cout, KS, B):
     _lib.call("tsr_pack_conv_weight_f16", w.data_ptr(), wf.data_ptr(), 0, Cout, Cin, KS, st)
     out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=dev)
     _lib.call("tsr_conv2d_tc", x.data_ptr(), Cin, wf.data_ptr(), bias.data_ptr(), res.data_ptr(), Cout, out.data_ptr(), Cout,
-              B, H, W, Cin, Cout, KS, 1 | 2, 0, 0, 0, st)
+              B, H, W, Cin, Cout, KS, 1 | 2, 0, 0, 0, 0, 0, st)
     ref = torch.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wh, bias, padding=KS // 2).permute(0, 2, 3, 1) + res.float())
     e = rel_l2(out.float(), ref)
     assert e < 5e-4, e                              # fp16 rounding of the stored output (2^-12 per element)
@@ -278,7 +278,7 @@ def test_tc_conv_fused_bn_statistics(Cout, KS, B, f16):
         out = torch.zeros(B, H, W, Cout, dtype=dt, device=dev)
         part = torch.full((rows, 2, Cout), 7.0, device=dev)       # the call must clear it
         _lib.call("tsr_conv2d_tc", x.data_ptr(), Cin, wf.data_ptr(), bias.data_ptr(), 0, 0, out.data_ptr(), Cout,
-                  B, H, W, Cin, Cout, KS, 2 if f16 else 0, 0, 0, part.data_ptr(), st)
+                  B, H, W, Cin, Cout, KS, 2 if f16 else 0, 0, 0, part.data_ptr(), 0, 0, st)
         outs.append((out, part))
     out, part = outs[0]
     assert torch.equal(part, outs[1][1]) and torch.equal(out, outs[1][0])

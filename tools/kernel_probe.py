@@ -16,7 +16,7 @@ dw = torch.empty_like(w)
 _lib.call("tsr_pack_conv_weight_bf16", w.data_ptr(), wf.data_ptr(), 0, Cout, Cin, KS, st)
 ws = torch.empty(max(int(L.tsr_conv2d_wgrad_tc_workspace(B, 40, 40, Cin, Cout, KS)), 256), dtype=torch.uint8, device="cuda")
 if which == "fwd":
-    f = lambda: _lib.call("tsr_conv2d_tc", x.data_ptr(), Cin, wf.data_ptr(), 0, 0, 0, out.data_ptr(), Cout, B, 40, 40, Cin, Cout, KS, 0, 0, 0, 0, st)
+    f = lambda: _lib.call("tsr_conv2d_tc", x.data_ptr(), Cin, wf.data_ptr(), 0, 0, 0, out.data_ptr(), Cout, B, 40, 40, Cin, Cout, KS, 0, 0, 0, 0, 0, 0, st)
 else:
     f = lambda: _lib.call("tsr_conv2d_wgrad_tc", x.data_ptr(), Cin, dy.data_ptr(), Cout, dw.data_ptr(), ws.data_ptr(), ws.numel(), B, 40, 40, Cin, Cout, KS, 0, st)
 for _ in range(3):

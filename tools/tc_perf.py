@@ -12,7 +12,7 @@ for (Cin, Cout, KS) in [(128, 128, 5), (128, 128, 3), (64, 64, 5), (64, 64, 3), 
     wf = torch.empty(KS * KS * Cin * Cout, dtype=torch.bfloat16, device="cuda")
     out = torch.empty(B * 1600, Cout, dtype=torch.bfloat16, device="cuda")
     _lib.call("tsr_pack_conv_weight_bf16", w.data_ptr(), wf.data_ptr(), 0, Cout, Cin, KS, st)
-    f = lambda: _lib.call("tsr_conv2d_tc", x.data_ptr(), Cin, wf.data_ptr(), 0, 0, 0, out.data_ptr(), Cout, B, 40, 40, Cin, Cout, KS, 0, 0, 0, 0, st)
+    f = lambda: _lib.call("tsr_conv2d_tc", x.data_ptr(), Cin, wf.data_ptr(), 0, 0, 0, out.data_ptr(), Cout, B, 40, 40, Cin, Cout, KS, 0, 0, 0, 0, 0, 0, st)
     for _ in range(3): f()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()

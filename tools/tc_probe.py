@@ -29,7 +29,7 @@ def case(KS, Cin, Cout, B, mode, H=40, W=40, flags=0):
     _lib.call("tsr_pack_conv_weight_bf16", w.data_ptr(), wf.data_ptr(), wd.data_ptr(), Cout, Cin, KS, st)
     out = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
     _lib.call("tsr_conv2d_tc", x.data_ptr(), Cin, wf.data_ptr(), bias.data_ptr(), res.data_ptr(), Cout, out.data_ptr(), Cout,
-              B, H, W, Cin, Cout, KS, 1, 0, 0, 0, st)
+              B, H, W, Cin, Cout, KS, 1, 0, 0, 0, 0, 0, st)
     torch.cuda.synchronize()
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wb, bias, padding=KS // 2).permute(0, 2, 3, 1) + res.float()
     ref = torch.relu(ref)
@@ -39,7 +39,7 @@ def case(KS, Cin, Cout, B, mode, H=40, W=40, flags=0):
     dx = torch.zeros(B, H, W, Cin, dtype=torch.bfloat16, device=dev)
     err2 = -1.0
     if Cin in (64, 128):
-        _lib.call("tsr_conv2d_tc", dy.data_ptr(), Cout, wd.data_ptr(), 0, 0, 0, dx.data_ptr(), Cin, B, H, W, Cout, Cin, KS, 0, 0, 0, 0, st)
+        _lib.call("tsr_conv2d_tc", dy.data_ptr(), Cout, wd.data_ptr(), 0, 0, 0, dx.data_ptr(), Cin, B, H, W, Cout, Cin, KS, 0, 0, 0, 0, 0, 0, st)
         torch.cuda.synchronize()
         refd = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), wb, padding=KS // 2).permute(0, 2, 3, 1)
         err2 = ((dx.float() - refd).norm() / refd.norm()).item()
