@@ -52,3 +52,40 @@ def test_graphed_training_is_bit_identical_to_eager(mode):
     for k in sd0:
         assert torch.equal(sd0[k], sd1[k]), k
     assert float(osd["state"][0]["step"]) == 7.0
+
+
+def test_graph_training_interleaved_with_eager_evaluation():
+    """Cache-invalidation check: graph-replayed training changes weights and BatchNorm statistics without running any
+    Python, while evaluation in between runs eagerly with BatchNorm folded into cached packed weights.  The interleaved
+    sequence must produce exactly the evaluation outputs of an all-eager run."""
+    import tactilesr_b200 as tb
+    from tactilesr_b200.train.tactileSR_train import Trainer_tactileSR, build_model_and_optimizer
+    outs = []
+    try:
+        for use_graph in (False, True):
+            tb.set_precision("fp16")
+            torch.manual_seed(42)
+            dev = torch.device("cuda", 0)
+            from oracle import tactilesr_oracle as so
+            cfg = dict(CFG, lr=2e-5)
+            model, opt = build_model_and_optimizer(cfg, dev)
+            model.load_state_dict(so.make_state(so.tactilesr_layout(1), 5), strict=True)   # every ReLU path alive
+            loader = [sr_inputs(8, 1, 400 + i) for i in range(8)]
+            tr = Trainer_tactileSR(cfg, model=model, optimizer=opt, lr_scheduler=torch.optim.lr_scheduler.StepLR(opt, 1, 0.9),
+                                   data_loader=loader, max_iters=100, log_period=10 ** 9, device=dev, cuda_graph=use_graph)
+            x = sr_inputs(5, 1, 999)[0].cuda()
+            evals = []
+            for it in range(8):
+                tr.cur_iter = it
+                model.train()
+                tr.train_one_iter()
+                if it in (3, 4, 7):
+                    model.eval()
+                    with torch.no_grad():
+                        evals.append(model(x).clone())
+            outs.append(evals)
+    finally:
+        tb.set_precision("fp32")
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    assert not torch.equal(outs[0][0], outs[0][1])      # the weights did move between evaluations

@@ -186,3 +186,40 @@ def test_trainer_tpsf_graph_and_eager_agree():
         assert torch.equal(a, b)
     mse, ssim = eval_func(model, data[:2], cfg)
     assert mse > 0 and -1.0 <= ssim <= 1.0
+
+
+def test_psf_kernels_size_independent_properties():
+    """Properties at a large ragged batch (B = 5000: 17 samples per CTA in the persistent loops): (a) permuting the batch
+    permutes the results bit for bit (forward and backward); (b) doubling alpha doubles HR, LR_degrade and psf exactly
+    (every scaling on the path is a power of two); (c) results do not depend on the launch's batch size."""
+    from oracle import tpsf_oracle as po
+    from tactilesr_b200 import _lib
+    L = _lib.lib()
+    B = 5000
+    g = torch.Generator().manual_seed(77)
+    ab = torch.stack([torch.rand(B, generator=g) + 0.3, torch.rand(B, generator=g) * 2 + 0.3,
+                      torch.rand(B, generator=g) * 20 + 0.5], 1).cuda().contiguous()
+    depth = po.synthetic_depth(32, 9).repeat((B + 31) // 32, 1, 1)[:B].cuda().contiguous()
+    dL = torch.randn(B, 16, generator=g).cuda().contiguous()
+    st = torch.cuda.current_stream().cuda_stream
+    naux = int(L.tsr_psf_aux_floats())
+
+    def run(ab_, depth_, dL_):
+        n = ab_.shape[0]
+        HR = torch.empty(n, 100, 100, device="cuda"); LRd = torch.empty(n, 16, device="cuda"); psf = torch.empty(n, 99, 99, device="cuda")
+        aux = torch.empty(n, naux, device="cuda"); dab = torch.empty(n, 3, device="cuda")
+        _lib.call("tsr_psf_forward_tc", ab_.data_ptr(), depth_.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), aux.data_ptr(), n, st)
+        _lib.call("tsr_psf_backward_tc", ab_.data_ptr(), depth_.data_ptr(), aux.data_ptr(), dL_.data_ptr(), dab.data_ptr(), n, st)
+        return HR, LRd, psf, dab
+    HR, LRd, psf, dab = run(ab, depth, dL)
+    assert all(torch.isfinite(t).all() for t in (HR, LRd, psf, dab))
+    perm = torch.randperm(B, generator=g).cuda()
+    HRp, LRdp, psfp, dabp = run(ab[perm].contiguous(), depth[perm].contiguous(), dL[perm].contiguous())
+    assert torch.equal(HRp, HR[perm]) and torch.equal(LRdp, LRd[perm]) and torch.equal(psfp, psf[perm]) and torch.equal(dabp, dab[perm])
+    ab2 = ab.clone(); ab2[:, 0] *= 2
+    HR2, LRd2, psf2, _ = run(ab2, depth, dL)
+    assert torch.equal(HR2, 2 * HR) and torch.equal(LRd2, 2 * LRd)
+    big = psf > 1e-30                       # (below, alpha * e(u) e(v) is rounded on the subnormal grid: doubling is not exact)
+    assert torch.equal(psf2[big], 2 * psf[big]) and torch.allclose(psf2, 2 * psf, rtol=0, atol=1e-37)
+    HRs, LRds, _, dabs = run(ab[:37].contiguous(), depth[:37].contiguous(), dL[:37].contiguous())
+    assert torch.equal(HRs, HR[:37]) and torch.equal(LRds, LRd[:37]) and torch.equal(dabs, dab[:37])
