@@ -176,6 +176,16 @@ int tsr_psf_backward(const float* alphaBeta, const float* depth, const float* HR
  * transposed set for the data gradient.  Cin, Cout % 64 == 0. */
 int tsr_pack_conv_weight_bf16(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int KS,
                               tsr_stream_t stream);
+/* every conv weight of a model in one launch (they all change at each optimizer step): a device-memory table of */
+typedef struct TsrPackDesc {
+  const float* w;   /* OIHW fp32 */
+  void* wf;         /* forward image or NULL */
+  void* wd;         /* data-gradient image or NULL */
+  int Cout, Cin, KS;
+  int dt_f, dt_d;   /* storage codes of wf / wd: 1 = bf16, 2 = fp16 */
+  int pad_;
+} TsrPackDesc;
+int tsr_pack_conv_weights_multi(const void* table_dev, int n, long long max_elems, tsr_stream_t stream);
 /* same packing with fp16 elements: forward weights of the "fp16" precision mode (fp16 activations, bf16 gradients) */
 int tsr_pack_conv_weight_f16(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int KS,
                              tsr_stream_t stream);

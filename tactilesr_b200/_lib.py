@@ -70,6 +70,7 @@ SIGNATURES = {
     # tensor-core (tcgen05) convolutions
     "tsr_pack_conv_weight_bf16": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "tsr_pack_conv_weight_f16": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "tsr_pack_conv_weights_multi": (_I, [_P, _I, _L, _P]),
     "tsr_pack_conv_weight_folded": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "tsr_conv2d_tc": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P, _P, _I, _P]),
     "tsr_conv2d_tc_stat_rows": (_I, []),

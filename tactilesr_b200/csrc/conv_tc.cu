@@ -658,6 +658,45 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, T* __restri
 }
 
 
+// All conv weights of a model in ONE launch (they all change at every optimizer step): blockIdx.y = table entry.
+struct PackDesc {          // mirrors TsrPackDesc of include/tactilesr_b200.h
+  const float* w;          // OIHW fp32
+  void* wf;                // forward image or null
+  void* wd;                // data-gradient image or null
+  int Cout, Cin, KS;
+  int dt_f, dt_d;          // storage codes of wf / wd: 1 = bf16, 2 = fp16
+  int pad_;
+};
+static_assert(sizeof(PackDesc) == 48, "TsrPackDesc layout");
+
+__device__ __forceinline__ void store16(void* base, long long idx, float v, int dt) {
+  if (dt == TSR_DT_F16) reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
+  else reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+}
+
+__global__ void pack_weights_multi_kernel(const PackDesc* __restrict__ table) {
+  const PackDesc e = table[blockIdx.y];
+  const int taps = e.KS * e.KS;
+  const long long n = (long long)e.Cout * e.Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const long long r = i / taps;
+    const int ci = (int)(r % e.Cin);
+    const int co = (int)(r / e.Cin);
+    const float v = e.w[i];
+    if (e.wf) {
+      const int c = ci >> 6, k = ci & 63;
+      const long long tile = ((long long)c * taps + t) * e.Cout * 64;
+      store16(e.wf, tile + (long long)co * 64 + (((k >> 3) ^ (co & 7)) << 3) + (k & 7), v, e.dt_f);
+    }
+    if (e.wd) {
+      const int c = co >> 6, k = co & 63;
+      const long long tile = ((long long)c * taps + (taps - 1 - t)) * e.Cin * 64;
+      store16(e.wd, tile + (long long)ci * 64 + (((k >> 3) ^ (ci & 7)) << 3) + (k & 7), v, e.dt_d);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // weight gradient on the tensor cores:
 //   dW[tap][ci][co] = sum_pix x[pix + shift(tap)][ci] * dy[pix][co]
@@ -960,6 +999,16 @@ int tsr_pack_conv_weight_bf16(const float* w_oihw, void* w_fwd, void* w_dgrad, i
   if (blocks > 2048) blocks = 2048;
   pack_weight_bf16_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(w_oihw, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad, Cout, Cin, KS);
   TSR_CHECK_LAUNCH("pack_conv_weight_bf16");
+  return TSR_OK;
+}
+
+// `n` table entries (TsrPackDesc, device memory) packed by one launch; max_elems = the largest Cout*Cin*KS*KS among them.
+int tsr_pack_conv_weights_multi(const void* table_dev, int n, long long max_elems, cudaStream_t stream) {
+  TSR_REQUIRE(table_dev && n > 0 && max_elems > 0, "pack_conv_weights_multi: bad argument");
+  int bx = (int)((max_elems + 255) / 256);
+  if (bx > 64) bx = 64;
+  pack_weights_multi_kernel<<<dim3(bx, n), 256, 0, stream>>>((const PackDesc*)table_dev);
+  TSR_CHECK_LAUNCH("pack_conv_weights_multi");
   return TSR_OK;
 }
 

@@ -172,6 +172,9 @@ class _PackCache:
     """Packed weights live on the Parameter object itself (``_tsr_pack``), so they die with it -- a process-wide dict
     keyed by id()/data_ptr would alias a freed parameter with a new one that reuses both."""
 
+    def __init__(self):
+        self._groups = {}      # (mode, ids of a program's conv weights) -> persistent buffers + device descriptor table
+
     def get(self, w: torch.Tensor, mode: str, need_dgrad: bool):
         tag = (w.data_ptr(), w._version, _WEIGHT_EPOCH, tuple(w.shape), w.device)
         store = w.__dict__.setdefault("_tsr_pack", {})
@@ -195,6 +198,54 @@ class _PackCache:
         store[mode] = (tag, wf, wd)
         return wf, wd
 
+
+    # -- all conv weights of a program in one launch ---------------------------------------------------------------
+    def prepack(self, weights, mode: str, need_dgrad: bool) -> None:
+        """Tensor-core modes: bring the packed images of every weight in ``weights`` up to date with ONE kernel launch
+        (the optimizer changes all of them at every step) and leave the per-parameter cache entries current, so the
+        ConvOps' ``get`` calls all hit.  Buffers and the device descriptor table are persistent per weight set."""
+        import numpy as np
+        key = (mode,) + tuple(id(w) for w in weights)
+        grp = self._groups.get(key)
+        if grp is not None and any(r() is None for r in grp["refs"]):
+            grp = None
+        if grp is None:
+            import weakref
+            grp = {"refs": [weakref.ref(w) for w in weights], "sig": None, "ptrs": None, "table": None, "bufs": [],
+                   "dgrad": False}
+            for k in [k for k, g in self._groups.items() if any(r() is None for r in g["refs"])]:
+                del self._groups[k]
+            self._groups[key] = grp
+        sig = (_WEIGHT_EPOCH, tuple(w._version for w in weights))
+        ptrs = tuple(w.data_ptr() for w in weights)
+        want_d = grp["dgrad"] or need_dgrad
+        if grp["sig"] == sig and grp["ptrs"] == ptrs and grp["dgrad"] == want_d:
+            return
+        dt_f = torch.float16 if mode == "fp16" else torch.bfloat16
+        if grp["table"] is None or grp["ptrs"] != ptrs or grp["dgrad"] != want_d:
+            desc = np.zeros(len(weights), dtype=np.dtype([("w", "<u8"), ("wf", "<u8"), ("wd", "<u8"), ("Cout", "<i4"),
+                                                          ("Cin", "<i4"), ("KS", "<i4"), ("dt_f", "<i4"), ("dt_d", "<i4"),
+                                                          ("pad", "<i4")]))
+            bufs = []
+            for i, w in enumerate(weights):
+                Cout, Cin, K, _ = w.shape
+                old = grp["bufs"][i] if i < len(grp["bufs"]) else (None, None)
+                wf = old[0] if old[0] is not None else torch.empty((K * K * Cin * Cout,), dtype=dt_f, device=w.device)
+                wd = old[1]
+                if want_d and wd is None:
+                    wd = torch.empty((K * K * Cin * Cout,), dtype=torch.bfloat16, device=w.device)
+                bufs.append((wf, wd))
+                assert w.is_contiguous()
+                desc[i] = (w.data_ptr(), wf.data_ptr(), 0 if wd is None else wd.data_ptr(), Cout, Cin, K,
+                           2 if mode == "fp16" else 1, 1, 0)
+            grp["bufs"], grp["dgrad"], grp["ptrs"] = bufs, want_d, ptrs
+            grp["table"] = torch.from_numpy(desc.view(np.uint8).copy()).to(weights[0].device)
+            grp["max"] = max(int(w.numel()) for w in weights)
+        _lib.call("tsr_pack_conv_weights_multi", grp["table"].data_ptr(), len(weights), grp["max"], _lib.stream_ptr())
+        grp["sig"] = sig
+        for w, (wf, wd) in zip(weights, grp["bufs"]):
+            tag = (w.data_ptr(), w._version, _WEIGHT_EPOCH, tuple(w.shape), w.device)
+            w.__dict__.setdefault("_tsr_pack", {})[mode] = (tag, wf, wd)
 
     def get_folded(self, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, mode: str):
         """Inference: forward pack of ``conv`` with the eval-mode BatchNorm ``bn`` folded in -> (packed weights, bias)."""
@@ -584,6 +635,14 @@ def run_forward(prog: Program, x: torch.Tensor, training: bool, need_grad: bool,
     c.x = x
     c.conv_inputs = {op.src.buf for op in prog.ops if isinstance(op, ConvOp)}
     c.keep_taps = keep_taps
+    if c.tc and (training or need_grad):
+        seen, ws = set(), []
+        for op in prog.ops:
+            if isinstance(op, ConvOp) and id(op.conv.weight) not in seen and op.conv.weight.is_contiguous():
+                seen.add(id(op.conv.weight))
+                ws.append(op.conv.weight)
+        if ws:
+            _PACK.prepack(ws, mode, need_grad)
     keep = need_grad or keep_taps
     last_use: Dict[Buf, int] = {}
     if not keep:
