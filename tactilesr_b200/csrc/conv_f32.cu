@@ -311,39 +311,42 @@ __device__ __forceinline__ void build_upsampled(const float* __restrict__ xs /*3
   }
 }
 
+// Persistent over samples; a thread owns one channel quad (16 quads) with its 27 x 4 weights in registers and strides over
+// the pixels (16 pixel lanes): per pixel 27 shared-memory reads of the upsampled frame (broadcast within the half-warp that
+// shares the pixel) feed 108 FMAs, and the 16 quads of a pixel store 64 contiguous channels.
 template <typename OutT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
 head_fwd_kernel(const float* __restrict__ x, long long x_bstride, const float* __restrict__ w /*64,3,3,3*/,
                 OutT* __restrict__ out, int out_ld, int B, int sf, int relu) {
   extern __shared__ float smem[];
-  float* ws = smem;              // [27][64]  (q = tap*3 + c)
-  float* xs = ws + 27 * 64;      // 48
+  float* xs = smem;              // 48
   float* up = xs + 48;           // (H+2)^2*3
   const int H = 4 * sf, P = H + 2;
-  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
-    int co = i & 63, q = i >> 6;
-    int tap = q / 3, c = q % 3;
-    ws[i] = w[(co * 3 + c) * 9 + tap];
-  }
+  const int g = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  float wr[27][4];               // [tap*3 + c][channel of the quad]
+#pragma unroll
+  for (int q = 0; q < 27; ++q)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wr[q][j] = w[((g * 4 + j) * 3 + q % 3) * 9 + q / 3];
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
     if (threadIdx.x < 48) xs[threadIdx.x] = x[(long long)b * x_bstride + threadIdx.x];
     __syncthreads();
     build_upsampled(xs, up, sf);
     __syncthreads();
-    for (int it = threadIdx.x; it < H * H * 16; it += blockDim.x) {
-      int g = it & 15, p = it >> 4;
-      int y = p / H, xx = p - y * H;
+    for (int p = pl; p < H * H; p += 16) {
+      const int y = p / H, xx = p - y * H;
+      const float* u0 = up + (y * P + xx) * 3;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        const float* u = up + ((y + tap / 3) * P + xx + tap % 3) * 3;
+        const float* u = u0 + ((tap / 3) * P + tap % 3) * 3;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          float a = u[c];
-          float4 wv = *reinterpret_cast<const float4*>(ws + (tap * 3 + c) * 64 + g * 4);
-          acc.x = fmaf(a, wv.x, acc.x); acc.y = fmaf(a, wv.y, acc.y);
-          acc.z = fmaf(a, wv.z, acc.z); acc.w = fmaf(a, wv.w, acc.w);
+          const float a = u[c];
+          const int q = tap * 3 + c;
+          acc.x = fmaf(a, wr[q][0], acc.x); acc.y = fmaf(a, wr[q][1], acc.y);
+          acc.z = fmaf(a, wr[q][2], acc.z); acc.w = fmaf(a, wr[q][3], acc.w);
         }
       }
       if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
@@ -353,52 +356,61 @@ head_fwd_kernel(const float* __restrict__ x, long long x_bstride, const float* _
 }
 
 // head weight gradient, level 1: one partial [27][64] per CTA, CTAs stride over samples.
-// 1024 threads = 64 output channels x 16 pixel lanes; a warp shares its pixel (the upsampled value is a shared-memory
-// broadcast) and reads 32 consecutive channels of dout (coalesced); each thread keeps all 27 (tap, axis) sums.
+// 512 threads = 16 channel quads x 32 pixel lanes; a thread keeps all 27 x 4 (tap, axis, channel) sums in registers, so a
+// pixel costs one 8/16-byte load of dout, 27 shared-memory reads of the upsampled frame and 108 FMAs.
 template <typename GT>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512, 1)
 head_wgrad_kernel(const float* __restrict__ x, long long x_bstride, const GT* __restrict__ dout, int dout_ld,
                   float* __restrict__ partial, int B, int sf) {
   extern __shared__ float smem[];
   float* xs = smem;                       // 48
-  float* up = xs + 48;                    // (H+2)^2 * 3, later reused for the lane reduction
+  float* up = xs + 48;                    // (H+2)^2 * 3, later reused for the lane reduction (32 x 64 floats)
   const int H = 4 * sf, P = H + 2;
-  const int co = threadIdx.x & 63, pl = threadIdx.x >> 6;   // pixel lane 0..15
-  float acc[27];
+  const int g = threadIdx.x & 15, pl = threadIdx.x >> 4;   // channel quad, pixel lane 0..31
+  float acc[27][4];
 #pragma unroll
-  for (int q = 0; q < 27; ++q) acc[q] = 0.f;
+  for (int q = 0; q < 27; ++q)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[q][j] = 0.f;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
     if (threadIdx.x < 48) xs[threadIdx.x] = x[(long long)b * x_bstride + threadIdx.x];
     __syncthreads();
     build_upsampled(xs, up, sf);
     __syncthreads();
-    const GT* d = dout + (long long)b * H * H * dout_ld + co;
-    for (int p = pl; p < H * H; p += 16) {
-      const float g = ldf(d + (long long)p * dout_ld);
+    const GT* d = dout + (long long)b * H * H * dout_ld + g * 4;
+    for (int p = pl; p < H * H; p += 32) {
+      const float4 gv = ld4(d + (long long)p * dout_ld);
       const int y = p / H, xx = p - y * H;
       const float* u = up + (y * P + xx) * 3;
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         const float* ut = u + ((tap / 3) * P + tap % 3) * 3;
-        acc[tap * 3 + 0] = fmaf(ut[0], g, acc[tap * 3 + 0]);
-        acc[tap * 3 + 1] = fmaf(ut[1], g, acc[tap * 3 + 1]);
-        acc[tap * 3 + 2] = fmaf(ut[2], g, acc[tap * 3 + 2]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float a = ut[c];
+          const int q = tap * 3 + c;
+          acc[q][0] = fmaf(a, gv.x, acc[q][0]); acc[q][1] = fmaf(a, gv.y, acc[q][1]);
+          acc[q][2] = fmaf(a, gv.z, acc[q][2]); acc[q][3] = fmaf(a, gv.w, acc[q][3]);
+        }
       }
     }
   }
-  // fixed-order reduction over the 16 pixel lanes, 27 values at a time through shared memory
+  // fixed-order reduction over the 32 pixel lanes, one (tap, axis) at a time through shared memory
   __syncthreads();
-  float* red = up;                        // needs 16*64*27 floats = 110 KB?  no: reduce one q at a time (1024 floats)
+  float4* red = reinterpret_cast<float4*>(up);      // [32 lanes][16 quads]
 #pragma unroll
   for (int q = 0; q < 27; ++q) {
-    red[pl * 64 + co] = acc[q];
+    red[pl * 16 + g] = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
     __syncthreads();
     if (pl == 0) {
-      float s = 0.f;
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int l = 0; l < 16; ++l) s += red[l * 64 + co];
-      partial[((long long)blockIdx.x * 27 + q) * 64 + co] = s;
+      for (int l = 0; l < 32; ++l) {
+        const float4 v = red[l * 16 + g];
+        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+      }
+      *reinterpret_cast<float4*>(partial + ((long long)blockIdx.x * 27 + q) * 64 + g * 4) = sum;
     }
     __syncthreads();
   }
@@ -434,13 +446,31 @@ tail_fwd_kernel(const InT* __restrict__ in, int in_ld, const float* __restrict__
   const int b = blockIdx.x / strips, y0 = (blockIdx.x % strips) * TAIL_TR;
   const int PW = W + 2, PH = TAIL_TR + 2;
   const int vpp = Cin / VEC;                            // vectors per pixel
-  for (int i = threadIdx.x; i < PH * PW * vpp; i += blockDim.x) {
-    const int v = i % vpp, pix = i / vpp;
-    const int px = pix % PW - 1, py = y0 + pix / PW - 1;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (px >= 0 && px < W && py >= 0 && py < H)
-      val = *reinterpret_cast<const uint4*>(in + ((long long)(b * H + py) * W + px) * in_ld + v * VEC);
-    *reinterpret_cast<uint4*>(tile + (long long)pix * pitch + v * VEC) = val;
+  // thread -> (vector v of a pixel, pixel lane); the pixel coordinates advance incrementally (no integer divisions in the
+  // loop: they cost more than the copy itself), 4 independent 16-byte loads in flight per thread
+  {
+    const int v = threadIdx.x % vpp, lanes = blockDim.x / vpp;      // blockDim.x is a multiple of vpp (Cin <= 1024)
+    const int npix = PH * PW;
+    int pix = threadIdx.x / vpp;
+    int py = pix / PW, px = pix - py * PW;
+    while (pix < npix) {
+      uint4 val[4];
+      int pixk[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        pixk[k] = pix;
+        val[k] = make_uint4(0u, 0u, 0u, 0u);
+        const int gx = px - 1, gy = y0 + py - 1;
+        if (pix < npix && gx >= 0 && gx < W && gy >= 0 && gy < H)
+          val[k] = *reinterpret_cast<const uint4*>(in + ((long long)(b * H + gy) * W + gx) * in_ld + v * VEC);
+        pix += lanes;
+        px += lanes;
+        while (px >= PW) { px -= PW; ++py; }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (pixk[k] < npix) *reinterpret_cast<uint4*>(tile + (long long)pixk[k] * pitch + v * VEC) = val[k];
+    }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   // this lane's weights: channels c = lane*4 + 128*k (k = 0 for Cin <= 128)
@@ -451,67 +481,99 @@ tail_fwd_kernel(const InT* __restrict__ in, int in_ld, const float* __restrict__
 #pragma unroll
     for (int j = 0; j < 4; ++j) wr[t][j] = (c0 + j < Cin) ? w[(c0 + j) * 9 + t] : 0.f;
   __syncthreads();
-  for (int p = warp; p < TAIL_TR * W; p += nw) {
-    const int ty = p / W, x = p - ty * W;
-    if (y0 + ty >= H) break;
-    float s = 0.f;
+  // 4 pixels per warp iteration (independent accumulation chains), then one transposing reduction of the 4 sums
+  const int npx = min(TAIL_TR, H - y0) * W;
+  for (int p0 = warp * 4; p0 < npx; p0 += nw * 4) {
+    float sum4[4] = {0.f, 0.f, 0.f, 0.f};
     if (c0 < Cin) {
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const InT* src = tile + (long long)((ty + t / 3) * PW + x + t % 3) * pitch + c0;
-        const float4 v = ld4(src);
-        s = fmaf(v.x, wr[t][0], fmaf(v.y, wr[t][1], fmaf(v.z, wr[t][2], fmaf(v.w, wr[t][3], s))));
+      for (int k = 0; k < 4; ++k) {
+        const int p = min(p0 + k, npx - 1);
+        const int ty = p / W, x = p - ty * W;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float4 v = ld4(tile + (long long)((ty + t / 3) * PW + x + t % 3) * pitch + c0);
+          sum4[k] = fmaf(v.x, wr[t][0], fmaf(v.y, wr[t][1], fmaf(v.z, wr[t][2], fmaf(v.w, wr[t][3], sum4[k]))));
+        }
       }
     }
     if (Cin > 128) {   // generic tail for wider inputs (not used by the reference networks)
-      for (int c = c0 + 128; c < Cin; c += 128)
-        for (int t = 0; t < 9; ++t) {
-          const float4 v = ld4(tile + (long long)((ty + t / 3) * PW + x + t % 3) * pitch + c);
-          s += v.x * w[c * 9 + t] + v.y * w[(c + 1) * 9 + t] + v.z * w[(c + 2) * 9 + t] + v.w * w[(c + 3) * 9 + t];
-        }
+      for (int k = 0; k < 4; ++k) {
+        const int p = min(p0 + k, npx - 1);
+        const int ty = p / W, x = p - ty * W;
+        for (int c = c0 + 128; c < Cin; c += 128)
+          for (int t = 0; t < 9; ++t) {
+            const float4 v = ld4(tile + (long long)((ty + t / 3) * PW + x + t % 3) * pitch + c);
+            sum4[k] += v.x * w[c * 9 + t] + v.y * w[(c + 1) * 9 + t] + v.z * w[(c + 2) * 9 + t] + v.w * w[(c + 3) * 9 + t];
+          }
+      }
     }
-    s = warp_sum(s);
-    if (lane == 0) out[((long long)b * H + y0 + ty) * W + x] = relu ? fmaxf(s, 0.f) : s;
+    // lanes exchange halves: after two exchanges lane l carries pixel ((l >> 4) & 1) * 2 + ((l >> 3) & 1)
+    {
+      const bool up16 = (lane & 16) != 0;
+      const float k0 = up16 ? sum4[2] : sum4[0], s0 = up16 ? sum4[0] : sum4[2];
+      const float k1 = up16 ? sum4[3] : sum4[1], s1 = up16 ? sum4[1] : sum4[3];
+      const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16), a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+      const bool up8 = (lane & 8) != 0;
+      float v = (up8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up8 ? a0 : a1, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      const int k = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+      if ((lane & 7) == 0 && p0 + k < npx) {
+        const int p = p0 + k, ty = p / W, x = p - ty * W;
+        out[((long long)b * H + y0 + ty) * W + x] = relu ? fmaxf(v, 0.f) : v;
+      }
+    }
   }
 }
 
 // tail data gradient: din[p][ci] = sum_tap dz[p - shift(tap)] * w[tap][ci],  dz = dout * (out > 0)
+// A CTA owns TAIL_TR rows of one sample: the masked output gradient of the strip (+ halo) is staged in shared memory once;
+// a thread owns a group of 8 channels (its 9 x 8 weights in registers) and strides over the strip's pixels: 9 shared
+// reads (broadcast to the 16 threads that share the pixel), 72 FMAs and one 16/32-byte store, a pixel's 16 groups
+// forming one contiguous channel row.
 template <typename GT>
 __global__ void __launch_bounds__(256)
 tail_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out_act,
-                  const float* __restrict__ w, GT* __restrict__ din, int din_ld, int Mtotal, int H, int W,
+                  const float* __restrict__ w, GT* __restrict__ din, int din_ld, int B, int H, int W,
                   int Cin, int relu) {
-  // one warp per pixel, lane = 4 channels (weights in registers); the 9 neighbouring output gradients are loaded
-  // first (independent, warp-uniform addresses), then 36 FMAs and one coalesced store of the pixel's channel row
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int HW = H * W;
-  for (int c0 = lane * 4; c0 < Cin; c0 += 128) {
-    float wr[9][4];
+  extern __shared__ float dz[];                     // (TAIL_TR + 2) x (W + 2), zero ring
+  const int strips = (H + TAIL_TR - 1) / TAIL_TR;
+  const int b = blockIdx.x / strips, y0 = (blockIdx.x % strips) * TAIL_TR;
+  const int PW = W + 2, PH = TAIL_TR + 2;
+  for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
+    const int px = i % PW - 1, py = y0 + i / PW - 1;
+    float gv = 0.f;
+    if (px >= 0 && px < W && py >= 0 && py < H) {
+      const long long o = ((long long)b * H + py) * W + px;
+      gv = dout[o];
+      if (relu && !(out_act[o] > 0.f)) gv = 0.f;
+    }
+    dz[i] = gv;
+  }
+  __syncthreads();
+  const int npx = min(TAIL_TR, H - y0) * W;
+  const int ngroups = Cin / 8;
+  for (int g = threadIdx.x & 15; g < ngroups; g += 16) {
+    float wr[9][8];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) wr[t][j] = w[(c0 + j) * 9 + t];
-    for (int p = blockIdx.x * nw + warp; p < Mtotal; p += gridDim.x * nw) {
-      const int b = p / HW, rem = p - b * HW;
-      const int y = rem / W, x = rem - y * W;
-      float g[9];
+      for (int j = 0; j < 8; ++j) wr[t][j] = w[(g * 8 + j) * 9 + t];
+    for (int p = threadIdx.x >> 4; p < npx; p += 16) {
+      const int ty = p / W, x = p - ty * W;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         // output pixel o = p - shift(tap) used input p with weight tap
-        const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
-        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-        const int o = ok ? b * HW + yy * W + xx : p;
-        float gv = ok ? dout[o] : 0.f;
-        if (relu && ok && !(out_act[o] > 0.f)) gv = 0.f;
-        g[t] = gv;
-      }
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float gv = dz[(ty + 1 - (t / 3 - 1)) * PW + x + 1 - (t % 3 - 1)];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        acc.x = fmaf(g[t], wr[t][0], acc.x); acc.y = fmaf(g[t], wr[t][1], acc.y);
-        acc.z = fmaf(g[t], wr[t][2], acc.z); acc.w = fmaf(g[t], wr[t][3], acc.w);
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv, wr[t][j], acc[j]);
       }
-      st4(din + (long long)p * din_ld + c0, acc);
+      GT* dst = din + (((long long)b * H + y0 + ty) * W + x) * din_ld + g * 8;
+      st4(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      st4(dst + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
     }
   }
 }
@@ -672,7 +734,7 @@ int tsr_colsum(const void* x, int ld, int x_bf16, long long npix, int C, float* 
   return TSR_OK;
 }
 
-static size_t head_smem(int sf) { return (size_t)(27 * 64 + 48 + (4 * sf + 2) * (4 * sf + 2) * 3) * sizeof(float); }
+static size_t head_smem(int sf) { return (size_t)(48 + (4 * sf + 2) * (4 * sf + 2) * 3) * sizeof(float); }
 
 int tsr_head_fwd(const float* x, long long x_bstride, const float* w_oihw, void* out, int out_ld, int out_bf16,
                  int B, int sf, int relu, cudaStream_t stream) {
@@ -680,7 +742,7 @@ int tsr_head_fwd(const float* x, long long x_bstride, const float* w_oihw, void*
   TSR_REQUIRE(sf >= 1 && sf <= 24, "head_fwd: scale_factor %d unsupported (1..24)", sf);
   TSR_REQUIRE(out_ld % 4 == 0, "head_fwd: out_ld must be a multiple of 4");
   size_t smem = head_smem(sf);
-  int grid = B < 148 * 4 ? B : 148 * 4;
+  int grid = B < 148 ? B : 148;
   TSR_DISPATCH_T(out_bf16, T,
                  TSR_CUDA(cudaFuncSetAttribute(head_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                  head_fwd_kernel<T><<<grid, 256, smem, stream>>>(x, x_bstride, w_oihw, (T*)out, out_ld, B, sf, relu));
@@ -701,11 +763,11 @@ int tsr_head_wgrad(const float* x, long long x_bstride, const void* dout, int do
   int grid = B < 296 ? B : 296;
   TSR_REQUIRE(ws_bytes >= (size_t)grid * 27 * 64 * sizeof(float), "head_wgrad: workspace too small");
   size_t up_floats = (size_t)(4 * sf + 2) * (4 * sf + 2) * 3;
-  if (up_floats < 1024) up_floats = 1024;
+  if (up_floats < 2048) up_floats = 2048;        // the lane reduction reuses it: 32 lanes x 64 channels
   size_t smem = (48 + up_floats) * sizeof(float);
   TSR_DISPATCH_T(dout_bf16, T,
                  TSR_CUDA(cudaFuncSetAttribute(head_wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                 head_wgrad_kernel<T><<<grid, 1024, smem, stream>>>(x, x_bstride, (const T*)dout, dout_ld, (float*)workspace, B, sf));
+                 head_wgrad_kernel<T><<<grid, 512, smem, stream>>>(x, x_bstride, (const T*)dout, dout_ld, (float*)workspace, B, sf));
   TSR_CHECK_LAUNCH("head_wgrad");
   head_wgrad_reduce_kernel<<<tsr_cdiv(27 * 64, 256), 256, 0, stream>>>((const float*)workspace, grid, dw_oihw, accumulate);
   TSR_CHECK_LAUNCH("head_wgrad_reduce");
@@ -717,6 +779,7 @@ int tsr_tail_fwd(const void* in, int in_ld, int in_bf16, const float* w_oihw, fl
   TSR_REQUIRE(in && w_oihw && out, "tail_fwd: null pointer");
   TSR_REQUIRE(Cin % 4 == 0 && Cin <= 1024 && in_ld % 4 == 0, "tail_fwd: Cin must be a multiple of 4");
   TSR_REQUIRE(Cin % 8 == 0, "tail_fwd: Cin must be a multiple of 8");
+  TSR_REQUIRE(256 % (Cin / 8) == 0 && 256 % (Cin / 4) == 0, "tail_fwd: Cin / 4 must divide 256 (got Cin = %d)", Cin);
   const int strips = (H + TAIL_TR - 1) / TAIL_TR;
   const int grid = B * strips;
   TSR_DISPATCH_T(in_bf16, T,
@@ -732,10 +795,10 @@ int tsr_tail_dgrad(const float* dout, const float* out_act, const float* w_oihw,
                    int din_bf16, int B, int H, int W, int Cin, int relu, cudaStream_t stream) {
   TSR_REQUIRE(dout && w_oihw && din && (!relu || out_act), "tail_dgrad: null pointer");
   TSR_REQUIRE(Cin % 4 == 0 && din_ld % 4 == 0, "tail_dgrad: Cin must be a multiple of 4");
-  long long M = (long long)B * H * W;
-  int grid = (int)((M + 7) / 8);
-  if (grid > 148 * 32) grid = 148 * 32;
-  TSR_DISPATCH_T(din_bf16, T, tail_dgrad_kernel<T><<<grid, 256, 0, stream>>>(dout, out_act, w_oihw, (T*)din, din_ld, (int)M, H, W, Cin, relu));
+  TSR_REQUIRE(Cin % 8 == 0, "tail_dgrad: Cin must be a multiple of 8");
+  const int strips = (H + TAIL_TR - 1) / TAIL_TR;
+  const size_t smem = (size_t)(TAIL_TR + 2) * (W + 2) * sizeof(float);
+  TSR_DISPATCH_T(din_bf16, T, tail_dgrad_kernel<T><<<B * strips, 256, smem, stream>>>(dout, out_act, w_oihw, (T*)din, din_ld, B, H, W, Cin, relu));
   TSR_CHECK_LAUNCH("tail_dgrad");
   return TSR_OK;
 }
