@@ -334,8 +334,8 @@ head_fwd_kernel(const float* __restrict__ x, long long x_bstride, const float* _
     __syncthreads();
     build_upsampled(xs, up, sf);
     __syncthreads();
-    for (int p = pl; p < H * H; p += 16) {
-      const int y = p / H, xx = p - y * H;
+    int y = pl / H, xx = pl - y * H;                 // advanced incrementally: an integer division per pixel costs as
+    for (int p = pl; p < H * H; p += 16) {           // much as a quarter of the pixel's FMAs
       const float* u0 = up + (y * P + xx) * 3;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -351,6 +351,8 @@ head_fwd_kernel(const float* __restrict__ x, long long x_bstride, const float* _
       }
       if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
       st4(out + ((long long)b * H * H + p) * out_ld + g * 4, acc);
+      xx += 16;
+      while (xx >= H) { xx -= H; ++y; }
     }
   }
 }
@@ -379,9 +381,11 @@ head_wgrad_kernel(const float* __restrict__ x, long long x_bstride, const GT* __
     build_upsampled(xs, up, sf);
     __syncthreads();
     const GT* d = dout + (long long)b * H * H * dout_ld + g * 4;
+    float4 nxt = pl < H * H ? ld4(d + (long long)pl * dout_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int y = pl / H, xx = pl - y * H;
     for (int p = pl; p < H * H; p += 32) {
-      const float4 gv = ld4(d + (long long)p * dout_ld);
-      const int y = p / H, xx = p - y * H;
+      const float4 gv = nxt;                                  // the next pixel's gradient is already in flight
+      if (p + 32 < H * H) nxt = ld4(d + (long long)(p + 32) * dout_ld);
       const float* u = up + (y * P + xx) * 3;
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
@@ -394,6 +398,8 @@ head_wgrad_kernel(const float* __restrict__ x, long long x_bstride, const GT* __
           acc[q][2] = fmaf(a, gv.z, acc[q][2]); acc[q][3] = fmaf(a, gv.w, acc[q][3]);
         }
       }
+      xx += 32;
+      while (xx >= H) { xx -= H; ++y; }
     }
   }
   // fixed-order reduction over the 32 pixel lanes, one (tap, axis) at a time through shared memory
@@ -486,10 +492,12 @@ tail_fwd_kernel(const InT* __restrict__ in, int in_ld, const float* __restrict__
   for (int p0 = warp * 4; p0 < npx; p0 += nw * 4) {
     float sum4[4] = {0.f, 0.f, 0.f, 0.f};
     if (c0 < Cin) {
+      const int ty0 = p0 / W, x0 = p0 - ty0 * W;      // one division per 4 pixels
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int p = min(p0 + k, npx - 1);
-        const int ty = p / W, x = p - ty * W;
+        int ty = ty0, x = x0 + k;
+        if (x >= W) { x -= W; ++ty; }
+        if (p0 + k >= npx) { ty = ty0; x = x0; }       // (padding lanes of the last group recompute pixel p0)
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const float4 v = ld4(tile + (long long)((ty + t / 3) * PW + x + t % 3) * pitch + c0);
@@ -540,40 +548,45 @@ tail_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out_
                   int Cin, int relu) {
   extern __shared__ float dz[];                     // (TAIL_TR + 2) x (W + 2), zero ring
   const int strips = (H + TAIL_TR - 1) / TAIL_TR;
-  const int b = blockIdx.x / strips, y0 = (blockIdx.x % strips) * TAIL_TR;
   const int PW = W + 2, PH = TAIL_TR + 2;
-  for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
-    const int px = i % PW - 1, py = y0 + i / PW - 1;
-    float gv = 0.f;
-    if (px >= 0 && px < W && py >= 0 && py < H) {
-      const long long o = ((long long)b * H + py) * W + px;
-      gv = dout[o];
-      if (relu && !(out_act[o] > 0.f)) gv = 0.f;
-    }
-    dz[i] = gv;
-  }
-  __syncthreads();
-  const int npx = min(TAIL_TR, H - y0) * W;
   const int ngroups = Cin / 8;
-  for (int g = threadIdx.x & 15; g < ngroups; g += 16) {
-    float wr[9][8];
+  for (int g = threadIdx.x & 15; g < ngroups; g += 16) {       // (one pass for Cin <= 128)
+    float wr[9][8];                                            // loaded once: the CTA is persistent over strips
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
       for (int j = 0; j < 8; ++j) wr[t][j] = w[(g * 8 + j) * 9 + t];
-    for (int p = threadIdx.x >> 4; p < npx; p += 16) {
-      const int ty = p / W, x = p - ty * W;
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        // output pixel o = p - shift(tap) used input p with weight tap
-        const float gv = dz[(ty + 1 - (t / 3 - 1)) * PW + x + 1 - (t % 3 - 1)];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv, wr[t][j], acc[j]);
+    for (int sidx = blockIdx.x; sidx < B * strips; sidx += gridDim.x) {
+      const int b = sidx / strips, y0 = (sidx - b * strips) * TAIL_TR;
+      __syncthreads();
+      for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
+        const int px = i % PW - 1, py = y0 + i / PW - 1;
+        float gv = 0.f;
+        if (px >= 0 && px < W && py >= 0 && py < H) {
+          const long long o = ((long long)b * H + py) * W + px;
+          gv = dout[o];
+          if (relu && !(out_act[o] > 0.f)) gv = 0.f;
+        }
+        dz[i] = gv;
       }
-      GT* dst = din + (((long long)b * H + y0 + ty) * W + x) * din_ld + g * 8;
-      st4(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
-      st4(dst + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+      __syncthreads();
+      const int npx = min(TAIL_TR, H - y0) * W;
+      int ty = (threadIdx.x >> 4) / W, x = (threadIdx.x >> 4) - ty * W;
+      for (int p = threadIdx.x >> 4; p < npx; p += 16) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          // output pixel o = p - shift(tap) used input p with weight tap
+          const float gv = dz[(ty + 1 - (t / 3 - 1)) * PW + x + 1 - (t % 3 - 1)];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv, wr[t][j], acc[j]);
+        }
+        GT* dst = din + (((long long)b * H + y0 + ty) * W + x) * din_ld + g * 8;
+        st4(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        st4(dst + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+        x += 16;
+        while (x >= W) { x -= W; ++ty; }
+      }
     }
   }
 }
@@ -798,7 +811,7 @@ int tsr_tail_dgrad(const float* dout, const float* out_act, const float* w_oihw,
   TSR_REQUIRE(Cin % 8 == 0, "tail_dgrad: Cin must be a multiple of 8");
   const int strips = (H + TAIL_TR - 1) / TAIL_TR;
   const size_t smem = (size_t)(TAIL_TR + 2) * (W + 2) * sizeof(float);
-  TSR_DISPATCH_T(din_bf16, T, tail_dgrad_kernel<T><<<B * strips, 256, smem, stream>>>(dout, out_act, w_oihw, (T*)din, din_ld, B, H, W, Cin, relu));
+  TSR_DISPATCH_T(din_bf16, T, tail_dgrad_kernel<T><<<(B * strips < 148 * 6 ? B * strips : 148 * 6), 256, smem, stream>>>(dout, out_act, w_oihw, (T*)din, din_ld, B, H, W, Cin, relu));
   TSR_CHECK_LAUNCH("tail_dgrad");
   return TSR_OK;
 }
