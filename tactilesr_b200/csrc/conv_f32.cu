@@ -307,7 +307,7 @@ __device__ __forceinline__ void build_upsampled(const float* __restrict__ xs /*3
       v0 = TSR_UP(0); v1 = TSR_UP(1); v2 = TSR_UP(2);
 #undef TSR_UP
     }
-    up[i * 3 + 0] = v0; up[i * 3 + 1] = v1; up[i * 3 + 2] = v2;
+    *reinterpret_cast<float4*>(up + i * 4) = make_float4(v0, v1, v2, 0.f);      // 16 bytes per pixel: one LDS.128
   }
 }
 
@@ -336,14 +336,15 @@ head_fwd_kernel(const float* __restrict__ x, long long x_bstride, const float* _
     __syncthreads();
     int y = pl / H, xx = pl - y * H;                 // advanced incrementally: an integer division per pixel costs as
     for (int p = pl; p < H * H; p += 16) {           // much as a quarter of the pixel's FMAs
-      const float* u0 = up + (y * P + xx) * 3;
+      const float4* u0 = reinterpret_cast<const float4*>(up) + (y * P + xx);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        const float* u = u0 + ((tap / 3) * P + tap % 3) * 3;
+        const float4 u4 = u0[(tap / 3) * P + tap % 3];       // the three axes of one neighbour pixel
+        const float uv[3] = {u4.x, u4.y, u4.z};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float a = u[c];
+          const float a = uv[c];
           const int q = tap * 3 + c;
           acc.x = fmaf(a, wr[q][0], acc.x); acc.y = fmaf(a, wr[q][1], acc.y);
           acc.z = fmaf(a, wr[q][2], acc.z); acc.w = fmaf(a, wr[q][3], acc.w);
@@ -356,6 +357,30 @@ head_fwd_kernel(const float* __restrict__ x, long long x_bstride, const float* _
     }
   }
 }
+
+// four consecutive channels as the raw words of their storage type (conversion deferred to the point of use)
+template <typename T> struct Raw4;
+template <> struct Raw4<float> {
+  typedef float4 type;
+  __device__ static __forceinline__ type load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  __device__ static __forceinline__ float4 cvt(type r) { return r; }
+};
+template <> struct Raw4<__nv_bfloat16> {
+  typedef uint2 type;
+  __device__ static __forceinline__ type load(const __nv_bfloat16* p) { return *reinterpret_cast<const uint2*>(p); }
+  __device__ static __forceinline__ float4 cvt(type r) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.x)), b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
+template <> struct Raw4<__half> {
+  typedef uint2 type;
+  __device__ static __forceinline__ type load(const __half* p) { return *reinterpret_cast<const uint2*>(p); }
+  __device__ static __forceinline__ float4 cvt(type r) {
+    const float2 a = __half22float2(*reinterpret_cast<__half2*>(&r.x)), b = __half22float2(*reinterpret_cast<__half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
 
 // head weight gradient, level 1: one partial [27][64] per CTA, CTAs stride over samples.
 // 512 threads = 16 channel quads x 32 pixel lanes; a thread keeps all 27 x 4 (tap, axis, channel) sums in registers, so a
@@ -381,18 +406,24 @@ head_wgrad_kernel(const float* __restrict__ x, long long x_bstride, const GT* __
     build_upsampled(xs, up, sf);
     __syncthreads();
     const GT* d = dout + (long long)b * H * H * dout_ld + g * 4;
-    float4 nxt = pl < H * H ? ld4(d + (long long)pl * dout_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // three pixels' gradients in flight per thread (kept as raw 8 / 16-byte words): with one CTA of 16 warps per SM a single
+    // outstanding load per thread leaves the HBM latency exposed
+    typename Raw4<GT>::type r0 = Raw4<GT>::load(d + (long long)min(pl, H * H - 1) * dout_ld);
+    typename Raw4<GT>::type r1 = Raw4<GT>::load(d + (long long)min(pl + 32, H * H - 1) * dout_ld);
+    typename Raw4<GT>::type r2 = Raw4<GT>::load(d + (long long)min(pl + 64, H * H - 1) * dout_ld);
     int y = pl / H, xx = pl - y * H;
     for (int p = pl; p < H * H; p += 32) {
-      const float4 gv = nxt;                                  // the next pixel's gradient is already in flight
-      if (p + 32 < H * H) nxt = ld4(d + (long long)(p + 32) * dout_ld);
-      const float* u = up + (y * P + xx) * 3;
+      const float4 gv = Raw4<GT>::cvt(r0);
+      r0 = r1; r1 = r2;
+      r2 = Raw4<GT>::load(d + (long long)min(p + 96, H * H - 1) * dout_ld);
+      const float4* u = reinterpret_cast<const float4*>(up) + (y * P + xx);
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        const float* ut = u + ((tap / 3) * P + tap % 3) * 3;
+        const float4 u4 = u[(tap / 3) * P + tap % 3];
+        const float uv[3] = {u4.x, u4.y, u4.z};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float a = ut[c];
+          const float a = uv[c];
           const int q = tap * 3 + c;
           acc[q][0] = fmaf(a, gv.x, acc[q][0]); acc[q][1] = fmaf(a, gv.y, acc[q][1]);
           acc[q][2] = fmaf(a, gv.z, acc[q][2]); acc[q][3] = fmaf(a, gv.w, acc[q][3]);
@@ -747,7 +778,7 @@ int tsr_colsum(const void* x, int ld, int x_bf16, long long npix, int C, float* 
   return TSR_OK;
 }
 
-static size_t head_smem(int sf) { return (size_t)(48 + (4 * sf + 2) * (4 * sf + 2) * 3) * sizeof(float); }
+static size_t head_smem(int sf) { return (size_t)(48 + (4 * sf + 2) * (4 * sf + 2) * 4) * sizeof(float); }
 
 int tsr_head_fwd(const float* x, long long x_bstride, const float* w_oihw, void* out, int out_ld, int out_bf16,
                  int B, int sf, int relu, cudaStream_t stream) {
@@ -775,7 +806,7 @@ int tsr_head_wgrad(const float* x, long long x_bstride, const void* dout, int do
   TSR_REQUIRE(sf >= 1 && sf <= 24, "head_wgrad: scale_factor %d unsupported", sf);
   int grid = B < 296 ? B : 296;
   TSR_REQUIRE(ws_bytes >= (size_t)grid * 27 * 64 * sizeof(float), "head_wgrad: workspace too small");
-  size_t up_floats = (size_t)(4 * sf + 2) * (4 * sf + 2) * 3;
+  size_t up_floats = (size_t)(4 * sf + 2) * (4 * sf + 2) * 4;
   if (up_floats < 2048) up_floats = 2048;        // the lane reduction reuses it: 32 lanes x 64 channels
   size_t smem = (48 + up_floats) * sizeof(float);
   TSR_DISPATCH_T(dout_bf16, T,
