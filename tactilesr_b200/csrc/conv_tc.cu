@@ -75,27 +75,105 @@ __device__ __forceinline__ float transpose_reduce16(float (&p)[16], int lane) {
   return p[0] + __shfl_xor_sync(0xffffffffu, p[0], 1);
 }
 
-// BatchNorm batch statistics of the 16 stored (rounded) output channels o[8] of this lane's pixel: per-channel sum and
-// sum of squares over the warp's 32 pixels, added to row `row` of the partial table.  Every (row, channel) address is
-// updated by exactly one lane of one warp, in program order => deterministic although it is a reduction instruction.
-__device__ __forceinline__ void bn_stats_accumulate(const uint32_t (&o)[8], bool valid, bool f16, float* __restrict__ part,
-                                                    int C, int row, int col0, int lane) {
-  float v[16], q[16];
+// BatchNorm batch statistics of the stored (rounded) outputs: every epilogue lane adds the 16 channels o[8] of its pixel
+// into per-lane sums (sv) and sums of squares (sq); once per block and channel chunk the warp reduces them over its 32
+// pixels and adds the result to row `row` of the partial table.  Every (row, channel) address is updated by exactly one
+// lane of one warp, in program order => deterministic although it is a reduction instruction.
+__device__ __forceinline__ void bn_stats_add(const uint32_t (&o)[8], bool valid, bool f16, float (&sv)[16], float (&sq)[16]) {
+  if (!valid) return;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     float2 t;
     if (f16) t = __half22float2(*reinterpret_cast<const __half2*>(&o[k]));
     else t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o[k]));
-    v[2 * k] = valid ? t.x : 0.f;
-    v[2 * k + 1] = valid ? t.y : 0.f;
+    sv[2 * k] += t.x; sv[2 * k + 1] += t.y;
+    sq[2 * k] = fmaf(t.x, t.x, sq[2 * k]); sq[2 * k + 1] = fmaf(t.y, t.y, sq[2 * k + 1]);
   }
-#pragma unroll
-  for (int k = 0; k < 16; ++k) q[k] = v[k] * v[k];
-  const float s = transpose_reduce16(v, lane), ss = transpose_reduce16(q, lane);
+}
+__device__ __forceinline__ void bn_stats_flush(float (&sv)[16], float (&sq)[16], float* __restrict__ part, int C, int row,
+                                               int col0, int lane) {
+  const float s = transpose_reduce16(sv, lane), ss = transpose_reduce16(sq, lane);
   if ((lane & 1) == 0) {
     const int c = col0 + (lane >> 1);
     atomicAdd(part + ((size_t)row * 2 + 0) * C + c, s);
     atomicAdd(part + ((size_t)row * 2 + 1) * C + c, ss);
+  }
+}
+
+// Epilogue of one block (T_TILES M-tiles of 128 pixels, N output channels) for the epilogue warp that owns TMEM lanes
+// acc0 >> 16 ..+31: TMEM -> registers -> + bias, + residual, ReLU -> 16-bit -> 16-byte stores (+ the optional bf16 copy).
+// Channel chunks are the outer loop so that the BatchNorm statistics of a chunk are reduced across the warp once per
+// block, not once per M-tile (the reduction is as long as the rest of the chunk's epilogue).
+template <int N>
+__device__ __forceinline__ void epilogue_block(const ConvParams& p, uint32_t acc0, const bool (&valid)[T_TILES],
+                                               const long long (&pix)[T_TILES], int stat_row, int lane) {
+  const bool f16 = (p.flags & FLAG_F16) != 0;
+#pragma unroll 1
+  for (int j = 0; j < N / 16; ++j) {
+    float sv[16], sq[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { sv[k] = 0.f; sq[k] = 0.f; }
+#pragma unroll
+    for (int mt = 0; mt < T_TILES; ++mt) {
+      uint32_t v[16];
+      tmem_ld16(acc0 + mt * N + j * 16, v);
+      tmem_ld_wait();
+      if (valid[mt]) {
+        float f[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
+        if (p.bias) {
+#pragma unroll
+          for (int k = 0; k < 16; k += 4) {
+            float4 bv = *reinterpret_cast<const float4*>(p.bias + j * 16 + k);
+            f[k] += bv.x; f[k + 1] += bv.y; f[k + 2] += bv.z; f[k + 3] += bv.w;
+          }
+        }
+        if (p.residual) {
+          const __nv_bfloat16* rp = p.residual + pix[mt] * p.res_ld + j * 16;
+#pragma unroll
+          for (int k = 0; k < 16; k += 4) {
+            float4 rv = f16 ? ld4(reinterpret_cast<const __half*>(rp) + k) : ld4(rp + k);
+            f[k] += rv.x; f[k + 1] += rv.y; f[k + 2] += rv.z; f[k + 3] += rv.w;
+          }
+        }
+        if (p.flags & FLAG_RELU) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
+        }
+        uint32_t o[8];
+        if (f16) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+            o[k] = *reinterpret_cast<uint32_t*>(&h);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+            o[k] = *reinterpret_cast<uint32_t*>(&h);
+          }
+        }
+        uint4* op = reinterpret_cast<uint4*>(p.out + pix[mt] * p.out_ld + j * 16);
+        op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        if (p.out2) {
+          uint32_t o2[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+            o2[k] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          uint4* op2 = reinterpret_cast<uint4*>(p.out2 + pix[mt] * p.out2_ld + j * 16);
+          op2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+          op2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
+        }
+        if (p.bn_partial) bn_stats_add(o, true, f16, sv, sq);
+      }
+    }
+    if (p.bn_partial)      // (warp-uniform: all 32 lanes take part in the shuffles)
+      bn_stats_flush(sv, sq, p.bn_partial, p.bn_C, stat_row, j * 16, lane);
   }
 }
 
@@ -255,73 +333,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
       mbar_wait(t_full(buf), (lb >> 1) & 1);
       tc_fence_after();
       const uint32_t acc0 = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
+      bool valid[T_TILES];
+      long long pix[T_TILES];
+#pragma unroll
       for (int mt = 0; mt < T_TILES; ++mt) {
         const int vr = v0 + mt * 16 + vrow;
         const int n = vr / p.Hp, y = vr - n * p.Hp;
-        const bool valid = vr < p.Vtotal && y < p.H;
-        const long long pix = ((long long)n * p.H + y) * p.W + x0 + wx;
-#pragma unroll 1
-        for (int j = 0; j < N / 16; ++j) {
-          uint32_t v[16];
-          tmem_ld16(acc0 + mt * N + j * 16, v);
-          tmem_ld_wait();
-          uint32_t o[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-          if (valid) {
-            float f[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
-            if (p.bias) {
-#pragma unroll
-              for (int k = 0; k < 16; k += 4) {
-                float4 bv = *reinterpret_cast<const float4*>(p.bias + j * 16 + k);
-                f[k] += bv.x; f[k + 1] += bv.y; f[k + 2] += bv.z; f[k + 3] += bv.w;
-              }
-            }
-            if (p.residual) {
-              const __nv_bfloat16* rp = p.residual + pix * p.res_ld + j * 16;
-#pragma unroll
-              for (int k = 0; k < 16; k += 4) {
-                float4 rv = (p.flags & FLAG_F16) ? ld4(reinterpret_cast<const __half*>(rp) + k) : ld4(rp + k);
-                f[k] += rv.x; f[k + 1] += rv.y; f[k + 2] += rv.z; f[k + 3] += rv.w;
-              }
-            }
-            if (p.flags & FLAG_RELU) {
-#pragma unroll
-              for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
-            }
-            if (p.flags & FLAG_F16) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
-                o[k] = *reinterpret_cast<uint32_t*>(&h);
-              }
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-                o[k] = *reinterpret_cast<uint32_t*>(&h);
-              }
-            }
-            uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_ld + j * 16);
-            op[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            op[1] = make_uint4(o[4], o[5], o[6], o[7]);
-            if (p.out2) {
-              uint32_t o2[8];
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-                o2[k] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              uint4* op2 = reinterpret_cast<uint4*>(p.out2 + pix * p.out2_ld + j * 16);
-              op2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
-              op2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
-            }
-          }
-          if (p.bn_partial)      // (warp-uniform: all 32 lanes take part in the shuffles)
-            bn_stats_accumulate(o, valid, (p.flags & FLAG_F16) != 0, p.bn_partial, p.bn_C, (int)blockIdx.x * 4 + q, j * 16, lane);
-        }
+        valid[mt] = vr < p.Vtotal && y < p.H;
+        pix[mt] = ((long long)n * p.H + y) * p.W + x0 + wx;
       }
+      epilogue_block<N>(p, acc0, valid, pix, (int)blockIdx.x * 4 + q, lane);
       // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -547,73 +568,16 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
       mbar_wait(t_full(buf), (lb >> 1) & 1);
       tc_fence_after();
       const uint32_t acc0 = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
+      bool valid[T_TILES];
+      long long pix[T_TILES];
+#pragma unroll
       for (int mt = 0; mt < T_TILES; ++mt) {
         const int vr = v0 + mt * 16 + vrow;
         const int n = vr / p.Hp, y = vr - n * p.Hp;
-        const bool valid = blk < p.nblocks && vr < p.Vtotal && y < p.H;
-        const long long pix = ((long long)n * p.H + y) * p.W + x0 + wx;
-#pragma unroll 1
-        for (int j = 0; j < N / 16; ++j) {
-          uint32_t v[16];
-          tmem_ld16(acc0 + mt * N + j * 16, v);
-          tmem_ld_wait();
-          uint32_t o[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-          if (valid) {
-            float f[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
-            if (p.bias) {
-#pragma unroll
-              for (int k = 0; k < 16; k += 4) {
-                float4 bv = *reinterpret_cast<const float4*>(p.bias + j * 16 + k);
-                f[k] += bv.x; f[k + 1] += bv.y; f[k + 2] += bv.z; f[k + 3] += bv.w;
-              }
-            }
-            if (p.residual) {
-              const __nv_bfloat16* rp = p.residual + pix * p.res_ld + j * 16;
-#pragma unroll
-              for (int k = 0; k < 16; k += 4) {
-                float4 rv = (p.flags & FLAG_F16) ? ld4(reinterpret_cast<const __half*>(rp) + k) : ld4(rp + k);
-                f[k] += rv.x; f[k + 1] += rv.y; f[k + 2] += rv.z; f[k + 3] += rv.w;
-              }
-            }
-            if (p.flags & FLAG_RELU) {
-#pragma unroll
-              for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
-            }
-            if (p.flags & FLAG_F16) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
-                o[k] = *reinterpret_cast<uint32_t*>(&h);
-              }
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-                o[k] = *reinterpret_cast<uint32_t*>(&h);
-              }
-            }
-            uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_ld + j * 16);
-            op[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            op[1] = make_uint4(o[4], o[5], o[6], o[7]);
-            if (p.out2) {
-              uint32_t o2[8];
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-                o2[k] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              uint4* op2 = reinterpret_cast<uint4*>(p.out2 + pix * p.out2_ld + j * 16);
-              op2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
-              op2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
-            }
-          }
-          if (p.bn_partial)      // (warp-uniform: all 32 lanes take part in the shuffles)
-            bn_stats_accumulate(o, valid, (p.flags & FLAG_F16) != 0, p.bn_partial, p.bn_C, (int)blockIdx.x * 4 + q, j * 16, lane);
-        }
+        valid[mt] = blk < p.nblocks && vr < p.Vtotal && y < p.H;
+        pix[mt] = ((long long)n * p.H + y) * p.W + x0 + wx;
       }
+      epilogue_block<N>(p, acc0, valid, pix, (int)blockIdx.x * 4 + q, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(t_empty(buf) & PEER_MASK);
