@@ -420,11 +420,13 @@ def run_ours(args):
     line = {
         "metric": "SR train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "fp16 activations / bf16 gradients", "fp32": "f32"}[args.precision], "data": "synthetic",
+        "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "fp16", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": {"workload": "TactileSR(seqsCnt=1) train step: fwd + fused HR-prep/MSE + bwd + fused Adam(lr 1e-3, wd 1e-2)"
                                + (" + bucketed NCCL grad all-reduce" if world > 1 else ""),
                    "per_gpu_batch": B, "global_batch": B * world, "input": "LR (B,3,4,4), HR (B,1,100,100)",
-                   "precision_mode": args.precision, "parallelism": f"dp{world}",
+                   "precision_mode": args.precision + {"fp16": " (fp16 activations / forward weights, bf16 gradients, fp32 accumulation and statistics)",
+                                                       "bf16": " (bf16 storage, fp32 accumulation and statistics)", "fp32": ""}[args.precision],
+                   "parallelism": f"dp{world}",
                    "l2": "per-step working set (saved activations, B x ~26-52 MB) >> 126 MB L2; 4 rotating input batches"},
         "tensor_roofline_frac_step": value / world * FLOP_PER_SAMPLE_TRAIN / 1e12 / pk["tf_sust"],
         "roofline": roof, "cpu_baseline": cpu,
