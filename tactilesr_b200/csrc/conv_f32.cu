@@ -753,18 +753,24 @@ int tsr_conv2d_wgrad_f32(const float* in, int in_ld, const float* dout, int dout
   return TSR_OK;
 }
 
-size_t tsr_colsum_workspace(long long npix, int C) {
+// level-1 blocks: 1024 rows each for big tensors (<= 1024 blocks), but never fewer than ~4 CTAs per SM worth of blocks
+// when the tensor is short and wide (the MLP bias gradients: 8192 x 1024), down to 16 rows per block
+static int colsum_blocks(long long npix) {
   int nb = tsr_cdiv(npix, 1024);
+  int want = tsr_cdiv(npix, 16);
+  if (want > 592) want = 592;
+  if (nb < want) nb = want;
   if (nb > 1024) nb = 1024;
-  return (size_t)nb * C * sizeof(float);
+  return nb;
 }
+
+size_t tsr_colsum_workspace(long long npix, int C) { return (size_t)colsum_blocks(npix) * C * sizeof(float); }
 
 int tsr_colsum(const void* x, int ld, int x_bf16, long long npix, int C, float* out, void* workspace, size_t ws_bytes,
                int accumulate, cudaStream_t stream) {
   TSR_REQUIRE(x && out && workspace, "colsum: null pointer");
   TSR_REQUIRE(C % 4 == 0 && C <= 1024 && ld % 4 == 0, "colsum: C must be a multiple of 4 and <= 1024");
-  int nb = tsr_cdiv(npix, 1024);
-  if (nb > 1024) nb = 1024;
+  int nb = colsum_blocks(npix);
   int rpb = tsr_cdiv(npix, nb);
   nb = tsr_cdiv(npix, rpb);
   TSR_REQUIRE(ws_bytes >= (size_t)nb * C * sizeof(float), "colsum: workspace too small");
