@@ -34,15 +34,20 @@ __global__ void pack_weight_f32_kernel(const float* __restrict__ w, float* __res
 
 // ---------------------------------------------------------------------------------------------
 // forward / data-gradient: out[p][co] = sum_{tap,ci} in[p+shift(tap)][ci] * wp[tap][ci][co]
-// tile 128 pixels x 64 couts x 16 channels, 256 threads, 8x4 outputs per thread
+// tile 128 pixels x (16 TN) couts x 16 channels, 256 threads, 8 x TN outputs per thread: TN = 4 (64 couts) or, when the
+// grid still fills the machine, TN = 8 (128 couts: 4 LDS.128 per 64 FFMA instead of 3 per 32).  Every output is one serial
+// fmaf chain over (tap, ci) in both variants, so they are bit-identical.
 // ---------------------------------------------------------------------------------------------
-constexpr int BM = 128, BN = 64, BK = 16, APAD = 4;
+constexpr int BM = 128, BK = 16, APAD = 4;
 
-__global__ void __launch_bounds__(256)
+template <int TN>
+__global__ void __launch_bounds__(256, TN == 8 ? 2 : 3)
 conv2d_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restrict__ wp,
                   const float* __restrict__ bias, const float* residual, int res_ld,
                   float* out, int out_ld, int Mtotal, int H, int W, int Cin, int Cout, int KS,
                   int flags) {
+  constexpr int BN = 16 * TN;
+  constexpr int NB4 = TN / 4;            // float4 groups of 4 couts per thread: columns g*64 + tn*4 (conflict-free LDS.128)
   __shared__ __align__(16) float As[2][BK][BM + APAD];
   __shared__ __align__(16) float Bs[2][BK][BN];
 
@@ -72,7 +77,7 @@ conv2d_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restri
   const int cchunks = Cin / BK;
   const int nk = KS * KS * cchunks;
 
-  float4 ra[2], rb;
+  float4 ra[2], rb[NB4];
   auto load_global = [&](int kc) {
     int tap = kc / cchunks;
     int c0 = (kc - tap * cchunks) * BK;
@@ -84,7 +89,9 @@ conv2d_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restri
       ra[s] = ok ? *reinterpret_cast<const float4*>(in + (abase[s] + (long long)yy * W + xx) * in_ld + c0 + ac4)
                  : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    rb = *reinterpret_cast<const float4*>(wp + ((long long)tap * Cin + c0 + bk) * Cout + n0 + bn4);
+#pragma unroll
+    for (int g = 0; g < NB4; ++g)
+      rb[g] = *reinterpret_cast<const float4*>(wp + ((long long)tap * Cin + c0 + bk) * Cout + n0 + g * 64 + bn4);
   };
   auto store_smem = [&](int buf) {
 #pragma unroll
@@ -95,14 +102,15 @@ conv2d_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restri
       As[buf][ac4 + 2][m] = ra[s].z;
       As[buf][ac4 + 3][m] = ra[s].w;
     }
-    *reinterpret_cast<float4*>(&Bs[buf][bk][bn4]) = rb;
+#pragma unroll
+    for (int g = 0; g < NB4; ++g) *reinterpret_cast<float4*>(&Bs[buf][bk][g * 64 + bn4]) = rb[g];
   };
 
-  float acc[8][4];
+  float acc[8][TN];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   load_global(0);
   store_smem(0);
@@ -114,34 +122,41 @@ conv2d_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restri
     for (int k = 0; k < BK; ++k) {
       float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8]);
       float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8 + 4]);
-      float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tn * 4]);
       float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      float bb[4] = {b.x, b.y, b.z, b.w};
+      float bb[TN];
+#pragma unroll
+      for (int g = 0; g < NB4; ++g) {
+        float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][g * 64 + tn * 4]);
+        bb[4 * g] = b.x; bb[4 * g + 1] = b.y; bb[4 * g + 2] = b.z; bb[4 * g + 3] = b.w;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
     if (kc + 1 < nk) store_smem(buf ^ 1);
     __syncthreads();
   }
 
-  const int n = n0 + tn * 4;
-  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (bias) bv = *reinterpret_cast<const float4*>(bias + n);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int p = m0 + tm * 8 + i;
-    if (p >= Mtotal) continue;
-    float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
-    if (residual) {
-      float4 r = *reinterpret_cast<const float4*>(residual + (long long)p * res_ld + n);
-      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+  for (int g = 0; g < NB4; ++g) {
+    const int n = n0 + g * 64 + tn * 4;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) bv = *reinterpret_cast<const float4*>(bias + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int p = m0 + tm * 8 + i;
+      if (p >= Mtotal) continue;
+      float4 v = make_float4(acc[i][4 * g] + bv.x, acc[i][4 * g + 1] + bv.y, acc[i][4 * g + 2] + bv.z, acc[i][4 * g + 3] + bv.w);
+      if (residual) {
+        float4 r = *reinterpret_cast<const float4*>(residual + (long long)p * res_ld + n);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      if (flags & FLAG_RELU) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      }
+      *reinterpret_cast<float4*>(out + (long long)p * out_ld + n) = v;
     }
-    if (flags & FLAG_RELU) {
-      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-    }
-    *reinterpret_cast<float4*>(out + (long long)p * out_ld + n) = v;
   }
 }
 
@@ -704,9 +719,16 @@ int tsr_conv2d_f32(const float* in, int in_ld, const float* w_packed, const floa
   TSR_REQUIRE(in_ld % 4 == 0 && out_ld % 4 == 0 && (!residual || res_ld % 4 == 0), "conv2d_f32: row strides must be multiples of 4");
   long long M = (long long)B * H * W;
   TSR_REQUIRE(M > 0 && M < (1ll << 31), "conv2d_f32: bad pixel count");
-  dim3 grid(tsr_cdiv(M, BM), Cout / BN);
-  conv2d_f32_kernel<<<grid, 256, 0, stream>>>(in, in_ld, w_packed, bias, residual, res_ld, out, out_ld, (int)M,
-                                              H, W, Cin, Cout, KS, flags);
+  // 128-wide cout tiles once they still give every SM its two resident CTAs
+  if (Cout % 128 == 0 && (long long)tsr_cdiv(M, BM) * (Cout / 128) >= 2 * 148) {
+    dim3 grid(tsr_cdiv(M, BM), Cout / 128);
+    conv2d_f32_kernel<8><<<grid, 256, 0, stream>>>(in, in_ld, w_packed, bias, residual, res_ld, out, out_ld, (int)M,
+                                                   H, W, Cin, Cout, KS, flags);
+  } else {
+    dim3 grid(tsr_cdiv(M, BM), Cout / 64);
+    conv2d_f32_kernel<4><<<grid, 256, 0, stream>>>(in, in_ld, w_packed, bias, residual, res_ld, out, out_ld, (int)M,
+                                                   H, W, Cin, Cout, KS, flags);
+  }
   TSR_CHECK_LAUNCH("conv2d_f32");
   return TSR_OK;
 }
