@@ -206,7 +206,8 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
    tactileSR_model.py:42,48,169,...); finish them with tsr_bn_finalize_partials. */
 int tsr_conv2d_tc_stat_rows(void);
 size_t tsr_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS);
-/* weight gradient (fp32 OIHW) of bf16 activations / gradients; bit-deterministic.  H, W % 8 == 0, Cout in {64,128}.
+/* weight gradient (fp32 OIHW) of bf16 activations / gradients; bit-deterministic.  H, W % 8 == 0, Cout = 64 or a multiple of 128
+   (128 output channels per launch).
    (The "fp16" precision mode hands this a bf16 copy of the conv input: tcgen05 kind::f16 rejects fp16 x bf16.) */
 int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
                         size_t ws_bytes, int B, int H, int W, int Cin, int Cout, int KS, int accumulate,

@@ -55,6 +55,8 @@ struct ConvParams {
   int out2_ld;                   // the "fp16" precision mode), else null
   float* bn_partial;             // optional [STAT_ROWS][2][bn_C] per-(CTA, epilogue warp) sums / sums of squares of the
   int bn_C;                      // stored output (BatchNorm batch statistics fused into the epilogue), else null
+  int ngroups;                   // pair kernel: output-channel groups of N handled by ONE launch (wide layers: the blocks
+                                 // of all groups share the grid instead of ngroups launches of a few blocks each)
 };
 
 constexpr int MAX_NB = 8;
@@ -106,7 +108,7 @@ __device__ __forceinline__ void bn_stats_flush(float (&sv)[16], float (&sq)[16],
 // block, not once per M-tile (the reduction is as long as the rest of the chunk's epilogue).
 template <int N>
 __device__ __forceinline__ void epilogue_block(const ConvParams& p, uint32_t acc0, const bool (&valid)[T_TILES],
-                                               const long long (&pix)[T_TILES], int stat_row, int lane) {
+                                               const long long (&pix)[T_TILES], int stat_row, int lane, int nofs = 0) {
   const bool f16 = (p.flags & FLAG_F16) != 0;
 #pragma unroll 1
   for (int j = 0; j < N / 16; ++j) {
@@ -125,12 +127,12 @@ __device__ __forceinline__ void epilogue_block(const ConvParams& p, uint32_t acc
         if (p.bias) {
 #pragma unroll
           for (int k = 0; k < 16; k += 4) {
-            float4 bv = *reinterpret_cast<const float4*>(p.bias + j * 16 + k);
+            float4 bv = *reinterpret_cast<const float4*>(p.bias + nofs + j * 16 + k);
             f[k] += bv.x; f[k + 1] += bv.y; f[k + 2] += bv.z; f[k + 3] += bv.w;
           }
         }
         if (p.residual) {
-          const __nv_bfloat16* rp = p.residual + pix[mt] * p.res_ld + j * 16;
+          const __nv_bfloat16* rp = p.residual + pix[mt] * p.res_ld + nofs + j * 16;
 #pragma unroll
           for (int k = 0; k < 16; k += 4) {
             float4 rv = f16 ? ld4(reinterpret_cast<const __half*>(rp) + k) : ld4(rp + k);
@@ -155,7 +157,7 @@ __device__ __forceinline__ void epilogue_block(const ConvParams& p, uint32_t acc
             o[k] = *reinterpret_cast<uint32_t*>(&h);
           }
         }
-        uint4* op = reinterpret_cast<uint4*>(p.out + pix[mt] * p.out_ld + j * 16);
+        uint4* op = reinterpret_cast<uint4*>(p.out + pix[mt] * p.out_ld + nofs + j * 16);
         op[0] = make_uint4(o[0], o[1], o[2], o[3]);
         op[1] = make_uint4(o[4], o[5], o[6], o[7]);
         if (p.out2) {
@@ -165,7 +167,7 @@ __device__ __forceinline__ void epilogue_block(const ConvParams& p, uint32_t acc
             __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
             o2[k] = *reinterpret_cast<uint32_t*>(&h);
           }
-          uint4* op2 = reinterpret_cast<uint4*>(p.out2 + pix[mt] * p.out2_ld + j * 16);
+          uint4* op2 = reinterpret_cast<uint4*>(p.out2 + pix[mt] * p.out2_ld + nofs + j * 16);
           op2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
           op2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
         }
@@ -173,7 +175,7 @@ __device__ __forceinline__ void epilogue_block(const ConvParams& p, uint32_t acc
       }
     }
     if (p.bn_partial)      // (warp-uniform: all 32 lanes take part in the shuffles)
-      bn_stats_flush(sv, sq, p.bn_partial, p.bn_C, stat_row, j * 16, lane);
+      bn_stats_flush(sv, sq, p.bn_partial, p.bn_C, stat_row, nofs + j * 16, lane);
   }
 }
 
@@ -439,7 +441,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
   constexpr uint32_t ACC_COLS = T_TILES * N;
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;    // 512 or 256
   const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
-  const int npb = (p.nblocks + 1) >> 1;           // pair-blocks
+  const int npb_pix = (p.nblocks + 1) >> 1;       // pair-blocks of one output-channel group
+  const int npb = npb_pix * p.ngroups;            // pair-block pb = (group pb / npb_pix, pixel pair-block pb % npb_pix)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA_SLOTS; ++i) { mbar_init(a_full(i), 2); mbar_init(a_empty(i), 1); }
@@ -461,7 +464,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     const uint32_t row_bytes = (uint32_t)(8 + 2 * p.pad) * 128u;
     int ac = 0;
     for (int pb = pair; pb < npb; pb += npairs) {
-      const int blk = 2 * pb + (int)rank;          // may be == nblocks for the last odd block: all rows out of range
+      const int blk = 2 * (pb % npb_pix) + (int)rank;   // may be == nblocks for the last odd block: all rows out of range
       const int xg = blk % p.nxg, vb = blk / p.nxg;
       const int x0 = xg * 8, v0 = vb * (16 * T_TILES);
       for (int c = 0; c < p.nchunks; ++c, ++ac) {
@@ -494,11 +497,12 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
       const int rows_per_tile = p.w_tile_elems / 64;     // Cout_total
       int it = 0;
       for (int pb = pair; pb < npb; pb += npairs) {
+        const int row0 = (pb / npb_pix) * N + (int)rank * (N / 2);
         for (int k = 0; k < per_block; ++k, ++it) {
           const int st = it % NB;
           const uint32_t full_leader = b_full(st) & PEER_MASK;
           mbar_wait(b_empty(st), ((it / NB) & 1) ^ 1);
-          tma_load_2d_2sm(b_base + st * B_HALF, &wmap, 0, k * rows_per_tile + (int)rank * (N / 2), full_leader);
+          tma_load_2d_2sm(b_base + st * B_HALF, &wmap, 0, k * rows_per_tile + row0, full_leader);
           if (leader) mbar_expect_tx(b_full(st), 2u * B_HALF);
           else mbar_arrive_cluster(full_leader);
         }
@@ -562,7 +566,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
     int lb = 0;
     for (int pb = pair; pb < npb; pb += npairs, ++lb) {
       const int buf = lb & 1;
-      const int blk = 2 * pb + (int)rank;
+      const int blk = 2 * (pb % npb_pix) + (int)rank;
       const int xg = blk % p.nxg, vb = blk / p.nxg;
       const int x0 = xg * 8, v0 = vb * (16 * T_TILES);
       mbar_wait(t_full(buf), (lb >> 1) & 1);
@@ -577,7 +581,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         valid[mt] = blk < p.nblocks && vr < p.Vtotal && y < p.H;
         pix[mt] = ((long long)n * p.H + y) * p.W + x0 + wx;
       }
-      epilogue_block<N>(p, acc0, valid, pix, (int)blockIdx.x * 4 + q, lane);
+      epilogue_block<N>(p, acc0, valid, pix, (int)blockIdx.x * 4 + q, lane, (pb / npb_pix) * N);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(t_empty(buf) & PEER_MASK);
@@ -927,7 +931,7 @@ int launch_conv_pair(const CUtensorMap& tmap, ConvParams p, int cout_total, int 
   p.nb_stages = stages;
   size_t smem = fixed + (size_t)stages * half;
   TSR_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int npb = (p.nblocks + 1) / 2;
+  int npb = (p.nblocks + 1) / 2 * p.ngroups;
   int pairs = npb < num_sms() / 2 ? npb : num_sms() / 2;
   conv_tc_pair_kernel<N><<<2 * pairs, NUM_THREADS, smem, stream>>>(tmap, wmap, p);
   TSR_CHECK_LAUNCH("conv2d_tc_pair");
@@ -1067,7 +1071,7 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
   p.nblocks = nvb * p.nxg;
   // output channels are produced in groups of 128 (or a trailing 64): rows n0.. of every pre-swizzled weight tile
   for (int n0 = 0; n0 < Cout;) {
-    const int nt = (Cout - n0) >= 128 ? 128 : 64;
+    int nt = (Cout - n0) >= 128 ? 128 : 64;
     p.w = (const __nv_bfloat16*)w_packed + (size_t)n0 * 64;
     p.bias = bias ? bias + n0 : nullptr;
     p.residual = residual ? (const __nv_bfloat16*)residual + n0 : nullptr;
@@ -1076,10 +1080,13 @@ int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* 
     p.out2_ld = out2_ld;
     p.bn_partial = bn_partial ? bn_partial + n0 : nullptr;
     p.bn_C = Cout;
+    p.ngroups = 1;
     int rc;
-    if (nt == 128 && !(g_desc_mode & 16))   // bit 4 set = force the single-CTA kernel
+    if (nt == 128 && !(g_desc_mode & 16)) { // bit 4 set = force the single-CTA kernel
+      p.ngroups = (Cout - n0) / 128;        // all remaining 128-wide groups in this one launch
       rc = launch_conv_pair<128>(tmap, p, Cout, n0, (const __nv_bfloat16*)w_packed + (size_t)n0 * 64, stream);
-    else if (nt == 64 && !(g_desc_mode & 16) && !(g_desc_mode & 32))
+      nt = 128 * p.ngroups;
+    } else if (nt == 64 && !(g_desc_mode & 16) && !(g_desc_mode & 32))
       rc = launch_conv_pair<64>(tmap, p, Cout, n0, (const __nv_bfloat16*)w_packed + (size_t)n0 * 64, stream);
     else
       rc = nt == 128 ? launch_conv<128>(tmap, p, stream) : launch_conv<64>(tmap, p, stream);
@@ -1116,16 +1123,37 @@ static void wgrad_plan(int B, int H, int W, int Cin, int Cout, int KS, int* nspl
 
 size_t tsr_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS) {
   int ns, nb, bps;
+  if (Cout > 128) Cout = 128;        // wider layers run 128 output channels at a time through the same workspace
   wgrad_plan(B, H, W, Cin, Cout, KS, &ns, &nb, &bps);
   return (size_t)ns * KS * KS * Cin * Cout * sizeof(float);
 }
 
 // dw_oihw (fp32, [Cout][Cin][KS][KS]) (+)= wgrad of the conv;  in / dout are bf16 NHWC views.
+// Cout = 64, 128, or a multiple of 128 (the MLP layers of tPSFNet): 128 output channels per launch, one after the other
+// on `stream` through the same workspace.
+static int wgrad_tc_group(const void* in, int in_ld, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
+                          size_t ws_bytes, int B, int H, int W, int Cin, int Cout, int KS, int accumulate,
+                          cudaStream_t stream);
+
 int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
                         size_t ws_bytes, int B, int H, int W, int Cin, int Cout, int KS, int accumulate,
                         cudaStream_t stream) {
   TSR_REQUIRE(in && dout && dw_oihw && workspace, "conv2d_wgrad_tc: null pointer");
-  TSR_REQUIRE(Cout == 64 || Cout == 128, "conv2d_wgrad_tc: Cout must be 64 or 128 (got %d)", Cout);
+  TSR_REQUIRE(Cout == 64 || (Cout > 0 && Cout % 128 == 0), "conv2d_wgrad_tc: Cout must be 64 or a multiple of 128 (got %d)", Cout);
+  if (Cout <= 128)
+    return wgrad_tc_group(in, in_ld, dout, dout_ld, dw_oihw, workspace, ws_bytes, B, H, W, Cin, Cout, KS, accumulate, stream);
+  for (int g = 0; g < Cout / 128; ++g) {
+    int rc = wgrad_tc_group(in, in_ld, (const __nv_bfloat16*)dout + g * 128, dout_ld,
+                            dw_oihw + (size_t)g * 128 * Cin * KS * KS, workspace, ws_bytes, B, H, W, Cin, 128, KS, accumulate,
+                            stream);
+    if (rc) return rc;
+  }
+  return TSR_OK;
+}
+
+static int wgrad_tc_group(const void* in, int in_ld, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
+                          size_t ws_bytes, int B, int H, int W, int Cin, int Cout, int KS, int accumulate,
+                          cudaStream_t stream) {
   TSR_REQUIRE(Cin % 64 == 0 && Cin > 0, "conv2d_wgrad_tc: Cin must be a multiple of 64 (got %d)", Cin);
   TSR_REQUIRE(KS == 1 || KS == 3 || KS == 5, "conv2d_wgrad_tc: kernel size %d unsupported", KS);
   TSR_REQUIRE(W % 8 == 0 && H % 8 == 0, "conv2d_wgrad_tc: H and W must be multiples of 8");

@@ -19,7 +19,7 @@ def _model(S, seed_w):
 
 
 @pytest.mark.parametrize("Cin,Cout,KS,B", [(64, 64, 3, 2), (128, 128, 5, 3), (64, 64, 5, 1), (128, 128, 3, 5), (256, 64, 1, 2),
-                                           (448, 64, 3, 2)])
+                                           (448, 64, 3, 2), (256, 256, 3, 2), (256, 1024, 1, 3), (1024, 256, 1, 2)])
 def test_tc_conv_fwd_dgrad_wgrad_against_fp32(Cin, Cout, KS, B):
     """tcgen05 kernels vs an fp32 convolution of the same bf16-rounded operands (ragged batch sizes included)."""
     import torch.nn.functional as F
@@ -257,7 +257,7 @@ def test_large_batch_properties(mode):
         tb.set_precision("fp32")
 
 
-@pytest.mark.parametrize("Cout,KS,B,f16", [(64, 3, 3, 1), (128, 5, 2, 0), (64, 1, 5, 1)])
+@pytest.mark.parametrize("Cout,KS,B,f16", [(64, 3, 3, 1), (128, 5, 2, 0), (64, 1, 5, 1), (384, 3, 2, 1)])
 def test_tc_conv_fused_bn_statistics(Cout, KS, B, f16):
     """Batch statistics from the conv epilogue (per-(CTA, warp) partials, finished by tsr_bn_finalize_partials) equal the
     statistics of the stored output tensor; bit-deterministic."""

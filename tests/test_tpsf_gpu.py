@@ -223,3 +223,90 @@ def test_psf_kernels_size_independent_properties():
     assert torch.equal(psf2[big], 2 * psf[big]) and torch.allclose(psf2, 2 * psf, rtol=0, atol=1e-37)
     HRs, LRds, _, dabs = run(ab[:37].contiguous(), depth[:37].contiguous(), dL[:37].contiguous())
     assert torch.equal(HRs, HR[:37]) and torch.equal(LRds, LRd[:37]) and torch.equal(dabs, dab[:37])
+
+
+@pytest.mark.parametrize("mode", ["fp16", "bf16"])
+def test_tpsf_16bit_modes_train_step_within_tensor_core_bound(mode, monkeypatch):
+    """16-bit precision modes: the two wide MLP layers run on the tcgen05 kernels (forward in fp16 / bf16, gradients on
+    bf16 tensors).  north_star's tensor-core bound is 1e-2 relative on the outputs; parameter gradients are held to 5e-2
+    rel-L2 (bf16 operands) against the CPU oracle's autograd; the fp32 mode of the same module is the yardstick."""
+    import tactilesr_b200 as tb
+    from oracle import tpsf_oracle as po
+    from tactilesr_b200 import _lib
+    from tactilesr_b200.model import tPSFNet
+    import sys
+    import tactilesr_b200.model  # noqa: F401
+    tmod = sys.modules["tactilesr_b200.model.tPSFNet"]       # (the package attribute of that name is the class)
+    monkeypatch.setattr(tmod, "_TC_MIN_BATCH", 64)      # (production gate: 1024 -- smaller batches are launch-bound)
+    B = 64
+    sd = po.make_state(31)
+    gen = torch.Generator().manual_seed(32)
+    LR = torch.rand(B, 3, 4, 4, generator=gen) * 13
+    depth = po.synthetic_depth(B, 33)
+    leaf = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    HRo, LRdo, _, abo = po.tpsf_forward(leaf, LR.double(), depth.double().unsqueeze(1))
+    torch.nn.functional.mse_loss(LR.double()[:, 2:3], LRdo).backward()
+    m = tPSFNet(1.4, None, device="cuda")
+    m.load_state_dict(sd)
+    m = m.cuda()
+    tol_out = {"fp16": 5e-3, "bf16": 1e-2}[mode]
+    try:
+        tb.set_precision(mode)
+        n0 = _lib.launch_count()
+        HR, LRd, _, ab = m(LR.cuda(), depth.cuda().unsqueeze(1))
+        torch.nn.functional.mse_loss(LR.cuda()[:, 2:3], LRd).backward()
+        assert _lib.launch_count() - n0 > 20
+        e = {k: rel_l2(v, r) for k, v, r in (("ab", ab, abo), ("HR", HR, HRo), ("LRd", LRd, LRdo))}
+        eg = {n: rel_l2(p.grad, leaf[n].grad) for n, p in m.named_parameters()}
+        print(mode, e, {k: f"{v:.1e}" for k, v in eg.items()})
+        assert max(e.values()) < tol_out, e
+        assert max(eg.values()) < 5e-2, eg
+        # ragged batch (not a multiple of 64): the fp32 kernels take over, results in the fp32 class
+        HR5, _, _, _ = m(LR[:5].cuda(), depth[:5].cuda().unsqueeze(1))
+        assert rel_l2(HR5, HRo[:5]) < 2e-5
+        # inference under no_grad takes the same tensor-core path
+        with torch.no_grad():
+            HRn, _, _, _ = m(LR.cuda(), depth.cuda().unsqueeze(1))
+        assert torch.equal(HRn, HR.detach())
+    finally:
+        tb.set_precision("fp32")
+
+
+def test_tpsf_fp16_mode_loss_curve_tracks_fp32_mode(monkeypatch):
+    """200 Adam steps of train/tPSFNet_train.py's iteration in fp32 and fp16 modes from the same weights and batches: the
+    loss curves stay within 2 % of each other (mean over the last 50 steps) and both decrease."""
+    import tactilesr_b200 as tb
+    from oracle import tpsf_oracle as po
+    from tactilesr_b200.model import tPSFNet
+    from tactilesr_b200.optim import FusedAdam
+    import sys
+    import tactilesr_b200.model  # noqa: F401
+    tmod = sys.modules["tactilesr_b200.model.tPSFNet"]       # (the package attribute of that name is the class)
+    monkeypatch.setattr(tmod, "_TC_MIN_BATCH", 64)
+    B, steps = 256, 200
+    depth = po.synthetic_depth(B, 41).cuda().unsqueeze(1)
+    gen = torch.Generator().manual_seed(42)
+    LRs = [(torch.rand(B, 3, 4, 4, generator=gen) * 13).cuda() for _ in range(8)]
+    curves = {}
+    try:
+        for mode in ("fp32", "fp16"):
+            tb.set_precision(mode)
+            m = tPSFNet(1.4, None, device="cuda")
+            m.load_state_dict(po.make_state(43))
+            m = m.cuda()
+            opt = FusedAdam(m.parameters(), lr=1e-4, weight_decay=1e-5)
+            losses = []
+            for i in range(steps):
+                LR = LRs[i % len(LRs)]
+                _, LRd, _, _ = m(LR, depth)
+                loss = torch.nn.functional.mse_loss(LR[:, 2:3], LRd)
+                opt.zero_grad(); loss.backward(); opt.step()
+                losses.append(loss)
+            curves[mode] = torch.stack(losses).float().cpu()
+    finally:
+        tb.set_precision("fp32")
+    a, b = curves["fp32"], curves["fp16"]
+    print("tPSF loss fp32 first/last", a[0].item(), a[-50:].mean().item(), "fp16", b[0].item(), b[-50:].mean().item())
+    assert a[-50:].mean() < a[:10].mean() and b[-50:].mean() < b[:10].mean()
+    assert abs(a[-50:].mean() - b[-50:].mean()) / a[-50:].mean() < 2e-2
+    assert ((a - b).abs() / a).max() < 0.1

@@ -1,10 +1,12 @@
-"""tPSFNet training-step timing (C2): python tools/tpsf_step.py [B ...]"""
+"""tPSFNet training-step timing (C2): [TSR_PRECISION=fp16] python tools/tpsf_step.py [B ...]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tactilesr_b200.model import tPSFNet
 from tactilesr_b200.optim import FusedAdam
 dev = "cuda"
+import tactilesr_b200 as tb
+tb.set_precision(os.environ.get("TSR_PRECISION", "fp32"))
 for Bp in [int(a) for a in sys.argv[1:]] or [256, 2048, 8192]:
     pm = tPSFNet(gama=1.4, perception_scale=None, device=dev).to(dev)
     popt = FusedAdam(pm.parameters(), lr=1e-4, weight_decay=1e-5)
