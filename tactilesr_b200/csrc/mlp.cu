@@ -119,6 +119,85 @@ __global__ void act_backward_kernel(const float* __restrict__ dy, const float* _
   }
 }
 
+// ---- thin layers (N <= 4 outputs: the 256 -> 3 softplus head of tPSFNet, reference model/tPSFNet.py:33-34) -------------------
+// A 128 x 64 GEMM tile would compute 61 dead columns; these kernels keep the N weight rows in registers instead.
+constexpr int THIN_MAX_N = 4;
+
+// y[m][n] = act(sum_k x[m][k] w[n][k] + b[n]): one warp per row, lane l owns k = 4 l + 128 j (K % 128 == 0, K <= 512)
+template <int KJ>
+__global__ void __launch_bounds__(256)
+thin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ y,
+                int M, int N, int act) {
+  const int lane = threadIdx.x & 31;
+  const int K = KJ * 128;
+  float4 wr[THIN_MAX_N][KJ];
+#pragma unroll
+  for (int n = 0; n < THIN_MAX_N; ++n)
+#pragma unroll
+    for (int j = 0; j < KJ; ++j)
+      wr[n][j] = n < N ? *reinterpret_cast<const float4*>(w + (size_t)n * K + j * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  for (int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M; m += warps) {
+    float s[THIN_MAX_N] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < KJ; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(x + (size_t)m * K + j * 128 + lane * 4);
+#pragma unroll
+      for (int n = 0; n < THIN_MAX_N; ++n)
+        s[n] = fmaf(v.x, wr[n][j].x, fmaf(v.y, wr[n][j].y, fmaf(v.z, wr[n][j].z, fmaf(v.w, wr[n][j].w, s[n]))));
+    }
+#pragma unroll
+    for (int n = 0; n < THIN_MAX_N; ++n) s[n] = warp_sum(s[n]);
+    if (lane < N) {
+      float v = (lane == 0 ? s[0] : lane == 1 ? s[1] : lane == 2 ? s[2] : s[3]) + (b ? b[lane] : 0.f);
+      if (act == 1) v = fmaxf(v, 0.f);
+      else if (act == 2) v = v > 20.f ? v : log1pf(expf(v));
+      y[(size_t)m * N + lane] = v;
+    }
+  }
+}
+
+// dx[m][k] = sum_n dpre[m][n] w[n][k]: one thread per (m, 4 k)
+__global__ void thin_dx_kernel(const float* __restrict__ dpre, const float* __restrict__ w, float* __restrict__ dx, int M, int N,
+                               int K) {
+  const int k4 = K >> 2;
+  const long long total = (long long)M * k4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % k4);
+    const long long m = i / k4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = 0; n < N; ++n) {
+      const float g = dpre[m * N + n];
+      const float4 wv = *reinterpret_cast<const float4*>(w + (size_t)n * K + q * 4);
+      a.x = fmaf(g, wv.x, a.x); a.y = fmaf(g, wv.y, a.y); a.z = fmaf(g, wv.z, a.z); a.w = fmaf(g, wv.w, a.w);
+    }
+    *reinterpret_cast<float4*>(dx + m * K + q * 4) = a;
+  }
+}
+
+// partial[slab][n][k] = sum_{m in slab} dpre[m][n] x[m][k]: block = one slab of rows, thread = k (fixed order => deterministic)
+__global__ void __launch_bounds__(256)
+thin_dw_kernel(const float* __restrict__ dpre, const float* __restrict__ x, float* __restrict__ partial, int M, int N, int K,
+               int rows_per_slab) {
+  const int m0 = blockIdx.x * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float a[THIN_MAX_N] = {0.f, 0.f, 0.f, 0.f};
+    for (int m = m0; m < m1; ++m) {
+      const float xv = x[(size_t)m * K + k];
+#pragma unroll
+      for (int n = 0; n < THIN_MAX_N; ++n)
+        if (n < N) a[n] = fmaf(dpre[(size_t)m * N + n], xv, a[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < THIN_MAX_N; ++n)
+      if (n < N) partial[((size_t)blockIdx.x * N + n) * K + k] = a[n];
+  }
+}
+
+constexpr int THIN_SLAB = 32;
+inline bool thin_shape(int N, int K) { return N <= THIN_MAX_N && K % 128 == 0 && K <= 512; }
+inline int thin_slabs(int M) { return tsr_cdiv(M, THIN_SLAB); }
+
 }  // namespace
 
 extern "C" {
@@ -136,6 +215,19 @@ int tsr_sgemm_strided(const float* A, long long sam, long long sak, const float*
 // y[M][N] = act(x[M][K] W[N][K]^T + b)          (nn.Linear forward)
 int tsr_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int N, int K, int act,
                    cudaStream_t stream) {
+  if (thin_shape(N, K)) {
+    TSR_REQUIRE(x && w && y && M > 0, "linear_fwd: bad argument");
+    int grid = tsr_cdiv(M, 8);
+    if (grid > 4 * 148) grid = 4 * 148;
+    switch (K / 128) {
+      case 1: thin_fwd_kernel<1><<<grid, 256, 0, stream>>>(x, w, b, y, M, N, act); break;
+      case 2: thin_fwd_kernel<2><<<grid, 256, 0, stream>>>(x, w, b, y, M, N, act); break;
+      case 3: thin_fwd_kernel<3><<<grid, 256, 0, stream>>>(x, w, b, y, M, N, act); break;
+      default: thin_fwd_kernel<4><<<grid, 256, 0, stream>>>(x, w, b, y, M, N, act); break;
+    }
+    TSR_CHECK_LAUNCH("thin_fwd");
+    return TSR_OK;
+  }
   return tsr_sgemm_strided(x, K, 1, w, 1, K, y, N, M, N, K, b, act, 0, stream);
 }
 
@@ -150,6 +242,7 @@ static int linear_wgrad_splits(int M, int N, int K) {
 }
 
 size_t tsr_linear_bwd_workspace(int M, int N, int K) {
+  if (thin_shape(N, K)) return (size_t)thin_slabs(M) * N * K * sizeof(float);
   int s = linear_wgrad_splits(M, N, K);
   return s > 1 ? (size_t)s * N * K * sizeof(float) : 0;
 }
@@ -165,6 +258,25 @@ int tsr_linear_bwd(const float* dy, const float* out, const float* x, const floa
   if (grid > 2048) grid = 2048;
   act_backward_kernel<<<grid, 256, 0, stream>>>(dy, out, dpre, n, act);
   TSR_CHECK_LAUNCH("act_backward");
+  if (thin_shape(N, K)) {
+    const int S = thin_slabs(M);
+    TSR_REQUIRE(workspace && ws_bytes >= (size_t)S * N * K * sizeof(float), "linear_bwd: workspace too small");
+    thin_dw_kernel<<<S, 256, 0, stream>>>(dpre, x, (float*)workspace, M, N, K, THIN_SLAB);
+    TSR_CHECK_LAUNCH("thin_dw");
+    long long nk = (long long)N * K;
+    sgemm_split_reduce_kernel<<<(int)((nk + 255) / 256), 256, 0, stream>>>((const float*)workspace, S, nk, dw, accumulate);
+    TSR_CHECK_LAUNCH("linear_wgrad_reduce");
+    colsum_block_kernel<<<N, 256, 0, stream>>>(dpre, M, N, db, accumulate);
+    TSR_CHECK_LAUNCH("colsum_block");
+    if (dx) {
+      long long t = (long long)M * (K / 4);
+      int g = (int)((t + 255) / 256);
+      if (g > 8 * 148) g = 8 * 148;
+      thin_dx_kernel<<<g, 256, 0, stream>>>(dpre, w, dx, M, N, K);
+      TSR_CHECK_LAUNCH("thin_dx");
+    }
+    return TSR_OK;
+  }
   // dW[n][k] = sum_m dpre[m][n] x[m][k]:  A(n, m) = dpre[m*N + n], B(m, k) = x[m*K + k]
   const int S = linear_wgrad_splits(M, N, K);
   if (S > 1) {
