@@ -684,7 +684,8 @@ constexpr int WG2_MAX_STAGES = 8;
 // halo tile), so a 64-channel layer fills all 128 rows with useful work (v2 duplicated 64 rows: half the MMAs wasted).
 // One accumulator of Cout columns per M-group; a CTA owns up to 512/Cout M-groups over its whole pixel range.
 struct Wgrad3Params {
-  float* partial;               // [nsplit][taps][Cin][Cout]
+  float* partial;               // [output group = blockIdx.z][nsplit][taps][Cin][Cout]
+  long long group_stride;       // floats between the partials of consecutive output groups (wide layers: Cout_total > 128)
   int B, H, W, KS, pad, P;
   int Cin, Cout, cochunks;
   int tap_mode;                 // 0: atoms = 2 chunks of one tap, 1: atoms = 2 taps of one chunk
@@ -746,7 +747,7 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int y0 = (t / p.tiles_x) * 8, x0 = (t % p.tiles_x) * 8;
         const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
         for (int cc = 0; cc < p.cochunks; ++cc)
-          tma_load_4d(dy0 + (uint32_t)cc * 8192u, &tmap_dy, cc * 64, x0, y0, n, full(st));
+          tma_load_4d(dy0 + (uint32_t)cc * 8192u, &tmap_dy, (int)blockIdx.z * p.Cout + cc * 64, x0, y0, n, full(st));
         for (int h = 0; h < nxt; ++h)
           tma_load_4d(dy0 + (uint32_t)p.dy_stage_bytes + (uint32_t)h * p.xtile_bytes, &tmap_x, (unit * nxt + h) * 64,
                       x0 - p.pad, y0 - p.pad, n, full(st));
@@ -822,7 +823,8 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         tap = g0 + g;
         ci = (unit * 2 + atom) * 64 + cil;
       }
-      float* dst = p.partial + (((size_t)blockIdx.y * taps + (valid ? tap : 0)) * p.Cin + ci) * p.Cout;
+      float* dst = p.partial + (size_t)blockIdx.z * p.group_stride +
+                   (((size_t)blockIdx.y * taps + (valid ? tap : 0)) * p.Cin + ci) * p.Cout;
 #pragma unroll 1
       for (int j = 0; j < p.Cout / 16; ++j) {
         uint32_t v[16];
@@ -852,19 +854,22 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   }
 }
 
-// level 2 (shared with the fp32 path's layout): dw_oihw[co][ci][tap] (+)= sum_s partial[s][tap][ci][co]
+// level 2 (shared with the fp32 path's layout): dw_oihw[g Cout + co][ci][tap] (+)= sum_s partial[g][s][tap][ci][co]
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int S, int taps,
-                                       int Cin, int Cout, int accumulate) {
+                                       int Cin, int Cout, int accumulate, int G) {
   long long n = (long long)taps * Cin * Cout;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n * G) return;
+  const int g = (int)(i / n);
+  i -= g * n;
   int co = (int)(i % Cout);
   long long r = i / Cout;
   int ci = (int)(r % Cin);
   int tap = (int)(r / Cin);
+  const float* pg = partial + (long long)g * S * n;
   float s = 0.f;
-  for (int k = 0; k < S; ++k) s += partial[(long long)k * n + i];
-  long long o = ((long long)co * Cin + ci) * taps + tap;
+  for (int k = 0; k < S; ++k) s += pg[(long long)k * n + i];
+  long long o = (((long long)g * Cout + co) * Cin + ci) * taps + tap;
   dw[o] = accumulate ? dw[o] + s : s;
 }
 
@@ -1110,10 +1115,10 @@ static Wgrad3Plan wgrad3_plan(int Cin, int Cout, int KS) {
 }
 
 // pixel-tile split: a single wave, never more CTAs than SMs
-static void wgrad_plan(int B, int H, int W, int Cin, int Cout, int KS, int* nsplit, int* nblocks, int* bps) {
+static void wgrad_plan(int B, int H, int W, int Cin, int Cout, int KS, int* nsplit, int* nblocks, int* bps, int G = 1) {
   Wgrad3Plan q = wgrad3_plan(Cin, Cout, KS);
   *nblocks = B * (H / 8) * (W / 8);
-  const int ctas = q.ncta_groups * q.nunits;
+  const int ctas = q.ncta_groups * q.nunits * G;
   int s = num_sms() / ctas;
   if (s > *nblocks) s = *nblocks;
   if (s < 1) s = 1;
@@ -1123,37 +1128,21 @@ static void wgrad_plan(int B, int H, int W, int Cin, int Cout, int KS, int* nspl
 
 size_t tsr_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS) {
   int ns, nb, bps;
-  if (Cout > 128) Cout = 128;        // wider layers run 128 output channels at a time through the same workspace
-  wgrad_plan(B, H, W, Cin, Cout, KS, &ns, &nb, &bps);
-  return (size_t)ns * KS * KS * Cin * Cout * sizeof(float);
+  const int G = Cout > 128 ? Cout / 128 : 1;      // wider layers: groups of 128 output channels (grid.z) in one launch
+  if (Cout > 128) Cout = 128;
+  wgrad_plan(B, H, W, Cin, Cout, KS, &ns, &nb, &bps, G);
+  return (size_t)G * ns * KS * KS * Cin * Cout * sizeof(float);
 }
 
 // dw_oihw (fp32, [Cout][Cin][KS][KS]) (+)= wgrad of the conv;  in / dout are bf16 NHWC views.
-// Cout = 64, 128, or a multiple of 128 (the MLP layers of tPSFNet): 128 output channels per launch, one after the other
-// on `stream` through the same workspace.
-static int wgrad_tc_group(const void* in, int in_ld, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
-                          size_t ws_bytes, int B, int H, int W, int Cin, int Cout, int KS, int accumulate,
-                          cudaStream_t stream);
-
+// Cout = 64, 128, or a multiple of 128 (the MLP layers of tPSFNet): groups of 128 output channels are grid.z of one launch.
 int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
-                        size_t ws_bytes, int B, int H, int W, int Cin, int Cout, int KS, int accumulate,
+                        size_t ws_bytes, int B, int H, int W, int Cin, int Cout_total, int KS, int accumulate,
                         cudaStream_t stream) {
   TSR_REQUIRE(in && dout && dw_oihw && workspace, "conv2d_wgrad_tc: null pointer");
-  TSR_REQUIRE(Cout == 64 || (Cout > 0 && Cout % 128 == 0), "conv2d_wgrad_tc: Cout must be 64 or a multiple of 128 (got %d)", Cout);
-  if (Cout <= 128)
-    return wgrad_tc_group(in, in_ld, dout, dout_ld, dw_oihw, workspace, ws_bytes, B, H, W, Cin, Cout, KS, accumulate, stream);
-  for (int g = 0; g < Cout / 128; ++g) {
-    int rc = wgrad_tc_group(in, in_ld, (const __nv_bfloat16*)dout + g * 128, dout_ld,
-                            dw_oihw + (size_t)g * 128 * Cin * KS * KS, workspace, ws_bytes, B, H, W, Cin, 128, KS, accumulate,
-                            stream);
-    if (rc) return rc;
-  }
-  return TSR_OK;
-}
-
-static int wgrad_tc_group(const void* in, int in_ld, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
-                          size_t ws_bytes, int B, int H, int W, int Cin, int Cout, int KS, int accumulate,
-                          cudaStream_t stream) {
+  TSR_REQUIRE(Cout_total == 64 || (Cout_total > 0 && Cout_total % 128 == 0), "conv2d_wgrad_tc: Cout must be 64 or a multiple of 128 (got %d)", Cout_total);
+  const int G = Cout_total > 128 ? Cout_total / 128 : 1;
+  const int Cout = Cout_total > 128 ? 128 : Cout_total;
   TSR_REQUIRE(Cin % 64 == 0 && Cin > 0, "conv2d_wgrad_tc: Cin must be a multiple of 64 (got %d)", Cin);
   TSR_REQUIRE(KS == 1 || KS == 3 || KS == 5, "conv2d_wgrad_tc: kernel size %d unsupported", KS);
   TSR_REQUIRE(W % 8 == 0 && H % 8 == 0, "conv2d_wgrad_tc: H and W must be multiples of 8");
@@ -1162,8 +1151,8 @@ static int wgrad_tc_group(const void* in, int in_ld, const void* dout, int dout_
   if (!enc) { tsr_set_error("conv2d_wgrad_tc: cuTensorMapEncodeTiled unavailable"); return TSR_ERR_CUDA; }
   const int pad = KS / 2, taps = KS * KS;
   int nsplit = 1, nblocks = 0, bps = 0;
-  wgrad_plan(B, H, W, Cin, Cout, KS, &nsplit, &nblocks, &bps);
-  size_t need = (size_t)nsplit * taps * Cin * Cout * sizeof(float);
+  wgrad_plan(B, H, W, Cin, Cout, KS, &nsplit, &nblocks, &bps, G);
+  size_t need = (size_t)G * nsplit * taps * Cin * Cout * sizeof(float);
   if (ws_bytes < need) { tsr_set_error("conv2d_wgrad_tc: workspace too small (%zu < %zu)", ws_bytes, need); return TSR_ERR_WORKSPACE; }
   CUtensorMap tmx, tmdy;
   cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -1177,7 +1166,7 @@ static int wgrad_tc_group(const void* in, int in_ld, const void* dout, int dout_
     if (r != CUDA_SUCCESS) { tsr_set_error("conv2d_wgrad_tc: tensor map (x) failed (%d)", (int)r); return TSR_ERR_CUDA; }
   }
   {
-    cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gdim[4] = {(cuuint64_t)Cout_total, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)dout_ld * 2, (cuuint64_t)W * dout_ld * 2, (cuuint64_t)H * W * dout_ld * 2};
     cuuint32_t box[4] = {64, 8, 8, 1};
     CUresult r = enc(&tmdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dout), gdim, gstr, box, estr,
@@ -1188,6 +1177,7 @@ static int wgrad_tc_group(const void* in, int in_ld, const void* dout, int dout_
   Wgrad3Plan pl = wgrad3_plan(Cin, Cout, KS);
   Wgrad3Params q;
   q.partial = (float*)workspace;
+  q.group_stride = (long long)nsplit * taps * Cin * Cout;
   q.B = B; q.H = H; q.W = W; q.KS = KS; q.pad = pad; q.P = 8 + 2 * pad;
   q.Cin = Cin; q.Cout = Cout; q.cochunks = Cout / 64;
   q.tap_mode = pl.tap_mode; q.ngroups_total = pl.ngroups_total; q.gpc = pl.gpc;
@@ -1202,12 +1192,12 @@ static int wgrad_tc_group(const void* in, int in_ld, const void* dout, int dout_
   q.nstages = ns;
   size_t smem = 1024 + (size_t)ns * q.stage_bytes + 512;
   TSR_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(q.ncta_groups * q.nunits, nsplit);
+  dim3 grid(q.ncta_groups * q.nunits, nsplit, G);
   wgrad_tc3_kernel<<<grid, NUM_THREADS, smem, stream>>>(tmx, tmdy, q);
   TSR_CHECK_LAUNCH("conv2d_wgrad_tc3");
-  long long n = (long long)taps * Cin * Cout;
+  long long n = (long long)taps * Cin * Cout * G;
   wgrad_tc_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>((const float*)workspace, dw_oihw, nsplit, taps, Cin,
-                                                                    Cout, accumulate);
+                                                                    Cout, accumulate, G);
   TSR_CHECK_LAUNCH("wgrad_tc_reduce");
   return TSR_OK;
 }
