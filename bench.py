@@ -264,6 +264,11 @@ def measure_extras(dev, model, B):
         with torch.no_grad():
             ms = timeit(lambda: pm(x, depth), 5)
         out[f"tpsf_fwd_samples_per_s{tag}"] = Bp / (ms * 1e-3)
+        if Bp != 256:      # the same step with the MLP pinned to the fp32 kernels (<= 1e-5 mode; in the 16-bit modes the two
+            pm.precision = "fp32"   # wide layers run on the tcgen05 conv kernels from B = 1024 up)
+            ms = timeit(pstep, 5)
+            out[f"tpsf_train_fp32_mode_samples_per_s{tag}"] = Bp / (ms * 1e-3)
+            pm.precision = None
         if Bp == 256:      # the same step through Trainer_tPSF with the iteration captured in a CUDA graph
             from tactilesr_b200.train.tPSFNet_train import Trainer_tPSF
             pdata = [(x * 100, depth[:, 0])] * 2
