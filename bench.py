@@ -87,13 +87,13 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synthetic_batches(n, B, seed, pin):
-    """LR (B,3,4,4) in taxel units 0..8 and HR_raw (B,1,100,100) in 0..250."""
+def synthetic_batches(n, B, seed, pin, S=1):
+    """LR (B,3S,4,4) in taxel units 0..8 and HR_raw (B,1,100,100) in 0..250."""
     import torch
     g = torch.Generator().manual_seed(seed)
     out = []
     for _ in range(n):
-        LR = torch.rand(B, 3, 4, 4, generator=g) * 8
+        LR = torch.rand(B, 3 * S, 4, 4, generator=g) * 8
         HR = torch.rand(B, 1, 100, 100, generator=g) * 250
         if pin:
             LR, HR = LR.pin_memory(), HR.pin_memory()
@@ -325,10 +325,15 @@ def run_ours(args):
     _lib.check(_lib.lib().tsr_check_device(), "device check")
     tb.set_precision(args.precision)
     B = args.batch
+    S = args.seqs                                           # 1 = the headline workload; 7 = the tactileSRSeqs model (C4)
+    global FLOP_PER_SAMPLE_TRAIN, FLOP_PER_SAMPLE_FWD
+    if S == 7:
+        FLOP_PER_SAMPLE_TRAIN, FLOP_PER_SAMPLE_FWD = 48.229e9, 16.091e9
+    sr_config = dict(SR_CONFIG, seqsCnt=S)
     torch.manual_seed(42)                                   # identical weights on every rank
-    model, opt = build_model_and_optimizer(SR_CONFIG, dev)
+    model, opt = build_model_and_optimizer(sr_config, dev)
     nb = 4                                                  # rotating distinct batches
-    host = synthetic_batches(nb, B, 1000 + rank, pin=True)
+    host = synthetic_batches(nb, B, 1000 + rank, pin=True, S=S)
     devb = [(a.to(dev), b.to(dev)) for a, b in host]
 
     class Loader:
@@ -340,7 +345,7 @@ def run_ours(args):
                     yield it
 
     sched = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.8)
-    tr = Trainer_tactileSR(SR_CONFIG, model=model, optimizer=opt, lr_scheduler=sched, data_loader=Loader(devb),
+    tr = Trainer_tactileSR(sr_config, model=model, optimizer=opt, lr_scheduler=sched, data_loader=Loader(devb),
                            max_iters=10 ** 9, log_period=10 ** 9, device=dev)
     tr._setup_dp()
 
@@ -418,7 +423,7 @@ def run_ours(args):
                 "achieved": value / world * FLOP_PER_SAMPLE_TRAIN / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": value / world * FLOP_PER_SAMPLE_TRAIN / 1e12 / pk["tf_sust"], "peak_source": pk["src"] + " bf16 sustained", "traffic": None}
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and S == 1:
         v, cores = cpu_reference_steps(32, 12, 1)
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                "sample": "12 train steps of B=32 (reference batch size, config/default.py:46) after 1 warm-up; oracle port of the reference CPU path"}
@@ -426,16 +431,16 @@ def run_ours(args):
         "metric": "SR train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "fp16", "fp32": "f32"}[args.precision], "data": "synthetic",
-        "config": {"workload": "TactileSR(seqsCnt=1) train step: fwd + fused HR-prep/MSE + bwd + fused Adam(lr 1e-3, wd 1e-2)"
+        "config": {"workload": f"TactileSR(seqsCnt={S}) train step: fwd + fused HR-prep/MSE + bwd + fused Adam(lr 1e-3, wd 1e-2)"
                                + (" + bucketed NCCL grad all-reduce" if world > 1 else ""),
-                   "per_gpu_batch": B, "global_batch": B * world, "input": "LR (B,3,4,4), HR (B,1,100,100)",
+                   "per_gpu_batch": B, "global_batch": B * world, "input": f"LR (B,{3 * S},4,4), HR (B,1,100,100)",
                    "precision_mode": args.precision + {"fp16": " (fp16 activations / forward weights, bf16 gradients, fp32 accumulation and statistics)",
                                                        "bf16": " (bf16 storage, fp32 accumulation and statistics)", "fp32": ""}[args.precision],
                    "parallelism": f"dp{world}",
                    "l2": "per-step working set (saved activations, B x ~26-52 MB) >> 126 MB L2; 4 rotating input batches"},
         "tensor_roofline_frac_step": value / world * FLOP_PER_SAMPLE_TRAIN / 1e12 / pk["tf_sust"],
         "roofline": roof, "cpu_baseline": cpu,
-        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": B * (3 * 16 + 100 * 100) * 4, "d2h_bytes_per_step": 4,
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": B * (3 * S * 16 + 100 * 100) * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clocks, "extra": extras,
     }
@@ -454,6 +459,8 @@ def main():
     # accumulation, bf16 gradients); "bf16" is ~5 % faster and 8x less accurate, "fp32" is the <= 1e-5 parity mode
     ap.add_argument("--precision", default=os.environ.get("TSR_BENCH_PRECISION", "fp16"), choices=["fp32", "bf16", "fp16"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("TSR_BENCH_BATCH", "1024")))
+    ap.add_argument("--seqs", type=int, default=int(os.environ.get("TSR_BENCH_SEQS", "1")), choices=[1, 7],
+                    help="frames per sample: 1 = headline workload, 7 = tactileSRSeqs model (BASELINE.json configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
