@@ -226,14 +226,15 @@ def test_standalone_blocks_match_torch_reference():
             assert rel_l2(p.grad, pr.grad) < 1e-3, n
 
 
-def test_conv_f32_wide_tile_bit_identical_to_narrow_tile():
+@pytest.mark.parametrize("Cout,B", [(128, 26), (256, 14)])
+def test_conv_f32_wide_tile_bit_identical_to_narrow_tile(Cout, B):
     """tsr_conv2d_f32 picks 128-cout tiles once the grid fills the machine and 64-cout tiles otherwise; every output is the
     same serial fmaf chain in both, so a large batch must equal its two halves (which take the narrow tiles) bit for bit --
     and an fp64 convolution to fp32 rounding."""
     import torch.nn.functional as F
     from tactilesr_b200 import _lib
     torch.manual_seed(9)
-    dev, B, H, W, Cin, Cout, KS = "cuda", 26, 40, 40, 64, 128, 3
+    dev, H, W, Cin, KS = "cuda", 40, 40, 64, 3
     st = torch.cuda.current_stream().cuda_stream
     x = torch.randn(B, H, W, Cin, device=dev)
     w = torch.randn(Cout, Cin, KS, KS, device=dev) * 0.05
@@ -247,8 +248,9 @@ def test_conv_f32_wide_tile_bit_identical_to_narrow_tile():
         _lib.call("tsr_conv2d_f32", xs.data_ptr(), Cin, wf.data_ptr(), bias.data_ptr(), rs.data_ptr(), Cout, o.data_ptr(), Cout,
                   xs.shape[0], H, W, Cin, Cout, KS, 1, st)
         return o
-    full = conv(x, res)                                        # 325 x 1 wide tiles
-    halves = torch.cat([conv(x[:13].contiguous(), res[:13].contiguous()), conv(x[13:].contiguous(), res[13:].contiguous())])
+    full = conv(x, res)                                        # 325 x 1 / 175 x 2 wide tiles
+    h = B // 2                                                 # halves: 163 / 176 tiles -> narrow path
+    halves = torch.cat([conv(x[:h].contiguous(), res[:h].contiguous()), conv(x[h:].contiguous(), res[h:].contiguous())])
     assert torch.equal(full, halves)
     ref = torch.relu(F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1) + res.double())
     assert rel_l2(full, ref) < 1e-6
