@@ -1,6 +1,7 @@
 """Drop-in tPSFNet: same class, constructor, attributes and ``state_dict`` (``MLP_layer.{1,3,5,7}``) as
 reference ``model/tPSFNet.py:13-141``; ``forward`` runs the MLP and the fused per-sample PSF kernels
-(csrc/mlp.cu, csrc/psf.cu) instead of the python ``for i in range(B)`` loop (:118-125).
+(csrc/mlp.cu, csrc/conv_f32.cu / conv_tc.cu for the wide layers, csrc/psf_tc.cu, csrc/psf.cu) instead of the python
+``for i in range(B)`` loop (:118-125).
 """
 from __future__ import annotations
 
@@ -9,6 +10,7 @@ import torch.nn as nn
 
 from .. import _lib
 from .. import ops  # noqa: F401  (registers torch.ops.tactilesr.*)
+from ..engine import get_precision
 
 _ACT = {"none": 0, "relu": 1, "softplus": 2}
 
@@ -240,7 +242,6 @@ class tPSFNet(nn.Module):
         assert x.shape[0] == depth.shape[0], "Batch size of LR tactile and depth should be the same!"
         L = self.MLP_layer
         B = x.shape[0]
-        from ..engine import get_precision
         mode = self.precision or get_precision()
         params = (L[1].weight, L[1].bias, L[3].weight, L[3].bias, L[5].weight, L[5].bias, L[7].weight, L[7].bias)
         if mode in ("fp16", "bf16") and B % 64 == 0 and B >= _TC_MIN_BATCH and x.is_cuda:
