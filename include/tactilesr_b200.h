@@ -89,9 +89,9 @@ int tsr_bn_train_stats(const void* y, int y_ld, int y_bf16, long long npix, int 
                        float momentum, float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
                        void* workspace, size_t ws_bytes, tsr_stream_t stream);
 /* eval mode: scale / shift from the running statistics. */
-int tsr_bn_finalize_partials(const float* partial, int nrows, long long npix, int C, const float* gamma, const float* beta,
-                             float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
-                             float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
+int tsr_bn_finalize_partials(const float* partial, int part_ld, int nrows, long long npix, int C, const float* gamma,
+                             const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
+                             float momentum, float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
                              tsr_stream_t stream);
 int tsr_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, float* scale, float* shift, float* save_mean,
@@ -183,7 +183,8 @@ typedef struct TsrPackDesc {
   void* wd;         /* data-gradient image or NULL */
   int Cout, Cin, KS;
   int dt_f, dt_d;   /* storage codes of wf / wd: 1 = bf16, 2 = fp16 */
-  int pad_;
+  int mode;         /* 0: wf = standard forward image; 1 / 2: wf = a dual-branch image (tsr_pack_conv_weight_dual) and this
+                       weight is its 3x3 / 5x5 branch */
 } TsrPackDesc;
 int tsr_pack_conv_weights_multi(const void* table_dev, int n, long long max_elems, tsr_stream_t stream);
 /* same packing with fp16 elements: forward weights of the "fp16" precision mode (fp16 activations, bf16 gradients) */
@@ -212,6 +213,69 @@ size_t tsr_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int
 int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
                         size_t ws_bytes, int B, int H, int W, int Cin, int Cout, int KS, int accumulate,
                         tsr_stream_t stream);
+
+/* ---- tensor-core convolution, generation 2 (csrc/conv_tc2.cu) -------------------------------------------------
+ * One launch = out = epilogue( sum over sources s, taps, channels of in_s[pix + shift] * w_s ), the sources accumulating
+ * into one accumulator:
+ *   nsrc = 1                the forward (or data gradient) of one nn.Conv2d, as tsr_conv2d_tc;
+ *   nsrc = 2                K-concatenation: the data gradient of the two convolutions that read the same tensor
+ *                           (MSRB conv_3_x / conv_5_x, model/tactileSR_model.py:198-199, 201-202) in one pass;
+ *   nsrc = 1, dual_fwd = 1  the 3x3 and the 5x5 convolution (64 output channels each) of one input from one halo tile:
+ *                           out channels [0, 64) = conv3, [64, 128) = conv5; src[0].KS = 5 and src[0].w_packed is the
+ *                           image of tsr_pack_conv_weight_dual.
+ * Epilogue, in this order: + bias, + residual, [mask], [ReLU], round to the output type (fp16 with TSR_TC2_F16, else
+ * bf16), store (+ bf16 copy out2), statistics.
+ *   TSR_TC2_MASK      aux = a saved activation (fp16 with TSR_TC2_AUX_F16, else bf16): the value is zeroed where
+ *                     aux <= 0 -- the ReLU backward of the layer that produced `aux` (replaces tsr_relu_backward);
+ *   TSR_TC2_BNB       aux = y, the input of a BatchNorm(+ReLU): with TSR_TC2_BNB_RELU the value is zeroed where
+ *                     aux_scale*y + aux_shift <= 0, and stat receives per-row partial sums of (g, g*y) over the stored g
+ *                     -- level 1 of the BatchNorm backward (finish with tsr_bn_bwd_finalize_partials, then
+ *                     tsr_bn_backward_apply with relu = 0);
+ *   otherwise         stat (may be NULL) receives partial sums of (o, o*o) over the stored output o -- the batch
+ *                     statistics of the BatchNorm that follows (finish with tsr_bn_finalize_partials).
+ * stat: [tsr_conv2d_tc2_stat_rows()][2][stat_ld] floats; cleared by the call unless TSR_TC2_STAT_PRECLEARED (required when
+ * `stat` points into a channel slice of a wider table).  Bit-deterministic. */
+#define TSR_TC2_RELU 1
+#define TSR_TC2_F16 2
+#define TSR_TC2_MASK 8
+#define TSR_TC2_BNB 16
+#define TSR_TC2_BNB_RELU 32
+#define TSR_TC2_AUX_F16 64
+#define TSR_TC2_STAT_PRECLEARED 128
+typedef struct TsrConvSrc {
+  const void* in;        /* NHWC, Cin channels from this pointer */
+  const void* w_packed;  /* tsr_pack_conv_weight_bf16 / _f16 image (forward or data-gradient), or the dual image */
+  int in_ld, Cin, KS, pad_;
+} TsrConvSrc;
+typedef struct TsrConvTc2 {
+  TsrConvSrc src[2];
+  const float* bias;       /* [Cout] or NULL */
+  const void* residual;    /* [pix][res_ld], output type, or NULL */
+  void* out;               /* [pix][out_ld] */
+  void* out2_bf16;         /* optional bf16 copy of an fp16 output */
+  float* stat;
+  const void* aux;
+  const float* aux_scale;
+  const float* aux_shift;
+  int nsrc, dual_fwd;
+  int res_ld, out_ld, out2_ld, stat_ld, aux_ld;
+  int B, H, W, Cout, flags;
+} TsrConvTc2;
+int tsr_conv2d_tc2(const void* args /* const TsrConvTc2*, host memory */, tsr_stream_t stream);
+int tsr_conv2d_tc2_stat_rows(void);
+/* w3 (64, Cin, 3, 3), w5 (64, Cin, 5, 5) fp32 OIHW -> dual-branch forward image (dtype 1 = bf16, 2 = fp16) of
+   tsr_pack_conv_weight_dual_elems(Cin) elements */
+size_t tsr_pack_conv_weight_dual_elems(int Cin);
+int tsr_pack_conv_weight_dual(const float* w3, const float* w5, void* out, int Cin, int dtype, tsr_stream_t stream);
+/* BatchNorm backward split for the fused data-gradient epilogue: level 2 from a (sum g, sum g*y) table, and level 3
+   (dy = scale * (g - c1 - xhat * c2)) on its own.  c1, c2: [C] floats.  nn.BatchNorm2d backward, cpu/trainer.py:353. */
+int tsr_bn_bwd_finalize_partials(const float* partial, int part_ld, int nrows, long long npix, int C, const float* save_mean,
+                                 const float* save_invstd, float* dgamma, float* dbeta, int accumulate, float* c1, float* c2,
+                                 int training, tsr_stream_t stream);
+int tsr_bn_backward_apply(const void* da, int da_ld, const void* y, int y_ld, void* dy, int dy_ld, int act_bf16,
+                          const float* scale, const float* shift, const float* save_mean, const float* save_invstd,
+                          const float* c1, const float* c2, long long npix, int C, int relu, tsr_stream_t stream);
+
 /* experiment switches of the tensor-core kernels (see csrc/conv_tc.cu); 0 = production configuration. */
 void tsr_set_tc_desc_mode(int mode);
 int tsr_get_tc_desc_mode(void);

@@ -40,7 +40,9 @@ SIGNATURES = {
     # elementwise / reductions
     "tsr_bn_workspace": (_Z, [_L, _I]),
     "tsr_bn_train_stats": (_I, [_P, _I, _I, _L, _I, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _Z, _P]),
-    "tsr_bn_finalize_partials": (_I, [_P, _I, _L, _I, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
+    "tsr_bn_finalize_partials": (_I, [_P, _I, _I, _L, _I, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
+    "tsr_bn_bwd_finalize_partials": (_I, [_P, _I, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _I, _P]),
+    "tsr_bn_backward_apply": (_I, [_P, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "tsr_bn_eval_coeffs": (_I, [_I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P]),
     "tsr_bn_apply": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _L, _I, _I, _P, _I, _P]),
     "tsr_bn_backward_workspace": (_Z, [_L, _I]),
@@ -77,9 +79,47 @@ SIGNATURES = {
     "tsr_conv2d_tc_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),
     "tsr_conv2d_wgrad_tc": (_I, [_P, _I, _P, _I, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tsr_conv2d_wgrad_tc_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),
+    "tsr_conv2d_tc2": (_I, [_P, _P]),
+    "tsr_conv2d_tc2_stat_rows": (_I, []),
+    "tsr_pack_conv_weight_dual_elems": (_Z, [_I]),
+    "tsr_pack_conv_weight_dual": (_I, [_P, _P, _P, _I, _I, _P]),
     "tsr_set_tc_desc_mode": (None, [_I]),
     "tsr_get_tc_desc_mode": (_I, []),
 }
+
+
+
+class ConvSrc(ctypes.Structure):
+    """TsrConvSrc of include/tactilesr_b200.h."""
+    _fields_ = [("inp", c_void_p), ("w_packed", c_void_p), ("in_ld", c_int), ("Cin", c_int), ("KS", c_int), ("pad_", c_int)]
+
+
+class ConvTc2(ctypes.Structure):
+    """TsrConvTc2 of include/tactilesr_b200.h (argument block of tsr_conv2d_tc2)."""
+    _fields_ = [("src", ConvSrc * 2), ("bias", c_void_p), ("residual", c_void_p), ("out", c_void_p), ("out2_bf16", c_void_p),
+                ("stat", c_void_p), ("aux", c_void_p), ("aux_scale", c_void_p), ("aux_shift", c_void_p),
+                ("nsrc", c_int), ("dual_fwd", c_int), ("res_ld", c_int), ("out_ld", c_int), ("out2_ld", c_int),
+                ("stat_ld", c_int), ("aux_ld", c_int), ("B", c_int), ("H", c_int), ("W", c_int), ("Cout", c_int),
+                ("flags", c_int)]
+
+
+TC2_RELU, TC2_F16, TC2_MASK, TC2_BNB, TC2_BNB_RELU, TC2_AUX_F16, TC2_STAT_PRECLEARED = 1, 2, 8, 16, 32, 64, 128
+
+
+def conv_tc2(srcs, out, out_ld, B, H, W, Cout, flags=0, bias=0, residual=0, res_ld=0, out2=0, out2_ld=0, stat=0, stat_ld=0,
+             aux=0, aux_ld=0, aux_scale=0, aux_shift=0, dual_fwd=0, stream=None):
+    """tsr_conv2d_tc2 with srcs = [(in_ptr, in_ld, Cin, KS, w_packed_ptr), ...] (one or two sources)."""
+    a = ConvTc2()
+    for i, (ip, ild, cin, ks, wp) in enumerate(srcs):
+        a.src[i].inp, a.src[i].in_ld, a.src[i].Cin, a.src[i].KS, a.src[i].w_packed = ip, ild, cin, ks, wp
+    a.nsrc, a.dual_fwd = len(srcs), dual_fwd
+    a.bias, a.residual, a.res_ld = bias or None, residual or None, res_ld
+    a.out, a.out_ld, a.out2_bf16, a.out2_ld = out, out_ld, out2 or None, out2_ld
+    a.stat, a.stat_ld = stat or None, stat_ld
+    a.aux, a.aux_ld, a.aux_scale, a.aux_shift = aux or None, aux_ld, aux_scale or None, aux_shift or None
+    a.B, a.H, a.W, a.Cout, a.flags = B, H, W, Cout, flags
+    call("tsr_conv2d_tc2", ctypes.addressof(a), stream_ptr() if stream is None else stream)
+
 
 _lib = None
 

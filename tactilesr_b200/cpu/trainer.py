@@ -165,36 +165,157 @@ class _LRUpdateHook(HookBase):
         self.trainer.lr_scheduler.iter_update()
 
 
-class MetricStorage(dict):
-    """name -> (window of recent values, running average, latest, iteration), reference :501-567."""
+class HistoryBuffer:
+    """Window + global statistics of one metric, same surface as reference cpu/history_buffer.py (``update``, ``latest``,
+    ``avg``, ``global_avg``, ``global_sum``), so the reference's own LoggerHook / EvalHook read our storage unchanged."""
 
-    def __init__(self, window_size: int = 20):
+    def __init__(self, window_size: int = 20) -> None:
+        self._history = deque(maxlen=window_size)
+        self._count = 0
+        self._sum = 0.0
+
+    def update(self, value: float) -> None:
+        self._history.append(value)
+        self._count += 1
+        self._sum += value
+
+    @property
+    def latest(self) -> float:
+        return self._history[-1]
+
+    @property
+    def avg(self) -> float:
+        return float(np.mean(self._history))
+
+    @property
+    def global_avg(self) -> float:
+        return self._sum / self._count
+
+    @property
+    def global_sum(self) -> float:
+        return self._sum
+
+
+class MetricStorage(dict):
+    """name -> HistoryBuffer, reference cpu/trainer.py:501-567: ``update(iter, smooth, **values)`` and
+    ``values_maybe_smooth`` = {name: (latest iteration, window average | latest value)}."""
+
+    def __init__(self, window_size: int = 20) -> None:
         super().__init__()
-        self._window = window_size
+        self._window_size = window_size
+        self._history = self
         self._smooth: Dict[str, bool] = {}
         self._latest_iter: Dict[str, int] = {}
 
     def update(self, iter: Optional[int] = None, smooth: bool = True, **kwargs) -> None:
-        for k, v in kwargs.items():
-            if k not in self:
-                dict.__setitem__(self, k, {"win": deque(maxlen=self._window), "sum": 0.0, "count": 0})
-                self._smooth[k] = smooth
-            rec = self[k]
-            rec["win"].append(float(v))
-            rec["sum"] += float(v)
-            rec["count"] += 1
-            self._latest_iter[k] = -1 if iter is None else iter
+        for key, value in kwargs.items():
+            if key in self._smooth:
+                assert self._smooth[key] == smooth, f"metric {key!r} changed its smoothing"
+            else:
+                self._smooth[key] = smooth
+                self[key] = HistoryBuffer(window_size=self._window_size)
+                self._latest_iter[key] = -1
+            if iter is not None:
+                assert iter > self._latest_iter[key], f"metric {key!r}: iteration {iter} not after {self._latest_iter[key]}"
+                self._latest_iter[key] = iter
+            else:
+                self._latest_iter[key] += 1
+            self[key].update(value)
 
     @property
-    def values_maybe_smooth(self) -> Dict[str, Tuple[float, int]]:
-        return {k: (float(np.mean(r["win"])) if self._smooth[k] else r["win"][-1], self._latest_iter[k])
-                for k, r in self.items()}
+    def values_maybe_smooth(self) -> Dict[str, Tuple[int, float]]:
+        return {k: (self._latest_iter[k], b.avg if self._smooth[k] else b.latest) for k, b in self.items()}
 
-    def latest(self, k: str) -> float:
-        return self[k]["win"][-1]
 
-    def global_avg(self, k: str) -> float:
-        return self[k]["sum"] / max(self[k]["count"], 1)
+class CheckpointHook(HookBase):
+    """Periodic checkpoints with pruning (reference cpu/hooks/checkpoint_hook.py): every ``period`` epochs / iterations and
+    at the end, keeping the ``max_to_keep`` most recent files."""
+
+    def __init__(self, period: int, max_to_keep: Optional[int] = None) -> None:
+        assert max_to_keep is None or max_to_keep > 0
+        self._period, self._max_to_keep = period, max_to_keep
+        self._recent_checkpoints: List[str] = []
+
+    def _save(self, name: str) -> None:
+        self.trainer.save_checkpoint(name)
+        if self._max_to_keep is not None:
+            self._recent_checkpoints.append(name)
+            while len(self._recent_checkpoints) > self._max_to_keep:
+                old = os.path.join(self.trainer.ckpt_dir, self._recent_checkpoints.pop(0))
+                if os.path.exists(old):
+                    os.remove(old)
+
+    def after_iter(self) -> None:
+        if not self.trainer.train_by_epoch and (self.every_n_iters(self._period) or self.is_last_iter()):
+            self._save(f"iter_{self.trainer.cur_iter}.pth")
+
+    def after_epoch(self) -> None:
+        if self.trainer.train_by_epoch and (self.every_n_epochs(self._period) or self.is_last_epoch()):
+            self._save(f"epoch_{self.trainer.cur_epoch}.pth")
+
+    def state_dict(self):
+        return {k: v for k, v in self.__dict__.items() if k != "trainer"}
+
+    def load_state_dict(self, state) -> None:
+        self.__dict__.update(state)
+
+
+class DistributedHook(HookBase):
+    """``DistributedSampler.set_epoch`` before every epoch (reference cpu/hooks/distributed_hook.py:7-13)."""
+
+    def before_epoch(self) -> None:
+        dl = self.trainer.data_loader
+        for owner in (getattr(dl, "sampler", None), getattr(getattr(dl, "batch_sampler", None), "sampler", None)):
+            if hasattr(owner, "set_epoch"):
+                owner.set_epoch(self.trainer.cur_epoch)
+                return
+
+
+class LoggerHook(HookBase):
+    """Console (and, when tensorboard is importable and ``tb_log_dir`` is given, TensorBoard) logging of the metric storage
+    every ``period`` iterations (reference cpu/hooks/logger_hook.py); lowest priority so it sees what other hooks logged."""
+    priority = 10
+
+    def __init__(self, period: int = 50, tb_log_dir: Optional[str] = None) -> None:
+        self._period = period
+        self._tb = None
+        self._last_write: Dict[str, int] = {}
+        if tb_log_dir is not None:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+                self._tb = SummaryWriter(tb_log_dir)
+            except Exception:      # tensorboard absent: console only
+                self._tb = None
+
+    def before_train(self) -> None:
+        self._t0 = time.perf_counter()
+
+    def _write(self) -> None:
+        ms = self.trainer.metric_storage
+        tr = self.trainer
+        where = (f"Epoch: [{tr.cur_epoch}][{tr.inner_iter}/{tr.epoch_len - 1}]" if tr.train_by_epoch
+                 else f"Iter: [{tr.cur_iter}/{tr.max_iters - 1}]")
+        parts = [where]
+        if "lr" in ms:
+            parts.append(f"lr: {ms['lr'].latest:.4g}")
+        parts += [f"{k}: {b.avg:.4g}" for k, b in ms.items() if "loss" in k]
+        if "iter_time" in ms:
+            parts.append(f"iter_time: {ms['iter_time'].avg:.4f}")
+        logger.info("  ".join(parts))
+        if self._tb is not None:
+            for k, (it, v) in ms.values_maybe_smooth.items():
+                if it > self._last_write.get(k, -1):
+                    self._tb.add_scalar(k, v, it)
+                    self._last_write[k] = it
+
+    def after_iter(self) -> None:
+        if self.every_n_iters(self._period) or self.is_last_iter():
+            self._write()
+
+    def after_train(self) -> None:
+        if self._tb is not None:
+            self._tb.close()
+        logger.info("Total training time: %.1f s", time.perf_counter() - self._t0)
 
 
 class Trainer:
@@ -236,7 +357,12 @@ class Trainer:
         self._use_graph = cuda_graph
         self._graphs: Dict[tuple, tuple] = {}
         self._eager_iters = 0
-        self.register_hooks([_LRUpdateHook()])
+        # default hooks as the reference registers them (cpu/trainer.py:194-200): LR update and sampler epoch on every rank,
+        # checkpoints and logging on the main process
+        hooks: List[HookBase] = [_LRUpdateHook(), DistributedHook()]
+        if D.is_main_process():
+            hooks += [CheckpointHook(checkpoint_period, max_num_checkpoints), LoggerHook(log_period)]
+        self.register_hooks(hooks)
 
     # -- bookkeeping identical in meaning to the reference ------------------------------------------
     @property
@@ -260,7 +386,7 @@ class Trainer:
 
     @property
     def hook_info(self) -> List[str]:
-        return [f"{h.class_name} (priority {h.priority})" for h in self._hooks]
+        return [f"{type(h).__name__} (priority {getattr(h, 'priority', 5)})" for h in self._hooks]
 
     def log(self, *args, **kwargs) -> None:
         self.metric_storage.update(*args, **kwargs)
@@ -269,10 +395,14 @@ class Trainer:
         for h in hooks:
             if h is None:
                 continue
-            assert isinstance(h, HookBase) and 1 <= h.priority <= 10
+            # duck-typed: the reference's own hooks (cpu/hooks/*.py, e.g. EvalHook at train/tactileSR_train.py:230) derive
+            # from ITS HookBase, not ours
+            assert all(callable(getattr(h, st, None)) for st in ("before_train", "after_train", "before_epoch", "after_epoch",
+                                                                 "before_iter", "after_iter")), f"{h!r} is not a hook"
+            assert 1 <= getattr(h, "priority", 5) <= 10
             h.trainer = self
             pos = len(self._hooks)
-            while pos > 0 and self._hooks[pos - 1].priority > h.priority:
+            while pos > 0 and getattr(self._hooks[pos - 1], "priority", 5) > getattr(h, "priority", 5):
                 pos -= 1
             self._hooks.insert(pos, h)
 
@@ -423,9 +553,9 @@ class Trainer:
             return
         data = {"num_gpus": D.get_world_size(), "model": self.model_or_module.state_dict(),
                 "optimizer": self.optimizer.state_dict(), "lr_scheduler": self.lr_scheduler.state_dict(),
-                "metric_storage": dict(self.metric_storage)}
+                "metric_storage": self.metric_storage}
         data["epoch" if self.train_by_epoch else "iter"] = self.cur_epoch if self.train_by_epoch else self.cur_iter
-        hook_states = {h.class_name: h.state_dict() for h in self._hooks if h.checkpointable}
+        hook_states = {type(h).__name__: h.state_dict() for h in self._hooks if callable(getattr(h, "state_dict", None))}
         if hook_states:
             data["hooks"] = hook_states
         os.makedirs(self.ckpt_dir, exist_ok=True)
@@ -451,6 +581,13 @@ class Trainer:
         self.optimizer.load_state_dict(ck["optimizer"])
         self.lr_scheduler.load_state_dict(ck["lr_scheduler"])
         self.model_or_module.load_state_dict(ck["model"], strict=False)
+        ms = ck.get("metric_storage")
+        if isinstance(ms, MetricStorage):
+            self.metric_storage = ms
+        elif ms is not None and all(hasattr(v, "avg") for v in getattr(ms, "values", lambda: [None])()):
+            # a checkpoint written by the reference trainer: its MetricStorage / HistoryBuffer objects have the same surface
+            self.metric_storage = ms
         for h in self._hooks:
-            if h.checkpointable and h.class_name in ck.get("hooks", {}):
-                h.load_state_dict(ck["hooks"][h.class_name])
+            name = type(h).__name__
+            if callable(getattr(h, "load_state_dict", None)) and name in ck.get("hooks", {}):
+                h.load_state_dict(ck["hooks"][name])

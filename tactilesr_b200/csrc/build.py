@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libtactilesr_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["core.cu", "conv_f32.cu", "elementwise.cu", "mlp.cu", "psf.cu", "psf_tc.cu", "conv_tc.cu"]
+SOURCES = ["core.cu", "conv_f32.cu", "elementwise.cu", "mlp.cu", "psf.cu", "psf_tc.cu", "conv_tc.cu", "conv_tc2.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

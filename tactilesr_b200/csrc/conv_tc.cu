@@ -370,47 +370,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
 // arrives remotely without tx); tcgen05.commit multicasts "empty"/"accumulator ready" to both CTAs; both epilogues
 // arrive (remotely for the peer) on the leader's "accumulator drained" barrier.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
-                                                uint32_t bar_leader) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_leader) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                              uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"((uint16_t)3)
-               : "memory");
-}
-
 template <int N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap wmap,
@@ -633,8 +592,8 @@ struct PackDesc {          // mirrors TsrPackDesc of include/tactilesr_b200.h
   void* wd;                // data-gradient image or null
   int Cout, Cin, KS;
   int dt_f, dt_d;          // storage codes of wf / wd: 1 = bf16, 2 = fp16
-  int pad_;
-};
+  int mode;                // 0: wf = standard forward image; 1 / 2: wf = dual-branch image (tc_ptx.cuh), this weight is its
+};                         // 3x3 / 5x5 branch (Cout = 64)
 static_assert(sizeof(PackDesc) == 48, "TsrPackDesc layout");
 
 __device__ __forceinline__ void store16(void* base, long long idx, float v, int dt) {
@@ -652,7 +611,11 @@ __global__ void pack_weights_multi_kernel(const PackDesc* __restrict__ table) {
     const int ci = (int)(r % e.Cin);
     const int co = (int)(r / e.Cin);
     const float v = e.w[i];
-    if (e.wf) {
+    if (e.wf && e.mode) {
+      const int c = ci >> 6, k = ci & 63;
+      const int row = c * DUAL_CHUNK_ROWS + dual_image_row(e.mode == 2, t / e.KS, t % e.KS, co);
+      store16(e.wf, (long long)row * 64 + (((k >> 3) ^ (row & 7)) << 3) + (k & 7), v, e.dt_f);
+    } else if (e.wf) {
       const int c = ci >> 6, k = ci & 63;
       const long long tile = ((long long)c * taps + t) * e.Cout * 64;
       store16(e.wf, tile + (long long)co * 64 + (((k >> 3) ^ (co & 7)) << 3) + (k & 7), v, e.dt_f);
@@ -872,34 +835,6 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float*
   long long o = (((long long)g * Cout + co) * Cin + ci) * taps + tap;
   dw[o] = accumulate ? dw[o] + s : s;
 }
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
-
-constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 // shared-memory plan of the forward kernel: A slots fixed by the geometry, the weight ring takes what is left
 void conv_smem_plan(int N, int rows, int P, int na, size_t* smem, int* nb) {

@@ -1,0 +1,673 @@
+// Tensor-core convolution, second generation (sm_100a): ONE persistent CTA-pair kernel (tcgen05.mma.cta_group::2, M = 256)
+// for every implicit-GEMM shape of the SR path, generalised over
+//
+//   * several A-operand SOURCES whose products accumulate into the same TMEM accumulator ("K concatenation"): the data
+//     gradient of two convolutions that read the same tensor -- MSRB conv_3_x / conv_5_x, reference
+//     model/tactileSR_model.py:198-199, 201-202 -- is one launch over both branches' dy instead of a second launch that
+//     re-reads and accumulates into the gradient tensor;
+//   * a per-tap N: the DUAL-BRANCH forward runs the 3x3 and the 5x5 convolution of one input from one halo tile -- the 9
+//     central taps issue N = 128 MMAs ([conv3 | conv5] output columns), the 16 outer taps N = 64 into the conv5 columns.
+//     An A tile read from shared memory costs the same for N = 64 and N = 128 (measured: 64-column MMAs run at the
+//     128-column rate), so the shared taps are free;
+//   * a wider epilogue: 8 epilogue warps (two per TMEM lane quarter, each owning half of the accumulator columns), loads
+//     of the residual / auxiliary tensor prefetched one step ahead, and three fused post-ops:
+//       - BatchNorm batch statistics of the stored output (forward; as in generation 1),
+//       - ReLU backward: zero the data gradient where the saved activation is <= 0 (replaces tsr_relu_backward),
+//       - BatchNorm backward, level 1: g = dgrad * [scale*y + shift > 0] is stored and sum g, sum g*y are reduced per
+//         (CTA, lane quarter) for tsr_bn_bwd_finalize_partials (replaces the bn_bwd_partial pass over da and y).
+//
+// Work decomposition, halo tiles, descriptors and the pair protocol are those of conv_tc.cu (generation 1; its forward
+// kernels are kept behind TSR_TC_MODE bit 6 for A/B runs): samples stacked vertically with `maxpad` virtual zero rows
+// between them, a CTA block = 32 virtual rows x 8 columns = 2 M-tiles, every tap a shifted window of the one halo tile.
+//
+// Warp roles (11 warps): 0 = A producer (TMA row boxes), 1 = MMA issuer + TMEM owner, 2 = B producer (weight tiles),
+// 3..10 = epilogue.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <stdlib.h>
+
+namespace {
+
+constexpr int T2_TILES = 2;
+constexpr int T2_THREADS = 352;
+constexpr int T2_MAX_NA = 8, T2_MAX_NB = 8;
+constexpr int T2_STAT_ROWS = 148 * 4;       // (CTA, TMEM lane quarter)
+constexpr int T2_MAX_TAPS = 25;
+
+// flags (public: TSR_TC2_* in include/tactilesr_b200.h)
+constexpr int F_RELU = 1, F_F16 = 2, F_MASK = 8, F_BNB = 16, F_BNB_RELU = 32, F_AUX_F16 = 64, F_STAT_PRECLEARED = 128;
+
+struct Seg {
+  int nchunks, ntaps, pad, P, rows, chunk_wrows, amap;
+  uint32_t row_bytes, mt_units, a_hi;
+};
+
+struct P2 {
+  Seg seg[2];
+  int nseg;
+  uint32_t tap[2][T2_MAX_TAPS];      // window offset in 16-byte units | weight map << 12 | half-N << 13
+  int wrow[2][T2_MAX_TAPS];          // first row of the tap's tile inside a chunk of the weight image
+  const float* bias;
+  const void* residual;
+  void* out;
+  __nv_bfloat16* out2;
+  float* stat;
+  const void* aux;
+  const float* aux_sc;
+  const float* aux_sh;
+  int res_ld, out_ld, out2_ld, stat_ld, aux_ld, flags;
+  int H, W, Hp, Vtotal, nxg, nblocks, ngroups;
+  int na_slots, nb_stages;
+  uint32_t a_slot_bytes;
+};
+
+__device__ __forceinline__ float transpose_reduce16_2(float (&p)[16], int lane) {
+#pragma unroll
+  for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int k = 0; k < w; ++k) {
+      const float keep = up ? p[k + w] : p[k], send = up ? p[k] : p[k + w];
+      p[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  return p[0] + __shfl_xor_sync(0xffffffffu, p[0], 1);
+}
+
+__device__ __forceinline__ void unpack16(const uint4 (&u)[2], bool f16, float (&f)[16]) {
+  const uint32_t w[8] = {u[0].x, u[0].y, u[0].z, u[0].w, u[1].x, u[1].y, u[1].z, u[1].w};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float2 t;
+    if (f16) t = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+    else t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+    f[2 * k] = t.x; f[2 * k + 1] = t.y;
+  }
+}
+
+// Epilogue of one block for the warp that owns TMEM lanes (acc >> 16)..+31 and accumulator columns col0..col0 + NACC/2:
+// both M-tiles, 16 columns at a time.  The residual / aux vectors of step i + 1 are requested before step i is processed
+// (and those of step 0 before the accumulator is awaited), so their latency overlaps the TMEM loads and the arithmetic.
+template <int NACC>
+__device__ __forceinline__ void epilogue2(const P2& p, uint32_t acc, int col0, const bool (&valid)[T2_TILES],
+                                          const long long (&pix)[T2_TILES], int stat_row, int lane, int nofs,
+                                          uint32_t bar, uint32_t parity) {
+  constexpr int NI = (NACC / 32) * T2_TILES;
+  const int flags = p.flags;
+  const bool f16 = (flags & F_F16) != 0, auxf16 = (flags & F_AUX_F16) != 0;
+  const bool has_res = p.residual != nullptr, has_aux = p.aux != nullptr;
+  const bool bnb = (flags & F_BNB) != 0;
+  uint4 rn[2], an[2];
+  rn[0] = rn[1] = an[0] = an[1] = make_uint4(0u, 0u, 0u, 0u);
+  // (selects, not indexed loads: a dynamically indexed valid[] / pix[] lives in local memory and every use then waits on
+  // an LDL behind the store traffic -- measured 2x on the epilogue-bound 1x1 data gradient)
+  const bool v0 = valid[0], v1 = valid[1];
+  const long long p0 = pix[0], p1 = pix[1];
+  auto prefetch = [&](int i) {
+    const int ch = nofs + col0 + (i >> 1) * 16;
+    const bool vm = (i & 1) ? v1 : v0;
+    const long long pm = (i & 1) ? p1 : p0;
+    if (vm) {
+      if (has_res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + pm * p.res_ld + ch);
+        rn[0] = rp[0]; rn[1] = rp[1];
+      }
+      if (has_aux) {
+        const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.aux) + pm * p.aux_ld + ch);
+        an[0] = ap[0]; an[1] = ap[1];
+      }
+    }
+  };
+  prefetch(0);
+  mbar_wait(bar, parity);
+  tc_fence_after();
+  float sv[16], sq[16];
+#pragma unroll 1
+  for (int i = 0; i < NI; ++i) {
+    const int mt = i & 1, j = i >> 1;
+    const int ch = nofs + col0 + j * 16;
+    const bool vm = mt ? v1 : v0;
+    const long long pm = mt ? p1 : p0;
+    const uint4 rc[2] = {rn[0], rn[1]}, ac[2] = {an[0], an[1]};
+    if (i + 1 < NI) prefetch(i + 1);
+    if (mt == 0) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { sv[k] = 0.f; sq[k] = 0.f; }
+    }
+    uint32_t v[16];
+    tmem_ld16(acc + mt * NACC + col0 + j * 16, v);
+    tmem_ld_wait();
+    if (vm) {
+      float f[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
+      if (p.bias) {
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(p.bias + ch + k);
+          f[k] += bv.x; f[k + 1] += bv.y; f[k + 2] += bv.z; f[k + 3] += bv.w;
+        }
+      }
+      if (has_res) {
+        float r[16];
+        unpack16(rc, f16, r);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f[k] += r[k];
+      }
+      float y[16];
+      if (has_aux) {
+        unpack16(ac, auxf16, y);
+        if (flags & F_MASK) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) f[k] = y[k] > 0.f ? f[k] : 0.f;
+        } else if (flags & F_BNB_RELU) {
+#pragma unroll
+          for (int k = 0; k < 16; k += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(p.aux_sc + ch + k);
+            const float4 sh = *reinterpret_cast<const float4*>(p.aux_sh + ch + k);
+            f[k] = fmaf(y[k], sc.x, sh.x) > 0.f ? f[k] : 0.f;
+            f[k + 1] = fmaf(y[k + 1], sc.y, sh.y) > 0.f ? f[k + 1] : 0.f;
+            f[k + 2] = fmaf(y[k + 2], sc.z, sh.z) > 0.f ? f[k + 2] : 0.f;
+            f[k + 3] = fmaf(y[k + 3], sc.w, sh.w) > 0.f ? f[k + 3] : 0.f;
+          }
+        }
+      }
+      if (flags & F_RELU) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
+      }
+      uint32_t o[8];
+      float fr[16];                       // the stored (rounded) values: what every later pass over the tensor reads
+      if (f16) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+          o[k] = *reinterpret_cast<const uint32_t*>(&h);
+          const float2 t = __half22float2(h);
+          fr[2 * k] = t.x; fr[2 * k + 1] = t.y;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+          o[k] = *reinterpret_cast<const uint32_t*>(&h);
+          const float2 t = __bfloat1622float2(h);
+          fr[2 * k] = t.x; fr[2 * k + 1] = t.y;
+        }
+      }
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + pm * p.out_ld + ch);
+      op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      if (p.out2) {
+        uint32_t o2[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+          o2[k] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        uint4* op2 = reinterpret_cast<uint4*>(p.out2 + pm * p.out2_ld + ch);
+        op2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+        op2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
+      }
+      if (p.stat) {
+        if (bnb) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) { sv[k] += fr[k]; sq[k] = fmaf(fr[k], y[k], sq[k]); }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) { sv[k] += fr[k]; sq[k] = fmaf(fr[k], fr[k], sq[k]); }
+        }
+      }
+    }
+    if (mt == T2_TILES - 1 && p.stat) {      // warp-uniform: all 32 lanes take part in the shuffles
+      const float s = transpose_reduce16_2(sv, lane), ss = transpose_reduce16_2(sq, lane);
+      if ((lane & 1) == 0) {
+        // every (row, channel) address has exactly one writer lane of one warp, in program order => deterministic
+        const int c = ch + (lane >> 1);
+        atomicAdd(p.stat + ((size_t)stat_row * 2 + 0) * p.stat_ld + c, s);
+        atomicAdd(p.stat + ((size_t)stat_row * 2 + 1) * p.stat_ld + c, ss);
+      }
+    }
+  }
+}
+
+template <int NACC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUtensorMap amap1,
+                const __grid_constant__ CUtensorMap wmap0, const __grid_constant__ CUtensorMap wmap1, const P2 p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_slot_bytes = p.a_slot_bytes;
+  const int NA = p.na_slots, NB = p.nb_stages;
+  const uint32_t a_base = base;
+  const uint32_t b_base = a_base + NA * a_slot_bytes;
+  constexpr uint32_t B_HALF = (NACC / 2) * 128u;     // this CTA's share of the widest weight tile
+  const uint32_t bar_base = b_base + NB * B_HALF;
+  auto a_full = [&](int i) { return bar_base + 8u * i; };
+  auto a_empty = [&](int i) { return bar_base + 8u * (T2_MAX_NA + i); };
+  auto b_full = [&](int i) { return bar_base + 8u * (2 * T2_MAX_NA + i); };
+  auto b_empty = [&](int i) { return bar_base + 8u * (2 * T2_MAX_NA + T2_MAX_NB + i); };
+  auto t_full = [&](int i) { return bar_base + 8u * (2 * T2_MAX_NA + 2 * T2_MAX_NB + i); };
+  auto t_empty = [&](int i) { return bar_base + 8u * (2 * T2_MAX_NA + 2 * T2_MAX_NB + 2 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * T2_MAX_NA + 2 * T2_MAX_NB + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  constexpr uint32_t ACC_COLS = T2_TILES * NACC;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;    // 512 or 256
+  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const int npb_pix = (p.nblocks + 1) >> 1;
+  const int npb = npb_pix * p.ngroups;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NA; ++i) { mbar_init(a_full(i), 2); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(b_full(i), 2); mbar_init(b_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 16); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== A producer (both CTAs): the halo rows of the CTA's own block, completing on the leader's a_full =====
+    int ac = 0;
+    for (int pb = pair; pb < npb; pb += npairs) {
+      const int blk = 2 * (pb % npb_pix) + (int)rank;   // may be == nblocks for the last odd block: all rows out of range
+      const int xg = blk % p.nxg, vb = blk / p.nxg;
+      const int x0 = xg * 8, v0 = vb * (16 * T2_TILES);
+      for (int s = 0; s < p.nseg; ++s) {
+        const Seg& sg = p.seg[s];
+        const CUtensorMap* am = sg.amap ? &amap1 : &amap0;
+        for (int c = 0; c < sg.nchunks; ++c, ++ac) {
+          const int slot = ac % NA;
+          const uint32_t dst0 = a_base + slot * a_slot_bytes;
+          const uint32_t full_leader = a_full(slot) & PEER_MASK;
+          if (lane == 0) mbar_wait(a_empty(slot), ((ac / NA) & 1) ^ 1);
+          __syncwarp();
+          if (sg.pad == 0) {
+            if (lane == 0) tma_load_4d_2sm(dst0, am, c * 64, x0, v0, 0, full_leader);
+          } else {
+            for (int r = lane; r < sg.rows; r += 32) {
+              const int vr = v0 - sg.pad + r;
+              int n = 0, y = p.H;   // out-of-bounds row => TMA zero fill
+              if (vr >= 0 && vr < p.Vtotal) { n = vr / p.Hp; y = vr - n * p.Hp; }
+              tma_load_4d_2sm(dst0 + (uint32_t)r * sg.P * 128u, am, c * 64, x0 - sg.pad, y, n, full_leader);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_expect_tx(a_full(slot), 2u * sg.row_bytes * sg.rows);
+            else mbar_arrive_cluster(full_leader);
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== B producer (both CTAs): this CTA's half of the rows of each weight tile =====
+    if (lane == 0) {
+      int it = 0;
+      for (int pb = pair; pb < npb; pb += npairs) {
+        const int g = pb / npb_pix;
+        for (int s = 0; s < p.nseg; ++s) {
+          const Seg& sg = p.seg[s];
+          for (int c = 0; c < sg.nchunks; ++c) {
+            for (int t = 0; t < sg.ntaps; ++t, ++it) {
+              const uint32_t e = p.tap[s][t];
+              const int rows_half = (e >> 13) & 1 ? NACC / 4 : NACC / 2;
+              const int row = c * sg.chunk_wrows + p.wrow[s][t] + g * NACC + (int)rank * rows_half;
+              const int st = it % NB;
+              const uint32_t full_leader = b_full(st) & PEER_MASK;
+              mbar_wait(b_empty(st), ((it / NB) & 1) ^ 1);
+              tma_load_2d_2sm(b_base + st * B_HALF, (e >> 12) & 1 ? &wmap1 : &wmap0, 0, row, full_leader);
+              if (leader) mbar_expect_tx(b_full(st), 2u * rows_half * 128u);
+              else mbar_arrive_cluster(full_leader);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: leader CTA only; the warp runs the loop converged, one elected lane issues =====
+    if (leader) {
+      const int bf = (p.flags & F_F16) ? 0 : 1;
+      const uint32_t idesc_full = make_idesc(256, NACC, 0, 0, bf, bf);
+      const uint32_t idesc_half = make_idesc(256, NACC / 2, 0, 0, bf, bf);
+      const uint32_t b_hi = desc_hi(1024u);
+      int it = 0, ac = 0, lb = 0;
+      for (int pb = pair; pb < npb; pb += npairs, ++lb) {
+        const int buf = lb & 1;
+        mbar_wait(t_empty(buf), ((lb >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + buf * ACC_COLS;
+        uint32_t first = 0u;
+        for (int s = 0; s < p.nseg; ++s) {
+          const Seg& sg = p.seg[s];
+          const uint32_t a_hi = sg.a_hi, mt_units = sg.mt_units;
+          for (int c = 0; c < sg.nchunks; ++c, ++ac) {
+            const int slot = ac % NA;
+            mbar_wait(a_full(slot), (ac / NA) & 1);
+            tc_fence_after();
+            const uint32_t a_lo0 = desc_lo(a_base + slot * a_slot_bytes, 16u);
+            for (int t = 0; t < sg.ntaps; ++t, ++it) {
+              const int st = it % NB;
+              const uint32_t e = p.tap[s][t];
+              mbar_wait(b_full(st), (it / NB) & 1);
+              tc_fence_after();
+              const uint32_t b_lo = desc_lo(b_base + st * B_HALF, 16u);
+              const uint32_t a_lo = a_lo0 + (e & 0xFFFu);
+              const bool half = (e >> 13) & 1;
+              const uint32_t idesc = half ? idesc_half : idesc_full;
+              const uint32_t acc = acc0 + (half ? NACC / 2 : 0);
+              if (elect_one()) {
+#pragma unroll
+                for (int mt = 0; mt < T2_TILES; ++mt) {
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) {
+                    umma_bf16_2sm(acc + mt * NACC, desc_join(a_lo + mt * mt_units + kk * 2u, a_hi),
+                                  desc_join(b_lo + kk * 2u, b_hi), idesc, (first | (uint32_t)kk) ? 1u : 0u);
+                  }
+                }
+                umma_commit_2sm(b_empty(st));
+              }
+              __syncwarp();
+              first = 1u;
+            }
+            if (elect_one()) umma_commit_2sm(a_empty(slot));
+            __syncwarp();
+          }
+        }
+        if (elect_one()) umma_commit_2sm(t_full(buf));
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): warps 3..10; lane quarter = warp % 4, column half = (warp - 3) / 4 =====
+    const int q = warp & 3, h = (warp - 3) >> 2;
+    const int r = q * 32 + lane;
+    const int wx = r & 7, vrow = r >> 3;
+    int lb = 0;
+    for (int pb = pair; pb < npb; pb += npairs, ++lb) {
+      const int buf = lb & 1;
+      const int blk = 2 * (pb % npb_pix) + (int)rank;
+      const int xg = blk % p.nxg, vb = blk / p.nxg;
+      const int x0 = xg * 8, v0 = vb * (16 * T2_TILES);
+      const uint32_t acc0 = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
+      bool valid[T2_TILES];
+      long long pix[T2_TILES];
+#pragma unroll
+      for (int mt = 0; mt < T2_TILES; ++mt) {
+        const int vr = v0 + mt * 16 + vrow;
+        const int n = vr / p.Hp, y = vr - n * p.Hp;
+        valid[mt] = blk < p.nblocks && vr < p.Vtotal && y < p.H;
+        pix[mt] = ((long long)n * p.H + y) * p.W + x0 + wx;
+      }
+      epilogue2<NACC>(p, acc0, h * (NACC / 2), valid, pix, (int)blockIdx.x * 4 + q, lane, (pb / npb_pix) * NACC,
+                      t_full(buf), (lb >> 1) & 1);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(t_empty(buf) & PEER_MASK);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dual-branch weight image: per 64-channel input chunk, 9 central taps x 128 rows ([conv3 co | conv5 co]) followed by the
+// 16 outer taps x 64 rows (conv5 co), rows of 64 K-elements in the SWIZZLE_128B shared-memory image
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_dual_kernel(const float* __restrict__ w3, const float* __restrict__ w5, T* __restrict__ out, int Cin) {
+  const long long n3 = 64ll * Cin * 9, n5 = 64ll * Cin * 25;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n3 + n5; i += (long long)gridDim.x * blockDim.x) {
+    const bool five = i >= n3;
+    const long long e = five ? i - n3 : i;
+    const int taps = five ? 25 : 9, KS = five ? 5 : 3;
+    const int t = (int)(e % taps);
+    const long long r = e / taps;
+    const int ci = (int)(r % Cin), co = (int)(r / Cin);
+    const int ky = t / KS, kx = t % KS;
+    const int c = ci >> 6, k = ci & 63;
+    const int row = c * DUAL_CHUNK_ROWS + dual_image_row(five, ky, kx, co);
+    T v;
+    stf(&v, five ? w5[e] : w3[e]);
+    out[(long long)row * 64 + (((k >> 3) ^ (row & 7)) << 3) + (k & 7)] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor-map cache (encoding a CUtensorMap costs ~1-2 us; the same (pointer, geometry) recurs every step
+// because PyTorch's caching allocator hands the same blocks to the same layers)
+// ------------------------------------------------------------------------------------------------
+struct MapKey {
+  const void* ptr;
+  unsigned long long d[4], s[3];
+  unsigned box[4];
+  int rank, swizzle;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapEntry { MapKey key; CUtensorMap map; bool used; };
+constexpr int MAP_CACHE = 512;
+MapEntry g_maps[MAP_CACHE];
+std::mutex g_map_mutex;
+
+int get_map(CUtensorMap* out, const void* ptr, int rank, const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* box,
+            CUtensorMapSwizzle swz) {
+  MapKey k;
+  memset(&k, 0, sizeof(k));
+  k.ptr = ptr; k.rank = rank; k.swizzle = (int)swz;
+  for (int i = 0; i < rank; ++i) { k.d[i] = gdim[i]; k.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) k.s[i] = gstr[i];
+  unsigned long long hsh = 1469598103934665603ull;
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(&k);
+  for (size_t i = 0; i < sizeof(k); ++i) { hsh ^= b[i]; hsh *= 1099511628211ull; }
+  const int slot = (int)(hsh % MAP_CACHE);
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  MapEntry& e = g_maps[slot];
+  if (e.used && e.key == k) { *out = e.map; return TSR_OK; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { tsr_set_error("conv2d_tc2: cuTensorMapEncodeTiled unavailable"); return TSR_ERR_CUDA; }
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&e.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { e.used = false; tsr_set_error("conv2d_tc2: cuTensorMapEncodeTiled failed (%d)", (int)r); return TSR_ERR_CUDA; }
+  e.key = k; e.used = true;
+  *out = e.map;
+  return TSR_OK;
+}
+
+struct ConvSrc {          // mirrors TsrConvSrc
+  const void* in;
+  const void* w_packed;
+  int in_ld, Cin, KS, pad_;
+};
+struct ConvTc2 {          // mirrors TsrConvTc2
+  ConvSrc src[2];
+  const float* bias;
+  const void* residual;
+  void* out;
+  void* out2_bf16;
+  float* stat;
+  const void* aux;
+  const float* aux_scale;
+  const float* aux_shift;
+  int nsrc, dual_fwd;
+  int res_ld, out_ld, out2_ld, stat_ld, aux_ld;
+  int B, H, W, Cout, flags;
+};
+static_assert(sizeof(ConvSrc) == 32, "TsrConvSrc layout");
+static_assert(sizeof(ConvTc2) == 64 + 8 * 8 + 12 * 4, "TsrConvTc2 layout");
+
+template <int NACC>
+int launch_tc2(const CUtensorMap (&am)[2], const CUtensorMap (&wm)[2], P2& p, cudaStream_t stream) {
+  p.na_slots = (p.nseg == 1 && p.seg[0].pad == 0) ? 5 : 2;
+  static const int env_na = getenv("TSR_TC2_NA") ? atoi(getenv("TSR_TC2_NA")) : 0;     // experiment overrides
+  static const int env_nb = getenv("TSR_TC2_NB") ? atoi(getenv("TSR_TC2_NB")) : 0;
+  if (env_na > 0 && env_na <= T2_MAX_NA && p.seg[0].pad != 0) p.na_slots = env_na;
+  const size_t fixed = 1024 + (size_t)p.na_slots * p.a_slot_bytes + 512;
+  constexpr size_t half = (size_t)(NACC / 2) * 128;
+  if (fixed + 2 * half > SMEM_LIMIT) { tsr_set_error("conv2d_tc2: shared memory plan infeasible"); return TSR_ERR_UNSUPPORTED; }
+  int stages = (int)((SMEM_LIMIT - fixed) / half);
+  if (stages > T2_MAX_NB) stages = T2_MAX_NB;
+  if (env_nb >= 2 && env_nb < stages) stages = env_nb;
+  if (stages < 2) { tsr_set_error("conv2d_tc2: shared memory plan infeasible"); return TSR_ERR_UNSUPPORTED; }
+  p.nb_stages = stages;
+  const size_t smem = fixed + (size_t)stages * half;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TSR_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    attr_set = true;
+  }
+  const int npb = (p.nblocks + 1) / 2 * p.ngroups;
+  const int pairs = npb < num_sms() / 2 ? npb : num_sms() / 2;
+  conv_tc2_kernel<NACC><<<2 * pairs, T2_THREADS, smem, stream>>>(am[0], am[1], wm[0], wm[1], p);
+  TSR_CHECK_LAUNCH("conv2d_tc2");
+  return TSR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tsr_conv2d_tc2_stat_rows(void) { return T2_STAT_ROWS; }
+
+size_t tsr_pack_conv_weight_dual_elems(int Cin) { return (size_t)(Cin / 64) * DUAL_CHUNK_ROWS * 64; }
+
+// w3: (64, Cin, 3, 3), w5: (64, Cin, 5, 5) fp32 OIHW -> dual-branch forward image (dtype 1 = bf16, 2 = fp16)
+int tsr_pack_conv_weight_dual(const float* w3, const float* w5, void* out, int Cin, int dtype, cudaStream_t stream) {
+  TSR_REQUIRE(w3 && w5 && out, "pack_conv_weight_dual: null pointer");
+  TSR_REQUIRE(Cin > 0 && Cin % 64 == 0, "pack_conv_weight_dual: Cin must be a multiple of 64");
+  TSR_REQUIRE(dtype == TSR_DT_BF16 || dtype == TSR_DT_F16, "pack_conv_weight_dual: dtype must be 1 (bf16) or 2 (fp16)");
+  const long long n = 64ll * Cin * 34;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 1024) blocks = 1024;
+  if (dtype == TSR_DT_F16) pack_dual_kernel<__half><<<blocks, 256, 0, stream>>>(w3, w5, (__half*)out, Cin);
+  else pack_dual_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(w3, w5, (__nv_bfloat16*)out, Cin);
+  TSR_CHECK_LAUNCH("pack_conv_weight_dual");
+  return TSR_OK;
+}
+
+int tsr_conv2d_tc2(const void* args, cudaStream_t stream) {
+  TSR_REQUIRE(args, "conv2d_tc2: null argument block");
+  const ConvTc2& a = *reinterpret_cast<const ConvTc2*>(args);
+  TSR_REQUIRE(a.nsrc == 1 || a.nsrc == 2, "conv2d_tc2: nsrc must be 1 or 2");
+  TSR_REQUIRE(!(a.dual_fwd && a.nsrc != 1), "conv2d_tc2: the dual-branch forward takes one source");
+  TSR_REQUIRE(a.out && a.B > 0 && a.H > 0, "conv2d_tc2: bad argument");
+  TSR_REQUIRE(a.W % 8 == 0, "conv2d_tc2: W must be a multiple of 8 (got %d)", a.W);
+  TSR_REQUIRE(a.Cout == 64 || (a.Cout > 0 && a.Cout % 128 == 0), "conv2d_tc2: Cout must be 64 or a multiple of 128 (got %d)", a.Cout);
+  TSR_REQUIRE(!a.dual_fwd || a.Cout == 128, "conv2d_tc2: the dual-branch forward produces 64 + 64 channels");
+  TSR_REQUIRE(a.out_ld % 8 == 0 && ((uintptr_t)a.out & 15) == 0, "conv2d_tc2: out must be 16-byte aligned, stride %% 8 == 0");
+  TSR_REQUIRE(!a.residual || (a.res_ld % 8 == 0 && ((uintptr_t)a.residual & 15) == 0), "conv2d_tc2: residual alignment");
+  TSR_REQUIRE(!a.out2_bf16 || (a.out2_ld % 8 == 0 && ((uintptr_t)a.out2_bf16 & 15) == 0), "conv2d_tc2: out2 alignment");
+  TSR_REQUIRE(!a.aux || (a.aux_ld % 8 == 0 && ((uintptr_t)a.aux & 15) == 0), "conv2d_tc2: aux alignment");
+  TSR_REQUIRE(!a.bias || ((uintptr_t)a.bias & 15) == 0, "conv2d_tc2: bias must be 16-byte aligned");
+  const int fl = a.flags;
+  TSR_REQUIRE(!(fl & (F_MASK | F_BNB)) || a.aux, "conv2d_tc2: mask / BN-backward epilogue needs the aux tensor");
+  TSR_REQUIRE(!(fl & F_BNB_RELU) || (a.aux_scale && a.aux_shift && ((uintptr_t)a.aux_scale & 15) == 0 && ((uintptr_t)a.aux_shift & 15) == 0),
+              "conv2d_tc2: BN-backward ReLU mask needs 16-byte aligned scale / shift");
+  TSR_REQUIRE(!a.stat || a.stat_ld >= a.Cout, "conv2d_tc2: stat_ld too small");
+
+  P2 p;
+  memset(&p, 0, sizeof(p));
+  int maxpad = 0;
+  for (int s = 0; s < a.nsrc; ++s) {
+    const ConvSrc& c = a.src[s];
+    TSR_REQUIRE(c.in && c.w_packed, "conv2d_tc2: null source pointer");
+    TSR_REQUIRE(c.Cin > 0 && c.Cin % 64 == 0, "conv2d_tc2: Cin must be a multiple of 64 (got %d)", c.Cin);
+    TSR_REQUIRE(c.KS == 1 || c.KS == 3 || c.KS == 5, "conv2d_tc2: kernel size %d unsupported", c.KS);
+    TSR_REQUIRE(c.in_ld % 8 == 0 && ((uintptr_t)c.in & 15) == 0 && ((uintptr_t)c.w_packed & 15) == 0, "conv2d_tc2: source alignment");
+    const int pad = a.dual_fwd ? 2 : c.KS / 2;
+    TSR_REQUIRE(!a.dual_fwd || c.KS == 5, "conv2d_tc2: dual-branch forward: give KS = 5 (the 3x3 shares the halo tile)");
+    if (pad > maxpad) maxpad = pad;
+  }
+  TSR_REQUIRE(a.nsrc == 1 || (a.src[0].KS > 1 && a.src[1].KS > 1), "conv2d_tc2: 1x1 sources cannot be K-concatenated");
+  const int NACC = a.Cout == 64 ? 64 : 128;
+  p.nseg = a.nsrc;
+  p.H = a.H; p.W = a.W; p.Hp = a.H + maxpad; p.Vtotal = a.B * p.Hp;
+  p.nxg = a.W / 8;
+  p.nblocks = tsr_cdiv(p.Vtotal, 16 * T2_TILES) * p.nxg;
+  p.ngroups = NACC == 128 ? a.Cout / 128 : 1;
+  CUtensorMap am[2], wm[2];
+  for (int s = 0; s < a.nsrc; ++s) {
+    const ConvSrc& c = a.src[s];
+    Seg& sg = p.seg[s];
+    const int pad = c.KS / 2, taps = c.KS * c.KS;
+    sg.nchunks = c.Cin / 64; sg.ntaps = taps; sg.pad = pad; sg.P = 8 + 2 * pad; sg.rows = 16 * T2_TILES + 2 * pad;
+    sg.amap = s;
+    sg.row_bytes = (uint32_t)sg.P * 128u;
+    sg.mt_units = 16u * sg.P * 8u;
+    sg.a_hi = desc_hi((uint32_t)sg.P * 128u);
+    const uint32_t slot = ((uint32_t)sg.rows * sg.P * 128u + 1023u) & ~1023u;
+    if (slot > p.a_slot_bytes) p.a_slot_bytes = slot;
+    {
+      cuuint64_t gdim[4] = {(cuuint64_t)c.Cin, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+      cuuint64_t gstr[3] = {(cuuint64_t)c.in_ld * 2, (cuuint64_t)a.W * c.in_ld * 2, (cuuint64_t)a.H * a.W * c.in_ld * 2};
+      cuuint32_t box[4] = {64, (cuuint32_t)(8 + 2 * pad), 1, 1};
+      if (pad == 0) {   // no halo: rows of consecutive samples are contiguous => one (B*H)-row dimension, 32-row boxes
+        gdim[2] = (cuuint64_t)a.H * a.B; gdim[3] = 1;
+        box[2] = 16 * T2_TILES;
+      }
+      int rc = get_map(&am[s], c.in, 4, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    if (a.dual_fwd) {
+      sg.chunk_wrows = DUAL_CHUNK_ROWS;
+      int u = 0;
+      for (int ky = 1; ky <= 3; ++ky)
+        for (int kx = 1; kx <= 3; ++kx, ++u) {
+          p.tap[0][u] = (uint32_t)((ky * sg.P + kx) * 8);
+          p.wrow[0][u] = u * 128;
+        }
+      for (int ky = 0; ky < 5; ++ky)
+        for (int kx = 0; kx < 5; ++kx) {
+          if (ky >= 1 && ky <= 3 && kx >= 1 && kx <= 3) continue;
+          p.tap[0][u] = (uint32_t)((ky * sg.P + kx) * 8) | (1u << 12) | (1u << 13);
+          p.wrow[0][u] = 9 * 128 + dual_outer_index(ky, kx) * 64;
+          ++u;
+        }
+      cuuint64_t gdim[2] = {64, (cuuint64_t)sg.nchunks * DUAL_CHUNK_ROWS};
+      cuuint64_t gstr[1] = {128};
+      cuuint32_t box0[2] = {64, 64}, box1[2] = {64, 32};
+      int rc = get_map(&wm[0], c.w_packed, 2, gdim, gstr, box0, CU_TENSOR_MAP_SWIZZLE_NONE);
+      if (rc) return rc;
+      rc = get_map(&wm[1], c.w_packed, 2, gdim, gstr, box1, CU_TENSOR_MAP_SWIZZLE_NONE);
+      if (rc) return rc;
+    } else {
+      sg.chunk_wrows = taps * a.Cout;
+      for (int t = 0; t < taps; ++t) {
+        p.tap[s][t] = (uint32_t)(((t / c.KS) * sg.P + t % c.KS) * 8) | ((uint32_t)s << 12);
+        p.wrow[s][t] = t * a.Cout;
+      }
+      cuuint64_t gdim[2] = {64, (cuuint64_t)sg.nchunks * taps * a.Cout};
+      cuuint64_t gstr[1] = {128};
+      cuuint32_t box[2] = {64, (cuuint32_t)(NACC / 2)};
+      int rc = get_map(&wm[s], c.w_packed, 2, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+      if (rc) return rc;
+    }
+  }
+  if (a.nsrc == 1) { am[1] = am[0]; if (!a.dual_fwd) wm[1] = wm[0]; }
+  p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.out2 = (__nv_bfloat16*)a.out2_bf16; p.stat = a.stat;
+  p.aux = a.aux; p.aux_sc = a.aux_scale; p.aux_sh = a.aux_shift;
+  p.res_ld = a.res_ld; p.out_ld = a.out_ld; p.out2_ld = a.out2_ld; p.stat_ld = a.stat_ld; p.aux_ld = a.aux_ld;
+  p.flags = fl;
+  if (a.stat && !(fl & F_STAT_PRECLEARED))
+    TSR_CUDA(cudaMemsetAsync(a.stat, 0, (size_t)T2_STAT_ROWS * 2 * a.stat_ld * sizeof(float), stream));
+  return NACC == 128 ? launch_tc2<128>(am, wm, p, stream) : launch_tc2<64>(am, wm, p, stream);
+}
+
+}  // extern "C"

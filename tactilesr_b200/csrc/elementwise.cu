@@ -16,13 +16,14 @@ namespace {
 // partial rows of quantities 0 and 1 of channel c (fixed-order tree => deterministic).
 constexpr int FIN_CH = 8, FIN_LANES = 128;
 __device__ __forceinline__ void reduce_partials2(const float* __restrict__ partial, int nblocks, int C, int c,
-                                                 double& s0, double& s1) {
+                                                 double& s0, double& s1, int ld = 0) {
   __shared__ double sh[2][FIN_LANES][FIN_CH + 1];
   double a = 0.0, b = 0.0;
+  if (ld <= 0) ld = C;            // row pitch of the table (a channel slice of a wider table: ld > C)
   if (c < C)
     for (int r = threadIdx.y; r < nblocks; r += FIN_LANES) {
-      a += (double)partial[((long long)r * 2 + 0) * C + c];
-      b += (double)partial[((long long)r * 2 + 1) * C + c];
+      a += (double)partial[((long long)r * 2 + 0) * ld + c];
+      b += (double)partial[((long long)r * 2 + 1) * ld + c];
     }
   sh[0][threadIdx.y][threadIdx.x] = a;
   sh[1][threadIdx.y][threadIdx.x] = b;
@@ -75,11 +76,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblock
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ nbt, float momentum, float eps,
                                    float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+                                   float* __restrict__ save_mean, float* __restrict__ save_invstd, int part_ld = 0) {
   const int c = blockIdx.x * FIN_CH + threadIdx.x;
   if (c == 0 && threadIdx.y == 0 && nbt) *nbt += 1;
   double s, ss;
-  reduce_partials2(partial, nblocks, C, c, s, ss);
+  reduce_partials2(partial, nblocks, C, c, s, ss, part_ld);
   if (c >= C || threadIdx.y != 0) return;
   double mean = s / n;
   double var = ss / n - mean * mean;
@@ -185,6 +186,23 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
   double s, sx;
   reduce_partials2(partial, nblocks, C, c, s, sx);
   if (c >= C || threadIdx.y != 0) return;
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)sx : (float)sx;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
+  c1[c] = training ? (float)(s / n) : 0.f;
+  c2[c] = training ? (float)(sx / n) : 0.f;
+}
+
+// level 2 of the BatchNorm backward when level 1 came out of a data-gradient epilogue (conv_tc2.cu): the table holds
+// sum g and sum g*y (y = the pre-normalisation tensor), so sum g*xhat = invstd * (sum g*y - mean * sum g)
+__global__ void bn_bwd_finalize_gy_kernel(const float* __restrict__ partial, int part_ld, int nblocks, int C, double n,
+                                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
+                                          float* __restrict__ c1, float* __restrict__ c2, int training) {
+  const int c = blockIdx.x * FIN_CH + threadIdx.x;
+  double s, sy;
+  reduce_partials2(partial, nblocks, C, c, s, sy, part_ld);
+  if (c >= C || threadIdx.y != 0) return;
+  const double sx = (double)invstd[c] * (sy - (double)mean[c] * s);
   if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)sx : (float)sx;
   if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
   c1[c] = training ? (float)(s / n) : 0.f;
@@ -705,15 +723,15 @@ int tsr_bn_train_stats(const void* y, int y_ld, int y_bf16, long long npix, int 
 
 // finalise batch statistics from partial sums some other kernel produced (the tensor-core conv epilogue):
 // partial[nrows][2][C] (sum, sum of squares) -> scale / shift / saved mean / invstd, running statistics updated.
-int tsr_bn_finalize_partials(const float* partial, int nrows, long long npix, int C, const float* gamma, const float* beta,
-                             float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
-                             float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
+int tsr_bn_finalize_partials(const float* partial, int part_ld, int nrows, long long npix, int C, const float* gamma,
+                             const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
+                             float momentum, float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
                              cudaStream_t stream) {
-  TSR_REQUIRE(partial && gamma && beta && scale && shift && save_mean && save_invstd && nrows > 0 && npix > 0,
+  TSR_REQUIRE(partial && gamma && beta && scale && shift && save_mean && save_invstd && nrows > 0 && npix > 0 && part_ld >= C,
               "bn_finalize_partials: bad argument");
   bn_finalize_kernel<<<tsr_cdiv(C, FIN_CH), dim3(FIN_CH, FIN_LANES), 0, stream>>>(partial, nrows, C, (double)npix, gamma, beta, running_mean,
                                                            running_var, num_batches_tracked, momentum, eps, scale, shift,
-                                                           save_mean, save_invstd);
+                                                           save_mean, save_invstd, part_ld);
   TSR_CHECK_LAUNCH("bn_finalize");
   return TSR_OK;
 }
@@ -822,6 +840,38 @@ int tsr_bn_backward(const void* da, int da_ld, const void* y, int y_ld, void* dy
 size_t tsr_bn_backward_workspace(long long npix, int C) {
   int rpb;
   return (size_t)red_blocks(npix, rpb) * 2 * C * sizeof(float) + 2 * (size_t)C * sizeof(float);
+}
+
+// BatchNorm backward, level 2, from the partial table a data-gradient epilogue produced (tsr_conv2d_tc2 with
+// TSR_TC2_BNB): partial[nrows][2][part_ld] = (sum g, sum g*y) with g already masked by the ReLU.  Writes dgamma / dbeta
+// and the two per-channel constants c1 = sum g / n, c2 = sum g*xhat / n that tsr_bn_backward_apply consumes.
+int tsr_bn_bwd_finalize_partials(const float* partial, int part_ld, int nrows, long long npix, int C, const float* save_mean,
+                                 const float* save_invstd, float* dgamma, float* dbeta, int accumulate, float* c1, float* c2,
+                                 int training, cudaStream_t stream) {
+  TSR_REQUIRE(partial && save_mean && save_invstd && c1 && c2 && nrows > 0 && npix > 0 && part_ld >= C,
+              "bn_bwd_finalize_partials: bad argument");
+  bn_bwd_finalize_gy_kernel<<<tsr_cdiv(C, FIN_CH), dim3(FIN_CH, FIN_LANES), 0, stream>>>(partial, part_ld, nrows, C, (double)npix, save_mean,
+                                                                                        save_invstd, dgamma, dbeta, accumulate, c1, c2, training);
+  TSR_CHECK_LAUNCH("bn_bwd_finalize_gy");
+  return TSR_OK;
+}
+
+// BatchNorm backward, level 3 alone: dy = scale * (g - c1 - xhat * c2) with g = da (relu = 0: already masked by the
+// producer's epilogue) or da * [scale*y + shift > 0] (relu = 1).  act_bf16 as in tsr_bn_backward (1 / 2: 16-bit operands).
+int tsr_bn_backward_apply(const void* da, int da_ld, const void* y, int y_ld, void* dy, int dy_ld, int act_bf16,
+                          const float* scale, const float* shift, const float* save_mean, const float* save_invstd,
+                          const float* c1, const float* c2, long long npix, int C, int relu, cudaStream_t stream) {
+  TSR_REQUIRE(da && y && dy && scale && shift && save_mean && save_invstd && c1 && c2, "bn_backward_apply: null pointer");
+  TSR_REQUIRE(act_bf16 == TSR_DT_BF16 || act_bf16 == TSR_DT_F16, "bn_backward_apply: 16-bit operands only");
+  TSR_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0 && da_ld % 8 == 0 && y_ld % 8 == 0 && dy_ld % 8 == 0,
+              "bn_backward_apply: C must be 8 * (a divisor of 256), strides multiples of 8");
+  typedef __nv_bfloat16 bf;
+  if (act_bf16 == TSR_DT_F16)
+    bn_bwd_apply_v_kernel<bf, __half><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>((const bf*)da, da_ld, (const __half*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (bf*)dy, dy_ld, npix, C, relu);
+  else
+    bn_bwd_apply_v_kernel<bf, bf><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>((const bf*)da, da_ld, (const bf*)y, y_ld, scale, shift, save_mean, save_invstd, c1, c2, (bf*)dy, dy_ld, npix, C, relu);
+  TSR_CHECK_LAUNCH("bn_bwd_apply");
+  return TSR_OK;
 }
 
 int tsr_relu_backward(const void* da, int da_ld, const void* a, int a_ld, void* dz, int dz_ld, int act_bf16,

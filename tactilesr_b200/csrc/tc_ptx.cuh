@@ -89,7 +89,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // the swizzle phase of TMA and UMMA follows the absolute shared-memory address), [61,64) layout=2 (SWIZZLE_128B).
 // The issuing thread is a single lane: every ALU instruction in its loop costs ~4 cycles of dependent issue, so the
 // descriptors are split into a constant high word and a low word that only ever needs an integer add.
-__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
+__host__ __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
 }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo_bytes) {
@@ -120,5 +120,105 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) helpers
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                                uint32_t bar_leader) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_leader) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// dual-branch (3x3 | 5x5, 64 + 64 output channels) forward weight image: per 64-channel input chunk, the 9 central taps
+// x 128 rows ([conv3 co | conv5 co]) followed by the 16 outer taps x 64 rows (conv5 co)
+// ------------------------------------------------------------------------------------------------
+constexpr int DUAL_CHUNK_ROWS = 9 * 128 + 16 * 64;     // 2176
+
+__host__ __device__ inline int dual_outer_index(int ky, int kx) {      // rank of an outer tap in raster order
+  const int t = ky * 5 + kx;
+  int central_before = 0;
+  for (int yy = 1; yy <= 3; ++yy)
+    for (int xx = 1; xx <= 3; ++xx)
+      if (yy * 5 + xx < t) ++central_before;
+  return t - central_before;
+}
+
+// row of output channel co of tap (ky, kx) of the 3x3 (five = false) or 5x5 branch inside a chunk of the image
+__host__ __device__ inline int dual_image_row(bool five, int ky, int kx, int co) {
+  if (!five) return (ky * 3 + kx) * 128 + co;
+  if (ky >= 1 && ky <= 3 && kx >= 1 && kx <= 3) return ((ky - 1) * 3 + (kx - 1)) * 128 + 64 + co;
+  return 9 * 128 + dual_outer_index(ky, kx) * 64 + co;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
 
 }  // namespace

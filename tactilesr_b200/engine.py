@@ -93,8 +93,13 @@ class RunCtx:
         self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         # "fp16" mode with gradients: bf16 shadow of every buffer some conv reads (the weight-gradient operand; tcgen05
         # kind::f16 cannot mix an fp16 x with a bf16 dy).  Producers write their channel slice of the shadow.
-        self.bn_partials: Dict[object, torch.Tensor] = {}      # BNReLUOp -> statistics partials from its conv's epilogue
-        self.folded: set = set()                               # BNReLUOps already applied by their (inference) conv
+        self.bn_partials: Dict[object, torch.Tensor] = {}      # BNReLUOp -> statistics partials from its convs' epilogues
+        self.bn_partials_parts: Dict[object, set] = {}         # ... and which of its parts they cover
+        self.folded: Dict[object, set] = {}                    # BNReLUOp -> parts already applied by their (inference) conv
+        self.grad_masked: set = set()                          # buffers whose gradient already carries the ReLU mask
+        self.grad_alias: Dict[Buf, tuple] = {}                 # residual gradients handed over by reference (ptr, ld, keepalive)
+        self.bnb: Dict[object, torch.Tensor] = {}              # BNReLUOp -> (sum g, sum g*y) partials from a dgrad epilogue
+        self.keep: list = []                                   # small temporaries that must outlive the launches reading them
         self.keep_taps = False
         self.shadow: Dict[Buf, torch.Tensor] = {}
         self.conv_inputs: set = set()
@@ -145,6 +150,16 @@ class RunCtx:
             sp, sld = self.sptr(v)
             _lib.call("tsr_copy_channels", ip, ild, 2, sp, sld, 1, self.npix, v.C, _lib.stream_ptr())
 
+    def stat_table(self, bnop, part: int) -> torch.Tensor:
+        """Zeroed [rows][2][channels of bnop] table that the conv epilogue(s) feeding ``bnop`` add their statistics to."""
+        t = self.bn_partials.get(bnop)
+        if t is None:
+            t = torch.zeros((_lib.lib().tsr_conv2d_tc2_stat_rows(), 2, bnop.src.C), dtype=torch.float32, device=self.device)
+            self.bn_partials[bnop] = t
+            self.bn_partials_parts[bnop] = set()
+        self.bn_partials_parts[bnop].add(part)
+        return t
+
     def workspace(self, nbytes: int) -> Tuple[int, int]:
         nbytes = max(int(nbytes), 256)
         if self._ws is None or self._ws.numel() < nbytes:
@@ -175,37 +190,70 @@ class _PackCache:
     def __init__(self):
         self._groups = {}      # (mode, ids of a program's conv weights) -> persistent buffers + device descriptor table
 
-    def get(self, w: torch.Tensor, mode: str, need_dgrad: bool):
-        tag = (w.data_ptr(), w._version, _WEIGHT_EPOCH, tuple(w.shape), w.device)
+    @staticmethod
+    def _tag(w: torch.Tensor):
+        return (w.data_ptr(), w._version, _WEIGHT_EPOCH, tuple(w.shape), w.device)
+
+    def get(self, w: torch.Tensor, mode: str, need_dgrad: bool, need_fwd: bool = True):
+        """(forward image, data-gradient image) of conv weight ``w``; an image that is not asked for may be None."""
+        tag = self._tag(w)
         store = w.__dict__.setdefault("_tsr_pack", {})
         hit = store.get(mode)
-        if hit is not None and hit[0] == tag and (hit[2] is not None or not need_dgrad):
-            return hit[1], hit[2]
+        if hit is not None and hit[0] != tag:
+            hit = None
+        wf = hit[1] if hit is not None else None
+        wd = hit[2] if hit is not None else None
+        if (wf is not None or not need_fwd) and (wd is not None or not need_dgrad):
+            return wf, wd
         Cout, Cin, K, _ = w.shape
-        dt = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[mode]
-        wf = torch.empty((K * K * Cin * Cout,), dtype=dt, device=w.device)
+        n = K * K * Cin * Cout
         wc = w.detach().contiguous()
         st = _lib.stream_ptr()
+        mk_f, mk_d = need_fwd and wf is None, need_dgrad and wd is None
         if mode == "fp16":       # forward weights fp16, data-gradient weights bf16 (gradients are bf16 tensors)
-            wd = torch.empty_like(wf, dtype=torch.bfloat16) if need_dgrad else None
-            _lib.call("tsr_pack_conv_weight_f16", wc.data_ptr(), wf.data_ptr(), 0, Cout, Cin, K, st)
-            if need_dgrad:
+            if mk_f:
+                wf = torch.empty((n,), dtype=torch.float16, device=w.device)
+                _lib.call("tsr_pack_conv_weight_f16", wc.data_ptr(), wf.data_ptr(), 0, Cout, Cin, K, st)
+            if mk_d:
+                wd = torch.empty((n,), dtype=torch.bfloat16, device=w.device)
                 _lib.call("tsr_pack_conv_weight_bf16", wc.data_ptr(), 0, wd.data_ptr(), Cout, Cin, K, st)
         else:
-            wd = torch.empty_like(wf) if need_dgrad else None
+            dt = torch.bfloat16 if mode == "bf16" else torch.float32
+            if mk_f:
+                wf = torch.empty((n,), dtype=dt, device=w.device)
+            if mk_d:
+                wd = torch.empty((n,), dtype=dt, device=w.device)
             fn = "tsr_pack_conv_weight_bf16" if mode == "bf16" else "tsr_pack_conv_weight_f32"
-            _lib.call(fn, wc.data_ptr(), wf.data_ptr(), _ptr(wd), Cout, Cin, K, st)
+            _lib.call(fn, wc.data_ptr(), wf.data_ptr() if mk_f else 0, wd.data_ptr() if mk_d else 0, Cout, Cin, K, st)
         store[mode] = (tag, wf, wd)
         return wf, wd
 
+    def get_dual(self, w3: torch.Tensor, w5: torch.Tensor, mode: str) -> torch.Tensor:
+        """Dual-branch forward image of a (3x3, 5x5) weight pair (tsr_pack_conv_weight_dual); kept on ``w3``."""
+        tag = (self._tag(w3), self._tag(w5))
+        store = w3.__dict__.setdefault("_tsr_pack", {})
+        hit = store.get(mode + ":dual")
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        Cin = w3.shape[1]
+        img = hit[1] if hit is not None else torch.empty((_lib.lib().tsr_pack_conv_weight_dual_elems(Cin),), device=w3.device,
+                                                         dtype=torch.float16 if mode == "fp16" else torch.bfloat16)
+        _lib.call("tsr_pack_conv_weight_dual", w3.detach().contiguous().data_ptr(), w5.detach().contiguous().data_ptr(),
+                  img.data_ptr(), Cin, 2 if mode == "fp16" else 1, _lib.stream_ptr())
+        store[mode + ":dual"] = (tag, img)
+        return img
+
 
     # -- all conv weights of a program in one launch ---------------------------------------------------------------
-    def prepack(self, weights, mode: str, need_dgrad: bool) -> None:
-        """Tensor-core modes: bring the packed images of every weight in ``weights`` up to date with ONE kernel launch
-        (the optimizer changes all of them at every step) and leave the per-parameter cache entries current, so the
-        ConvOps' ``get`` calls all hit.  Buffers and the device descriptor table are persistent per weight set."""
+    def prepack(self, items, mode: str, need_dgrad: bool) -> None:
+        """Tensor-core modes: bring the packed images of every weight in ``items`` = [(weight, role)] up to date with ONE
+        kernel launch (the optimizer changes all of them at every step) and leave the per-parameter cache entries current,
+        so the ops' ``get`` / ``get_dual`` calls all hit.  role 0: standard forward image; roles 1 / 2: the 3x3 / 5x5 branch
+        of a dual-branch image shared by two consecutive items.  Buffers and the device descriptor table are persistent
+        per weight set."""
         import numpy as np
-        key = (mode,) + tuple(id(w) for w in weights)
+        weights = [w for w, _ in items]
+        key = (mode,) + tuple((id(w), r) for w, r in items)
         grp = self._groups.get(key)
         if grp is not None and any(r() is None for r in grp["refs"]):
             grp = None
@@ -225,27 +273,39 @@ class _PackCache:
         if grp["table"] is None or grp["ptrs"] != ptrs or grp["dgrad"] != want_d:
             desc = np.zeros(len(weights), dtype=np.dtype([("w", "<u8"), ("wf", "<u8"), ("wd", "<u8"), ("Cout", "<i4"),
                                                           ("Cin", "<i4"), ("KS", "<i4"), ("dt_f", "<i4"), ("dt_d", "<i4"),
-                                                          ("pad", "<i4")]))
+                                                          ("mode", "<i4")]))
             bufs = []
-            for i, w in enumerate(weights):
+            for i, (w, role) in enumerate(items):
                 Cout, Cin, K, _ = w.shape
                 old = grp["bufs"][i] if i < len(grp["bufs"]) else (None, None)
-                wf = old[0] if old[0] is not None else torch.empty((K * K * Cin * Cout,), dtype=dt_f, device=w.device)
+                if role == 2:
+                    wf = bufs[i - 1][0]                       # the image of the preceding role-1 item
+                elif old[0] is not None:
+                    wf = old[0]
+                elif role == 1:
+                    wf = torch.empty((_lib.lib().tsr_pack_conv_weight_dual_elems(Cin),), dtype=dt_f, device=w.device)
+                else:
+                    wf = torch.empty((K * K * Cin * Cout,), dtype=dt_f, device=w.device)
                 wd = old[1]
                 if want_d and wd is None:
                     wd = torch.empty((K * K * Cin * Cout,), dtype=torch.bfloat16, device=w.device)
                 bufs.append((wf, wd))
                 assert w.is_contiguous()
                 desc[i] = (w.data_ptr(), wf.data_ptr(), 0 if wd is None else wd.data_ptr(), Cout, Cin, K,
-                           2 if mode == "fp16" else 1, 1, 0)
+                           2 if mode == "fp16" else 1, 1, role)
             grp["bufs"], grp["dgrad"], grp["ptrs"] = bufs, want_d, ptrs
             grp["table"] = torch.from_numpy(desc.view(np.uint8).copy()).to(weights[0].device)
             grp["max"] = max(int(w.numel()) for w in weights)
         _lib.call("tsr_pack_conv_weights_multi", grp["table"].data_ptr(), len(weights), grp["max"], _lib.stream_ptr())
         grp["sig"] = sig
-        for w, (wf, wd) in zip(weights, grp["bufs"]):
-            tag = (w.data_ptr(), w._version, _WEIGHT_EPOCH, tuple(w.shape), w.device)
-            w.__dict__.setdefault("_tsr_pack", {})[mode] = (tag, wf, wd)
+        for i, ((w, role), (wf, wd)) in enumerate(zip(items, grp["bufs"])):
+            store = w.__dict__.setdefault("_tsr_pack", {})
+            if role == 0:
+                store[mode] = (self._tag(w), wf, wd)
+            else:
+                store[mode] = (self._tag(w), None, wd)
+                if role == 1:
+                    store[mode + ":dual"] = ((self._tag(w), self._tag(items[i + 1][0])), wf)
 
     def get_folded(self, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, mode: str):
         """Inference: forward pack of ``conv`` with the eval-mode BatchNorm ``bn`` folded in -> (packed weights, bias)."""
@@ -293,6 +353,16 @@ class Op:
     def writes(self) -> Sequence[Buf]:
         return ()
 
+    # -- static structure used by Program.plan() --------------------------------------------------
+    def out_views(self) -> Sequence[View]:
+        """Activation views this op produces."""
+        return ()
+
+    def grad_targets(self) -> Sequence[Tuple[View, str]]:
+        """(view, kind) pairs whose gradient this op's backward writes: kind 'conv' (data gradient of a convolution),
+        'res' (residual hand-over), 'other'."""
+        return ()
+
 
 def _first_write(c: RunCtx, buf: Buf) -> bool:
     """True if this is the first gradient contribution to ``buf`` in the current backward."""
@@ -300,6 +370,20 @@ def _first_write(c: RunCtx, buf: Buf) -> bool:
     first = not c.grad_written[buf]
     c.grad_written[buf] = True
     return first
+
+
+@dataclass
+class Sink:
+    """Post-processing the LAST data-gradient writer of a buffer applies in its epilogue (Program.plan()):
+    kind 'relu': the buffer is the ReLU output of convolutions -> zero the gradient where the activation is <= 0
+    (replaces the tsr_relu_backward pass of the producing ops); kind 'bn': the buffer is the output of one BatchNorm(+ReLU)
+    op -> mask through scale*y + shift > 0 and reduce (sum g, sum g*y) for its backward (replaces the bn_bwd_partial pass)."""
+    kind: str
+    bn: Optional["BNReLUOp"] = None
+
+
+def _stat_rows() -> int:
+    return _lib.lib().tsr_conv2d_tc2_stat_rows()
 
 
 class HeadOp(Op):
@@ -315,6 +399,9 @@ class HeadOp(Op):
     def writes(self):
         return (self.out.buf,)
 
+    def out_views(self):
+        return (self.out,)
+
     def _x(self, c: RunCtx):
         x = c.x
         return x.data_ptr() + self.ch0 * 16 * 4, x.shape[1] * 16
@@ -329,7 +416,7 @@ class HeadOp(Op):
     def bwd(self, c):
         st = _lib.stream_ptr()
         gp, gld = c.vptr(self.out, grad=True)
-        if self.relu:
+        if self.relu and self.out.buf not in c.grad_masked:
             ap, ald = c.vptr(self.out)
             _lib.call("tsr_relu_backward", gp, gld, ap, ald, gp, gld, c.mix, c.npix, self.out.C, st)
         xp, xbs = self._x(c)
@@ -346,7 +433,10 @@ class ConvOp(Op):
                  residual: Optional[View] = None, src_needs_grad: bool = True):
         self.src, self.conv, self.out, self.relu, self.residual = src, conv, out, relu, residual
         self.src_needs_grad = src_needs_grad
-        self.bn_consumer = None      # set by the program builder when the output feeds a BNReLUOp directly
+        self.bn_consumer: Optional["BNReLUOp"] = None   # set by the program builder when the output feeds a BNReLUOp directly
+        self.bn_part = 0                                # ... as its part number `bn_part`
+        self.sink: Optional[Sink] = None                # Program.plan(): fused epilogue of the data gradient into `src`
+        self.alias_residual_grad = False                # Program.plan(): d(residual) may be handed over by reference
         self.K = conv.kernel_size[0]
         self.Cin, self.Cout = conv.in_channels, conv.out_channels
         assert src.C == self.Cin and out.C == self.Cout
@@ -361,90 +451,120 @@ class ConvOp(Op):
     def writes(self):
         return (self.out.buf,)
 
-    def _conv(self, c: RunCtx, inp, inld, wpk, bias, res, resld, outp, outld, Cin, Cout, flags, on_grads=False,
-              bn_partial=0, out2=0, out2_ld=0):
-        st = _lib.stream_ptr()
-        if c.tc:
-            need = _lib.lib().tsr_conv2d_tc_workspace(c.B, c.H, c.W, Cin, Cout, self.K)
-            ws, wsb = c.workspace(need)
-            if c.act == 2 and not on_grads:
-                flags |= 2      # fp16 activations / weights (forward); data gradients run on bf16 tensors
-            _lib.call("tsr_conv2d_tc", inp, inld, wpk, bias, res, resld, outp, outld, c.B, c.H, c.W, Cin, Cout,
-                      self.K, flags, ws, wsb, bn_partial, out2, out2_ld, st)
-        else:
-            _lib.call("tsr_conv2d_f32", inp, inld, wpk, bias, res, resld, outp, outld, c.B, c.H, c.W, Cin, Cout,
-                      self.K, flags, st)
+    def out_views(self):
+        return (self.out,)
 
-    def _wgrad_input(self, c: RunCtx):
-        """(pointer, ld) of the conv input as the weight-gradient kernel wants it (bf16 in both tensor-core modes)."""
-        return c.sptr(self.src) if c.act == 2 else c.vptr(self.src)
+    def grad_targets(self):
+        t = [(self.src, "conv")] if self.src_needs_grad else []
+        if self.residual is not None:
+            t.append((self.residual, "res"))
+        return t
+
+    # -- forward ------------------------------------------------------------------------------------
+    def _bn_slice(self):
+        """(BatchNorm module, output view) of the consumer part this convolution feeds."""
+        bnop = self.bn_consumer
+        bn, off, C = bnop.parts[self.bn_part]
+        return bn, View(bnop.out.buf, bnop.out.c0 + off, C)
+
+    def _feeds_bn(self) -> bool:
+        bnop = self.bn_consumer
+        if bnop is None or self.relu or self.residual is not None or bnop.src.buf is not self.out.buf:
+            return False
+        _, off, C = bnop.parts[self.bn_part]
+        return bnop.src.c0 + off == self.out.c0 and C == self.Cout
 
     def fwd(self, c):
         ip, ild = c.vptr(self.src)
-        bn = self.bn_consumer
-        if (c.tc and bn is not None and not c.training and not c.need_grad and not c.keep_taps and not self.relu
-                and self.residual is None and bn.bn.running_mean is not None and bn.bn.weight is not None
-                and bn.src.buf is self.out.buf
-                and bn.src.c0 == self.out.c0 and bn.src.C == self.Cout):
-            # inference: the eval-mode BatchNorm (+ReLU) that follows is folded into the weights / bias, and the result
-            # goes straight into the BatchNorm's output slice -- no BN kernels, no intermediate tensor
-            wf, bias = _PACK.get_folded(self.conv, bn.bn, c.mode)
-            op, old = c.vptr(bn.out)
-            self._conv(c, ip, ild, wf.data_ptr(), bias.data_ptr(), 0, 0, op, old, self.Cin, self.Cout,
-                       1 if bn.relu else 0)
-            c.folded.add(bn)
+        st = _lib.stream_ptr()
+        if not c.tc:
+            wf, _ = _PACK.get(self.conv.weight, c.mode, False)
+            op, old = c.vptr(self.out)
+            rp, rld = c.vptr(self.residual) if self.residual is not None else (0, 0)
+            _lib.call("tsr_conv2d_f32", ip, ild, wf.data_ptr(), _ptr(self.conv.bias), rp, rld, op, old, c.B, c.H, c.W, self.Cin,
+                      self.Cout, self.K, 1 if self.relu else 0, st)
             return
+        f16 = _lib.TC2_F16 if c.act == 2 else 0
+        feeds = self._feeds_bn()
+        if feeds and not c.training and not c.need_grad and not c.keep_taps:
+            bn, bn_out = self._bn_slice()
+            if bn.running_mean is not None and bn.weight is not None:
+                # inference: the eval-mode BatchNorm (+ReLU) that follows is folded into the weights / bias, and the result
+                # goes straight into the BatchNorm's output slice -- no BN kernels, no intermediate tensor
+                wf, bias = _PACK.get_folded(self.conv, bn, c.mode)
+                op, old = c.vptr(bn_out)
+                _lib.conv_tc2([(ip, ild, self.Cin, self.K, wf.data_ptr())], op, old, c.B, c.H, c.W, self.Cout,
+                              flags=f16 | (_lib.TC2_RELU if self.bn_consumer.relu else 0), bias=bias.data_ptr(), stream=st)
+                c.folded.setdefault(self.bn_consumer, set()).add(self.bn_part)
+                return
         wf, _ = _PACK.get(self.conv.weight, c.mode, False)
         op, old = c.vptr(self.out)
         rp, rld = c.vptr(self.residual) if self.residual is not None else (0, 0)
-        # batch statistics of the BatchNorm that consumes this output come out of the conv epilogue (tensor-core modes)
-        part = 0
-        if (c.tc and bn is not None and not (_lib.lib().tsr_get_tc_desc_mode() & 128)      # bit 7: separate statistics pass
-                and not self.relu and self.residual is None and bn.src.buf is self.out.buf
-                and bn.src.c0 == self.out.c0 and (c.training or bn.bn.running_mean is None)):
-            t = torch.empty((_lib.lib().tsr_conv2d_tc_stat_rows(), 2, self.Cout), dtype=torch.float32, device=c.device)
-            c.bn_partials[bn] = t
-            part = t.data_ptr()
-        if c.tc and c.wants_shadow(self.out.buf):     # bf16 shadow of an fp16 output straight from the epilogue
+        kw = {}
+        flags = f16 | (_lib.TC2_RELU if self.relu else 0)
+        # batch statistics of the BatchNorm that consumes this output come out of the conv epilogue
+        if feeds and not (_lib.lib().tsr_get_tc_desc_mode() & 128):      # bit 7: separate statistics pass
+            bn, _ = self._bn_slice()
+            if c.training or bn.running_mean is None:
+                t = c.stat_table(self.bn_consumer, self.bn_part)
+                off = self.bn_consumer.parts[self.bn_part][1]
+                kw.update(stat=t.data_ptr() + off * 4, stat_ld=t.shape[2])
+                flags |= _lib.TC2_STAT_PRECLEARED
+        if c.wants_shadow(self.out.buf):     # bf16 shadow of an fp16 output straight from the epilogue
             o2, o2ld = c.sptr(self.out)
-            self._conv(c, ip, ild, wf.data_ptr(), _ptr(self.conv.bias), rp, rld, op, old, self.Cin, self.Cout,
-                       1 if self.relu else 0, bn_partial=part, out2=o2, out2_ld=o2ld)
-        else:
-            self._conv(c, ip, ild, wf.data_ptr(), _ptr(self.conv.bias), rp, rld, op, old, self.Cin, self.Cout,
-                       1 if self.relu else 0, bn_partial=part)
+            kw.update(out2=o2, out2_ld=o2ld)
+        _lib.conv_tc2([(ip, ild, self.Cin, self.K, wf.data_ptr())], op, old, c.B, c.H, c.W, self.Cout, flags=flags,
+                      bias=_ptr(self.conv.bias), residual=rp, res_ld=rld, stream=st, **kw)
 
+    # -- backward -----------------------------------------------------------------------------------
     def bwd(self, c):
+        self.bwd_pre(c)
+        self.bwd_weights(c)
+        if self.src_needs_grad:
+            _dgrad(c, [self], self.sink)
+
+    def bwd_pre(self, c):
+        """ReLU backward of the fused epilogue (unless the producer of the gradient already masked it) and the residual
+        branch: d(residual) += dz."""
         st = _lib.stream_ptr()
         gp, gld = c.vptr(self.out, grad=True)
-        if self.relu:
+        if self.relu and self.out.buf not in c.grad_masked:
             ap, ald = c.vptr(self.out)
             _lib.call("tsr_relu_backward", gp, gld, ap, ald, gp, gld, c.mix, c.npix, self.Cout, st)
-        # residual branch: d(residual) += dz
         if self.residual is not None:
-            first = _first_write(c, self.residual.buf)
+            rbuf = self.residual.buf
+            if self.alias_residual_grad and c.tc and rbuf not in c.grads and rbuf not in c.grad_alias:
+                # the next (and last) writer of this gradient is a tensor-core data gradient: it reads dz through its
+                # residual input instead of a copy being made here
+                c.grad_alias[rbuf] = (gp, gld, c.grads[self.out.buf])
+                return
+            first = _first_write(c, rbuf)
             rp, rld = c.vptr(self.residual, grad=True)
             if first:
                 _lib.call("tsr_copy_channels", gp, gld, c.grd, rp, rld, c.grd, c.npix, self.Cout, st)
             else:
                 raise NotImplementedError("residual gradient accumulation after another writer")
-        # weight / bias gradients
-        ip, ild = c.vptr(self.src)
+
+    def bwd_weights(self, c):
+        st = _lib.stream_ptr()
+        gp, gld = c.vptr(self.out, grad=True)
         g, acc = c.pgrad(self.conv.weight)
         if c.tc:
             need = _lib.lib().tsr_conv2d_wgrad_tc_workspace(c.B, c.H, c.W, self.Cin, self.Cout, self.K)
             ws, wsb = c.workspace(need)
-            xp, xld = self._wgrad_input(c)
+            xp, xld = c.sptr(self.src) if c.act == 2 else c.vptr(self.src)     # bf16 in both tensor-core modes
             _lib.call("tsr_conv2d_wgrad_tc", xp, xld, gp, gld, g.data_ptr(), ws, wsb, c.B, c.H, c.W, self.Cin,
                       self.Cout, self.K, acc, st)
         else:
+            ip, ild = c.vptr(self.src)
             need = _lib.lib().tsr_conv2d_wgrad_f32_workspace(c.B, c.H, c.W, self.Cin, self.Cout, self.K)
             ws, wsb = c.workspace(need)
             _lib.call("tsr_conv2d_wgrad_f32", ip, ild, gp, gld, g.data_ptr(), ws, wsb, c.B, c.H, c.W, self.Cin,
                       self.Cout, self.K, acc, st)
         if self.conv.bias is not None:
             gb, accb = c.pgrad(self.conv.bias)
-            bn = self.bn_consumer
-            if bn is not None and c.saved[bn][1]:
+            bnop = self.bn_consumer
+            if bnop is not None and self._feeds_bn() and c.saved[bnop][1][self.bn_part]:
                 # The gradient reaching a bias that feeds a batch-statistics BatchNorm is sum_pix dy with dy the BN
                 # backward output, which is identically 0 (the reference computes fp32 rounding noise ~1e-8 of the layer's
                 # gradient scale here, SURVEY section 0 pitfall 2): write the exact value instead of reducing 2 GB of zeros.
@@ -453,25 +573,84 @@ class ConvOp(Op):
             else:
                 ws, wsb = c.workspace(_lib.lib().tsr_colsum_workspace(c.npix, self.Cout))
                 _lib.call("tsr_colsum", gp, gld, c.grd, c.npix, self.Cout, gb.data_ptr(), ws, wsb, accb, st)
-        # data gradient
-        if self.src_needs_grad:
-            _, wd = _PACK.get(self.conv.weight, c.mode, True)
-            first = _first_write(c, self.src.buf)
-            dp, dld = c.vptr(self.src, grad=True)
-            self._conv(c, gp, gld, wd.data_ptr(), 0, 0 if first else dp, 0 if first else dld, dp, dld, self.Cout,
-                       self.Cin, 0, on_grads=True)
 
 
-class BNReLUOp(Op):
-    """BatchNorm2d (train: batch statistics + running-stat update; eval: running stats) [+ ReLU]
-    (reference tactileSR_model.py:38-39, 42-43, 48-49, 169-170, 175-176, 181-182, 187-188)."""
+def _dgrad(c: RunCtx, ops: List[ConvOp], sink: Optional[Sink]) -> None:
+    """Data gradient of one convolution, or of two convolutions that read the same view (their contributions are
+    K-concatenated into ONE tensor-core launch), into the gradient of ``ops[0].src`` -- adding to what earlier writers
+    left there (through the epilogue's residual input) and applying the buffer's Sink when this is its last writer."""
+    st = _lib.stream_ptr()
+    src = ops[0].src
+    buf = src.buf
+    if not c.tc:
+        for op in ops:
+            _, wd = _PACK.get(op.conv.weight, c.mode, True)
+            first = _first_write(c, buf)
+            dp, dld = c.vptr(src, grad=True)
+            gp, gld = c.vptr(op.out, grad=True)
+            _lib.call("tsr_conv2d_f32", gp, gld, wd.data_ptr(), 0, 0 if first else dp, 0 if first else dld, dp, dld, c.B, c.H,
+                      c.W, op.Cout, op.Cin, op.K, 0, st)
+        return
+    alias = c.grad_alias.pop(buf, None)
+    first = _first_write(c, buf)
+    dp, dld = c.vptr(src, grad=True)
+    if alias is not None:
+        rp, rld = alias[0], alias[1]
+    elif not first:
+        rp, rld = dp, dld
+    else:
+        rp, rld = 0, 0
+    srcs = []
+    for op in ops:
+        _, wd = _PACK.get(op.conv.weight, c.mode, True, need_fwd=False)
+        gp, gld = c.vptr(op.out, grad=True)
+        srcs.append((gp, gld, op.Cout, op.K, wd.data_ptr()))
+    if len(srcs) == 2 and (srcs[0][3] == 1 or srcs[1][3] == 1):        # 1x1 sources cannot be K-concatenated: two launches
+        _lib.conv_tc2(srcs[:1], dp, dld, c.B, c.H, c.W, src.C, residual=rp, res_ld=rld, stream=st)
+        srcs, rp, rld = srcs[1:], dp, dld
+    flags, kw = 0, {}
+    whole = src.c0 == 0 and src.C == buf.C
+    if sink is not None and whole and not (_lib.lib().tsr_get_tc_desc_mode() & 256):     # bit 8: no fused gradient sinks
+        auxf = _lib.TC2_AUX_F16 if c.act == 2 else 0
+        if sink.kind == "relu":
+            ap, ald = c.vptr(View.of(buf))
+            flags = _lib.TC2_MASK | auxf
+            kw.update(aux=ap, aux_ld=ald)
+            c.grad_masked.add(buf)
+        elif sink.kind == "bn" and sink.bn in c.saved:
+            bnop = sink.bn
+            coef = c.saved[bnop][0]
+            yp, yld = c.vptr(bnop.src)
+            part = torch.zeros((_stat_rows(), 2, buf.C), dtype=torch.float32, device=c.device)
+            flags = _lib.TC2_BNB | (_lib.TC2_BNB_RELU if bnop.relu else 0) | auxf | _lib.TC2_STAT_PRECLEARED
+            kw.update(aux=yp, aux_ld=yld, aux_scale=coef[0].data_ptr(), aux_shift=coef[1].data_ptr(), stat=part.data_ptr(),
+                      stat_ld=buf.C)
+            c.bnb[bnop] = part
+    _lib.conv_tc2(srcs, dp, dld, c.B, c.H, c.W, src.C, flags=flags, residual=rp, res_ld=rld, stream=st, **kw)
 
-    def __init__(self, src: View, bn: torch.nn.BatchNorm2d, out: View, relu: bool = True):
-        self.src, self.bn, self.out, self.relu = src, bn, out, relu
-        assert src.C == bn.num_features == out.C
+
+class DualConvOp(Op):
+    """The 3x3 and the 5x5 convolution of one input, outputs side by side in one buffer (MSRB.forward, reference
+    tactileSR_model.py:198-199 and :201-202; the torch.cat of :200 / :203 is the shared buffer).  Forward: ONE dual-branch
+    tensor-core launch when both produce 64 channels (the 9 shared taps run at N = 128), else two launches; backward: two
+    weight gradients and ONE K-concatenated data gradient."""
+
+    def __init__(self, src: View, conv_a: torch.nn.Conv2d, conv_b: torch.nn.Conv2d, out: View):
+        Ca, Cb = conv_a.out_channels, conv_b.out_channels
+        assert out.C == Ca + Cb
+        self.a = ConvOp(src, conv_a, View(out.buf, out.c0, Ca))
+        self.b = ConvOp(src, conv_b, View(out.buf, out.c0 + Ca, Cb))
+        self.src, self.out = src, out
+        self.sink: Optional[Sink] = None
+        self.dual_ok = (self.a.K == 3 and self.b.K == 5 and Ca == 64 and Cb == 64 and src.C % 64 == 0)
+
+    def feed(self, bnop: "BNReLUOp") -> "BNReLUOp":
+        self.a.bn_consumer, self.a.bn_part = bnop, 0
+        self.b.bn_consumer, self.b.bn_part = bnop, 1
+        return bnop
 
     def params(self):
-        return (self.bn.weight, self.bn.bias)
+        return tuple(self.a.params()) + tuple(self.b.params())
 
     def reads(self):
         return (self.src.buf,)
@@ -479,56 +658,155 @@ class BNReLUOp(Op):
     def writes(self):
         return (self.out.buf,)
 
+    def out_views(self):
+        return (self.a.out, self.b.out)
+
+    def grad_targets(self):
+        return [(self.src, "conv")]
+
     def fwd(self, c):
-        if self in c.folded:
+        bnop = self.a.bn_consumer
+        use_dual = (c.tc and self.dual_ok and (c.training or c.need_grad) and bnop is not None and bnop is self.b.bn_consumer
+                    and self.a._feeds_bn() and self.b._feeds_bn() and not (_lib.lib().tsr_get_tc_desc_mode() & 512))   # bit 9
+        if not use_dual:
+            self.a.fwd(c)
+            self.b.fwd(c)
             return
+        img = _PACK.get_dual(self.a.conv.weight, self.b.conv.weight, c.mode)
+        ip, ild = c.vptr(self.src)
+        op, old = c.vptr(self.out)
+        ba, bb = self.a.conv.bias, self.b.conv.bias
+        bias = 0
+        if ba is not None or bb is not None:
+            z = torch.zeros(64, dtype=torch.float32, device=c.device) if (ba is None or bb is None) else None
+            bias_t = torch.cat([z if ba is None else ba.detach(), z if bb is None else bb.detach()])
+            c.keep.append(bias_t)
+            bias = bias_t.data_ptr()
+        flags = _lib.TC2_F16 if c.act == 2 else 0
+        kw = {}
+        bna, bnb_ = self.a._bn_slice()[0], self.b._bn_slice()[0]
+        if ((c.training or (bna.running_mean is None and bnb_.running_mean is None))
+                and not (_lib.lib().tsr_get_tc_desc_mode() & 128)):
+            t = c.stat_table(bnop, 0)
+            c.stat_table(bnop, 1)
+            kw.update(stat=t.data_ptr(), stat_ld=t.shape[2])
+            flags |= _lib.TC2_STAT_PRECLEARED
+        _lib.conv_tc2([(ip, ild, self.src.C, 5, img.data_ptr())], op, old, c.B, c.H, c.W, 128, flags=flags, bias=bias,
+                      dual_fwd=1, stream=_lib.stream_ptr(), **kw)
+
+    def bwd(self, c):
+        self.a.bwd_weights(c)
+        self.b.bwd_weights(c)
+        _dgrad(c, [self.a, self.b], self.sink)
+
+
+class BNReLUOp(Op):
+    """BatchNorm2d (train: batch statistics + running-stat update; eval: running stats) [+ ReLU]
+    (reference tactileSR_model.py:38-39, 42-43, 48-49, 169-170, 175-176, 181-182, 187-188).  ``bn`` may be a list of
+    BatchNorm2d modules that normalise consecutive channel slices of ``src`` (the two branches of an MSRB stage whose
+    outputs are concatenated, :200 / :203): statistics are finished per module, the elementwise passes run once over all
+    channels."""
+
+    def __init__(self, src: View, bn, out: View, relu: bool = True):
+        self.bns = list(bn) if isinstance(bn, (list, tuple)) else [bn]
+        self.bn = self.bns[0]
+        self.src, self.out, self.relu = src, out, relu
+        self.parts = []
+        off = 0
+        for m in self.bns:
+            if m.momentum is None or not m.affine:
+                raise _lib.TsrError("tactilesr_b200: BatchNorm2d with momentum=None (cumulative average) or affine=False is "
+                                    "not supported by the fused kernels")
+            self.parts.append((m, off, m.num_features))
+            off += m.num_features
+        assert src.C == off == out.C
+
+    def params(self):
+        return tuple(p for m in self.bns for p in (m.weight, m.bias))
+
+    def reads(self):
+        return (self.src.buf,)
+
+    def writes(self):
+        return (self.out.buf,)
+
+    def out_views(self):
+        return (self.out,)
+
+    def grad_targets(self):
+        return [(self.src, "other")]
+
+    def fwd(self, c):
+        folded = c.folded.get(self, ())
+        if len(folded) == len(self.parts):
+            return
+        assert not folded, "partially folded BatchNorm group"
         st = _lib.stream_ptr()
-        bn, C = self.bn, self.src.C
-        coef = torch.empty((4, C), dtype=torch.float32, device=c.device)
-        sc, sh, mu, iv = (coef[i].data_ptr() for i in range(4))
+        Ct = self.src.C
+        coef = torch.empty((4, Ct), dtype=torch.float32, device=c.device)
         yp, yld = c.vptr(self.src)
-        use_batch = c.training or bn.running_mean is None
-        part = c.bn_partials.pop(self, None)
-        if use_batch and c.training and bn.track_running_stats and bn.running_mean is not None:
-            global _STATS_EPOCH
-            _STATS_EPOCH += 1
-        if use_batch and part is not None:
+        table = c.bn_partials.pop(self, None)
+        covered = c.bn_partials_parts.pop(self, set())
+        used = []
+        for i, (bn, off, C) in enumerate(self.parts):
+            sc, sh, mu, iv = (coef[k].data_ptr() + off * 4 for k in range(4))
+            use_batch = c.training or bn.running_mean is None
+            used.append(use_batch)
             track = c.training and bn.track_running_stats and bn.running_mean is not None
-            mom = 0.1 if bn.momentum is None else bn.momentum
-            _lib.call("tsr_bn_finalize_partials", part.data_ptr(), part.shape[0], c.npix, C, bn.weight.data_ptr(),
-                      bn.bias.data_ptr(), _ptr(bn.running_mean) if track else 0, _ptr(bn.running_var) if track else 0,
-                      _ptr(bn.num_batches_tracked) if track else 0, mom, bn.eps, sc, sh, mu, iv, st)
-        elif use_batch:
-            ws, wsb = c.workspace(_lib.lib().tsr_bn_workspace(c.npix, C))
-            track = c.training and bn.track_running_stats and bn.running_mean is not None
-            mom = 0.1 if bn.momentum is None else bn.momentum
-            _lib.call("tsr_bn_train_stats", yp, yld, c.act, c.npix, C, bn.weight.data_ptr(), bn.bias.data_ptr(),
-                      _ptr(bn.running_mean) if track else 0, _ptr(bn.running_var) if track else 0,
-                      _ptr(bn.num_batches_tracked) if track else 0, mom, bn.eps, sc, sh, mu, iv, ws, wsb, st)
-        else:
-            _lib.call("tsr_bn_eval_coeffs", C, bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
-                      bn.running_var.data_ptr(), bn.eps, sc, sh, mu, iv, st)
+            if use_batch and track:
+                global _STATS_EPOCH
+                _STATS_EPOCH += 1
+            if use_batch and table is not None and i in covered:
+                _lib.call("tsr_bn_finalize_partials", table.data_ptr() + off * 4, table.shape[2], table.shape[0], c.npix, C,
+                          bn.weight.data_ptr(), bn.bias.data_ptr(), _ptr(bn.running_mean) if track else 0,
+                          _ptr(bn.running_var) if track else 0, _ptr(bn.num_batches_tracked) if track else 0, bn.momentum,
+                          bn.eps, sc, sh, mu, iv, st)
+            elif use_batch:
+                ws, wsb = c.workspace(_lib.lib().tsr_bn_workspace(c.npix, C))
+                _lib.call("tsr_bn_train_stats", yp + off * c.esize, yld, c.act, c.npix, C, bn.weight.data_ptr(),
+                          bn.bias.data_ptr(), _ptr(bn.running_mean) if track else 0, _ptr(bn.running_var) if track else 0,
+                          _ptr(bn.num_batches_tracked) if track else 0, bn.momentum, bn.eps, sc, sh, mu, iv, ws, wsb, st)
+            else:
+                _lib.call("tsr_bn_eval_coeffs", C, bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                          bn.running_var.data_ptr(), bn.eps, sc, sh, mu, iv, st)
         op, old = c.vptr(self.out)
         o2, o2ld = c.sptr(self.out) if c.wants_shadow(self.out.buf) else (0, 0)
-        _lib.call("tsr_bn_apply", yp, yld, c.act, sc, sh, op, old, c.act, c.npix, C, 1 if self.relu else 0, o2, o2ld, st)
-        c.saved[self] = (coef, use_batch)
+        _lib.call("tsr_bn_apply", yp, yld, c.act, coef[0].data_ptr(), coef[1].data_ptr(), op, old, c.act, c.npix, Ct,
+                  1 if self.relu else 0, o2, o2ld, st)
+        c.saved[self] = (coef, used)
 
     def bwd(self, c):
         st = _lib.stream_ptr()
-        C = self.src.C
-        coef, use_batch = c.saved[self]
-        sc, sh, mu, iv = (coef[i].data_ptr() for i in range(4))
+        Ct = self.src.C
+        coef, used = c.saved[self]
         gp, gld = c.vptr(self.out, grad=True)
         yp, yld = c.vptr(self.src)
         first = _first_write(c, self.src.buf)
         assert first, "BN input has a single consumer"
         dp, dld = c.vptr(self.src, grad=True)
-        gw, accw = c.pgrad(self.bn.weight)
-        gb, accb = c.pgrad(self.bn.bias)
-        assert accw == accb
-        ws, wsb = c.workspace(_lib.lib().tsr_bn_backward_workspace(c.npix, C))
-        _lib.call("tsr_bn_backward", gp, gld, yp, yld, dp, dld, c.mix, sc, sh, mu, iv, gw.data_ptr(), gb.data_ptr(),
-                  accw, c.npix, C, 1 if self.relu else 0, 1 if use_batch else 0, ws, wsb, st)
+        table = c.bnb.pop(self, None)
+        if table is not None:
+            # level 1 (masked g, sum g, sum g*y) came out of the epilogue of the data gradient that produced `gp`
+            c12 = torch.empty((2, Ct), dtype=torch.float32, device=c.device)
+            for i, (bn, off, C) in enumerate(self.parts):
+                gw, accw = c.pgrad(bn.weight)
+                gb, accb = c.pgrad(bn.bias)
+                assert accw == accb
+                _lib.call("tsr_bn_bwd_finalize_partials", table.data_ptr() + off * 4, table.shape[2], table.shape[0], c.npix, C,
+                          coef[2].data_ptr() + off * 4, coef[3].data_ptr() + off * 4, gw.data_ptr(), gb.data_ptr(), accw,
+                          c12[0].data_ptr() + off * 4, c12[1].data_ptr() + off * 4, 1 if used[i] else 0, st)
+            _lib.call("tsr_bn_backward_apply", gp, gld, yp, yld, dp, dld, c.mix, coef[0].data_ptr(), coef[1].data_ptr(),
+                      coef[2].data_ptr(), coef[3].data_ptr(), c12[0].data_ptr(), c12[1].data_ptr(), c.npix, Ct, 0, st)
+            return
+        for i, (bn, off, C) in enumerate(self.parts):
+            sc, sh, mu, iv = (coef[k].data_ptr() + off * 4 for k in range(4))
+            gw, accw = c.pgrad(bn.weight)
+            gb, accb = c.pgrad(bn.bias)
+            assert accw == accb
+            ws, wsb = c.workspace(_lib.lib().tsr_bn_backward_workspace(c.npix, C))
+            gsz = 4 if c.grd == 0 else 2
+            _lib.call("tsr_bn_backward", gp + off * gsz, gld, yp + off * c.esize, yld, dp + off * gsz, dld, c.mix, sc, sh, mu, iv,
+                      gw.data_ptr(), gb.data_ptr(), accw, c.npix, C, 1 if self.relu else 0, 1 if used[i] else 0, ws, wsb, st)
 
 
 class TailOp(Op):
@@ -547,6 +825,9 @@ class TailOp(Op):
 
     def writes(self):
         return (self.out,)
+
+    def grad_targets(self):
+        return [(self.src, "other")]
 
     def fwd(self, c):
         ip, ild = c.vptr(self.src)
@@ -578,6 +859,9 @@ class InputOp(Op):
     def writes(self):
         return (self.out,)
 
+    def out_views(self):
+        return (View.of(self.out),)
+
     def fwd(self, c):
         x = c.x
         t = c.alloc(self.out)
@@ -601,10 +885,40 @@ class Program:
     wants_input_grad: bool = False
     in_buf: Optional[Buf] = None
     taps: Dict[str, View] = field(default_factory=dict)
+    _planned: bool = False
 
     def add(self, op: Op) -> Op:
         self.ops.append(op)
         return op
+
+    def plan(self) -> None:
+        """Static analysis of the gradient flow, once per program: for every buffer, the LAST op (in backward order) that
+        writes its gradient.  If that is a tensor-core data gradient over the whole buffer it gets the buffer's Sink (ReLU
+        mask or BatchNorm-backward level 1 fused into its epilogue), and a residual hand-over whose only successor is such
+        a data gradient is done by reference instead of a copy."""
+        if self._planned:
+            return
+        self._planned = True
+        producers: Dict[Buf, list] = {}
+        writers: Dict[Buf, list] = {}
+        for i, op in enumerate(self.ops):
+            for v in op.out_views():
+                producers.setdefault(v.buf, []).append((op, v))
+            for v, kind in op.grad_targets():
+                writers.setdefault(v.buf, []).append((i, op, v, kind))
+        for buf, ws in writers.items():
+            ws.sort(key=lambda t: t[0])                    # backward runs from the highest index down: ws[0] is the last writer
+            i, op, v, kind = ws[0]
+            whole = v.c0 == 0 and v.C == buf.C
+            if kind == "conv" and whole:
+                prods = producers.get(buf, [])
+                if len(prods) == 1 and isinstance(prods[0][0], BNReLUOp) and prods[0][1].c0 == 0 and prods[0][1].C == buf.C:
+                    op.sink = Sink("bn", prods[0][0])
+                elif (prods and all(isinstance(p, (ConvOp, HeadOp)) and p.relu for p, _ in prods)
+                      and sum(pv.C for _, pv in prods) == buf.C):
+                    op.sink = Sink("relu")
+            if len(ws) == 2 and ws[1][3] == "res" and kind == "conv" and ws[1][2].c0 == v.c0 and ws[1][2].C == v.C:
+                ws[1][1].alias_residual_grad = True
 
     def parameters(self) -> List[torch.nn.Parameter]:
         seen, out = set(), []
@@ -633,16 +947,23 @@ def run_forward(prog: Program, x: torch.Tensor, training: bool, need_grad: bool,
         H, W = x.shape[-2], x.shape[-1]
     c = RunCtx(mode, B, H, W, x.device, training, need_grad)
     c.x = x
-    c.conv_inputs = {op.src.buf for op in prog.ops if isinstance(op, ConvOp)}
+    prog.plan()
+    c.conv_inputs = {op.src.buf for op in prog.ops if isinstance(op, (ConvOp, DualConvOp))}
     c.keep_taps = keep_taps
     if c.tc and (training or need_grad):
-        seen, ws = set(), []
+        seen, items = set(), []
         for op in prog.ops:
-            if isinstance(op, ConvOp) and id(op.conv.weight) not in seen and op.conv.weight.is_contiguous():
+            if isinstance(op, DualConvOp):
+                wa, wb = op.a.conv.weight, op.b.conv.weight
+                if id(wa) in seen or id(wb) in seen or not (wa.is_contiguous() and wb.is_contiguous()):
+                    continue
+                seen.update((id(wa), id(wb)))
+                items += [(wa, 1), (wb, 2)] if op.dual_ok else [(wa, 0), (wb, 0)]
+            elif isinstance(op, ConvOp) and id(op.conv.weight) not in seen and op.conv.weight.is_contiguous():
                 seen.add(id(op.conv.weight))
-                ws.append(op.conv.weight)
-        if ws:
-            _PACK.prepack(ws, mode, need_grad)
+                items.append((op.conv.weight, 0))
+        if items:
+            _PACK.prepack(items, mode, need_grad)
     keep = need_grad or keep_taps
     last_use: Dict[Buf, int] = {}
     if not keep:

@@ -63,15 +63,16 @@ class MSRB(_ProgramModule):
         _kaiming_and_bn_init(self)
 
     def _emit(self, prog: E.Program, x: E.View, out: E.View, tag: str) -> None:
+        # each stage = the 3x3 and the 5x5 branch of one input, their pre-normalisation outputs side by side in one buffer
+        # (y1 / y2), ONE BatchNorm+ReLU op over both branches writing the concatenated activation (i2 / i3 = torch.cat of
+        # reference :200 / :203)
         n = self.confusion.out_channels
-        i2 = E.Buf(tag + ".i2", 2 * n)
-        i3 = E.Buf(tag + ".i3", 4 * n)
-        for seq, src, dst in ((self.conv_3_1, x, E.View(i2, 0, n)), (self.conv_5_1, x, E.View(i2, n, n)),
-                              (self.conv_3_2, E.View.of(i2), E.View(i3, 0, 2 * n)),
-                              (self.conv_5_2, E.View.of(i2), E.View(i3, 2 * n, 2 * n))):
-            y = E.Buf(f"{tag}.y{dst.c0}_{dst.C}_{seq[0].kernel_size[0]}", dst.C)
-            cv = prog.add(E.ConvOp(src, seq[0], E.View.of(y)))
-            cv.bn_consumer = prog.add(E.BNReLUOp(E.View.of(y), seq[1], dst, relu=True))
+        y1, i2 = E.Buf(tag + ".y1", 2 * n), E.Buf(tag + ".i2", 2 * n)
+        y2, i3 = E.Buf(tag + ".y2", 4 * n), E.Buf(tag + ".i3", 4 * n)
+        d1 = prog.add(E.DualConvOp(x, self.conv_3_1[0], self.conv_5_1[0], E.View.of(y1)))
+        d1.feed(prog.add(E.BNReLUOp(E.View.of(y1), [self.conv_3_1[1], self.conv_5_1[1]], E.View.of(i2), relu=True)))
+        d2 = prog.add(E.DualConvOp(E.View.of(i2), self.conv_3_2[0], self.conv_5_2[0], E.View.of(y2)))
+        d2.feed(prog.add(E.BNReLUOp(E.View.of(y2), [self.conv_3_2[1], self.conv_5_2[1]], E.View.of(i3), relu=True)))
         prog.add(E.ConvOp(E.View.of(i3), self.confusion, out, relu=True, residual=x))
 
     def forward(self, x):

@@ -103,8 +103,102 @@ def test_metric_storage_window_and_average():
     m = MetricStorage(window_size=3)
     for i, v in enumerate([1.0, 2.0, 3.0, 4.0]):
         m.update(i, total_loss=v)
-    assert m.values_maybe_smooth["total_loss"] == (3.0, 3)
-    assert m.global_avg("total_loss") == 2.5 and m.latest("total_loss") == 4.0
+    assert m.values_maybe_smooth["total_loss"] == (3, 3.0)      # (latest iteration, value): the reference order
+    # records are HistoryBuffer-like (reference cpu/history_buffer.py): what LoggerHook / EvalHook read
+    assert m["total_loss"].global_avg == 2.5 and m["total_loss"].latest == 4.0 and m["total_loss"].avg == 3.0
+    assert m["total_loss"].global_sum == 10.0
+    m.update(7, lr=0.5, smooth=False)
+    assert m.values_maybe_smooth["lr"] == (7, 0.5)
+    with pytest.raises(AssertionError):
+        m.update(7, lr=0.4, smooth=False)                        # iterations must increase, as in the reference
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/cpu/history_buffer.py"), reason="reference tree not mounted")
+def test_metric_storage_matches_reference_history_buffer():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_history_buffer", "/root/reference/cpu/history_buffer.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    from tactilesr_b200.cpu.trainer import HistoryBuffer
+    a, b = HistoryBuffer(5), ref.HistoryBuffer(5)
+    for v in [0.1, 0.5, 2.0, 3.0, -1.0, 4.0, 0.25]:
+        a.update(v); b.update(v)
+        assert (a.latest, a.avg, a.global_avg, a.global_sum) == (b.latest, float(b.avg), b.global_avg, b.global_sum)
+
+
+class _TinyModel(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.ones(3))
+
+    def forward(self, batch):
+        return ((self.w * batch[0]).sum() - 1.0) ** 2
+
+
+def _tiny_trainer(tmp_path, max_epochs=3, **kw):
+    from tactilesr_b200.cpu.trainer import Trainer
+    torch.manual_seed(0)
+    data = [(torch.rand(3),) for _ in range(4)]
+    model = _TinyModel()
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    sched = torch.optim.lr_scheduler.StepLR(opt, 1, 0.9)
+    return Trainer(model, opt, sched, data, max_epochs=max_epochs, work_dir=str(tmp_path), log_period=2, **kw)
+
+
+def test_train_writes_checkpoints_logs_and_resumes(tmp_path):
+    """Default hooks as in the reference (cpu/trainer.py:194-200): checkpoints every ``checkpoint_period`` epochs with
+    pruning, latest.pth resumes (iteration counter, optimizer, scheduler, metric storage)."""
+    from tactilesr_b200.cpu.trainer import CheckpointHook, DistributedHook, LoggerHook
+    tr = _tiny_trainer(tmp_path, max_epochs=3, checkpoint_period=1, max_num_checkpoints=2)
+    names = [type(h).__name__ for h in tr._hooks]
+    assert {"_LRUpdateHook", "DistributedHook", "CheckpointHook", "LoggerHook"} <= set(names) and names[-1] == "LoggerHook"
+    tr.train(auto_resume=False)
+    ck = sorted(os.listdir(tr.ckpt_dir))
+    assert ck == ["epoch_1.pth", "epoch_2.pth", "latest.pth"], ck          # epoch_0 pruned (max_num_checkpoints = 2)
+    assert tr.metric_storage["total_loss"].latest >= 0.0
+    w_end = tr.model.w.detach().clone()
+    tr2 = _tiny_trainer(tmp_path, max_epochs=5, checkpoint_period=1, max_num_checkpoints=2)
+    tr2.load_checkpoint(auto_resume=True)
+    assert tr2.start_iter == 3 * 4 and torch.equal(tr2.model.w.detach(), w_end)
+    assert "total_loss" in tr2.metric_storage and tr2.metric_storage["total_loss"].latest == tr.metric_storage["total_loss"].latest
+    tr2.metric_storage.update(tr2.start_iter, total_loss=0.0)              # a resumed storage keeps working
+    tr2.train()
+    assert tr2.cur_iter == 5 * 4 - 1
+
+
+def test_foreign_hooks_are_accepted(tmp_path):
+    """A hook that does not derive from our HookBase (the reference's EvalHook does not) only needs the six stage methods."""
+    calls = []
+
+    class Foreign:
+        priority = 1
+
+        def __getattr__(self, name):
+            if name in ("before_train", "after_train", "before_epoch", "after_epoch", "before_iter", "after_iter"):
+                return lambda: calls.append(name)
+            raise AttributeError(name)
+
+    tr = _tiny_trainer(tmp_path, max_epochs=1)
+    tr.register_hooks([Foreign()])
+    assert type(tr._hooks[0]).__name__ == "Foreign"                         # priority 1 sorts first
+    tr.train(auto_resume=False)
+    assert calls.count("after_iter") == 4 and calls[0] == "before_train" and calls[-1] == "after_train"
+
+
+def test_distributed_hook_sets_sampler_epoch(tmp_path):
+    from torch.utils.data import DataLoader, DistributedSampler, TensorDataset
+    from tactilesr_b200.cpu.trainer import Trainer
+    ds = TensorDataset(torch.rand(8, 3))
+    sampler = DistributedSampler(ds, num_replicas=2, rank=0, shuffle=True)
+    dl = DataLoader(ds, batch_size=2, sampler=sampler)
+    model = _TinyModel()
+    opt = torch.optim.SGD(model.parameters(), lr=0.01)
+    tr = Trainer(model, opt, torch.optim.lr_scheduler.StepLR(opt, 1, 0.9), dl, max_epochs=3, work_dir=str(tmp_path))
+    seen = []
+    orig = sampler.set_epoch
+    sampler.set_epoch = lambda e: (seen.append(e), orig(e))
+    tr.train(auto_resume=False)
+    assert seen == [0, 1, 2]
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/cpu/lr_scheduler.py"), reason="reference tree not mounted")

@@ -291,7 +291,7 @@ def test_tc_conv_fused_bn_statistics(Cout, KS, B, f16):
     gamma = torch.full((Cout,), 0.1, device=dev); beta = torch.full((Cout,), 0.1, device=dev)
     rm = torch.zeros(Cout, device=dev); rv = torch.ones(Cout, device=dev); nbt = torch.zeros((), dtype=torch.int64, device=dev)
     coef = torch.empty(4, Cout, device=dev)
-    _lib.call("tsr_bn_finalize_partials", part.data_ptr(), rows, n, Cout, gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(),
+    _lib.call("tsr_bn_finalize_partials", part.data_ptr(), Cout, rows, n, Cout, gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(),
               rv.data_ptr(), nbt.data_ptr(), 0.1, 1e-5, coef[0].data_ptr(), coef[1].data_ptr(), coef[2].data_ptr(),
               coef[3].data_ptr(), st)
     mean, var = y.mean(0), y.var(0, unbiased=False)
