@@ -35,6 +35,9 @@ typedef struct CUstream_st* tsr_stream_t; /* == cudaStream_t */
 const char* tsr_last_error(void);
 int tsr_version(void);
 int tsr_check_device(void);               /* 0 iff the current device is compute capability 10.x */
+/* "fp16" precision mode guard: a caller-owned device int that kernels storing fp16 activations set to 1 when a stored value is
+   not finite (|x| > 65504 or NaN); NULL switches the check off.  Read it at logging cadence, not per step. */
+void tsr_set_f16_overflow_flag(int* flag_dev);
 long long tsr_launch_count(void);         /* kernels launched by this library since the last reset */
 void tsr_launch_count_reset(void);
 
@@ -263,6 +266,9 @@ typedef struct TsrConvTc2 {
 } TsrConvTc2;
 int tsr_conv2d_tc2(const void* args /* const TsrConvTc2*, host memory */, tsr_stream_t stream);
 int tsr_conv2d_tc2_stat_rows(void);
+/* diagnostics: 8 device counters filled by CTA 0 of the following tsr_conv2d_tc2 launches with the cycles its warp roles
+   spent waiting (see csrc/conv_tc2.cu); NULL switches it off */
+void tsr_conv2d_tc2_debug(unsigned long long* counters_dev);
 /* w3 (64, Cin, 3, 3), w5 (64, Cin, 5, 5) fp32 OIHW -> dual-branch forward image (dtype 1 = bf16, 2 = fp16) of
    tsr_pack_conv_weight_dual_elems(Cin) elements */
 size_t tsr_pack_conv_weight_dual_elems(int Cin);

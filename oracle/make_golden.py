@@ -116,6 +116,91 @@ def golden_sr_fwdbwd():
         np.savez_compressed(os.path.join(OUT, f"tactilesr_fwdbwd_s{S}.npz"), **rec)
 
 
+def _reference_step(m, LR, HR_raw, dtype):
+    """One train_cal_loss + backward of an already constructed reference module; returns out, loss, taps."""
+    LR, HR_raw = LR.to(dtype), HR_raw.to(dtype)
+    taps = {}
+    hooks = [m.inputContact_layer.register_forward_hook(lambda _m, _i, o: taps.__setitem__("inputContact", o.detach().clone()))]
+    for i, blk in enumerate(m.patternFeatureExtra_layer):
+        hooks.append(blk.register_forward_hook(lambda _m, _i, o, i=i: taps.__setitem__(f"msrb{i}", o.detach().clone())))
+    hooks.append(m.forceFeatureExtra_layer.register_forward_hook(lambda _m, _i, o: taps.__setitem__("force", o.detach().clone())))
+    hooks.append(m.output_layer[1].register_forward_hook(lambda _m, _i, o: taps.__setitem__("output0", o.detach().clone())))
+    HR = F.interpolate(HR_raw / 10, size=(40, 40), mode="bilinear", align_corners=False)
+    out = m(LR)
+    loss = nn.MSELoss()(out, HR)
+    loss.backward()
+    for h in hooks:
+        h.remove()
+    return out.detach(), loss.detach(), taps
+
+
+def _record_step(rec, tag, m, out, loss, taps):
+    rec[f"{tag}/out_summary"] = summarize(out)
+    rec[f"{tag}/out_nonzero"] = float((out > 0).double().mean())
+    rec[f"{tag}/loss"] = loss.double().numpy()
+    for k, v in taps.items():
+        rec[f"{tag}/tap/{k}"] = summarize(v)
+    rec["param_names"] = np.array([k for k, _ in m.named_parameters()])
+    rec[f"{tag}/grad_summary"] = np.stack([summarize(p.grad) for _, p in m.named_parameters()])
+    bn = {k: v for k, v in m.state_dict().items() if "running" in k}
+    rec["bn_names"] = np.array(list(bn.keys()))
+    rec[f"{tag}/bn_summary"] = np.stack([summarize(v) for v in bn.values()])
+
+
+def golden_sr_c1():
+    """BASELINE.json configs[0] (SURVEY 8d "C1") exactly: the reference's own construction at seed 42
+    (config/default.py:10), train mode, B = 32, LR = rand * 8, HR = rand * 250, one train_cal_loss + backward."""
+    from model.tactileSR_model import TactileSR
+    rec = {"B": 32, "seed_init": 42, "seed_x": 4242}
+    LR, HR_raw = sr_inputs(32, 1, rec["seed_x"])
+    for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        torch.manual_seed(42)
+        m = TactileSR().to(dtype).train()
+        out, loss, taps = _reference_step(m, LR, HR_raw, dtype)
+        _record_step(rec, tag, m, out, loss, taps)
+        rec[f"{tag}/out"] = out.float().numpy()
+    np.savez_compressed(os.path.join(OUT, "tactilesr_c1_b32.npz"), **rec)
+
+
+def golden_sr_b256():
+    """A batch that makes the persistent tensor-core kernels loop (B = 256: ~9 blocks per CTA pair): non-degenerate seeded
+    weights, one training step of the reference in fp64 (and fp32 as the yardstick)."""
+    from model.tactileSR_model import TactileSR
+    rec = {"B": 256, "S": 1, "seed_w": 13, "seed_x": 2256}
+    LR, HR_raw = sr_inputs(256, 1, rec["seed_x"])
+    for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        m = TactileSR()
+        m.load_state_dict(so.make_state(so.tactilesr_layout(1), rec["seed_w"]), strict=True)
+        m = m.to(dtype).train()
+        out, loss, taps = _reference_step(m, LR, HR_raw, dtype)
+        _record_step(rec, tag, m, out, loss, taps)
+        del m, out, taps
+    np.savez_compressed(os.path.join(OUT, "tactilesr_b256.npz"), **rec)
+
+
+def golden_srcnn_bwd():
+    """TactileSRCNN (model/tactileSR_model.py:101-153) forward + MSE + backward, train mode, fp32 and fp64."""
+    from model.tactileSR_model import TactileSRCNN
+    rec = {"B": 3, "seed_w": 33, "seed_x": 403}
+    sd = so.make_state(so.tactilesrcnn_layout(), rec["seed_w"])
+    LR, HR_raw = sr_inputs(3, 1, rec["seed_x"])
+    for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        m = TactileSRCNN()
+        m.load_state_dict(sd, strict=True)
+        m = m.to(dtype).train()
+        HR = F.interpolate(HR_raw.to(dtype) / 10, size=(40, 40), mode="bilinear", align_corners=False)
+        out = m(LR.to(dtype))
+        loss = nn.MSELoss()(out, HR)
+        loss.backward()
+        rec[f"{tag}/out"] = out.detach().double().numpy()
+        rec[f"{tag}/loss"] = loss.detach().double().numpy()
+        rec["param_names"] = np.array([k for k, _ in m.named_parameters()])
+        rec[f"{tag}/grad_summary"] = np.stack([summarize(p.grad) for _, p in m.named_parameters()])
+        rec[f"{tag}/grad_output_w"] = m.output[0].weight.grad.detach().double().numpy()
+        rec[f"{tag}/grad_in0_w"] = m.input_zyx[0].weight.grad.detach().double().numpy()
+    np.savez_compressed(os.path.join(OUT, "tactilesrcnn_bwd.npz"), **rec)
+
+
 def golden_sr_adam():
     """3 steps of fwd + MSE + bwd + stock Adam(lr 1e-3, wd 1e-2) (train/tactileSR_train.py:212)."""
     from model.tactileSR_model import TactileSR
@@ -231,6 +316,14 @@ if __name__ == "__main__":
     if "--eval-only" in sys.argv:
         golden_eval()
         sys.exit(0)
+    if "--round2" in sys.argv:          # the fixtures added in round 2 (the others are unchanged)
+        golden_srcnn_bwd()
+        print("srcnn bwd done")
+        golden_sr_c1()
+        print("c1 done")
+        golden_sr_b256()
+        print("b256 done")
+        sys.exit(0)
     golden_sr_init()
     print("init done")
     golden_tpsf()
@@ -241,6 +334,10 @@ if __name__ == "__main__":
     print("fwdbwd done")
     golden_sr_adam()
     print("adam done")
+    golden_srcnn_bwd()
+    golden_sr_c1()
+    golden_sr_b256()
+    print("round-2 fixtures done")
     golden_eval()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -80,7 +80,7 @@ def tpsf_forward(sd: Dict[str, Tensor], x: Tensor, depth: Tensor):
     dt = x.dtype
     ab = mlp(sd, x)                                                     # (B,3)
     alpha, beta, gamma = ab[:, 0], ab[:, 1], ab[:, 2]
-    sdf = psf_sdf(dt)
+    sdf = psf_sdf(dt).to(x.device)
     psf = alpha[:, None, None, None] * torch.exp(-sdf ** 2 / (beta ** 2)[:, None, None, None])   # :83
     # depth2tactile (:85-100)
     dmax = depth.flatten(1).max(dim=1).values
@@ -90,7 +90,7 @@ def tpsf_forward(sd: Dict[str, Tensor], x: Tensor, depth: Tensor):
     second_max = conv.detach().masked_fill(mask, 0).flatten(1).max(dim=1).values          # :95-97
     HR = torch.where(mask, second_max[:, None, None, None], conv)
     # degradation_process (:129-141)
-    msdf = masking_sdf(dt)
+    msdf = masking_sdf(dt).to(x.device)
     masking = torch.exp(-msdf[None] ** 2 / gamma[:, None, None, None, None])             # (B,4,4,100,100)
     mn = masking.flatten(1).min(dim=1).values[:, None, None, None, None]
     mx = masking.flatten(1).max(dim=1).values[:, None, None, None, None]

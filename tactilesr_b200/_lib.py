@@ -21,6 +21,7 @@ SIGNATURES = {
     "tsr_last_error": (c_char_p, []),
     "tsr_version": (_I, []),
     "tsr_check_device": (_I, []),
+    "tsr_set_f16_overflow_flag": (None, [_P]),
     "tsr_launch_count": (_L, []),
     "tsr_launch_count_reset": (None, []),
     # fp32 convolutions
@@ -81,6 +82,7 @@ SIGNATURES = {
     "tsr_conv2d_wgrad_tc_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),
     "tsr_conv2d_tc2": (_I, [_P, _P]),
     "tsr_conv2d_tc2_stat_rows": (_I, []),
+    "tsr_conv2d_tc2_debug": (None, [_P]),
     "tsr_pack_conv_weight_dual_elems": (_Z, [_I]),
     "tsr_pack_conv_weight_dual": (_I, [_P, _P, _P, _I, _I, _P]),
     "tsr_set_tc_desc_mode": (None, [_I]),

@@ -99,8 +99,14 @@ class GradAllReduce:
     dedicated stream ordered after the producing kernels by an event; ``finish()`` makes the compute stream wait
     for all outstanding buckets (call before ``optimizer.step``)."""
 
-    def __init__(self, flat: torch.Tensor, bucket_bytes: int = 8 << 20, group=None):
+    def __init__(self, flat: torch.Tensor, bucket_bytes: int = 8 << 20, group=None, overlap: Optional[bool] = None):
         self.flat, self.group = flat, group
+        # overlap = False: ONE all-reduce over the whole buffer after backward, on the compute stream (A/B switch; also
+        # TSR_DP_OVERLAP=0).  The overlapped form hides the transfer but its NCCL kernels share the SMs with the persistent
+        # one-CTA-per-SM convolution kernels of backward.
+        if overlap is None:
+            overlap = os.environ.get("TSR_DP_OVERLAP", "1") != "0"
+        self.overlap = overlap
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bucket_elems = max(bucket_bytes // 4, 1)
         self.pending: List[Tuple[int, int]] = []
@@ -111,7 +117,7 @@ class GradAllReduce:
         self.launched: List[Tuple[int, int]] = []
 
     def ready(self, lo: int, hi: int) -> None:
-        if self.world < 2 or hi <= lo:
+        if self.world < 2 or hi <= lo or not self.overlap:
             return
         self.pending.append((lo, hi))
         self.pending_elems += hi - lo
@@ -149,6 +155,12 @@ class GradAllReduce:
 
     def finish(self) -> None:
         if self.world < 2:
+            return
+        if not self.overlap:
+            nccl = dist.get_backend(self.group) == "nccl"
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM, group=self.group)
+            if not nccl:
+                self.flat /= self.world
             return
         self._flush()
         if self.cuda:

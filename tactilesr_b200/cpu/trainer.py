@@ -353,7 +353,8 @@ class Trainer:
         self._grad_bucket_bytes = grad_bucket_bytes
         # cuda_graph (extension; the reference has no such switch): after two ordinary iterations the whole iteration
         # (train_cal_loss + backward + optimizer step, ~450 kernel launches) is captured once per batch shape and
-        # replayed -- at the reference's batch size 32 the iteration is launch-bound, not GPU-bound.  Single GPU only.
+        # replayed -- at the reference's batch size 32 the iteration is launch-bound, not GPU-bound.  Under data parallelism
+        # the NCCL all-reduces are part of the captured graph.
         self._use_graph = cuda_graph
         self._graphs: Dict[tuple, tuple] = {}
         self._eager_iters = 0
@@ -416,6 +417,19 @@ class Trainer:
         if D.get_world_size() < 2 or self._dp is not None or not hasattr(self.optimizer, "flat_grad"):
             return
         flat = self.optimizer.flat_grad(0)
+        # as DistributedDataParallel does at construction: every rank starts from rank 0's parameters and buffers
+        # (BatchNorm running statistics stay rank-local afterwards: DDP semantics)
+        import torch.distributed as dist
+        with torch.no_grad():
+            for f in self.optimizer._flat.values():
+                if f:
+                    dist.broadcast(f["p"], 0)
+            flat_ids = {id(p) for f in self.optimizer._flat.values() if f for p in f["params"]}
+            for p in self.model_or_module.parameters():
+                if id(p) not in flat_ids:
+                    dist.broadcast(p.data, 0)
+            for b in self.model_or_module.buffers():
+                dist.broadcast(b, 0)
         dp = D.GradAllReduce(flat, self._grad_bucket_bytes)
         base = flat.data_ptr()
         end = base + flat.numel() * 4
@@ -467,7 +481,7 @@ class Trainer:
 
     # -- CUDA-graph replay of the iteration ---------------------------------------------------------------
     def _graph_eligible(self, batch) -> bool:
-        return (self._use_graph and self._eager_iters >= 2 and self._dp is None and D.get_world_size() == 1
+        return (self._use_graph and self._eager_iters >= 2 and (self._dp is not None or D.get_world_size() == 1)
                 and self._clip_grad_norm <= 0 and hasattr(self.optimizer, "enable_graph_mode")
                 and isinstance(batch, (tuple, list)) and all(torch.is_tensor(t) for t in batch))
 
@@ -485,10 +499,14 @@ class Trainer:
             opt.update_graph_hyper()
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
+            # data parallel: the bucketed NCCL all-reduces of backward (side stream, forked / joined by events) are captured
+            # with the iteration, so the replay keeps the overlap; every rank captures the same sequence
             with torch.cuda.graph(graph):
                 losses, loss_dict = self.train_cal_loss(tuple(static))
                 opt.zero_grad()
                 losses.backward()
+                if self._dp is not None:
+                    self._dp.finish()
                 opt.step()                   # (host side of this call advanced the step counters once)
             graph.replay()
             entry = (graph, static, loss_dict)
@@ -516,6 +534,9 @@ class Trainer:
         if D.get_world_size() > 1:
             mean = D.reduce_dict({"total_loss": mean})["total_loss"]
         value = float(mean.item())
+        if torch.cuda.is_available():
+            from ..engine import check_fp16_overflow      # sticky flag of the "fp16" mode, read at the same cadence
+            check_fp16_overflow()
         if not np.isfinite(value):
             raise FloatingPointError(f"Loss became infinite or NaN at iteration={self.cur_iter}!")
         if D.is_main_process():

@@ -15,6 +15,7 @@
 
 void tsr_set_error(const char* fmt, ...);
 extern "C" long long tsr_launch_count_inc(int n);   // internal: counts kernel launches
+int* tsr_f16_overflow_ptr();                        // internal: device flag of the fp16 overflow guard, or null
 
 #define TSR_REQUIRE(cond, ...)                                                   \
   do {                                                                           \

@@ -596,12 +596,16 @@ tail_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out_
   const int strips = (H + TAIL_TR - 1) / TAIL_TR;
   const int PW = W + 2, PH = TAIL_TR + 2;
   const int ngroups = Cin / 8;
-  for (int g = threadIdx.x & 15; g < ngroups; g += 16) {       // (one pass for Cin <= 128)
+  // Every thread runs every pass and strip (the staging loop and its barriers need the whole CTA); a thread whose channel
+  // group does not exist (Cin < 128: TactileSRCNN's 64 -> 1 tail) only skips the arithmetic and the store.
+  for (int g0 = 0; g0 < ngroups; g0 += 16) {                   // (one pass for Cin <= 128)
+    const int g = g0 + (threadIdx.x & 15);
+    const bool active = g < ngroups;
     float wr[9][8];                                            // loaded once: the CTA is persistent over strips
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) wr[t][j] = w[(g * 8 + j) * 9 + t];
+      for (int j = 0; j < 8; ++j) wr[t][j] = active ? w[(g * 8 + j) * 9 + t] : 0.f;
     for (int sidx = blockIdx.x; sidx < B * strips; sidx += gridDim.x) {
       const int b = sidx / strips, y0 = (sidx - b * strips) * TAIL_TR;
       __syncthreads();
@@ -618,7 +622,7 @@ tail_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out_
       __syncthreads();
       const int npx = min(TAIL_TR, H - y0) * W;
       int ty = (threadIdx.x >> 4) / W, x = (threadIdx.x >> 4) - ty * W;
-      for (int p = threadIdx.x >> 4; p < npx; p += 16) {
+      for (int p = threadIdx.x >> 4; active && p < npx; p += 16) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int t = 0; t < 9; ++t) {

@@ -61,6 +61,8 @@ struct P2 {
   int H, W, Hp, Vtotal, nxg, nblocks, ngroups;
   int na_slots, nb_stages;
   uint32_t a_slot_bytes;
+  int* ovf;                          // fp16 overflow guard: set to 1 when a stored fp16 value is not finite, else null
+  unsigned long long* dbg;           // diagnostics (tsr_conv2d_tc2_debug): cycles CTA 0's roles spend waiting, else null
 };
 
 __device__ __forceinline__ float transpose_reduce16_2(float (&p)[16], int lane) {
@@ -87,141 +89,146 @@ __device__ __forceinline__ void unpack16(const uint4 (&u)[2], bool f16, float (&
   }
 }
 
-// Epilogue of one block for the warp that owns TMEM lanes (acc >> 16)..+31 and accumulator columns col0..col0 + NACC/2:
-// both M-tiles, 16 columns at a time.  The residual / aux vectors of step i + 1 are requested before step i is processed
-// (and those of step 0 before the accumulator is awaited), so their latency overlaps the TMEM loads and the arithmetic.
-template <int NACC>
-__device__ __forceinline__ void epilogue2(const P2& p, uint32_t acc, int col0, const bool (&valid)[T2_TILES],
-                                          const long long (&pix)[T2_TILES], int stat_row, int lane, int nofs,
-                                          uint32_t bar, uint32_t parity) {
-  constexpr int NI = (NACC / 32) * T2_TILES;
+// Post-processing of 16 accumulator columns of one pixel: + bias, + residual, mask, ReLU, rounding, stores, statistics.
+__device__ __forceinline__ void epilogue_px(const P2& p, const uint32_t (&v)[16], const uint4 (&rc)[2], const uint4 (&ac)[2],
+                                            long long pm, int ch, float (&sv)[16], float (&sq)[16]) {
   const int flags = p.flags;
-  const bool f16 = (flags & F_F16) != 0, auxf16 = (flags & F_AUX_F16) != 0;
+  const bool f16 = (flags & F_F16) != 0;
+  float f[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
+  if (p.bias) {
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) {
+      const float4 bv = *reinterpret_cast<const float4*>(p.bias + ch + k);
+      f[k] += bv.x; f[k + 1] += bv.y; f[k + 2] += bv.z; f[k + 3] += bv.w;
+    }
+  }
+  if (p.residual) {
+    float r[16];
+    unpack16(rc, f16, r);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) f[k] += r[k];
+  }
+  float y[16];
+  if (p.aux) {
+    unpack16(ac, (flags & F_AUX_F16) != 0, y);
+    if (flags & F_MASK) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) f[k] = y[k] > 0.f ? f[k] : 0.f;
+    } else if (flags & F_BNB_RELU) {
+#pragma unroll
+      for (int k = 0; k < 16; k += 4) {
+        const float4 sc = *reinterpret_cast<const float4*>(p.aux_sc + ch + k);
+        const float4 sh = *reinterpret_cast<const float4*>(p.aux_sh + ch + k);
+        f[k] = fmaf(y[k], sc.x, sh.x) > 0.f ? f[k] : 0.f;
+        f[k + 1] = fmaf(y[k + 1], sc.y, sh.y) > 0.f ? f[k + 1] : 0.f;
+        f[k + 2] = fmaf(y[k + 2], sc.z, sh.z) > 0.f ? f[k + 2] : 0.f;
+        f[k + 3] = fmaf(y[k + 3], sc.w, sh.w) > 0.f ? f[k + 3] : 0.f;
+      }
+    }
+  }
+  if (flags & F_RELU) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
+  }
+  uint32_t o[8];
+  if (f16) {
+    if (p.ovf) {           // sticky overflow guard of the "fp16" mode (NaN-safe: !(NaN <= x))
+      float m = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) m = fmaxf(m, fabsf(f[k]));
+      bool bad = !(m <= 65504.f);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) bad |= (f[k] != f[k]);
+      if (bad) *p.ovf = 1;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+      o[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+      o[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  }
+  uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + pm * p.out_ld + ch);
+  op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  if (p.out2) {
+    uint32_t o2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+      o2[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    uint4* op2 = reinterpret_cast<uint4*>(p.out2 + pm * p.out2_ld + ch);
+    op2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+    op2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
+  }
+  if (p.stat) {
+    // statistics of the STORED (rounded) values: what every later pass over the tensor reads
+    const uint4 oc[2] = {make_uint4(o[0], o[1], o[2], o[3]), make_uint4(o[4], o[5], o[6], o[7])};
+    float fr[16];
+    unpack16(oc, f16, fr);
+    if (flags & F_BNB) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { sv[k] += fr[k]; sq[k] = fmaf(fr[k], y[k], sq[k]); }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { sv[k] += fr[k]; sq[k] = fmaf(fr[k], fr[k], sq[k]); }
+    }
+  }
+}
+
+// Epilogue of one block for the warp that owns TMEM lanes (acc >> 16)..+31 and accumulator columns col0..col0 + NACC/2:
+// 16 columns of both M-tiles per step (two TMEM loads in flight, one wait).  The residual / aux vectors of step j + 1 are
+// requested before step j is processed (and those of step 0 before the accumulator is awaited), so their latency overlaps
+// the TMEM loads and the arithmetic.  valid / pix are taken as scalars: a dynamically indexed array would live in local
+// memory and every use would wait on an LDL behind the store traffic (measured 2x on the epilogue-bound 1x1 data gradient).
+template <int NACC>
+__device__ __forceinline__ void epilogue2(const P2& p, uint32_t acc, int col0, bool v0, bool v1, long long p0, long long p1,
+                                          int stat_row, int lane, int nofs, uint32_t bar, uint32_t parity) {
+  constexpr int NJ = NACC / 32;
   const bool has_res = p.residual != nullptr, has_aux = p.aux != nullptr;
-  const bool bnb = (flags & F_BNB) != 0;
-  uint4 rn[2], an[2];
-  rn[0] = rn[1] = an[0] = an[1] = make_uint4(0u, 0u, 0u, 0u);
-  // (selects, not indexed loads: a dynamically indexed valid[] / pix[] lives in local memory and every use then waits on
-  // an LDL behind the store traffic -- measured 2x on the epilogue-bound 1x1 data gradient)
-  const bool v0 = valid[0], v1 = valid[1];
-  const long long p0 = pix[0], p1 = pix[1];
-  auto prefetch = [&](int i) {
-    const int ch = nofs + col0 + (i >> 1) * 16;
-    const bool vm = (i & 1) ? v1 : v0;
-    const long long pm = (i & 1) ? p1 : p0;
-    if (vm) {
-      if (has_res) {
-        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + pm * p.res_ld + ch);
-        rn[0] = rp[0]; rn[1] = rp[1];
-      }
-      if (has_aux) {
-        const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.aux) + pm * p.aux_ld + ch);
-        an[0] = ap[0]; an[1] = ap[1];
-      }
+  uint4 r0[2], r1[2], a0[2], a1[2];
+  r0[0] = r0[1] = r1[0] = r1[1] = a0[0] = a0[1] = a1[0] = a1[1] = make_uint4(0u, 0u, 0u, 0u);
+  // request the residual / aux vectors of pixel pm, columns ch.. (consumed one step later)
+  auto prefetch = [&](bool vm, long long pm, int ch, uint4 (&r)[2], uint4 (&a)[2]) {
+    if (!vm) return;
+    if (has_res) {
+      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + pm * p.res_ld + ch);
+      r[0] = rp[0]; r[1] = rp[1];
+    }
+    if (has_aux) {
+      const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.aux) + pm * p.aux_ld + ch);
+      a[0] = ap[0]; a[1] = ap[1];
     }
   };
-  prefetch(0);
+  prefetch(v0, p0, nofs + col0, r0, a0);
+  prefetch(v1, p1, nofs + col0, r1, a1);
   mbar_wait(bar, parity);
   tc_fence_after();
-  float sv[16], sq[16];
 #pragma unroll 1
-  for (int i = 0; i < NI; ++i) {
-    const int mt = i & 1, j = i >> 1;
+  for (int j = 0; j < NJ; ++j) {
     const int ch = nofs + col0 + j * 16;
-    const bool vm = mt ? v1 : v0;
-    const long long pm = mt ? p1 : p0;
-    const uint4 rc[2] = {rn[0], rn[1]}, ac[2] = {an[0], an[1]};
-    if (i + 1 < NI) prefetch(i + 1);
-    if (mt == 0) {
+    uint32_t va[16], vb[16];
+    tmem_ld16(acc + col0 + j * 16, va);
+    tmem_ld16(acc + NACC + col0 + j * 16, vb);
+    float sv[16], sq[16];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) { sv[k] = 0.f; sq[k] = 0.f; }
-    }
-    uint32_t v[16];
-    tmem_ld16(acc + mt * NACC + col0 + j * 16, v);
+    for (int k = 0; k < 16; ++k) { sv[k] = 0.f; sq[k] = 0.f; }
     tmem_ld_wait();
-    if (vm) {
-      float f[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
-      if (p.bias) {
-#pragma unroll
-        for (int k = 0; k < 16; k += 4) {
-          const float4 bv = *reinterpret_cast<const float4*>(p.bias + ch + k);
-          f[k] += bv.x; f[k + 1] += bv.y; f[k + 2] += bv.z; f[k + 3] += bv.w;
-        }
-      }
-      if (has_res) {
-        float r[16];
-        unpack16(rc, f16, r);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) f[k] += r[k];
-      }
-      float y[16];
-      if (has_aux) {
-        unpack16(ac, auxf16, y);
-        if (flags & F_MASK) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) f[k] = y[k] > 0.f ? f[k] : 0.f;
-        } else if (flags & F_BNB_RELU) {
-#pragma unroll
-          for (int k = 0; k < 16; k += 4) {
-            const float4 sc = *reinterpret_cast<const float4*>(p.aux_sc + ch + k);
-            const float4 sh = *reinterpret_cast<const float4*>(p.aux_sh + ch + k);
-            f[k] = fmaf(y[k], sc.x, sh.x) > 0.f ? f[k] : 0.f;
-            f[k + 1] = fmaf(y[k + 1], sc.y, sh.y) > 0.f ? f[k + 1] : 0.f;
-            f[k + 2] = fmaf(y[k + 2], sc.z, sh.z) > 0.f ? f[k + 2] : 0.f;
-            f[k + 3] = fmaf(y[k + 3], sc.w, sh.w) > 0.f ? f[k + 3] : 0.f;
-          }
-        }
-      }
-      if (flags & F_RELU) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
-      }
-      uint32_t o[8];
-      float fr[16];                       // the stored (rounded) values: what every later pass over the tensor reads
-      if (f16) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
-          o[k] = *reinterpret_cast<const uint32_t*>(&h);
-          const float2 t = __half22float2(h);
-          fr[2 * k] = t.x; fr[2 * k + 1] = t.y;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-          o[k] = *reinterpret_cast<const uint32_t*>(&h);
-          const float2 t = __bfloat1622float2(h);
-          fr[2 * k] = t.x; fr[2 * k + 1] = t.y;
-        }
-      }
-      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + pm * p.out_ld + ch);
-      op[0] = make_uint4(o[0], o[1], o[2], o[3]);
-      op[1] = make_uint4(o[4], o[5], o[6], o[7]);
-      if (p.out2) {
-        uint32_t o2[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-          o2[k] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        uint4* op2 = reinterpret_cast<uint4*>(p.out2 + pm * p.out2_ld + ch);
-        op2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
-        op2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
-      }
-      if (p.stat) {
-        if (bnb) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) { sv[k] += fr[k]; sq[k] = fmaf(fr[k], y[k], sq[k]); }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) { sv[k] += fr[k]; sq[k] = fmaf(fr[k], fr[k], sq[k]); }
-        }
-      }
-    }
-    if (mt == T2_TILES - 1 && p.stat) {      // warp-uniform: all 32 lanes take part in the shuffles
+    // pixel 0 consumes its prefetched vectors, then their registers take the next step's request, which has the whole of
+    // pixel 1's processing (and the next TMEM loads) to arrive; likewise for pixel 1
+    if (v0) epilogue_px(p, va, r0, a0, p0, ch, sv, sq);
+    if (j + 1 < NJ) prefetch(v0, p0, ch + 16, r0, a0);
+    if (v1) epilogue_px(p, vb, r1, a1, p1, ch, sv, sq);
+    if (j + 1 < NJ) prefetch(v1, p1, ch + 16, r1, a1);
+    if (p.stat) {      // warp-uniform: all 32 lanes take part in the shuffles
       const float s = transpose_reduce16_2(sv, lane), ss = transpose_reduce16_2(sq, lane);
       if ((lane & 1) == 0) {
         // every (row, channel) address has exactly one writer lane of one warp, in program order => deterministic
@@ -233,7 +240,11 @@ __device__ __forceinline__ void epilogue2(const P2& p, uint32_t acc, int col0, c
   }
 }
 
-template <int NACC>
+// TAB: per-tap table (window offset, N variant, weight map) -- the dual-branch forward; otherwise taps are walked
+// incrementally with one N.  DBG: wait-cycle counters (tsr_conv2d_tc2_debug).  The issue loop of the single MMA thread is the
+// critical path of every shape with a real main loop (measured: it, not the tensor pipe, was ~77 % busy), so ring positions
+// are running counters (no division), addresses advance by adds, and everything optional is compiled out.
+template <int NACC, bool TAB, bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUtensorMap amap1,
                 const __grid_constant__ CUtensorMap wmap0, const __grid_constant__ CUtensorMap wmap1, const P2 p) {
@@ -245,10 +256,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant
   const uint32_t b_base = a_base + NA * a_slot_bytes;
   constexpr uint32_t B_HALF = (NACC / 2) * 128u;     // this CTA's share of the widest weight tile
   const uint32_t bar_base = b_base + NB * B_HALF;
-  auto a_full = [&](int i) { return bar_base + 8u * i; };
-  auto a_empty = [&](int i) { return bar_base + 8u * (T2_MAX_NA + i); };
-  auto b_full = [&](int i) { return bar_base + 8u * (2 * T2_MAX_NA + i); };
-  auto b_empty = [&](int i) { return bar_base + 8u * (2 * T2_MAX_NA + T2_MAX_NB + i); };
+  const uint32_t a_full0 = bar_base, a_empty0 = bar_base + 8u * T2_MAX_NA;
+  const uint32_t b_full0 = bar_base + 8u * (2 * T2_MAX_NA), b_empty0 = bar_base + 8u * (2 * T2_MAX_NA + T2_MAX_NB);
   auto t_full = [&](int i) { return bar_base + 8u * (2 * T2_MAX_NA + 2 * T2_MAX_NB + i); };
   auto t_empty = [&](int i) { return bar_base + 8u * (2 * T2_MAX_NA + 2 * T2_MAX_NB + 2 + i); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * T2_MAX_NA + 2 * T2_MAX_NB + 4);
@@ -263,10 +272,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant
   const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
   const int npb_pix = (p.nblocks + 1) >> 1;
   const int npb = npb_pix * p.ngroups;
+  const bool dbg = DBG && p.dbg != nullptr && blockIdx.x == 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(a_full(i), 2); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < NB; ++i) { mbar_init(b_full(i), 2); mbar_init(b_empty(i), 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(a_full0 + 8u * i, 2); mbar_init(a_empty0 + 8u * i, 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(b_full0 + 8u * i, 2); mbar_init(b_empty0 + 8u * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 16); }
     fence_barrier_init();
   }
@@ -281,7 +291,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant
 
   if (warp == 0) {
     // ===== A producer (both CTAs): the halo rows of the CTA's own block, completing on the leader's a_full =====
-    int ac = 0;
+    uint32_t slot = 0, ph = 1;            // parity a fresh "empty" barrier is waited with
+    long long dbg_w0 = 0;
     for (int pb = pair; pb < npb; pb += npairs) {
       const int blk = 2 * (pb % npb_pix) + (int)rank;   // may be == nblocks for the last odd block: all rows out of range
       const int xg = blk % p.nxg, vb = blk / p.nxg;
@@ -289,11 +300,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant
       for (int s = 0; s < p.nseg; ++s) {
         const Seg& sg = p.seg[s];
         const CUtensorMap* am = sg.amap ? &amap1 : &amap0;
-        for (int c = 0; c < sg.nchunks; ++c, ++ac) {
-          const int slot = ac % NA;
+        for (int c = 0; c < sg.nchunks; ++c) {
           const uint32_t dst0 = a_base + slot * a_slot_bytes;
-          const uint32_t full_leader = a_full(slot) & PEER_MASK;
-          if (lane == 0) mbar_wait(a_empty(slot), ((ac / NA) & 1) ^ 1);
+          const uint32_t full_leader = (a_full0 + 8u * slot) & PEER_MASK;
+          if (lane == 0) {
+            const long long t0 = dbg ? clock64() : 0;
+            mbar_wait(a_empty0 + 8u * slot, ph);
+            if (dbg) dbg_w0 += clock64() - t0;
+          }
           __syncwarp();
           if (sg.pad == 0) {
             if (lane == 0) tma_load_4d_2sm(dst0, am, c * 64, x0, v0, 0, full_leader);
@@ -307,35 +321,48 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant
           }
           __syncwarp();
           if (lane == 0) {
-            if (leader) mbar_expect_tx(a_full(slot), 2u * sg.row_bytes * sg.rows);
+            if (leader) mbar_expect_tx(a_full0 + 8u * slot, 2u * sg.row_bytes * sg.rows);
             else mbar_arrive_cluster(full_leader);
           }
+          if (++slot == (uint32_t)NA) { slot = 0; ph ^= 1u; }
         }
       }
     }
+    if (dbg && lane == 0) p.dbg[0] = (unsigned long long)dbg_w0;
   } else if (warp == 2) {
     // ===== B producer (both CTAs): this CTA's half of the rows of each weight tile =====
     if (lane == 0) {
-      int it = 0;
+      uint32_t st = 0, ph = 1;
+      long long dbg_w2 = 0;
       for (int pb = pair; pb < npb; pb += npairs) {
         const int g = pb / npb_pix;
         for (int s = 0; s < p.nseg; ++s) {
           const Seg& sg = p.seg[s];
-          for (int c = 0; c < sg.nchunks; ++c) {
-            for (int t = 0; t < sg.ntaps; ++t, ++it) {
-              const uint32_t e = p.tap[s][t];
-              const int rows_half = (e >> 13) & 1 ? NACC / 4 : NACC / 2;
-              const int row = c * sg.chunk_wrows + p.wrow[s][t] + g * NACC + (int)rank * rows_half;
-              const int st = it % NB;
-              const uint32_t full_leader = b_full(st) & PEER_MASK;
-              mbar_wait(b_empty(st), ((it / NB) & 1) ^ 1);
-              tma_load_2d_2sm(b_base + st * B_HALF, (e >> 12) & 1 ? &wmap1 : &wmap0, 0, row, full_leader);
-              if (leader) mbar_expect_tx(b_full(st), 2u * rows_half * 128u);
+          const CUtensorMap* wm = s ? &wmap1 : &wmap0;
+          int row_c = g * NACC + (TAB ? 0 : (int)rank * (NACC / 2));
+          for (int c = 0; c < sg.nchunks; ++c, row_c += sg.chunk_wrows) {
+            for (int t = 0; t < sg.ntaps; ++t) {
+              int rows_half = NACC / 2, row = row_c + p.wrow[s][t];
+              const CUtensorMap* wmt = wm;
+              if (TAB) {
+                const uint32_t e = p.tap[s][t];
+                rows_half = (e >> 13) & 1 ? NACC / 4 : NACC / 2;
+                row += (int)rank * rows_half;
+                wmt = (e >> 12) & 1 ? &wmap1 : &wmap0;
+              }
+              const uint32_t full_leader = (b_full0 + 8u * st) & PEER_MASK;
+              const long long t0 = dbg ? clock64() : 0;
+              mbar_wait(b_empty0 + 8u * st, ph);
+              if (dbg) dbg_w2 += clock64() - t0;
+              tma_load_2d_2sm(b_base + st * B_HALF, wmt, 0, row, full_leader);
+              if (leader) mbar_expect_tx(b_full0 + 8u * st, 2u * rows_half * 128u);
               else mbar_arrive_cluster(full_leader);
+              if (++st == (uint32_t)NB) { st = 0; ph ^= 1u; }
             }
           }
         }
       }
+      if (dbg) p.dbg[1] = (unsigned long long)dbg_w2;
     }
   } else if (warp == 1) {
     // ===== MMA issuer: leader CTA only; the warp runs the loop converged, one elected lane issues =====
@@ -344,51 +371,77 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant
       const uint32_t idesc_full = make_idesc(256, NACC, 0, 0, bf, bf);
       const uint32_t idesc_half = make_idesc(256, NACC / 2, 0, 0, bf, bf);
       const uint32_t b_hi = desc_hi(1024u);
-      int it = 0, ac = 0, lb = 0;
+      const uint32_t a_lo_base = desc_lo(a_base, 16u), b_lo_base = desc_lo(b_base, 16u);
+      const uint32_t a_slot_units = a_slot_bytes >> 4;
+      constexpr uint32_t B_UNITS = B_HALF >> 4;
+      uint32_t st = 0, bph = 0, b_lo = b_lo_base, bf_bar = b_full0, be_bar = b_empty0;     // weight ring position
+      uint32_t as = 0, aph = 0, a_lo_slot = a_lo_base, af_bar = a_full0, ae_bar = a_empty0; // halo ring position
+      int lb = 0;
+      long long dbg_te = 0, dbg_af = 0, dbg_bf = 0;
+      const long long dbg_start = dbg ? clock64() : 0;
       for (int pb = pair; pb < npb; pb += npairs, ++lb) {
         const int buf = lb & 1;
+        long long t0 = dbg ? clock64() : 0;
         mbar_wait(t_empty(buf), ((lb >> 1) & 1) ^ 1);
+        if (dbg) dbg_te += clock64() - t0;
         tc_fence_after();
         const uint32_t acc0 = tmem_base + buf * ACC_COLS;
         uint32_t first = 0u;
         for (int s = 0; s < p.nseg; ++s) {
           const Seg& sg = p.seg[s];
           const uint32_t a_hi = sg.a_hi, mt_units = sg.mt_units;
-          for (int c = 0; c < sg.nchunks; ++c, ++ac) {
-            const int slot = ac % NA;
-            mbar_wait(a_full(slot), (ac / NA) & 1);
+          const int ntaps = sg.ntaps, KS = sg.pad * 2 + 1;
+          const uint32_t wrap_units = (uint32_t)sg.P * 8u - (uint32_t)KS * 8u;
+          for (int c = 0; c < sg.nchunks; ++c) {
+            if (DBG) t0 = dbg ? clock64() : 0;
+            mbar_wait(af_bar, aph);
+            if (DBG && dbg) dbg_af += clock64() - t0;
             tc_fence_after();
-            const uint32_t a_lo0 = desc_lo(a_base + slot * a_slot_bytes, 16u);
-            for (int t = 0; t < sg.ntaps; ++t, ++it) {
-              const int st = it % NB;
-              const uint32_t e = p.tap[s][t];
-              mbar_wait(b_full(st), (it / NB) & 1);
+            uint32_t a_lo = a_lo_slot;
+            int kx = 0;
+            for (int t = 0; t < ntaps; ++t) {
+              if (DBG) t0 = dbg ? clock64() : 0;
+              mbar_wait(bf_bar, bph);
+              if (DBG && dbg) dbg_bf += clock64() - t0;
               tc_fence_after();
-              const uint32_t b_lo = desc_lo(b_base + st * B_HALF, 16u);
-              const uint32_t a_lo = a_lo0 + (e & 0xFFFu);
-              const bool half = (e >> 13) & 1;
-              const uint32_t idesc = half ? idesc_half : idesc_full;
-              const uint32_t acc = acc0 + (half ? NACC / 2 : 0);
+              uint32_t a_tap = a_lo, idesc = idesc_full, acc = acc0;
+              if (TAB) {
+                const uint32_t e = p.tap[s][t];
+                a_tap = a_lo_slot + (e & 0xFFFu);
+                if ((e >> 13) & 1) { idesc = idesc_half; acc = acc0 + NACC / 2; }
+              }
               if (elect_one()) {
 #pragma unroll
                 for (int mt = 0; mt < T2_TILES; ++mt) {
 #pragma unroll
                   for (int kk = 0; kk < 4; ++kk) {
-                    umma_bf16_2sm(acc + mt * NACC, desc_join(a_lo + mt * mt_units + kk * 2u, a_hi),
+                    umma_bf16_2sm(acc + mt * NACC, desc_join(a_tap + mt * mt_units + kk * 2u, a_hi),
                                   desc_join(b_lo + kk * 2u, b_hi), idesc, (first | (uint32_t)kk) ? 1u : 0u);
                   }
                 }
-                umma_commit_2sm(b_empty(st));
+                umma_commit_2sm(be_bar);
               }
               __syncwarp();
               first = 1u;
+              b_lo += B_UNITS; bf_bar += 8u; be_bar += 8u;
+              if (++st == (uint32_t)NB) { st = 0; bph ^= 1u; b_lo = b_lo_base; bf_bar = b_full0; be_bar = b_empty0; }
+              if (!TAB) {          // next tap: one pixel to the right, or wrap to the start of the next halo row
+                a_lo += 8u;
+                if (++kx == KS) { kx = 0; a_lo += wrap_units; }
+              }
             }
-            if (elect_one()) umma_commit_2sm(a_empty(slot));
+            if (elect_one()) umma_commit_2sm(ae_bar);
             __syncwarp();
+            a_lo_slot += a_slot_units; af_bar += 8u; ae_bar += 8u;
+            if (++as == (uint32_t)NA) { as = 0; aph ^= 1u; a_lo_slot = a_lo_base; af_bar = a_full0; ae_bar = a_empty0; }
           }
         }
         if (elect_one()) umma_commit_2sm(t_full(buf));
         __syncwarp();
+      }
+      if (dbg && lane == 0) {
+        p.dbg[2] = (unsigned long long)dbg_te; p.dbg[3] = (unsigned long long)dbg_af; p.dbg[4] = (unsigned long long)dbg_bf;
+        p.dbg[5] = (unsigned long long)(clock64() - dbg_start); p.dbg[6] = (unsigned long long)lb;
       }
     }
   } else {
@@ -397,27 +450,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant
     const int r = q * 32 + lane;
     const int wx = r & 7, vrow = r >> 3;
     int lb = 0;
+    long long dbg_ep = 0;        // (includes the wait for the accumulator)
     for (int pb = pair; pb < npb; pb += npairs, ++lb) {
       const int buf = lb & 1;
       const int blk = 2 * (pb % npb_pix) + (int)rank;
       const int xg = blk % p.nxg, vb = blk / p.nxg;
       const int x0 = xg * 8, v0 = vb * (16 * T2_TILES);
       const uint32_t acc0 = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
-      bool valid[T2_TILES];
-      long long pix[T2_TILES];
-#pragma unroll
-      for (int mt = 0; mt < T2_TILES; ++mt) {
-        const int vr = v0 + mt * 16 + vrow;
-        const int n = vr / p.Hp, y = vr - n * p.Hp;
-        valid[mt] = blk < p.nblocks && vr < p.Vtotal && y < p.H;
-        pix[mt] = ((long long)n * p.H + y) * p.W + x0 + wx;
-      }
-      epilogue2<NACC>(p, acc0, h * (NACC / 2), valid, pix, (int)blockIdx.x * 4 + q, lane, (pb / npb_pix) * NACC,
+      const int vr0 = v0 + vrow, vr1 = vr0 + 16;
+      const int n0 = vr0 / p.Hp, y0 = vr0 - n0 * p.Hp, n1 = vr1 / p.Hp, y1 = vr1 - n1 * p.Hp;
+      const bool ok0 = blk < p.nblocks && vr0 < p.Vtotal && y0 < p.H, ok1 = blk < p.nblocks && vr1 < p.Vtotal && y1 < p.H;
+      const long long px0 = ((long long)n0 * p.H + y0) * p.W + x0 + wx, px1 = ((long long)n1 * p.H + y1) * p.W + x0 + wx;
+      const long long t0 = dbg ? clock64() : 0;
+      epilogue2<NACC>(p, acc0, h * (NACC / 2), ok0, ok1, px0, px1, (int)blockIdx.x * 4 + q, lane, (pb / npb_pix) * NACC,
                       t_full(buf), (lb >> 1) & 1);
+      if (dbg) dbg_ep += clock64() - t0;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(t_empty(buf) & PEER_MASK);
     }
+    if (dbg && warp == 3 && lane == 0) p.dbg[7] = (unsigned long long)dbg_ep;
   }
   tc_fence_before();
   cluster_sync_all();
@@ -513,8 +565,20 @@ struct ConvTc2 {          // mirrors TsrConvTc2
 static_assert(sizeof(ConvSrc) == 32, "TsrConvSrc layout");
 static_assert(sizeof(ConvTc2) == 64 + 8 * 8 + 12 * 4, "TsrConvTc2 layout");
 
+template <int NACC, bool TAB, bool DBG>
+int launch_tc2_k(const CUtensorMap (&am)[2], const CUtensorMap (&wm)[2], const P2& p, size_t smem, int grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    TSR_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<NACC, TAB, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    attr_set = true;
+  }
+  conv_tc2_kernel<NACC, TAB, DBG><<<grid, T2_THREADS, smem, stream>>>(am[0], am[1], wm[0], wm[1], p);
+  TSR_CHECK_LAUNCH("conv2d_tc2");
+  return TSR_OK;
+}
+
 template <int NACC>
-int launch_tc2(const CUtensorMap (&am)[2], const CUtensorMap (&wm)[2], P2& p, cudaStream_t stream) {
+int launch_tc2(const CUtensorMap (&am)[2], const CUtensorMap (&wm)[2], P2& p, bool tab, cudaStream_t stream) {
   p.na_slots = (p.nseg == 1 && p.seg[0].pad == 0) ? 5 : 2;
   static const int env_na = getenv("TSR_TC2_NA") ? atoi(getenv("TSR_TC2_NA")) : 0;     // experiment overrides
   static const int env_nb = getenv("TSR_TC2_NB") ? atoi(getenv("TSR_TC2_NB")) : 0;
@@ -525,26 +589,28 @@ int launch_tc2(const CUtensorMap (&am)[2], const CUtensorMap (&wm)[2], P2& p, cu
   int stages = (int)((SMEM_LIMIT - fixed) / half);
   if (stages > T2_MAX_NB) stages = T2_MAX_NB;
   if (env_nb >= 2 && env_nb < stages) stages = env_nb;
-  if (stages < 2) { tsr_set_error("conv2d_tc2: shared memory plan infeasible"); return TSR_ERR_UNSUPPORTED; }
   p.nb_stages = stages;
   const size_t smem = fixed + (size_t)stages * half;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TSR_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-    attr_set = true;
-  }
   const int npb = (p.nblocks + 1) / 2 * p.ngroups;
   const int pairs = npb < num_sms() / 2 ? npb : num_sms() / 2;
-  conv_tc2_kernel<NACC><<<2 * pairs, T2_THREADS, smem, stream>>>(am[0], am[1], wm[0], wm[1], p);
-  TSR_CHECK_LAUNCH("conv2d_tc2");
-  return TSR_OK;
+  const int grid = 2 * pairs;
+  if (p.dbg) return tab ? launch_tc2_k<NACC, true, true>(am, wm, p, smem, grid, stream) : launch_tc2_k<NACC, false, true>(am, wm, p, smem, grid, stream);
+  return tab ? launch_tc2_k<NACC, true, false>(am, wm, p, smem, grid, stream) : launch_tc2_k<NACC, false, false>(am, wm, p, smem, grid, stream);
 }
 
 }  // namespace
 
+namespace { unsigned long long* g_tc2_dbg = nullptr; }
+
 extern "C" {
 
 int tsr_conv2d_tc2_stat_rows(void) { return T2_STAT_ROWS; }
+
+// diagnostics: 8 device counters that CTA 0 of the following launches fills with the cycles its roles spent waiting --
+// [0] A producer on a free halo slot, [1] B producer on a free weight stage, MMA issuer on [2] a drained accumulator,
+// [3] a halo tile, [4] a weight tile, [5] its whole loop, [6] blocks done, [7] epilogue warp 3 incl. accumulator wait.
+// NULL switches it off.
+void tsr_conv2d_tc2_debug(unsigned long long* counters_dev) { g_tc2_dbg = counters_dev; }
 
 size_t tsr_pack_conv_weight_dual_elems(int Cin) { return (size_t)(Cin / 64) * DUAL_CHUNK_ROWS * 64; }
 
@@ -562,14 +628,40 @@ int tsr_pack_conv_weight_dual(const float* w3, const float* w5, void* out, int C
   return TSR_OK;
 }
 
+// columns [n0, n0 + a.Cout) of a convolution with cout_total output channels (pointers of `a` already advanced)
+static int conv2d_tc2_cols(const ConvTc2& a, int cout_total, int n0, cudaStream_t stream);
+
 int tsr_conv2d_tc2(const void* args, cudaStream_t stream) {
   TSR_REQUIRE(args, "conv2d_tc2: null argument block");
-  const ConvTc2& a = *reinterpret_cast<const ConvTc2*>(args);
+  const ConvTc2& a0 = *reinterpret_cast<const ConvTc2*>(args);
+  TSR_REQUIRE(a0.Cout > 0 && a0.Cout % 64 == 0, "conv2d_tc2: Cout must be a multiple of 64 (got %d)", a0.Cout);
+  if (a0.stat && !(a0.flags & F_STAT_PRECLEARED))
+    TSR_CUDA(cudaMemsetAsync(a0.stat, 0, (size_t)T2_STAT_ROWS * 2 * a0.stat_ld * sizeof(float), stream));
+  if (a0.Cout == 64 || a0.Cout % 128 == 0) return conv2d_tc2_cols(a0, a0.Cout, 0, stream);
+  // 128 * k + 64 output channels (the data gradient of the 7-frame inputContact convolution: 448): the 128-wide groups in one
+  // launch, the trailing 64 in a second one
+  ConvTc2 a = a0;
+  a.Cout = a0.Cout - 64;
+  int rc = conv2d_tc2_cols(a, a0.Cout, 0, stream);
+  if (rc) return rc;
+  const int n0 = a.Cout;
+  a.Cout = 64;
+  if (a.bias) a.bias += n0;
+  if (a.residual) a.residual = (const char*)a.residual + 2 * (size_t)n0;
+  a.out = (char*)a.out + 2 * (size_t)n0;
+  if (a.out2_bf16) a.out2_bf16 = (char*)a.out2_bf16 + 2 * (size_t)n0;
+  if (a.stat) a.stat += n0;
+  if (a.aux) a.aux = (const char*)a.aux + 2 * (size_t)n0;
+  if (a.aux_scale) a.aux_scale += n0;
+  if (a.aux_shift) a.aux_shift += n0;
+  return conv2d_tc2_cols(a, a0.Cout, n0, stream);
+}
+
+static int conv2d_tc2_cols(const ConvTc2& a, int cout_total, int n0, cudaStream_t stream) {
   TSR_REQUIRE(a.nsrc == 1 || a.nsrc == 2, "conv2d_tc2: nsrc must be 1 or 2");
   TSR_REQUIRE(!(a.dual_fwd && a.nsrc != 1), "conv2d_tc2: the dual-branch forward takes one source");
   TSR_REQUIRE(a.out && a.B > 0 && a.H > 0, "conv2d_tc2: bad argument");
   TSR_REQUIRE(a.W % 8 == 0, "conv2d_tc2: W must be a multiple of 8 (got %d)", a.W);
-  TSR_REQUIRE(a.Cout == 64 || (a.Cout > 0 && a.Cout % 128 == 0), "conv2d_tc2: Cout must be 64 or a multiple of 128 (got %d)", a.Cout);
   TSR_REQUIRE(!a.dual_fwd || a.Cout == 128, "conv2d_tc2: the dual-branch forward produces 64 + 64 channels");
   TSR_REQUIRE(a.out_ld % 8 == 0 && ((uintptr_t)a.out & 15) == 0, "conv2d_tc2: out must be 16-byte aligned, stride %% 8 == 0");
   TSR_REQUIRE(!a.residual || (a.res_ld % 8 == 0 && ((uintptr_t)a.residual & 15) == 0), "conv2d_tc2: residual alignment");
@@ -581,6 +673,7 @@ int tsr_conv2d_tc2(const void* args, cudaStream_t stream) {
   TSR_REQUIRE(!(fl & F_BNB_RELU) || (a.aux_scale && a.aux_shift && ((uintptr_t)a.aux_scale & 15) == 0 && ((uintptr_t)a.aux_shift & 15) == 0),
               "conv2d_tc2: BN-backward ReLU mask needs 16-byte aligned scale / shift");
   TSR_REQUIRE(!a.stat || a.stat_ld >= a.Cout, "conv2d_tc2: stat_ld too small");
+  TSR_REQUIRE(!a.dual_fwd || cout_total == 128, "conv2d_tc2: the dual-branch forward produces 64 + 64 channels");
 
   P2 p;
   memset(&p, 0, sizeof(p));
@@ -648,12 +741,12 @@ int tsr_conv2d_tc2(const void* args, cudaStream_t stream) {
       rc = get_map(&wm[1], c.w_packed, 2, gdim, gstr, box1, CU_TENSOR_MAP_SWIZZLE_NONE);
       if (rc) return rc;
     } else {
-      sg.chunk_wrows = taps * a.Cout;
+      sg.chunk_wrows = taps * cout_total;
       for (int t = 0; t < taps; ++t) {
         p.tap[s][t] = (uint32_t)(((t / c.KS) * sg.P + t % c.KS) * 8) | ((uint32_t)s << 12);
-        p.wrow[s][t] = t * a.Cout;
+        p.wrow[s][t] = t * cout_total + n0;
       }
-      cuuint64_t gdim[2] = {64, (cuuint64_t)sg.nchunks * taps * a.Cout};
+      cuuint64_t gdim[2] = {64, (cuuint64_t)sg.nchunks * taps * cout_total};
       cuuint64_t gstr[1] = {128};
       cuuint32_t box[2] = {64, (cuuint32_t)(NACC / 2)};
       int rc = get_map(&wm[s], c.w_packed, 2, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_NONE);
@@ -665,9 +758,9 @@ int tsr_conv2d_tc2(const void* args, cudaStream_t stream) {
   p.aux = a.aux; p.aux_sc = a.aux_scale; p.aux_sh = a.aux_shift;
   p.res_ld = a.res_ld; p.out_ld = a.out_ld; p.out2_ld = a.out2_ld; p.stat_ld = a.stat_ld; p.aux_ld = a.aux_ld;
   p.flags = fl;
-  if (a.stat && !(fl & F_STAT_PRECLEARED))
-    TSR_CUDA(cudaMemsetAsync(a.stat, 0, (size_t)T2_STAT_ROWS * 2 * a.stat_ld * sizeof(float), stream));
-  return NACC == 128 ? launch_tc2<128>(am, wm, p, stream) : launch_tc2<64>(am, wm, p, stream);
+  p.dbg = g_tc2_dbg;
+  p.ovf = (fl & F_F16) ? tsr_f16_overflow_ptr() : nullptr;
+  return NACC == 128 ? launch_tc2<128>(am, wm, p, a.dual_fwd != 0, stream) : launch_tc2<64>(am, wm, p, a.dual_fwd != 0, stream);
 }
 
 }  // extern "C"

@@ -5,6 +5,9 @@
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
+static int* g_f16_overflow = nullptr;      // device flag registered by the host side (tsr_set_f16_overflow_flag)
+
+int* tsr_f16_overflow_ptr() { return g_f16_overflow; }
 
 void tsr_set_error(const char* fmt, ...) {
   va_list ap;
@@ -22,6 +25,11 @@ int tsr_version(void) { return 100; }
 long long tsr_launch_count_inc(int n) { return g_launches.fetch_add(n) + n; }
 long long tsr_launch_count(void) { return g_launches.load(); }
 void tsr_launch_count_reset(void) { g_launches.store(0); }
+
+// "fp16" precision mode: a sticky device int that the kernels storing fp16 activations (tsr_conv2d_tc2 with TSR_TC2_F16,
+// tsr_bn_apply with fp16 output) set to 1 when a value they store is not finite (|x| > 65504 or NaN).  The caller owns
+// the memory (the library never allocates); NULL switches the check off.
+void tsr_set_f16_overflow_flag(int* flag_dev) { g_f16_overflow = flag_dev; }
 
 // 0 when the current device can run this library (compute capability 10.x), an error code otherwise.
 int tsr_check_device(void) {

@@ -515,7 +515,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_apply_v_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ scale, const float* __restrict__ shift,
                   T* __restrict__ out, int out_ld, long long npix, int C, int relu, __nv_bfloat16* __restrict__ out2,
-                  int out2_ld) {
+                  int out2_ld, int* __restrict__ ovf = nullptr) {
   // each thread owns one 16-byte channel vector (fixed q) and strides over pixels: coefficients live in registers.
   // out2 (optional, 16-bit T only): a second, bf16 copy of the result -- the weight-gradient operand of the "fp16" mode
   constexpr int N = V16<T>::N;
@@ -536,6 +536,13 @@ bn_apply_v_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ s
     V16<T>::store(out + p * out_ld + q * N, v);
     if constexpr (N == 8) {
       if (out2) V16<__nv_bfloat16>::store(out2 + p * out2_ld + q * N, v);
+      if (ovf) {             // fp16 output: sticky overflow guard
+        float m = 0.f;
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { m = fmaxf(m, fabsf(v[k])); bad |= (v[k] != v[k]); }
+        if (bad || !(m <= 65504.f)) *ovf = 1;
+      }
     }
   }
 }
@@ -765,7 +772,7 @@ int tsr_bn_apply(const void* y, int y_ld, int y_bf16, const float* scale, const 
 #define ARGS(Ti, To) (const Ti*)y, y_ld, scale, shift, (To*)out, out_ld, npix, C, relu
   if (y_bf16 && y_bf16 == out_bf16 && C % 8 == 0 && 256 % (C / 8) == 0 && y_ld % 8 == 0 && out_ld % 8 == 0 &&
       (!o2 || out2_ld % 8 == 0)) {
-    if (y_bf16 == TSR_DT_F16) bn_apply_v_kernel<__half><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>(ARGS(__half, __half), o2, out2_ld);
+    if (y_bf16 == TSR_DT_F16) bn_apply_v_kernel<__half><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>(ARGS(__half, __half), o2, out2_ld, tsr_f16_overflow_ptr());
     else bn_apply_v_kernel<__nv_bfloat16><<<ew_grid(npix * (C / 8)), 256, 0, stream>>>(ARGS(__nv_bfloat16, __nv_bfloat16), o2, out2_ld);
   } else {
     TSR_REQUIRE(!o2, "bn_apply: the second (bf16) output needs 16-bit operands with C %% 8 == 0");

@@ -39,6 +39,32 @@ def get_precision() -> str:
     return _PRECISION
 
 
+_OVERFLOW_FLAG: Dict[int, torch.Tensor] = {}       # device index -> int32 flag registered with the library
+
+
+def _arm_overflow_guard(device) -> None:
+    """"fp16" mode: hand the library a sticky device flag that its fp16-storing kernels raise on a non-finite value."""
+    idx = torch.device(device).index or 0
+    t = _OVERFLOW_FLAG.get(idx)
+    if t is None:
+        t = torch.zeros((), dtype=torch.int32, device=device)
+        _OVERFLOW_FLAG[idx] = t
+    _lib.lib().tsr_set_f16_overflow_flag(t.data_ptr())
+
+
+def check_fp16_overflow(device=None) -> None:
+    """Raise if a stored fp16 activation overflowed since the last check (one device -> host read: call it at logging
+    cadence, as the trainer does, not per step).  fp16 holds |x| <= 65504; un-normalised activations beyond that need the
+    bf16 or fp32 mode."""
+    for idx, t in _OVERFLOW_FLAG.items():
+        if device is not None and (torch.device(device).index or 0) != idx:
+            continue
+        if int(t.item()) != 0:
+            t.zero_()
+            raise _lib.TsrError("tactilesr_b200: an fp16 activation overflowed (|x| > 65504 or NaN) in the 'fp16' precision "
+                                "mode -- use set_precision('bf16') or set_precision('fp32') for this model / data")
+
+
 def bump_weight_epoch() -> None:
     global _WEIGHT_EPOCH
     _WEIGHT_EPOCH += 1
@@ -390,8 +416,12 @@ class HeadOp(Op):
     """Upsample(x sf, bilinear) + Conv2d(3 -> 64, 3x3, no bias) [+ ReLU]
     (reference tactileSR_model.py:35-37, 60-62, 107 + 122)."""
 
-    def __init__(self, ch0: int, weight, out: View, relu: bool, sf: int):
-        self.ch0, self.weight, self.out, self.relu, self.sf = ch0, weight, out, relu, sf
+    def __init__(self, ch0: int, conv: torch.nn.Conv2d, out: View, relu: bool, sf: int):
+        self.ch0, self.conv, self.out, self.relu, self.sf = ch0, conv, out, relu, sf
+
+    @property
+    def weight(self):              # read through the module at run time (programs are cached across parameter updates)
+        return self.conv.weight
 
     def params(self):
         return (self.weight,)
@@ -913,7 +943,10 @@ class Program:
             if kind == "conv" and whole:
                 prods = producers.get(buf, [])
                 if len(prods) == 1 and isinstance(prods[0][0], BNReLUOp) and prods[0][1].c0 == 0 and prods[0][1].C == buf.C:
-                    op.sink = Sink("bn", prods[0][0])
+                    # (not on a 1x1 data gradient: it has no main loop to hide the longer epilogue behind -- measured 1.10 ms
+                    # fused vs 0.45 + 0.16 ms as two passes for the 64 -> 256 confusion gradient at B = 1024)
+                    if getattr(op, "K", 3) != 1:
+                        op.sink = Sink("bn", prods[0][0])
                 elif (prods and all(isinstance(p, (ConvOp, HeadOp)) and p.relu for p, _ in prods)
                       and sum(pv.C for _, pv in prods) == buf.C):
                     op.sink = Sink("relu")
@@ -942,11 +975,15 @@ def run_forward(prog: Program, x: torch.Tensor, training: bool, need_grad: bool,
     x = x.detach().contiguous().float()
     B = x.shape[0]
     if prog.input_is_taxel:
+        if x.dim() != 4 or tuple(x.shape[-2:]) != (4, 4):
+            raise _lib.TsrError(f"tactilesr_b200: the taxel head kernels take (B, 3*seqsCnt, 4, 4) inputs, got {tuple(x.shape)}")
         H = W = x.shape[-1] * prog.sf
     else:
         H, W = x.shape[-2], x.shape[-1]
     c = RunCtx(mode, B, H, W, x.device, training, need_grad)
     c.x = x
+    if c.act == 2:
+        _arm_overflow_guard(x.device)
     prog.plan()
     c.conv_inputs = {op.src.buf for op in prog.ops if isinstance(op, (ConvOp, DualConvOp))}
     c.keep_taps = keep_taps

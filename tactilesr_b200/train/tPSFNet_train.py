@@ -61,3 +61,48 @@ def eval_func(model, test_loader, config, device=None):
     s12 = (d * z).mean(axis=(1, 2)) - mu1 * mu2
     ssim = ((2 * mu1 * mu2 + C1) * (2 * s12 + C2)) / ((mu1 * mu1 + mu2 * mu2 + C1) * (s1 + s2 + C2))
     return float(mse.mean()), float(ssim.mean())
+
+
+def build_dataloader(config, rank: int = 0, world: int = 1):
+    """reference :30-48 (train / test loaders; the two single-tap inference loaders belong to the PNG hook).  The raw-data
+    reader (utility/raw_data_process.py) is outside the hot path, so real data comes as a dataset object in
+    ``config['train_dataset']`` / ``config['test_dataset']`` yielding (LR raw (3,4,4), depth (100,100)); ``_synthetic`` = N
+    builds N random records of those shapes."""
+    from .common import SyntheticPSFDataset, make_loader
+    n = int(config.get("_synthetic", 0))
+    if n > 0:
+        train_set = SyntheticPSFDataset(n, seed=config["random_seed"])
+        test_set = SyntheticPSFDataset(max(config["test_batch_size"] * 2, 16), seed=config["random_seed"] + 1)
+    elif "train_dataset" in config:
+        train_set, test_set = config["train_dataset"], config["test_dataset"]
+    else:
+        raise FileNotFoundError("tPSFNet training data: pass dataset objects in config['train_dataset'] / ['test_dataset'] "
+                                "or use --synthetic N (the reference's raw-data reader is not part of this package)")
+    return (make_loader(train_set, config["train_batch_size"], True, world, rank, seed=config["random_seed"]),
+            make_loader(test_set, config["test_batch_size"], False, world, rank))
+
+
+def main(config):
+    """reference main() :193-229."""
+    from .. import set_precision
+    from .common import EvalHook, set_random_seed, setup_device
+    rank, world, device = setup_device()
+    set_precision(config.get("_precision", "fp32"))
+    set_random_seed(config["random_seed"])
+    train_loader, test_loader = build_dataloader(config, rank, world)
+    model, optimizer = build_model_and_optimizer(config, device)
+    lr_scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=config["lr_scheduler_step_size"],
+                                                   gamma=config["lr_scheduler_gamma"])
+    kw = {"max_iters": config["_max_iters"], "by_epoch": False} if config.get("_max_iters", 0) > 0 else {"max_epochs": config["epochs"]}
+    trainer = Trainer_tPSF(config["scale_num"], model, optimizer, lr_scheduler, train_loader, work_dir=config["save_dir"],
+                           checkpoint_period=config["checkpoint_period"], device=device, **kw)
+    if trainer.train_by_epoch:
+        trainer.register_hooks([EvalHook(1, lambda: eval_func(model, test_loader, config, device), names=("test_mse", "test_ssim"))])
+    trainer.train(auto_resume=False)
+    return trainer
+
+
+if __name__ == "__main__":
+    from ..config import tPSFNet_config
+    from .common import parse_cli
+    main(parse_cli("tPSFNet training on the tactilesr_b200 kernels", tPSFNet_config))

@@ -40,3 +40,33 @@ def build_model_and_optimizer(config, singleSR_config, device):
     optimizer = FusedAdam(model.parameters(), lr=config["lr"], weight_decay=config["weight_decay"])
     model = model_param_init(singleSR_config, config, model, device)
     return model, optimizer
+
+
+def main(config, single_config=None):
+    """reference main() :62-98: the optimizer is built BEFORE ``model_param_init`` transplants the pretrained stacks (so they
+    stay frozen), no warm-up.  Without a ``load_checkpoint_dir`` file the transplant is skipped (synthetic smoke runs)."""
+    import os
+
+    from .. import set_precision
+    from ..config import tactileSR_config
+    from .common import EvalHook, set_random_seed, setup_device
+    from .tactileSR_train import build_dataloader, make_trainer
+    rank, world, device = setup_device()
+    set_precision(config.get("_precision", "fp16"))
+    set_random_seed(config["random_seed"])
+    train_loader, test_loader = build_dataloader(config, rank, world)
+    model, optimizer = build_model_and_optimizer(config, device)
+    if os.path.exists(config.get("load_checkpoint_dir", "")):
+        model = model_param_init(single_config or tactileSR_config, config, model, device)
+    cfg = {k: v for k, v in config.items() if not k.startswith("warmup_")}          # :79-87 passes no warm-up arguments
+    trainer = make_trainer(cfg, model, optimizer, train_loader, device)
+    if trainer.train_by_epoch:
+        trainer.register_hooks([EvalHook(1, lambda: eval_func(model, test_loader, config, device))])
+    trainer.train(auto_resume=False)
+    return trainer
+
+
+if __name__ == "__main__":
+    from ..config import tactileSeqs_config
+    from .common import parse_cli
+    main(parse_cli("TactileSR (7-frame sequence) training on the tactilesr_b200 kernels", tactileSeqs_config))

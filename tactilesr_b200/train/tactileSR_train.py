@@ -1,6 +1,8 @@
-"""Hot-path part of reference train/tactileSR_train.py: ``Trainer_tactileSR.train_cal_loss`` (:41-51) and the
-model / optimizer construction of ``main`` (:204-213), running on the tactilesr_b200 kernels.  Plotting, PNG
-inference hooks and dataset readers (the rest of that file) are outside the hot path."""
+"""Reference train/tactileSR_train.py on the tactilesr_b200 kernels: ``Trainer_tactileSR.train_cal_loss`` (:41-51),
+``build_dataloader`` (:28-38), ``eval_func`` (:64-101) and the entry point ``main(config)`` (:199-242) -- runnable as
+``python -m tactilesr_b200.train.tactileSR_train`` or, data parallel,
+``torchrun --nproc-per-node N -m tactilesr_b200.train.tactileSR_train`` (the batch is sharded over the ranks with a
+``DistributedSampler``).  The matplotlib PNG inference hook of that file is outside the hot path."""
 from __future__ import annotations
 
 import torch
@@ -62,3 +64,59 @@ def eval_func(model, test_loader, config, device=None):
             n += 1
     loss, ssim, psnr = (acc / max(n, 1)).tolist()
     return loss, ssim, psnr
+
+
+def build_dataloader(config, rank: int = 0, world: int = 1):
+    """reference :28-38: (train_loader, test_loader) over the pickled-dict ``.npy`` files -- or, with ``_synthetic`` = N,
+    over N random records of the same shapes.  ``train_batch_size`` is the per-rank batch, as in the reference under DDP."""
+    from ..data.srdataset import TactileSRDataset
+    from .common import SyntheticSRDataset, make_loader
+    n = int(config.get("_synthetic", 0))
+    if n > 0:
+        train_set = SyntheticSRDataset(n, config["seqsCnt"], seed=config["random_seed"])
+        test_set = SyntheticSRDataset(max(config["test_batch_size"] * 2, 16), config["seqsCnt"], seed=config["random_seed"] + 1)
+    else:
+        train_set, test_set = TactileSRDataset(config["train_dataset_dir"]), TactileSRDataset(config["test_dataset_dir"])
+    train_loader = make_loader(train_set, config["train_batch_size"], True, world, rank, seed=config["random_seed"])
+    test_loader = make_loader(test_set, config["test_batch_size"], False, world, rank)
+    return train_loader, test_loader
+
+
+def make_trainer(config, model, optimizer, train_loader, device):
+    """reference main() :213-228: StepLR + the warm-up arguments exactly as that call passes them (``warmup_by_epoch`` is
+    not forwarded, so the 2000-step warm-up runs per iteration)."""
+    lr_scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=config["lr_scheduler_step_size"],
+                                                   gamma=config["lr_scheduler_gamma"])
+    kw = {}
+    if config.get("_max_iters", 0) > 0:
+        kw["max_iters"] = config["_max_iters"]
+    else:
+        kw["max_epochs"] = config["epochs"]
+    warm = {k: config[k] for k in ("warmup_t", "warmup_mode", "warmup_init_lr", "warmup_factor") if k in config}
+    if "max_iters" in kw:
+        warm["by_epoch"] = False
+    return Trainer_tactileSR(config, model, optimizer, lr_scheduler, train_loader, work_dir=config["save_dir"],
+                             checkpoint_period=config["checkpoint_period"], device=device,
+                             cuda_graph=bool(config.get("_cuda_graph", False)), **kw, **warm)
+
+
+def main(config):
+    """reference main() :199-242."""
+    from .. import set_precision
+    from .common import EvalHook, set_random_seed, setup_device
+    rank, world, device = setup_device()
+    set_precision(config.get("_precision", "fp16"))
+    set_random_seed(config["random_seed"])           # identical initial weights on every rank
+    train_loader, test_loader = build_dataloader(config, rank, world)
+    model, optimizer = build_model_and_optimizer(config, device)
+    trainer = make_trainer(config, model, optimizer, train_loader, device)
+    if trainer.train_by_epoch:
+        trainer.register_hooks([EvalHook(1, lambda: eval_func(model, test_loader, config, device))])
+    trainer.train(auto_resume=False)
+    return trainer
+
+
+if __name__ == "__main__":
+    from ..config import tactileSR_config
+    from .common import parse_cli
+    main(parse_cli("TactileSR (single frame) training on the tactilesr_b200 kernels", tactileSR_config))

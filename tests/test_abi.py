@@ -68,3 +68,14 @@ def test_cpu_tensors_are_rejected_not_silently_computed():
         TactileSR()(torch.zeros(1, 3, 4, 4))
     with pytest.raises(TsrError):
         tPSFNet(1.4, None, device="cpu")(torch.zeros(1, 3, 4, 4), torch.zeros(1, 1, 100, 100))
+
+
+def test_unsupported_configurations_raise_instead_of_computing_garbage():
+    """Shapes / BatchNorm variants the fused kernels do not implement must fail loudly (they would read the wrong memory)."""
+    import torch
+    from tactilesr_b200 import TsrError, engine as E
+    bn = torch.nn.BatchNorm2d(64, momentum=None)
+    with pytest.raises(TsrError):
+        E.BNReLUOp(E.View.of(E.Buf("y", 64)), bn, E.View.of(E.Buf("a", 64)))
+    with pytest.raises(TsrError):
+        E.BNReLUOp(E.View.of(E.Buf("y", 64)), torch.nn.BatchNorm2d(64, affine=False), E.View.of(E.Buf("a", 64)))

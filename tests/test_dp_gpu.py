@@ -43,7 +43,7 @@ def _worker(rank, world, port, q):
     tr.train(auto_resume=False)
     assert tr._dp is not None and tr._dp.world == 2
     flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu()
-    q.put((rank, flat, tr.metric_storage.latest("total_loss") if rank == 0 else None))
+    q.put((rank, flat, tr.metric_storage["total_loss"].latest if rank == 0 else None))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -298,3 +298,34 @@ def test_tc_conv_fused_bn_statistics(Cout, KS, B, f16):
     assert (coef[2].double() - mean).abs().max() < 1e-5 * max(1.0, mean.abs().max().item())
     assert ((coef[3].double() - 1 / (var + 1e-5).sqrt()).abs() / (1 / (var + 1e-5).sqrt())).max() < 1e-5
     assert int(nbt.item()) == 1 and (rm.double() - 0.1 * mean).abs().max() < 1e-5
+
+
+def test_fp16_overflow_guard():
+    """The "fp16" mode's caveat (|x| <= 65504) is guarded: weights scaled until an activation overflows raise a clear error
+    at the next check; the same model in the bf16 mode runs, and the flag is sticky-then-cleared."""
+    import tactilesr_b200 as tb
+    from tactilesr_b200 import TsrError
+    from tactilesr_b200.model import TactileSR
+    torch.manual_seed(3)
+    m = TactileSR().cuda().eval()
+    LR, _ = sr_inputs(4, 1, 5)
+    with torch.no_grad():
+        for p in m.output_layer[0].parameters():
+            p.mul_(3e5)                                # the 128 -> 128 conv in front of the tail now produces > 65504
+        for blk in m.patternFeatureExtra_layer:
+            blk.confusion.weight.mul_(30.0)
+    try:
+        tb.set_precision("fp16")
+        tb.check_fp16_overflow()                        # clean state
+        with torch.no_grad():
+            m(LR.cuda())
+        with pytest.raises(TsrError, match="overflow"):
+            tb.check_fp16_overflow()
+        tb.check_fp16_overflow()                        # cleared by the failed check
+        tb.set_precision("bf16")
+        with torch.no_grad():
+            out = m(LR.cuda())
+        assert torch.isfinite(out).all()
+        tb.check_fp16_overflow()
+    finally:
+        tb.set_precision("fp32")

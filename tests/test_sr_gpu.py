@@ -55,6 +55,12 @@ def test_sr_train_forward_backward_matches_reference(S):
     loss = mse_hr_loss(out, HR_raw, 10.0)
     assert abs(loss.item() - float(g["f64/loss"])) / float(g["f64/loss"]) < 1e-5
     loss.backward()
+    from oracle import tactilesr_oracle as so
+    sd0 = so.make_state(so.tactilesr_layout(S), int(g["seed_w"]))
+    LRc, HRc = sr_inputs(int(g["B"]), S, int(g["seed_x"]))
+    _, _, grads64, _ = so.loss_and_grads({k: v.double() if v.is_floating_point() else v for k, v in sd0.items()},
+                                         LRc.double(), HRc.double(), True)
+    _, _, grads32, _ = so.loss_and_grads(sd0, LRc, HRc, True)
     worst = 0.0
     names = [str(x) for x in g["param_names"]]
     assert [n for n, _ in m.named_parameters()] == names
@@ -74,9 +80,13 @@ def test_sr_train_forward_backward_matches_reference(S):
         _, ref_err = summary_close(g["f32/grad_summary"][names.index(n)], want, 1.0)
         _, err = summary_close(got, want, 1.0)
         assert err[0] < max(5e-3, 6 * ref_err[0]), (n, err, ref_err)
-        assert err[1] < max(2e-2, 6 * ref_err[1]), (n, err, ref_err)
-        worst = max(worst, max(err))
-    print("worst grad summary error", worst)
+        # the WHOLE gradient tensor against the fp64 oracle (pinned to the reference by tests/test_oracle_golden.py), not 16
+        # sampled elements: 5e-3 rel-L2, or 6x what the reference's own fp32 arithmetic deviates on this parameter
+        full = rel_l2(p.grad, grads64[n])
+        ref_full = rel_l2(grads32[n], grads64[n])
+        assert full < max(5e-3, 6 * ref_full), (n, full, ref_full)
+        worst = max(worst, err[0], full)
+    print("worst gradient error (norm / full tensor rel-L2)", worst)
     sd = m.state_dict()
     for n, want in zip([str(x) for x in g["bn_names"]], g["f64/bn_summary"]):
         ok, err = summary_close(summarize(sd[n]), want, 2e-5)

@@ -58,7 +58,8 @@ def _rand_w(Cout, Cin, KS, dt):
 
 @pytest.mark.parametrize("Cin,Cout,KS,B,f16", [
     (64, 64, 3, 1024, 1), (128, 128, 5, 1024, 0), (64, 64, 5, 256, 0), (128, 128, 3, 256, 1), (256, 64, 1, 256, 1),
-    (448, 64, 3, 64, 0), (64, 256, 1, 256, 0), (64, 64, 3, 3, 1), (128, 128, 5, 1, 0), (64, 128, 3, 37, 1)])
+    (448, 64, 3, 64, 0), (64, 256, 1, 256, 0), (64, 64, 3, 3, 1), (128, 128, 5, 1, 0), (64, 128, 3, 37, 1),
+    (64, 448, 3, 9, 0), (64, 192, 1, 70, 1)])
 def test_tc2_forward_bias_residual_relu(Cin, Cout, KS, B, f16):
     """Forward with the whole epilogue (+ bias, + residual, ReLU, bf16 copy) incl. ragged / tiny batches."""
     from tactilesr_b200 import _lib
@@ -274,7 +275,7 @@ def test_wgrad_tc_large_batch(Cin, Cout, KS, B):
     # exact bf16 products, fp32 accumulation over up to 1.6e6 pixels: against the fp64 result the error is the summation
     # order's (~sqrt(K) * 2^-24); cuDNN's own fp32 weight gradient sits at the same distance from fp64
     ref = torch.nn.grad.conv2d_weight(_nchw(x).double(), (Cout, Cin, KS, KS), _nchw(dy).double(), padding=KS // 2)
-    assert rel_l2(dw, ref) < 5e-5, rel_l2(dw, ref)
+    assert rel_l2(dw, ref) < max(5e-5, 1.5e-7 * (B * H * W) ** 0.5), rel_l2(dw, ref)      # 1.9e-4 at B = 1024 (K = 1.6e6)
     dw2 = dw.clone()
     _lib.call("tsr_conv2d_wgrad_tc", x.data_ptr(), Cin, dy.data_ptr(), Cout, dw2.data_ptr(), ws.data_ptr(), ws.numel(), B, H, W,
               Cin, Cout, KS, 1, _st())

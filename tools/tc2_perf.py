@@ -43,11 +43,34 @@ def act(C, dt):
     return [torch.randn(B, H, W, C, device=dev).to(dt) for _ in range(NROT)]
 
 
+DBG = torch.zeros(8, dtype=torch.int64, device=dev)
+LAST = [None]
+
+
+def timeit_dbg(fn, n=6):
+    """timeit for a generation-2 launch; afterwards one more launch with the wait-cycle counters switched on."""
+    t = timeit(fn, n)
+    LAST[0] = fn
+    return t
+
+
 def report(name, flops, us_new, us_old=None):
     s = f"{name:46s} tc2 {us_new:8.1f} us {flops / us_new / 1e6:7.1f} TF/s"
     if us_old is not None:
         s += f" | gen1 {us_old:8.1f} us {flops / us_old / 1e6:7.1f} TF/s"
     print(s, flush=True)
+    if LAST[0] is not None:
+        DBG.zero_()
+        L.tsr_conv2d_tc2_debug(DBG.data_ptr())
+        LAST[0](0)
+        torch.cuda.synchronize()
+        L.tsr_conv2d_tc2_debug(0)
+        d = DBG.tolist()
+        tot = max(d[5], 1)
+        print(f"      CTA0 cycles: loop {tot}  blocks {d[6]}  MMA waits: accum-drained {100 * d[2] / tot:.0f}%  A tile {100 * d[3] / tot:.0f}%  "
+              f"B tile {100 * d[4] / tot:.0f}% | A-producer idle {100 * d[0] / tot:.0f}%  B-producer idle {100 * d[1] / tot:.0f}%  "
+              f"epilogue warp busy+wait {100 * d[7] / tot:.0f}%", flush=True)
+        LAST[0] = None
 
 
 rows = L.tsr_conv2d_tc2_stat_rows()
@@ -64,7 +87,7 @@ for Cin, Cout, KS in [(64, 64, 3), (64, 64, 5), (128, 128, 3), (128, 128, 5)]:
     bias = torch.randn(Cout, device=dev)
     part = torch.empty(rows, 2, Cout, device=dev)
     part1 = torch.empty(rows1, 2, Cout, device=dev)
-    new = timeit(lambda i: _lib.conv_tc2([(x[i].data_ptr(), Cin, Cin, KS, wf.data_ptr())], out[i].data_ptr(), Cout, B, H, W, Cout,
+    new = timeit_dbg(lambda i: _lib.conv_tc2([(x[i].data_ptr(), Cin, Cin, KS, wf.data_ptr())], out[i].data_ptr(), Cout, B, H, W, Cout,
                                          flags=_lib.TC2_F16, bias=bias.data_ptr(), stat=part.data_ptr(), stat_ld=Cout))
     old = timeit(lambda i: _lib.call("tsr_conv2d_tc", x[i].data_ptr(), Cin, wf.data_ptr(), bias.data_ptr(), 0, 0, out[i].data_ptr(), Cout,
                                      B, H, W, Cin, Cout, KS, 2, 0, 0, part1.data_ptr(), 0, 0, st))
@@ -79,7 +102,7 @@ img = torch.empty(L.tsr_pack_conv_weight_dual_elems(64), dtype=f16, device=dev)
 _lib.call("tsr_pack_conv_weight_dual", w3.data_ptr(), w5.data_ptr(), img.data_ptr(), 64, 2, st)
 bias = torch.randn(128, device=dev)
 part = torch.empty(rows, 2, 128, device=dev)
-new = timeit(lambda i: _lib.conv_tc2([(x[i].data_ptr(), 64, 64, 5, img.data_ptr())], out[i].data_ptr(), 128, B, H, W, 128,
+new = timeit_dbg(lambda i: _lib.conv_tc2([(x[i].data_ptr(), 64, 64, 5, img.data_ptr())], out[i].data_ptr(), 128, B, H, W, 128,
                                      flags=_lib.TC2_F16, bias=bias.data_ptr(), stat=part.data_ptr(), stat_ld=128, dual_fwd=1))
 report("dual fwd+stats 64 -> 64|64 (3x3 | 5x5)", 2.0 * npix * 64 * 64 * 34, new)
 
@@ -88,7 +111,7 @@ x = act(256, f16); out = act(64, f16); res = act(64, f16); o2 = act(64, bf)
 w = torch.randn(64, 256, 1, 1, device=dev) * 0.05
 wf = pack(w, True)
 bias = torch.randn(64, device=dev)
-new = timeit(lambda i: _lib.conv_tc2([(x[i].data_ptr(), 256, 256, 1, wf.data_ptr())], out[i].data_ptr(), 64, B, H, W, 64,
+new = timeit_dbg(lambda i: _lib.conv_tc2([(x[i].data_ptr(), 256, 256, 1, wf.data_ptr())], out[i].data_ptr(), 64, B, H, W, 64,
                                      flags=_lib.TC2_F16 | _lib.TC2_RELU, bias=bias.data_ptr(), residual=res[i].data_ptr(), res_ld=64,
                                      out2=o2[i].data_ptr(), out2_ld=64))
 old = timeit(lambda i: _lib.call("tsr_conv2d_tc", x[i].data_ptr(), 256, wf.data_ptr(), bias.data_ptr(), res[i].data_ptr(), 64,
@@ -102,11 +125,11 @@ dy = act(64, bf); dx = act(256, bf); y = act(256, f16)
 wd = pack(w, False, dgrad=True)
 coef = torch.randn(2, 256, device=dev)
 part = torch.empty(rows, 2, 256, device=dev)
-new = timeit(lambda i: _lib.conv_tc2([(dy[i].data_ptr(), 64, 64, 1, wd.data_ptr())], dx[i].data_ptr(), 256, B, H, W, 256))
+new = timeit_dbg(lambda i: _lib.conv_tc2([(dy[i].data_ptr(), 64, 64, 1, wd.data_ptr())], dx[i].data_ptr(), 256, B, H, W, 256))
 old = timeit(lambda i: _lib.call("tsr_conv2d_tc", dy[i].data_ptr(), 64, wd.data_ptr(), 0, 0, 0, dx[i].data_ptr(), 256, B, H, W, 64, 256,
                                  1, 0, 0, 0, 0, 0, 0, st))
 report("dgrad 1x1 64->256", 2.0 * npix * 256 * 64, new, old)
-new = timeit(lambda i: _lib.conv_tc2([(dy[i].data_ptr(), 64, 64, 1, wd.data_ptr())], dx[i].data_ptr(), 256, B, H, W, 256,
+new = timeit_dbg(lambda i: _lib.conv_tc2([(dy[i].data_ptr(), 64, 64, 1, wd.data_ptr())], dx[i].data_ptr(), 256, B, H, W, 256,
                                      flags=_lib.TC2_BNB | _lib.TC2_BNB_RELU | _lib.TC2_AUX_F16, aux=y[i].data_ptr(), aux_ld=256,
                                      aux_scale=coef[0].data_ptr(), aux_shift=coef[1].data_ptr(), stat=part.data_ptr(), stat_ld=256))
 report("dgrad 1x1 64->256 + BN-bwd epilogue", 2.0 * npix * 256 * 64, new)
@@ -127,12 +150,12 @@ for C in (64, 128):
 
     old = timeit(old_pair)
     srcs = lambda i: [(dy3[i].data_ptr(), C, C, 3, wd3.data_ptr()), (dy5[i].data_ptr(), C, C, 5, wd5.data_ptr())]
-    new = timeit(lambda i: _lib.conv_tc2(srcs(i), dx[i].data_ptr(), C, B, H, W, C))
+    new = timeit_dbg(lambda i: _lib.conv_tc2(srcs(i), dx[i].data_ptr(), C, B, H, W, C))
     report(f"dual dgrad {C} (3x3 + 5x5), plain", fl, new, old)
-    new = timeit(lambda i: _lib.conv_tc2(srcs(i), dx[i].data_ptr(), C, B, H, W, C, flags=_lib.TC2_BNB | _lib.TC2_BNB_RELU | _lib.TC2_AUX_F16,
+    new = timeit_dbg(lambda i: _lib.conv_tc2(srcs(i), dx[i].data_ptr(), C, B, H, W, C, flags=_lib.TC2_BNB | _lib.TC2_BNB_RELU | _lib.TC2_AUX_F16,
                                          aux=y[i].data_ptr(), aux_ld=C, aux_scale=coef[0].data_ptr(), aux_shift=coef[1].data_ptr(),
                                          stat=part.data_ptr(), stat_ld=C))
     report(f"dual dgrad {C} + BN-bwd epilogue", fl, new)
-    new = timeit(lambda i: _lib.conv_tc2(srcs(i), dx[i].data_ptr(), C, B, H, W, C, flags=_lib.TC2_MASK | _lib.TC2_AUX_F16,
+    new = timeit_dbg(lambda i: _lib.conv_tc2(srcs(i), dx[i].data_ptr(), C, B, H, W, C, flags=_lib.TC2_MASK | _lib.TC2_AUX_F16,
                                          aux=y[i].data_ptr(), aux_ld=C, residual=res[i].data_ptr(), res_ld=C))
     report(f"dual dgrad {C} + residual + ReLU mask", fl, new)
