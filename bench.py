@@ -101,11 +101,37 @@ def synthetic_batches(n, B, seed, pin, S=1):
     return out
 
 
+REFERENCE_ROOT = os.environ.get("TACTILESR_REFERENCE", "/root/reference")
+
+
 def cpu_reference_steps(B, steps, warmup, seed=42):
-    """The reference's CPU path (oracle port: PyTorch-CPU arithmetic, stock autograd, Adam) on `steps` batches of B."""
+    """The reference's CPU training step on `steps` batches of B -> (samples/s, threads, kind).  kind "reference": the
+    UNMODIFIED modules of /root/reference (model/tactileSR_model.py + stock torch.optim.Adam), used whenever that tree is
+    mounted (the build container); kind "port": the oracle's restatement of the same ATen / oneDNN calls (the GPU box, where
+    the reference tree does not exist)."""
     import torch
-    from oracle import tactilesr_oracle as so
     torch.set_num_threads(os.cpu_count() or 1)
+    if os.path.exists(os.path.join(REFERENCE_ROOT, "model", "tactileSR_model.py")):
+        sys.path.insert(0, REFERENCE_ROOT)
+        try:
+            from model.tactileSR_model import TactileSR as RefSR      # noqa: E402
+            torch.manual_seed(seed)
+            m = RefSR().train()
+            opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-2)
+            times = []
+            for LR, HR in synthetic_batches(steps + warmup, B, seed + 1, False):
+                t0 = time.perf_counter()
+                HRp = torch.nn.functional.interpolate(HR / 10, size=(40, 40), mode="bilinear", align_corners=False)
+                loss = torch.nn.functional.mse_loss(m(LR), HRp)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                times.append(time.perf_counter() - t0)
+            times = times[warmup:]
+            return B * len(times) / sum(times), torch.get_num_threads(), "reference"
+        finally:
+            sys.path.remove(REFERENCE_ROOT)
+    from oracle import tactilesr_oracle as so
     sd = so.make_state(so.tactilesr_layout(1), seed, nondegenerate=False)
     batches = synthetic_batches(steps + warmup, B, seed + 1, False)
     keys = so.param_keys(sd)
@@ -120,7 +146,7 @@ def cpu_reference_steps(B, steps, warmup, seed=42):
         sd.update(new_stats)
         times.append(time.perf_counter() - t0)
     times = times[warmup:]
-    return B * len(times) / sum(times), torch.get_num_threads()
+    return B * len(times) / sum(times), torch.get_num_threads(), "port"
 
 
 def run_reference(args):
@@ -130,14 +156,14 @@ def run_reference(args):
     B = 32
     # bounded sample: every step is one batch of the reference's own size (0.7 s on 16 cores), at most 20 steps
     steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
-    val, cores = cpu_reference_steps(B, steps, warmup)
+    val, cores, kind = cpu_reference_steps(B, steps, warmup)
     line = {
         "impl": "reference", "metric": "SR train samples/sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 * B / val, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "TactileSR(seqsCnt=1) train step: fwd + HR-prep/MSE + bwd + Adam(lr 1e-3, wd 1e-2), fp32, CPU",
                    "batch_per_step": B, "bounded_sample": f"{steps} steps of the reference's own batch size 32"},
-        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": kind,
                          "sample": f"{steps} train steps of B=32 (reference config/default.py:46) after {warmup} warm-up"},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -146,7 +172,7 @@ def run_reference(args):
 
 
 def time_dominant_kernel(B, reps=10, f16=False):
-    """conv_tc_kernel<128> on the MSRB conv_5_2 shape (128->128, 5x5, 53.7 % of the forward FLOPs): algorithmic FLOPs per
+    """conv_tc2_kernel<128> on the MSRB conv_5_2 shape (128->128, 5x5, 53.7 % of the forward FLOPs): algorithmic FLOPs per
     launch / CUDA-event time on the launching stream."""
     import torch
     from tactilesr_b200 import _lib
@@ -158,10 +184,10 @@ def time_dominant_kernel(B, reps=10, f16=False):
     out = torch.empty(B * 1600, 128, dtype=dt, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     _lib.call("tsr_pack_conv_weight_f16" if f16 else "tsr_pack_conv_weight_bf16", w.data_ptr(), wf.data_ptr(), 0, 128, 128, 5, st)
-    flags = 2 if f16 else 0
+    flags = _lib.TC2_F16 if f16 else 0
 
     def launch():
-        _lib.call("tsr_conv2d_tc", x.data_ptr(), 128, wf.data_ptr(), 0, 0, 0, out.data_ptr(), 128, B, 40, 40, 128, 128, 5, flags, 0, 0, 0, 0, 0, st)
+        _lib.conv_tc2([(x.data_ptr(), 128, 128, 5, wf.data_ptr())], out.data_ptr(), 128, B, 40, 40, 128, flags=flags, stream=st)
     for _ in range(3):
         launch()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -175,6 +201,78 @@ def time_dominant_kernel(B, reps=10, f16=False):
     flops = 2.0 * B * 1600 * 128 * 128 * 25
     return flops / (ms * 1e-3) / 1e12, ms, flops
 
+
+def committed_traffic(B):
+    """DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` summary
+    (profiles/roofline_traffic.json, written by tools/ncu_summary.py from the .ncu-rep of that capture) -- null when this
+    batch size was never captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            rec = json.load(f)
+        e = rec.get(str(B))
+        return (e["dram_read_bytes"] + e["dram_write_bytes"], e["source"]) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+def stock_forward(m, x):
+    """The reference's TactileSR.forward (model/tactileSR_model.py:67-84, MSRB :196-206, ResBlock :222-225) written with
+    stock PyTorch ops over OUR module's parameter holders -- the yardstick "reference arithmetic through ATen / cuDNN on the
+    same GPU".  Measurement only: the product path never calls it."""
+    import torch
+    import torch.nn.functional as F
+
+    def seq(mods, t):
+        for mod in mods:
+            t = mod(t)
+        return t
+
+    def msrb(b, t):
+        i2 = torch.cat([seq(b.conv_3_1, t), seq(b.conv_5_1, t)], 1)
+        i3 = torch.cat([seq(b.conv_3_2, i2), seq(b.conv_5_2, i2)], 1)
+        return F.relu(b.confusion(i3) + t)
+
+    frames = [seq(m.inputLayer_pattern_list[s], x[:, 3 * s:3 * s + 3]) for s in range(m.seqsCnt)]
+    p = seq(m.inputContact_layer, torch.cat(frames, 1))
+    for b in m.patternFeatureExtra_layer:
+        p = msrb(b, p)
+    f = seq(m.input_layer_force, x[:, :3])
+    for b in m.forceFeatureExtra_layer:
+        f = F.relu(f + b.conv2(F.relu(b.conv1(f))))
+    return seq(m.output_layer, torch.cat([f, p], 1))
+
+
+def cudnn_yardstick(dev, timeit):
+    """Stock PyTorch eager / cuDNN running the reference's training step on this GPU (fp32, TF32, autocast bf16) at the
+    reference batch 32 and at 512: the number the hand-written path has to beat on the same hardware."""
+    import torch
+    from tactilesr_b200.model import TactileSR
+    res = {}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for Bc in (32, 512):
+            LR = torch.rand(Bc, 3, 4, 4, device=dev) * 8
+            HR = torch.rand(Bc, 1, 100, 100, device=dev) * 250
+            for tag in ("fp32", "tf32", "autocast_bf16"):
+                torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = tag != "fp32"
+                torch.manual_seed(0)
+                m = TactileSR().to(dev).train()
+                opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-2)
+
+                def step():
+                    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=tag == "autocast_bf16"):
+                        out = stock_forward(m, LR)
+                    HRp = torch.nn.functional.interpolate(HR / 10, size=(40, 40), mode="bilinear", align_corners=False)
+                    loss = torch.nn.functional.mse_loss(out.float(), HRp)
+                    opt.zero_grad()
+                    loss.backward()
+                    opt.step()
+                ms = timeit(step, 4 if Bc == 512 else 10)
+                res[f"{tag}_b{Bc}_samples_per_s"] = Bc / (ms * 1e-3)
+                del m, opt
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return res
 
 
 def measure_extras(dev, model, B):
@@ -222,6 +320,7 @@ def measure_extras(dev, model, B):
         ms = timeit(t32.train_one_iter, 20)
         out["sr_train_b32_cuda_graph_samples_per_s" if use_graph else "sr_train_b32_eager_samples_per_s"] = 32 / (ms * 1e-3)
         del t32, m32, o32
+    out["cudnn_yardstick"] = cudnn_yardstick(dev, timeit)
     # TactileSRCNN (reference model/tactileSR_model.py:101-153; same kernels, different wiring): train step at the same batch
     from tactilesr_b200.functional import mse_hr_loss
     from tactilesr_b200.model import TactileSRCNN
@@ -325,6 +424,9 @@ def run_ours(args):
     _lib.check(_lib.lib().tsr_check_device(), "device check")
     tb.set_precision(args.precision)
     B = args.batch
+    if args.global_batch:                                   # strong scaling: the global batch is fixed, the per-GPU batch shrinks
+        assert args.global_batch % world == 0
+        B = args.global_batch // world
     S = args.seqs                                           # 1 = the headline workload; 7 = the tactileSRSeqs model (C4)
     global FLOP_PER_SAMPLE_TRAIN, FLOP_PER_SAMPLE_FWD
     if S == 7:
@@ -346,7 +448,7 @@ def run_ours(args):
 
     sched = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.8)
     tr = Trainer_tactileSR(sr_config, model=model, optimizer=opt, lr_scheduler=sched, data_loader=Loader(devb),
-                           max_iters=10 ** 9, log_period=10 ** 9, device=dev)
+                           max_iters=10 ** 9, log_period=10 ** 9, device=dev, cuda_graph=args.cuda_graph)
     tr._setup_dp()
 
     def barrier():
@@ -384,6 +486,22 @@ def run_ours(args):
         tr.train_one_iter()
     ms_e2e, _ = timed(tr, args.steps, True)
 
+    # per-kernel-class breakdown of one device-resident step (CUDA events around every op of the layer program)
+    breakdown = None
+    if world == 1:
+        from tactilesr_b200 import engine as E
+        tr._data_iter = iter(Loader(devb))
+        tr.train_one_iter()
+        torch.cuda.synchronize()
+        E.profile_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tr.train_one_iter()
+        e1.record()
+        cls = E.profile_end()
+        breakdown = {k: round(v, 3) for k, v in sorted(cls.items(), key=lambda kv: -kv[1])}
+        breakdown["step_total_with_event_overhead"] = round(e0.elapsed_time(e1), 3)
+
     extras = {}
     if world == 1 and not args.no_extras:
         try:                                  # reported extras must never take the headline line down with them
@@ -409,14 +527,11 @@ def run_ours(args):
     roof = None
     if args.precision in ("bf16", "fp16"):
         tf, kms, kflops = time_dominant_kernel(B, f16=args.precision == "fp16")
-        # DRAM traffic per launch from the committed ncu --set full captures of this kernel
-        # (profiles/r01_conv_tc_pair_5x5_128_b512.txt: read 210.6 MB + write 160.8 MB, algorithmic in+out 419 MB;
-        #  profiles/r01_conv_tc_pair_5x5_128_b1024.txt: read 420.4 MB + write 370.0 MB, algorithmic 840 MB)
-        traffic = {512: 371.39e6, 1024: 790.39e6}.get(B)     # None if this batch size was never captured
-        roof = {"bound": "tensor", "kernel": "conv_tc_pair_kernel<128> (cta_group::2) 5x5 128->128, MSRB conv_5_2 forward shape",
+        traffic, traffic_src = committed_traffic(B)
+        roof = {"bound": "tensor", "kernel": "conv_tc2_kernel<128> (cta_group::2) 5x5 128->128, MSRB conv_5_2 forward shape",
                 "achieved": tf, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": tf / pk["tf_burst"],
                 "peak_source": pk["src"] + " bf16 burst (kernel timed alone)", "ms_per_launch": kms, "flops_per_launch": kflops,
-                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)", "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": B * 1600 * (128 + 128) * 2 + 25 * 128 * 128 * 2}
     else:
         roof = {"bound": "tensor", "kernel": "whole fp32 step (FFMA implicit GEMM; fp32-accurate parity mode)",
@@ -424,25 +539,28 @@ def run_ours(args):
                 "frac": value / world * FLOP_PER_SAMPLE_TRAIN / 1e12 / pk["tf_sust"], "peak_source": pk["src"] + " bf16 sustained", "traffic": None}
     cpu = None
     if world == 1 and not args.no_cpu_baseline and S == 1:
-        v, cores = cpu_reference_steps(32, 12, 1)
-        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": "12 train steps of B=32 (reference batch size, config/default.py:46) after 1 warm-up; oracle port of the reference CPU path"}
+        v, cores, kind = cpu_reference_steps(32, 12, 1)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": kind,
+               "sample": "12 train steps of B=32 (reference batch size, config/default.py:46) after 1 warm-up; "
+                         + ("unmodified reference modules" if kind == "reference" else "oracle port of the reference CPU path")}
     line = {
         "metric": "SR train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.global_batch else "weak",
         "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "fp16", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": {"workload": f"TactileSR(seqsCnt={S}) train step: fwd + fused HR-prep/MSE + bwd + fused Adam(lr 1e-3, wd 1e-2)"
                                + (" + bucketed NCCL grad all-reduce" if world > 1 else ""),
                    "per_gpu_batch": B, "global_batch": B * world, "input": f"LR (B,{3 * S},4,4), HR (B,1,100,100)",
                    "precision_mode": args.precision + {"fp16": " (fp16 activations / forward weights, bf16 gradients, fp32 accumulation and statistics)",
                                                        "bf16": " (bf16 storage, fp32 accumulation and statistics)", "fp32": ""}[args.precision],
-                   "parallelism": f"dp{world}",
+                   "parallelism": f"dp{world}", "cuda_graph": bool(args.cuda_graph),
+                   "grad_allreduce": ("bucketed, overlapped with backward" if os.environ.get("TSR_DP_OVERLAP", "1") != "0" else "one call after backward") if world > 1 else None,
                    "l2": "per-step working set (saved activations, B x ~26-52 MB) >> 126 MB L2; 4 rotating input batches"},
         "tensor_roofline_frac_step": value / world * FLOP_PER_SAMPLE_TRAIN / 1e12 / pk["tf_sust"],
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": B * (3 * S * 16 + 100 * 100) * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "extra": extras,
+        "gpu_launches": launches, "clocks": clocks, "step_breakdown_ms": breakdown, "extra": extras,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -461,6 +579,8 @@ def main():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("TSR_BENCH_BATCH", "1024")))
     ap.add_argument("--seqs", type=int, default=int(os.environ.get("TSR_BENCH_SEQS", "1")), choices=[1, 7],
                     help="frames per sample: 1 = headline workload, 7 = tactileSRSeqs model (BASELINE.json configs[3])")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: fixed global batch, per-GPU batch = this / N")
+    ap.add_argument("--cuda-graph", action="store_true", help="Trainer(cuda_graph=True): replay the iteration as a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()

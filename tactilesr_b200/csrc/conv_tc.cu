@@ -701,19 +701,23 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t tx = (uint32_t)p.P * p.P * 128u * nxt + 8192u * p.cochunks;
+      int st = 0;
+      uint32_t ph = 1;
+      int n = blk0 / p.tiles_per_sample, t = blk0 - n * p.tiles_per_sample;     // running (sample, tile) position
+      int ty = t / p.tiles_x, tx_ = t - ty * p.tiles_x;
       for (int i = 0; i < nblk; ++i) {
-        const int st = i % NS;
-        mbar_wait(empty(st), ((i / NS) & 1) ^ 1);
+        mbar_wait(empty(st), ph);
         mbar_expect_tx(full(st), tx);
-        const int b = blk0 + i;
-        const int n = b / p.tiles_per_sample, t = b - n * p.tiles_per_sample;
-        const int y0 = (t / p.tiles_x) * 8, x0 = (t % p.tiles_x) * 8;
+        const int y0 = ty * 8, x0 = tx_ * 8;
         const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
         for (int cc = 0; cc < p.cochunks; ++cc)
           tma_load_4d(dy0 + (uint32_t)cc * 8192u, &tmap_dy, (int)blockIdx.z * p.Cout + cc * 64, x0, y0, n, full(st));
         for (int h = 0; h < nxt; ++h)
           tma_load_4d(dy0 + (uint32_t)p.dy_stage_bytes + (uint32_t)h * p.xtile_bytes, &tmap_x, (unit * nxt + h) * 64,
                       x0 - p.pad, y0 - p.pad, n, full(st));
+        if (++st == NS) { st = 0; ph ^= 1u; }
+        if (++tx_ == p.tiles_x) { tx_ = 0; ++ty; }
+        if (++t == p.tiles_per_sample) { t = 0; ty = 0; tx_ = 0; ++n; }
       }
     }
   } else if (warp == 1) {
@@ -740,14 +744,15 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
       gword[g] = w;
     }
+    // (the single issuing lane is the critical path for the 64-channel layers -- 32 N = 64 MMAs per 64-pixel stage: ring
+    // position, barrier addresses and descriptor bases advance by adds, no division in the loop)
     uint32_t first = 0u;
+    const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4, row2 = 2u * row_units, Cout = (uint32_t)p.Cout;
+    const uint32_t xs_lo0 = desc_lo(base + (uint32_t)p.dy_stage_bytes, 0u), b_lo0 = desc_lo(base, lbo_b);
+    uint32_t st = 0, ph = 0, xs_lo = xs_lo0, b_lo = b_lo0, full_bar = full(0), empty_bar = empty(0);
     for (int i = 0; i < nblk; ++i) {
-      const int st = i % NS;
-      mbar_wait(full(st), (i / NS) & 1);
+      mbar_wait(full_bar, ph);
       tc_fence_after();
-      const uint32_t dy0 = base + st * (uint32_t)p.stage_bytes;
-      const uint32_t xs_lo = desc_lo(dy0 + (uint32_t)p.dy_stage_bytes, 0u);
-      const uint32_t b_lo = desc_lo(dy0, lbo_b);
       if (elect_one()) {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -755,14 +760,16 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const uint32_t a_lo = xs_lo + gword[g];
 #pragma unroll
             for (int s = 0; s < 4; ++s)
-              umma_bf16(tmem_base + g * p.Cout, desc_join(a_lo + s * 2u * row_units, a_hi),
+              umma_bf16(tmem_base + g * Cout, desc_join(a_lo + s * row2, a_hi),
                         desc_join(b_lo + s * 128u, b_hi), idesc, (first | (uint32_t)s) ? 1u : 0u);
           }
         }
-        umma_commit(empty(st));
+        umma_commit(empty_bar);
       }
       __syncwarp();
       first = 1u;
+      xs_lo += stage_units; b_lo += stage_units; full_bar += 8u; empty_bar += 8u;
+      if (++st == (uint32_t)NS) { st = 0; ph ^= 1u; xs_lo = xs_lo0; b_lo = b_lo0; full_bar = full(0); empty_bar = empty(0); }
     }
     if (elect_one()) umma_commit(tmem_full);
     __syncwarp();

@@ -38,6 +38,33 @@ constexpr int T2_MAX_TAPS = 25;
 
 // flags (public: TSR_TC2_* in include/tactilesr_b200.h)
 constexpr int F_RELU = 1, F_F16 = 2, F_MASK = 8, F_BNB = 16, F_BNB_RELU = 32, F_AUX_F16 = 64, F_STAT_PRECLEARED = 128;
+// internal (set by the launcher from pointer / stride alignment): 32-byte vector access of the pixel rows.  A thread owns
+// 16 consecutive channels = 32 B of a pixel row; as two 16-byte stores every sector is written in two halves by two
+// instructions, as ONE 256-bit store (sm_100: st.global.v8) it is a full-sector write -- the epilogue-bound 1x1 shapes are
+// limited by exactly this traffic.
+constexpr int F_OUT256 = 1 << 16, F_RES256 = 1 << 17, F_AUX256 = 1 << 18, F_OUT2_256 = 1 << 19;
+
+__device__ __forceinline__ void st_row32(void* ptr, const uint32_t (&o)[8], bool v256) {
+  if (v256) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+                 "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                 : "memory");
+  } else {
+    uint4* op = reinterpret_cast<uint4*>(ptr);
+    op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+__device__ __forceinline__ void ld_row32(const void* ptr, uint4 (&r)[2], bool v256) {
+  if (v256) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0].x), "=r"(r[0].y), "=r"(r[0].z), "=r"(r[0].w), "=r"(r[1].x), "=r"(r[1].y), "=r"(r[1].z), "=r"(r[1].w)
+                 : "l"(ptr));
+  } else {
+    const uint4* rp = reinterpret_cast<const uint4*>(ptr);
+    r[0] = rp[0]; r[1] = rp[1];
+  }
+}
 
 struct Seg {
   int nchunks, ntaps, pad, P, rows, chunk_wrows, amap;
@@ -155,9 +182,7 @@ __device__ __forceinline__ void epilogue_px(const P2& p, const uint32_t (&v)[16]
       o[k] = *reinterpret_cast<const uint32_t*>(&h);
     }
   }
-  uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + pm * p.out_ld + ch);
-  op[0] = make_uint4(o[0], o[1], o[2], o[3]);
-  op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  st_row32(reinterpret_cast<uint16_t*>(p.out) + pm * p.out_ld + ch, o, (flags & F_OUT256) != 0);
   if (p.out2) {
     uint32_t o2[8];
 #pragma unroll
@@ -165,9 +190,7 @@ __device__ __forceinline__ void epilogue_px(const P2& p, const uint32_t (&v)[16]
       const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
       o2[k] = *reinterpret_cast<const uint32_t*>(&h);
     }
-    uint4* op2 = reinterpret_cast<uint4*>(p.out2 + pm * p.out2_ld + ch);
-    op2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
-    op2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
+    st_row32(p.out2 + pm * p.out2_ld + ch, o2, (flags & F_OUT2_256) != 0);
   }
   if (p.stat) {
     // statistics of the STORED (rounded) values: what every later pass over the tensor reads
@@ -199,14 +222,8 @@ __device__ __forceinline__ void epilogue2(const P2& p, uint32_t acc, int col0, b
   // request the residual / aux vectors of pixel pm, columns ch.. (consumed one step later)
   auto prefetch = [&](bool vm, long long pm, int ch, uint4 (&r)[2], uint4 (&a)[2]) {
     if (!vm) return;
-    if (has_res) {
-      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + pm * p.res_ld + ch);
-      r[0] = rp[0]; r[1] = rp[1];
-    }
-    if (has_aux) {
-      const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.aux) + pm * p.aux_ld + ch);
-      a[0] = ap[0]; a[1] = ap[1];
-    }
+    if (has_res) ld_row32(reinterpret_cast<const uint16_t*>(p.residual) + pm * p.res_ld + ch, r, (p.flags & F_RES256) != 0);
+    if (has_aux) ld_row32(reinterpret_cast<const uint16_t*>(p.aux) + pm * p.aux_ld + ch, a, (p.flags & F_AUX256) != 0);
   };
   prefetch(v0, p0, nofs + col0, r0, a0);
   prefetch(v1, p1, nofs + col0, r1, a1);
@@ -757,7 +774,11 @@ static int conv2d_tc2_cols(const ConvTc2& a, int cout_total, int n0, cudaStream_
   p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.out2 = (__nv_bfloat16*)a.out2_bf16; p.stat = a.stat;
   p.aux = a.aux; p.aux_sc = a.aux_scale; p.aux_sh = a.aux_shift;
   p.res_ld = a.res_ld; p.out_ld = a.out_ld; p.out2_ld = a.out2_ld; p.stat_ld = a.stat_ld; p.aux_ld = a.aux_ld;
-  p.flags = fl;
+  p.flags = fl & 0xFFFF;
+  if (((uintptr_t)a.out & 31) == 0 && a.out_ld % 16 == 0) p.flags |= F_OUT256;
+  if (a.residual && ((uintptr_t)a.residual & 31) == 0 && a.res_ld % 16 == 0) p.flags |= F_RES256;
+  if (a.aux && ((uintptr_t)a.aux & 31) == 0 && a.aux_ld % 16 == 0) p.flags |= F_AUX256;
+  if (a.out2_bf16 && ((uintptr_t)a.out2_bf16 & 31) == 0 && a.out2_ld % 16 == 0) p.flags |= F_OUT2_256;
   p.dbg = g_tc2_dbg;
   p.ovf = (fl & F_F16) ? tsr_f16_overflow_ptr() : nullptr;
   return NACC == 128 ? launch_tc2<128>(am, wm, p, a.dual_fwd != 0, stream) : launch_tc2<64>(am, wm, p, a.dual_fwd != 0, stream);

@@ -70,6 +70,41 @@ def bump_weight_epoch() -> None:
     _WEIGHT_EPOCH += 1
 
 
+# ---------------------------------------------------------------------------------------------
+# optional per-kernel-class timing (bench.py: step_breakdown_ms); off by default, no cost when off
+# ---------------------------------------------------------------------------------------------
+_PROF: Optional[Dict[str, list]] = None
+
+
+def profile_begin() -> None:
+    global _PROF
+    _PROF = {}
+
+
+def profile_end() -> Dict[str, float]:
+    """Milliseconds per kernel class since profile_begin() (CUDA events on the launching stream)."""
+    global _PROF
+    rec, _PROF = _PROF, None
+    torch.cuda.synchronize()
+    return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in (rec or {}).items()}
+
+
+class _prof:
+    def __init__(self, key: str):
+        self.key = key
+
+    def __enter__(self):
+        if _PROF is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if _PROF is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _PROF.setdefault(self.key, []).append((self.e0, e1))
+
+
 def _ptr(t: Optional[torch.Tensor]) -> int:
     return 0 if t is None else t.data_ptr()
 
@@ -576,6 +611,10 @@ class ConvOp(Op):
                 raise NotImplementedError("residual gradient accumulation after another writer")
 
     def bwd_weights(self, c):
+        with _prof("bwd:wgrad"):
+            self._bwd_weights(c)
+
+    def _bwd_weights(self, c):
         st = _lib.stream_ptr()
         gp, gld = c.vptr(self.out, grad=True)
         g, acc = c.pgrad(self.conv.weight)
@@ -606,6 +645,11 @@ class ConvOp(Op):
 
 
 def _dgrad(c: RunCtx, ops: List[ConvOp], sink: Optional[Sink]) -> None:
+    with _prof("bwd:dgrad"):
+        _dgrad_impl(c, ops, sink)
+
+
+def _dgrad_impl(c: RunCtx, ops: List[ConvOp], sink: Optional[Sink]) -> None:
     """Data gradient of one convolution, or of two convolutions that read the same view (their contributions are
     K-concatenated into ONE tensor-core launch), into the gradient of ``ops[0].src`` -- adding to what earlier writers
     left there (through the epilogue's residual input) and applying the buffer's Sink when this is its last writer."""
@@ -1008,7 +1052,8 @@ def run_forward(prog: Program, x: torch.Tensor, training: bool, need_grad: bool,
             for b in op.reads():
                 last_use[b] = i
     for i, op in enumerate(prog.ops):
-        op.fwd(c)
+        with _prof("fwd:" + type(op).__name__):
+            op.fwd(c)
         if not keep:
             for b in op.reads():
                 if last_use.get(b) == i and b is not prog.out:
@@ -1039,7 +1084,11 @@ def run_backward(prog: Program, c: RunCtx, dout: torch.Tensor, hooks=None) -> Di
         needed = [b for b in op.writes()]
         if any(b not in c.grads for b in needed):
             continue   # dead branch (no gradient reaches this op)
-        op.bwd(c)
+        if isinstance(op, (ConvOp, DualConvOp)):
+            op.bwd(c)                      # (timed inside: bwd:wgrad / bwd:dgrad; the rest is ReLU / residual hand-over)
+        else:
+            with _prof("bwd:" + type(op).__name__):
+                op.bwd(c)
         if hooks is not None:
             hooks(i, op, c)
         for b in needed:

@@ -109,7 +109,7 @@ def test_sr_1k_step_loss_curve_matches_reference_arithmetic():
         tb.check_fp16_overflow()
     finally:
         tb.set_precision("fp32")
-    _compare("TactileSR", got, ref, mean_tol=0.05, max_tol=0.30)
+    _compare("TactileSR", got, ref, mean_tol=0.02, max_tol=0.10)        # measured on B200: 0.45 % / 2.8 %
 
 
 yy, xx = torch.meshgrid(torch.arange(100.0), torch.arange(100.0), indexing="ij")
@@ -182,5 +182,5 @@ def test_joint_c5_loss_curves_match_reference_arithmetic():
         got_p, got_s = torch.stack(got_p).cpu().numpy(), torch.stack(got_s).cpu().numpy()
     finally:
         tb.set_precision("fp32")
-    _compare("C5 tPSFNet", got_p, ref_p, mean_tol=0.02, max_tol=0.10)
-    _compare("C5 TactileSR", got_s, ref_s, mean_tol=0.05, max_tol=0.30)
+    _compare("C5 tPSFNet", got_p, ref_p, mean_tol=0.005, max_tol=0.02)      # measured: 0.01 % / 0.05 %
+    _compare("C5 TactileSR", got_s, ref_s, mean_tol=0.02, max_tol=0.08)     # measured: 0.13 % / 0.54 %

@@ -123,10 +123,26 @@ def test_srcnn_forward_backward(mode, tol_out, tol_grad):
             _, ref_err = summary_close(ref32, want, 1.0)
             _, err = summary_close(summarize(p.grad), want, 1.0)
             assert err[0] < max(tol_grad, 6 * ref_err[0]), (n, err, ref_err)
+        # two whole gradient tensors: the last layer and the first (three BatchNorm backward passes and six MSRBs upstream).
+        # In the fp16 mode gradients are bf16 tensors; the yardstick there is what stock PyTorch autocast(bf16) -- the
+        # reference stack's own reduced-precision mode -- gets on the same weights on this GPU, as in tests/test_sr_bf16_gpu.py
+        yard = {}
+        if mode != "fp32":
+            sd = so.make_state(so.tactilesrcnn_layout(), int(g["seed_w"]))
+            keys = set(so.param_keys(sd))
+            leaf = {k: v.cuda().requires_grad_(k in keys) for k, v in sd.items()}
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                o = so.tactilesrcnn_forward(leaf, LR.cuda(), True)
+            l = torch.mean((o.float() - so.prep_hr(HR_raw.cuda(), 10.0, 40)) ** 2)
+            l.backward()
+            yard = {"output.0.weight": rel_l2(leaf["output.0.weight"].grad, g["f64/grad_output_w"]),
+                    "input_zyx.0.weight": rel_l2(leaf["input_zyx.0.weight"].grad, g["f64/grad_in0_w"])}
         for name, key in (("output.0.weight", "grad_output_w"), ("input_zyx.0.weight", "grad_in0_w")):
             got = dict(m.named_parameters())[name].grad
             ref_err = rel_l2(g[f"f32/{key}"], g[f"f64/{key}"])
-            assert rel_l2(got, g[f"f64/{key}"]) < max(tol_grad, 6 * ref_err), (name, rel_l2(got, g[f"f64/{key}"]), ref_err)
+            e = rel_l2(got, g[f"f64/{key}"])
+            print(f"TactileSRCNN {mode} {name}: grad rel-L2 {e:.3e} (reference fp32 {ref_err:.1e}, autocast-bf16 yardstick {yard.get(name, float('nan')):.3e})")
+            assert e < max(tol_grad, 6 * ref_err, 1.5 * yard.get(name, 0.0)), (name, e, ref_err, yard)
     finally:
         tb.set_precision("fp32")
 

@@ -50,6 +50,16 @@ elif case in ("fwd3x3_128", "fwd3x3_64"):
     else:
         fn = lambda: _lib.call("tsr_conv2d_tc", x.data_ptr(), C, wf.data_ptr(), bias.data_ptr(), 0, 0, out.data_ptr(), C, B, H, W, C, C, 3, 2,
                                0, 0, part.data_ptr(), 0, 0, st)
+elif case.startswith("wgrad"):          # wgrad5x5_128 | wgrad3x3_128 | wgrad5x5_64 | wgrad3x3_64
+    KS = int(case[5])
+    C = int(case.split("_")[1])
+    x = torch.randn(B, H, W, C, device=dev).to(bf)
+    dy = torch.randn(B, H, W, C, device=dev).to(bf)
+    need = L.tsr_conv2d_wgrad_tc_workspace(B, H, W, C, C, KS)
+    ws = torch.empty(max(int(need), 256), dtype=torch.uint8, device=dev)
+    dw = torch.zeros(C, C, KS, KS, device=dev)
+    fn = lambda: _lib.call("tsr_conv2d_wgrad_tc", x.data_ptr(), C, dy.data_ptr(), C, dw.data_ptr(), ws.data_ptr(), ws.numel(), B, H, W,
+                           C, C, KS, 0, st)
 else:
     raise SystemExit("unknown case")
 for _ in range(3):
