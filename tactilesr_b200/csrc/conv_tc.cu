@@ -1,23 +1,9 @@
-// Tensor-core convolution for sm_100a: implicit GEMM on tcgen05.mma with TMEM accumulators, activation
-// halo tiles staged once per CTA by TMA (zero-filled padding), weights streamed through an mbarrier ring
-// by bulk copies.  bf16 operands, fp32 accumulation.
+// Tensor-core support kernels for sm_100a: weight packing into the SWIZZLE_128B shared-memory image and the weight gradient
+// (wgrad_tc3_kernel: tcgen05.mma with both operands MN-major, accumulators in TMEM over the CTA's whole pixel range,
+// deterministic two-level reduction).  The forward / data-gradient implicit GEMM lives in conv_tc2.cu.
 //
-//   out[p][co] = epilogue( sum_{tap, ci} in[p + shift(tap)][ci] * w[tap][ci][co] )
-//
-// Work decomposition ("tall plane"): the B samples are stacked vertically with `pad` virtual zero rows
-// after each sample (pitch Hp = H + pad), so a CTA block is simply TM/8 consecutive virtual rows x 8
-// columns = T M-tiles of 128 pixels, and every tap is a pure (row, column) shift inside one shared-memory
-// halo tile.  The A operand of each MMA is a *window* of that halo tile: the UMMA shared-memory descriptor
-// starts at row (ky*P + kx) of the tile, 8-row core groups are P*128 B apart (P = 16-pixel pitch), so no
-// im2col copy is ever materialised and each activation byte is read from L2 once per CTA instead of once
-// per tap.  The B operand (weights, pre-swizzled on the host side into the SWIZZLE_128B image) is streamed
-// per (channel chunk, tap) with cp.async.bulk.
-//
-// Warp roles (7 warps): 0 = A/TMA producer, 1 = MMA issuer + TMEM owner, 2 = B producer, 3..6 = epilogue
-// (TMEM -> registers -> bias / residual / ReLU -> bf16 global stores).
-//
-// Replaces the cuDNN dispatch behind nn.Conv2d for the channel-heavy convs of reference
-// model/tactileSR_model.py:41,47,53,168,174,180,186,191,219,220 (forward) and their data gradients.
+// Replaces the cuDNN dispatch behind the weight gradient of nn.Conv2d (reference model/tactileSR_model.py:41,47,53,168,
+// 174,180,186,191,219,220 through autograd, cpu/trainer.py:353).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <cuda.h>
@@ -25,534 +11,12 @@
 
 namespace {
 
-constexpr int FLAG_RELU = 1;
-constexpr int FLAG_F16 = 2;          // activations / weights / residual / output are fp16 instead of bf16
-constexpr int T_TILES = 2;          // M-tiles (128 pixels each) per CTA
-constexpr int MAX_NA = 8;           // activation chunk slots (2 for 3x3 / 5x5, more for the bandwidth-bound 1x1)
 constexpr int NUM_THREADS = 224;
-constexpr int STAT_ROWS = 148 * 4;  // rows of the fused BatchNorm-statistics partials: (CTA, epilogue warp)
 
-// experiment switches (env TSR_TC_MODE or tsr_set_tc_desc_mode): bit1 = 16-pixel halo pitch in the forward kernel
-// instead of the dense TMA-box pitch, bit4 = single-CTA (cta_group::1) forward kernel also for N = 128, bit5 = the same
-// for N = 64,
-// bit7 = (engine) BatchNorm statistics in a separate pass instead of the conv epilogue.
+// experiment switches (env TSR_TC_MODE or tsr_set_tc_desc_mode), read by the engine: bit 7 = BatchNorm statistics in a separate
+// pass instead of the conv epilogue, bit 8 = no fused gradient sinks, bit 9 = no dual-branch forward.
 static int env_mode() { const char* e = getenv("TSR_TC_MODE"); return e ? atoi(e) : 0; }
 int g_desc_mode = env_mode();
-
-struct ConvParams {
-  const __nv_bfloat16* w;        // pre-swizzled [chunk][tap][Cout_total][64]
-  const float* bias;             // [N] or null
-  const __nv_bfloat16* residual; // [pix][res_ld] or null
-  __nv_bfloat16* out;            // [pix][out_ld]
-  int res_ld, out_ld;
-  int B, H, W, Hp, Vtotal;       // Hp = H + pad, Vtotal = B * Hp
-  int KS, pad, P, rows;          // P = smem pixel pitch of a halo row, rows = 16*T + 2*pad
-  int nchunks, nxg, flags;
-  int w_tile_elems;              // elements between consecutive (chunk, tap) weight tiles = Cout_total * 64
-  int nblocks, nb_stages;        // CTA blocks (persistent loop), depth of the weight ring (<= MAX_NB)
-  int na_slots;                  // activation chunk slots (<= MAX_NA)
-  __nv_bfloat16* out2;           // optional second, bf16 copy of an fp16 output [pix][out2_ld] (weight-gradient operand of
-  int out2_ld;                   // the "fp16" precision mode), else null
-  float* bn_partial;             // optional [STAT_ROWS][2][bn_C] per-(CTA, epilogue warp) sums / sums of squares of the
-  int bn_C;                      // stored output (BatchNorm batch statistics fused into the epilogue), else null
-  int ngroups;                   // pair kernel: output-channel groups of N handled by ONE launch (wide layers: the blocks
-                                 // of all groups share the grid instead of ngroups launches of a few blocks each)
-};
-
-constexpr int MAX_NB = 8;
-
-
-// Sum over the 32 lanes of a warp of 16 values per lane with 16 shuffles: every exchange halves the values a lane
-// carries; lane l ends with the warp sum of value (l >> 1).
-__device__ __forceinline__ float transpose_reduce16(float (&p)[16], int lane) {
-#pragma unroll
-  for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
-    const bool up = (lane & bit) != 0;
-#pragma unroll
-    for (int k = 0; k < w; ++k) {
-      const float keep = up ? p[k + w] : p[k], send = up ? p[k] : p[k + w];
-      p[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-    }
-  }
-  return p[0] + __shfl_xor_sync(0xffffffffu, p[0], 1);
-}
-
-// BatchNorm batch statistics of the stored (rounded) outputs: every epilogue lane adds the 16 channels o[8] of its pixel
-// into per-lane sums (sv) and sums of squares (sq); once per block and channel chunk the warp reduces them over its 32
-// pixels and adds the result to row `row` of the partial table.  Every (row, channel) address is updated by exactly one
-// lane of one warp, in program order => deterministic although it is a reduction instruction.
-__device__ __forceinline__ void bn_stats_add(const uint32_t (&o)[8], bool valid, bool f16, float (&sv)[16], float (&sq)[16]) {
-  if (!valid) return;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float2 t;
-    if (f16) t = __half22float2(*reinterpret_cast<const __half2*>(&o[k]));
-    else t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o[k]));
-    sv[2 * k] += t.x; sv[2 * k + 1] += t.y;
-    sq[2 * k] = fmaf(t.x, t.x, sq[2 * k]); sq[2 * k + 1] = fmaf(t.y, t.y, sq[2 * k + 1]);
-  }
-}
-__device__ __forceinline__ void bn_stats_flush(float (&sv)[16], float (&sq)[16], float* __restrict__ part, int C, int row,
-                                               int col0, int lane) {
-  const float s = transpose_reduce16(sv, lane), ss = transpose_reduce16(sq, lane);
-  if ((lane & 1) == 0) {
-    const int c = col0 + (lane >> 1);
-    atomicAdd(part + ((size_t)row * 2 + 0) * C + c, s);
-    atomicAdd(part + ((size_t)row * 2 + 1) * C + c, ss);
-  }
-}
-
-// Epilogue of one block (T_TILES M-tiles of 128 pixels, N output channels) for the epilogue warp that owns TMEM lanes
-// acc0 >> 16 ..+31: TMEM -> registers -> + bias, + residual, ReLU -> 16-bit -> 16-byte stores (+ the optional bf16 copy).
-// Channel chunks are the outer loop so that the BatchNorm statistics of a chunk are reduced across the warp once per
-// block, not once per M-tile (the reduction is as long as the rest of the chunk's epilogue).
-template <int N>
-__device__ __forceinline__ void epilogue_block(const ConvParams& p, uint32_t acc0, const bool (&valid)[T_TILES],
-                                               const long long (&pix)[T_TILES], int stat_row, int lane, int nofs = 0) {
-  const bool f16 = (p.flags & FLAG_F16) != 0;
-#pragma unroll 1
-  for (int j = 0; j < N / 16; ++j) {
-    float sv[16], sq[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { sv[k] = 0.f; sq[k] = 0.f; }
-#pragma unroll
-    for (int mt = 0; mt < T_TILES; ++mt) {
-      uint32_t v[16];
-      tmem_ld16(acc0 + mt * N + j * 16, v);
-      tmem_ld_wait();
-      if (valid[mt]) {
-        float f[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
-        if (p.bias) {
-#pragma unroll
-          for (int k = 0; k < 16; k += 4) {
-            float4 bv = *reinterpret_cast<const float4*>(p.bias + nofs + j * 16 + k);
-            f[k] += bv.x; f[k + 1] += bv.y; f[k + 2] += bv.z; f[k + 3] += bv.w;
-          }
-        }
-        if (p.residual) {
-          const __nv_bfloat16* rp = p.residual + pix[mt] * p.res_ld + nofs + j * 16;
-#pragma unroll
-          for (int k = 0; k < 16; k += 4) {
-            float4 rv = f16 ? ld4(reinterpret_cast<const __half*>(rp) + k) : ld4(rp + k);
-            f[k] += rv.x; f[k + 1] += rv.y; f[k + 2] += rv.z; f[k + 3] += rv.w;
-          }
-        }
-        if (p.flags & FLAG_RELU) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
-        }
-        uint32_t o[8];
-        if (f16) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
-            o[k] = *reinterpret_cast<uint32_t*>(&h);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-            o[k] = *reinterpret_cast<uint32_t*>(&h);
-          }
-        }
-        uint4* op = reinterpret_cast<uint4*>(p.out + pix[mt] * p.out_ld + nofs + j * 16);
-        op[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        op[1] = make_uint4(o[4], o[5], o[6], o[7]);
-        if (p.out2) {
-          uint32_t o2[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-            o2[k] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          uint4* op2 = reinterpret_cast<uint4*>(p.out2 + pix[mt] * p.out2_ld + nofs + j * 16);
-          op2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
-          op2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
-        }
-        if (p.bn_partial) bn_stats_add(o, true, f16, sv, sq);
-      }
-    }
-    if (p.bn_partial)      // (warp-uniform: all 32 lanes take part in the shuffles)
-      bn_stats_flush(sv, sq, p.bn_partial, p.bn_C, stat_row, nofs + j * 16, lane);
-  }
-}
-
-// Persistent: gridDim.x CTAs (one per SM) stride over the blocks.  The activation-chunk ring, the weight ring and the
-// two TMEM accumulator buffers all run on global counters, so the TMA producers prefetch the next block's halo while
-// the current block is still in its main loop and the epilogue of block i overlaps the MMAs of block i+1.
-template <int N>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_slot_bytes = ((uint32_t)p.rows * p.P * 128u + 1023u) & ~1023u;
-  const uint32_t a_base = base;
-  const int NA_SLOTS = p.na_slots;
-  const uint32_t b_base = a_base + NA_SLOTS * a_slot_bytes;
-  constexpr uint32_t B_STAGE = N * 128u;
-  const int NB = p.nb_stages;
-  const uint32_t bar_base = b_base + NB * B_STAGE;
-  auto a_full = [&](int i) { return bar_base + 8u * i; };
-  auto a_empty = [&](int i) { return bar_base + 8u * (MAX_NA + i); };
-  auto b_full = [&](int i) { return bar_base + 8u * (2 * MAX_NA + i); };
-  auto b_empty = [&](int i) { return bar_base + 8u * (2 * MAX_NA + MAX_NB + i); };
-  auto t_full = [&](int i) { return bar_base + 8u * (2 * MAX_NA + 2 * MAX_NB + i); };
-  auto t_empty = [&](int i) { return bar_base + 8u * (2 * MAX_NA + 2 * MAX_NB + 2 + i); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_NA + 2 * MAX_NB + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int taps = p.KS * p.KS;
-  constexpr uint32_t ACC_COLS = T_TILES * N;      // one accumulator buffer
-  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;    // 256 or 512
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NA_SLOTS; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < NB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 4); }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if (warp == 0) {
-    // ===== A producer: one TMA box (64 ch x (8+2pad) px x 1 row) per virtual halo row, issued by all 32 lanes in
-    // parallel (a single lane issuing 36 boxes per chunk was the bottleneck of the short 64-channel main loops);
-    // the 1x1 conv has no halo and its rows are contiguous across samples, so one 32-row box per chunk suffices =====
-    {
-      const uint32_t row_bytes = (uint32_t)(8 + 2 * p.pad) * 128u;
-      int ac = 0;
-      for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x) {
-        const int xg = blk % p.nxg, vb = blk / p.nxg;
-        const int x0 = xg * 8, v0 = vb * (16 * T_TILES);
-        for (int c = 0; c < p.nchunks; ++c, ++ac) {
-          const int slot = ac % NA_SLOTS;
-          const uint32_t dst0 = a_base + slot * a_slot_bytes;
-          if (lane == 0) {
-            mbar_wait(a_empty(slot), ((ac / NA_SLOTS) & 1) ^ 1);
-            mbar_expect_tx(a_full(slot), row_bytes * p.rows);
-          }
-          __syncwarp();
-          if (p.pad == 0) {
-            if (lane == 0) tma_load_4d(dst0, &tmap, c * 64, x0, v0, 0, a_full(slot));
-          } else {
-            for (int r = lane; r < p.rows; r += 32) {
-              const int vr = v0 - p.pad + r;
-              int n = 0, y = p.H;   // out-of-bounds row => TMA zero fill
-              if (vr >= 0 && vr < p.Vtotal) { n = vr / p.Hp; y = vr - n * p.Hp; }
-              tma_load_4d(dst0 + (uint32_t)r * p.P * 128u, &tmap, c * 64, x0 - p.pad, y, n, a_full(slot));
-            }
-          }
-          __syncwarp();
-        }
-      }
-    }
-  } else if (warp == 2) {
-    // ===== B producer: one pre-swizzled [N][64] weight tile per (chunk, tap), same sequence for every block =====
-    if (lane == 0) {
-      const int per_block = p.nchunks * taps;
-      int it = 0;
-      for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x) {
-        for (int k = 0; k < per_block; ++k, ++it) {
-          const int st = it % NB;
-          mbar_wait(b_empty(st), ((it / NB) & 1) ^ 1);
-          mbar_expect_tx(b_full(st), B_STAGE);
-          bulk_load(b_base + st * B_STAGE, p.w + (size_t)k * p.w_tile_elems, B_STAGE, b_full(st));
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer: the whole warp runs the loop converged (keeps the address math in uniform registers);
-    // one elected lane issues the tcgen05 instructions =====
-    {
-      const int bf = (p.flags & FLAG_F16) ? 0 : 1;
-      const uint32_t idesc = make_idesc(128, N, 0, 0, bf, bf);
-      const uint32_t a_hi = desc_hi((uint32_t)p.P * 128u), b_hi = desc_hi(1024u);
-      const uint32_t row_units = (uint32_t)p.P * 8u;            // one halo row, in 16-byte descriptor units
-      const uint32_t mt_units = 16u * row_units;                 // next M-tile = 16 halo rows further
-      const uint32_t wrap_units = row_units - (uint32_t)p.KS * 8u;
-      int it = 0, ac = 0, lb = 0;
-      for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x, ++lb) {
-        const int buf = lb & 1;
-        mbar_wait(t_empty(buf), ((lb >> 1) & 1) ^ 1);     // epilogue has drained this accumulator buffer
-        tc_fence_after();
-        const uint32_t acc0 = tmem_base + buf * ACC_COLS;
-        uint32_t first = 0u;                              // 0 only for the very first MMA of the block
-        for (int c = 0; c < p.nchunks; ++c, ++ac) {
-          const int slot = ac % NA_SLOTS;
-          mbar_wait(a_full(slot), (ac / NA_SLOTS) & 1);
-          tc_fence_after();
-          uint32_t a_lo = desc_lo(a_base + slot * a_slot_bytes, 16u);   // window start of tap (0,0), M-tile 0
-          int kx = 0;
-          for (int t = 0; t < taps; ++t, ++it) {
-            const int st = it % NB;
-            mbar_wait(b_full(st), (it / NB) & 1);
-            tc_fence_after();
-            const uint32_t b_lo = desc_lo(b_base + st * B_STAGE, 16u);
-            if (elect_one()) {
-#pragma unroll
-              for (int mt = 0; mt < T_TILES; ++mt) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  umma_bf16(acc0 + mt * N, desc_join(a_lo + mt * mt_units + kk * 2u, a_hi), desc_join(b_lo + kk * 2u, b_hi),
-                            idesc, (first | (uint32_t)kk) ? 1u : 0u);
-                }
-              }
-              umma_commit(b_empty(st));
-            }
-            __syncwarp();
-            first = 1u;
-            // next tap: one pixel to the right, or wrap to the start of the next halo row
-            a_lo += 8u;
-            if (++kx == p.KS) { kx = 0; a_lo += wrap_units; }
-          }
-          if (elect_one()) umma_commit(a_empty(slot));
-          __syncwarp();
-        }
-        if (elect_one()) umma_commit(t_full(buf));
-        __syncwarp();
-      }
-    }
-  } else {
-    // ===== epilogue: warps 3..6 own TMEM lanes 32*(warp%4).. =====
-    const int q = warp & 3;
-    const int r = q * 32 + lane;          // accumulator row = pixel within the M-tile
-    const int wx = r & 7, vrow = r >> 3;
-    int lb = 0;
-    for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x, ++lb) {
-      const int buf = lb & 1;
-      const int xg = blk % p.nxg, vb = blk / p.nxg;
-      const int x0 = xg * 8, v0 = vb * (16 * T_TILES);
-      mbar_wait(t_full(buf), (lb >> 1) & 1);
-      tc_fence_after();
-      const uint32_t acc0 = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
-      bool valid[T_TILES];
-      long long pix[T_TILES];
-#pragma unroll
-      for (int mt = 0; mt < T_TILES; ++mt) {
-        const int vr = v0 + mt * 16 + vrow;
-        const int n = vr / p.Hp, y = vr - n * p.Hp;
-        valid[mt] = vr < p.Vtotal && y < p.H;
-        pix[mt] = ((long long)n * p.H + y) * p.W + x0 + wx;
-      }
-      epilogue_block<N>(p, acc0, valid, pix, (int)blockIdx.x * 4 + q, lane);
-      // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty(buf));
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// CTA-pair variant (cta_group::2) of the forward kernel for N = 128: two CTAs of one cluster (adjacent SMs of a TPC)
-// each own one block (their own halo tile and their own 128 TMEM lanes per M-tile); the 128x64 weight tile is split
-// between them (64 rows each, same shared-memory offset) and ONE tcgen05.mma.cta_group::2 of the leader CTA (M = 256)
-// drives both tensor cores.  Per SM and MMA this reads 4 KB of A + 2 KB of B from shared memory (96 B/clk instead of
-// the 128 B/clk that saturate the shared-memory port with cta_group::1) and halves the weight traffic from L2.
-// Protocol (as in the canonical 2-SM GEMM): both CTAs' TMA loads complete on the LEADER's "full" barriers
-// (.cta_group::2, peer bit of the barrier address cleared; leader arrives with expect_tx of both halves, the peer
-// arrives remotely without tx); tcgen05.commit multicasts "empty"/"accumulator ready" to both CTAs; both epilogues
-// arrive (remotely for the peer) on the leader's "accumulator drained" barrier.
-// ------------------------------------------------------------------------------------------------
-template <int N>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap wmap,
-                    const ConvParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_slot_bytes = ((uint32_t)p.rows * p.P * 128u + 1023u) & ~1023u;
-  const int NA_SLOTS = p.na_slots;
-  const uint32_t a_base = base;
-  const uint32_t b_base = a_base + NA_SLOTS * a_slot_bytes;
-  constexpr uint32_t B_HALF = (N / 2) * 128u;     // this CTA's N/2 rows of the N x 64 weight tile
-  const int NB = p.nb_stages;
-  const uint32_t bar_base = b_base + NB * B_HALF;
-  auto a_full = [&](int i) { return bar_base + 8u * i; };
-  auto a_empty = [&](int i) { return bar_base + 8u * (MAX_NA + i); };
-  auto b_full = [&](int i) { return bar_base + 8u * (2 * MAX_NA + i); };
-  auto b_empty = [&](int i) { return bar_base + 8u * (2 * MAX_NA + MAX_NB + i); };
-  auto t_full = [&](int i) { return bar_base + 8u * (2 * MAX_NA + 2 * MAX_NB + i); };
-  auto t_empty = [&](int i) { return bar_base + 8u * (2 * MAX_NA + 2 * MAX_NB + 2 + i); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_NA + 2 * MAX_NB + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  const int taps = p.KS * p.KS;
-  constexpr uint32_t ACC_COLS = T_TILES * N;
-  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;    // 512 or 256
-  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
-  const int npb_pix = (p.nblocks + 1) >> 1;       // pair-blocks of one output-channel group
-  const int npb = npb_pix * p.ngroups;            // pair-block pb = (group pb / npb_pix, pixel pair-block pb % npb_pix)
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NA_SLOTS; ++i) { mbar_init(a_full(i), 2); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < NB; ++i) { mbar_init(b_full(i), 2); mbar_init(b_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 8); }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if (warp == 0) {
-    // ===== A producer (both CTAs): own block's halo rows, completing on the leader's a_full =====
-    const uint32_t row_bytes = (uint32_t)(8 + 2 * p.pad) * 128u;
-    int ac = 0;
-    for (int pb = pair; pb < npb; pb += npairs) {
-      const int blk = 2 * (pb % npb_pix) + (int)rank;   // may be == nblocks for the last odd block: all rows out of range
-      const int xg = blk % p.nxg, vb = blk / p.nxg;
-      const int x0 = xg * 8, v0 = vb * (16 * T_TILES);
-      for (int c = 0; c < p.nchunks; ++c, ++ac) {
-        const int slot = ac % NA_SLOTS;
-        const uint32_t dst0 = a_base + slot * a_slot_bytes;
-        const uint32_t full_leader = a_full(slot) & PEER_MASK;
-        if (lane == 0) mbar_wait(a_empty(slot), ((ac / NA_SLOTS) & 1) ^ 1);
-        __syncwarp();
-        if (p.pad == 0) {
-          if (lane == 0) tma_load_4d_2sm(dst0, &tmap, c * 64, x0, v0, 0, full_leader);
-        } else {
-          for (int r = lane; r < p.rows; r += 32) {
-            const int vr = v0 - p.pad + r;
-            int n = 0, y = p.H;
-            if (vr >= 0 && vr < p.Vtotal) { n = vr / p.Hp; y = vr - n * p.Hp; }
-            tma_load_4d_2sm(dst0 + (uint32_t)r * p.P * 128u, &tmap, c * 64, x0 - p.pad, y, n, full_leader);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) {
-          if (leader) mbar_expect_tx(a_full(slot), 2u * row_bytes * p.rows);
-          else mbar_arrive_cluster(full_leader);
-        }
-      }
-    }
-  } else if (warp == 2) {
-    // ===== B producer (both CTAs): rows rank*64.. of each [128][64] weight tile =====
-    if (lane == 0) {
-      const int per_block = p.nchunks * taps;
-      const int rows_per_tile = p.w_tile_elems / 64;     // Cout_total
-      int it = 0;
-      for (int pb = pair; pb < npb; pb += npairs) {
-        const int row0 = (pb / npb_pix) * N + (int)rank * (N / 2);
-        for (int k = 0; k < per_block; ++k, ++it) {
-          const int st = it % NB;
-          const uint32_t full_leader = b_full(st) & PEER_MASK;
-          mbar_wait(b_empty(st), ((it / NB) & 1) ^ 1);
-          tma_load_2d_2sm(b_base + st * B_HALF, &wmap, 0, k * rows_per_tile + row0, full_leader);
-          if (leader) mbar_expect_tx(b_full(st), 2u * B_HALF);
-          else mbar_arrive_cluster(full_leader);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer: leader CTA only =====
-    if (leader) {
-      const int bf = (p.flags & FLAG_F16) ? 0 : 1;
-      const uint32_t idesc = make_idesc(256, N, 0, 0, bf, bf);
-      const uint32_t a_hi = desc_hi((uint32_t)p.P * 128u), b_hi = desc_hi(1024u);
-      const uint32_t row_units = (uint32_t)p.P * 8u;
-      const uint32_t mt_units = 16u * row_units;
-      const uint32_t wrap_units = row_units - (uint32_t)p.KS * 8u;
-      int it = 0, ac = 0, lb = 0;
-      for (int pb = pair; pb < npb; pb += npairs, ++lb) {
-        const int buf = lb & 1;
-        mbar_wait(t_empty(buf), ((lb >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t acc0 = tmem_base + buf * ACC_COLS;
-        uint32_t first = 0u;
-        for (int c = 0; c < p.nchunks; ++c, ++ac) {
-          const int slot = ac % NA_SLOTS;
-          mbar_wait(a_full(slot), (ac / NA_SLOTS) & 1);
-          tc_fence_after();
-          uint32_t a_lo = desc_lo(a_base + slot * a_slot_bytes, 16u);
-          int kx = 0;
-          for (int t = 0; t < taps; ++t, ++it) {
-            const int st = it % NB;
-            mbar_wait(b_full(st), (it / NB) & 1);
-            tc_fence_after();
-            const uint32_t b_lo = desc_lo(b_base + st * B_HALF, 16u);
-            if (elect_one()) {
-#pragma unroll
-              for (int mt = 0; mt < T_TILES; ++mt) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  umma_bf16_2sm(acc0 + mt * N, desc_join(a_lo + mt * mt_units + kk * 2u, a_hi),
-                                desc_join(b_lo + kk * 2u, b_hi), idesc, (first | (uint32_t)kk) ? 1u : 0u);
-                }
-              }
-              umma_commit_2sm(b_empty(st));
-            }
-            __syncwarp();
-            first = 1u;
-            a_lo += 8u;
-            if (++kx == p.KS) { kx = 0; a_lo += wrap_units; }
-          }
-          if (elect_one()) umma_commit_2sm(a_empty(slot));
-          __syncwarp();
-        }
-        if (elect_one()) umma_commit_2sm(t_full(buf));
-        __syncwarp();
-      }
-    }
-  } else {
-    // ===== epilogue (both CTAs): own 128 TMEM lanes =====
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int wx = r & 7, vrow = r >> 3;
-    int lb = 0;
-    for (int pb = pair; pb < npb; pb += npairs, ++lb) {
-      const int buf = lb & 1;
-      const int blk = 2 * (pb % npb_pix) + (int)rank;
-      const int xg = blk % p.nxg, vb = blk / p.nxg;
-      const int x0 = xg * 8, v0 = vb * (16 * T_TILES);
-      mbar_wait(t_full(buf), (lb >> 1) & 1);
-      tc_fence_after();
-      const uint32_t acc0 = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
-      bool valid[T_TILES];
-      long long pix[T_TILES];
-#pragma unroll
-      for (int mt = 0; mt < T_TILES; ++mt) {
-        const int vr = v0 + mt * 16 + vrow;
-        const int n = vr / p.Hp, y = vr - n * p.Hp;
-        valid[mt] = blk < p.nblocks && vr < p.Vtotal && y < p.H;
-        pix[mt] = ((long long)n * p.H + y) * p.W + x0 + wx;
-      }
-      epilogue_block<N>(p, acc0, valid, pix, (int)blockIdx.x * 4 + q, lane, (pb / npb_pix) * N);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(t_empty(buf) & PEER_MASK);
-    }
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // weight packing: OIHW fp32 -> bf16 [chunk][tap][N rows][64] in the SWIZZLE_128B shared-memory image
@@ -685,8 +149,8 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   const int nblk = max(blk1 - blk0, 0);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 2); }     // two MMA-issuing warps release a stage
+    mbar_init(tmem_full, 2);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -720,7 +184,12 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (++t == p.tiles_per_sample) { t = 0; ty = 0; tx_ = 0; ++n; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 2) {
+    // TWO issuing warps (on different scheduler partitions): the single issuing lane is the critical path of the 64-channel
+    // layers (32 N = 64 MMAs per 64-pixel stage, ~30 tensor cycles each); warp 1 takes the even accumulator groups, warp 2
+    // the odd ones.  Groups are independent accumulators, both warps wait on the same "full" barrier and each commits its
+    // own MMAs to the stage's "empty" barrier (count 2).
+    const int par = warp - 1;
     const uint32_t idesc = make_idesc(128, p.Cout, 1, 1);
     const uint32_t a_hi = desc_hi((uint32_t)p.P * 128u), b_hi = desc_hi(1024u);
     const uint32_t row_units = (uint32_t)p.P * 8u;
@@ -756,7 +225,7 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (elect_one()) {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          if (g < ng) {
+          if (g < ng && (g & 1) == par) {
             const uint32_t a_lo = xs_lo + gword[g];
 #pragma unroll
             for (int s = 0; s < 4; ++s)
@@ -843,61 +312,6 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, float*
   dw[o] = accumulate ? dw[o] + s : s;
 }
 
-// shared-memory plan of the forward kernel: A slots fixed by the geometry, the weight ring takes what is left
-void conv_smem_plan(int N, int rows, int P, int na, size_t* smem, int* nb) {
-  size_t a = ((size_t)rows * P * 128 + 1023) & ~(size_t)1023;
-  size_t fixed = 1024 + na * a + 512;
-  int stages = (int)((SMEM_LIMIT - fixed) / ((size_t)N * 128));
-  if (stages > MAX_NB) stages = MAX_NB;
-  *nb = stages;
-  *smem = fixed + (size_t)stages * N * 128;
-}
-
-template <int N>
-int launch_conv_pair(const CUtensorMap& tmap, ConvParams p, int cout_total, int n0, const void* w_packed,
-                     cudaStream_t stream) {
-  EncodeTiledFn enc = get_encode();
-  // weights as a plain 2D byte image [nchunks*taps*Cout_total rows][128 B]; already in the swizzled layout
-  CUtensorMap wmap;
-  const int taps = p.KS * p.KS;
-  cuuint64_t gdim[2] = {64, (cuuint64_t)p.nchunks * taps * cout_total};
-  cuuint64_t gstr[1] = {128};
-  cuuint32_t box[2] = {64, N / 2};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(&wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { tsr_set_error("conv2d_tc: weight tensor map failed (%d)", (int)r); return TSR_ERR_CUDA; }
-  (void)n0;
-  p.na_slots = p.KS == 1 ? 5 : 2;
-  size_t a = ((size_t)p.rows * p.P * 128 + 1023) & ~(size_t)1023;
-  size_t fixed = 1024 + p.na_slots * a + 512;
-  constexpr size_t half = (size_t)(N / 2) * 128;
-  int stages = (int)((SMEM_LIMIT - fixed) / half);
-  if (stages > MAX_NB) stages = MAX_NB;
-  p.nb_stages = stages;
-  size_t smem = fixed + (size_t)stages * half;
-  TSR_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int npb = (p.nblocks + 1) / 2 * p.ngroups;
-  int pairs = npb < num_sms() / 2 ? npb : num_sms() / 2;
-  conv_tc_pair_kernel<N><<<2 * pairs, NUM_THREADS, smem, stream>>>(tmap, wmap, p);
-  TSR_CHECK_LAUNCH("conv2d_tc_pair");
-  return TSR_OK;
-}
-
-template <int N>
-int launch_conv(const CUtensorMap& tmap, ConvParams p, cudaStream_t stream) {
-  size_t smem;
-  p.na_slots = p.KS == 1 ? 5 : 2;
-  conv_smem_plan(N, p.rows, p.P, p.na_slots, &smem, &p.nb_stages);
-  if (p.nb_stages < 2) { tsr_set_error("conv2d_tc: shared memory plan infeasible"); return TSR_ERR_UNSUPPORTED; }
-  TSR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = p.nblocks < num_sms() ? p.nblocks : num_sms();
-  conv_tc_kernel<N><<<grid, NUM_THREADS, smem, stream>>>(tmap, p);
-  TSR_CHECK_LAUNCH("conv2d_tc");
-  return TSR_OK;
-}
-
 }  // namespace
 
 extern "C" {
@@ -964,82 +378,6 @@ int tsr_pack_conv_weight_folded(const float* w_oihw, const float* bias, const fl
   TSR_CHECK_LAUNCH("pack_conv_weight_folded");
   fold_bias_kernel<<<tsr_cdiv(Cout, 128), 128, 0, stream>>>(bias, scale, shift, bias_out, Cout);
   TSR_CHECK_LAUNCH("fold_bias");
-  return TSR_OK;
-}
-
-size_t tsr_conv2d_tc_workspace(int, int, int, int, int, int) { return 0; }
-
-// bf16 NHWC convolution on the tensor cores.  in: [B*H*W][in_ld] (Cin channels from `in`), w_packed from
-// tsr_pack_conv_weight_bf16, bias fp32 [Cout] or NULL, residual bf16 [pix][res_ld] or NULL, out bf16.
-// out2_bf16 (may be NULL): a second copy of the result rounded to bf16, row stride out2_ld (the "fp16" precision mode keeps
-// it as the weight-gradient operand of the next convolution).
-// bn_partial (may be NULL): [tsr_conv2d_tc_stat_rows()][2][Cout] floats that receive per-(CTA, warp) partial sums and sums of
-// squares of the stored output -- the batch statistics of a BatchNorm that consumes this convolution, finished by
-// tsr_bn_finalize_partials without another pass over the tensor.
-int tsr_conv2d_tc_stat_rows(void) { return STAT_ROWS; }
-
-int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* bias, const void* residual,
-                  int res_ld, void* out, int out_ld, int B, int H, int W, int Cin, int Cout, int KS, int flags,
-                  void* workspace, size_t ws_bytes, float* bn_partial, void* out2_bf16, int out2_ld, cudaStream_t stream) {
-  (void)workspace; (void)ws_bytes;
-  TSR_REQUIRE(!out2_bf16 || (out2_ld % 8 == 0 && ((uintptr_t)out2_bf16 & 15) == 0), "conv2d_tc: second output must be 16-byte aligned with a row stride that is a multiple of 8");
-  if (bn_partial) TSR_CUDA(cudaMemsetAsync(bn_partial, 0, (size_t)STAT_ROWS * 2 * Cout * sizeof(float), stream));
-  TSR_REQUIRE(in && w_packed && out, "conv2d_tc: null pointer");
-  TSR_REQUIRE(Cout % 64 == 0 && Cout > 0, "conv2d_tc: Cout must be a multiple of 64 (got %d)", Cout);
-  TSR_REQUIRE(Cin % 64 == 0 && Cin > 0, "conv2d_tc: Cin must be a multiple of 64 (got %d)", Cin);
-  TSR_REQUIRE(KS == 1 || KS == 3 || KS == 5, "conv2d_tc: kernel size %d unsupported", KS);
-  TSR_REQUIRE(W % 8 == 0, "conv2d_tc: W must be a multiple of 8 (got %d)", W);
-  TSR_REQUIRE(in_ld % 8 == 0 && out_ld % 8 == 0 && (!residual || res_ld % 8 == 0), "conv2d_tc: row strides must be multiples of 8");
-  TSR_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)w_packed & 15) == 0, "conv2d_tc: pointers must be 16-byte aligned");
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { tsr_set_error("conv2d_tc: cuTensorMapEncodeTiled unavailable"); return TSR_ERR_CUDA; }
-  const int pad = KS / 2;
-  CUtensorMap tmap;
-  cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t gstr[3] = {(cuuint64_t)in_ld * 2, (cuuint64_t)W * in_ld * 2, (cuuint64_t)H * W * in_ld * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)(8 + 2 * pad), 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  if (pad == 0) {   // no halo: rows of consecutive samples are contiguous => one (B*H)-row dimension, 32-row boxes
-    gdim[2] = (cuuint64_t)H * B; gdim[3] = 1;
-    box[2] = 16 * T_TILES;
-  }
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { tsr_set_error("conv2d_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return TSR_ERR_CUDA; }
-  ConvParams p;
-  p.res_ld = res_ld; p.out_ld = out_ld;
-  p.B = B; p.H = H; p.W = W; p.Hp = H + pad; p.Vtotal = B * (H + pad);
-  // halo pitch: dense (8 + 2*pad pixels, the TMA box width) unless desc-mode bit 1 asks for the 16-pixel pitch
-  p.KS = KS; p.pad = pad; p.P = (g_desc_mode & 2) ? (pad ? 16 : 8) : 8 + 2 * pad; p.rows = 16 * T_TILES + 2 * pad;
-  p.nchunks = Cin / 64; p.nxg = W / 8; p.flags = flags;
-  p.w_tile_elems = Cout * 64;
-  const int nvb = tsr_cdiv(p.Vtotal, 16 * T_TILES);
-  p.nblocks = nvb * p.nxg;
-  // output channels are produced in groups of 128 (or a trailing 64): rows n0.. of every pre-swizzled weight tile
-  for (int n0 = 0; n0 < Cout;) {
-    int nt = (Cout - n0) >= 128 ? 128 : 64;
-    p.w = (const __nv_bfloat16*)w_packed + (size_t)n0 * 64;
-    p.bias = bias ? bias + n0 : nullptr;
-    p.residual = residual ? (const __nv_bfloat16*)residual + n0 : nullptr;
-    p.out = (__nv_bfloat16*)out + n0;
-    p.out2 = out2_bf16 ? (__nv_bfloat16*)out2_bf16 + n0 : nullptr;
-    p.out2_ld = out2_ld;
-    p.bn_partial = bn_partial ? bn_partial + n0 : nullptr;
-    p.bn_C = Cout;
-    p.ngroups = 1;
-    int rc;
-    if (nt == 128 && !(g_desc_mode & 16)) { // bit 4 set = force the single-CTA kernel
-      p.ngroups = (Cout - n0) / 128;        // all remaining 128-wide groups in this one launch
-      rc = launch_conv_pair<128>(tmap, p, Cout, n0, (const __nv_bfloat16*)w_packed + (size_t)n0 * 64, stream);
-      nt = 128 * p.ngroups;
-    } else if (nt == 64 && !(g_desc_mode & 16) && !(g_desc_mode & 32))
-      rc = launch_conv_pair<64>(tmap, p, Cout, n0, (const __nv_bfloat16*)w_packed + (size_t)n0 * 64, stream);
-    else
-      rc = nt == 128 ? launch_conv<128>(tmap, p, stream) : launch_conv<64>(tmap, p, stream);
-    if (rc) return rc;
-    n0 += nt;
-  }
   return TSR_OK;
 }
 

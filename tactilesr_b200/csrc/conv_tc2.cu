@@ -16,9 +16,13 @@
 //       - BatchNorm backward, level 1: g = dgrad * [scale*y + shift > 0] is stored and sum g, sum g*y are reduced per
 //         (CTA, lane quarter) for tsr_bn_bwd_finalize_partials (replaces the bn_bwd_partial pass over da and y).
 //
-// Work decomposition, halo tiles, descriptors and the pair protocol are those of conv_tc.cu (generation 1; its forward
-// kernels are kept behind TSR_TC_MODE bit 6 for A/B runs): samples stacked vertically with `maxpad` virtual zero rows
-// between them, a CTA block = 32 virtual rows x 8 columns = 2 M-tiles, every tap a shifted window of the one halo tile.
+// Work decomposition ("tall plane"): the B samples are stacked vertically with `maxpad` virtual zero rows between them
+// (pitch Hp = H + maxpad), so a CTA block is 32 consecutive virtual rows x 8 columns = 2 M-tiles of 128 pixels and every tap
+// is a pure (row, column) shift inside ONE shared-memory halo tile, loaded once per block and 64-channel chunk by TMA row
+// boxes (OOB zero fill = the conv padding, SWIZZLE_128B).  The A operand of each MMA is a *window* of it: the UMMA descriptor
+// starts at row (ky * P + kx) of the tile with 8-row core groups P * 128 B apart -- no im2col.  CTA pairs: each CTA owns one
+// block and half of the rows of every weight tile, ONE tcgen05.mma.cta_group::2 (M = 256) of the leader drives both tensor
+// cores; TMA loads of both CTAs complete on the leader's barriers, tcgen05.commit multicasts to both.
 //
 // Warp roles (11 warps): 0 = A producer (TMA row boxes), 1 = MMA issuer + TMEM owner, 2 = B producer (weight tiles),
 // 3..10 = epilogue.
@@ -672,6 +676,27 @@ int tsr_conv2d_tc2(const void* args, cudaStream_t stream) {
   if (a.aux_scale) a.aux_scale += n0;
   if (a.aux_shift) a.aux_shift += n0;
   return conv2d_tc2_cols(a, a0.Cout, n0, stream);
+}
+
+// The single-convolution entry point of generation 1, kept as a thin front end of tsr_conv2d_tc2 (same arguments and
+// semantics; flags bit 0 = ReLU, bit 1 = fp16 operands).
+size_t tsr_conv2d_tc_workspace(int, int, int, int, int, int) { return 0; }
+int tsr_conv2d_tc_stat_rows(void) { return T2_STAT_ROWS; }
+
+int tsr_conv2d_tc(const void* in, int in_ld, const void* w_packed, const float* bias, const void* residual, int res_ld,
+                  void* out, int out_ld, int B, int H, int W, int Cin, int Cout, int KS, int flags, void* workspace,
+                  size_t ws_bytes, float* bn_partial, void* out2_bf16, int out2_ld, cudaStream_t stream) {
+  (void)workspace; (void)ws_bytes;
+  TSR_REQUIRE(in && w_packed && out, "conv2d_tc: null pointer");
+  ConvTc2 a;
+  memset(&a, 0, sizeof(a));
+  a.src[0].in = in; a.src[0].w_packed = w_packed; a.src[0].in_ld = in_ld; a.src[0].Cin = Cin; a.src[0].KS = KS;
+  a.nsrc = 1;
+  a.bias = bias; a.residual = residual; a.res_ld = res_ld;
+  a.out = out; a.out_ld = out_ld; a.out2_bf16 = out2_bf16; a.out2_ld = out2_ld;
+  a.stat = bn_partial; a.stat_ld = Cout;
+  a.B = B; a.H = H; a.W = W; a.Cout = Cout; a.flags = flags & (F_RELU | F_F16);
+  return tsr_conv2d_tc2(&a, stream);
 }
 
 static int conv2d_tc2_cols(const ConvTc2& a, int cout_total, int n0, cudaStream_t stream) {

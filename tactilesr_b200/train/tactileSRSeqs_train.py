@@ -51,13 +51,15 @@ def main(config, single_config=None):
     from ..config import tactileSR_config
     from .common import EvalHook, set_random_seed, setup_device
     from .tactileSR_train import build_dataloader, make_trainer
+    from .tactileSR_train import build_model_and_optimizer as build_plain
     rank, world, device = setup_device()
     set_precision(config.get("_precision", "fp16"))
     set_random_seed(config["random_seed"])
     train_loader, test_loader = build_dataloader(config, rank, world)
-    model, optimizer = build_model_and_optimizer(config, device)
     if os.path.exists(config.get("load_checkpoint_dir", "")):
-        model = model_param_init(single_config or tactileSR_config, config, model, device)
+        model, optimizer = build_model_and_optimizer(config, single_config or tactileSR_config, device)
+    else:
+        model, optimizer = build_plain(config, device)
     cfg = {k: v for k, v in config.items() if not k.startswith("warmup_")}          # :79-87 passes no warm-up arguments
     trainer = make_trainer(cfg, model, optimizer, train_loader, device)
     if trainer.train_by_epoch:

@@ -1,5 +1,5 @@
 """Per-launch timing (CUDA events, L2 flushed between launches by rotating buffers) of the generation-2 tensor-core
-convolution against generation 1 on the shapes of one MSRB at a given batch.  usage: python tools/tc2_perf.py [B]"""
+convolution on the shapes of one MSRB at a given batch (B = argv[1]), with the wait-cycle breakdown of CTA 0.  usage: python tools/tc2_perf.py [B]"""
 import os
 import sys
 
@@ -57,7 +57,7 @@ def timeit_dbg(fn, n=6):
 def report(name, flops, us_new, us_old=None):
     s = f"{name:46s} tc2 {us_new:8.1f} us {flops / us_new / 1e6:7.1f} TF/s"
     if us_old is not None:
-        s += f" | gen1 {us_old:8.1f} us {flops / us_old / 1e6:7.1f} TF/s"
+        s += f" | {us_old:8.1f} us"
     print(s, flush=True)
     if LAST[0] is not None:
         DBG.zero_()
@@ -74,7 +74,6 @@ def report(name, flops, us_new, us_old=None):
 
 
 rows = L.tsr_conv2d_tc2_stat_rows()
-rows1 = L.tsr_conv2d_tc_stat_rows()
 f16 = torch.float16
 bf = torch.bfloat16
 npix = B * H * W
@@ -86,11 +85,9 @@ for Cin, Cout, KS in [(64, 64, 3), (64, 64, 5), (128, 128, 3), (128, 128, 5)]:
     wf = pack(w, True)
     bias = torch.randn(Cout, device=dev)
     part = torch.empty(rows, 2, Cout, device=dev)
-    part1 = torch.empty(rows1, 2, Cout, device=dev)
     new = timeit_dbg(lambda i: _lib.conv_tc2([(x[i].data_ptr(), Cin, Cin, KS, wf.data_ptr())], out[i].data_ptr(), Cout, B, H, W, Cout,
                                          flags=_lib.TC2_F16, bias=bias.data_ptr(), stat=part.data_ptr(), stat_ld=Cout))
-    old = timeit(lambda i: _lib.call("tsr_conv2d_tc", x[i].data_ptr(), Cin, wf.data_ptr(), bias.data_ptr(), 0, 0, out[i].data_ptr(), Cout,
-                                     B, H, W, Cin, Cout, KS, 2, 0, 0, part1.data_ptr(), 0, 0, st))
+    old = None
     report(f"fwd+stats {Cin}->{Cout} {KS}x{KS}", 2.0 * npix * Cin * Cout * KS * KS, new, old)
 
 if len(sys.argv) > 2 and sys.argv[2] == "fwd":
@@ -114,8 +111,7 @@ bias = torch.randn(64, device=dev)
 new = timeit_dbg(lambda i: _lib.conv_tc2([(x[i].data_ptr(), 256, 256, 1, wf.data_ptr())], out[i].data_ptr(), 64, B, H, W, 64,
                                      flags=_lib.TC2_F16 | _lib.TC2_RELU, bias=bias.data_ptr(), residual=res[i].data_ptr(), res_ld=64,
                                      out2=o2[i].data_ptr(), out2_ld=64))
-old = timeit(lambda i: _lib.call("tsr_conv2d_tc", x[i].data_ptr(), 256, wf.data_ptr(), bias.data_ptr(), res[i].data_ptr(), 64,
-                                 out[i].data_ptr(), 64, B, H, W, 256, 64, 1, 3, 0, 0, 0, o2[i].data_ptr(), 64, st))
+old = None
 report("fwd 1x1 256->64 +res+relu+copy", 2.0 * npix * 256 * 64, new, old)
 gb = npix * (256 + 64 + 64 + 64) * 2 / 1e9
 print(f"    compulsory bytes {gb:.2f} GB -> tc2 {gb / new * 1e3:.0f} GB/s", flush=True)
@@ -126,8 +122,7 @@ wd = pack(w, False, dgrad=True)
 coef = torch.randn(2, 256, device=dev)
 part = torch.empty(rows, 2, 256, device=dev)
 new = timeit_dbg(lambda i: _lib.conv_tc2([(dy[i].data_ptr(), 64, 64, 1, wd.data_ptr())], dx[i].data_ptr(), 256, B, H, W, 256))
-old = timeit(lambda i: _lib.call("tsr_conv2d_tc", dy[i].data_ptr(), 64, wd.data_ptr(), 0, 0, 0, dx[i].data_ptr(), 256, B, H, W, 64, 256,
-                                 1, 0, 0, 0, 0, 0, 0, st))
+old = None
 report("dgrad 1x1 64->256", 2.0 * npix * 256 * 64, new, old)
 new = timeit_dbg(lambda i: _lib.conv_tc2([(dy[i].data_ptr(), 64, 64, 1, wd.data_ptr())], dx[i].data_ptr(), 256, B, H, W, 256,
                                      flags=_lib.TC2_BNB | _lib.TC2_BNB_RELU | _lib.TC2_AUX_F16, aux=y[i].data_ptr(), aux_ld=256,
@@ -143,12 +138,7 @@ for C in (64, 128):
     part = torch.empty(rows, 2, C, device=dev)
     fl = 2.0 * npix * C * C * 34
 
-    def old_pair(i):
-        _lib.call("tsr_conv2d_tc", dy5[i].data_ptr(), C, wd5.data_ptr(), 0, 0, 0, dx[i].data_ptr(), C, B, H, W, C, C, 5, 0, 0, 0, 0, 0, 0, st)
-        _lib.call("tsr_conv2d_tc", dy3[i].data_ptr(), C, wd3.data_ptr(), 0, dx[i].data_ptr(), C, dx[i].data_ptr(), C, B, H, W, C, C, 3, 0,
-                  0, 0, 0, 0, 0, st)
-
-    old = timeit(old_pair)
+    old = None
     srcs = lambda i: [(dy3[i].data_ptr(), C, C, 3, wd3.data_ptr()), (dy5[i].data_ptr(), C, C, 5, wd5.data_ptr())]
     new = timeit_dbg(lambda i: _lib.conv_tc2(srcs(i), dx[i].data_ptr(), C, B, H, W, C))
     report(f"dual dgrad {C} (3x3 + 5x5), plain", fl, new, old)
