@@ -47,9 +47,11 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def __enter__(self):
+        if os.environ.get("TSR_BENCH_NO_CLOCKS") == "1":      # A/B switch: is the sampler itself perturbing the step?
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", os.environ.get("TSR_BENCH_CLOCK_MS", "200"), "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
@@ -549,12 +551,12 @@ def run_ours(args):
         "scaling": "strong" if args.global_batch else "weak",
         "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "fp16", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": {"workload": f"TactileSR(seqsCnt={S}) train step: fwd + fused HR-prep/MSE + bwd + fused Adam(lr 1e-3, wd 1e-2)"
-                               + (" + bucketed NCCL grad all-reduce" if world > 1 else ""),
+                               + (" + NCCL gradient all-reduce" if world > 1 else ""),
                    "per_gpu_batch": B, "global_batch": B * world, "input": f"LR (B,{3 * S},4,4), HR (B,1,100,100)",
                    "precision_mode": args.precision + {"fp16": " (fp16 activations / forward weights, bf16 gradients, fp32 accumulation and statistics)",
                                                        "bf16": " (bf16 storage, fp32 accumulation and statistics)", "fp32": ""}[args.precision],
                    "parallelism": f"dp{world}", "cuda_graph": bool(args.cuda_graph),
-                   "grad_allreduce": ("bucketed, overlapped with backward" if os.environ.get("TSR_DP_OVERLAP", "1") != "0" else "one call after backward") if world > 1 else None,
+                   "grad_allreduce": ("bucketed, overlapped with backward" if os.environ.get("TSR_DP_OVERLAP", "0") == "1" else "one NCCL call after backward") if world > 1 else None,
                    "l2": "per-step working set (saved activations, B x ~26-52 MB) >> 126 MB L2; 4 rotating input batches"},
         "tensor_roofline_frac_step": value / world * FLOP_PER_SAMPLE_TRAIN / 1e12 / pk["tf_sust"],
         "roofline": roof, "cpu_baseline": cpu,

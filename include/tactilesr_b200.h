@@ -282,6 +282,12 @@ int tsr_bn_backward_apply(const void* da, int da_ld, const void* y, int y_ld, vo
                           const float* scale, const float* shift, const float* save_mean, const float* save_invstd,
                           const float* c1, const float* c2, long long npix, int C, int relu, tsr_stream_t stream);
 
+/* tsr_conv2d_wgrad_tc with the storage type of `in` given (1 = bf16, 2 = fp16): an fp16 input -- the forward activations of the
+   "fp16" precision mode -- is converted to bf16 in shared memory by otherwise idle warps before the MMAs read it, so no
+   bf16 copy of the conv input has to exist in HBM.  dout stays bf16. */
+int tsr_conv2d_wgrad_tc_x(const void* in, int in_ld, int in_dtype, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
+                          size_t ws_bytes, int B, int H, int W, int Cin, int Cout, int KS, int accumulate,
+                          tsr_stream_t stream);
 /* experiment switches of the tensor-core kernels (see csrc/conv_tc.cu); 0 = production configuration. */
 void tsr_set_tc_desc_mode(int mode);
 int tsr_get_tc_desc_mode(void);

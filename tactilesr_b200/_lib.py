@@ -80,6 +80,7 @@ SIGNATURES = {
     "tsr_conv2d_tc_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),
     "tsr_conv2d_wgrad_tc": (_I, [_P, _I, _P, _I, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tsr_conv2d_wgrad_tc_workspace": (_Z, [_I, _I, _I, _I, _I, _I]),
+    "tsr_conv2d_wgrad_tc_x": (_I, [_P, _I, _I, _P, _I, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _I, _P]),
     "tsr_conv2d_tc2": (_I, [_P, _P]),
     "tsr_conv2d_tc2_stat_rows": (_I, []),
     "tsr_conv2d_tc2_debug": (None, [_P]),

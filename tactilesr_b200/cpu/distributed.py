@@ -101,11 +101,14 @@ class GradAllReduce:
 
     def __init__(self, flat: torch.Tensor, bucket_bytes: int = 8 << 20, group=None, overlap: Optional[bool] = None):
         self.flat, self.group = flat, group
-        # overlap = False: ONE all-reduce over the whole buffer after backward, on the compute stream (A/B switch; also
-        # TSR_DP_OVERLAP=0).  The overlapped form hides the transfer but its NCCL kernels share the SMs with the persistent
-        # one-CTA-per-SM convolution kernels of backward.
+        # overlap = False (default): ONE all-reduce over the whole buffer after backward, on the compute stream.
+        # overlap = True (or TSR_DP_OVERLAP=1): buckets are reduced on a side stream while backward is still running.
+        # Measured on 8 x B200 (B = 1024 per GPU, profiles/r02_scaling.md): the single call costs 0.8 ms of a 54.9 ms step
+        # (18.3 MB over NVLink: ~0.25 ms exposed, the rest is the max over ranks), the overlapped form 1.3 ms -- its NCCL
+        # CTAs cannot co-reside with the one-CTA-per-SM persistent convolution kernels of backward (registers), so each
+        # bucket takes SMs away from the cluster-pair kernels that follow; hiding 0.25 ms is not worth that.
         if overlap is None:
-            overlap = os.environ.get("TSR_DP_OVERLAP", "1") != "0"
+            overlap = os.environ.get("TSR_DP_OVERLAP", "0") == "1"
         self.overlap = overlap
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bucket_elems = max(bucket_bytes // 4, 1)

@@ -324,7 +324,8 @@ class Trainer:
                  max_num_checkpoints: Optional[int] = None, checkpoint_period: int = 1, log_period: int = 50,
                  clip_grad_norm: float = 0.0, enable_amp: bool = False, by_epoch: bool = True, warmup_t: int = 0,
                  warmup_by_epoch: bool = False, warmup_mode: str = "fix", warmup_init_lr: float = 0.0,
-                 warmup_factor: float = 0.0, grad_bucket_bytes: int = 8 << 20, cuda_graph: bool = False):
+                 warmup_factor: float = 0.0, grad_bucket_bytes: int = 8 << 20, cuda_graph: bool = False,
+                 grad_overlap: Optional[bool] = None):
         if enable_amp:
             raise NotImplementedError("enable_amp: use tactilesr_b200.set_precision('bf16') instead of autocast")
         model.train()
@@ -351,6 +352,7 @@ class Trainer:
         self._time_acc = {"data_time": 0.0, "iter_time": 0.0}
         self._dp: Optional[D.GradAllReduce] = None
         self._grad_bucket_bytes = grad_bucket_bytes
+        self._grad_overlap = grad_overlap      # None: cpu.distributed.GradAllReduce's default (one call after backward)
         # cuda_graph (extension; the reference has no such switch): after two ordinary iterations the whole iteration
         # (train_cal_loss + backward + optimizer step, ~450 kernel launches) is captured once per batch shape and
         # replayed -- at the reference's batch size 32 the iteration is launch-bound, not GPU-bound.  Under data parallelism
@@ -430,7 +432,7 @@ class Trainer:
                     dist.broadcast(p.data, 0)
             for b in self.model_or_module.buffers():
                 dist.broadcast(b, 0)
-        dp = D.GradAllReduce(flat, self._grad_bucket_bytes)
+        dp = D.GradAllReduce(flat, self._grad_bucket_bytes, overlap=self._grad_overlap)
         base = flat.data_ptr()
         end = base + flat.numel() * 4
 

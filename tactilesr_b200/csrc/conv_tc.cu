@@ -121,7 +121,8 @@ struct Wgrad3Params {
   int ncta_groups, nunits;      // CTA grid.x = ncta_groups * nunits (unit = chunk pair / chunk)
   int tiles_x, tiles_per_sample, nblocks, blocks_per_split;
   int dy_stage_bytes, xtile_bytes, stage_bytes, nstages;
-};
+  int x_f16;                    // the x operand arrives as fp16 (the "fp16" precision mode's activations) and is converted to
+};                              // bf16 in shared memory before the MMAs read it (kind::f16 rejects fp16 x bf16 operands)
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
@@ -134,6 +135,7 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   auto empty = [&](int i) { return bar_base + 8u * (WG2_MAX_STAGES + i); };
   const uint32_t tmem_full = bar_base + 8u * (2 * WG2_MAX_STAGES);
   const uint32_t tmem_slot = tmem_full + 8u;
+  auto ready = [&](int i) { return bar_base + 8u * (2 * WG2_MAX_STAGES + 2 + i); };     // x tile converted (x_f16 only)
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -150,6 +152,7 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 2); }     // two MMA-issuing warps release a stage
+    for (int i = 0; i < NS; ++i) mbar_init(ready(i), 4);                                // one arrival per converting warp
     mbar_init(tmem_full, 2);
     fence_barrier_init();
   }
@@ -218,7 +221,8 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     uint32_t first = 0u;
     const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4, row2 = 2u * row_units, Cout = (uint32_t)p.Cout;
     const uint32_t xs_lo0 = desc_lo(base + (uint32_t)p.dy_stage_bytes, 0u), b_lo0 = desc_lo(base, lbo_b);
-    uint32_t st = 0, ph = 0, xs_lo = xs_lo0, b_lo = b_lo0, full_bar = full(0), empty_bar = empty(0);
+    const uint32_t wait0 = p.x_f16 ? ready(0) : full(0);       // fp16 x: wait for the converted tile, not for the raw TMA data
+    uint32_t st = 0, ph = 0, xs_lo = xs_lo0, b_lo = b_lo0, full_bar = wait0, empty_bar = empty(0);
     for (int i = 0; i < nblk; ++i) {
       mbar_wait(full_bar, ph);
       tc_fence_after();
@@ -238,11 +242,42 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       __syncwarp();
       first = 1u;
       xs_lo += stage_units; b_lo += stage_units; full_bar += 8u; empty_bar += 8u;
-      if (++st == (uint32_t)NS) { st = 0; ph ^= 1u; xs_lo = xs_lo0; b_lo = b_lo0; full_bar = full(0); empty_bar = empty(0); }
+      if (++st == (uint32_t)NS) { st = 0; ph ^= 1u; xs_lo = xs_lo0; b_lo = b_lo0; full_bar = wait0; empty_bar = empty(0); }
     }
     if (elect_one()) umma_commit(tmem_full);
     __syncwarp();
   } else if (warp >= 3) {
+    if (p.x_f16) {
+      // ===== fp16 -> bf16 conversion of the x halo tile(s) of every stage, in place (element-wise: the swizzled layout is
+      // untouched), by the four warps that otherwise idle until the epilogue.  The weight gradient then reads the forward
+      // activations directly: no bf16 "shadow" copy of every conv input has to be written by the forward pass. =====
+      const int ct = threadIdx.x - 96;             // 0..127
+      const uint32_t xbytes = (uint32_t)p.P * p.P * 128u;
+      int st = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nblk; ++i) {
+        mbar_wait(full(st), ph);
+        uint8_t* xs = smem_raw + (base - smem_u32(smem_raw)) + (size_t)st * p.stage_bytes + p.dy_stage_bytes;
+        for (int h = 0; h < nxt; ++h) {
+          uint4* v = reinterpret_cast<uint4*>(xs + (size_t)h * p.xtile_bytes);
+          for (uint32_t k = ct; k < xbytes / 16u; k += 128u) {
+            uint4 u = v[k];
+            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+              const __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);
+              w[j] = *reinterpret_cast<const uint32_t*>(&b);
+            }
+            v[k] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready(st));
+        if (++st == NS) { st = 0; ph ^= 1u; }
+      }
+    }
     const int q = warp & 3;
     const int r = q * 32 + lane;                 // accumulator row: atom = r / 64, ci_local = r % 64
     const int atom = r >> 6, cil = r & 63;
@@ -416,9 +451,29 @@ size_t tsr_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int
 
 // dw_oihw (fp32, [Cout][Cin][KS][KS]) (+)= wgrad of the conv;  in / dout are bf16 NHWC views.
 // Cout = 64, 128, or a multiple of 128 (the MLP layers of tPSFNet): groups of 128 output channels are grid.z of one launch.
+static int wgrad_tc_impl(const void* in, int in_ld, int in_f16, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
+                         size_t ws_bytes, int B, int H, int W, int Cin, int Cout_total, int KS, int accumulate,
+                         cudaStream_t stream);
+
 int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
                         size_t ws_bytes, int B, int H, int W, int Cin, int Cout_total, int KS, int accumulate,
                         cudaStream_t stream) {
+  return wgrad_tc_impl(in, in_ld, 0, dout, dout_ld, dw_oihw, workspace, ws_bytes, B, H, W, Cin, Cout_total, KS, accumulate, stream);
+}
+
+// the same with the storage type of `in` given: in_dtype 1 = bf16, 2 = fp16 (converted to bf16 inside the kernel; dout
+// stays bf16) -- what the "fp16" precision mode calls with its forward activations
+int tsr_conv2d_wgrad_tc_x(const void* in, int in_ld, int in_dtype, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
+                          size_t ws_bytes, int B, int H, int W, int Cin, int Cout_total, int KS, int accumulate,
+                          cudaStream_t stream) {
+  TSR_REQUIRE(in_dtype == TSR_DT_BF16 || in_dtype == TSR_DT_F16, "conv2d_wgrad_tc_x: in_dtype must be 1 (bf16) or 2 (fp16)");
+  return wgrad_tc_impl(in, in_ld, in_dtype == TSR_DT_F16, dout, dout_ld, dw_oihw, workspace, ws_bytes, B, H, W, Cin, Cout_total, KS,
+                       accumulate, stream);
+}
+
+static int wgrad_tc_impl(const void* in, int in_ld, int in_f16, const void* dout, int dout_ld, float* dw_oihw, void* workspace,
+                         size_t ws_bytes, int B, int H, int W, int Cin, int Cout_total, int KS, int accumulate,
+                         cudaStream_t stream) {
   TSR_REQUIRE(in && dout && dw_oihw && workspace, "conv2d_wgrad_tc: null pointer");
   TSR_REQUIRE(Cout_total == 64 || (Cout_total > 0 && Cout_total % 128 == 0), "conv2d_wgrad_tc: Cout must be 64 or a multiple of 128 (got %d)", Cout_total);
   const int G = Cout_total > 128 ? Cout_total / 128 : 1;
@@ -470,6 +525,7 @@ int tsr_conv2d_wgrad_tc(const void* in, int in_ld, const void* dout, int dout_ld
   int ns = (int)((SMEM_LIMIT - 1024 - 512) / (size_t)q.stage_bytes);
   if (ns > WG2_MAX_STAGES) ns = WG2_MAX_STAGES;
   q.nstages = ns;
+  q.x_f16 = in_f16;
   size_t smem = 1024 + (size_t)ns * q.stage_bytes + 512;
   TSR_CUDA(cudaFuncSetAttribute(wgrad_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(q.ncta_groups * q.nunits, nsplit, G);

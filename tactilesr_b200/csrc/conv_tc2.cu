@@ -24,8 +24,9 @@
 // block and half of the rows of every weight tile, ONE tcgen05.mma.cta_group::2 (M = 256) of the leader drives both tensor
 // cores; TMA loads of both CTAs complete on the leader's barriers, tcgen05.commit multicasts to both.
 //
-// Warp roles (11 warps): 0 = A producer (TMA row boxes), 1 = MMA issuer + TMEM owner, 2 = B producer (weight tiles),
-// 3..10 = epilogue.
+// Warp roles (12 warps): 0 = A producer (TMA row boxes), 1 = MMA issuer of M-tile 0 + TMEM owner, 2 = B producer (weight
+// tiles), 3..10 = epilogue, 11 = MMA issuer of M-tile 1.  Two issuing warps on different scheduler partitions: with 64
+// output columns an MMA occupies the tensor pipe for ~30 cycles and a single issuing lane cannot keep up.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <cuda.h>
@@ -35,7 +36,7 @@
 namespace {
 
 constexpr int T2_TILES = 2;
-constexpr int T2_THREADS = 352;
+constexpr int T2_THREADS = 384;
 constexpr int T2_MAX_NA = 8, T2_MAX_NB = 8;
 constexpr int T2_STAT_ROWS = 148 * 4;       // (CTA, TMEM lane quarter)
 constexpr int T2_MAX_TAPS = 25;
@@ -296,9 +297,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant
   const bool dbg = DBG && p.dbg != nullptr && blockIdx.x == 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(a_full0 + 8u * i, 2); mbar_init(a_empty0 + 8u * i, 1); }
-    for (int i = 0; i < NB; ++i) { mbar_init(b_full0 + 8u * i, 2); mbar_init(b_empty0 + 8u * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), 16); }
+    // "empty" / "accumulator ready" barriers collect one tcgen05.commit from each of the two MMA-issuing warps
+    for (int i = 0; i < NA; ++i) { mbar_init(a_full0 + 8u * i, 2); mbar_init(a_empty0 + 8u * i, 2); }
+    for (int i = 0; i < NB; ++i) { mbar_init(b_full0 + 8u * i, 2); mbar_init(b_empty0 + 8u * i, 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 2); mbar_init(t_empty(i), 16); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -385,9 +387,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant
       }
       if (dbg) p.dbg[1] = (unsigned long long)dbg_w2;
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer: leader CTA only; the warp runs the loop converged, one elected lane issues =====
+  } else if (warp == 1 || warp == 11) {
+    // ===== MMA issuers: leader CTA only; warp 1 owns M-tile 0, warp 11 M-tile 1 (independent accumulators; both wait on the
+    // same "full" barriers, each commits its own MMAs).  A warp runs the loop converged, one elected lane issues =====
     if (leader) {
+      const int mt = warp == 1 ? 0 : 1;
       const int bf = (p.flags & F_F16) ? 0 : 1;
       const uint32_t idesc_full = make_idesc(256, NACC, 0, 0, bf, bf);
       const uint32_t idesc_half = make_idesc(256, NACC / 2, 0, 0, bf, bf);
@@ -433,12 +437,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant
               }
               if (elect_one()) {
 #pragma unroll
-                for (int mt = 0; mt < T2_TILES; ++mt) {
-#pragma unroll
-                  for (int kk = 0; kk < 4; ++kk) {
-                    umma_bf16_2sm(acc + mt * NACC, desc_join(a_tap + mt * mt_units + kk * 2u, a_hi),
-                                  desc_join(b_lo + kk * 2u, b_hi), idesc, (first | (uint32_t)kk) ? 1u : 0u);
-                  }
+                for (int kk = 0; kk < 4; ++kk) {
+                  umma_bf16_2sm(acc + mt * NACC, desc_join(a_tap + mt * mt_units + kk * 2u, a_hi),
+                                desc_join(b_lo + kk * 2u, b_hi), idesc, (first | (uint32_t)kk) ? 1u : 0u);
                 }
                 umma_commit_2sm(be_bar);
               }
@@ -460,7 +461,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap amap0, const __grid_constant
         if (elect_one()) umma_commit_2sm(t_full(buf));
         __syncwarp();
       }
-      if (dbg && lane == 0) {
+      if (dbg && lane == 0 && mt == 0) {
         p.dbg[2] = (unsigned long long)dbg_te; p.dbg[3] = (unsigned long long)dbg_af; p.dbg[4] = (unsigned long long)dbg_bf;
         p.dbg[5] = (unsigned long long)(clock64() - dbg_start); p.dbg[6] = (unsigned long long)lb;
       }

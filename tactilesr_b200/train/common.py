@@ -44,6 +44,14 @@ def setup_device():
     return rank, world, dev
 
 
+def shutdown() -> None:
+    """Leave the process group cleanly at the end of an entry point."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 class SyntheticSRDataset(Dataset):
     """Random (LR, HR) records with the shapes and value ranges of the reference's SR dataset files
     (LR (3*seqsCnt, 4, 4) taxel frames in 0..8, HR (1, 100, 100) in 0..250)."""

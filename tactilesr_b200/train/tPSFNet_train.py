@@ -85,7 +85,7 @@ def build_dataloader(config, rank: int = 0, world: int = 1):
 def main(config):
     """reference main() :193-229."""
     from .. import set_precision
-    from .common import EvalHook, set_random_seed, setup_device
+    from .common import EvalHook, set_random_seed, setup_device, shutdown
     rank, world, device = setup_device()
     set_precision(config.get("_precision", "fp32"))
     set_random_seed(config["random_seed"])
@@ -99,6 +99,7 @@ def main(config):
     if trainer.train_by_epoch:
         trainer.register_hooks([EvalHook(1, lambda: eval_func(model, test_loader, config, device), names=("test_mse", "test_ssim"))])
     trainer.train(auto_resume=False)
+    shutdown()
     return trainer
 
 

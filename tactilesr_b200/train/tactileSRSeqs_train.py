@@ -49,7 +49,7 @@ def main(config, single_config=None):
 
     from .. import set_precision
     from ..config import tactileSR_config
-    from .common import EvalHook, set_random_seed, setup_device
+    from .common import EvalHook, set_random_seed, setup_device, shutdown
     from .tactileSR_train import build_dataloader, make_trainer
     from .tactileSR_train import build_model_and_optimizer as build_plain
     rank, world, device = setup_device()
@@ -65,6 +65,7 @@ def main(config, single_config=None):
     if trainer.train_by_epoch:
         trainer.register_hooks([EvalHook(1, lambda: eval_func(model, test_loader, config, device))])
     trainer.train(auto_resume=False)
+    shutdown()
     return trainer
 
 

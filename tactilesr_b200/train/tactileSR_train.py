@@ -103,7 +103,7 @@ def make_trainer(config, model, optimizer, train_loader, device):
 def main(config):
     """reference main() :199-242."""
     from .. import set_precision
-    from .common import EvalHook, set_random_seed, setup_device
+    from .common import EvalHook, set_random_seed, setup_device, shutdown
     rank, world, device = setup_device()
     set_precision(config.get("_precision", "fp16"))
     set_random_seed(config["random_seed"])           # identical initial weights on every rank
@@ -113,6 +113,7 @@ def main(config):
     if trainer.train_by_epoch:
         trainer.register_hooks([EvalHook(1, lambda: eval_func(model, test_loader, config, device))])
     trainer.train(auto_resume=False)
+    shutdown()
     return trainer
 
 

@@ -36,15 +36,18 @@ def _worker(rank, world, port, out):
     torch.manual_seed(100 + rank)
     flat = torch.randn(10_000)
     mine = flat.clone()
-    ar = D.GradAllReduce(flat, bucket_bytes=4 * 3000)
-    edges = [10_000, 9_000, 6_500, 6_400, 3_000, 1_234, 0]
-    for hi, lo in zip(edges[:-1], edges[1:]):
-        ar.ready(lo, hi)
-    ar.finish()
     other = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(other, mine)
     want = sum(other) / world
-    assert torch.allclose(flat, want, atol=1e-6), (flat - want).abs().max()
+    # both forms of the gradient average: bucketed while "backward" reports ranges, and one call after backward (default)
+    for overlap in (True, False):
+        flat.copy_(mine)
+        ar = D.GradAllReduce(flat, bucket_bytes=4 * 3000, overlap=overlap)
+        edges = [10_000, 9_000, 6_500, 6_400, 3_000, 1_234, 0]
+        for hi, lo in zip(edges[:-1], edges[1:]):
+            ar.ready(lo, hi)
+        ar.finish()
+        assert torch.allclose(flat, want, atol=1e-6), (overlap, (flat - want).abs().max())
     out.put((rank, float(flat.sum())))
     dist.barrier()
     dist.destroy_process_group()

@@ -280,3 +280,28 @@ def test_wgrad_tc_large_batch(Cin, Cout, KS, B):
     _lib.call("tsr_conv2d_wgrad_tc", x.data_ptr(), Cin, dy.data_ptr(), Cout, dw2.data_ptr(), ws.data_ptr(), ws.numel(), B, H, W,
               Cin, Cout, KS, 1, _st())
     assert torch.equal(dw2, dw + dw)
+
+
+@pytest.mark.parametrize("Cin,Cout,KS,B", [(64, 64, 3, 256), (64, 64, 5, 64), (128, 128, 3, 64), (128, 128, 5, 256), (256, 64, 1, 64),
+                                           (64, 64, 3, 1)])
+def test_wgrad_tc_fp16_activations(Cin, Cout, KS, B):
+    """The "fp16" mode hands the weight gradient its fp16 forward activations: the kernel converts every x halo tile to bf16
+    in shared memory (tcgen05 kind::f16 cannot mix fp16 x with bf16 dy).  Must equal -- bit for bit -- the gradient computed
+    from an explicit bf16 copy of x, and the fp64 gradient of that copy to summation-order accuracy."""
+    from tactilesr_b200 import _lib
+    L = _lib.lib()
+    torch.manual_seed(Cin + Cout + KS + B)
+    x16 = torch.randn(B, H, W, Cin, device="cuda").to(torch.float16)
+    xb = x16.to(torch.bfloat16)
+    dy = torch.randn(B, H, W, Cout, device="cuda").to(torch.bfloat16)
+    need = L.tsr_conv2d_wgrad_tc_workspace(B, H, W, Cin, Cout, KS)
+    ws = torch.empty(max(int(need), 256), dtype=torch.uint8, device="cuda")
+    dw16 = torch.zeros(Cout, Cin, KS, KS, device="cuda")
+    dwb = torch.zeros_like(dw16)
+    _lib.call("tsr_conv2d_wgrad_tc_x", x16.data_ptr(), Cin, 2, dy.data_ptr(), Cout, dw16.data_ptr(), ws.data_ptr(), ws.numel(), B, H, W,
+              Cin, Cout, KS, 0, _st())
+    _lib.call("tsr_conv2d_wgrad_tc_x", xb.data_ptr(), Cin, 1, dy.data_ptr(), Cout, dwb.data_ptr(), ws.data_ptr(), ws.numel(), B, H, W,
+              Cin, Cout, KS, 0, _st())
+    assert torch.equal(dw16, dwb)
+    ref = torch.nn.grad.conv2d_weight(_nchw(xb).double(), (Cout, Cin, KS, KS), _nchw(dy).double(), padding=KS // 2)
+    assert rel_l2(dw16, ref) < max(5e-5, 1.5e-7 * (B * H * W) ** 0.5)

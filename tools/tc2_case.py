@@ -50,6 +50,12 @@ elif case in ("fwd3x3_128", "fwd3x3_64"):
     else:
         fn = lambda: _lib.call("tsr_conv2d_tc", x.data_ptr(), C, wf.data_ptr(), bias.data_ptr(), 0, 0, out.data_ptr(), C, B, H, W, C, C, 3, 2,
                                0, 0, part.data_ptr(), 0, 0, st)
+elif case == "fwd5x5_128":        # the roofline kernel of bench.py: MSRB conv_5_2 forward shape, no epilogue extras
+    w = torch.randn(128, 128, 5, 5, device=dev) * 0.02
+    wf = pack(w, True)
+    x = torch.randn(B, H, W, 128, device=dev).to(f16)
+    out = torch.empty_like(x)
+    fn = lambda: _lib.conv_tc2([(x.data_ptr(), 128, 128, 5, wf.data_ptr())], out.data_ptr(), 128, B, H, W, 128, flags=_lib.TC2_F16)
 elif case.startswith("wgrad"):          # wgrad5x5_128 | wgrad3x3_128 | wgrad5x5_64 | wgrad3x3_64
     KS = int(case[5])
     C = int(case.split("_")[1])
