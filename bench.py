@@ -493,6 +493,7 @@ def run_ours(args):
     if world == 1:
         from tactilesr_b200 import engine as E
         tr._data_iter = iter(Loader(devb))
+        use_graph, tr._use_graph = tr._use_graph, False      # (the breakdown times the ops of an eager iteration)
         tr.train_one_iter()
         torch.cuda.synchronize()
         E.profile_begin()
@@ -503,6 +504,7 @@ def run_ours(args):
         cls = E.profile_end()
         breakdown = {k: round(v, 3) for k, v in sorted(cls.items(), key=lambda kv: -kv[1])}
         breakdown["step_total_with_event_overhead"] = round(e0.elapsed_time(e1), 3)
+        tr._use_graph = use_graph
 
     extras = {}
     if world == 1 and not args.no_extras:

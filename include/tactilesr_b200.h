@@ -40,6 +40,7 @@ int tsr_check_device(void);               /* 0 iff the current device is compute
 void tsr_set_f16_overflow_flag(int* flag_dev);
 long long tsr_launch_count(void);         /* kernels launched by this library since the last reset */
 void tsr_launch_count_reset(void);
+void tsr_launch_count_add(long long n);   /* account n launches replayed from a captured CUDA graph */
 
 /* ---- fp32-accurate convolutions (FFMA implicit GEMM) -------------------------------------------------------- */
 /* nn.Conv2d weights (model/tactileSR_model.py:41,47,53,168,174,180,186,191,219,220) -> [tap][ci][co] (forward) and
@@ -77,6 +78,11 @@ int tsr_tail_fwd(const void* in, int in_ld, int in_bf16, const float* w_oihw, fl
                  int relu, tsr_stream_t stream);
 int tsr_tail_dgrad(const float* dout, const float* out_act, const float* w_oihw, void* din, int din_ld, int din_bf16,
                    int B, int H, int W, int Cin, int relu, tsr_stream_t stream);
+/* the same, with the ReLU backward of the layer that produced the tail's input fused in: din = dgrad * [in_act > 0]
+   (in_act: that layer's stored activation, in_dtype 1 = bf16 / 2 = fp16) */
+int tsr_tail_dgrad_masked(const float* dout, const float* out_act, const float* w_oihw, void* din, int din_ld, int din_bf16,
+                          int B, int H, int W, int Cin, int relu, const void* in_act, int in_ld, int in_dtype,
+                          tsr_stream_t stream);
 size_t tsr_tail_wgrad_workspace(int B, int H, int W, int Cin);
 int tsr_tail_wgrad(const void* in, int in_ld, int in_bf16, const float* dout, const float* out_act, float* dw_oihw,
                    void* workspace, size_t ws_bytes, int B, int H, int W, int Cin, int relu, int accumulate,

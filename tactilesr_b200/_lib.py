@@ -24,6 +24,7 @@ SIGNATURES = {
     "tsr_set_f16_overflow_flag": (None, [_P]),
     "tsr_launch_count": (_L, []),
     "tsr_launch_count_reset": (None, []),
+    "tsr_launch_count_add": (None, [_L]),
     # fp32 convolutions
     "tsr_pack_conv_weight_f32": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "tsr_conv2d_f32": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
@@ -36,6 +37,7 @@ SIGNATURES = {
     "tsr_head_wgrad": (_I, [_P, _L, _P, _I, _I, _P, _P, _Z, _I, _I, _I, _P]),
     "tsr_tail_fwd": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "tsr_tail_dgrad": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "tsr_tail_dgrad_masked": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     "tsr_tail_wgrad_workspace": (_Z, [_I, _I, _I, _I]),
     "tsr_tail_wgrad": (_I, [_P, _I, _I, _P, _P, _P, _P, _Z, _I, _I, _I, _I, _I, _I, _P]),
     # elementwise / reductions

@@ -503,6 +503,8 @@ class Trainer:
             graph = torch.cuda.CUDAGraph()
             # data parallel: the bucketed NCCL all-reduces of backward (side stream, forked / joined by events) are captured
             # with the iteration, so the replay keeps the overlap; every rank captures the same sequence
+            from .. import _lib
+            n0 = _lib.launch_count()
             with torch.cuda.graph(graph):
                 losses, loss_dict = self.train_cal_loss(tuple(static))
                 opt.zero_grad()
@@ -510,15 +512,18 @@ class Trainer:
                 if self._dp is not None:
                     self._dp.finish()
                 opt.step()                   # (host side of this call advanced the step counters once)
+            nk = _lib.launch_count() - n0       # kernels of this library inside the graph (counted again at every replay)
             graph.replay()
-            entry = (graph, static, loss_dict)
+            entry = (graph, static, loss_dict, nk)
             self._graphs[key] = entry
             return loss_dict
-        graph, static, loss_dict = entry
+        graph, static, loss_dict, nk = entry
         for s_, t in zip(static, batch):
             s_.copy_(t, non_blocking=True)
         opt.update_graph_hyper()
         graph.replay()
+        from .. import _lib
+        _lib.lib().tsr_launch_count_add(nk)
         opt.graph_advance()
         return loss_dict
 

@@ -591,7 +591,7 @@ template <typename GT>
 __global__ void __launch_bounds__(256)
 tail_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out_act,
                   const float* __restrict__ w, GT* __restrict__ din, int din_ld, int B, int H, int W,
-                  int Cin, int relu) {
+                  int Cin, int relu, const void* __restrict__ in_act, int in_ld, int in_f16) {
   extern __shared__ float dz[];                     // (TAIL_TR + 2) x (W + 2), zero ring
   const int strips = (H + TAIL_TR - 1) / TAIL_TR;
   const int PW = W + 2, PH = TAIL_TR + 2;
@@ -631,7 +631,15 @@ tail_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out_
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv, wr[t][j], acc[j]);
         }
-        GT* dst = din + (((long long)b * H + y0 + ty) * W + x) * din_ld + g * 8;
+        const long long pixel = ((long long)b * H + y0 + ty) * W + x;
+        if (in_act) {        // ReLU backward of the layer that produced the tail's input: zero where its activation is <= 0
+          float a8[8];
+          if (in_f16) V16<__half>::load(reinterpret_cast<const __half*>(in_act) + pixel * in_ld + g * 8, a8);
+          else V16<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(in_act) + pixel * in_ld + g * 8, a8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = a8[j] > 0.f ? acc[j] : 0.f;
+        }
+        GT* dst = din + pixel * din_ld + g * 8;
         st4(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
         st4(dst + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
         x += 16;
@@ -867,14 +875,34 @@ int tsr_tail_fwd(const void* in, int in_ld, int in_bf16, const float* w_oihw, fl
   return TSR_OK;
 }
 
+static int tail_dgrad_impl(const float* dout, const float* out_act, const float* w_oihw, void* din, int din_ld,
+                           int din_bf16, int B, int H, int W, int Cin, int relu, const void* in_act, int in_ld, int in_dtype,
+                           cudaStream_t stream);
+
 int tsr_tail_dgrad(const float* dout, const float* out_act, const float* w_oihw, void* din, int din_ld,
                    int din_bf16, int B, int H, int W, int Cin, int relu, cudaStream_t stream) {
+  return tail_dgrad_impl(dout, out_act, w_oihw, din, din_ld, din_bf16, B, H, W, Cin, relu, nullptr, 0, 0, stream);
+}
+
+// tsr_tail_dgrad that also applies the ReLU backward of the layer that PRODUCED the tail's input (in_act: its stored 16-bit
+// activation, in_dtype 1 = bf16 / 2 = fp16): din = dgrad * [in_act > 0] -- saves a separate tsr_relu_backward pass
+int tsr_tail_dgrad_masked(const float* dout, const float* out_act, const float* w_oihw, void* din, int din_ld, int din_bf16,
+                          int B, int H, int W, int Cin, int relu, const void* in_act, int in_ld, int in_dtype,
+                          cudaStream_t stream) {
+  TSR_REQUIRE(in_act && (in_dtype == TSR_DT_BF16 || in_dtype == TSR_DT_F16) && in_ld % 8 == 0 && ((uintptr_t)in_act & 15) == 0,
+              "tail_dgrad_masked: needs a 16-byte aligned 16-bit activation");
+  return tail_dgrad_impl(dout, out_act, w_oihw, din, din_ld, din_bf16, B, H, W, Cin, relu, in_act, in_ld, in_dtype, stream);
+}
+
+static int tail_dgrad_impl(const float* dout, const float* out_act, const float* w_oihw, void* din, int din_ld,
+                           int din_bf16, int B, int H, int W, int Cin, int relu, const void* in_act, int in_ld, int in_dtype,
+                           cudaStream_t stream) {
   TSR_REQUIRE(dout && w_oihw && din && (!relu || out_act), "tail_dgrad: null pointer");
   TSR_REQUIRE(Cin % 4 == 0 && din_ld % 4 == 0, "tail_dgrad: Cin must be a multiple of 4");
   TSR_REQUIRE(Cin % 8 == 0, "tail_dgrad: Cin must be a multiple of 8");
   const int strips = (H + TAIL_TR - 1) / TAIL_TR;
   const size_t smem = (size_t)(TAIL_TR + 2) * (W + 2) * sizeof(float);
-  TSR_DISPATCH_T(din_bf16, T, tail_dgrad_kernel<T><<<(B * strips < 148 * 6 ? B * strips : 148 * 6), 256, smem, stream>>>(dout, out_act, w_oihw, (T*)din, din_ld, B, H, W, Cin, relu));
+  TSR_DISPATCH_T(din_bf16, T, tail_dgrad_kernel<T><<<(B * strips < 148 * 6 ? B * strips : 148 * 6), 256, smem, stream>>>(dout, out_act, w_oihw, (T*)din, din_ld, B, H, W, Cin, relu, in_act, in_ld, in_dtype == TSR_DT_F16));
   TSR_CHECK_LAUNCH("tail_dgrad");
   return TSR_OK;
 }

@@ -14,7 +14,8 @@ namespace {
 constexpr int NUM_THREADS = 224;
 
 // experiment switches (env TSR_TC_MODE or tsr_set_tc_desc_mode), read by the engine: bit 7 = BatchNorm statistics in a separate
-// pass instead of the conv epilogue, bit 8 = no fused gradient sinks, bit 9 = no dual-branch forward.
+// pass instead of the conv epilogue, bit 8 = no fused gradient sinks, bit 9 = no dual-branch forward, bit 10 = no bf16 shadows
+// in the "fp16" mode (the weight gradient converts fp16 x tiles in shared memory instead).
 static int env_mode() { const char* e = getenv("TSR_TC_MODE"); return e ? atoi(e) : 0; }
 int g_desc_mode = env_mode();
 
@@ -249,8 +250,11 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   } else if (warp >= 3) {
     if (p.x_f16) {
       // ===== fp16 -> bf16 conversion of the x halo tile(s) of every stage, in place (element-wise: the swizzled layout is
-      // untouched), by the four warps that otherwise idle until the epilogue.  The weight gradient then reads the forward
-      // activations directly: no bf16 "shadow" copy of every conv input has to be written by the forward pass. =====
+      // untouched), by the four warps that otherwise idle until the epilogue.  The weight gradient can then read the forward
+      // activations directly, without a bf16 "shadow" copy in HBM (9 MB per sample).  Measured at B = 1024: the 64-channel
+      // layers pay +20 %, the 128-channel layers +60..95 % -- their MMAs (4 KB of A + 4 KB of B per 64 cycles) already take
+      // the whole shared-memory bandwidth and the conversion adds 72 B/clk on top -- so the engine keeps the shadows by
+      // default and uses this path only when memory matters (TSR_TC_MODE bit 10). =====
       const int ct = threadIdx.x - 96;             // 0..127
       const uint32_t xbytes = (uint32_t)p.P * p.P * 128u;
       int st = 0;
@@ -260,16 +264,28 @@ wgrad_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         uint8_t* xs = smem_raw + (base - smem_u32(smem_raw)) + (size_t)st * p.stage_bytes + p.dy_stage_bytes;
         for (int h = 0; h < nxt; ++h) {
           uint4* v = reinterpret_cast<uint4*>(xs + (size_t)h * p.xtile_bytes);
-          for (uint32_t k = ct; k < xbytes / 16u; k += 128u) {
-            uint4 u = v[k];
-            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          const uint32_t nvec = xbytes / 16u;
+          // six 16-byte vectors in flight per thread (loads first, then conversions, then stores): an element-at-a-time
+          // loop is a chain of shared-memory latencies and made this warp group, not the tensor pipe, the stage's pace
+          for (uint32_t k0 = ct; k0 < nvec; k0 += 6u * 128u) {
+            uint4 u[6];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-              const __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);
-              w[j] = *reinterpret_cast<const uint32_t*>(&b);
+            for (int e = 0; e < 6; ++e)
+              if (k0 + e * 128u < nvec) u[e] = v[k0 + e * 128u];
+#pragma unroll
+            for (int e = 0; e < 6; ++e) {
+              uint32_t w[4] = {u[e].x, u[e].y, u[e].z, u[e].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+                const __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);
+                w[j] = *reinterpret_cast<const uint32_t*>(&b);
+              }
+              u[e] = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            v[k] = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+            for (int e = 0; e < 6; ++e)
+              if (k0 + e * 128u < nvec) v[k0 + e * 128u] = u[e];
           }
         }
         fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core's async-proxy reads

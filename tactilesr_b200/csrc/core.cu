@@ -25,6 +25,8 @@ int tsr_version(void) { return 100; }
 long long tsr_launch_count_inc(int n) { return g_launches.fetch_add(n) + n; }
 long long tsr_launch_count(void) { return g_launches.load(); }
 void tsr_launch_count_reset(void) { g_launches.store(0); }
+// kernels launched on the library's behalf without passing through its entry points: a CUDA-graph replay of n captured launches
+void tsr_launch_count_add(long long n) { g_launches.fetch_add(n); }
 
 // "fp16" precision mode: a sticky device int that the kernels storing fp16 activations (tsr_conv2d_tc2 with TSR_TC2_F16,
 // tsr_bn_apply with fp16 output) set to 1 when a value they store is not finite (|x| > 65504 or NaN).  The caller owns

@@ -11,8 +11,10 @@ Three numeric modes (``tactilesr_b200.set_precision``):
   * "bf16": activations and gradients bf16, tcgen05 implicit-GEMM kernels (conv_tc.cu), fp32 accumulate/statistics.
   * "fp16": same tcgen05 kernels at the same speed, but activations and forward weights are stored as fp16
     (10 mantissa bits, the TF32 mantissa: ~8x less rounding error than bf16 -- the <= 1e-2 tensor-core mode);
-    gradients stay bf16 (range matters there); tcgen05 kind::f16 rejects fp16 x bf16 operands, so the weight-gradient
-    kernel converts its fp16 x tiles to bf16 in shared memory (no second copy of the activations in HBM).
+    gradients stay bf16 (range matters there); tcgen05 kind::f16 rejects fp16 x bf16 operands, so when gradients
+    are needed every conv keeps a bf16 copy ("shadow") of its input for the weight-gradient kernel.  (TSR_TC_MODE bit 10
+    trades them for an in-kernel conversion: 9 MB per sample less memory, but the 128-channel weight gradients run ~1.8x
+    slower -- their MMAs already take the whole shared-memory bandwidth, measured in round 2.)
 """
 from __future__ import annotations
 
@@ -152,6 +154,11 @@ class RunCtx:
         self.saved: Dict[object, tuple] = {}
         self.x: Optional[torch.Tensor] = None
         self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        # "fp16" mode with gradients: bf16 shadow of every buffer some conv reads (the weight-gradient operand; tcgen05
+        # kind::f16 cannot mix an fp16 x with a bf16 dy).  Producers write their channel slice of the shadow.
+        self.shadow: Dict[Buf, torch.Tensor] = {}
+        self.conv_inputs: set = set()
+        self.no_shadow = bool(_lib.lib().tsr_get_tc_desc_mode() & 1024) if self.tc else False
         self.bn_partials: Dict[object, torch.Tensor] = {}      # BNReLUOp -> statistics partials from its convs' epilogues
         self.bn_partials_parts: Dict[object, set] = {}         # ... and which of its parts they cover
         self.folded: Dict[object, set] = {}                    # BNReLUOp -> parts already applied by their (inference) conv
@@ -188,6 +195,24 @@ class RunCtx:
             self.grads[buf] = t
             self.grad_written[buf] = False
         return t
+
+    def wants_shadow(self, buf: Buf) -> bool:
+        return self.act == 2 and self.need_grad and not self.no_shadow and buf in self.conv_inputs
+
+    def sptr(self, v: View) -> Tuple[int, int]:
+        """(pointer, ld) of view v inside the bf16 shadow of its buffer."""
+        t = self.shadow.get(v.buf)
+        if t is None:
+            t = torch.empty((self.npix, v.buf.C), dtype=torch.bfloat16, device=self.device)
+            self.shadow[v.buf] = t
+        return t.data_ptr() + v.c0 * 2, v.buf.C
+
+    def shadow_fill(self, v: View) -> None:
+        """Copy the freshly written fp16 view into the shadow (producers without a fused second output)."""
+        if self.wants_shadow(v.buf):
+            ip, ild = self.vptr(v)
+            sp, sld = self.sptr(v)
+            _lib.call("tsr_copy_channels", ip, ild, 2, sp, sld, 1, self.npix, v.C, _lib.stream_ptr())
 
     def stat_table(self, bnop, part: int) -> torch.Tensor:
         """Zeroed [rows][2][channels of bnop] table that the conv epilogue(s) feeding ``bnop`` add their statistics to."""
@@ -454,6 +479,7 @@ class HeadOp(Op):
         op, old = c.vptr(self.out)
         _lib.call("tsr_head_fwd", xp, xbs, self.weight.data_ptr(), op, old, c.act, c.B, self.sf,
                   1 if self.relu else 0, _lib.stream_ptr())
+        c.shadow_fill(self.out)
 
     def bwd(self, c):
         st = _lib.stream_ptr()
@@ -552,6 +578,9 @@ class ConvOp(Op):
                 off = self.bn_consumer.parts[self.bn_part][1]
                 kw.update(stat=t.data_ptr() + off * 4, stat_ld=t.shape[2])
                 flags |= _lib.TC2_STAT_PRECLEARED
+        if c.wants_shadow(self.out.buf):     # bf16 shadow of an fp16 output straight from the epilogue
+            o2, o2ld = c.sptr(self.out)
+            kw.update(out2=o2, out2_ld=o2ld)
         _lib.conv_tc2([(ip, ild, self.Cin, self.K, wf.data_ptr())], op, old, c.B, c.H, c.W, self.Cout, flags=flags,
                       bias=_ptr(self.conv.bias), residual=rp, res_ld=rld, stream=st, **kw)
 
@@ -595,10 +624,13 @@ class ConvOp(Op):
         if c.tc:
             need = _lib.lib().tsr_conv2d_wgrad_tc_workspace(c.B, c.H, c.W, self.Cin, self.Cout, self.K)
             ws, wsb = c.workspace(need)
-            # the conv input as the forward stored it (bf16, or fp16 in the "fp16" mode: the kernel converts its x tiles to
-            # bf16 in shared memory -- tcgen05 kind::f16 cannot mix an fp16 x with the bf16 dy)
-            xp, xld = c.vptr(self.src)
-            _lib.call("tsr_conv2d_wgrad_tc_x", xp, xld, c.act, gp, gld, g.data_ptr(), ws, wsb, c.B, c.H, c.W, self.Cin,
+            # x as bf16: the activation itself (bf16 mode), its bf16 shadow (fp16 mode), or -- without shadows -- the fp16
+            # activation, converted in shared memory by the kernel
+            if c.act == 2 and not c.no_shadow:
+                (xp, xld), xdt = c.sptr(self.src), 1
+            else:
+                (xp, xld), xdt = c.vptr(self.src), c.act
+            _lib.call("tsr_conv2d_wgrad_tc_x", xp, xld, xdt, gp, gld, g.data_ptr(), ws, wsb, c.B, c.H, c.W, self.Cin,
                       self.Cout, self.K, acc, st)
         else:
             ip, ild = c.vptr(self.src)
@@ -820,8 +852,9 @@ class BNReLUOp(Op):
                 _lib.call("tsr_bn_eval_coeffs", C, bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
                           bn.running_var.data_ptr(), bn.eps, sc, sh, mu, iv, st)
         op, old = c.vptr(self.out)
+        o2, o2ld = c.sptr(self.out) if c.wants_shadow(self.out.buf) else (0, 0)
         _lib.call("tsr_bn_apply", yp, yld, c.act, coef[0].data_ptr(), coef[1].data_ptr(), op, old, c.act, c.npix, Ct,
-                  1 if self.relu else 0, 0, 0, st)
+                  1 if self.relu else 0, o2, o2ld, st)
         c.saved[self] = (coef, used)
 
     def bwd(self, c):
@@ -864,6 +897,7 @@ class TailOp(Op):
 
     def __init__(self, src: View, conv: torch.nn.Conv2d, out: Buf, relu: bool = True):
         self.src, self.conv, self.out, self.relu = src, conv, out, relu
+        self.mask_input = False            # Program.plan(): the only writer of the gradient of a ReLU-conv output
         assert conv.out_channels == 1 and conv.kernel_size == (3, 3) and conv.bias is None
 
     def params(self):
@@ -895,6 +929,12 @@ class TailOp(Op):
         first = _first_write(c, self.src.buf)
         assert first
         dp, dld = c.vptr(self.src, grad=True)
+        if self.mask_input and c.tc:
+            # the tail's input is the ReLU output of one convolution (Program.plan()): its ReLU backward is applied here
+            _lib.call("tsr_tail_dgrad_masked", dout.data_ptr(), out.data_ptr(), self.conv.weight.data_ptr(), dp, dld, c.grd, c.B,
+                      c.H, c.W, self.src.C, 1 if self.relu else 0, ip, ild, c.act, st)
+            c.grad_masked.add(self.src.buf)
+            return
         _lib.call("tsr_tail_dgrad", dout.data_ptr(), out.data_ptr(), self.conv.weight.data_ptr(), dp, dld, c.grd, c.B,
                   c.H, c.W, self.src.C, 1 if self.relu else 0, st)
 
@@ -916,6 +956,7 @@ class InputOp(Op):
         t = c.alloc(self.out)
         _lib.call("tsr_nchw_to_nhwc", x.data_ptr(), t.data_ptr(), self.out.C, c.act, c.B, self.out.C, c.H * c.W,
                   _lib.stream_ptr())
+        c.shadow_fill(View.of(self.out))
 
     def bwd(self, c):
         pass
@@ -970,6 +1011,11 @@ class Program:
                     op.sink = Sink("relu")
             if len(ws) == 2 and ws[1][3] == "res" and kind == "conv" and ws[1][2].c0 == v.c0 and ws[1][2].C == v.C:
                 ws[1][1].alias_residual_grad = True
+            if isinstance(op, TailOp) and len(ws) == 1 and whole:
+                prods = producers.get(buf, [])
+                if (prods and all(isinstance(pr, (ConvOp, HeadOp)) and pr.relu for pr, _ in prods)
+                        and sum(pv.C for _, pv in prods) == buf.C):
+                    op.mask_input = True
 
     def parameters(self) -> List[torch.nn.Parameter]:
         seen, out = set(), []
@@ -1003,6 +1049,7 @@ def run_forward(prog: Program, x: torch.Tensor, training: bool, need_grad: bool,
     if c.act == 2:
         _arm_overflow_guard(x.device)
     prog.plan()
+    c.conv_inputs = {op.src.buf for op in prog.ops if isinstance(op, (ConvOp, DualConvOp))}
     c.keep_taps = keep_taps
     if c.tc and (training or need_grad):
         seen, items = set(), []

@@ -149,3 +149,17 @@ for C in (64, 128):
     new = timeit_dbg(lambda i: _lib.conv_tc2(srcs(i), dx[i].data_ptr(), C, B, H, W, C, flags=_lib.TC2_MASK | _lib.TC2_AUX_F16,
                                          aux=y[i].data_ptr(), aux_ld=C, residual=res[i].data_ptr(), res_ld=C))
     report(f"dual dgrad {C} + residual + ReLU mask", fl, new)
+
+# weight gradients: bf16 x (no conversion) vs fp16 x (converted to bf16 in shared memory by the idle warps)
+for Cin, Cout, KS in [(64, 64, 3), (64, 64, 5), (128, 128, 3), (128, 128, 5), (256, 64, 1)]:
+    xb = act(Cin, bf); xh = act(Cin, f16); dy = act(Cout, bf)
+    need = L.tsr_conv2d_wgrad_tc_workspace(B, H, W, Cin, Cout, KS)
+    ws = torch.empty(max(int(need), 256), dtype=torch.uint8, device=dev)
+    dw = torch.zeros(Cout, Cin, KS, KS, device=dev)
+    tb_ = timeit(lambda i: _lib.call("tsr_conv2d_wgrad_tc_x", xb[i].data_ptr(), Cin, 1, dy[i].data_ptr(), Cout, dw.data_ptr(), ws.data_ptr(),
+                                     ws.numel(), B, H, W, Cin, Cout, KS, 0, st))
+    th_ = timeit(lambda i: _lib.call("tsr_conv2d_wgrad_tc_x", xh[i].data_ptr(), Cin, 2, dy[i].data_ptr(), Cout, dw.data_ptr(), ws.data_ptr(),
+                                     ws.numel(), B, H, W, Cin, Cout, KS, 0, st))
+    fl = 2.0 * npix * Cin * Cout * KS * KS
+    print(f"wgrad {Cin}->{Cout} {KS}x{KS}: bf16 x {tb_:8.1f} us {fl / tb_ / 1e6:7.1f} TF/s | fp16 x (in-smem conversion) {th_:8.1f} us {fl / th_ / 1e6:7.1f} TF/s",
+          flush=True)
