@@ -407,6 +407,16 @@ def measure_extras(dev, model, B):
             out["psf_bwd_kernel"] = {"samples_per_s": Bp / (ms_b * 1e-3), "GBps_compulsory": Bp / (ms_b * 1e-3) * 44924 / 1e9,
                                      "hbm_frac": Bp / (ms_b * 1e-3) * 44924 / 1e9 / peaks()["hbm"], "batch": Bp,
                                      "tensor_TFLOPs": Bp / (ms_b * 1e-3) * 4 * 3 * 2 * 128 * 112 * 112 / 1e12}
+            # the single-pass fp16 variants the 16-bit precision modes use (same compulsory bytes, a third of the MMAs)
+            ms_f = timeit(lambda: _lib.call("tsr_psf_forward_tc_f16", ab.data_ptr(), d3.data_ptr(), HR.data_ptr(), LRd.data_ptr(),
+                                            psf.data_ptr(), 0, Bp, st), 10)
+            ms_b = timeit(lambda: _lib.call("tsr_psf_backward_tc_f16", ab.data_ptr(), d3.data_ptr(), aux.data_ptr(), dL.data_ptr(),
+                                            dab.data_ptr(), Bp, st), 10)
+            out["psf_fwd_kernel_f16"] = {"samples_per_s": Bp / (ms_f * 1e-3), "GBps_compulsory": Bp / (ms_f * 1e-3) * 119472 / 1e9,
+                                         "hbm_frac": Bp / (ms_f * 1e-3) * 119472 / 1e9 / peaks()["hbm"], "batch": Bp}
+            out["psf_bwd_kernel_f16"] = {"samples_per_s": Bp / (ms_b * 1e-3), "GBps_compulsory": Bp / (ms_b * 1e-3) * 44924 / 1e9,
+                                         "hbm_frac": Bp / (ms_b * 1e-3) * 44924 / 1e9 / peaks()["hbm"], "batch": Bp,
+                                         "tensor_TFLOPs": Bp / (ms_b * 1e-3) * 4 * 2 * 128 * 112 * 112 / 1e12}
     return out
 
 

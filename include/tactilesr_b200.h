@@ -163,15 +163,20 @@ int tsr_linear_bwd(const float* dy, const float* out, const float* x, const floa
  * alphaBeta (B,3), depth (B,100,100) -> HR (B,100,100), LRd (B,16), psf (B,99,99; may be NULL). */
 int tsr_psf_forward(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, int B,
                     tsr_stream_t stream);
-/* the two implementations behind tsr_psf_forward: tcgen05 (fp16 hi/lo split operands, fp32-accurate; default) and FFMA;
- * tsr_set_psf_mode(0 | 1) selects which one tsr_psf_forward runs.  The tcgen05 forward can leave per-row statistics of
- * HR in `aux` (B x tsr_psf_aux_floats() floats, 16-byte aligned, may be NULL) for tsr_psf_backward_tc, the tcgen05
+/* the implementations behind tsr_psf_forward: tcgen05 with fp16 hi/lo split operands (fp32-accurate; default, mode 0),
+ * FFMA (mode 1) and tcgen05 with ONE fp16 pass (~3e-4; the 16-bit tensor-core precision modes, mode 2);
+ * tsr_set_psf_mode(0 | 1 | 2) selects which one tsr_psf_forward runs.  The tcgen05 forwards can leave per-row statistics
+ * of HR in `aux` (B x tsr_psf_aux_floats() floats, 16-byte aligned, may be NULL) for tsr_psf_backward_tc[_f16], the tcgen05
  * backward of the training case (gradient through LR_degrade only, train/tPSFNet_train.py:186-189). */
 size_t tsr_psf_aux_floats(void);
 int tsr_psf_forward_tc(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, float* aux, int B,
                        tsr_stream_t stream);
 int tsr_psf_backward_tc(const float* alphaBeta, const float* depth, const float* aux, const float* dLRd,
                         float* dalphaBeta, int B, tsr_stream_t stream);
+int tsr_psf_forward_tc_f16(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, float* aux, int B,
+                           tsr_stream_t stream);
+int tsr_psf_backward_tc_f16(const float* alphaBeta, const float* depth, const float* aux, const float* dLRd,
+                            float* dalphaBeta, int B, tsr_stream_t stream);
 int tsr_psf_forward_ffma(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, int B,
                          tsr_stream_t stream);
 void tsr_set_psf_mode(int mode);

@@ -67,6 +67,8 @@ SIGNATURES = {
     "tsr_psf_forward": (_I, [_P, _P, _P, _P, _P, _I, _P]),
     "tsr_psf_forward_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
     "tsr_psf_backward_tc": (_I, [_P, _P, _P, _P, _P, _I, _P]),
+    "tsr_psf_forward_tc_f16": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
+    "tsr_psf_backward_tc_f16": (_I, [_P, _P, _P, _P, _P, _I, _P]),
     "tsr_psf_aux_floats": (_Z, []),
     "tsr_psf_forward_ffma": (_I, [_P, _P, _P, _P, _P, _I, _P]),
     "tsr_set_psf_mode": (None, [_I]),

@@ -1,24 +1,31 @@
-// tPSFNet point-spread-function forward model on the tensor cores (tcgen05 / TMEM), fp32-accurate.
+// tPSFNet point-spread-function forward model on the tensor cores (tcgen05 / TMEM).
 //
 // Same contract as psf_fwd_kernel (psf.cu): replaces the python per-sample loop of reference model/tPSFNet.py:118-125
 // (tactilePSF :78-83, depth2tactile :85-100, degradation_process :129-141).  The 99x99 correlation is separable
 // (SURVEY.md Appendix B):  conv = alpha * E D E,  E[m][k] = e(|k-m|) for |k-m| <= 49 else 0,  e(t) = exp(-cp2 t^2 / beta^2)
-// (100x100, symmetric banded Toeplitz, different for every sample because beta is), i.e. two dense 100^3 contractions per sample = 4 MFLOP against
-// 119 KB of compulsory HBM traffic: on FFMA pipes that is 3x over the HBM time, so the two products run as tcgen05.mma.
+// (100x100, symmetric banded Toeplitz, different for every sample because beta is), i.e. two dense 100^3 contractions per
+// sample = 4 MFLOP against 119 KB of compulsory HBM traffic: on FFMA pipes that is 3x over the HBM time, so the two products
+// run as tcgen05.mma.
 //
-// fp32 accuracy from 16-bit operands: every operand is split x = hi + lo into two fp16 numbers (power-of-two pre-scaling
-// keeps both halves in fp16's normal range) and each product is three MMAs  hi*hi + lo*hi + hi*lo  accumulated in fp32
-// in TMEM (the dropped lo*lo term is 2^-22 relative).  Measured against the fp64 reference run: ~1e-6 rel-L2.
+// Two arithmetic variants (template PASSES):
+//   3  fp32-accurate (the "fp32" precision mode): every operand is split x = hi + lo into two fp16 numbers (power-of-two
+//      pre-scaling keeps both halves in fp16's normal range) and each product is three MMAs  hi*hi + lo*hi + hi*lo
+//      accumulated in fp32 in TMEM (the dropped lo*lo term is 2^-22 relative).  ~1e-6 rel-L2 against the fp64 reference run.
+//   1  one fp16 pass (the 16-bit tensor-core precision modes, tolerance 1e-2): a third of the MMAs, half of the operand
+//      tiles and conversions.  ~3e-4 rel-L2.
 //
-// Per sample (one CTA, 256 threads; two CTAs per SM overlap each other's phases):
-//   A  depth plane -> registers (its only global read: 32 contiguous bytes per thread and item); tables e(t), Ex_i(t);
-//      depth max (contact threshold);  E -> smem (K-major SWIZZLE_128B, hi and lo tiles);  depth -> smem as it lies in
-//      HBM (row = k: the MN-major B operand, hi and lo tiles) + contact-mask bytes
-//   B  GEMM1  T = E * D      (M=128, N=112, K=7x16; 21 MMAs)      -> TMEM columns [0,112)
-//      (the psf output, a pure function of alpha / beta, is written to HBM while GEMM1 runs)
-//   X  T: TMEM -> registers -> hi/lo fp16 -> smem, over the dead depth tiles (all 8 warps: 4 lane quarters x 2 halves)
-//   C  GEMM2  HR = T * E     (E symmetric: the same E tiles are the B operand)   -> TMEM columns [128,240)
-//   E  epilogue: second-max fill (tPSFNet.py:95-97), HR store, LRd = 1e-4 (Ex HR Ex^T - m sum HR) / (1 - m)
+// Per sample (one CTA, 256 threads; two CTAs per SM overlap each other's phases; 6 block barriers per sample):
+//   A  the depth plane arrives in shared memory by ONE bulk copy issued a sample ahead (over the dead depth tiles, or
+//      -- PASSES 1 -- into its own buffer); plane -> registers; depth max (contact threshold) and |max| (scaling) in one
+//      block reduction; tables e(t), Ex_i(t);  depth -> smem as it lies in HBM (row = k: the MN-major B operand) +
+//      contact-mask bytes;  E -> smem (K-major SWIZZLE_128B)
+//   B  GEMM1  T = E * D      (M=128, N=112, K=7x16)   -> TMEM columns [0,112)
+//      (the psf output, a pure function of alpha / beta, is written to HBM while the MMAs run)
+//   X  T: TMEM -> registers -> fp16 (hi, lo) -> TMEM columns [128,240) (tcgen05.st): GEMM2 takes its A operand straight
+//      from tensor memory, so T never touches shared memory
+//   C  GEMM2  HR = T * E     (E symmetric: the same E tiles are the B operand)   -> TMEM columns [0,112)
+//   E  epilogue, ONE pass over the accumulator held in registers: second-max fill (tPSFNet.py:95-97), HR rows staged in
+//      shared memory (over the dead E tiles) and stored by one bulk copy, LRd = 1e-4 (Ex HR Ex^T - m sum HR) / (1 - m)
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -32,21 +39,44 @@ constexpr float CM2 = 100.0f / 15138.0f;
 constexpr uint32_t ROWS = 104;                 // allocated rows of a tile (13 groups of 8); MMAs over-read up to row 127
 constexpr uint32_t ATOM = ROWS * 128u;         // one 64-wide atom: rows x 128 B, SWIZZLE_128B
 constexpr uint32_t TILE = 2u * ATOM;           // 112 = 64 + 48 elements along the atom direction
-// X tiles first: GEMM1 reads K rows 96..111 of the (MN-major) depth tiles, i.e. 1 KB past a tile's 104 rows -- for X_lo
-// that lands in E_hi (always finite; it meets the zero K-padding of E).  Over-reads of M / N rows >= 104 only produce
-// accumulator rows / columns that are never used.
-constexpr uint32_t OFF_X_HI = 0, OFF_X_LO = TILE, OFF_E_HI = 2 * TILE, OFF_E_LO = 3 * TILE;
-constexpr uint32_t OFF_TAB = 4 * TILE;                       // float e(t), t = 0..99 (+ pad)
-constexpr uint32_t TAB2_LEN = 208;                           // per shifted copy
-constexpr uint32_t OFF_TAB2 = OFF_TAB + 128 * 4;             // 4 shifted copies of uint32 (hi | lo << 16) of 16 e(|j - 99|) [banded]
-constexpr uint32_t OFF_EX = OFF_TAB2 + 4 * TAB2_LEN * 4;     // float4 (Ex_0..Ex_3)(t), t = 0..99
-constexpr uint32_t OFF_MASK = OFF_EX + 100 * 16;             // contact bytes [104][16]: bit j of [k][cg] <-> depth[k][8 cg + j]
-constexpr uint32_t OFF_RED = OFF_MASK + 104 * 16;            // float scratch [8][20]
-constexpr uint32_t OFF_BAR = (OFF_RED + 8 * 20 * 4 + 15u) & ~15u;   // 2 mbarriers + tmem slot
-constexpr uint32_t SMEM_USED = OFF_BAR + 32;
-static_assert(SMEM_USED - 4 * TILE >= 3072, "the tables must cover the over-read of the last tile");
-constexpr size_t SMEM_BYTES = (SMEM_USED + 15) & ~15u;
-static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
+constexpr uint32_t PLANE_BYTES = N * N * 4u;   // 40 000
+constexpr uint32_t TAB2_LEN = 208;             // per shifted copy
+
+// forward -> backward hand-over, AUX_STRIDE floats per sample: rows m = 0..99 hold U_j(m) = sum_n HR[m][n] Ex_j(n),
+// U2_j(m) = sum_n HR[m][n] Ex_j(n) (n - 12 - 25 j)^2 (j = 0..3), the row sum and 3 pad floats; row 100 = {second max}
+constexpr int AUX_ROW = 12;
+constexpr int AUX_STRIDE = 101 * AUX_ROW;
+
+// Shared-memory map.  Depth tiles first: GEMM1 reads K rows 96..111 of the (MN-major) depth tiles, i.e. 1 KB past a tile's
+// 104 rows -- for the last depth tile that lands in E_hi (always finite; it meets the zero K-padding of E).  Over-reads of
+// M / N rows >= 104 only produce accumulator rows / columns that are never used.
+template <int PASSES>
+struct Lay {
+  static constexpr uint32_t NH = PASSES == 3 ? 2u : 1u;                  // tiles per operand: hi [, lo]
+  static constexpr uint32_t OFF_D = 0;                                   // D_hi [, D_lo]
+  static constexpr uint32_t OFF_E = NH * TILE;                           // E_hi [, E_lo]
+  static constexpr uint32_t TILES_END = 2u * NH * TILE;
+  // the raw fp32 depth plane of the NEXT sample (bulk copy): over the depth tiles once GEMM1 has read them (PASSES 3: no
+  // shared memory to spare), or in a buffer of its own, loaded a whole sample ahead (PASSES 1)
+  static constexpr uint32_t OFF_RAW = PASSES == 3 ? 0u : TILES_END;
+  static constexpr uint32_t OFF_TAB = PASSES == 3 ? TILES_END : TILES_END + PLANE_BYTES;   // float e(t), t = 0..99 (+ pad)
+  static constexpr uint32_t OFF_TAB2 = OFF_TAB + 128 * 4;                // 4 shifted copies of uint32 (hi | lo << 16) of 16 e(|j - 99|)
+  static constexpr uint32_t OFF_EX = OFF_TAB2 + 4 * TAB2_LEN * 4;        // float4 (Ex_0..Ex_3)(t), t = 0..99
+  static constexpr uint32_t OFF_MASK = OFF_EX + 100 * 16;                // contact bytes [104][16]: bit j of [k][cg] <-> depth[k][8 cg + j]
+  static constexpr uint32_t OFF_RED = OFF_MASK + 104 * 16;               // float scratch: 3 x [8] block-max partials, [8][20] sums
+  static constexpr uint32_t OFF_BAR = OFF_RED + (24 + 8 * 20) * 4;       // 3 mbarriers + tmem slot
+  static constexpr uint32_t OFF_X24 = PASSES == 3 ? 40960u : OFF_BAR + 32u;   // float4 Ex_j(t) (t - 12 - 25 j)^2 (training hand-over)
+  static constexpr uint32_t OFF_XCH = OFF_X24 + 2048u;                        // half-row exchange of the hand-over statistics
+  static constexpr uint32_t USED = PASSES == 3 ? OFF_BAR + 32u : OFF_XCH + 100 * AUX_ROW * 4;
+  // the finished HR plane (dense rows) before its bulk store: over tiles that are dead after GEMM2
+  static constexpr uint32_t OFF_STAGE = PASSES == 3 ? OFF_E : 0u;
+  static constexpr size_t BYTES = (USED + 15u) & ~15u;
+  static_assert(OFF_BAR % 8 == 0 && OFF_TAB % 16 == 0 && OFF_RAW % 16 == 0, "alignment");
+  static_assert(USED - TILES_END >= 3072, "the last tile's over-read must stay inside the allocation");
+  static_assert(PASSES != 3 || OFF_XCH + 100 * AUX_ROW * 4 <= OFF_E, "hand-over scratch inside the dead depth tiles");
+  static_assert(OFF_STAGE + PLANE_BYTES <= TILES_END, "HR staging inside the tiles");
+  static_assert(2 * (BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
+};
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -56,6 +86,49 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// A operand in tensor memory (lane = row m, one 32-bit column = two consecutive K elements), B in shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // byte offset of the 16-byte chunk cg (elements 8 cg .. 8 cg + 7 along the contiguous direction) of row r of a tile
 __device__ __forceinline__ uint32_t chunk_off(int r, int cg) {
@@ -72,35 +145,71 @@ __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint3
   lo = h2_bits(__floats2half2_rn(x0 - f.x, x1 - f.y));
 }
 
-__device__ __forceinline__ float block_max256(float v, float* red) {
-  v = warp_max(v);
+// block maximum of up to two values with ONE barrier: partials in red[0..7] / red[8..15]; the caller alternates between
+// two scratch areas or has another barrier before the next call
+__device__ __forceinline__ void block_max2(float& a, float& b, float* red) {
+  a = warp_max(a);
+  b = warp_max(b);
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = a; red[8 + (threadIdx.x >> 5)] = b; }
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float t = red[0];
-#pragma unroll
-  for (int i = 1; i < NT / 32; ++i) t = fmaxf(t, red[i]);
-  return t;
+  const float4 a0 = reinterpret_cast<const float4*>(red)[0], a1 = reinterpret_cast<const float4*>(red)[1];
+  const float4 b0 = reinterpret_cast<const float4*>(red)[2], b1 = reinterpret_cast<const float4*>(red)[3];
+  a = fmaxf(fmaxf(fmaxf(a0.x, a0.y), fmaxf(a0.z, a0.w)), fmaxf(fmaxf(a1.x, a1.y), fmaxf(a1.z, a1.w)));
+  b = fmaxf(fmaxf(fmaxf(b0.x, b0.y), fmaxf(b0.z, b0.w)), fmaxf(fmaxf(b1.x, b1.y), fmaxf(b1.z, b1.w)));
 }
 
-// D[128 x 112] (TMEM) = A_hi B_hi + A_lo B_hi + A_hi B_lo.  A: K-major tile.  B: K-major tile (b_mn = 0) or MN-major
-// tile (b_mn = 1: rows = K, the two 64-wide N atoms are ATOM bytes apart).
-template <int B_MN, int ACCUMULATE = 0>
-__device__ __forceinline__ void issue_gemm3(uint32_t tmem_d, uint32_t a_hi_addr, uint32_t a_lo_addr, uint32_t b_hi_addr,
-                                            uint32_t b_lo_addr, uint32_t idesc) {
+// D[128 x 112] (TMEM) = A B over PASSES operand pairs (hi hi [+ lo hi + hi lo]).  A: K-major smem tile.  B: MN-major smem
+// tile (rows = K; the two 64-wide N atoms are ATOM bytes apart).
+template <int PASSES, int ACCUMULATE = 0>
+__device__ __forceinline__ void issue_gemm_kmn(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                               uint32_t idesc) {
   const uint32_t hi_word = desc_hi(1024u);
   uint32_t acc = ACCUMULATE;
 #pragma unroll
-  for (int pass = 0; pass < 3; ++pass) {
-    const uint32_t a0 = pass == 1 ? a_lo_addr : a_hi_addr;
-    const uint32_t b0 = pass == 2 ? b_lo_addr : b_hi_addr;
+  for (int pass = 0; pass < PASSES; ++pass) {
+    const uint32_t a0 = pass == 1 ? a_lo : a_hi;
+    const uint32_t b0 = pass == 2 ? b_lo : b_hi;
 #pragma unroll
     for (int ks = 0; ks < 7; ++ks) {
       const uint32_t koff = (uint32_t)(ks >> 2) * ATOM + (uint32_t)(ks & 3) * 32u;     // 16 elements along K, K-major
-      const uint64_t ad = desc_join(desc_lo(a0 + koff, 16u), hi_word);
-      const uint64_t bd = B_MN ? desc_join(desc_lo(b0 + (uint32_t)ks * 2048u, ATOM), hi_word)   // 16 K rows further
-                               : desc_join(desc_lo(b0 + koff, 16u), hi_word);
-      umma_f16(tmem_d, ad, bd, idesc, acc);
+      umma_f16(tmem_d, desc_join(desc_lo(a0 + koff, 16u), hi_word),
+               desc_join(desc_lo(b0 + (uint32_t)ks * 2048u, ATOM), hi_word), idesc, acc);     // B: 16 K rows further
+      acc = 1u;
+    }
+  }
+}
+// both operands K-major smem tiles
+template <int PASSES, int ACCUMULATE = 0>
+__device__ __forceinline__ void issue_gemm_kk(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                              uint32_t idesc) {
+  const uint32_t hi_word = desc_hi(1024u);
+  uint32_t acc = ACCUMULATE;
+#pragma unroll
+  for (int pass = 0; pass < PASSES; ++pass) {
+    const uint32_t a0 = pass == 1 ? a_lo : a_hi;
+    const uint32_t b0 = pass == 2 ? b_lo : b_hi;
+#pragma unroll
+    for (int ks = 0; ks < 7; ++ks) {
+      const uint32_t koff = (uint32_t)(ks >> 2) * ATOM + (uint32_t)(ks & 3) * 32u;
+      umma_f16(tmem_d, desc_join(desc_lo(a0 + koff, 16u), hi_word), desc_join(desc_lo(b0 + koff, 16u), hi_word), idesc, acc);
+      acc = 1u;
+    }
+  }
+}
+// A in tensor memory (packed fp16 pairs: 8 columns per K step), B a K-major smem tile
+template <int PASSES>
+__device__ __forceinline__ void issue_gemm_tk(uint32_t tmem_d, uint32_t t_hi, uint32_t t_lo, uint32_t b_hi, uint32_t b_lo,
+                                              uint32_t idesc) {
+  const uint32_t hi_word = desc_hi(1024u);
+  uint32_t acc = 0u;
+#pragma unroll
+  for (int pass = 0; pass < PASSES; ++pass) {
+    const uint32_t a0 = pass == 1 ? t_lo : t_hi;
+    const uint32_t b0 = pass == 2 ? b_lo : b_hi;
+#pragma unroll
+    for (int ks = 0; ks < 7; ++ks) {
+      const uint32_t koff = (uint32_t)(ks >> 2) * ATOM + (uint32_t)(ks & 3) * 32u;
+      umma_f16_ts(tmem_d, a0 + (uint32_t)ks * 8u, desc_join(desc_lo(b0 + koff, 16u), hi_word), idesc, acc);
       acc = 1u;
     }
   }
@@ -108,9 +217,13 @@ __device__ __forceinline__ void issue_gemm3(uint32_t tmem_d, uint32_t a_hi_addr,
 
 constexpr int ITEMS = 13 * N;                  // (row, 8-element chunk) work items of a 100 x 100 plane
 constexpr int IPT = (ITEMS + NT - 1) / NT;     // 6 (the last round only for 20 threads)
+constexpr int ITEMS_E = 14 * N;                // ... of a Toeplitz tile incl. its zero K-padding chunk 13
+constexpr int IPT_E = (ITEMS_E + NT - 1) / NT; // 6
 
 // this thread's chunks of one depth plane -> registers: item = (row k, columns 8 cg .. 8 cg + 7), consecutive lanes read
-// consecutive 32-byte pieces; chunk 12 of a row holds columns 96..99 only (the rest reads as 0)
+// consecutive 32-byte pieces; chunk 12 of a row holds columns 96..99 only (the rest reads as 0).  SMEM: the plane lies in
+// shared memory (bulk copy), else in global memory.
+template <bool SMEM>
 __device__ __forceinline__ void load_plane(const float* __restrict__ dsrc, int tid, float (&dreg)[IPT][8]) {
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
@@ -119,14 +232,18 @@ __device__ __forceinline__ void load_plane(const float* __restrict__ dsrc, int t
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
     if (item < ITEMS) {
       const float4* src = reinterpret_cast<const float4*>(dsrc + k * N + cg * 8);
-      a = __ldg(src);
-      if (cg < 12) c = __ldg(src + 1);
+      if (SMEM) {
+        a = src[0];
+        if (cg < 12) c = src[1];
+      } else {
+        a = __ldg(src);
+        if (cg < 12) c = __ldg(src + 1);
+      }
     }
     dreg[i][0] = a.x; dreg[i][1] = a.y; dreg[i][2] = a.z; dreg[i][3] = a.w;
     dreg[i][4] = c.x; dreg[i][5] = c.y; dreg[i][6] = c.z; dreg[i][7] = c.w;
   }
 }
-
 
 // 4 shifted copies of the packed (hi | lo << 16) fp16 table of the banded Toeplitz generator, so that any 8 consecutive
 // entries are two aligned 16-byte loads.  kind 0: 16 e(t);  1: 16 e(t) t^2;  2: 32768 e(t)   (t = |j - 99| <= 49, else 0:
@@ -145,29 +262,38 @@ __device__ __forceinline__ void build_tab2(const float* tab, uint32_t* tab2, int
   }
 }
 
-// K-major hi / lo tiles of the Toeplitz matrix from the table: M[r][8 cg + j] = gen(|8 cg + j - r|)
+// K-major hi [/ lo] tiles of the Toeplitz matrix from the table: M[r][8 cg + j] = gen(|8 cg + j - r|); chunk 13 (the K
+// padding 104..111, which the MMAs read) is rewritten as zeros: HR staging / raw planes lie over the tiles between samples
+template <int PASSES>
 __device__ __forceinline__ void build_toeplitz_tiles(const uint32_t* tab2, uint8_t* t_hi, uint8_t* t_lo, int tid) {
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
+  for (int i = 0; i < IPT_E; ++i) {
     const int item = tid + i * NT;
-    if (item < ITEMS) {
-      const int r = item / 13, cg = item - r * 13;
-      const int start = 8 * cg - r + 99;
-      const int s = start & 3;
-      const uint4* tp = reinterpret_cast<const uint4*>(tab2 + s * (int)TAB2_LEN + (start - s));
-      const uint4 p0 = tp[0];
-      uint4 p1 = tp[1];
-      if (cg == 12) p1 = make_uint4(0u, 0u, 0u, 0u);       // k = 100..103: K padding
+    if (item < ITEMS_E) {
+      const int r = item / 14, cg = item - r * 14;
       const uint32_t off = chunk_off(r, cg);
+      uint4 p0 = make_uint4(0u, 0u, 0u, 0u), p1 = p0;
+      if (cg < 13) {
+        const int start = 8 * cg - r + 99;
+        const int s = start & 3;
+        const uint4* tp = reinterpret_cast<const uint4*>(tab2 + s * (int)TAB2_LEN + (start - s));
+        p0 = tp[0];
+        if (cg < 12) p1 = tp[1];                             // chunk 12: k = 100..103 are K padding
+      }
       *reinterpret_cast<uint4*>(t_hi + off) = make_uint4(__byte_perm(p0.x, p0.y, 0x5410), __byte_perm(p0.z, p0.w, 0x5410),
                                                          __byte_perm(p1.x, p1.y, 0x5410), __byte_perm(p1.z, p1.w, 0x5410));
-      *reinterpret_cast<uint4*>(t_lo + off) = make_uint4(__byte_perm(p0.x, p0.y, 0x7632), __byte_perm(p0.z, p0.w, 0x7632),
-                                                         __byte_perm(p1.x, p1.y, 0x7632), __byte_perm(p1.z, p1.w, 0x7632));
+      if (PASSES == 3)
+        *reinterpret_cast<uint4*>(t_lo + off) = make_uint4(__byte_perm(p0.x, p0.y, 0x7632), __byte_perm(p0.z, p0.w, 0x7632),
+                                                           __byte_perm(p1.x, p1.y, 0x7632), __byte_perm(p1.z, p1.w, 0x7632));
     }
   }
 }
 
-// the register-held depth plane -> hi / lo tiles as it lies in HBM (row = k: the MN-major B operand) + contact bytes
+// the register-held depth plane -> hi [/ lo] tiles as it lies in HBM (row = k: the MN-major B operand) + contact bytes.
+// Everything GEMM1 reads as K rows 100..111 meets the zero K-padding of E and must be finite, and other data has been lying
+// over the tiles: rows 100..103 of every atom are zeroed, and -- rows 104..111 of an atom-0 are the first 8 rows of the
+// following atom-1 -- the column chunks 5..7 of those rows, which no depth store covers (columns 104..127)
+template <int PASSES>
 __device__ __forceinline__ void store_plane_tiles(const float (&dreg)[IPT][8], float sD, float thr, uint8_t* x_hi,
                                                   uint8_t* x_lo, uint8_t* maskb, int tid) {
 #pragma unroll
@@ -183,34 +309,79 @@ __device__ __forceinline__ void store_plane_tiles(const float (&dreg)[IPT][8], f
       for (int j = 0; j < 8; ++j)
         if (dreg[i][j] > thr && (cg < 12 || j < 4)) bits |= 1u << j;
       *reinterpret_cast<uint4*>(x_hi + off) = make_uint4(dh[0], dh[1], dh[2], dh[3]);
-      *reinterpret_cast<uint4*>(x_lo + off) = make_uint4(dl[0], dl[1], dl[2], dl[3]);
+      if (PASSES == 3) *reinterpret_cast<uint4*>(x_lo + off) = make_uint4(dl[0], dl[1], dl[2], dl[3]);
       maskb[r * 16 + cg] = (uint8_t)bits;
+    }
+  }
+  constexpr int NATOM = PASSES == 3 ? 4 : 2;
+  if (tid < NATOM * 32) {
+    const int a = tid >> 5, r = 100 + ((tid >> 3) & 3), c = tid & 7;      // atom x row x 16-byte chunk
+    *reinterpret_cast<uint4*>(x_hi + a * ATOM + r * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+  } else if (tid < NATOM * 32 + NATOM * 12) {
+    const int t = tid - NATOM * 32, tile = t / 24, r = (t % 24) / 3, c = 5 + t % 3;
+    *reinterpret_cast<uint4*>(x_hi + tile * TILE + ATOM + r * 128 + ((c ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// accumulator (TMEM, this thread's 56 columns at acc) * scale -> K-major hi [/ lo] smem tiles; thread = (row m, column half)
+template <int PASSES>
+__device__ __forceinline__ void acc_to_tiles(uint32_t acc, float scale, uint8_t* x_hi, uint8_t* x_lo, int m, int half) {
+#pragma unroll
+  for (int part = 0; part < 2; ++part) {                     // 2 x 28 columns: 32 registers in flight
+    uint32_t v[28];
+    const uint32_t c0 = acc + (uint32_t)(half * 56 + part * 28);
+    tmem_ld16(c0, v);
+    tmem_ld8(c0 + 16u, v + 16);
+    tmem_ld4(c0 + 24u, v + 24);
+    tmem_ld_wait();
+    if (m < (int)ROWS) {
+#pragma unroll
+      for (int g = 0; g < 7; ++g) {                          // 16-byte chunk = 8 columns; a part covers 3.5 chunks
+        const int col0 = half * 56 + part * 28 + g * 4;      // 4 columns = half a chunk
+        const int cg = col0 >> 3, hsel = (col0 >> 2) & 1;
+        uint32_t th[2], tl[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          // columns >= 100 are padding (depth-tile garbage): force 0
+          const float x0 = col0 + 2 * j < N ? __uint_as_float(v[g * 4 + 2 * j]) * scale : 0.f;
+          const float x1 = col0 + 2 * j + 1 < N ? __uint_as_float(v[g * 4 + 2 * j + 1]) * scale : 0.f;
+          split_h2(x0, x1, th[j], tl[j]);
+        }
+        const uint32_t off = chunk_off(m, cg) + (uint32_t)hsel * 8u;
+        *reinterpret_cast<uint2*>(x_hi + off) = make_uint2(th[0], th[1]);
+        if (PASSES == 3) *reinterpret_cast<uint2*>(x_lo + off) = make_uint2(tl[0], tl[1]);
+      }
     }
   }
 }
 
-// accumulator (TMEM, 112 columns at acc) * scale -> K-major hi / lo tiles; thread = (row m, column half)
-__device__ __forceinline__ void acc_to_tiles(uint32_t acc, float scale, uint8_t* x_hi, uint8_t* x_lo, int m, int half) {
-#pragma unroll 1
-  for (int g = 0; g < 7; ++g) {
-    const int cg = half * 7 + g;
-    uint32_t v[8];
-    tmem_ld8(acc + (uint32_t)(cg * 8), v);
-    tmem_ld_wait();
-    if (m < (int)ROWS) {
-      uint32_t th[4], tl[4];
+// accumulator (TMEM, this thread's 56 columns at acc) -> packed fp16 hi [/ lo] pairs in tensor memory at t_hi / t_lo (this
+// thread's 28 columns of each): the A operand of the next product.  K columns >= 100 (depth-tile garbage) are zeroed.
+template <int PASSES>
+__device__ __forceinline__ void acc_to_tmem(uint32_t acc, uint32_t t_hi, uint32_t t_lo, int half) {
+  uint32_t v[56];
+  const uint32_t c0 = acc + (uint32_t)(half * 56);
+  tmem_ld32(c0, v);
+  tmem_ld16(c0 + 32u, v + 32);
+  tmem_ld8(c0 + 48u, v + 48);
+  tmem_ld_wait();
+  uint32_t th[28], tl[28];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // columns >= 100 are padding (depth-tile garbage): force 0
-        const float x0 = cg * 8 + 2 * j < N ? __uint_as_float(v[2 * j]) * scale : 0.f;
-        const float x1 = cg * 8 + 2 * j + 1 < N ? __uint_as_float(v[2 * j + 1]) * scale : 0.f;
-        split_h2(x0, x1, th[j], tl[j]);
-      }
-      const uint32_t off = chunk_off(m, cg);
-      *reinterpret_cast<uint4*>(x_hi + off) = make_uint4(th[0], th[1], th[2], th[3]);
-      *reinterpret_cast<uint4*>(x_lo + off) = make_uint4(tl[0], tl[1], tl[2], tl[3]);
-    }
+  for (int j = 0; j < 28; ++j) split_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), th[j], tl[j]);
+  if (half) {
+#pragma unroll
+    for (int j = 22; j < 28; ++j) { th[j] = 0u; tl[j] = 0u; }          // k = 56 + 2 j >= 100
   }
+  const uint32_t p0 = (uint32_t)(half * 28);
+  tmem_st16(t_hi + p0, th);
+  tmem_st8(t_hi + p0 + 16u, th + 16);
+  tmem_st4(t_hi + p0 + 24u, th + 24);
+  if (PASSES == 3) {
+    tmem_st16(t_lo + p0, tl);
+    tmem_st8(t_lo + p0 + 16u, tl + 16);
+    tmem_st4(t_lo + p0 + 24u, tl + 24);
+  }
+  tmem_st_wait();
 }
 
 // depth max / abs-max over this thread's register-held chunks
@@ -242,23 +413,37 @@ __device__ __forceinline__ void build_tables(float beta, float gamma, float* tab
   }
 }
 
-// forward -> backward hand-over, AUX_STRIDE floats per sample: rows m = 0..99 hold U_j(m) = sum_n HR[m][n] Ex_j(n),
-// U2_j(m) = sum_n HR[m][n] Ex_j(n) (n - 12 - 25 j)^2 (j = 0..3), the row sum and 3 pad floats; row 100 = {second max}
-constexpr int AUX_ROW = 12;
-constexpr int AUX_STRIDE = 101 * AUX_ROW;
+// this thread's 56 contact bits: bit j <-> column half * 56 + j of row `row` (bytes 7 half .. 7 half + 6 of the 16-byte row)
+__device__ __forceinline__ void contact_bits(const uint8_t* maskb, int row, int half, uint32_t& blo, uint32_t& bhi) {
+  const uint4 mw = *reinterpret_cast<const uint4*>(maskb + row * 16);
+  if (half == 0) {
+    blo = mw.x;
+    bhi = mw.y & 0x00FFFFFFu;
+  } else {
+    blo = __funnelshift_r(mw.y, mw.z, 24);
+    bhi = __funnelshift_r(mw.z, mw.w, 24) & 0x00000FFFu;     // columns 88..99
+  }
+}
+__device__ __forceinline__ bool bit56(uint32_t blo, uint32_t bhi, int j) { return ((j < 32 ? blo >> j : bhi >> (j - 32)) & 1u) != 0u; }
 
+template <int PASSES>
 __global__ void __launch_bounds__(NT, 2)
 psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth, float* __restrict__ HR,
                   float* __restrict__ LRd, float* __restrict__ psf, float* __restrict__ aux, int B) {
+  using L = Lay<PASSES>;
   extern __shared__ __align__(1024) uint8_t sm[];
   const uint32_t base = smem_u32(sm);
-  float* tab = reinterpret_cast<float*>(sm + OFF_TAB);
-  uint32_t* tab2 = reinterpret_cast<uint32_t*>(sm + OFF_TAB2);
-  float4* ex4 = reinterpret_cast<float4*>(sm + OFF_EX);
-  uint8_t* maskb = sm + OFF_MASK;
-  float* red = reinterpret_cast<float*>(sm + OFF_RED);
-  const uint32_t bar1 = base + OFF_BAR, bar2 = bar1 + 8u, tmem_slot = bar1 + 16u;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + 16);
+  float* tab = reinterpret_cast<float*>(sm + L::OFF_TAB);
+  uint32_t* tab2 = reinterpret_cast<uint32_t*>(sm + L::OFF_TAB2);
+  float4* ex4 = reinterpret_cast<float4*>(sm + L::OFF_EX);
+  uint8_t* maskb = sm + L::OFF_MASK;
+  float* red = reinterpret_cast<float*>(sm + L::OFF_RED);           // [0,16) depth max / |max|, [16,24) second max, [24,..) sums
+  const uint32_t bar1 = base + L::OFF_BAR, bar2 = bar1 + 8u, bar_raw = bar1 + 16u, tmem_slot = bar1 + 24u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + L::OFF_BAR + 24);
+  uint8_t* const d_hi = sm + L::OFF_D; uint8_t* const d_lo = sm + L::OFF_D + TILE;
+  uint8_t* const e_hi = sm + L::OFF_E; uint8_t* const e_lo = sm + L::OFF_E + TILE;
+  const uint32_t a_d_hi = base + L::OFF_D, a_d_lo = a_d_hi + TILE, a_e_hi = base + L::OFF_E, a_e_lo = a_e_hi + TILE;
+  const float* raw = reinterpret_cast<const float*>(sm + L::OFF_RAW);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if ((base & 1023u) != 0u) {                  // SWIZZLE_128B atoms are addressed by absolute shared-memory address bits
@@ -266,67 +451,67 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     __trap();
   }
 
-  // one-time: zero all four tiles (padding chunks, rows 100..103) and the mask table, barriers, TMEM
-  for (uint32_t i = tid; i < 4 * TILE / 16; i += NT) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // one-time: zero the tiles (padding chunks) and the mask table, barriers, TMEM
+  for (uint32_t i = tid; i < L::TILES_END / 16; i += NT) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (uint32_t i = tid; i < 104 * 16 / 4; i += NT) reinterpret_cast<uint32_t*>(maskb)[i] = 0u;
   if (tid == 0) {
     mbar_init(bar1, 1);
     mbar_init(bar2, 1);
+    mbar_init(bar_raw, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  fence_proxy_async();                         // the zeroing above -> ordered before the first bulk copy into the tiles
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t idesc1 = make_idesc(128, 112, 0, 1, 0, 0);   // fp16 x fp16 -> fp32; A K-major, B MN-major
-  const uint32_t idesc2 = make_idesc(128, 112, 0, 0, 0, 0);   // both K-major
+  const uint32_t idesc2 = make_idesc(128, 112, 0, 0, 0, 0);   // A from tensor memory, B K-major
 
   // epilogue geometry: TMEM lane quarter q = warp % 4, row m = 32 q + lane; column half = warp / 4 (56 columns each)
   const int q = warp & 3, half = warp >> 2;
   const int m = q * 32 + lane;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+  const uint32_t acc = tmem_base + lane_addr;                  // accumulator of both products: columns [0,112)
+  const uint32_t t_hi = tmem_base + 128u, t_lo = tmem_base + 184u;     // packed T: 56 columns each
 
-  float dreg[IPT][8];
-  if ((int)blockIdx.x < B) load_plane(depth + (size_t)blockIdx.x * N * N, tid, dreg);
+  auto load_raw = [&](int bn) {                // one elected thread: bulk copy of sample bn's depth plane
+    mbar_expect_tx(bar_raw, PLANE_BYTES);
+    bulk_load(base + L::OFF_RAW, depth + (size_t)bn * N * N, PLANE_BYTES, bar_raw);
+  };
+  if (tid == 0 && (int)blockIdx.x < B) load_raw(blockIdx.x);
+
   int it = 0;
   for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
     const uint32_t ph = (uint32_t)(it & 1);
+    const bool has_next = b + (int)gridDim.x < B;
     const float alpha = ab[b * 3 + 0], beta = ab[b * 3 + 1], gamma = ab[b * 3 + 2];
 
-    // the previous sample's HR plane has left shared memory before store_plane_tiles overwrites it (the block_max
-    // barriers below order this wait against every other thread)
-    if (tid == 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    // ---- phase A1: depth max over this thread's chunks (loaded into registers one sample ahead); tables ----
-    float lmax, lamax;
-    plane_max(dreg, tid, lmax, lamax);
+    // ---- phase A1: plane -> registers, depth max / |max|, tables ----
+    float dreg[IPT][8];
+    mbar_wait(bar_raw, ph);
+    load_plane<true>(raw, tid, dreg);
+    float dmax, amax;
+    plane_max(dreg, tid, dmax, amax);
     build_tables(beta, gamma, tab, ex4, tid);
-    const float dmax = block_max256(lmax, red);        // (syncs: tab visible)
-    const float amax = block_max256(lamax, red);
+    // the previous sample's HR plane has left shared memory before the tiles under it are rebuilt (the barrier inside
+    // block_max2 orders this wait against every other thread)
+    if (tid == 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    block_max2(dmax, amax, red);                       // (syncs: tab / ex4 visible, every thread holds its part of the plane)
+    if (PASSES == 1 && tid == 0 && has_next) load_raw(b + gridDim.x);      // own buffer: a whole sample ahead
     const float thr = dmax - 1e-3f;
     int dexp = 0;
     if (amax > 0.f) (void)frexpf(amax, &dexp);         // amax = f * 2^dexp, f in [0.5, 1)
     const float sD = ldexpf(1.0f, 4 - dexp);           // |depth| sD < 16
     build_tab2<0>(tab, tab2, tid);
+    // ---- phase A2: depth tiles (MN-major: row = k, as in HBM) + contact bytes; then the E tiles (K-major) ----
+    store_plane_tiles<PASSES>(dreg, sD, thr, d_hi, d_lo, maskb, tid);
     __syncthreads();
-
-    // ---- phase A2: E tiles (K-major), depth tiles (MN-major: row = k, as in HBM) + contact bytes ----
-    build_toeplitz_tiles(tab2, sm + OFF_E_HI, sm + OFF_E_LO, tid);
-    store_plane_tiles(dreg, sD, thr, sm + OFF_X_HI, sm + OFF_X_LO, maskb, tid);
-    // Everything GEMM1 reads as K rows 100..111 meets the zero K-padding of E and must be finite, and the HR staging of
-    // the previous sample has been lying over the tiles: rows 100..103 of all four atoms, and -- rows 104..111 of an
-    // atom-0 are the first 8 rows of the following atom-1 -- the column chunks 5..7 of those rows, which no depth
-    // store covers (columns 104..127)
-    if (tid < 128) {
-      const int t4 = tid >> 5, r = 100 + ((tid >> 3) & 3), c = tid & 7;      // (tile half, atom) x row x 16-byte chunk
-      *reinterpret_cast<uint4*>(sm + (t4 >> 1) * TILE + (t4 & 1) * ATOM + r * 128 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
-    } else if (tid < 128 + 48) {
-      const int t = tid - 128, tile = t / 24, r = (t % 24) / 3, c = 5 + t % 3;
-      *reinterpret_cast<uint4*>(sm + tile * TILE + ATOM + r * 128 + ((c ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-    }
+    build_toeplitz_tiles<PASSES>(tab2, e_hi, e_lo, tid);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -335,13 +520,11 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_gemm3<1>(tmem_base, base + OFF_E_HI, base + OFF_E_LO, base + OFF_X_HI, base + OFF_X_LO, idesc1);
+        issue_gemm_kmn<PASSES>(tmem_base, a_e_hi, a_e_lo, a_d_hi, a_d_lo, idesc1);
         umma_commit(bar1);
       }
       __syncwarp();
     }
-    // the next sample's plane: its loads stay in flight until the top of the next iteration
-    if (b + (int)gridDim.x < B) load_plane(depth + (size_t)(b + gridDim.x) * N * N, tid, dreg);
     // psf = alpha e(u) e(v)  (tPSFNet.py:83): warp w owns rows u = u0 + w, u0 + w + 8, ...; rows 0..49 are written while
     // GEMM1 runs, rows 50..98 while GEMM2 runs
     auto write_psf = [&](int u0, int u1) {
@@ -357,18 +540,18 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
         const float eu = tab[u < 49 ? 49 - u : u - 49];
         float* row = pdst + u * 99;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (lane + 32 * c < 99) row[lane + 32 * c] = alpha * (eu * ev[c]);
+        for (int c = 0; c < 3; ++c) row[lane + 32 * c] = alpha * (eu * ev[c]);
+        if (lane < 3) row[lane + 96] = alpha * (eu * ev[3]);
       }
     };
     write_psf(0, 50);
     mbar_wait(bar1, ph);
     tc_fence_after();
+    if (PASSES == 3 && tid == 0 && has_next) load_raw(b + gridDim.x);      // over the depth tiles GEMM1 has finished reading
 
-    // ---- phase X: T -> hi/lo fp16 -> smem (K-major, over the depth tiles, which GEMM1 has finished reading) ----
+    // ---- phase X: T -> fp16 hi [/ lo] -> tensor memory (the A operand of GEMM2) ----
     // accumulator = 16 sD T = 2^(8 - dexp) T,  |T| <= 99 |depth|max  =>  < 2^15: no rescaling needed
-    acc_to_tiles(tmem_base + lane_addr, 1.0f, sm + OFF_X_HI, sm + OFF_X_LO, m, half);
-    fence_proxy_async();
+    acc_to_tmem<PASSES>(acc, t_hi + lane_addr, t_lo + lane_addr, half);
     tc_fence_before();
     __syncthreads();
 
@@ -376,21 +559,16 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_gemm3<0>(tmem_base + 128u, base + OFF_X_HI, base + OFF_X_LO, base + OFF_E_HI, base + OFF_E_LO, idesc2);
+        issue_gemm_tk<PASSES>(tmem_base, t_hi, t_lo, a_e_hi, a_e_lo, idesc2);
         umma_commit(bar2);
       }
       __syncwarp();
     }
     write_psf(50, 99);
-    mbar_wait(bar2, ph);
-    tc_fence_after();
-    // the T tiles are dead now: their memory holds (Ex_j(t) (t - 12 - 25 j)^2) and the half-row hand-over of the
-    // backward statistics (both only needed when the backward hand-over `aux` is requested)
-    float4* ex24 = reinterpret_cast<float4*>(sm + OFF_X_HI);
-    float* xch = reinterpret_cast<float*>(sm + OFF_X_HI + 2048);
-    // ... and the finished HR plane (40 000 B, dense rows), which leaves for HBM as ONE bulk copy: a row per thread
-    // scattered straight to global memory costs 32 partial sectors per store instruction
-    float* hstage = reinterpret_cast<float*>(sm + OFF_X_HI + 8192);
+    // (Ex_j(t) (t - 12 - 25 j)^2) and the half-row hand-over of the backward statistics (only needed when the backward
+    // hand-over `aux` is requested) live in memory that is dead by now
+    float4* ex24 = reinterpret_cast<float4*>(sm + L::OFF_X24);
+    float* xch = reinterpret_cast<float*>(sm + L::OFF_XCH);
     if (aux) {
       for (int i = tid; i < 4 * N; i += NT) {
         const int t = i >> 2, k = i & 3;
@@ -398,57 +576,78 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
         reinterpret_cast<float*>(ex24)[i] = reinterpret_cast<const float*>(ex4)[i] * (d * d);
       }
     }
+    uint32_t blo, bhi;
+    contact_bits(maskb, m < N ? m : 0, half, blo, bhi);
+    mbar_wait(bar2, ph);
+    tc_fence_after();
 
-    // ---- phase E: epilogue.  accumulator = 2^(8 - dexp) 16 (E D E) ----
+    // ---- phase E: epilogue.  accumulator = 2^(8 - dexp) 16 (E D E); this thread: row m, columns c0 .. c0 + 55 ----
     const float cs = alpha * ldexpf(1.0f, dexp - 12);
-    const uint32_t acc2 = tmem_base + 128u + lane_addr;
-    const uint8_t* mrow = maskb + (m < (int)ROWS ? m : 0) * 16;
-    // pass 1: second max = max over the conv result with the contact pixels zeroed (tPSFNet.py:95-97)
-    float m2 = 0.f;
-#pragma unroll 1
-    for (int g = 0; g < 7; ++g) {
-      const int cg = half * 7 + g;
-      uint32_t v[8];
-      tmem_ld8(acc2 + (uint32_t)(cg * 8), v);
+    const int c0 = half * 56;
+    float h[56];
+    {
+      uint32_t v[56];
+      tmem_ld32(acc + (uint32_t)c0, v);
+      tmem_ld16(acc + (uint32_t)c0 + 32u, v + 32);
+      tmem_ld8(acc + (uint32_t)c0 + 48u, v + 48);
       tmem_ld_wait();
-      if (m < N && cg < 13) {
-        const uint32_t bits = mrow[cg] | (cg == 12 ? 0xF0u : 0u);       // columns >= 100: treated like contact (skipped)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (!((bits >> j) & 1u)) m2 = fmaxf(m2, __uint_as_float(v[j]) * cs);
+      for (int j = 0; j < 56; ++j) h[j] = __uint_as_float(v[j]) * cs;
+    }
+    tc_fence_before();                                  // (all TMEM reads of this sample are complete)
+    // second max = max over the conv result with the contact pixels zeroed (tPSFNet.py:95-97)
+    const bool any_contact = (blo | bhi) != 0u;
+    float m2 = 0.f, unused = 0.f;
+    if (m < N) {
+      if (!any_contact) {
+#pragma unroll
+        for (int j = 0; j < 44; ++j) m2 = fmaxf(m2, h[j]);
+        if (half == 0) {
+#pragma unroll
+          for (int j = 44; j < 56; ++j) m2 = fmaxf(m2, h[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 44; ++j)
+          if (!bit56(blo, bhi, j)) m2 = fmaxf(m2, h[j]);
+        if (half == 0) {
+#pragma unroll
+          for (int j = 44; j < 56; ++j)
+            if (!bit56(blo, bhi, j)) m2 = fmaxf(m2, h[j]);
+        }
       }
     }
-    m2 = block_max256(m2, red);
-    // pass 2: fill, store HR, accumulate the degradation sums of this thread's row segment
+    block_max2(m2, unused, red);               // (the tile barriers since the depth-max call protect the scratch)
+    // fill, stage HR, accumulate the degradation sums of this thread's row segment
     float rj[4] = {0.f, 0.f, 0.f, 0.f}, r2[4] = {0.f, 0.f, 0.f, 0.f}, rs = 0.f;
-    float* hdst = hstage + m * N;
-#pragma unroll 1
-    for (int g = 0; g < 7; ++g) {
-      const int cg = half * 7 + g;
-      uint32_t v[8];
-      tmem_ld8(acc2 + (uint32_t)(cg * 8), v);
-      tmem_ld_wait();
-      if (m < N && cg < 13) {
-        const uint32_t bits = mrow[cg];
-        const int nv = cg == 12 ? 4 : 8;
-        float h[8];
+    float* hstage = reinterpret_cast<float*>(sm + L::OFF_STAGE);
+    if (m < N) {
+      if (any_contact) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          h[j] = ((bits >> j) & 1u) ? m2 : __uint_as_float(v[j]) * cs;
-          if (j < nv) {
-            const float4 e4 = ex4[cg * 8 + j];
-            rs += h[j];
-            rj[0] = fmaf(h[j], e4.x, rj[0]); rj[1] = fmaf(h[j], e4.y, rj[1]);
-            rj[2] = fmaf(h[j], e4.z, rj[2]); rj[3] = fmaf(h[j], e4.w, rj[3]);
-            if (aux) {
-              const float4 f4 = ex24[cg * 8 + j];
-              r2[0] = fmaf(h[j], f4.x, r2[0]); r2[1] = fmaf(h[j], f4.y, r2[1]);
-              r2[2] = fmaf(h[j], f4.z, r2[2]); r2[3] = fmaf(h[j], f4.w, r2[3]);
-            }
-          }
+        for (int j = 0; j < 56; ++j)
+          if (bit56(blo, bhi, j)) h[j] = m2;
+      }
+      auto accumulate = [&](int j) {
+        const float4 e4 = ex4[c0 + j];
+        rs += h[j];
+        rj[0] = fmaf(h[j], e4.x, rj[0]); rj[1] = fmaf(h[j], e4.y, rj[1]);
+        rj[2] = fmaf(h[j], e4.z, rj[2]); rj[3] = fmaf(h[j], e4.w, rj[3]);
+        if (aux) {
+          const float4 f4 = ex24[c0 + j];
+          r2[0] = fmaf(h[j], f4.x, r2[0]); r2[1] = fmaf(h[j], f4.y, r2[1]);
+          r2[2] = fmaf(h[j], f4.z, r2[2]); r2[3] = fmaf(h[j], f4.w, r2[3]);
         }
-        *reinterpret_cast<float4*>(hdst + cg * 8) = make_float4(h[0], h[1], h[2], h[3]);
-        if (cg < 12) *reinterpret_cast<float4*>(hdst + cg * 8 + 4) = make_float4(h[4], h[5], h[6], h[7]);
+      };
+      float4* hdst = reinterpret_cast<float4*>(hstage + m * N + c0);
+#pragma unroll
+      for (int j = 0; j < 44; ++j) accumulate(j);
+#pragma unroll
+      for (int j4 = 0; j4 < 11; ++j4) hdst[j4] = make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
+      if (half == 0) {
+#pragma unroll
+        for (int j = 44; j < 56; ++j) accumulate(j);
+#pragma unroll
+        for (int j4 = 11; j4 < 14; ++j4) hdst[j4] = make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
       }
     }
     // LRd[i][j] = 1e-4 (sum_m Ex_i(m) R_j(m) - mm sum HR) / (1 - mm),  R_j(m) = sum_n HR[m][n] Ex_j(n)
@@ -481,20 +680,20 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
         x4[1] = make_float4(r2[0], r2[1], r2[2], r2[3]);
         x4[2] = make_float4(rs, 0.f, 0.f, 0.f);
       }
-      __syncthreads();                                  // (red was last read by block_max256)
-      if ((lane & 1) == 0) red[warp * 20 + (lane >> 1)] = p[0];
-      if (lane == 0) red[warp * 20 + 16] = tot_w;
+      float* reds = red + 24;
+      if ((lane & 1) == 0) reds[warp * 20 + (lane >> 1)] = p[0];
+      if (lane == 0) reds[warp * 20 + 16] = tot_w;
       __syncthreads();
-      if (tid == 32) {                                  // (all rows are staged: second __syncthreads above)
+      if (tid == 32) {                                  // (all rows are staged)
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(HR + (size_t)b * N * N),
-                     "r"(base + OFF_X_HI + 8192u), "r"((uint32_t)(N * N * sizeof(float)))
+                     "r"(base + L::OFF_STAGE), "r"(PLANE_BYTES)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       if (tid < 16) {
         float s = 0.f, tot = 0.f;
 #pragma unroll
-        for (int w = 0; w < NT / 32; ++w) { s += red[w * 20 + tid]; tot += red[w * 20 + 16]; }
+        for (int w = 0; w < NT / 32; ++w) { s += reds[w * 20 + tid]; tot += reds[w * 20 + 16]; }
         const float mm = expf(-100.0f / gamma);
         LRd[b * 16 + tid] = 1e-4f * (s - mm * tot) / (1.0f - mm);
       }
@@ -508,10 +707,7 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       }
       if (aux && tid == 0) aux[(size_t)b * AUX_STRIDE + 100 * AUX_ROW] = m2;
     }
-    // all TMEM reads and shared-memory reads of this sample are complete before the next sample overwrites them
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    // the next sample's barriers (block_max2 and the two tile barriers) order everything above before its first MMA
   }
 
   if (tid == 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -532,29 +728,31 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
 //   d beta  = alpha 2 cp2 / beta^3 * sum_{non-contact} w P3,   P3 = E2 D E + E D E2,  E2[m][k] = e(|k-m|) (k-m)^2
 //   d gamma = closed form in G0 = sum g_ij S_ij, G1 = sum g_ij S1_ij, sum HR (psf.cu psf_bwd_kernel), all three linear in
 //             the per-row statistics U, U2, row sum that the forward left in `aux`
-// P3 takes four 100^3 contractions; they run as tcgen05.mma on fp16 hi/lo split operands exactly like the forward:
+// P3 takes four 100^3 contractions; they run as tcgen05.mma on fp16 (PASSES 3: hi/lo split) operands like the forward:
 //   T = E D -> acc0;  T2 = E2 D -> acc1;  acc0' = T E2  (+)=  T2 E      (the two products share one accumulator: the
 //   operand scales are chosen so that both carry 2^(12 - dexp))
 // ------------------------------------------------------------------------------------------------------------------
+template <int PASSES>
 __global__ void __launch_bounds__(NT, 2)
 psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth, const float* __restrict__ aux,
                   const float* __restrict__ dLRd, float* __restrict__ dab, int B) {
+  using L = Lay<PASSES>;
   extern __shared__ __align__(1024) uint8_t sm[];
   const uint32_t base = smem_u32(sm);
-  float* tab = reinterpret_cast<float*>(sm + OFF_TAB);
-  uint32_t* tab2 = reinterpret_cast<uint32_t*>(sm + OFF_TAB2);
-  float4* ex4 = reinterpret_cast<float4*>(sm + OFF_EX);
-  uint8_t* maskb = sm + OFF_MASK;
-  float* red = reinterpret_cast<float*>(sm + OFF_RED);
-  const uint32_t bar1 = base + OFF_BAR, tmem_slot = bar1 + 16u;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + 16);
+  float* tab = reinterpret_cast<float*>(sm + L::OFF_TAB);
+  uint32_t* tab2 = reinterpret_cast<uint32_t*>(sm + L::OFF_TAB2);
+  float4* ex4 = reinterpret_cast<float4*>(sm + L::OFF_EX);
+  uint8_t* maskb = sm + L::OFF_MASK;
+  float* red = reinterpret_cast<float*>(sm + L::OFF_RED);
+  const uint32_t bar1 = base + L::OFF_BAR, tmem_slot = bar1 + 24u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + L::OFF_BAR + 24);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if ((base & 1023u) != 0u) {
     if (tid == 0) printf("tactilesr_b200 psf_tc: dynamic shared memory is not 1024-byte aligned\n");
     __trap();
   }
-  for (uint32_t i = tid; i < 4 * TILE / 16; i += NT) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (uint32_t i = tid; i < L::TILES_END / 16; i += NT) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (uint32_t i = tid; i < 104 * 16 / 4; i += NT) reinterpret_cast<uint32_t*>(maskb)[i] = 0u;
   if (tid == 0) {
     mbar_init(bar1, 1);
@@ -575,11 +773,12 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
   const int m = q * 32 + lane;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
   const uint32_t acc0 = tmem_base + lane_addr, acc1 = tmem_base + 128u + lane_addr;
-  uint8_t* const e_hi = sm + OFF_E_HI; uint8_t* const e_lo = sm + OFF_E_LO;
-  uint8_t* const x_hi = sm + OFF_X_HI; uint8_t* const x_lo = sm + OFF_X_LO;
+  uint8_t* const x_hi = sm + L::OFF_D; uint8_t* const x_lo = sm + L::OFF_D + TILE;
+  uint8_t* const e_hi = sm + L::OFF_E; uint8_t* const e_lo = sm + L::OFF_E + TILE;
+  const uint32_t a_x_hi = base + L::OFF_D, a_x_lo = a_x_hi + TILE, a_e_hi = base + L::OFF_E, a_e_lo = a_e_hi + TILE;
 
   float dreg[IPT][8];
-  if ((int)blockIdx.x < B) load_plane(depth + (size_t)blockIdx.x * N * N, tid, dreg);
+  if ((int)blockIdx.x < B) load_plane<false>(depth + (size_t)blockIdx.x * N * N, tid, dreg);
   uint32_t nph = 0;                       // completed phases of bar1 (4 per sample)
   auto wait_mma = [&]() {
     mbar_wait(bar1, nph & 1u);
@@ -599,70 +798,69 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     for (int t = 0; t < 16; ++t) { g[t] = dLRd[b * 16 + t]; gsum += g[t]; }
 
     // ---- tables, depth max, E and depth tiles ----
-    float lmax, lamax;
-    plane_max(dreg, tid, lmax, lamax);
+    float dmax, amax;
+    plane_max(dreg, tid, dmax, amax);
     build_tables(beta, gamma, tab, ex4, tid);
-    const float dmax = block_max256(lmax, red);
-    const float amax = block_max256(lamax, red);
+    block_max2(dmax, amax, red);
     const float thr = dmax - 1e-3f;
     int dexp = 0;
     if (amax > 0.f) (void)frexpf(amax, &dexp);
     const float sD = ldexpf(1.0f, 4 - dexp);
     build_tab2<0>(tab, tab2, tid);
+    store_plane_tiles<PASSES>(dreg, sD, thr, x_hi, x_lo, maskb, tid);
     __syncthreads();
-    build_toeplitz_tiles(tab2, e_hi, e_lo, tid);
-    store_plane_tiles(dreg, sD, thr, x_hi, x_lo, maskb, tid);
+    build_toeplitz_tiles<PASSES>(tab2, e_hi, e_lo, tid);
     publish();
 
     // ---- GEMM 1: T = E D -> acc0  (2^(8 - dexp) T) ----
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_gemm3<1>(tmem_base, base + OFF_E_HI, base + OFF_E_LO, base + OFF_X_HI, base + OFF_X_LO, idesc1);
+        issue_gemm_kmn<PASSES>(tmem_base, a_e_hi, a_e_lo, a_x_hi, a_x_lo, idesc1);
         umma_commit(bar1);
       }
       __syncwarp();
     }
-    if (b + (int)gridDim.x < B) load_plane(depth + (size_t)(b + gridDim.x) * N * N, tid, dreg);
+    if (b + (int)gridDim.x < B) load_plane<false>(depth + (size_t)(b + gridDim.x) * N * N, tid, dreg);
     build_tab2<1>(tab, tab2, tid);        // (all reads of the E table finished before publish())
     __syncthreads();
     wait_mma();
-    build_toeplitz_tiles(tab2, e_hi, e_lo, tid);      // E2 over E
+    build_toeplitz_tiles<PASSES>(tab2, e_hi, e_lo, tid);      // E2 over E
     publish();
 
     // ---- GEMM 2: T2 = E2 D -> acc1  (2^(8 - dexp) T2) ----
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_gemm3<1>(tmem_base + 128u, base + OFF_E_HI, base + OFF_E_LO, base + OFF_X_HI, base + OFF_X_LO, idesc1);
+        issue_gemm_kmn<PASSES>(tmem_base + 128u, a_e_hi, a_e_lo, a_x_hi, a_x_lo, idesc1);
         umma_commit(bar1);
       }
       __syncwarp();
     }
     build_tab2<2>(tab, tab2, tid);        // 2^15 e(t) for the last product
     wait_mma();
-    acc_to_tiles(acc0, 1.0f, x_hi, x_lo, m, half);    // T over the depth tiles
+    acc_to_tiles<PASSES>(acc0, 1.0f, x_hi, x_lo, m, half);    // T over the depth tiles
     publish();
 
     // ---- GEMM 3: acc0 = T E2  (2^(12 - dexp)) ----
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_gemm3<0>(tmem_base, base + OFF_X_HI, base + OFF_X_LO, base + OFF_E_HI, base + OFF_E_LO, idesc2);
+        issue_gemm_kk<PASSES>(tmem_base, a_x_hi, a_x_lo, a_e_hi, a_e_lo, idesc2);
         umma_commit(bar1);
       }
       __syncwarp();
     }
     wait_mma();
-    acc_to_tiles(acc1, 1.0f / 2048.0f, x_hi, x_lo, m, half);    // 2^(-3 - dexp) T2 over T;  |T2| < 2^(18 + dexp)
-    build_toeplitz_tiles(tab2, e_hi, e_lo, tid);                // 2^15 E over E2
+    acc_to_tiles<PASSES>(acc1, 1.0f / 2048.0f, x_hi, x_lo, m, half);    // 2^(-3 - dexp) T2 over T;  |T2| < 2^(18 + dexp)
+    build_toeplitz_tiles<PASSES>(tab2, e_hi, e_lo, tid);                // 2^15 E over E2
     publish();
 
     // ---- GEMM 4: acc0 += T2 E ----
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        issue_gemm3<0, 1>(tmem_base, base + OFF_X_HI, base + OFF_X_LO, base + OFF_E_HI, base + OFF_E_LO, idesc2);
+        issue_gemm_kk<PASSES, 1>(tmem_base, a_x_hi, a_x_lo, a_e_hi, a_e_lo, idesc2);
         umma_commit(bar1);
       }
       __syncwarp();
@@ -691,48 +889,52 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
         G1 = fmaf(ei[i] * (d * d), ai, fmaf(ei[i], bi, G1));
       }
     }
+    uint32_t blo, bhi;
+    contact_bits(maskb, m < N ? m : 0, half, blo, bhi);
     wait_mma();
 
-    // ---- epilogue over acc0 = 2^(12 - dexp) P3 ----
-    float dbs = 0.f, cw = 0.f, cnt = 0.f;
-    const uint8_t* mrow = maskb + (m < (int)ROWS ? m : 0) * 16;
-#pragma unroll 1
-    for (int gI = 0; gI < 7; ++gI) {
-      const int cg = half * 7 + gI;
-      uint32_t v[8];
-      tmem_ld8(acc0 + (uint32_t)(cg * 8), v);
-      tmem_ld_wait();
-      if (m < N && cg < 13) {
-        const uint32_t bits = mrow[cg];
-        const int nv = cg == 12 ? 4 : 8;
+    // ---- epilogue over acc0 = 2^(12 - dexp) P3: this thread's 56 columns in two register batches ----
+    float dbs = 0.f, cw = 0.f;
+    const int c0 = half * 56;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < nv) {
-            const float4 e4 = ex4[cg * 8 + j];
+    for (int part = 0; part < 2; ++part) {
+      uint32_t v[28];
+      const uint32_t ca = acc0 + (uint32_t)(c0 + part * 28);
+      tmem_ld16(ca, v);
+      tmem_ld8(ca + 16u, v + 16);
+      tmem_ld4(ca + 24u, v + 24);
+      tmem_ld_wait();
+      if (m < N) {
+#pragma unroll
+        for (int jj = 0; jj < 28; ++jj) {
+          const int j = part * 28 + jj;
+          if (j < 44 || half == 0) {
+            const float4 e4 = ex4[c0 + j];
             const float wc = fmaf(e4.x, qt[0], fmaf(e4.y, qt[1], fmaf(e4.z, qt[2], e4.w * qt[3])));
-            const bool contact = (bits >> j) & 1u;
-            dbs = fmaf(contact ? 0.f : wc - mg, __uint_as_float(v[j]), dbs);
+            const bool contact = bit56(blo, bhi, j);
+            dbs = fmaf(contact ? 0.f : wc - mg, __uint_as_float(v[jj]), dbs);
             cw += contact ? wc : 0.f;
           }
         }
-        cnt += (float)__popc(bits & (cg == 12 ? 0x0Fu : 0xFFu));
       }
     }
+    const float cnt = m < N ? (float)(__popc(blo) + __popc(bhi)) : 0.f;
     {
       float p[6] = {dbs, cw, cnt, G0, G1, tot};
 #pragma unroll
       for (int k = 0; k < 6; ++k) p[k] = warp_sum(p[k]);
-      __syncthreads();
+      float* reds = red + 24;
       if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) red[warp * 20 + k] = p[k];
+        for (int k = 0; k < 6; ++k) reds[warp * 20 + k] = p[k];
       }
+      tc_fence_before();
       __syncthreads();
       if (tid == 0) {
         float r[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int w = 0; w < NT / 32; ++w)
 #pragma unroll
-          for (int k = 0; k < 6; ++k) r[k] += red[w * 20 + k];
+          for (int k = 0; k < 6; ++k) r[k] += reds[w * 20 + k];
         const float om = 1.0f - mm, kk = 1e-4f / om;
         const float m2 = aux[(size_t)b * AUX_STRIDE + 100 * AUX_ROW];
         const float s_all = kk * (r[3] - mg * r[5]);                 // sum over all pixels of w HR
@@ -744,9 +946,7 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
         dab[b * 3 + 2] = 1e-4f * ((CM2 * inv_g2 * r[4] - mp * r[5] * gsum) / om + (r[3] - mm * r[5] * gsum) * mp / (om * om));
       }
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    // (the barriers of the next sample's tile phase order everything above before its first MMA)
   }
 
   tc_fence_before();
@@ -759,7 +959,35 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
 
 }  // namespace
 
-int g_psf_mode = 0;     // 0 = tensor-core forward (default), 1 = FFMA forward (psf.cu)
+int g_psf_mode = 0;     // 0 = tensor-core forward, fp32-accurate (default), 1 = FFMA forward (psf.cu), 2 = tensor cores, one fp16 pass
+
+static int psf_tc_grid(int B) {
+  const int sms = num_sms();
+  return B < 2 * sms ? B : 2 * sms;
+}
+
+template <int PASSES>
+static int psf_forward_tc_impl(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, float* aux, int B,
+                               cudaStream_t stream) {
+  TSR_REQUIRE(alphaBeta && depth && HR && LRd && B > 0, "psf_forward_tc: bad argument");
+  TSR_REQUIRE(((uintptr_t)depth & 15) == 0 && ((uintptr_t)HR & 15) == 0 && ((uintptr_t)aux & 15) == 0,
+              "psf_forward_tc: depth / HR / aux must be 16-byte aligned");
+  TSR_CUDA(cudaFuncSetAttribute(psf_fwd_tc_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<PASSES>::BYTES));
+  psf_fwd_tc_kernel<PASSES><<<psf_tc_grid(B), NT, Lay<PASSES>::BYTES, stream>>>(alphaBeta, depth, HR, LRd, psf, aux, B);
+  TSR_CHECK_LAUNCH("psf_forward_tc");
+  return TSR_OK;
+}
+
+template <int PASSES>
+static int psf_backward_tc_impl(const float* alphaBeta, const float* depth, const float* aux, const float* dLRd,
+                                float* dalphaBeta, int B, cudaStream_t stream) {
+  TSR_REQUIRE(alphaBeta && depth && aux && dLRd && dalphaBeta && B > 0, "psf_backward_tc: bad argument");
+  TSR_REQUIRE(((uintptr_t)depth & 15) == 0 && ((uintptr_t)aux & 15) == 0, "psf_backward_tc: depth / aux must be 16-byte aligned");
+  TSR_CUDA(cudaFuncSetAttribute(psf_bwd_tc_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<PASSES>::BYTES));
+  psf_bwd_tc_kernel<PASSES><<<psf_tc_grid(B), NT, Lay<PASSES>::BYTES, stream>>>(alphaBeta, depth, aux, dLRd, dalphaBeta, B);
+  TSR_CHECK_LAUNCH("psf_backward_tc");
+  return TSR_OK;
+}
 
 extern "C" {
 
@@ -771,41 +999,34 @@ int tsr_psf_forward_ffma(const float* alphaBeta, const float* depth, float* HR, 
 
 size_t tsr_psf_aux_floats(void) { return (size_t)AUX_STRIDE; }
 
-static int psf_tc_grid(int B) {
-  int sms = 148, dev = 0;
-  cudaGetDevice(&dev);
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  return B < 2 * sms ? B : 2 * sms;
-}
-
-// aux (B x tsr_psf_aux_floats() floats, or NULL): per-row statistics of HR for tsr_psf_backward_tc
+// fp32-accurate (fp16 hi/lo split operands).  aux (B x tsr_psf_aux_floats() floats, or NULL): per-row statistics of HR for
+// tsr_psf_backward_tc
 int tsr_psf_forward_tc(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, float* aux, int B,
                        cudaStream_t stream) {
-  TSR_REQUIRE(alphaBeta && depth && HR && LRd && B > 0, "psf_forward_tc: bad argument");
-  TSR_REQUIRE(((uintptr_t)depth & 15) == 0 && ((uintptr_t)HR & 15) == 0 && ((uintptr_t)aux & 15) == 0,
-              "psf_forward_tc: depth / HR / aux must be 16-byte aligned");
-  TSR_CUDA(cudaFuncSetAttribute(psf_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  psf_fwd_tc_kernel<<<psf_tc_grid(B), NT, SMEM_BYTES, stream>>>(alphaBeta, depth, HR, LRd, psf, aux, B);
-  TSR_CHECK_LAUNCH("psf_forward_tc");
-  return TSR_OK;
+  return psf_forward_tc_impl<3>(alphaBeta, depth, HR, LRd, psf, aux, B, stream);
+}
+// one fp16 pass (the 16-bit tensor-core precision modes)
+int tsr_psf_forward_tc_f16(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, float* aux, int B,
+                           cudaStream_t stream) {
+  return psf_forward_tc_impl<1>(alphaBeta, depth, HR, LRd, psf, aux, B, stream);
 }
 
 // d alphaBeta (B,3) from dLRd (B,16) alone (the training case), from the depth planes and the forward's aux
 int tsr_psf_backward_tc(const float* alphaBeta, const float* depth, const float* aux, const float* dLRd,
                         float* dalphaBeta, int B, cudaStream_t stream) {
-  TSR_REQUIRE(alphaBeta && depth && aux && dLRd && dalphaBeta && B > 0, "psf_backward_tc: bad argument");
-  TSR_REQUIRE(((uintptr_t)depth & 15) == 0 && ((uintptr_t)aux & 15) == 0, "psf_backward_tc: depth / aux must be 16-byte aligned");
-  TSR_CUDA(cudaFuncSetAttribute(psf_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  psf_bwd_tc_kernel<<<psf_tc_grid(B), NT, SMEM_BYTES, stream>>>(alphaBeta, depth, aux, dLRd, dalphaBeta, B);
-  TSR_CHECK_LAUNCH("psf_backward_tc");
-  return TSR_OK;
+  return psf_backward_tc_impl<3>(alphaBeta, depth, aux, dLRd, dalphaBeta, B, stream);
+}
+int tsr_psf_backward_tc_f16(const float* alphaBeta, const float* depth, const float* aux, const float* dLRd,
+                            float* dalphaBeta, int B, cudaStream_t stream) {
+  return psf_backward_tc_impl<1>(alphaBeta, depth, aux, dLRd, dalphaBeta, B, stream);
 }
 
 // (HR, LRd, psf) = PSF forward model of `depth` (B,100,100) under alphaBeta (B,3).  psf may be NULL.
 int tsr_psf_forward(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, int B,
                     cudaStream_t stream) {
   if (g_psf_mode == 1) return tsr_psf_forward_ffma(alphaBeta, depth, HR, LRd, psf, B, stream);
-  return tsr_psf_forward_tc(alphaBeta, depth, HR, LRd, psf, nullptr, B, stream);
+  if (g_psf_mode == 2) return psf_forward_tc_impl<1>(alphaBeta, depth, HR, LRd, psf, nullptr, B, stream);
+  return psf_forward_tc_impl<3>(alphaBeta, depth, HR, LRd, psf, nullptr, B, stream);
 }
 
 }  // extern "C"

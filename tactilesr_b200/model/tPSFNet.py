@@ -250,5 +250,8 @@ class tPSFNet(nn.Module):
             ab = _MLPFn.apply(x, *params)      # small batches, which are launch-bound (the fp32 path has half the launches)
         # the python ``for i in range(B)`` loop of the reference (:118-125) is one custom op with autograd
         # (torch.ops.tactilesr.psf_model); the forward -> backward hand-over is only produced when a backward can follow
-        HR, LRd, psf, _ = torch.ops.tactilesr.psf_model(ab, depth, torch.is_grad_enabled() and ab.requires_grad)
+        # 16-bit precision modes: the PSF products run as one fp16 tensor-core pass (~3e-4 on HR / LR_degrade, inside the
+        # modes' 1e-2 tolerance); "fp32": the split-operand kernels (~1e-6)
+        HR, LRd, psf, _ = torch.ops.tactilesr.psf_model(ab, depth, torch.is_grad_enabled() and ab.requires_grad,
+                                                        mode in ("fp16", "bf16"))
         return HR, LRd, psf, ab.view(B, 1, 3)

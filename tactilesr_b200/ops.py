@@ -79,10 +79,11 @@ def _(out, hr_raw, scale_num, max_value, c1, c2):
 # the per-sample PSF model of tPSFNet.forward (reference model/tPSFNet.py:118-125) and its backward
 # ---------------------------------------------------------------------------------------------------------------
 @custom_op("tactilesr::psf_model", mutates_args=(), device_types="cuda")
-def psf_model(alpha_beta: Tensor, depth: Tensor, want_aux: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+def psf_model(alpha_beta: Tensor, depth: Tensor, want_aux: bool, f16: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """alphaBeta (B,3), depth (B,100,100) -> HR (B,1,100,100), LR_degrade (B,1,4,4), psf (B,1,99,99), aux.
     aux: the forward -> backward hand-over of the tcgen05 path (per-row statistics of HR), empty when not requested or
-    when the FFMA forward is selected (tsr_set_psf_mode(1))."""
+    when the FFMA forward is selected (tsr_set_psf_mode(1)).  f16: the single-pass fp16 tensor-core kernels (16-bit
+    precision modes, ~3e-4) instead of the fp32-accurate split-operand ones."""
     L = _lib.lib()
     B = alpha_beta.shape[0]
     dev = alpha_beta.device
@@ -92,9 +93,9 @@ def psf_model(alpha_beta: Tensor, depth: Tensor, want_aux: bool) -> Tuple[Tensor
     LRd = torch.empty((B, 1, 4, 4), dtype=torch.float32, device=dev)
     psf = torch.empty((B, 1, 99, 99), dtype=torch.float32, device=dev)
     st = _lib.stream_ptr()
-    if L.tsr_get_psf_mode() == 0:
+    if L.tsr_get_psf_mode() != 1:
         aux = torch.empty((B, int(L.tsr_psf_aux_floats()) if want_aux else 0), dtype=torch.float32, device=dev)
-        _lib.call("tsr_psf_forward_tc", ab.data_ptr(), d.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(),
+        _lib.call("tsr_psf_forward_tc_f16" if (f16 or L.tsr_get_psf_mode() == 2) else "tsr_psf_forward_tc", ab.data_ptr(), d.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(),
                   aux.data_ptr() if want_aux else 0, B, st)
     else:
         aux = torch.empty((B, 0), dtype=torch.float32, device=dev)
@@ -103,7 +104,7 @@ def psf_model(alpha_beta: Tensor, depth: Tensor, want_aux: bool) -> Tuple[Tensor
 
 
 @register_fake("tactilesr::psf_model")
-def _(alpha_beta, depth, want_aux):
+def _(alpha_beta, depth, want_aux, f16=False):
     B = alpha_beta.shape[0]
     f = dict(dtype=torch.float32, device=alpha_beta.device)
     return (torch.empty((B, 1, 100, 100), **f), torch.empty((B, 1, 4, 4), **f), torch.empty((B, 1, 99, 99), **f),
@@ -112,7 +113,7 @@ def _(alpha_beta, depth, want_aux):
 
 @custom_op("tactilesr::psf_model_backward", mutates_args=(), device_types="cuda")
 def psf_model_backward(alpha_beta: Tensor, depth: Tensor, HR: Tensor, aux: Tensor, dLRd: Tensor, dHR: Tensor,
-                       dpsf: Tensor) -> Tensor:
+                       dpsf: Tensor, f16: bool = False) -> Tensor:
     """d alphaBeta (B,3).  Absent upstream gradients are passed as empty tensors.  The training case (gradient through
     LR_degrade only, train/tPSFNet_train.py:186-189) with a forward hand-over runs the tcgen05 backward; everything else
     the general FFMA backward."""
@@ -124,7 +125,8 @@ def psf_model_backward(alpha_beta: Tensor, depth: Tensor, HR: Tensor, aux: Tenso
     keep = [t.detach().contiguous().float() for t in (dLRd, dHR, dpsf)]       # keep converted copies alive
     ptrs = [0 if t.numel() == 0 else t.data_ptr() for t in keep]
     if aux.numel() > 0 and ptrs[0] and not ptrs[1] and not ptrs[2]:
-        _lib.call("tsr_psf_backward_tc", ab.data_ptr(), d.data_ptr(), aux.data_ptr(), ptrs[0], dab.data_ptr(), B, st)
+        _lib.call("tsr_psf_backward_tc_f16" if f16 else "tsr_psf_backward_tc", ab.data_ptr(), d.data_ptr(), aux.data_ptr(), ptrs[0],
+                  dab.data_ptr(), B, st)
     else:
         _lib.call("tsr_psf_backward", ab.data_ptr(), d.data_ptr(), HR.detach().contiguous().data_ptr(), ptrs[0], ptrs[1],
                   ptrs[2], dab.data_ptr(), B, st)
@@ -132,13 +134,14 @@ def psf_model_backward(alpha_beta: Tensor, depth: Tensor, HR: Tensor, aux: Tenso
 
 
 @register_fake("tactilesr::psf_model_backward")
-def _(alpha_beta, depth, HR, aux, dLRd, dHR, dpsf):
+def _(alpha_beta, depth, HR, aux, dLRd, dHR, dpsf, f16=False):
     return alpha_beta.new_empty((alpha_beta.shape[0], 3), dtype=torch.float32)
 
 
 def _psf_setup(ctx, inputs, output):
-    alpha_beta, depth, _ = inputs
+    alpha_beta, depth, _, f16 = inputs
     HR, _, _, aux = output
+    ctx.f16 = bool(f16) or _lib.lib().tsr_get_psf_mode() == 2
     # outputs that take no part in the loss must reach backward as None, not as materialised zeros: the training case
     # (gradient through LR_degrade only) is what selects the tcgen05 backward
     ctx.set_materialize_grads(False)
@@ -148,11 +151,11 @@ def _psf_setup(ctx, inputs, output):
 def _psf_backward(ctx, dHR, dLRd, dpsf, daux):
     alpha_beta, depth, HR, aux = ctx.saved_tensors
     if dHR is None and dLRd is None and dpsf is None:
-        return None, None, None
+        return None, None, None, None
     e = alpha_beta.new_empty((0,))
     dab = torch.ops.tactilesr.psf_model_backward(alpha_beta, depth, HR, aux, e if dLRd is None else dLRd,
-                                                 e if dHR is None else dHR, e if dpsf is None else dpsf)
-    return dab, None, None
+                                                 e if dHR is None else dHR, e if dpsf is None else dpsf, ctx.f16)
+    return dab, None, None, None
 
 
 register_autograd("tactilesr::psf_model", _psf_backward, setup_context=_psf_setup)

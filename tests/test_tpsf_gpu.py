@@ -261,9 +261,10 @@ def test_tpsf_16bit_modes_train_step_within_tensor_core_bound(mode, monkeypatch)
         print(mode, e, {k: f"{v:.1e}" for k, v in eg.items()})
         assert max(e.values()) < tol_out, e
         assert max(eg.values()) < 5e-2, eg
-        # ragged batch (not a multiple of 64): the fp32 kernels take over, results in the fp32 class
+        # ragged batch (not a multiple of 64): the fp32 MLP kernels take over; the PSF products stay on the mode's single
+        # fp16 pass (measured 8e-5 .. 3e-4)
         HR5, _, _, _ = m(LR[:5].cuda(), depth[:5].cuda().unsqueeze(1))
-        assert rel_l2(HR5, HRo[:5]) < 2e-5
+        assert rel_l2(HR5, HRo[:5]) < 2e-3
         # inference under no_grad takes the same tensor-core path
         with torch.no_grad():
             HRn, _, _, _ = m(LR.cuda(), depth.cuda().unsqueeze(1))
@@ -310,3 +311,60 @@ def test_tpsf_fp16_mode_loss_curve_tracks_fp32_mode(monkeypatch):
     assert a[-50:].mean() < a[:10].mean() and b[-50:].mean() < b[:10].mean()
     assert abs(a[-50:].mean() - b[-50:].mean()) / a[-50:].mean() < 2e-2
     assert ((a - b).abs() / a).max() < 0.1
+
+
+@pytest.mark.parametrize("B", [5, 700])
+def test_psf_single_pass_fp16_kernels_within_tensor_core_mode_tolerance(B):
+    """The one-pass fp16 tcgen05 kernels (16-bit precision modes, north_star tolerance 1e-2) against the FFMA forward /
+    backward through the C ABI: HR and LR_degrade within 2e-3 (measured ~3e-4), d(alpha, beta, gamma) within 1e-2."""
+    from oracle import tpsf_oracle as po
+    from tactilesr_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(300 + B)
+    ab = torch.stack([torch.rand(B, generator=g) * 2 + 0.2, torch.rand(B, generator=g) * 3 + 0.25,
+                      torch.rand(B, generator=g) * 40 + 0.4], 1).cuda().contiguous()
+    depth = po.synthetic_depth(min(B, 16), 7).repeat((B + 15) // 16, 1, 1)[:B].clone()
+    depth[1] *= 3.0
+    depth[2] = 0.0
+    depth = depth.cuda().contiguous()
+    dL = (torch.randn(B, 16, generator=g) * 0.3).cuda().contiguous()
+    st = torch.cuda.current_stream().cuda_stream
+    mk = lambda: (torch.empty(B, 100, 100, device="cuda"), torch.empty(B, 16, device="cuda"), torch.empty(B, 99, 99, device="cuda"))
+    h0, l0, p0 = mk(); h1, l1, p1 = mk()
+    aux = torch.empty(B, int(L.tsr_psf_aux_floats()), device="cuda")
+    _lib.call("tsr_psf_forward_ffma", ab.data_ptr(), depth.data_ptr(), h0.data_ptr(), l0.data_ptr(), p0.data_ptr(), B, st)
+    _lib.call("tsr_psf_forward_tc_f16", ab.data_ptr(), depth.data_ptr(), h1.data_ptr(), l1.data_ptr(), p1.data_ptr(), aux.data_ptr(), B, st)
+    assert torch.isfinite(h1).all() and torch.isfinite(l1).all() and torch.equal(p0, p1)
+    scale = h0.flatten(1).abs().amax(1).clamp_min(1e-20)[:, None, None]
+    err = ((h1 - h0).abs() / scale).max().item()
+    print(f"psf f16 vs ffma B={B}: HR max err / sample max {err:.2e}, rel-L2 {rel_l2(h1, h0):.2e}, LRd rel-L2 {rel_l2(l1, l0):.2e}")
+    assert err < 4e-3 and rel_l2(h1, h0) < 2e-3 and rel_l2(l1, l0) < 2e-3
+    d0 = torch.empty(B, 3, device="cuda"); d1 = torch.empty(B, 3, device="cuda")
+    _lib.call("tsr_psf_backward", ab.data_ptr(), depth.data_ptr(), h0.data_ptr(), dL.data_ptr(), 0, 0, d0.data_ptr(), B, st)
+    _lib.call("tsr_psf_backward_tc_f16", ab.data_ptr(), depth.data_ptr(), aux.data_ptr(), dL.data_ptr(), d1.data_ptr(), B, st)
+    assert torch.isfinite(d1).all()
+    for c, name in enumerate(("alpha", "beta", "gamma")):
+        e = rel_l2(d1[:, c], d0[:, c])
+        print(f"psf bwd f16 vs ffma B={B} d{name}: rel-L2 {e:.2e}")
+        assert e < 1e-2, (name, e)
+
+
+def test_tpsf_module_fp16_mode_within_1e2_of_reference():
+    """tPSFNet under set_precision("fp16"): single-pass PSF kernels (and, at B >= 1024, the tensor-core MLP) against the
+    golden vectors of the unmodified reference: outputs and loss within north_star's 1e-2 tensor-core-mode bound."""
+    import tactilesr_b200 as tb
+    g = load_golden("tpsf_fwdbwd.npz")
+    m, LR_raw, depth = _setup(g)
+    tb.set_precision("fp16")
+    try:
+        LR = LR_raw.cuda() / 100
+        HR, LRd, psf, ab = m(LR, depth.cuda().unsqueeze(1))
+        assert rel_l2(HR, g["f64/HR"]) < 1e-2 and rel_l2(LRd, g["f64/LRd"]) < 1e-2
+        loss = torch.nn.functional.mse_loss(LR[:, 2:3], LRd)
+        assert abs(loss.item() - float(g["f64/loss"])) / float(g["f64/loss"]) < 1e-2
+        loss.backward()
+        for (n, p), want in zip(m.named_parameters(), g["f64/grad_summary"]):
+            got = summarize(p.grad)
+            assert abs(got[0] - want[0]) / want[0] < 2e-2, (n, got[0], want[0])
+    finally:
+        tb.set_precision("fp32")

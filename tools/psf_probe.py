@@ -14,9 +14,13 @@ aux = torch.empty(B, int(_lib.lib().tsr_psf_aux_floats()), device="cuda")
 f_tc = lambda: _lib.call("tsr_psf_forward_tc", ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), 0, B, st)
 f_tca = lambda: _lib.call("tsr_psf_forward_tc", ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), aux.data_ptr(), B, st)
 b_tc = lambda: _lib.call("tsr_psf_backward_tc", ab.data_ptr(), depth.data_ptr(), aux.data_ptr(), dL.data_ptr(), dab.data_ptr(), B, st)
+f_16 = lambda: _lib.call("tsr_psf_forward_tc_f16", ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), 0, B, st)
+f_16a = lambda: _lib.call("tsr_psf_forward_tc_f16", ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), aux.data_ptr(), B, st)
+b_16 = lambda: _lib.call("tsr_psf_backward_tc_f16", ab.data_ptr(), depth.data_ptr(), aux.data_ptr(), dL.data_ptr(), dab.data_ptr(), B, st)
 f_ff = lambda: _lib.call("tsr_psf_forward_ffma", ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), LRd.data_ptr(), psf.data_ptr(), B, st)
 b = lambda: _lib.call("tsr_psf_backward", ab.data_ptr(), depth.data_ptr(), HR.data_ptr(), dL.data_ptr(), 0, 0, dab.data_ptr(), B, st)
-for name, fn in (("fwd tcgen05", f_tc), ("fwd tcgen05 + aux", f_tca), ("fwd ffma", f_ff), ("bwd tcgen05", b_tc), ("bwd ffma", b)):
+for name, fn in (("fwd tcgen05", f_tc), ("fwd tcgen05 + aux", f_tca), ("fwd tcgen05 f16", f_16), ("fwd tcgen05 f16 + aux", f_16a),
+                 ("fwd ffma", f_ff), ("bwd tcgen05", b_tc), ("bwd tcgen05 f16", b_16), ("bwd ffma", b)):
     for _ in range(2): fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
