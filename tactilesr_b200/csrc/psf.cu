@@ -174,7 +174,7 @@ psf_fwd_kernel(const float* __restrict__ ab, const float* __restrict__ depth, fl
     const float dmax = block_max(lmax, scratch);   // (syncs: tables and P0 visible)
     if (psf) {
       float* pdst = psf + (long long)b * 99 * 99;
-      for (int i = threadIdx.x; i < 99 * 99; i += NT) pdst[i] = alpha * (tabE[50 + i / 99] * tabE[50 + i % 99]);
+      for (int i = threadIdx.x; i < 99 * 99; i += NT) pdst[i] = (alpha * tabE[50 + i / 99]) * tabE[50 + i % 99];
     }
     colpass<false>(P0, tabE, nullptr, P1, nullptr);
     __syncthreads();

@@ -32,7 +32,8 @@
 namespace {
 
 constexpr int N = 100;
-constexpr int NT = 256;
+constexpr int PSF_THREADS = 256;   // (512 = four threads per accumulator row was measured 5..25 % slower: the kernels are
+                                   //  bound by shared-memory wavefronts, not by latency hiding)
 constexpr float CP2 = 100.0f / 4802.0f;
 constexpr float CM2 = 100.0f / 15138.0f;
 
@@ -40,7 +41,7 @@ constexpr uint32_t ROWS = 104;                 // allocated rows of a tile (13 g
 constexpr uint32_t ATOM = ROWS * 128u;         // one 64-wide atom: rows x 128 B, SWIZZLE_128B
 constexpr uint32_t TILE = 2u * ATOM;           // 112 = 64 + 48 elements along the atom direction
 constexpr uint32_t PLANE_BYTES = N * N * 4u;   // 40 000
-constexpr uint32_t TAB2_LEN = 208;             // per shifted copy
+constexpr uint32_t TAB2_LEN = 216;             // per shifted copy (>= 204; 216: a quarter-warp of consecutive rows reads 8 distinct bank groups)
 
 // forward -> backward hand-over, AUX_STRIDE floats per sample: rows m = 0..99 hold U_j(m) = sum_n HR[m][n] Ex_j(n),
 // U2_j(m) = sum_n HR[m][n] Ex_j(n) (n - 12 - 25 j)^2 (j = 0..3), the row sum and 3 pad floats; row 100 = {second max}
@@ -50,8 +51,13 @@ constexpr int AUX_STRIDE = 101 * AUX_ROW;
 // Shared-memory map.  Depth tiles first: GEMM1 reads K rows 96..111 of the (MN-major) depth tiles, i.e. 1 KB past a tile's
 // 104 rows -- for the last depth tile that lands in E_hi (always finite; it meets the zero K-padding of E).  Over-reads of
 // M / N rows >= 104 only produce accumulator rows / columns that are never used.
-template <int PASSES>
+// NT threads per CTA = 128 x SEGS: SEGS threads share an accumulator row (NT = 256: two threads, 56 columns each)
+template <int PASSES, int NT>
 struct Lay {
+  static constexpr int NW = NT / 32;                                     // warps
+  static constexpr int SEGS = NT / 128;                                  // column segments per accumulator row
+  static constexpr int COLS = 112 / SEGS;                                // accumulator columns per thread
+  static constexpr int NV_LAST = N - (SEGS - 1) * COLS;                  // valid (< 100) columns of the last segment
   static constexpr uint32_t NH = PASSES == 3 ? 2u : 1u;                  // tiles per operand: hi [, lo]
   static constexpr uint32_t OFF_D = 0;                                   // D_hi [, D_lo]
   static constexpr uint32_t OFF_E = NH * TILE;                           // E_hi [, E_lo]
@@ -62,18 +68,21 @@ struct Lay {
   static constexpr uint32_t OFF_TAB = PASSES == 3 ? TILES_END : TILES_END + PLANE_BYTES;   // float e(t), t = 0..99 (+ pad)
   static constexpr uint32_t OFF_TAB2 = OFF_TAB + 128 * 4;                // 4 shifted copies of uint32 (hi | lo << 16) of 16 e(|j - 99|)
   static constexpr uint32_t OFF_EX = OFF_TAB2 + 4 * TAB2_LEN * 4;        // float4 (Ex_0..Ex_3)(t), t = 0..99
-  static constexpr uint32_t OFF_MASK = OFF_EX + 100 * 16;                // contact bytes [104][16]: bit j of [k][cg] <-> depth[k][8 cg + j]
-  static constexpr uint32_t OFF_RED = OFF_MASK + 104 * 16;               // float scratch: 3 x [8] block-max partials, [8][20] sums
-  static constexpr uint32_t OFF_BAR = OFF_RED + (24 + 8 * 20) * 4;       // 3 mbarriers + tmem slot
-  static constexpr uint32_t OFF_X24 = PASSES == 3 ? 40960u : OFF_BAR + 32u;   // float4 Ex_j(t) (t - 12 - 25 j)^2 (training hand-over)
-  static constexpr uint32_t OFF_XCH = OFF_X24 + 2048u;                        // half-row exchange of the hand-over statistics
-  static constexpr uint32_t USED = PASSES == 3 ? OFF_BAR + 32u : OFF_XCH + 100 * AUX_ROW * 4;
+  static constexpr uint32_t OFF_MASK = OFF_EX + 100 * 16;                // contact bytes [13][104]: bit j of [cg][k] <-> depth[k][8 cg + j]
+  static constexpr uint32_t OFF_RED = OFF_MASK + 104 * 16;               // float scratch: 2 x [NW] block-max partials, [NW][20] sums
+  static constexpr uint32_t OFF_BAR = OFF_RED + (2 * NW + NW * 20) * 4;  // 3 mbarriers + tmem slot
+  static constexpr uint32_t OFF_X24 = PASSES == 3 ? 40064u : OFF_BAR + 32u;   // float4 Ex_j(t) (t - 12 - 25 j)^2 (training hand-over)
+  // row-segment exchange of the hand-over statistics: per writer segment [100] float4 U, [100] float4 U2, [100] float sum
+  static constexpr uint32_t OFF_XCH = OFF_X24 + 1600u;
+  static constexpr uint32_t XCH_SEG = 100 * 36;
+  static constexpr uint32_t XCH_END = OFF_XCH + (SEGS - 1) * XCH_SEG;
+  static constexpr uint32_t USED = PASSES == 3 ? OFF_BAR + 32u : XCH_END;
   // the finished HR plane (dense rows) before its bulk store: over tiles that are dead after GEMM2
   static constexpr uint32_t OFF_STAGE = PASSES == 3 ? OFF_E : 0u;
   static constexpr size_t BYTES = (USED + 15u) & ~15u;
   static_assert(OFF_BAR % 8 == 0 && OFF_TAB % 16 == 0 && OFF_RAW % 16 == 0, "alignment");
   static_assert(USED - TILES_END >= 3072, "the last tile's over-read must stay inside the allocation");
-  static_assert(PASSES != 3 || OFF_XCH + 100 * AUX_ROW * 4 <= OFF_E, "hand-over scratch inside the dead depth tiles");
+  static_assert(PASSES != 3 || XCH_END <= OFF_E, "hand-over scratch inside the dead depth tiles");
   static_assert(OFF_STAGE + PLANE_BYTES <= TILES_END, "HR staging inside the tiles");
   static_assert(2 * (BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
 };
@@ -145,17 +154,23 @@ __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint3
   lo = h2_bits(__floats2half2_rn(x0 - f.x, x1 - f.y));
 }
 
-// block maximum of up to two values with ONE barrier: partials in red[0..7] / red[8..15]; the caller alternates between
-// two scratch areas or has another barrier before the next call
+// block maximum of two values with ONE barrier: partials in red[0..NW) / red[NW..2 NW); the caller has another barrier
+// before the next call
+template <int NT>
 __device__ __forceinline__ void block_max2(float& a, float& b, float* red) {
+  constexpr int NW = NT / 32;
   a = warp_max(a);
   b = warp_max(b);
-  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = a; red[8 + (threadIdx.x >> 5)] = b; }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = a; red[NW + (threadIdx.x >> 5)] = b; }
   __syncthreads();
-  const float4 a0 = reinterpret_cast<const float4*>(red)[0], a1 = reinterpret_cast<const float4*>(red)[1];
-  const float4 b0 = reinterpret_cast<const float4*>(red)[2], b1 = reinterpret_cast<const float4*>(red)[3];
-  a = fmaxf(fmaxf(fmaxf(a0.x, a0.y), fmaxf(a0.z, a0.w)), fmaxf(fmaxf(a1.x, a1.y), fmaxf(a1.z, a1.w)));
-  b = fmaxf(fmaxf(fmaxf(b0.x, b0.y), fmaxf(b0.z, b0.w)), fmaxf(fmaxf(b1.x, b1.y), fmaxf(b1.z, b1.w)));
+  const float4* r4 = reinterpret_cast<const float4*>(red);
+  a = -INFINITY; b = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NW / 4; ++i) {
+    const float4 x = r4[i], y = r4[NW / 4 + i];
+    a = fmaxf(a, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+    b = fmaxf(b, fmaxf(fmaxf(y.x, y.y), fmaxf(y.z, y.w)));
+  }
 }
 
 // D[128 x 112] (TMEM) = A B over PASSES operand pairs (hi hi [+ lo hi + hi lo]).  A: K-major smem tile.  B: MN-major smem
@@ -215,22 +230,38 @@ __device__ __forceinline__ void issue_gemm_tk(uint32_t tmem_d, uint32_t t_hi, ui
   }
 }
 
-constexpr int ITEMS = 13 * N;                  // (row, 8-element chunk) work items of a 100 x 100 plane
-constexpr int IPT = (ITEMS + NT - 1) / NT;     // 6 (the last round only for 20 threads)
-constexpr int ITEMS_E = 14 * N;                // ... of a Toeplitz tile incl. its zero K-padding chunk 13
-constexpr int IPT_E = (ITEMS_E + NT - 1) / NT; // 6
+// (row, 8-element chunk) work items of a 100 x 100 plane / of a Toeplitz tile incl. its zero K-padding chunk 13.
+// RMAJOR: consecutive lanes take consecutive ROWS of one chunk column (rows padded to 104, so 8-row groups stay inside a
+// quarter-warp): every 16-byte shared-memory access of a quarter-warp -- row-major fp32 plane (row pitch 400 B), swizzled
+// tile, shifted table -- then falls into 8 distinct bank groups.  Chunk-fastest order (consecutive lanes = consecutive
+// 32-byte pieces of a row) is kept for planes read straight from global memory, where it coalesces.
+constexpr int ITEMS = 13 * 104;
+constexpr int ITEMS_E = 14 * 104;
+template <int NT> __host__ __device__ constexpr int ipt() { return (ITEMS + NT - 1) / NT; }        // 6 rounds per thread
+template <int NT> __host__ __device__ constexpr int ipt_e() { return (ITEMS_E + NT - 1) / NT; }
+template <bool RMAJOR>
+__device__ __forceinline__ bool item_rc(int item, int nchunks, int& r, int& cg) {
+  if (RMAJOR) {
+    cg = item / 104;
+    r = item - cg * 104;
+    return cg < nchunks && r < N;
+  }
+  r = item / nchunks;
+  cg = item - r * nchunks;
+  return r < N;
+}
 
 // this thread's chunks of one depth plane -> registers: item = (row k, columns 8 cg .. 8 cg + 7), consecutive lanes read
 // consecutive 32-byte pieces; chunk 12 of a row holds columns 96..99 only (the rest reads as 0).  SMEM: the plane lies in
 // shared memory (bulk copy), else in global memory.
-template <bool SMEM>
-__device__ __forceinline__ void load_plane(const float* __restrict__ dsrc, int tid, float (&dreg)[IPT][8]) {
+template <bool SMEM, int NT>
+__device__ __forceinline__ void load_plane(const float* __restrict__ dsrc, int tid, float (&dreg)[ipt<NT>()][8]) {
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const int item = tid + i * NT;
-    const int k = item / 13, cg = item - k * 13;
+  for (int i = 0; i < ipt<NT>(); ++i) {
+    int k, cg;
+    const bool ok = item_rc<SMEM>(tid + i * NT, 13, k, cg);
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
-    if (item < ITEMS) {
+    if (ok) {
       const float4* src = reinterpret_cast<const float4*>(dsrc + k * N + cg * 8);
       if (SMEM) {
         a = src[0];
@@ -248,7 +279,7 @@ __device__ __forceinline__ void load_plane(const float* __restrict__ dsrc, int t
 // 4 shifted copies of the packed (hi | lo << 16) fp16 table of the banded Toeplitz generator, so that any 8 consecutive
 // entries are two aligned 16-byte loads.  kind 0: 16 e(t);  1: 16 e(t) t^2;  2: 32768 e(t)   (t = |j - 99| <= 49, else 0:
 // the PSF has 99 taps)
-template <int KIND>
+template <int KIND, int NT>
 __device__ __forceinline__ void build_tab2(const float* tab, uint32_t* tab2, int tid) {
   for (int i = tid; i < 4 * (int)TAB2_LEN; i += NT) {
     const int s = i / (int)TAB2_LEN, qn = i - s * (int)TAB2_LEN;
@@ -264,13 +295,12 @@ __device__ __forceinline__ void build_tab2(const float* tab, uint32_t* tab2, int
 
 // K-major hi [/ lo] tiles of the Toeplitz matrix from the table: M[r][8 cg + j] = gen(|8 cg + j - r|); chunk 13 (the K
 // padding 104..111, which the MMAs read) is rewritten as zeros: HR staging / raw planes lie over the tiles between samples
-template <int PASSES>
+template <int PASSES, int NT>
 __device__ __forceinline__ void build_toeplitz_tiles(const uint32_t* tab2, uint8_t* t_hi, uint8_t* t_lo, int tid) {
 #pragma unroll
-  for (int i = 0; i < IPT_E; ++i) {
-    const int item = tid + i * NT;
-    if (item < ITEMS_E) {
-      const int r = item / 14, cg = item - r * 14;
+  for (int i = 0; i < ipt_e<NT>(); ++i) {
+    int r, cg;
+    if (item_rc<true>(tid + i * NT, 14, r, cg)) {
       const uint32_t off = chunk_off(r, cg);
       uint4 p0 = make_uint4(0u, 0u, 0u, 0u), p1 = p0;
       if (cg < 13) {
@@ -293,14 +323,13 @@ __device__ __forceinline__ void build_toeplitz_tiles(const uint32_t* tab2, uint8
 // Everything GEMM1 reads as K rows 100..111 meets the zero K-padding of E and must be finite, and other data has been lying
 // over the tiles: rows 100..103 of every atom are zeroed, and -- rows 104..111 of an atom-0 are the first 8 rows of the
 // following atom-1 -- the column chunks 5..7 of those rows, which no depth store covers (columns 104..127)
-template <int PASSES>
-__device__ __forceinline__ void store_plane_tiles(const float (&dreg)[IPT][8], float sD, float thr, uint8_t* x_hi,
+template <int PASSES, int NT, bool RMAJOR>
+__device__ __forceinline__ void store_plane_tiles(const float (&dreg)[ipt<NT>()][8], float sD, float thr, uint8_t* x_hi,
                                                   uint8_t* x_lo, uint8_t* maskb, int tid) {
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const int item = tid + i * NT;
-    if (item < ITEMS) {
-      const int r = item / 13, cg = item - r * 13;
+  for (int i = 0; i < ipt<NT>(); ++i) {
+    int r, cg;
+    if (item_rc<RMAJOR>(tid + i * NT, 13, r, cg)) {
       const uint32_t off = chunk_off(r, cg);
       uint32_t dh[4], dl[4], bits = 0u;
 #pragma unroll
@@ -310,7 +339,7 @@ __device__ __forceinline__ void store_plane_tiles(const float (&dreg)[IPT][8], f
         if (dreg[i][j] > thr && (cg < 12 || j < 4)) bits |= 1u << j;
       *reinterpret_cast<uint4*>(x_hi + off) = make_uint4(dh[0], dh[1], dh[2], dh[3]);
       if (PASSES == 3) *reinterpret_cast<uint4*>(x_lo + off) = make_uint4(dl[0], dl[1], dl[2], dl[3]);
-      maskb[r * 16 + cg] = (uint8_t)bits;
+      maskb[cg * 104 + r] = (uint8_t)bits;
     }
   }
   constexpr int NATOM = PASSES == 3 ? 4 : 2;
@@ -323,21 +352,50 @@ __device__ __forceinline__ void store_plane_tiles(const float (&dreg)[IPT][8], f
   }
 }
 
-// accumulator (TMEM, this thread's 56 columns at acc) * scale -> K-major hi [/ lo] smem tiles; thread = (row m, column half)
-template <int PASSES>
-__device__ __forceinline__ void acc_to_tiles(uint32_t acc, float scale, uint8_t* x_hi, uint8_t* x_lo, int m, int half) {
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+}
+// COLS (56 or 28) consecutive accumulator columns of this thread's lane -> registers (loads in flight: call tmem_ld_wait)
+template <int COLS>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
+  if (COLS == 56) {
+    tmem_ld32(taddr, v);
+    tmem_ld16(taddr + 32u, v + 32);
+    tmem_ld8(taddr + 48u, v + 48);
+  } else {
+    tmem_ld16(taddr, v);
+    tmem_ld8(taddr + 16u, v + 16);
+    tmem_ld4(taddr + 24u, v + 24);
+  }
+}
+// NP (28 or 14) consecutive columns of packed fp16 pairs
+template <int NP>
+__device__ __forceinline__ void tmem_st_pairs(uint32_t taddr, const uint32_t* r) {
+  if (NP == 28) {
+    tmem_st16(taddr, r);
+    tmem_st8(taddr + 16u, r + 16);
+    tmem_st4(taddr + 24u, r + 24);
+  } else {
+    tmem_st8(taddr, r);
+    tmem_st4(taddr + 8u, r + 8);
+    tmem_st2(taddr + 12u, r + 12);
+  }
+}
+
+// accumulator (TMEM, this thread's COLS columns from column seg * COLS of `acc`) * scale -> K-major hi [/ lo] smem tiles;
+// thread = (row m, column segment)
+template <int PASSES, int COLS>
+__device__ __forceinline__ void acc_to_tiles(uint32_t acc, float scale, uint8_t* x_hi, uint8_t* x_lo, int m, int seg) {
 #pragma unroll
-  for (int part = 0; part < 2; ++part) {                     // 2 x 28 columns: 32 registers in flight
+  for (int part = 0; part < COLS / 28; ++part) {             // 28 columns at a time: 32 registers in flight
     uint32_t v[28];
-    const uint32_t c0 = acc + (uint32_t)(half * 56 + part * 28);
-    tmem_ld16(c0, v);
-    tmem_ld8(c0 + 16u, v + 16);
-    tmem_ld4(c0 + 24u, v + 24);
+    const int cbase = seg * COLS + part * 28;
+    tmem_ld_cols<28>(acc + (uint32_t)cbase, v);
     tmem_ld_wait();
     if (m < (int)ROWS) {
 #pragma unroll
-      for (int g = 0; g < 7; ++g) {                          // 16-byte chunk = 8 columns; a part covers 3.5 chunks
-        const int col0 = half * 56 + part * 28 + g * 4;      // 4 columns = half a chunk
+      for (int g = 0; g < 7; ++g) {                          // 4 columns = half a 16-byte chunk
+        const int col0 = cbase + g * 4;
         const int cg = col0 >> 3, hsel = (col0 >> 2) & 1;
         uint32_t th[2], tl[2];
 #pragma unroll
@@ -355,43 +413,34 @@ __device__ __forceinline__ void acc_to_tiles(uint32_t acc, float scale, uint8_t*
   }
 }
 
-// accumulator (TMEM, this thread's 56 columns at acc) -> packed fp16 hi [/ lo] pairs in tensor memory at t_hi / t_lo (this
-// thread's 28 columns of each): the A operand of the next product.  K columns >= 100 (depth-tile garbage) are zeroed.
-template <int PASSES>
-__device__ __forceinline__ void acc_to_tmem(uint32_t acc, uint32_t t_hi, uint32_t t_lo, int half) {
-  uint32_t v[56];
-  const uint32_t c0 = acc + (uint32_t)(half * 56);
-  tmem_ld32(c0, v);
-  tmem_ld16(c0 + 32u, v + 32);
-  tmem_ld8(c0 + 48u, v + 48);
+// accumulator (TMEM, this thread's COLS columns) -> packed fp16 hi [/ lo] pairs in tensor memory at t_hi / t_lo (this
+// thread's COLS / 2 columns of each): the A operand of the next product.  K columns >= 100 (depth-tile garbage) are zeroed.
+template <int PASSES, int COLS>
+__device__ __forceinline__ void acc_to_tmem(uint32_t acc, uint32_t t_hi, uint32_t t_lo, int seg) {
+  constexpr int NP = COLS / 2;
+  uint32_t v[COLS];
+  tmem_ld_cols<COLS>(acc + (uint32_t)(seg * COLS), v);
   tmem_ld_wait();
-  uint32_t th[28], tl[28];
+  uint32_t th[NP], tl[NP];
 #pragma unroll
-  for (int j = 0; j < 28; ++j) split_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), th[j], tl[j]);
-  if (half) {
-#pragma unroll
-    for (int j = 22; j < 28; ++j) { th[j] = 0u; tl[j] = 0u; }          // k = 56 + 2 j >= 100
+  for (int j = 0; j < NP; ++j) {
+    split_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), th[j], tl[j]);
+    if (seg * COLS + 2 * j >= N) { th[j] = 0u; tl[j] = 0u; }            // k >= 100 (only in the last segment)
   }
-  const uint32_t p0 = (uint32_t)(half * 28);
-  tmem_st16(t_hi + p0, th);
-  tmem_st8(t_hi + p0 + 16u, th + 16);
-  tmem_st4(t_hi + p0 + 24u, th + 24);
-  if (PASSES == 3) {
-    tmem_st16(t_lo + p0, tl);
-    tmem_st8(t_lo + p0 + 16u, tl + 16);
-    tmem_st4(t_lo + p0 + 24u, tl + 24);
-  }
+  const uint32_t p0 = (uint32_t)(seg * NP);
+  tmem_st_pairs<NP>(t_hi + p0, th);
+  if (PASSES == 3) tmem_st_pairs<NP>(t_lo + p0, tl);
   tmem_st_wait();
 }
 
 // depth max / abs-max over this thread's register-held chunks
-__device__ __forceinline__ void plane_max(const float (&dreg)[IPT][8], int tid, float& lmax, float& lamax) {
+template <int NT, bool RMAJOR>
+__device__ __forceinline__ void plane_max(const float (&dreg)[ipt<NT>()][8], int tid, float& lmax, float& lamax) {
   lmax = -INFINITY; lamax = 0.f;
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const int item = tid + i * NT;
-    const int cg = item % 13;
-    if (item < ITEMS) {
+  for (int i = 0; i < ipt<NT>(); ++i) {
+    int r, cg;
+    if (item_rc<RMAJOR>(tid + i * NT, 13, r, cg)) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (j < 4 || cg < 12) lmax = fmaxf(lmax, dreg[i][j]);      // chunk 12 holds columns 96..99 only
@@ -402,6 +451,7 @@ __device__ __forceinline__ void plane_max(const float (&dreg)[IPT][8], int tid, 
 }
 
 // e(t) and the (Ex_0..Ex_3)(t) table of one sample
+template <int NT>
 __device__ __forceinline__ void build_tables(float beta, float gamma, float* tab, float4* ex4, int tid) {
   const float inv_b2 = 1.0f / (beta * beta);
   if (tid < N) tab[tid] = expf(-(CP2 * (float)(tid * tid)) * inv_b2);
@@ -413,31 +463,37 @@ __device__ __forceinline__ void build_tables(float beta, float gamma, float* tab
   }
 }
 
-// this thread's 56 contact bits: bit j <-> column half * 56 + j of row `row` (bytes 7 half .. 7 half + 6 of the 16-byte row)
-__device__ __forceinline__ void contact_bits(const uint8_t* maskb, int row, int half, uint32_t& blo, uint32_t& bhi) {
-  const uint4 mw = *reinterpret_cast<const uint4*>(maskb + row * 16);
-  if (half == 0) {
-    blo = mw.x;
-    bhi = mw.y & 0x00FFFFFFu;
-  } else {
-    blo = __funnelshift_r(mw.y, mw.z, 24);
-    bhi = __funnelshift_r(mw.z, mw.w, 24) & 0x00000FFFu;     // columns 88..99
+// this thread's 56 contact bits: bit j <-> column seg * 56 + j of row `row`.  Contact bytes [13][104]: bit j of [cg][k] <->
+// depth[k][8 cg + j] (chunk-major: consecutive rows = consecutive bytes for the row-per-lane writers and readers)
+template <int COLS>
+__device__ __forceinline__ uint64_t contact_bits(const uint8_t* maskb, int row, int seg) {
+  static_assert(COLS == 56, "seven mask bytes per thread");
+  uint64_t b = 0ull;
+#pragma unroll
+  for (int c = 0; c < 7; ++c) {
+    const int cg = seg * 7 + c;
+    if (cg < 13) b |= (uint64_t)maskb[cg * 104 + row] << (8 * c);
   }
+  return b;
 }
-__device__ __forceinline__ bool bit56(uint32_t blo, uint32_t bhi, int j) { return ((j < 32 ? blo >> j : bhi >> (j - 32)) & 1u) != 0u; }
+__device__ __forceinline__ bool bitof(uint64_t bits, int j) { return ((bits >> j) & 1ull) != 0ull; }
 
-template <int PASSES>
+// AUX: also leave the backward hand-over in `aux` (a compile-time switch: as a run-time one its 5 instructions per pixel
+// were issued predicated-off in every inference launch)
+template <int PASSES, bool AUX, int NT>
 __global__ void __launch_bounds__(NT, 2)
 psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth, float* __restrict__ HR,
                   float* __restrict__ LRd, float* __restrict__ psf, float* __restrict__ aux, int B) {
-  using L = Lay<PASSES>;
+  using L = Lay<PASSES, NT>;
+  constexpr int NW = L::NW, SEGS = L::SEGS, COLS = L::COLS, NV_LAST = L::NV_LAST, IPT = ipt<NT>();
   extern __shared__ __align__(1024) uint8_t sm[];
   const uint32_t base = smem_u32(sm);
   float* tab = reinterpret_cast<float*>(sm + L::OFF_TAB);
   uint32_t* tab2 = reinterpret_cast<uint32_t*>(sm + L::OFF_TAB2);
   float4* ex4 = reinterpret_cast<float4*>(sm + L::OFF_EX);
   uint8_t* maskb = sm + L::OFF_MASK;
-  float* red = reinterpret_cast<float*>(sm + L::OFF_RED);           // [0,16) depth max / |max|, [16,24) second max, [24,..) sums
+  float* red = reinterpret_cast<float*>(sm + L::OFF_RED);           // [0, 2 NW) block-max partials, then [NW][20] sums
+  float* reds = red + 2 * NW;
   const uint32_t bar1 = base + L::OFF_BAR, bar2 = bar1 + 8u, bar_raw = bar1 + 16u, tmem_slot = bar1 + 24u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + L::OFF_BAR + 24);
   uint8_t* const d_hi = sm + L::OFF_D; uint8_t* const d_lo = sm + L::OFF_D + TILE;
@@ -472,8 +528,8 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
   const uint32_t idesc1 = make_idesc(128, 112, 0, 1, 0, 0);   // fp16 x fp16 -> fp32; A K-major, B MN-major
   const uint32_t idesc2 = make_idesc(128, 112, 0, 0, 0, 0);   // A from tensor memory, B K-major
 
-  // epilogue geometry: TMEM lane quarter q = warp % 4, row m = 32 q + lane; column half = warp / 4 (56 columns each)
-  const int q = warp & 3, half = warp >> 2;
+  // epilogue geometry: TMEM lane quarter q = warp % 4, row m = 32 q + lane; column segment seg = warp / 4 (COLS columns)
+  const int q = warp & 3, seg = warp >> 2;
   const int m = q * 32 + lane;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
   const uint32_t acc = tmem_base + lane_addr;                  // accumulator of both products: columns [0,112)
@@ -494,24 +550,24 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
     // ---- phase A1: plane -> registers, depth max / |max|, tables ----
     float dreg[IPT][8];
     mbar_wait(bar_raw, ph);
-    load_plane<true>(raw, tid, dreg);
+    load_plane<true, NT>(raw, tid, dreg);
     float dmax, amax;
-    plane_max(dreg, tid, dmax, amax);
-    build_tables(beta, gamma, tab, ex4, tid);
+    plane_max<NT, true>(dreg, tid, dmax, amax);
+    build_tables<NT>(beta, gamma, tab, ex4, tid);
     // the previous sample's HR plane has left shared memory before the tiles under it are rebuilt (the barrier inside
     // block_max2 orders this wait against every other thread)
     if (tid == 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    block_max2(dmax, amax, red);                       // (syncs: tab / ex4 visible, every thread holds its part of the plane)
+    block_max2<NT>(dmax, amax, red);                   // (syncs: tab / ex4 visible, every thread holds its part of the plane)
     if (PASSES == 1 && tid == 0 && has_next) load_raw(b + gridDim.x);      // own buffer: a whole sample ahead
     const float thr = dmax - 1e-3f;
     int dexp = 0;
     if (amax > 0.f) (void)frexpf(amax, &dexp);         // amax = f * 2^dexp, f in [0.5, 1)
     const float sD = ldexpf(1.0f, 4 - dexp);           // |depth| sD < 16
-    build_tab2<0>(tab, tab2, tid);
+    build_tab2<0, NT>(tab, tab2, tid);
     // ---- phase A2: depth tiles (MN-major: row = k, as in HBM) + contact bytes; then the E tiles (K-major) ----
-    store_plane_tiles<PASSES>(dreg, sD, thr, d_hi, d_lo, maskb, tid);
+    store_plane_tiles<PASSES, NT, true>(dreg, sD, thr, d_hi, d_lo, maskb, tid);
     __syncthreads();
-    build_toeplitz_tiles<PASSES>(tab2, e_hi, e_lo, tid);
+    build_toeplitz_tiles<PASSES, NT>(tab2, e_hi, e_lo, tid);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -525,7 +581,7 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       }
       __syncwarp();
     }
-    // psf = alpha e(u) e(v)  (tPSFNet.py:83): warp w owns rows u = u0 + w, u0 + w + 8, ...; rows 0..49 are written while
+    // psf = alpha e(u) e(v)  (tPSFNet.py:83): warp w owns rows u = u0 + w, u0 + w + NW, ...; rows 0..49 are written while
     // GEMM1 runs, rows 50..98 while GEMM2 runs
     auto write_psf = [&](int u0, int u1) {
       if (!psf) return;
@@ -536,12 +592,12 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
         const int v = lane + 32 * c;
         ev[c] = v < 99 ? tab[v < 49 ? 49 - v : v - 49] : 0.f;
       }
-      for (int u = u0 + warp; u < u1; u += NT / 32) {
-        const float eu = tab[u < 49 ? 49 - u : u - 49];
+      for (int u = u0 + warp; u < u1; u += NW) {
+        const float aeu = alpha * tab[u < 49 ? 49 - u : u - 49];
         float* row = pdst + u * 99;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) row[lane + 32 * c] = alpha * (eu * ev[c]);
-        if (lane < 3) row[lane + 96] = alpha * (eu * ev[3]);
+        for (int c = 0; c < 3; ++c) row[lane + 32 * c] = aeu * ev[c];
+        if (lane < 3) row[lane + 96] = aeu * ev[3];
       }
     };
     write_psf(0, 50);
@@ -551,7 +607,7 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
 
     // ---- phase X: T -> fp16 hi [/ lo] -> tensor memory (the A operand of GEMM2) ----
     // accumulator = 16 sD T = 2^(8 - dexp) T,  |T| <= 99 |depth|max  =>  < 2^15: no rescaling needed
-    acc_to_tmem<PASSES>(acc, t_hi + lane_addr, t_lo + lane_addr, half);
+    acc_to_tmem<PASSES, COLS>(acc, t_hi + lane_addr, t_lo + lane_addr, seg);
     tc_fence_before();
     __syncthreads();
 
@@ -565,74 +621,71 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       __syncwarp();
     }
     write_psf(50, 99);
-    // (Ex_j(t) (t - 12 - 25 j)^2) and the half-row hand-over of the backward statistics (only needed when the backward
-    // hand-over `aux` is requested) live in memory that is dead by now
+    // (Ex_j(t) (t - 12 - 25 j)^2) and the row-segment hand-over of the backward statistics (AUX only) live in memory that
+    // is dead by now
     float4* ex24 = reinterpret_cast<float4*>(sm + L::OFF_X24);
-    float* xch = reinterpret_cast<float*>(sm + L::OFF_XCH);
-    if (aux) {
+    if (AUX) {
       for (int i = tid; i < 4 * N; i += NT) {
         const int t = i >> 2, k = i & 3;
         const float d = (float)(t - 12 - 25 * k);
         reinterpret_cast<float*>(ex24)[i] = reinterpret_cast<const float*>(ex4)[i] * (d * d);
       }
     }
-    uint32_t blo, bhi;
-    contact_bits(maskb, m < N ? m : 0, half, blo, bhi);
+    const uint64_t bits = contact_bits<COLS>(maskb, m < N ? m : 0, seg);
     mbar_wait(bar2, ph);
     tc_fence_after();
 
-    // ---- phase E: epilogue.  accumulator = 2^(8 - dexp) 16 (E D E); this thread: row m, columns c0 .. c0 + 55 ----
+    // ---- phase E: epilogue.  accumulator = 2^(8 - dexp) 16 (E D E); this thread: row m, columns c0 .. c0 + COLS - 1 ----
     const float cs = alpha * ldexpf(1.0f, dexp - 12);
-    const int c0 = half * 56;
-    float h[56];
+    const int c0 = seg * COLS;
+    const bool last = seg == SEGS - 1;                  // the last segment has NV_LAST valid columns, the rest is padding
+    float h[COLS];
     {
-      uint32_t v[56];
-      tmem_ld32(acc + (uint32_t)c0, v);
-      tmem_ld16(acc + (uint32_t)c0 + 32u, v + 32);
-      tmem_ld8(acc + (uint32_t)c0 + 48u, v + 48);
+      uint32_t v[COLS];
+      tmem_ld_cols<COLS>(acc + (uint32_t)c0, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 56; ++j) h[j] = __uint_as_float(v[j]) * cs;
+      for (int j = 0; j < COLS; ++j) h[j] = __uint_as_float(v[j]) * cs;
     }
     tc_fence_before();                                  // (all TMEM reads of this sample are complete)
     // second max = max over the conv result with the contact pixels zeroed (tPSFNet.py:95-97)
-    const bool any_contact = (blo | bhi) != 0u;
+    const bool any_contact = bits != 0ull;
     float m2 = 0.f, unused = 0.f;
     if (m < N) {
       if (!any_contact) {
 #pragma unroll
-        for (int j = 0; j < 44; ++j) m2 = fmaxf(m2, h[j]);
-        if (half == 0) {
+        for (int j = 0; j < NV_LAST; ++j) m2 = fmaxf(m2, h[j]);
+        if (!last) {
 #pragma unroll
-          for (int j = 44; j < 56; ++j) m2 = fmaxf(m2, h[j]);
+          for (int j = NV_LAST; j < COLS; ++j) m2 = fmaxf(m2, h[j]);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 44; ++j)
-          if (!bit56(blo, bhi, j)) m2 = fmaxf(m2, h[j]);
-        if (half == 0) {
+        for (int j = 0; j < NV_LAST; ++j)
+          if (!bitof(bits, j)) m2 = fmaxf(m2, h[j]);
+        if (!last) {
 #pragma unroll
-          for (int j = 44; j < 56; ++j)
-            if (!bit56(blo, bhi, j)) m2 = fmaxf(m2, h[j]);
+          for (int j = NV_LAST; j < COLS; ++j)
+            if (!bitof(bits, j)) m2 = fmaxf(m2, h[j]);
         }
       }
     }
-    block_max2(m2, unused, red);               // (the tile barriers since the depth-max call protect the scratch)
+    block_max2<NT>(m2, unused, red);                    // (the tile barriers since the depth-max call protect the scratch)
     // fill, stage HR, accumulate the degradation sums of this thread's row segment
     float rj[4] = {0.f, 0.f, 0.f, 0.f}, r2[4] = {0.f, 0.f, 0.f, 0.f}, rs = 0.f;
     float* hstage = reinterpret_cast<float*>(sm + L::OFF_STAGE);
     if (m < N) {
       if (any_contact) {
 #pragma unroll
-        for (int j = 0; j < 56; ++j)
-          if (bit56(blo, bhi, j)) h[j] = m2;
+        for (int j = 0; j < COLS; ++j)
+          if (bitof(bits, j)) h[j] = m2;
       }
       auto accumulate = [&](int j) {
         const float4 e4 = ex4[c0 + j];
         rs += h[j];
         rj[0] = fmaf(h[j], e4.x, rj[0]); rj[1] = fmaf(h[j], e4.y, rj[1]);
         rj[2] = fmaf(h[j], e4.z, rj[2]); rj[3] = fmaf(h[j], e4.w, rj[3]);
-        if (aux) {
+        if (AUX) {
           const float4 f4 = ex24[c0 + j];
           r2[0] = fmaf(h[j], f4.x, r2[0]); r2[1] = fmaf(h[j], f4.y, r2[1]);
           r2[2] = fmaf(h[j], f4.z, r2[2]); r2[3] = fmaf(h[j], f4.w, r2[3]);
@@ -640,14 +693,14 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       };
       float4* hdst = reinterpret_cast<float4*>(hstage + m * N + c0);
 #pragma unroll
-      for (int j = 0; j < 44; ++j) accumulate(j);
+      for (int j = 0; j < NV_LAST; ++j) accumulate(j);
 #pragma unroll
-      for (int j4 = 0; j4 < 11; ++j4) hdst[j4] = make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
-      if (half == 0) {
+      for (int j4 = 0; j4 < NV_LAST / 4; ++j4) hdst[j4] = make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
+      if (!last) {
 #pragma unroll
-        for (int j = 44; j < 56; ++j) accumulate(j);
+        for (int j = NV_LAST; j < COLS; ++j) accumulate(j);
 #pragma unroll
-        for (int j4 = 11; j4 < 14; ++j4) hdst[j4] = make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
+        for (int j4 = NV_LAST / 4; j4 < COLS / 4; ++j4) hdst[j4] = make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
       }
     }
     // LRd[i][j] = 1e-4 (sum_m Ex_i(m) R_j(m) - mm sum HR) / (1 - mm),  R_j(m) = sum_n HR[m][n] Ex_j(n)
@@ -674,13 +727,12 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       p[0] += __shfl_xor_sync(0xffffffffu, p[0], 1);
       const float tot_w = warp_sum(m < N ? rs : 0.f);
       fence_proxy_async();                              // the staged HR rows -> visible to the bulk-copy engine
-      if (aux && half == 1 && m < N) {                  // upper column half -> lower-half thread of the same row
-        float4* x4 = reinterpret_cast<float4*>(xch + m * AUX_ROW);
-        x4[0] = make_float4(rj[0], rj[1], rj[2], rj[3]);
-        x4[1] = make_float4(r2[0], r2[1], r2[2], r2[3]);
-        x4[2] = make_float4(rs, 0.f, 0.f, 0.f);
+      if (AUX && seg > 0 && m < N) {                    // upper column segments -> the segment-0 thread of the same row
+        uint8_t* xs = sm + L::OFF_XCH + (uint32_t)(seg - 1) * L::XCH_SEG;
+        reinterpret_cast<float4*>(xs)[m] = make_float4(rj[0], rj[1], rj[2], rj[3]);
+        reinterpret_cast<float4*>(xs + 1600)[m] = make_float4(r2[0], r2[1], r2[2], r2[3]);
+        reinterpret_cast<float*>(xs + 3200)[m] = rs;
       }
-      float* reds = red + 24;
       if ((lane & 1) == 0) reds[warp * 20 + (lane >> 1)] = p[0];
       if (lane == 0) reds[warp * 20 + 16] = tot_w;
       __syncthreads();
@@ -693,19 +745,26 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       if (tid < 16) {
         float s = 0.f, tot = 0.f;
 #pragma unroll
-        for (int w = 0; w < NT / 32; ++w) { s += reds[w * 20 + tid]; tot += reds[w * 20 + 16]; }
+        for (int w = 0; w < NW; ++w) { s += reds[w * 20 + tid]; tot += reds[w * 20 + 16]; }
         const float mm = expf(-100.0f / gamma);
         LRd[b * 16 + tid] = 1e-4f * (s - mm * tot) / (1.0f - mm);
       }
-      if (aux && half == 0 && m < N) {
-        const float4* x4 = reinterpret_cast<const float4*>(xch + m * AUX_ROW);
-        const float4 a0 = x4[0], a1 = x4[1], a2 = x4[2];
+      if (AUX && seg == 0 && m < N) {
+        float a[9] = {rj[0], rj[1], rj[2], rj[3], r2[0], r2[1], r2[2], r2[3], rs};
+#pragma unroll
+        for (int sg = 0; sg < SEGS - 1; ++sg) {         // fixed order: deterministic
+          const uint8_t* xs = sm + L::OFF_XCH + (uint32_t)sg * L::XCH_SEG;
+          const float4 a0 = reinterpret_cast<const float4*>(xs)[m], a1 = reinterpret_cast<const float4*>(xs + 1600)[m];
+          a[0] += a0.x; a[1] += a0.y; a[2] += a0.z; a[3] += a0.w;
+          a[4] += a1.x; a[5] += a1.y; a[6] += a1.z; a[7] += a1.w;
+          a[8] += reinterpret_cast<const float*>(xs + 3200)[m];
+        }
         float4* dst = reinterpret_cast<float4*>(aux + (size_t)b * AUX_STRIDE + m * AUX_ROW);
-        dst[0] = make_float4(rj[0] + a0.x, rj[1] + a0.y, rj[2] + a0.z, rj[3] + a0.w);
-        dst[1] = make_float4(r2[0] + a1.x, r2[1] + a1.y, r2[2] + a1.z, r2[3] + a1.w);
-        dst[2] = make_float4(rs + a2.x, 0.f, 0.f, 0.f);
+        dst[0] = make_float4(a[0], a[1], a[2], a[3]);
+        dst[1] = make_float4(a[4], a[5], a[6], a[7]);
+        dst[2] = make_float4(a[8], 0.f, 0.f, 0.f);
       }
-      if (aux && tid == 0) aux[(size_t)b * AUX_STRIDE + 100 * AUX_ROW] = m2;
+      if (AUX && tid == 0) aux[(size_t)b * AUX_STRIDE + 100 * AUX_ROW] = m2;
     }
     // the next sample's barriers (block_max2 and the two tile barriers) order everything above before its first MMA
   }
@@ -732,11 +791,12 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
 //   T = E D -> acc0;  T2 = E2 D -> acc1;  acc0' = T E2  (+)=  T2 E      (the two products share one accumulator: the
 //   operand scales are chosen so that both carry 2^(12 - dexp))
 // ------------------------------------------------------------------------------------------------------------------
-template <int PASSES>
+template <int PASSES, int NT>
 __global__ void __launch_bounds__(NT, 2)
 psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth, const float* __restrict__ aux,
                   const float* __restrict__ dLRd, float* __restrict__ dab, int B) {
-  using L = Lay<PASSES>;
+  using L = Lay<PASSES, NT>;
+  constexpr int NW = L::NW, SEGS = L::SEGS, COLS = L::COLS, IPT = ipt<NT>();
   extern __shared__ __align__(1024) uint8_t sm[];
   const uint32_t base = smem_u32(sm);
   float* tab = reinterpret_cast<float*>(sm + L::OFF_TAB);
@@ -744,6 +804,7 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
   float4* ex4 = reinterpret_cast<float4*>(sm + L::OFF_EX);
   uint8_t* maskb = sm + L::OFF_MASK;
   float* red = reinterpret_cast<float*>(sm + L::OFF_RED);
+  float* reds = red + 2 * NW;
   const uint32_t bar1 = base + L::OFF_BAR, tmem_slot = bar1 + 24u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + L::OFF_BAR + 24);
 
@@ -769,7 +830,7 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
   const uint32_t idesc1 = make_idesc(128, 112, 0, 1, 0, 0);   // A K-major, B MN-major (depth as it lies in HBM)
   const uint32_t idesc2 = make_idesc(128, 112, 0, 0, 0, 0);   // both K-major
 
-  const int q = warp & 3, half = warp >> 2;
+  const int q = warp & 3, seg = warp >> 2;
   const int m = q * 32 + lane;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
   const uint32_t acc0 = tmem_base + lane_addr, acc1 = tmem_base + 128u + lane_addr;
@@ -778,11 +839,17 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
   const uint32_t a_x_hi = base + L::OFF_D, a_x_lo = a_x_hi + TILE, a_e_hi = base + L::OFF_E, a_e_lo = a_e_hi + TILE;
 
   float dreg[IPT][8];
-  if ((int)blockIdx.x < B) load_plane<false>(depth + (size_t)blockIdx.x * N * N, tid, dreg);
+  if ((int)blockIdx.x < B) load_plane<false, NT>(depth + (size_t)blockIdx.x * N * N, tid, dreg);
   uint32_t nph = 0;                       // completed phases of bar1 (4 per sample)
+  // ONE warp polls the MMA-completion mbarrier, the others wait at the block barrier behind it: 256 polling threads
+  // cost 9 % of the kernel's issue slots, which the co-resident CTA needs
   auto wait_mma = [&]() {
-    mbar_wait(bar1, nph & 1u);
+    if (warp == 1) {
+      mbar_wait(bar1, nph & 1u);
+      tc_fence_before();
+    }
     ++nph;
+    __syncthreads();
     tc_fence_after();
   };
   auto publish = [&]() {                  // generic-proxy smem writes -> visible to the MMA; all TMEM reads retired
@@ -793,23 +860,20 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
 
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const float alpha = ab[b * 3 + 0], beta = ab[b * 3 + 1], gamma = ab[b * 3 + 2];
-    float g[16], gsum = 0.f;
-#pragma unroll
-    for (int t = 0; t < 16; ++t) { g[t] = dLRd[b * 16 + t]; gsum += g[t]; }
 
     // ---- tables, depth max, E and depth tiles ----
     float dmax, amax;
-    plane_max(dreg, tid, dmax, amax);
-    build_tables(beta, gamma, tab, ex4, tid);
-    block_max2(dmax, amax, red);
+    plane_max<NT, false>(dreg, tid, dmax, amax);
+    build_tables<NT>(beta, gamma, tab, ex4, tid);
+    block_max2<NT>(dmax, amax, red);
     const float thr = dmax - 1e-3f;
     int dexp = 0;
     if (amax > 0.f) (void)frexpf(amax, &dexp);
     const float sD = ldexpf(1.0f, 4 - dexp);
-    build_tab2<0>(tab, tab2, tid);
-    store_plane_tiles<PASSES>(dreg, sD, thr, x_hi, x_lo, maskb, tid);
+    build_tab2<0, NT>(tab, tab2, tid);
+    store_plane_tiles<PASSES, NT, false>(dreg, sD, thr, x_hi, x_lo, maskb, tid);
     __syncthreads();
-    build_toeplitz_tiles<PASSES>(tab2, e_hi, e_lo, tid);
+    build_toeplitz_tiles<PASSES, NT>(tab2, e_hi, e_lo, tid);
     publish();
 
     // ---- GEMM 1: T = E D -> acc0  (2^(8 - dexp) T) ----
@@ -821,11 +885,10 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       }
       __syncwarp();
     }
-    if (b + (int)gridDim.x < B) load_plane<false>(depth + (size_t)(b + gridDim.x) * N * N, tid, dreg);
-    build_tab2<1>(tab, tab2, tid);        // (all reads of the E table finished before publish())
-    __syncthreads();
-    wait_mma();
-    build_toeplitz_tiles<PASSES>(tab2, e_hi, e_lo, tid);      // E2 over E
+    if (b + (int)gridDim.x < B) load_plane<false, NT>(depth + (size_t)(b + gridDim.x) * N * N, tid, dreg);
+    build_tab2<1, NT>(tab, tab2, tid);    // (all reads of the E table finished before publish())
+    wait_mma();                           // (its barrier also publishes the table)
+    build_toeplitz_tiles<PASSES, NT>(tab2, e_hi, e_lo, tid);      // E2 over E
     publish();
 
     // ---- GEMM 2: T2 = E2 D -> acc1  (2^(8 - dexp) T2) ----
@@ -837,9 +900,9 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       }
       __syncwarp();
     }
-    build_tab2<2>(tab, tab2, tid);        // 2^15 e(t) for the last product
+    build_tab2<2, NT>(tab, tab2, tid);    // 2^15 e(t) for the last product
     wait_mma();
-    acc_to_tiles<PASSES>(acc0, 1.0f, x_hi, x_lo, m, half);    // T over the depth tiles
+    acc_to_tiles<PASSES, COLS>(acc0, 1.0f, x_hi, x_lo, m, seg);   // T over the depth tiles
     publish();
 
     // ---- GEMM 3: acc0 = T E2  (2^(12 - dexp)) ----
@@ -852,8 +915,8 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       __syncwarp();
     }
     wait_mma();
-    acc_to_tiles<PASSES>(acc1, 1.0f / 2048.0f, x_hi, x_lo, m, half);    // 2^(-3 - dexp) T2 over T;  |T2| < 2^(18 + dexp)
-    build_toeplitz_tiles<PASSES>(tab2, e_hi, e_lo, tid);                // 2^15 E over E2
+    acc_to_tiles<PASSES, COLS>(acc1, 1.0f / 2048.0f, x_hi, x_lo, m, seg);   // 2^(-3 - dexp) T2 over T;  |T2| < 2^(18 + dexp)
+    build_toeplitz_tiles<PASSES, NT>(tab2, e_hi, e_lo, tid);                // 2^15 E over E2
     publish();
 
     // ---- GEMM 4: acc0 += T2 E ----
@@ -866,6 +929,9 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       __syncwarp();
     }
     // per-row factors while the MMAs run
+    float g[16], gsum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) { g[t] = dLRd[b * 16 + t]; gsum += g[t]; }
     const float mm = expf(-100.0f / gamma);
     const float mg = mm * gsum;
     const float4 em = m < N ? ex4[m] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -874,7 +940,7 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
 #pragma unroll
     for (int j = 0; j < 4; ++j) qt[j] = ei[0] * g[j] + ei[1] * g[4 + j] + ei[2] * g[8 + j] + ei[3] * g[12 + j];
     float G0 = 0.f, G1 = 0.f, tot = 0.f;
-    if (half == 0 && m < N) {             // d gamma / d alpha statistics from the forward's per-row sums
+    if (seg == 0 && m < N) {              // d gamma / d alpha statistics from the forward's per-row sums
       const float4* a4 = reinterpret_cast<const float4*>(aux + (size_t)b * AUX_STRIDE + m * AUX_ROW);
       const float4 u = a4[0], u2 = a4[1];
       tot = a4[2].x;
@@ -889,41 +955,36 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
         G1 = fmaf(ei[i] * (d * d), ai, fmaf(ei[i], bi, G1));
       }
     }
-    uint32_t blo, bhi;
-    contact_bits(maskb, m < N ? m : 0, half, blo, bhi);
+    const uint64_t bits = contact_bits<COLS>(maskb, m < N ? m : 0, seg);
     wait_mma();
 
-    // ---- epilogue over acc0 = 2^(12 - dexp) P3: this thread's 56 columns in two register batches ----
+    // ---- epilogue over acc0 = 2^(12 - dexp) P3: this thread's COLS columns, 28 at a time ----
     float dbs = 0.f, cw = 0.f;
-    const int c0 = half * 56;
+    const int c0 = seg * COLS;
 #pragma unroll
-    for (int part = 0; part < 2; ++part) {
+    for (int part = 0; part < COLS / 28; ++part) {
       uint32_t v[28];
-      const uint32_t ca = acc0 + (uint32_t)(c0 + part * 28);
-      tmem_ld16(ca, v);
-      tmem_ld8(ca + 16u, v + 16);
-      tmem_ld4(ca + 24u, v + 24);
+      tmem_ld_cols<28>(acc0 + (uint32_t)(c0 + part * 28), v);
       tmem_ld_wait();
       if (m < N) {
 #pragma unroll
         for (int jj = 0; jj < 28; ++jj) {
           const int j = part * 28 + jj;
-          if (j < 44 || half == 0) {
+          if (j < L::NV_LAST || seg < SEGS - 1) {
             const float4 e4 = ex4[c0 + j];
             const float wc = fmaf(e4.x, qt[0], fmaf(e4.y, qt[1], fmaf(e4.z, qt[2], e4.w * qt[3])));
-            const bool contact = bit56(blo, bhi, j);
+            const bool contact = bitof(bits, j);
             dbs = fmaf(contact ? 0.f : wc - mg, __uint_as_float(v[jj]), dbs);
             cw += contact ? wc : 0.f;
           }
         }
       }
     }
-    const float cnt = m < N ? (float)(__popc(blo) + __popc(bhi)) : 0.f;
+    const float cnt = m < N ? (float)__popcll(bits) : 0.f;
     {
       float p[6] = {dbs, cw, cnt, G0, G1, tot};
 #pragma unroll
       for (int k = 0; k < 6; ++k) p[k] = warp_sum(p[k]);
-      float* reds = red + 24;
       if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) reds[warp * 20 + k] = p[k];
@@ -932,7 +993,7 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       __syncthreads();
       if (tid == 0) {
         float r[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int w = 0; w < NT / 32; ++w)
+        for (int w = 0; w < NW; ++w)
 #pragma unroll
           for (int k = 0; k < 6; ++k) r[k] += reds[w * 20 + k];
         const float om = 1.0f - mm, kk = 1e-4f / om;
@@ -966,15 +1027,33 @@ static int psf_tc_grid(int B) {
   return B < 2 * sms ? B : 2 * sms;
 }
 
+template <int PASSES, bool AUX, int NT>
+static int psf_forward_tc_launch(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, float* aux, int B,
+                                 cudaStream_t stream) {
+  const size_t smem = Lay<PASSES, NT>::BYTES;
+  TSR_CUDA(cudaFuncSetAttribute(psf_fwd_tc_kernel<PASSES, AUX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  psf_fwd_tc_kernel<PASSES, AUX, NT><<<psf_tc_grid(B), NT, smem, stream>>>(alphaBeta, depth, HR, LRd, psf, aux, B);
+  TSR_CHECK_LAUNCH("psf_forward_tc");
+  return TSR_OK;
+}
+
 template <int PASSES>
 static int psf_forward_tc_impl(const float* alphaBeta, const float* depth, float* HR, float* LRd, float* psf, float* aux, int B,
                                cudaStream_t stream) {
   TSR_REQUIRE(alphaBeta && depth && HR && LRd && B > 0, "psf_forward_tc: bad argument");
   TSR_REQUIRE(((uintptr_t)depth & 15) == 0 && ((uintptr_t)HR & 15) == 0 && ((uintptr_t)aux & 15) == 0,
               "psf_forward_tc: depth / HR / aux must be 16-byte aligned");
-  TSR_CUDA(cudaFuncSetAttribute(psf_fwd_tc_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<PASSES>::BYTES));
-  psf_fwd_tc_kernel<PASSES><<<psf_tc_grid(B), NT, Lay<PASSES>::BYTES, stream>>>(alphaBeta, depth, HR, LRd, psf, aux, B);
-  TSR_CHECK_LAUNCH("psf_forward_tc");
+  return aux ? psf_forward_tc_launch<PASSES, true, PSF_THREADS>(alphaBeta, depth, HR, LRd, psf, aux, B, stream)
+             : psf_forward_tc_launch<PASSES, false, PSF_THREADS>(alphaBeta, depth, HR, LRd, psf, aux, B, stream);
+}
+
+template <int PASSES, int NT>
+static int psf_backward_tc_launch(const float* alphaBeta, const float* depth, const float* aux, const float* dLRd,
+                                  float* dalphaBeta, int B, cudaStream_t stream) {
+  const size_t smem = Lay<PASSES, NT>::BYTES;
+  TSR_CUDA(cudaFuncSetAttribute(psf_bwd_tc_kernel<PASSES, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  psf_bwd_tc_kernel<PASSES, NT><<<psf_tc_grid(B), NT, smem, stream>>>(alphaBeta, depth, aux, dLRd, dalphaBeta, B);
+  TSR_CHECK_LAUNCH("psf_backward_tc");
   return TSR_OK;
 }
 
@@ -983,10 +1062,7 @@ static int psf_backward_tc_impl(const float* alphaBeta, const float* depth, cons
                                 float* dalphaBeta, int B, cudaStream_t stream) {
   TSR_REQUIRE(alphaBeta && depth && aux && dLRd && dalphaBeta && B > 0, "psf_backward_tc: bad argument");
   TSR_REQUIRE(((uintptr_t)depth & 15) == 0 && ((uintptr_t)aux & 15) == 0, "psf_backward_tc: depth / aux must be 16-byte aligned");
-  TSR_CUDA(cudaFuncSetAttribute(psf_bwd_tc_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<PASSES>::BYTES));
-  psf_bwd_tc_kernel<PASSES><<<psf_tc_grid(B), NT, Lay<PASSES>::BYTES, stream>>>(alphaBeta, depth, aux, dLRd, dalphaBeta, B);
-  TSR_CHECK_LAUNCH("psf_backward_tc");
-  return TSR_OK;
+  return psf_backward_tc_launch<PASSES, PSF_THREADS>(alphaBeta, depth, aux, dLRd, dalphaBeta, B, stream);
 }
 
 extern "C" {
