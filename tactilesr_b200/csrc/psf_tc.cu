@@ -277,8 +277,8 @@ __device__ __forceinline__ void load_plane(const float* __restrict__ dsrc, int t
 }
 
 // 4 shifted copies of the packed (hi | lo << 16) fp16 table of the banded Toeplitz generator, so that any 8 consecutive
-// entries are two aligned 16-byte loads.  kind 0: 16 e(t);  1: 16 e(t) t^2;  2: 32768 e(t)   (t = |j - 99| <= 49, else 0:
-// the PSF has 99 taps)
+// entries are two aligned 16-byte loads.  kind 0: 16 e(t);  1: 16 e(t) t^2;  2 / 3: 32768 e(t)   (t = |j - 99| <= 49, else 0:
+// the PSF has 99 taps); kind 3 carries 16 e(t) t^2 as a single fp16 in the lo half instead of the residual
 template <int KIND, int NT>
 __device__ __forceinline__ void build_tab2(const float* tab, uint32_t* tab2, int tid) {
   for (int i = tid; i < 4 * (int)TAB2_LEN; i += NT) {
@@ -288,6 +288,11 @@ __device__ __forceinline__ void build_tab2(const float* tab, uint32_t* tab2, int
     float x = 0.f;
     if (t <= 49) x = KIND == 0 ? tab[t] * 16.0f : (KIND == 1 ? tab[t] * (float)(16 * t * t) : tab[t] * 32768.0f);
     uint32_t hi, lo;
+    if (KIND == 3) {          // two single-fp16 generators in one entry: 32768 e(t) | 16 e(t) t^2 << 16
+      const float y = t <= 49 ? tab[t] * (float)(16 * t * t) : 0.f;
+      tab2[i] = h2_bits(__floats2half2_rn(x, y));
+      continue;
+    }
     split_h2(x, 0.f, hi, lo);
     tab2[i] = (hi & 0xFFFFu) | (lo << 16);
   }
@@ -382,32 +387,37 @@ __device__ __forceinline__ void tmem_st_pairs(uint32_t taddr, const uint32_t* r)
   }
 }
 
-// accumulator (TMEM, this thread's COLS columns from column seg * COLS of `acc`) * scale -> K-major hi [/ lo] smem tiles;
-// thread = (row m, column segment)
+// accumulator (TMEM, this thread's 56 columns from column seg * 56 of `acc`) * scale -> K-major hi [/ lo] smem tiles (whole
+// 16-byte chunks: 4 + 3 chunks in two register batches); thread = (row m, column segment)
 template <int PASSES, int COLS>
 __device__ __forceinline__ void acc_to_tiles(uint32_t acc, float scale, uint8_t* x_hi, uint8_t* x_lo, int m, int seg) {
+  static_assert(COLS == 56, "seven chunks per thread");
 #pragma unroll
-  for (int part = 0; part < COLS / 28; ++part) {             // 28 columns at a time: 32 registers in flight
-    uint32_t v[28];
-    const int cbase = seg * COLS + part * 28;
-    tmem_ld_cols<28>(acc + (uint32_t)cbase, v);
+  for (int part = 0; part < 2; ++part) {
+    uint32_t v[32];
+    const int cbase = seg * COLS + part * 32;
+    if (part == 0) {
+      tmem_ld32(acc + (uint32_t)cbase, v);
+    } else {
+      tmem_ld16(acc + (uint32_t)cbase, v);
+      tmem_ld8(acc + (uint32_t)cbase + 16u, v + 16);
+    }
     tmem_ld_wait();
     if (m < (int)ROWS) {
 #pragma unroll
-      for (int g = 0; g < 7; ++g) {                          // 4 columns = half a 16-byte chunk
-        const int col0 = cbase + g * 4;
-        const int cg = col0 >> 3, hsel = (col0 >> 2) & 1;
-        uint32_t th[2], tl[2];
+      for (int g = 0; g < (part == 0 ? 4 : 3); ++g) {
+        const int col0 = cbase + g * 8;
+        uint32_t th[4], tl[4];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < 4; ++j) {
           // columns >= 100 are padding (depth-tile garbage): force 0
-          const float x0 = col0 + 2 * j < N ? __uint_as_float(v[g * 4 + 2 * j]) * scale : 0.f;
-          const float x1 = col0 + 2 * j + 1 < N ? __uint_as_float(v[g * 4 + 2 * j + 1]) * scale : 0.f;
+          const float x0 = col0 + 2 * j < N ? __uint_as_float(v[g * 8 + 2 * j]) * scale : 0.f;
+          const float x1 = col0 + 2 * j + 1 < N ? __uint_as_float(v[g * 8 + 2 * j + 1]) * scale : 0.f;
           split_h2(x0, x1, th[j], tl[j]);
         }
-        const uint32_t off = chunk_off(m, cg) + (uint32_t)hsel * 8u;
-        *reinterpret_cast<uint2*>(x_hi + off) = make_uint2(th[0], th[1]);
-        if (PASSES == 3) *reinterpret_cast<uint2*>(x_lo + off) = make_uint2(tl[0], tl[1]);
+        const uint32_t off = chunk_off(m, col0 >> 3);
+        *reinterpret_cast<uint4*>(x_hi + off) = make_uint4(th[0], th[1], th[2], th[3]);
+        if (PASSES == 3) *reinterpret_cast<uint4*>(x_lo + off) = make_uint4(tl[0], tl[1], tl[2], tl[3]);
       }
     }
   }
@@ -1018,6 +1028,212 @@ psf_bwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// The same backward for the 16-bit precision modes: single fp16 operands halve every tile, so E and E2 AND T and T2 fit
+// in shared memory at once (the four tile slots of the split layout).  The products then run as two groups of two --
+// [T = E D | T2 = E2 D] and [P3 = T E2 + T2 E] -- with one completion wait each, E / E2 come out of ONE table pass, and a
+// sample takes 7 block barriers instead of 11.  Scales: E tile 2^15 e, E2 tile 16 e t^2, both accumulators are converted
+// with 2^-11, so both halves of P3 carry 2^(12 - dexp).
+// ------------------------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT, 2)
+psf_bwd_f16_kernel(const float* __restrict__ ab, const float* __restrict__ depth, const float* __restrict__ aux,
+                   const float* __restrict__ dLRd, float* __restrict__ dab, int B) {
+  using L = Lay<3, NT>;                    // slots: [D -> T | T2 | E | E2]
+  constexpr int NW = L::NW, SEGS = L::SEGS, COLS = L::COLS, IPT = ipt<NT>();
+  extern __shared__ __align__(1024) uint8_t sm[];
+  const uint32_t base = smem_u32(sm);
+  float* tab = reinterpret_cast<float*>(sm + L::OFF_TAB);
+  uint32_t* tab2 = reinterpret_cast<uint32_t*>(sm + L::OFF_TAB2);
+  float4* ex4 = reinterpret_cast<float4*>(sm + L::OFF_EX);
+  uint8_t* maskb = sm + L::OFF_MASK;
+  float* red = reinterpret_cast<float*>(sm + L::OFF_RED);
+  float* reds = red + 2 * NW;
+  const uint32_t bar1 = base + L::OFF_BAR, tmem_slot = bar1 + 24u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + L::OFF_BAR + 24);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((base & 1023u) != 0u) {
+    if (tid == 0) printf("tactilesr_b200 psf_tc: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  for (uint32_t i = tid; i < L::TILES_END / 16; i += NT) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (uint32_t i = tid; i < 104 * 16 / 4; i += NT) reinterpret_cast<uint32_t*>(maskb)[i] = 0u;
+  if (tid == 0) {
+    mbar_init(bar1, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t idesc1 = make_idesc(128, 112, 0, 1, 0, 0);   // A K-major, B MN-major (depth as it lies in HBM)
+  const uint32_t idesc2 = make_idesc(128, 112, 0, 0, 0, 0);   // both K-major
+
+  const int q = warp & 3, seg = warp >> 2;
+  const int m = q * 32 + lane;
+  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+  const uint32_t acc0 = tmem_base + lane_addr, acc1 = tmem_base + 128u + lane_addr;
+  uint8_t* const x1 = sm + L::OFF_D; uint8_t* const x2 = sm + L::OFF_D + TILE;
+  uint8_t* const e1 = sm + L::OFF_E; uint8_t* const e2 = sm + L::OFF_E + TILE;
+  const uint32_t a_x1 = base + L::OFF_D, a_x2 = a_x1 + TILE, a_e1 = base + L::OFF_E, a_e2 = a_e1 + TILE;
+
+  float dreg[IPT][8];
+  if ((int)blockIdx.x < B) load_plane<false, NT>(depth + (size_t)blockIdx.x * N * N, tid, dreg);
+  uint32_t nph = 0;                       // completed phases of bar1 (2 per sample)
+  auto wait_mma = [&]() {                 // one warp polls, the others wait at the block barrier behind it
+    if (warp == 1) {
+      mbar_wait(bar1, nph & 1u);
+      tc_fence_before();
+    }
+    ++nph;
+    __syncthreads();
+    tc_fence_after();
+  };
+  auto publish = [&]() {                  // generic-proxy smem writes -> visible to the MMA; all TMEM reads retired
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+  };
+
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const float alpha = ab[b * 3 + 0], beta = ab[b * 3 + 1], gamma = ab[b * 3 + 2];
+
+    // ---- tables, depth max, depth tile, E and E2 tiles ----
+    float dmax, amax;
+    plane_max<NT, false>(dreg, tid, dmax, amax);
+    build_tables<NT>(beta, gamma, tab, ex4, tid);
+    block_max2<NT>(dmax, amax, red);
+    const float thr = dmax - 1e-3f;
+    int dexp = 0;
+    if (amax > 0.f) (void)frexpf(amax, &dexp);
+    const float sD = ldexpf(1.0f, 4 - dexp);
+    build_tab2<3, NT>(tab, tab2, tid);
+    store_plane_tiles<1, NT, false>(dreg, sD, thr, x1, x1, maskb, tid);
+    __syncthreads();
+    build_toeplitz_tiles<3, NT>(tab2, e1, e2, tid);           // "hi" halves -> 2^15 E, "lo" halves -> 16 E2
+    publish();
+
+    // ---- T = E D -> acc0 (2^(19 - dexp) T),  T2 = E2 D -> acc1 (2^(8 - dexp) T2) ----
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        issue_gemm_kmn<1>(tmem_base, a_e1, a_e1, a_x1, a_x1, idesc1);
+        issue_gemm_kmn<1>(tmem_base + 128u, a_e2, a_e2, a_x1, a_x1, idesc1);
+        umma_commit(bar1);
+      }
+      __syncwarp();
+    }
+    if (b + (int)gridDim.x < B) load_plane<false, NT>(depth + (size_t)(b + gridDim.x) * N * N, tid, dreg);
+    wait_mma();
+    acc_to_tiles<1, COLS>(acc0, 1.0f / 2048.0f, x1, x1, m, seg);     // 2^(8 - dexp) T over the depth tile
+    acc_to_tiles<1, COLS>(acc1, 1.0f / 2048.0f, x2, x2, m, seg);     // 2^(-3 - dexp) T2;  |T2| < 2^(18 + dexp)
+    publish();
+
+    // ---- acc0 = T E2 + T2 E  (2^(12 - dexp) P3) ----
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        issue_gemm_kk<1>(tmem_base, a_x1, a_x1, a_e2, a_e2, idesc2);
+        issue_gemm_kk<1, 1>(tmem_base, a_x2, a_x2, a_e1, a_e1, idesc2);
+        umma_commit(bar1);
+      }
+      __syncwarp();
+    }
+    // per-row factors while the MMAs run
+    float g[16], gsum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) { g[t] = dLRd[b * 16 + t]; gsum += g[t]; }
+    const float mm = expf(-100.0f / gamma);
+    const float mg = mm * gsum;
+    const float4 em = m < N ? ex4[m] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float ei[4] = {em.x, em.y, em.z, em.w};
+    float qt[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) qt[j] = ei[0] * g[j] + ei[1] * g[4 + j] + ei[2] * g[8 + j] + ei[3] * g[12 + j];
+    float G0 = 0.f, G1 = 0.f, tot = 0.f;
+    if (seg == 0 && m < N) {              // d gamma / d alpha statistics from the forward's per-row sums
+      const float4* a4 = reinterpret_cast<const float4*>(aux + (size_t)b * AUX_STRIDE + m * AUX_ROW);
+      const float4 u = a4[0], u2 = a4[1];
+      tot = a4[2].x;
+      const float uu[4] = {u.x, u.y, u.z, u.w}, vv[4] = {u2.x, u2.y, u2.z, u2.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float ai = 0.f, bi = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { ai = fmaf(g[i * 4 + j], uu[j], ai); bi = fmaf(g[i * 4 + j], vv[j], bi); }
+        const float d = (float)(m - 12 - 25 * i);
+        G0 = fmaf(ei[i], ai, G0);
+        G1 = fmaf(ei[i] * (d * d), ai, fmaf(ei[i], bi, G1));
+      }
+    }
+    const uint64_t bits = contact_bits<COLS>(maskb, m < N ? m : 0, seg);
+    wait_mma();
+
+    // ---- epilogue over acc0 = 2^(12 - dexp) P3: this thread's COLS columns, 28 at a time ----
+    float dbs = 0.f, cw = 0.f;
+    const int c0 = seg * COLS;
+#pragma unroll
+    for (int part = 0; part < COLS / 28; ++part) {
+      uint32_t v[28];
+      tmem_ld_cols<28>(acc0 + (uint32_t)(c0 + part * 28), v);
+      tmem_ld_wait();
+      if (m < N) {
+#pragma unroll
+        for (int jj = 0; jj < 28; ++jj) {
+          const int j = part * 28 + jj;
+          if (j < L::NV_LAST || seg < SEGS - 1) {
+            const float4 e4 = ex4[c0 + j];
+            const float wc = fmaf(e4.x, qt[0], fmaf(e4.y, qt[1], fmaf(e4.z, qt[2], e4.w * qt[3])));
+            const bool contact = bitof(bits, j);
+            dbs = fmaf(contact ? 0.f : wc - mg, __uint_as_float(v[jj]), dbs);
+            cw += contact ? wc : 0.f;
+          }
+        }
+      }
+    }
+    const float cnt = m < N ? (float)__popcll(bits) : 0.f;
+    {
+      float p[6] = {dbs, cw, cnt, G0, G1, tot};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) p[k] = warp_sum(p[k]);
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) reds[warp * 20 + k] = p[k];
+      }
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        float r[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int w = 0; w < NW; ++w)
+#pragma unroll
+          for (int k = 0; k < 6; ++k) r[k] += reds[w * 20 + k];
+        const float om = 1.0f - mm, kk = 1e-4f / om;
+        const float m2 = aux[(size_t)b * AUX_STRIDE + 100 * AUX_ROW];
+        const float s_all = kk * (r[3] - mg * r[5]);                 // sum over all pixels of w HR
+        const float s_c = m2 * kk * (r[1] - mg * r[2]);              // its contact part (HR = m2 there)
+        const float inv_g2 = 1.0f / (gamma * gamma);
+        const float mp = mm * 100.0f * inv_g2;
+        dab[b * 3 + 0] = (s_all - s_c) / alpha;
+        dab[b * 3 + 1] = alpha * 2.0f * CP2 / (beta * beta * beta) * kk * ldexpf(1.0f, dexp - 12) * r[0];
+        dab[b * 3 + 2] = 1e-4f * ((CM2 * inv_g2 * r[4] - mp * r[5] * gsum) / om + (r[3] - mm * r[5] * gsum) * mp / (om * om));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+  }
+}
+
 }  // namespace
 
 int g_psf_mode = 0;     // 0 = tensor-core forward, fp32-accurate (default), 1 = FFMA forward (psf.cu), 2 = tensor cores, one fp16 pass
@@ -1094,7 +1310,13 @@ int tsr_psf_backward_tc(const float* alphaBeta, const float* depth, const float*
 }
 int tsr_psf_backward_tc_f16(const float* alphaBeta, const float* depth, const float* aux, const float* dLRd,
                             float* dalphaBeta, int B, cudaStream_t stream) {
-  return psf_backward_tc_impl<1>(alphaBeta, depth, aux, dLRd, dalphaBeta, B, stream);
+  TSR_REQUIRE(alphaBeta && depth && aux && dLRd && dalphaBeta && B > 0, "psf_backward_tc_f16: bad argument");
+  TSR_REQUIRE(((uintptr_t)depth & 15) == 0 && ((uintptr_t)aux & 15) == 0, "psf_backward_tc_f16: depth / aux must be 16-byte aligned");
+  const size_t smem = Lay<3, PSF_THREADS>::BYTES;
+  TSR_CUDA(cudaFuncSetAttribute(psf_bwd_f16_kernel<PSF_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  psf_bwd_f16_kernel<PSF_THREADS><<<psf_tc_grid(B), PSF_THREADS, smem, stream>>>(alphaBeta, depth, aux, dLRd, dalphaBeta, B);
+  TSR_CHECK_LAUNCH("psf_backward_tc_f16");
+  return TSR_OK;
 }
 
 // (HR, LRd, psf) = PSF forward model of `depth` (B,100,100) under alphaBeta (B,3).  psf may be NULL.
