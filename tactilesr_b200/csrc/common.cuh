@@ -57,6 +57,17 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Two independent IEEE fp32 FMAs in one instruction (FFMA2): d.x = a.x b.x + d.x, d.y = a.y b.y + d.y.  On sm_100 a scalar
+// three-register FFMA issues every other cycle per scheduler, FFMA2 at the same rate: the packed form is what reaches the
+// fp32 peak.  Each half rounds exactly like fmaf, so kernels converted to it stay bit-identical.  ptxas folds a pair built
+// as (s, s) into the instruction's scalar-broadcast operand form.
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+}
+__device__ __forceinline__ void ffma2s(float2& d, const float s, const float2 b) { ffma2(d, make_float2(s, s), b); }
+
 // element load/store as float for the two storage types of the activation buffers
 __device__ __forceinline__ float ldf(const float* p) { return *p; }
 __device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }

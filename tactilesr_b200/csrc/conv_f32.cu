@@ -106,11 +106,11 @@ conv2d_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restri
     for (int g = 0; g < NB4; ++g) *reinterpret_cast<float4*>(&Bs[buf][bk][g * 64 + bn4]) = rb[g];
   };
 
-  float acc[8][TN];
+  float2 acc[8][TN / 2];               // pairs of couts: the inner product runs as FFMA2 (pixel broadcast x cout pair)
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
   load_global(0);
   store_smem(0);
@@ -123,16 +123,16 @@ conv2d_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restri
       float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8]);
       float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8 + 4]);
       float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      float bb[TN];
+      float2 bb[TN / 2];
 #pragma unroll
       for (int g = 0; g < NB4; ++g) {
         float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][g * 64 + tn * 4]);
-        bb[4 * g] = b.x; bb[4 * g + 1] = b.y; bb[4 * g + 2] = b.z; bb[4 * g + 3] = b.w;
+        bb[2 * g] = make_float2(b.x, b.y); bb[2 * g + 1] = make_float2(b.z, b.w);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        for (int j = 0; j < TN / 2; ++j) ffma2s(acc[i][j], a[i], bb[j]);
     }
     if (kc + 1 < nk) store_smem(buf ^ 1);
     __syncthreads();
@@ -147,7 +147,7 @@ conv2d_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restri
     for (int i = 0; i < 8; ++i) {
       int p = m0 + tm * 8 + i;
       if (p >= Mtotal) continue;
-      float4 v = make_float4(acc[i][4 * g] + bv.x, acc[i][4 * g + 1] + bv.y, acc[i][4 * g + 2] + bv.z, acc[i][4 * g + 3] + bv.w);
+      float4 v = make_float4(acc[i][2 * g].x + bv.x, acc[i][2 * g].y + bv.y, acc[i][2 * g + 1].x + bv.z, acc[i][2 * g + 1].y + bv.w);
       if (residual) {
         float4 r = *reinterpret_cast<const float4*>(residual + (long long)p * res_ld + n);
         v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
@@ -162,80 +162,124 @@ conv2d_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restri
 
 // ---------------------------------------------------------------------------------------------
 // weight gradient, level 1: partial[s][tap][ci][co] = sum_{p in split s} in[p+shift][ci]*dout[p][co]
-// tile 64 ci x 64 co, 16 pixels per K step, 256 threads, 4x4 outputs per thread
+// A GEMM over the pixels of the split with both operands pixel-major as they lie in HBM (NHWC): rows = (tap, ci), columns =
+// co.  CTA tile 128 rows x 16 TN columns, 16 pixels per K step, 256 threads, 8 x TN outputs per thread (FFMA2 on column
+// pairs; 3 or 4 LDS.128 per 16 / 32 FFMA2 -- the 4 x 4 tiles of round 1 were bound by their shared-memory reads).  The 128
+// rows are two half-tiles of 64 input channels, each with its own tap: two channel chunks of one tap (Cin >= 128) or the
+// same 64 channels under two consecutive taps (Cin = 64), so the same kernel serves every layer width.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <int TN>
+__global__ void __launch_bounds__(256, 2)
 conv2d_wgrad_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restrict__ dout,
                         int dout_ld, float* __restrict__ partial, int Mtotal, int H, int W, int Cin,
                         int Cout, int KS, int pix_per_split) {
-  __shared__ __align__(16) float As[2][16][64];
-  __shared__ __align__(16) float Bs[2][16][64];
+  constexpr int BN = 16 * TN, NB4 = TN / 4;
+  __shared__ __align__(16) float As[2][16][128];
+  __shared__ __align__(16) float Bs[2][16][BN];
   const int tid = threadIdx.x;
-  const int ctiles = Cin / 64, otiles = Cout / 64;
-  int t = blockIdx.x;
-  const int ot = t % otiles; t /= otiles;
-  const int ct = t % ctiles; t /= ctiles;
-  const int tap = t;
+  const int tn = tid & 15, tm = tid >> 4;          // columns g*64 + tn*4.., rows tm*8..
+  const int otiles = Cout / BN, cchunks = Cin / 64;
+  const int ot = blockIdx.x % otiles, rt = blockIdx.x / otiles;
+  const int nhalves = KS * KS * cchunks;
   const int pad = KS >> 1;
-  const int dy = tap / KS - pad, dx = tap % KS - pad;
-  const int HW = H * W;
-  const int ci0 = ct * 64, co0 = ot * 64;
+  const int co0 = ot * BN;
+  // the two half-tiles of this CTA
+  int hdy[2], hdx[2], hci[2], htap[2];
+  bool hok[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int hh = 2 * rt + h;
+    hok[h] = hh < nhalves;
+    htap[h] = hok[h] ? hh / cchunks : 0;
+    hci[h] = hok[h] ? (hh - htap[h] * cchunks) * 64 : 0;
+    hdy[h] = htap[h] / KS - pad;
+    hdx[h] = htap[h] % KS - pad;
+  }
   const int pbeg = blockIdx.y * pix_per_split;
   const int pend = min(pbeg + pix_per_split, Mtotal);
-  const int lk = tid >> 4, l4 = (tid & 15) * 4;
-  const int ti = tid >> 4, tj = tid & 15;   // ci = ti*4.., co = tj*4..
+  const int lk = tid >> 4, l4 = (tid & 15) * 4;    // load slot: pixel lk of the step, 4 channels from l4
 
-  float4 ra, rb;
-  auto load_global = [&](int p0) {
-    int p = p0 + lk;
-    ra = make_float4(0.f, 0.f, 0.f, 0.f);
-    rb = ra;
-    if (p < pend) {
-      int b = p / HW, rem = p - b * HW;
-      int y = rem / W, x = rem - y * W;
-      int yy = y + dy, xx = x + dx;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-        ra = *reinterpret_cast<const float4*>(in + ((long long)b * HW + (long long)yy * W + xx) * in_ld + ci0 + l4);
-      rb = *reinterpret_cast<const float4*>(dout + (long long)p * dout_ld + co0 + l4);
+  // this thread's load pixel, advanced by 16 per step without divisions
+  int lp = pbeg + lk;
+  int lb, ly, lx;
+  {
+    const int HW = H * W;
+    const int pp = lp < Mtotal ? lp : 0;
+    lb = pp / HW;
+    const int rem = pp - lb * HW;
+    ly = rem / W;
+    lx = rem - ly * W;
+  }
+  float4 ra[2], rb[NB4];
+  auto load_global = [&]() {
+    const bool pv = lp < pend;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int yy = ly + hdy[h], xx = lx + hdx[h];
+      const bool ok = pv && hok[h] && yy >= 0 && yy < H && xx >= 0 && xx < W;
+      ra[h] = ok ? *reinterpret_cast<const float4*>(in + (((long long)lb * H + yy) * W + xx) * in_ld + hci[h] + l4)
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+#pragma unroll
+    for (int g = 0; g < NB4; ++g)
+      rb[g] = pv ? *reinterpret_cast<const float4*>(dout + (long long)lp * dout_ld + co0 + g * 64 + l4)
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    lp += 16;
+    lx += 16;
+    while (lx >= W) { lx -= W; ++ly; }
+    while (ly >= H) { ly -= H; ++lb; }
   };
-  float acc[4][4];
+  auto store_smem = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][lk][l4]) = ra[0];
+    *reinterpret_cast<float4*>(&As[buf][lk][64 + l4]) = ra[1];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int g = 0; g < NB4; ++g) *reinterpret_cast<float4*>(&Bs[buf][lk][g * 64 + l4]) = rb[g];
+  };
 
-  int nsteps = (pend - pbeg + 15) / 16;
+  float2 acc[8][TN / 2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
+
+  const int nsteps = (pend - pbeg + 15) / 16;
   if (nsteps > 0) {
-    load_global(pbeg);
-    *reinterpret_cast<float4*>(&As[0][lk][l4]) = ra;
-    *reinterpret_cast<float4*>(&Bs[0][lk][l4]) = rb;
+    load_global();
+    store_smem(0);
   }
   __syncthreads();
   for (int s = 0; s < nsteps; ++s) {
-    int buf = s & 1;
-    if (s + 1 < nsteps) load_global(pbeg + (s + 1) * 16);
+    const int buf = s & 1;
+    if (s + 1 < nsteps) load_global();
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ti * 4]);
-      float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tj * 4]);
-      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8 + 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float2 bb[TN / 2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int g = 0; g < NB4; ++g) {
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][g * 64 + tn * 4]);
+        bb[2 * g] = make_float2(b.x, b.y); bb[2 * g + 1] = make_float2(b.z, b.w);
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN / 2; ++j) ffma2s(acc[i][j], a[i], bb[j]);
     }
-    if (s + 1 < nsteps) {
-      *reinterpret_cast<float4*>(&As[buf ^ 1][lk][l4]) = ra;
-      *reinterpret_cast<float4*>(&Bs[buf ^ 1][lk][l4]) = rb;
-    }
+    if (s + 1 < nsteps) store_smem(buf ^ 1);
     __syncthreads();
   }
-  float* dst = partial + ((long long)blockIdx.y * KS * KS + tap) * Cin * Cout;
+  const bool h1 = tm >= 8;                          // rows tm*8 .. tm*8+7 lie in one half-tile
+  if (!(h1 ? hok[1] : hok[0])) return;
+  float* dst = partial + (((long long)blockIdx.y * KS * KS + (h1 ? htap[1] : htap[0])) * Cin + (h1 ? hci[1] : hci[0]) +
+                          (tm & 7) * 8) * Cout + co0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    *reinterpret_cast<float4*>(dst + (long long)(ci0 + ti * 4 + i) * Cout + co0 + tj * 4) =
-        make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int g = 0; g < NB4; ++g)
+      *reinterpret_cast<float4*>(dst + (long long)i * Cout + g * 64 + tn * 4) =
+          make_float4(acc[i][2 * g].x, acc[i][2 * g].y, acc[i][2 * g + 1].x, acc[i][2 * g + 1].y);
 }
 
 // level 2: dw_oihw[co][ci][tap] (+)= sum_s partial[s][tap][ci][co]   (fixed order => deterministic)
@@ -338,11 +382,12 @@ head_fwd_kernel(const float* __restrict__ x, long long x_bstride, const float* _
   float* up = xs + 48;           // (H+2)^2*3
   const int H = 4 * sf, P = H + 2;
   const int g = threadIdx.x & 15, pl = threadIdx.x >> 4;
-  float wr[27][4];               // [tap*3 + c][channel of the quad]
+  float2 wr[27][2];              // [tap*3 + c][channel pair of the quad]
 #pragma unroll
   for (int q = 0; q < 27; ++q)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) wr[q][j] = w[((g * 4 + j) * 3 + q % 3) * 9 + q / 3];
+    for (int j = 0; j < 2; ++j)
+      wr[q][j] = make_float2(w[((g * 4 + 2 * j) * 3 + q % 3) * 9 + q / 3], w[((g * 4 + 2 * j + 1) * 3 + q % 3) * 9 + q / 3]);
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
     if (threadIdx.x < 48) xs[threadIdx.x] = x[(long long)b * x_bstride + threadIdx.x];
@@ -352,19 +397,19 @@ head_fwd_kernel(const float* __restrict__ x, long long x_bstride, const float* _
     int y = pl / H, xx = pl - y * H;                 // advanced incrementally: an integer division per pixel costs as
     for (int p = pl; p < H * H; p += 16) {           // much as a quarter of the pixel's FMAs
       const float4* u0 = reinterpret_cast<const float4*>(up) + (y * P + xx);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float2 a01 = make_float2(0.f, 0.f), a23 = a01;         // channel pairs: FFMA2
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         const float4 u4 = u0[(tap / 3) * P + tap % 3];       // the three axes of one neighbour pixel
         const float uv[3] = {u4.x, u4.y, u4.z};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float a = uv[c];
           const int q = tap * 3 + c;
-          acc.x = fmaf(a, wr[q][0], acc.x); acc.y = fmaf(a, wr[q][1], acc.y);
-          acc.z = fmaf(a, wr[q][2], acc.z); acc.w = fmaf(a, wr[q][3], acc.w);
+          ffma2s(a01, uv[c], wr[q][0]);
+          ffma2s(a23, uv[c], wr[q][1]);
         }
       }
+      float4 acc = make_float4(a01.x, a01.y, a23.x, a23.y);
       if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
       st4(out + ((long long)b * H * H + p) * out_ld + g * 4, acc);
       xx += 16;
@@ -398,22 +443,25 @@ template <> struct Raw4<__half> {
 };
 
 // head weight gradient, level 1: one partial [27][64] per CTA, CTAs stride over samples.
-// 512 threads = 16 channel quads x 32 pixel lanes; a thread keeps all 27 x 4 (tap, axis, channel) sums in registers, so a
-// pixel costs one 8/16-byte load of dout, 27 shared-memory reads of the upsampled frame and 108 FMAs.
+// HEAD_WG_NT threads = 16 channel quads x 16 pixel lanes; a thread keeps all 27 x 4 (tap, axis, channel) sums in registers
+// (as 54 channel pairs: FFMA2), so a pixel costs one 8/16-byte load of dout, 9 shared-memory reads of the upsampled frame
+// and 54 FFMA2.  256 threads per CTA: the paired accumulators spill under the 128- and 168-register caps of 512 / 384 threads.
+constexpr int HEAD_WG_NT = 256, HEAD_WG_LANES = HEAD_WG_NT / 16;
 template <typename GT>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(HEAD_WG_NT, 1)
 head_wgrad_kernel(const float* __restrict__ x, long long x_bstride, const GT* __restrict__ dout, int dout_ld,
                   float* __restrict__ partial, int B, int sf) {
+  constexpr int LN = HEAD_WG_LANES;
   extern __shared__ float smem[];
   float* xs = smem;                       // 48
-  float* up = xs + 48;                    // (H+2)^2 * 3, later reused for the lane reduction (32 x 64 floats)
+  float* up = xs + 48;                    // (H+2)^2 * 4, later reused for the lane reduction (LN x 64 floats)
   const int H = 4 * sf, P = H + 2;
-  const int g = threadIdx.x & 15, pl = threadIdx.x >> 4;   // channel quad, pixel lane 0..31
-  float acc[27][4];
+  const int g = threadIdx.x & 15, pl = threadIdx.x >> 4;   // channel quad, pixel lane 0..LN-1
+  float2 acc[27][2];                      // channel pairs: FFMA2
 #pragma unroll
   for (int q = 0; q < 27; ++q)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[q][j] = 0.f;
+    for (int j = 0; j < 2; ++j) acc[q][j] = make_float2(0.f, 0.f);
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
     if (threadIdx.x < 48) xs[threadIdx.x] = x[(long long)b * x_bstride + threadIdx.x];
@@ -421,16 +469,17 @@ head_wgrad_kernel(const float* __restrict__ x, long long x_bstride, const GT* __
     build_upsampled(xs, up, sf);
     __syncthreads();
     const GT* d = dout + (long long)b * H * H * dout_ld + g * 4;
-    // three pixels' gradients in flight per thread (kept as raw 8 / 16-byte words): with one CTA of 16 warps per SM a single
+    // three pixels' gradients in flight per thread (kept as raw 8 / 16-byte words): with one CTA per SM a single
     // outstanding load per thread leaves the HBM latency exposed
     typename Raw4<GT>::type r0 = Raw4<GT>::load(d + (long long)min(pl, H * H - 1) * dout_ld);
-    typename Raw4<GT>::type r1 = Raw4<GT>::load(d + (long long)min(pl + 32, H * H - 1) * dout_ld);
-    typename Raw4<GT>::type r2 = Raw4<GT>::load(d + (long long)min(pl + 64, H * H - 1) * dout_ld);
+    typename Raw4<GT>::type r1 = Raw4<GT>::load(d + (long long)min(pl + LN, H * H - 1) * dout_ld);
+    typename Raw4<GT>::type r2 = Raw4<GT>::load(d + (long long)min(pl + 2 * LN, H * H - 1) * dout_ld);
     int y = pl / H, xx = pl - y * H;
-    for (int p = pl; p < H * H; p += 32) {
+    for (int p = pl; p < H * H; p += LN) {
       const float4 gv = Raw4<GT>::cvt(r0);
       r0 = r1; r1 = r2;
-      r2 = Raw4<GT>::load(d + (long long)min(p + 96, H * H - 1) * dout_ld);
+      r2 = Raw4<GT>::load(d + (long long)min(p + 3 * LN, H * H - 1) * dout_ld);
+      const float2 g01 = make_float2(gv.x, gv.y), g23 = make_float2(gv.z, gv.w);
       const float4* u = reinterpret_cast<const float4*>(up) + (y * P + xx);
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
@@ -438,27 +487,26 @@ head_wgrad_kernel(const float* __restrict__ x, long long x_bstride, const GT* __
         const float uv[3] = {u4.x, u4.y, u4.z};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float a = uv[c];
           const int q = tap * 3 + c;
-          acc[q][0] = fmaf(a, gv.x, acc[q][0]); acc[q][1] = fmaf(a, gv.y, acc[q][1]);
-          acc[q][2] = fmaf(a, gv.z, acc[q][2]); acc[q][3] = fmaf(a, gv.w, acc[q][3]);
+          ffma2s(acc[q][0], uv[c], g01);
+          ffma2s(acc[q][1], uv[c], g23);
         }
       }
-      xx += 32;
+      xx += LN;
       while (xx >= H) { xx -= H; ++y; }
     }
   }
-  // fixed-order reduction over the 32 pixel lanes, one (tap, axis) at a time through shared memory
+  // fixed-order reduction over the pixel lanes, one (tap, axis) at a time through shared memory
   __syncthreads();
-  float4* red = reinterpret_cast<float4*>(up);      // [32 lanes][16 quads]
+  float4* red = reinterpret_cast<float4*>(up);      // [LN lanes][16 quads]
 #pragma unroll
   for (int q = 0; q < 27; ++q) {
-    red[pl * 16 + g] = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+    red[pl * 16 + g] = make_float4(acc[q][0].x, acc[q][0].y, acc[q][1].x, acc[q][1].y);
     __syncthreads();
     if (pl == 0) {
       float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int l = 0; l < 32; ++l) {
+      for (int l = 0; l < LN; ++l) {
         const float4 v = red[l * 16 + g];
         sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
       }
@@ -601,11 +649,12 @@ tail_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out_
   for (int g0 = 0; g0 < ngroups; g0 += 16) {                   // (one pass for Cin <= 128)
     const int g = g0 + (threadIdx.x & 15);
     const bool active = g < ngroups;
-    float wr[9][8];                                            // loaded once: the CTA is persistent over strips
+    float2 wr[9][4];                                           // (channel pairs: FFMA2) loaded once: the CTA is persistent over strips
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) wr[t][j] = active ? w[(g * 8 + j) * 9 + t] : 0.f;
+      for (int j = 0; j < 4; ++j)
+        wr[t][j] = active ? make_float2(w[(g * 8 + 2 * j) * 9 + t], w[(g * 8 + 2 * j + 1) * 9 + t]) : make_float2(0.f, 0.f);
     for (int sidx = blockIdx.x; sidx < B * strips; sidx += gridDim.x) {
       const int b = sidx / strips, y0 = (sidx - b * strips) * TAIL_TR;
       __syncthreads();
@@ -623,14 +672,15 @@ tail_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out_
       const int npx = min(TAIL_TR, H - y0) * W;
       int ty = (threadIdx.x >> 4) / W, x = (threadIdx.x >> 4) - ty * W;
       for (int p = threadIdx.x >> 4; active && p < npx; p += 16) {
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float2 acc2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           // output pixel o = p - shift(tap) used input p with weight tap
           const float gv = dz[(ty + 1 - (t / 3 - 1)) * PW + x + 1 - (t % 3 - 1)];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv, wr[t][j], acc[j]);
+          for (int j = 0; j < 4; ++j) ffma2s(acc2[j], gv, wr[t][j]);
         }
+        float acc[8] = {acc2[0].x, acc2[0].y, acc2[1].x, acc2[1].y, acc2[2].x, acc2[2].y, acc2[3].x, acc2[3].y};
         const long long pixel = ((long long)b * H + y0 + ty) * W + x;
         if (in_act) {        // ReLU backward of the layer that produced the tail's input: zero where its activation is <= 0
           float a8[8];
@@ -754,9 +804,15 @@ static int wgrad_splits(long long M, int tiles) {
   return s;
 }
 
+// level-1 CTAs of one split: pairs of (tap, 64-channel chunk) half-tiles x column tiles of 128 (or 64) output channels
+static int wgrad_f32_tiles(int Cin, int Cout, int KS) {
+  const int nhalves = KS * KS * (Cin / 64);
+  return ((nhalves + 1) / 2) * (Cout % 128 == 0 ? Cout / 128 : Cout / 64);
+}
+
 size_t tsr_conv2d_wgrad_f32_workspace(int B, int H, int W, int Cin, int Cout, int KS) {
   long long M = (long long)B * H * W;
-  int tiles = KS * KS * (Cin / 64) * (Cout / 64);
+  int tiles = wgrad_f32_tiles(Cin, Cout, KS);
   if (tiles <= 0) return 0;
   return (size_t)wgrad_splits(M, tiles) * KS * KS * Cin * Cout * sizeof(float);
 }
@@ -769,7 +825,7 @@ int tsr_conv2d_wgrad_f32(const float* in, int in_ld, const float* dout, int dout
   TSR_REQUIRE(in_ld % 4 == 0 && dout_ld % 4 == 0, "conv2d_wgrad_f32: row strides must be multiples of 4");
   long long M = (long long)B * H * W;
   int taps = KS * KS;
-  int tiles = taps * (Cin / 64) * (Cout / 64);
+  int tiles = wgrad_f32_tiles(Cin, Cout, KS);
   int S = wgrad_splits(M, tiles);
   size_t need = (size_t)S * taps * Cin * Cout * sizeof(float);
   if (ws_bytes < need) {
@@ -777,8 +833,12 @@ int tsr_conv2d_wgrad_f32(const float* in, int in_ld, const float* dout, int dout
     return TSR_ERR_WORKSPACE;
   }
   int pps = (int)(((M + S - 1) / S + 15) / 16 * 16);
-  conv2d_wgrad_f32_kernel<<<dim3(tiles, S), 256, 0, stream>>>(in, in_ld, dout, dout_ld, (float*)workspace,
-                                                              (int)M, H, W, Cin, Cout, KS, pps);
+  if (Cout % 128 == 0)
+    conv2d_wgrad_f32_kernel<8><<<dim3(tiles, S), 256, 0, stream>>>(in, in_ld, dout, dout_ld, (float*)workspace, (int)M, H, W,
+                                                                   Cin, Cout, KS, pps);
+  else
+    conv2d_wgrad_f32_kernel<4><<<dim3(tiles, S), 256, 0, stream>>>(in, in_ld, dout, dout_ld, (float*)workspace, (int)M, H, W,
+                                                                   Cin, Cout, KS, pps);
   TSR_CHECK_LAUNCH("conv2d_wgrad_f32");
   long long n = (long long)taps * Cin * Cout;
   wgrad_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>((const float*)workspace, dw_oihw, S, taps, Cin,
@@ -847,11 +907,11 @@ int tsr_head_wgrad(const float* x, long long x_bstride, const void* dout, int do
   int grid = B < 296 ? B : 296;
   TSR_REQUIRE(ws_bytes >= (size_t)grid * 27 * 64 * sizeof(float), "head_wgrad: workspace too small");
   size_t up_floats = (size_t)(4 * sf + 2) * (4 * sf + 2) * 4;
-  if (up_floats < 2048) up_floats = 2048;        // the lane reduction reuses it: 32 lanes x 64 channels
+  if (up_floats < 2048) up_floats = 2048;        // the lane reduction reuses it: <= 32 lanes x 64 channels
   size_t smem = (48 + up_floats) * sizeof(float);
   TSR_DISPATCH_T(dout_bf16, T,
                  TSR_CUDA(cudaFuncSetAttribute(head_wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                 head_wgrad_kernel<T><<<grid, 512, smem, stream>>>(x, x_bstride, (const T*)dout, dout_ld, (float*)workspace, B, sf));
+                 head_wgrad_kernel<T><<<grid, HEAD_WG_NT, smem, stream>>>(x, x_bstride, (const T*)dout, dout_ld, (float*)workspace, B, sf));
   TSR_CHECK_LAUNCH("head_wgrad");
   head_wgrad_reduce_kernel<<<tsr_cdiv(27 * 64, 256), 256, 0, stream>>>((const float*)workspace, grid, dw_oihw, accumulate);
   TSR_CHECK_LAUNCH("head_wgrad_reduce");

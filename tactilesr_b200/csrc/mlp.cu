@@ -23,11 +23,11 @@ sgemm_strided_kernel(const float* __restrict__ A, long long sam, long long sak, 
   const int tx = tid & 15, ty = tid >> 4;          // thread tile: rows ty*8.., columns tx*4..
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
-  float acc[8][4];
+  float2 acc2[8][2];                               // column pairs: the inner product runs as FFMA2
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 2; ++j) acc2[i][j] = make_float2(0.f, 0.f);
   for (int k0 = kbeg; k0 < kend; k0 += TK) {
 #pragma unroll
     for (int r = 0; r < TM * TK / 256; ++r) {
@@ -53,13 +53,18 @@ sgemm_strided_kernel(const float* __restrict__ A, long long sam, long long sak, 
       const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
       const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
       const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+      const float2 bb[2] = {make_float2(b4.x, b4.y), make_float2(b4.z, b4.w)};
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        for (int j = 0; j < 2; ++j) ffma2s(acc2[i][j], a[i], bb[j]);
     }
     __syncthreads();
+  }
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i][0] = acc2[i][0].x; acc[i][1] = acc2[i][0].y; acc[i][2] = acc2[i][1].x; acc[i][3] = acc2[i][1].y;
   }
   float* Cz = C + (long long)blockIdx.z * split_stride;
   const bool partial = gridDim.z > 1;
