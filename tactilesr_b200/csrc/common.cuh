@@ -68,6 +68,15 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
 }
 __device__ __forceinline__ void ffma2s(float2& d, const float s, const float2 b) { ffma2(d, make_float2(s, s), b); }
 
+// 16-byte asynchronous copy global -> shared without staging registers (LDGSTS); !valid writes zeros (src-size 0: nothing
+// is read, the pointer only has to be a mapped address)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // element load/store as float for the two storage types of the activation buffers
 __device__ __forceinline__ float ldf(const float* p) { return *p; }
 __device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }

@@ -57,10 +57,14 @@ conv2d_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restri
   const int pad = KS >> 1;
   const int HW = H * W;
 
-  // the two A-load slots of this thread: pixel (tid>>2) and 64 + (tid>>2), channel quad tid&3
+  // the two A-load slots of this thread: pixel (tid>>2) and 64 + (tid>>2), channel quad tid&3.  NHWC with (b, y, x)
+  // flattened: the neighbour (y + dy, x + dx) of pixel p is pixel p + dy W + dx, so a slot keeps ONE pointer to its centre
+  // pixel and the (tap, channel chunk) walk only adds CTA-uniform offsets (no division or 64-bit multiply per K step: in the
+  // first version that address arithmetic was half of all executed instructions).
   int ay[2], ax[2];
-  long long abase[2];
+  const float* acen[2];
   bool avalid[2];
+  const int ac4 = (tid & 3) * 4;
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     int m = (tid >> 2) + s * 64;
@@ -70,28 +74,35 @@ conv2d_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restri
     int b = pp / HW, rem = pp - b * HW;
     ay[s] = rem / W;
     ax[s] = rem - ay[s] * W;
-    abase[s] = (long long)b * HW;
+    acen[s] = in + (long long)pp * in_ld + ac4;
   }
-  const int ac4 = (tid & 3) * 4;
   const int bk = tid >> 4, bn4 = (tid & 15) * 4;
   const int cchunks = Cin / BK;
   const int nk = KS * KS * cchunks;
+  const float* wptr = wp + (long long)bk * Cout + n0 + bn4;      // advances by BK rows of the [tap][ci][co] matrix per K step
+  const int wstep = BK * Cout;
+  int tdy = -pad, tdx = -pad, c0 = 0;                            // the K step about to be loaded: tap offset, channel chunk
+  int tapoff = (tdy * W + tdx) * in_ld;
 
-  float4 ra[2], rb[NB4];
-  auto load_global = [&](int kc) {
-    int tap = kc / cchunks;
-    int c0 = (kc - tap * cchunks) * BK;
-    int dy = tap / KS - pad, dx = tap % KS - pad;
+  // A (transposed on its way into shared memory) is staged in registers across the compute block; the weight tile is a
+  // straight copy and goes global -> shared asynchronously (staging both in registers spilled under the 128-register cap,
+  // and the spill store waited for the load right where it was meant to be hidden)
+  float4 ra[2];
+  auto load_global = [&](int buf) {                              // loads the next K step and advances the walk
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      int yy = ay[s] + dy, xx = ax[s] + dx;
-      bool ok = avalid[s] && yy >= 0 && yy < H && xx >= 0 && xx < W;
-      ra[s] = ok ? *reinterpret_cast<const float4*>(in + (abase[s] + (long long)yy * W + xx) * in_ld + c0 + ac4)
-                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool ok = avalid[s] && (unsigned)(ay[s] + tdy) < (unsigned)H && (unsigned)(ax[s] + tdx) < (unsigned)W;
+      ra[s] = ok ? *reinterpret_cast<const float4*>(acen[s] + tapoff + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int g = 0; g < NB4; ++g)
-      rb[g] = *reinterpret_cast<const float4*>(wp + ((long long)tap * Cin + c0 + bk) * Cout + n0 + g * 64 + bn4);
+    for (int g = 0; g < NB4; ++g) cp_async16(&Bs[buf][bk][g * 64 + bn4], wptr + g * 64, true);
+    wptr += wstep;
+    c0 += BK;
+    if (c0 == Cin) {
+      c0 = 0;
+      if (++tdx > pad) { tdx = -pad; ++tdy; }
+      tapoff = (tdy * W + tdx) * in_ld;
+    }
   };
   auto store_smem = [&](int buf) {
 #pragma unroll
@@ -102,8 +113,7 @@ conv2d_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restri
       As[buf][ac4 + 2][m] = ra[s].z;
       As[buf][ac4 + 3][m] = ra[s].w;
     }
-#pragma unroll
-    for (int g = 0; g < NB4; ++g) *reinterpret_cast<float4*>(&Bs[buf][bk][g * 64 + bn4]) = rb[g];
+    cp_async_wait_all();
   };
 
   float2 acc[8][TN / 2];               // pairs of couts: the inner product runs as FFMA2 (pixel broadcast x cout pair)
@@ -117,7 +127,7 @@ conv2d_f32_kernel(const float* __restrict__ in, int in_ld, const float* __restri
   __syncthreads();
   for (int kc = 0; kc < nk; ++kc) {
     int buf = kc & 1;
-    if (kc + 1 < nk) load_global(kc + 1);
+    if (kc + 1 < nk) load_global(buf ^ 1);      // (buffer buf^1 was last read before the barrier that ended step kc-1)
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8]);
@@ -199,41 +209,39 @@ conv2d_wgrad_f32_kernel(const float* __restrict__ in, int in_ld, const float* __
   const int pend = min(pbeg + pix_per_split, Mtotal);
   const int lk = tid >> 4, l4 = (tid & 15) * 4;    // load slot: pixel lk of the step, 4 channels from l4
 
-  // this thread's load pixel, advanced by 16 per step without divisions
+  // this thread's load pixel, advanced by 16 per step without divisions; the shifted pixel of a tap is the linear pixel
+  // index plus dy W + dx (NHWC with (b, y, x) flattened), so each half-tile keeps one running pointer
   int lp = pbeg + lk;
-  int lb, ly, lx;
+  int ly, lx;
   {
     const int HW = H * W;
     const int pp = lp < Mtotal ? lp : 0;
-    lb = pp / HW;
-    const int rem = pp - lb * HW;
+    const int rem = pp - (pp / HW) * HW;
     ly = rem / W;
     lx = rem - ly * W;
   }
-  float4 ra[2], rb[NB4];
-  auto load_global = [&]() {
+  const float* aptr[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) aptr[h] = in + ((long long)lp + hdy[h] * W + hdx[h]) * in_ld + hci[h] + l4;
+  const float* bptr = dout + (long long)lp * dout_ld + co0 + l4;
+  const int astep = 16 * in_ld, bstep = 16 * dout_ld;
+  // both tiles are straight 16-byte copies: global -> shared asynchronously (zero fill outside the image / the split), no
+  // staging registers
+  auto load_tiles = [&](int buf) {
     const bool pv = lp < pend;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int yy = ly + hdy[h], xx = lx + hdx[h];
-      const bool ok = pv && hok[h] && yy >= 0 && yy < H && xx >= 0 && xx < W;
-      ra[h] = ok ? *reinterpret_cast<const float4*>(in + (((long long)lb * H + yy) * W + xx) * in_ld + hci[h] + l4)
-                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool ok = pv && hok[h] && (unsigned)(ly + hdy[h]) < (unsigned)H && (unsigned)(lx + hdx[h]) < (unsigned)W;
+      cp_async16(&As[buf][lk][h * 64 + l4], ok ? aptr[h] : in, ok);
+      aptr[h] += astep;
     }
 #pragma unroll
-    for (int g = 0; g < NB4; ++g)
-      rb[g] = pv ? *reinterpret_cast<const float4*>(dout + (long long)lp * dout_ld + co0 + g * 64 + l4)
-                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int g = 0; g < NB4; ++g) cp_async16(&Bs[buf][lk][g * 64 + l4], pv ? bptr + g * 64 : dout, pv);
+    bptr += bstep;
     lp += 16;
     lx += 16;
     while (lx >= W) { lx -= W; ++ly; }
-    while (ly >= H) { ly -= H; ++lb; }
-  };
-  auto store_smem = [&](int buf) {
-    *reinterpret_cast<float4*>(&As[buf][lk][l4]) = ra[0];
-    *reinterpret_cast<float4*>(&As[buf][lk][64 + l4]) = ra[1];
-#pragma unroll
-    for (int g = 0; g < NB4; ++g) *reinterpret_cast<float4*>(&Bs[buf][lk][g * 64 + l4]) = rb[g];
+    while (ly >= H) ly -= H;
   };
 
   float2 acc[8][TN / 2];
@@ -243,14 +251,12 @@ conv2d_wgrad_f32_kernel(const float* __restrict__ in, int in_ld, const float* __
     for (int j = 0; j < TN / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
   const int nsteps = (pend - pbeg + 15) / 16;
-  if (nsteps > 0) {
-    load_global();
-    store_smem(0);
-  }
+  if (nsteps > 0) load_tiles(0);
+  cp_async_wait_all();
   __syncthreads();
   for (int s = 0; s < nsteps; ++s) {
     const int buf = s & 1;
-    if (s + 1 < nsteps) load_global();
+    if (s + 1 < nsteps) load_tiles(buf ^ 1);     // (buffer buf^1 was last read before the barrier that ended step s-1)
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8]);
@@ -267,7 +273,7 @@ conv2d_wgrad_f32_kernel(const float* __restrict__ in, int in_ld, const float* __
 #pragma unroll
         for (int j = 0; j < TN / 2; ++j) ffma2s(acc[i][j], a[i], bb[j]);
     }
-    if (s + 1 < nsteps) store_smem(buf ^ 1);
+    cp_async_wait_all();
     __syncthreads();
   }
   const bool h1 = tm >= 8;                          // rows tm*8 .. tm*8+7 lie in one half-tile
@@ -796,7 +802,7 @@ int tsr_conv2d_f32(const float* in, int in_ld, const float* w_packed, const floa
 }
 
 static int wgrad_splits(long long M, int tiles) {
-  int s = (4 * 148 + tiles - 1) / tiles;
+  int s = (4 * 148) / tiles;       // two full waves at 2 CTAs per SM, never a third (rounding up cost 20 % as a 2-CTA tail wave)
   int maxs = (int)((M + 255) / 256);
   if (s > maxs) s = maxs;
   if (s < 1) s = 1;
