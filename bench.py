@@ -277,6 +277,51 @@ def cudnn_yardstick(dev, timeit):
     return res
 
 
+def fp32_mode_numbers(dev, timeit):
+    """The <= 1e-5 parity mode (FFMA2 implicit GEMM, csrc/conv_f32.cu) on the workloads of `cudnn_yardstick`: train step at
+    the reference batch 32 and at 512, eval forward at 1024 (with stock cuDNN fp32 on the same forward beside it)."""
+    import torch
+    import tactilesr_b200 as tb
+    from tactilesr_b200.functional import mse_hr_loss
+    from tactilesr_b200.model import TactileSR
+    from tactilesr_b200.optim import FusedAdam
+    res = {}
+    prev = tb.get_precision()
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        tb.set_precision("fp32")
+        torch.manual_seed(0)
+        m = TactileSR().to(dev).train()
+        opt = FusedAdam(m.parameters(), lr=1e-3, weight_decay=1e-2)
+        for Bc in (32, 512):
+            LR = torch.rand(Bc, 3, 4, 4, device=dev) * 8
+            HR = torch.rand(Bc, 1, 100, 100, device=dev) * 250
+
+            def step():
+                loss = mse_hr_loss(m(LR), HR, 10.0)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+            ms = timeit(step, 3 if Bc == 512 else 10)
+            res[f"train_b{Bc}_samples_per_s"] = Bc / (ms * 1e-3)
+            res[f"train_b{Bc}_TFLOPs"] = Bc / (ms * 1e-3) * 3 * FLOP_PER_SAMPLE_FWD / 1e12
+        m.eval()
+        LR = torch.rand(1024, 3, 4, 4, device=dev) * 8
+        with torch.no_grad():
+            ms = timeit(lambda: m(LR), 3)
+            res["eval_b1024_samples_per_s"] = 1024 / (ms * 1e-3)
+            res["eval_b1024_TFLOPs"] = 1024 / (ms * 1e-3) * FLOP_PER_SAMPLE_FWD / 1e12
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+            ms = timeit(lambda: stock_forward(m, LR), 3)
+            res["cudnn_fp32_eval_b1024_samples_per_s"] = 1024 / (ms * 1e-3)
+        res["fp32_fma_peak_TFLOPs_measured"] = 73.2      # tools/microbench/ffma2_rate.cu on this pool's B200 (FFMA2, 1.9 GHz)
+        del m, opt
+    finally:
+        tb.set_precision(prev)
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return res
+
+
 def measure_extras(dev, model, B):
     """Other configurations of BASELINE.json (reported, not the headline): SR inference (C3) and tPSFNet train (C2)."""
     import torch
@@ -323,6 +368,7 @@ def measure_extras(dev, model, B):
         out["sr_train_b32_cuda_graph_samples_per_s" if use_graph else "sr_train_b32_eager_samples_per_s"] = 32 / (ms * 1e-3)
         del t32, m32, o32
     out["cudnn_yardstick"] = cudnn_yardstick(dev, timeit)
+    out["fp32_mode"] = fp32_mode_numbers(dev, timeit)
     # TactileSRCNN (reference model/tactileSR_model.py:101-153; same kernels, different wiring): train step at the same batch
     from tactilesr_b200.functional import mse_hr_loss
     from tactilesr_b200.model import TactileSRCNN

@@ -67,6 +67,14 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
       : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
 }
 __device__ __forceinline__ void ffma2s(float2& d, const float s, const float2 b) { ffma2(d, make_float2(s, s), b); }
+__device__ __forceinline__ float2 fmul2s(const float2 a, const float s) {          // (a.x s, a.y s) in one FMUL2
+  float2 d;
+  const float2 ss = make_float2(s, s);
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(ss)));
+  return d;
+}
 
 // 16-byte asynchronous copy global -> shared without staging registers (LDGSTS); !valid writes zeros (src-size 0: nothing
 // is read, the pointer only has to be a mapped address)

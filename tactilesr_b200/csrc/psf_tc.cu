@@ -281,8 +281,11 @@ __device__ __forceinline__ void load_plane(const float* __restrict__ dsrc, int t
 // the PSF has 99 taps); kind 3 carries 16 e(t) t^2 as a single fp16 in the lo half instead of the residual
 template <int KIND, int NT>
 __device__ __forceinline__ void build_tab2(const float* tab, uint32_t* tab2, int tid) {
-  for (int i = tid; i < 4 * (int)TAB2_LEN; i += NT) {
-    const int s = i / (int)TAB2_LEN, qn = i - s * (int)TAB2_LEN;
+  static_assert(NT >= (int)TAB2_LEN, "one thread per table entry, the four shifted copies unrolled (no index division)");
+  if (tid >= (int)TAB2_LEN) return;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int qn = tid, i = s * (int)TAB2_LEN + qn;
     const int j = qn + s;
     const int t = j < 99 ? 99 - j : j - 99;
     float x = 0.f;
@@ -341,7 +344,8 @@ __device__ __forceinline__ void store_plane_tiles(const float (&dreg)[ipt<NT>()]
       for (int j = 0; j < 4; ++j) split_h2(dreg[i][2 * j] * sD, dreg[i][2 * j + 1] * sD, dh[j], dl[j]);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (dreg[i][j] > thr && (cg < 12 || j < 4)) bits |= 1u << j;
+        if (dreg[i][j] > thr) bits |= 1u << j;
+      if (cg == 12) bits &= 0x0Fu;                       // chunk 12 holds columns 96..99 only
       *reinterpret_cast<uint4*>(x_hi + off) = make_uint4(dh[0], dh[1], dh[2], dh[3]);
       if (PASSES == 3) *reinterpret_cast<uint4*>(x_lo + off) = make_uint4(dl[0], dl[1], dl[2], dl[3]);
       maskb[cg * 104 + r] = (uint8_t)bits;
@@ -432,10 +436,12 @@ __device__ __forceinline__ void acc_to_tmem(uint32_t acc, uint32_t t_hi, uint32_
   tmem_ld_cols<COLS>(acc + (uint32_t)(seg * COLS), v);
   tmem_ld_wait();
   uint32_t th[NP], tl[NP];
+  constexpr int SEGS_ = 112 / COLS, JV = (N - (SEGS_ - 1) * COLS) / 2;     // pairs of the last segment below k = 100
+  const bool lastseg = seg == SEGS_ - 1;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     split_h2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), th[j], tl[j]);
-    if (seg * COLS + 2 * j >= N) { th[j] = 0u; tl[j] = 0u; }            // k >= 100 (only in the last segment)
+    if (j >= JV && lastseg) { th[j] = 0u; tl[j] = 0u; }                 // k >= 100
   }
   const uint32_t p0 = (uint32_t)(seg * NP);
   tmem_st_pairs<NP>(t_hi + p0, th);
@@ -655,7 +661,10 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
       tmem_ld_cols<COLS>(acc + (uint32_t)c0, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < COLS; ++j) h[j] = __uint_as_float(v[j]) * cs;
+      for (int j = 0; j < COLS / 2; ++j) {
+        const float2 t = fmul2s(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), cs);
+        h[2 * j] = t.x; h[2 * j + 1] = t.y;
+      }
     }
     tc_fence_before();                                  // (all TMEM reads of this sample are complete)
     // second max = max over the conv result with the contact pixels zeroed (tPSFNet.py:95-97)
@@ -690,15 +699,16 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
         for (int j = 0; j < COLS; ++j)
           if (bitof(bits, j)) h[j] = m2;
       }
+      float2 rj01 = make_float2(0.f, 0.f), rj23 = rj01, r201 = rj01, r223 = rj01;   // (FFMA2: two sums per instruction)
       auto accumulate = [&](int j) {
         const float4 e4 = ex4[c0 + j];
         rs += h[j];
-        rj[0] = fmaf(h[j], e4.x, rj[0]); rj[1] = fmaf(h[j], e4.y, rj[1]);
-        rj[2] = fmaf(h[j], e4.z, rj[2]); rj[3] = fmaf(h[j], e4.w, rj[3]);
+        ffma2s(rj01, h[j], make_float2(e4.x, e4.y));
+        ffma2s(rj23, h[j], make_float2(e4.z, e4.w));
         if (AUX) {
           const float4 f4 = ex24[c0 + j];
-          r2[0] = fmaf(h[j], f4.x, r2[0]); r2[1] = fmaf(h[j], f4.y, r2[1]);
-          r2[2] = fmaf(h[j], f4.z, r2[2]); r2[3] = fmaf(h[j], f4.w, r2[3]);
+          ffma2s(r201, h[j], make_float2(f4.x, f4.y));
+          ffma2s(r223, h[j], make_float2(f4.z, f4.w));
         }
       };
       float4* hdst = reinterpret_cast<float4*>(hstage + m * N + c0);
@@ -712,6 +722,8 @@ psf_fwd_tc_kernel(const float* __restrict__ ab, const float* __restrict__ depth,
 #pragma unroll
         for (int j4 = NV_LAST / 4; j4 < COLS / 4; ++j4) hdst[j4] = make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
       }
+      rj[0] = rj01.x; rj[1] = rj01.y; rj[2] = rj23.x; rj[3] = rj23.y;
+      r2[0] = r201.x; r2[1] = r201.y; r2[2] = r223.x; r2[3] = r223.y;
     }
     // LRd[i][j] = 1e-4 (sum_m Ex_i(m) R_j(m) - mm sum HR) / (1 - mm),  R_j(m) = sum_n HR[m][n] Ex_j(n)
     {
