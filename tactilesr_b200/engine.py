@@ -72,6 +72,16 @@ def bump_weight_epoch() -> None:
     _WEIGHT_EPOCH += 1
 
 
+def invalidate_packed_weights() -> None:
+    """Drop every cached packed / folded copy of the convolution weights at the next forward.
+
+    The caches are keyed on ``(data_ptr, Tensor._version, optimizer epoch)``.  ``FusedAdam.step`` bumps the epoch itself and
+    ``load_state_dict`` / ``copy_`` / ``nn.init`` bump ``_version``; writes that bypass both -- ``p.data.copy_(...)``,
+    ``p.data.mul_(...)`` (EMA, manual re-initialisation), a foreign optimizer implemented with raw kernels -- must call this
+    once afterwards."""
+    bump_weight_epoch()
+
+
 # ---------------------------------------------------------------------------------------------
 # optional per-kernel-class timing (bench.py: step_breakdown_ms); off by default, no cost when off
 # ---------------------------------------------------------------------------------------------
@@ -1177,6 +1187,14 @@ def apply_program(prog: Program, x: torch.Tensor, training: bool, mode: Optional
     params = prog.parameters()
     need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or
                                              (prog.wants_input_grad and x.requires_grad))
+    if need_grad:
+        # gradients are written straight into ``.grad`` (see _ProgramFn.backward): tensor hooks on parameters would never fire
+        for p in params:
+            if p.requires_grad and (p._backward_hooks or getattr(p, "_post_accumulate_grad_hooks", None)):
+                raise _lib.TsrError("tactilesr_b200: gradient hooks on parameters (Tensor.register_hook / "
+                                    "register_post_accumulate_grad_hook, e.g. DDP, GradScaler unscale hooks) are not supported: "
+                                    "the kernels write parameter gradients straight into .grad; use Trainer's gradient "
+                                    "all-reduce (cpu/distributed.py GradAllReduce) instead")
     holder = {"prog": prog, "training": training, "need_grad": need_grad, "mode": mode}
     if extra:
         holder.update(extra)

@@ -304,3 +304,59 @@ def test_fused_adam_kernel_matches_torch_adam_exactly():
     pa[0].grad = torch.ones_like(pa[0])
     oa.step()
     assert torch.equal(pa[1].detach(), before)
+
+
+@pytest.mark.parametrize("Cin,Cout,KS,B", [(64, 64, 5, 3), (64, 64, 3, 2), (128, 128, 3, 2), (128, 128, 5, 1), (256, 64, 1, 3),
+                                            (64, 256, 1, 2), (448, 64, 3, 1), (64, 128, 3, 5)])
+def test_conv_wgrad_f32_matches_fp64(Cin, Cout, KS, B):
+    """tsr_conv2d_wgrad_f32 (128-row x 64/128-column FFMA2 tiles; a row tile = two (tap, 64-channel chunk) halves, the last
+    one half empty when taps x chunks is odd) against torch.nn.grad.conv2d_weight in fp64: operands inside wider (concat)
+    buffers, accumulate on and off, and bit-determinism."""
+    from tactilesr_b200 import _lib
+    torch.manual_seed(Cin + Cout + KS)
+    dev, H, W = "cuda", 40, 40
+    st = torch.cuda.current_stream().cuda_stream
+    xb = torch.randn(B, H, W, Cin + 64, device=dev)            # the operand is a channel slice of a wider buffer
+    gb = torch.randn(B, H, W, Cout + 128, device=dev)
+    x, g = xb[..., 64:], gb[..., 64:64 + Cout]
+    need = int(_lib.lib().tsr_conv2d_wgrad_f32_workspace(B, H, W, Cin, Cout, KS))
+    ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+    dw0 = torch.randn(Cout, Cin, KS, KS, device=dev)
+
+    def run(acc):
+        dw = dw0.clone()
+        _lib.call("tsr_conv2d_wgrad_f32", x.data_ptr(), Cin + 64, g.data_ptr(), Cout + 128, dw.data_ptr(), ws.data_ptr(), ws.numel(),
+                  B, H, W, Cin, Cout, KS, acc, st)
+        return dw
+    ref = torch.nn.grad.conv2d_weight(x.double().permute(0, 3, 1, 2), (Cout, Cin, KS, KS), g.double().permute(0, 3, 1, 2),
+                                      padding=KS // 2)
+    a, b = run(0), run(1)
+    assert rel_l2(a, ref) < 2e-6
+    assert rel_l2(b, ref + dw0.double()) < 2e-6
+    assert torch.equal(a, run(0))
+
+
+def test_parameter_hooks_are_rejected_and_data_writes_need_invalidation():
+    """Gradients are written straight into .grad, so tensor hooks on parameters cannot fire: forward raises instead of
+    silently skipping them.  Writes through .data bypass the packed-weight cache keys until invalidate_packed_weights()."""
+    import tactilesr_b200 as tb
+    m = _model(1, 3).train()
+    x = sr_inputs(2, 1, 5)[0].cuda()
+    p = m.output_layer[0].weight
+    h = p.register_hook(lambda g: g)
+    with pytest.raises(tb.TsrError):
+        m(x)
+    h.remove()
+    m.eval()
+    pc = m.patternFeatureExtra_layer[0].conv_3_2[0].weight     # a conv whose weights live in the packed-copy cache
+    with torch.no_grad():
+        o1 = m(x)
+        pc.data.mul_(0.5)
+        tb.invalidate_packed_weights()
+        o2 = m(x)
+    fresh = _model(1, 3).eval()
+    fresh.load_state_dict(m.state_dict())
+    with torch.no_grad():
+        o3 = fresh(x)
+    assert not torch.equal(o1, o2)
+    assert torch.equal(o2, o3)
