@@ -450,41 +450,72 @@ template <> struct Raw4<__half> {
 
 // head weight gradient, level 1: one partial [27][64] per CTA, CTAs stride over samples.
 // HEAD_WG_NT threads = 16 channel quads x 16 pixel lanes; a thread keeps all 27 x 4 (tap, axis, channel) sums in registers
-// (as 54 channel pairs: FFMA2), so a pixel costs one 8/16-byte load of dout, 9 shared-memory reads of the upsampled frame
-// and 54 FFMA2.  256 threads per CTA: the paired accumulators spill under the 128- and 168-register caps of 512 / 384 threads.
+// (as 54 channel pairs: FFMA2; 256 threads per CTA: the paired accumulators spill under the 128- / 168-register caps of
+// 512 / 384 threads), so a pixel costs 9 shared-memory reads of the upsampled frame, one of the gradient and 54 FFMA2.
+// The gradient rows are staged in shared memory by 16-byte asynchronous copies, `chpix` pixels (<= 40 KB) per chunk, double
+// buffered across chunks AND samples: with one 8-warp CTA per SM, register prefetch kept only 6 KB per SM in flight and the
+// kernel ran at 0.57 TB/s of HBM latency; a staged chunk keeps 40 KB in flight.
 constexpr int HEAD_WG_NT = 256, HEAD_WG_LANES = HEAD_WG_NT / 16;
+template <typename GT> struct HeadWg {
+  static constexpr int ROWB = 64 * (int)sizeof(GT);            // bytes of one pixel's 64 gradients
+  static constexpr int CH_MAX = 40960 / ROWB;                  // pixels per staged chunk (320 / 160)
+};
 template <typename GT>
 __global__ void __launch_bounds__(HEAD_WG_NT, 1)
 head_wgrad_kernel(const float* __restrict__ x, long long x_bstride, const GT* __restrict__ dout, int dout_ld,
-                  float* __restrict__ partial, int B, int sf) {
-  constexpr int LN = HEAD_WG_LANES;
-  extern __shared__ float smem[];
+                  float* __restrict__ partial, int B, int sf, int up_floats, int chpix) {
+  constexpr int LN = HEAD_WG_LANES, ROWB = HeadWg<GT>::ROWB, PIECES = ROWB / 16;
+  extern __shared__ __align__(16) float smem[];
   float* xs = smem;                       // 48
-  float* up = xs + 48;                    // (H+2)^2 * 4, later reused for the lane reduction (LN x 64 floats)
-  const int H = 4 * sf, P = H + 2;
-  const int g = threadIdx.x & 15, pl = threadIdx.x >> 4;   // channel quad, pixel lane 0..LN-1
+  float* up = xs + 48;                    // (H+2)^2 * 4 (>= 2048), later reused for the lane reduction (LN x 64 floats)
+  uint8_t* stage = reinterpret_cast<uint8_t*>(up + up_floats);   // 2 x chpix x ROWB
+  const int H = 4 * sf, P = H + 2, HH = H * H;
+  const int tid = threadIdx.x;
+  const int g = tid & 15, pl = tid >> 4;  // channel quad, pixel lane 0..LN-1
   float2 acc[27][2];                      // channel pairs: FFMA2
 #pragma unroll
   for (int q = 0; q < 27; ++q)
 #pragma unroll
     for (int j = 0; j < 2; ++j) acc[q][j] = make_float2(0.f, 0.f);
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
-    __syncthreads();
-    if (threadIdx.x < 48) xs[threadIdx.x] = x[(long long)b * x_bstride + threadIdx.x];
-    __syncthreads();
-    build_upsampled(xs, up, sf);
-    __syncthreads();
-    const GT* d = dout + (long long)b * H * H * dout_ld + g * 4;
-    // three pixels' gradients in flight per thread (kept as raw 8 / 16-byte words): with one CTA per SM a single
-    // outstanding load per thread leaves the HBM latency exposed
-    typename Raw4<GT>::type r0 = Raw4<GT>::load(d + (long long)min(pl, H * H - 1) * dout_ld);
-    typename Raw4<GT>::type r1 = Raw4<GT>::load(d + (long long)min(pl + LN, H * H - 1) * dout_ld);
-    typename Raw4<GT>::type r2 = Raw4<GT>::load(d + (long long)min(pl + 2 * LN, H * H - 1) * dout_ld);
-    int y = pl / H, xx = pl - y * H;
-    for (int p = pl; p < H * H; p += LN) {
-      const float4 gv = Raw4<GT>::cvt(r0);
-      r0 = r1; r1 = r2;
-      r2 = Raw4<GT>::load(d + (long long)min(p + 3 * LN, H * H - 1) * dout_ld);
+
+  const int nch = (HH + chpix - 1) / chpix;
+  const int nsamples = (int)blockIdx.x < B ? (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int nitems = nsamples * nch;      // work items (sample, chunk) of this CTA, in order
+  auto issue = [&](int it, int buf) {     // asynchronous copy of item it's gradient rows into stage buffer buf
+    const int si = it / nch, c0 = (it - si * nch) * chpix;
+    const int b = blockIdx.x + si * gridDim.x;
+    const int n = min(chpix, HH - c0);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(dout + ((long long)b * HH + c0) * dout_ld);
+    uint8_t* dst = stage + (size_t)buf * chpix * ROWB;
+    const long long rstride = (long long)dout_ld * (long long)sizeof(GT);
+    for (int i = tid; i < n * PIECES; i += HEAD_WG_NT) {
+      const int row = i / PIECES, q = i - row * PIECES;
+      cp_async16(dst + row * ROWB + q * 16, src + row * rstride + q * 16, true);
+    }
+    cp_async_commit();
+  };
+  if (nitems > 0) issue(0, 0);
+  for (int it = 0; it < nitems; ++it) {
+    const int buf = it & 1;
+    const int si = it / nch, c0 = (it - si * nch) * chpix;
+    if (c0 == 0) {                        // a new sample: its upsampled frame (the previous sample's pixels are all consumed:
+      const int b = blockIdx.x + si * gridDim.x;      //  barrier at the end of the previous item)
+      if (tid < 48) xs[tid] = x[(long long)b * x_bstride + tid];
+      __syncthreads();
+      build_upsampled(xs, up, sf);
+    }
+    if (it + 1 < nitems) {
+      issue(it + 1, buf ^ 1);             // (buffer buf^1 was read in item it-1, which ended with a barrier)
+      cp_async_wait_group<1>();
+    } else {
+      cp_async_wait_group<0>();
+    }
+    __syncthreads();                      // this item's rows (every thread's copies) and `up` are visible
+    const int n = min(chpix, HH - c0);
+    const uint8_t* rows = stage + (size_t)buf * chpix * ROWB + g * 4 * sizeof(GT);
+    int y = (c0 + pl) / H, xx = (c0 + pl) - y * H;
+    for (int p = pl; p < n; p += LN) {
+      const float4 gv = Raw4<GT>::cvt(Raw4<GT>::load(reinterpret_cast<const GT*>(rows + (size_t)p * ROWB)));
       const float2 g01 = make_float2(gv.x, gv.y), g23 = make_float2(gv.z, gv.w);
       const float4* u = reinterpret_cast<const float4*>(up) + (y * P + xx);
 #pragma unroll
@@ -501,9 +532,9 @@ head_wgrad_kernel(const float* __restrict__ x, long long x_bstride, const GT* __
       xx += LN;
       while (xx >= H) { xx -= H; ++y; }
     }
+    __syncthreads();                      // stage[buf] and (at a sample's last chunk) `up` may be overwritten
   }
   // fixed-order reduction over the pixel lanes, one (tap, axis) at a time through shared memory
-  __syncthreads();
   float4* red = reinterpret_cast<float4*>(up);      // [LN lanes][16 quads]
 #pragma unroll
   for (int q = 0; q < 27; ++q) {
@@ -580,12 +611,13 @@ tail_fwd_kernel(const InT* __restrict__ in, int in_ld, const float* __restrict__
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   // this lane's weights: channels c = lane*4 + 128*k (k = 0 for Cin <= 128)
-  float wr[9][4];
+  float2 wr[9][2];                                      // channel pairs (FFMA2)
   const int c0 = lane * 4;
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) wr[t][j] = (c0 + j < Cin) ? w[(c0 + j) * 9 + t] : 0.f;
+    for (int j = 0; j < 2; ++j)
+      wr[t][j] = make_float2((c0 + 2 * j < Cin) ? w[(c0 + 2 * j) * 9 + t] : 0.f, (c0 + 2 * j + 1 < Cin) ? w[(c0 + 2 * j + 1) * 9 + t] : 0.f);
   __syncthreads();
   // 4 pixels per warp iteration (independent accumulation chains), then one transposing reduction of the 4 sums
   const int npx = min(TAIL_TR, H - y0) * W;
@@ -598,11 +630,14 @@ tail_fwd_kernel(const InT* __restrict__ in, int in_ld, const float* __restrict__
         int ty = ty0, x = x0 + k;
         if (x >= W) { x -= W; ++ty; }
         if (p0 + k >= npx) { ty = ty0; x = x0; }       // (padding lanes of the last group recompute pixel p0)
+        float2 s01 = make_float2(0.f, 0.f), s23 = s01; // even / odd channel partial sums: two 9-long FFMA2 chains per pixel
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const float4 v = ld4(tile + (long long)((ty + t / 3) * PW + x + t % 3) * pitch + c0);
-          sum4[k] = fmaf(v.x, wr[t][0], fmaf(v.y, wr[t][1], fmaf(v.z, wr[t][2], fmaf(v.w, wr[t][3], sum4[k]))));
+          ffma2(s01, make_float2(v.x, v.y), wr[t][0]);
+          ffma2(s23, make_float2(v.z, v.w), wr[t][1]);
         }
+        sum4[k] = (s01.x + s01.y) + (s23.x + s23.y);
       }
     }
     if (Cin > 128) {   // generic tail for wider inputs (not used by the reference networks)
@@ -914,10 +949,17 @@ int tsr_head_wgrad(const float* x, long long x_bstride, const void* dout, int do
   TSR_REQUIRE(ws_bytes >= (size_t)grid * 27 * 64 * sizeof(float), "head_wgrad: workspace too small");
   size_t up_floats = (size_t)(4 * sf + 2) * (4 * sf + 2) * 4;
   if (up_floats < 2048) up_floats = 2048;        // the lane reduction reuses it: <= 32 lanes x 64 channels
-  size_t smem = (48 + up_floats) * sizeof(float);
+  TSR_REQUIRE(dout_ld % 8 == 0, "head_wgrad: dout row stride must be a multiple of 8 elements (16-byte copies)");
   TSR_DISPATCH_T(dout_bf16, T,
+                 // staged chunk: up to 40 KB, less when a large scale factor's upsampled frame leaves less shared memory
+                 const long long room = 227LL * 1024 - (long long)(48 + up_floats) * 4;
+                 long long chpix = room / (2 * HeadWg<T>::ROWB);
+                 if (chpix > HeadWg<T>::CH_MAX) chpix = HeadWg<T>::CH_MAX;
+                 TSR_REQUIRE(chpix >= 16, "head_wgrad: scale_factor %d leaves no shared memory for the gradient stage", sf);
+                 size_t smem = (48 + up_floats) * sizeof(float) + (size_t)2 * chpix * HeadWg<T>::ROWB;
                  TSR_CUDA(cudaFuncSetAttribute(head_wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                 head_wgrad_kernel<T><<<grid, HEAD_WG_NT, smem, stream>>>(x, x_bstride, (const T*)dout, dout_ld, (float*)workspace, B, sf));
+                 head_wgrad_kernel<T><<<grid, HEAD_WG_NT, smem, stream>>>(x, x_bstride, (const T*)dout, dout_ld, (float*)workspace, B, sf,
+                                                                          (int)up_floats, (int)chpix));
   TSR_CHECK_LAUNCH("head_wgrad");
   head_wgrad_reduce_kernel<<<tsr_cdiv(27 * 64, 256), 256, 0, stream>>>((const float*)workspace, grid, dw_oihw, accumulate);
   TSR_CHECK_LAUNCH("head_wgrad_reduce");

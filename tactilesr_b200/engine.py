@@ -178,6 +178,13 @@ class RunCtx:
         self.keep: list = []                                   # small temporaries that must outlive the launches reading them
         self.keep_taps = False
         self._ws: Optional[torch.Tensor] = None
+        # zero-initialised fp32 scratch (statistics tables the conv epilogues add to): carved out of one arena per sweep, so a
+        # sweep costs ONE fill launch instead of one per table (24 per training step of TactileSR)
+        self.zero_cap = 0
+        self._zarena: Optional[torch.Tensor] = None
+        self._zoff = 0
+        self.zero_later: list = []                             # gradients that are identically zero: cleared by one launch
+        self.defer_zero = True
 
     # -- buffers ------------------------------------------------------------------------------
     def alloc(self, buf: Buf) -> torch.Tensor:
@@ -224,11 +231,26 @@ class RunCtx:
             sp, sld = self.sptr(v)
             _lib.call("tsr_copy_channels", ip, ild, 2, sp, sld, 1, self.npix, v.C, _lib.stream_ptr())
 
+    def zeros_f32(self, n: int) -> torch.Tensor:
+        """n fp32 zeros from the sweep's arena (256-byte aligned); a too-small estimate just opens another zeroed block."""
+        n4 = (n + 63) // 64 * 64
+        if self._zarena is None or self._zoff + n4 > self._zarena.numel():
+            self._zarena = torch.zeros(max(self.zero_cap, n4), dtype=torch.float32, device=self.device)
+            self._zoff = 0
+        t = self._zarena[self._zoff:self._zoff + n]
+        self._zoff += n4
+        return t
+
+    def new_sweep(self) -> None:
+        """Backward starts with a fresh arena (tables of the forward may still be referenced)."""
+        self._zarena, self._zoff = None, 0
+
     def stat_table(self, bnop, part: int) -> torch.Tensor:
         """Zeroed [rows][2][channels of bnop] table that the conv epilogue(s) feeding ``bnop`` add their statistics to."""
         t = self.bn_partials.get(bnop)
         if t is None:
-            t = torch.zeros((_lib.lib().tsr_conv2d_tc2_stat_rows(), 2, bnop.src.C), dtype=torch.float32, device=self.device)
+            rows = _lib.lib().tsr_conv2d_tc2_stat_rows()
+            t = self.zeros_f32(rows * 2 * bnop.src.C).view(rows, 2, bnop.src.C)
             self.bn_partials[bnop] = t
             self.bn_partials_parts[bnop] = set()
         self.bn_partials_parts[bnop].add(part)
@@ -656,7 +678,10 @@ class ConvOp(Op):
                 # backward output, which is identically 0 (the reference computes fp32 rounding noise ~1e-8 of the layer's
                 # gradient scale here, SURVEY section 0 pitfall 2): write the exact value instead of reducing 2 GB of zeros.
                 if not accb:
-                    gb.zero_()
+                    if c.defer_zero:
+                        c.zero_later.append(gb)
+                    else:
+                        gb.zero_()
             else:
                 ws, wsb = c.workspace(_lib.lib().tsr_colsum_workspace(c.npix, self.Cout))
                 _lib.call("tsr_colsum", gp, gld, c.grd, c.npix, self.Cout, gb.data_ptr(), ws, wsb, accb, st)
@@ -713,7 +738,7 @@ def _dgrad_impl(c: RunCtx, ops: List[ConvOp], sink: Optional[Sink]) -> None:
             bnop = sink.bn
             coef = c.saved[bnop][0]
             yp, yld = c.vptr(bnop.src)
-            part = torch.zeros((_stat_rows(), 2, buf.C), dtype=torch.float32, device=c.device)
+            part = c.zeros_f32(_stat_rows() * 2 * buf.C).view(_stat_rows(), 2, buf.C)
             flags = _lib.TC2_BNB | (_lib.TC2_BNB_RELU if bnop.relu else 0) | auxf | _lib.TC2_STAT_PRECLEARED
             kw.update(aux=yp, aux_ld=yld, aux_scale=coef[0].data_ptr(), aux_shift=coef[1].data_ptr(), stat=part.data_ptr(),
                       stat_ld=buf.C)
@@ -1060,6 +1085,8 @@ def run_forward(prog: Program, x: torch.Tensor, training: bool, need_grad: bool,
         _arm_overflow_guard(x.device)
     prog.plan()
     c.conv_inputs = {op.src.buf for op in prog.ops if isinstance(op, (ConvOp, DualConvOp))}
+    if c.tc:
+        c.zero_cap = _stat_rows() * 2 * (sum(op.src.C for op in prog.ops if isinstance(op, BNReLUOp)) + 16)
     c.keep_taps = keep_taps
     if c.tc and (training or need_grad):
         seen, items = set(), []
@@ -1108,6 +1135,8 @@ def run_backward(prog: Program, c: RunCtx, dout: torch.Tensor, hooks=None) -> Di
         c.grad_written[prog.out] = True
         _lib.call("tsr_nchw_to_nhwc", dout.data_ptr(), g.data_ptr(), prog.out.C, c.grd, c.B, prog.out.C, c.H * c.W,
                   _lib.stream_ptr())
+    c.new_sweep()
+    c.defer_zero = hooks is None       # (a per-op hook may ship gradient buckets before the sweep ends: zero those at once)
     # reverse sweep; gradient buffers are dropped as soon as their producer has consumed them
     for i in range(len(prog.ops) - 1, -1, -1):
         op = prog.ops[i]
@@ -1124,6 +1153,9 @@ def run_backward(prog: Program, c: RunCtx, dout: torch.Tensor, hooks=None) -> Di
         for b in needed:
             if not (prog.wants_input_grad and b is prog.in_buf) and not _written_earlier(prog, i, b):
                 c.grads.pop(b, None)
+    if c.zero_later:
+        torch._foreach_zero_(c.zero_later)
+        c.zero_later = []
     return c.param_grads
 
 
