@@ -37,7 +37,7 @@ with torch.no_grad():
     m(torch.rand(64, 3, 4, 4, device=dev) * 8)       # non-trivial running stats
 m.eval()
 quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
-for mode, batches in (("fp16", [1024, 4096, 16384, 65536, 262144]), ("bf16", [1024, 16384, 262144]), ("fp32", [1024, 4096])):
+for mode, batches in (("fp16", [1024, 4096, 16384, 65536, 262144]), ("bf16", [1024, 16384, 262144]), ("fp32", [1024, 4096, 16384])):
     tb.set_precision(mode)
     for B in batches:
         if quick and B > 16384:
@@ -47,7 +47,7 @@ for mode, batches in (("fp16", [1024, 4096, 16384, 65536, 262144]), ("bf16", [10
             ms = timeit(lambda: m(LR), 1 if B >= 65536 else 3, warm=1)
         print(f"| C3 TactileSR S=1 eval forward | {mode} | {B} | {ms:.1f} | {B / ms * 1e3:.0f} | {B / ms * 1e3 * FWD[1] / 1e12:.0f} |", flush=True)
 for S in (1, 7):
-    for mode, B in (("fp16", 1024), ("bf16", 1024), ("fp32", 64)):
+    for mode, B in (("fp16", 1024), ("bf16", 1024), ("fp32", 256)):
         tb.set_precision(mode)
         torch.manual_seed(1)
         ms_ = TactileSR(seqsCnt=S).to(dev).train()
