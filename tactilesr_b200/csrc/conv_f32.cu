@@ -671,6 +671,147 @@ tail_fwd_kernel(const InT* __restrict__ in, int in_ld, const float* __restrict__
   }
 }
 
+// Register-blocked tail forward for Cin <= 128 (every reference network): same strip tile as above, staged by 16-byte
+// asynchronous copies (zero fill = padding), then ONE WARP PER 4 x 5 BLOCK OF OUTPUT PIXELS (8 blocks = 8 warps for W = 40):
+// lane = 4 channels, its 9 x 4 weights in registers; each of the block's 6 x 7 input pixels is read from shared memory ONCE
+// and feeds up to nine outputs (2.1 shared-memory reads and conversions per output instead of 9: the one-pixel-per-warp
+// kernel was bound by exactly those -- 398 us at B = 1024 against 64 us of HBM time), accumulators as (even, odd) channel
+// pairs (FFMA2), then a transposing warp reduction of the 20 sums (22 shuffles).
+constexpr int TAIL_BW = 5;
+template <typename InT>
+__global__ void __launch_bounds__(512, 1)
+tail_fwd_blocked_kernel(const InT* __restrict__ in, int in_ld, const float* __restrict__ w /*1,Cin,3,3*/,
+                        float* __restrict__ out, int B, int H, int W, int Cin, int relu, int nbuf) {
+  // nbuf = 2: persistent CTAs (one per SM), the next strip's tile is copied while this one is computed (16-bit inputs: two
+  // tiles fit); nbuf = 1: one strip per CTA (fp32 inputs), the CTAs of an SM overlap each other instead.
+  extern __shared__ __align__(16) uint8_t tail_smem[];
+  constexpr int VEC = 16 / sizeof(InT);
+  const int pitch = Cin + VEC;
+  const int strips = (H + TAIL_TR - 1) / TAIL_TR, total = B * strips;
+  const int PW = W + 2, PH = TAIL_TR + 2;
+  const size_t tile_elems = (size_t)PH * PW * pitch;
+  const int vpp = Cin / VEC;
+  // Tile copy: thread = (16-byte vector v of a pixel, pixel lane).  All address arithmetic is hoisted: the shared-memory
+  // address advances by a constant, the global one is a per-strip base plus a 32-bit (row, column) offset (in the first
+  // version the 64-bit products and generic-to-shared conversions made this loop 46 % of the kernel's instructions).
+  const int cv = threadIdx.x % vpp, clanes = blockDim.x / vpp;      // blockDim.x is a multiple of vpp
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(tail_smem);
+  const uint32_t tile_bytes = (uint32_t)(tile_elems * sizeof(InT)), pix_bytes = (uint32_t)(pitch * sizeof(InT));
+  auto issue = [&](int sidx, int buf) {
+    const int b = sidx / strips, y0 = (sidx - b * strips) * TAIL_TR;
+    const InT* g0 = in + ((long long)(b * H + y0 - 1) * W - 1) * in_ld + cv * VEC;     // pixel (py, px) = (0, 0) of the tile
+    const int npix = PH * PW;
+    int pix = threadIdx.x / vpp;
+    int py = pix / PW, px = pix - py * PW;
+    uint32_t dst = smem0 + (uint32_t)buf * tile_bytes + (uint32_t)pix * pix_bytes + (uint32_t)(cv * 16);
+    const uint32_t dstep = (uint32_t)clanes * pix_bytes;
+    while (pix < npix) {
+      const bool ok = (unsigned)(px - 1) < (unsigned)W && (unsigned)(y0 + py - 1) < (unsigned)H;
+      const InT* src = ok ? g0 + (py * W + px) * in_ld : in;
+      const int sz = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+      dst += dstep;
+      pix += clanes;
+      px += clanes;
+      while (px >= PW) { px -= PW; ++py; }
+    }
+    cp_async_commit();
+  };
+  if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int c0 = lane * 4;
+  float2 wr[9][2];                                      // this lane's weights as channel pairs
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      wr[t][j] = make_float2((c0 + 2 * j < Cin) ? w[(c0 + 2 * j) * 9 + t] : 0.f, (c0 + 2 * j + 1 < Cin) ? w[(c0 + 2 * j + 1) * 9 + t] : 0.f);
+  const int nblk = (W + TAIL_BW - 1) / TAIL_BW;
+  int it = 0;
+  for (int sidx = blockIdx.x; sidx < total; sidx += gridDim.x, ++it) {
+    const int buf = nbuf == 2 ? (it & 1) : 0;
+    const int next = sidx + gridDim.x;
+    if (nbuf == 2 && next < total) {
+      issue(next, buf ^ 1);                             // (tile buf^1 was read in the previous iteration, which ended with a barrier)
+      cp_async_wait_group<1>();
+    } else {
+      cp_async_wait_group<0>();
+    }
+    __syncthreads();
+    const int b = sidx / strips, y0 = (sidx - b * strips) * TAIL_TR;
+    const InT* tile = reinterpret_cast<const InT*>(tail_smem) + buf * tile_elems;
+    for (int blk = warp; blk < nblk; blk += nw) {
+      const int x0 = blk * TAIL_BW;
+      float2 acc[TAIL_TR][TAIL_BW];
+#pragma unroll
+      for (int oy = 0; oy < TAIL_TR; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < TAIL_BW; ++ox) acc[oy][ox] = make_float2(0.f, 0.f);
+      if (c0 < Cin) {
+#pragma unroll
+        for (int iy = 0; iy < TAIL_TR + 2; ++iy) {
+#pragma unroll
+          for (int ix = 0; ix < TAIL_BW + 2; ++ix) {
+            const int col = min(x0 + ix, PW - 1);        // (a partial last block re-reads the right padding column: masked)
+            const float4 v = ld4(tile + (long long)(iy * PW + col) * pitch + c0);
+            const float2 v01 = make_float2(v.x, v.y), v23 = make_float2(v.z, v.w);
+#pragma unroll
+            for (int oy = 0; oy < TAIL_TR; ++oy) {
+              const int ty = iy - oy;
+              if (ty < 0 || ty > 2) continue;
+#pragma unroll
+              for (int ox = 0; ox < TAIL_BW; ++ox) {
+                const int tx = ix - ox;
+                if (tx < 0 || tx > 2) continue;
+                ffma2(acc[oy][ox], v01, wr[ty * 3 + tx][0]);
+                ffma2(acc[oy][ox], v23, wr[ty * 3 + tx][1]);
+              }
+            }
+          }
+        }
+      }
+      // 20 per-lane sums -> warp sums.  Values 0..15: every exchange halves what a lane carries (lane l ends with value
+      // l >> 1); values 16..19: two halving exchanges, then three plain ones (lane l ends with value 16 + (l >> 3)).
+      float p[16], q4[4];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) p[i] = acc[i / TAIL_BW][i % TAIL_BW].x + acc[i / TAIL_BW][i % TAIL_BW].y;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) q4[i] = acc[(16 + i) / TAIL_BW][(16 + i) % TAIL_BW].x + acc[(16 + i) / TAIL_BW][(16 + i) % TAIL_BW].y;
+#pragma unroll
+      for (int wdt = 8, bit = 16; wdt >= 1; wdt >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int k = 0; k < wdt; ++k) {
+          const float keep = up ? p[k + wdt] : p[k], send = up ? p[k] : p[k + wdt];
+          p[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+      }
+      p[0] += __shfl_xor_sync(0xffffffffu, p[0], 1);
+#pragma unroll
+      for (int wdt = 2, bit = 16; wdt >= 1; wdt >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int k = 0; k < wdt; ++k) {
+          const float keep = up ? q4[k + wdt] : q4[k], send = up ? q4[k] : q4[k + wdt];
+          q4[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+      }
+      q4[0] += __shfl_xor_sync(0xffffffffu, q4[0], 4);
+      q4[0] += __shfl_xor_sync(0xffffffffu, q4[0], 2);
+      q4[0] += __shfl_xor_sync(0xffffffffu, q4[0], 1);
+      int idx = -1;
+      float val = 0.f;
+      if ((lane & 1) == 0) { idx = lane >> 1; val = p[0]; }
+      if ((lane & 7) == 1) { idx = 16 + (lane >> 3); val = q4[0]; }     // (odd lanes 1, 9, 17, 25: free in the first group)
+      if (idx >= 0) {
+        const int oy = idx / TAIL_BW, ox = idx - oy * TAIL_BW;
+        if (y0 + oy < H && x0 + ox < W) out[((long long)b * H + y0 + oy) * W + x0 + ox] = relu ? fmaxf(val, 0.f) : val;
+      }
+    }
+    __syncthreads();                                    // every warp is done with tile buf before it is refilled
+  }
+}
+
 // tail data gradient: din[p][ci] = sum_tap dz[p - shift(tap)] * w[tap][ci],  dz = dout * (out > 0)
 // A CTA owns TAIL_TR rows of one sample: the masked output gradient of the strip (+ halo) is staged in shared memory once;
 // a thread owns a group of 8 channels (its 9 x 8 weights in registers) and strides over the strip's pixels: 9 shared
@@ -991,8 +1132,17 @@ int tsr_tail_fwd(const void* in, int in_ld, int in_bf16, const float* w_oihw, fl
   TSR_DISPATCH_T(in_bf16, T,
                  size_t smem = (size_t)(TAIL_TR + 2) * (W + 2) * (Cin + 16 / sizeof(T)) * sizeof(T);
                  TSR_REQUIRE(smem <= 227 * 1024, "tail_fwd: tile does not fit in shared memory");
-                 TSR_CUDA(cudaFuncSetAttribute(tail_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                 tail_fwd_kernel<T><<<grid, 256, smem, stream>>>((const T*)in, in_ld, w_oihw, out, B, H, W, Cin, relu));
+                 if (Cin <= 128 && ((uintptr_t)in & 15) == 0 && (in_ld * sizeof(T)) % 16 == 0) {
+                   // two tiles and one persistent CTA per SM when they fit (16-bit inputs), else one strip per CTA
+                   const int nbuf = 2 * smem <= 227 * 1024 ? 2 : 1;
+                   const int g2 = nbuf == 2 ? (grid < 148 ? grid : 148) : grid;
+                   TSR_CUDA(cudaFuncSetAttribute(tail_fwd_blocked_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(nbuf * smem)));
+                   // persistent form: 16 warps copy, the first W / 5 of them compute; one-strip form: 8 warps, 2-3 CTAs per SM
+                   tail_fwd_blocked_kernel<T><<<g2, nbuf == 2 ? 512 : 256, nbuf * smem, stream>>>((const T*)in, in_ld, w_oihw, out, B, H, W, Cin, relu, nbuf);
+                 } else {
+                   TSR_CUDA(cudaFuncSetAttribute(tail_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                   tail_fwd_kernel<T><<<grid, 256, smem, stream>>>((const T*)in, in_ld, w_oihw, out, B, H, W, Cin, relu);
+                 });
   TSR_CHECK_LAUNCH("tail_fwd");
   return TSR_OK;
 }
