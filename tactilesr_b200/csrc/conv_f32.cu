@@ -289,19 +289,33 @@ conv2d_wgrad_f32_kernel(const float* __restrict__ in, int in_ld, const float* __
 }
 
 // level 2: dw_oihw[co][ci][tap] (+)= sum_s partial[s][tap][ci][co]   (fixed order => deterministic)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int S,
-                                    int taps, int Cin, int Cout, int accumulate) {
-  long long n = (long long)taps * Cin * Cout;
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int co = (int)(i % Cout);
-  long long r = i / Cout;
-  int ci = (int)(r % Cin);
-  int tap = (int)(r / Cin);
+// block = 32 consecutive outputs x 8 split lanes (warp j sums the splits j, j + 8, ...; lane sums combined in lane order
+// through shared memory): the dependent-load chain is S / 8 long instead of S
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int S,
+                    int taps, int Cin, int Cout, int accumulate) {
+  __shared__ float sh[8][32];
+  const long long n = (long long)taps * Cin * Cout;
+  const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + lane;
+  const bool ok = i < n;
   float s = 0.f;
-  for (int k = 0; k < S; ++k) s += partial[(long long)k * n + i];
-  long long o = ((long long)co * Cin + ci) * taps + tap;
-  dw[o] = accumulate ? dw[o] + s : s;
+  if (ok) {
+#pragma unroll 4
+    for (int k = j; k < S; k += 8) s += partial[(long long)k * n + i];
+  }
+  sh[j][lane] = s;
+  __syncthreads();
+  if (j != 0 || !ok) return;
+  float t = sh[0][lane];
+#pragma unroll
+  for (int q = 1; q < 8; ++q) t += sh[q][lane];
+  const int co = (int)(i % Cout);
+  const long long r = i / Cout;
+  const int ci = (int)(r % Cin);
+  const int tap = (int)(r / Cin);
+  const long long o = ((long long)co * Cin + ci) * taps + tap;
+  dw[o] = accumulate ? dw[o] + t : t;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -939,15 +953,27 @@ tail_wgrad_kernel(const InT* __restrict__ in, int in_ld, const float* __restrict
     }
   }
 }
-__global__ void tail_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int Cin,
-                                         float* __restrict__ dw, int accumulate) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;   // i = tap*Cin + ci
-  if (i >= 9 * Cin) return;
-  int ci = i % Cin, tap = i / Cin;
+// (32 outputs x 8 split lanes per block, lane sums combined in lane order: the chain of 592 dependent double additions per
+//  output becomes 74)
+__global__ void __launch_bounds__(256)
+tail_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int Cin,
+                         float* __restrict__ dw, int accumulate) {
+  __shared__ double sh[8][32];
+  const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;   // i = tap*Cin + ci
+  const bool ok = i < 9 * Cin;
   double s = 0.0;
-  for (int k = 0; k < nparts; ++k) s += (double)partial[(long long)k * 9 * Cin + i];
-  int o = ci * 9 + tap;
-  dw[o] = accumulate ? dw[o] + (float)s : (float)s;
+  if (ok)
+    for (int k = j; k < nparts; k += 8) s += (double)partial[(long long)k * 9 * Cin + i];
+  sh[j][lane] = s;
+  __syncthreads();
+  if (j != 0 || !ok) return;
+  double t = sh[0][lane];
+#pragma unroll
+  for (int q = 1; q < 8; ++q) t += sh[q][lane];
+  const int ci = i % Cin, tap = i / Cin;
+  const int o = ci * 9 + tap;
+  dw[o] = accumulate ? dw[o] + (float)t : (float)t;
 }
 
 }  // namespace
@@ -1037,8 +1063,8 @@ int tsr_conv2d_wgrad_f32(const float* in, int in_ld, const float* dout, int dout
                                                                    Cin, Cout, KS, pps);
   TSR_CHECK_LAUNCH("conv2d_wgrad_f32");
   long long n = (long long)taps * Cin * Cout;
-  wgrad_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>((const float*)workspace, dw_oihw, S, taps, Cin,
-                                                                  Cout, accumulate);
+  wgrad_reduce_kernel<<<(int)((n + 31) / 32), 256, 0, stream>>>((const float*)workspace, dw_oihw, S, taps, Cin,
+                                                                Cout, accumulate);
   TSR_CHECK_LAUNCH("wgrad_reduce");
   return TSR_OK;
 }
@@ -1204,7 +1230,7 @@ int tsr_tail_wgrad(const void* in, int in_ld, int in_bf16, const float* dout, co
   size_t smem = (size_t)threads * sizeof(float4);
   TSR_DISPATCH_T(in_bf16, T, tail_wgrad_kernel<T><<<nb, threads, smem, stream>>>((const T*)in, in_ld, dout, out_act, (float*)workspace, (int)M, H, W, Cin, relu, ppb));
   TSR_CHECK_LAUNCH("tail_wgrad");
-  tail_wgrad_reduce_kernel<<<tsr_cdiv(9 * Cin, 256), 256, 0, stream>>>((const float*)workspace, nb, Cin, dw_oihw, accumulate);
+  tail_wgrad_reduce_kernel<<<tsr_cdiv(9 * Cin, 32), 256, 0, stream>>>((const float*)workspace, nb, Cin, dw_oihw, accumulate);
   TSR_CHECK_LAUNCH("tail_wgrad_reduce");
   return TSR_OK;
 }
