@@ -49,6 +49,10 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     for mnem in ("UTCHMMA", "LDTM", "UTMALDG", "UBLKCP"):
         assert mnem in r.stdout, mnem
     assert "HGMMA" not in r.stdout
+    # the fp32 (<= 1e-5) mode: packed fp32 FMAs (fma.rn.f32x2 -> FFMA2) and register-free global -> shared copies
+    # (cp.async -> LDGSTS) in the conv / weight-gradient / head / tail kernels
+    assert r.stdout.count("FFMA2") > 1000
+    assert "LDGSTS" in r.stdout
 
 
 def test_product_never_imports_the_oracle():
