@@ -71,6 +71,9 @@ int tsr_colsum(const void* x, int ld, int x_bf16, long long npix, int C, float* 
 int tsr_head_fwd(const float* x, long long x_bstride, const float* w_oihw, void* out, int out_ld, int out_bf16, int B,
                  int sf, int relu, tsr_stream_t stream);
 size_t tsr_head_wgrad_workspace(int B);
+/* d(loss)/d(w) of the head convolution from the gradient of its output (autograd of :37 / :61; cpu/trainer.py:353).
+ * dout: NHWC, 64 channels starting at `dout`, row stride dout_ld elements (a multiple of 8: the rows are staged by 16-byte
+ * asynchronous copies), storage type dout_bf16 (0 fp32, 1 bf16, 2 fp16).  Deterministic two-level reduction. */
 int tsr_head_wgrad(const float* x, long long x_bstride, const void* dout, int dout_ld, int dout_bf16, float* dw_oihw,
                    void* workspace, size_t ws_bytes, int B, int sf, int accumulate, tsr_stream_t stream);
 /* nn.Conv2d(Cin -> 1, 3x3, no bias) + ReLU (model/tactileSR_model.py:55-56, :125-126); out is (B,1,H,W) fp32. */
